@@ -1,0 +1,427 @@
+"""ctypes binding of the C ABI (include/cbgpu.h, include/cb_exec.h): libcbgpu.so + libcbexec.so.
+
+Host-side glue for tests, smoke() and bench.py.  All compute is behind the C ABI; this module never
+falls back to numpy / torch / the oracle: if the CUDA library is missing or no GPU is present, the
+calls fail loudly.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from . import plan as P
+from .relation import HostRelation, NP_DTYPE
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+_GPU = None
+_EXEC = None
+
+
+class CbgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cbgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CbNumericDatum(C.Structure):
+    _fields_ = [("lo", C.c_int64), ("hi", C.c_int64), ("dscale", C.c_int32), ("text", C.c_char * 84)]
+
+
+class CbTupleTableSlot(C.Structure):
+    _fields_ = [("tts_empty", C.c_bool), ("tts_nvalid", C.c_int32), ("tts_types", C.POINTER(C.c_int32)),
+                ("tts_values", C.POINTER(C.c_int64)), ("tts_isnull", C.POINTER(C.c_bool)),
+                ("tts_state_n", C.POINTER(C.c_int64)), ("tts_state_lo", C.POINTER(C.c_int64)),
+                ("tts_state_hi", C.POINTER(C.c_int64))]
+
+
+class CbInstrumentation(C.Structure):
+    _fields_ = [("ntuples", C.c_double), ("nloops", C.c_double), ("kernels", C.c_int64), ("device_ms", C.c_double),
+                ("rows_in", C.c_int64)]
+
+
+class CbPlanState(C.Structure):
+    pass
+
+
+CbPlanState._fields_ = [
+    ("type", C.c_int), ("plan", C.POINTER(P.CbPlan)), ("state", C.c_void_p), ("ExecProcNode", C.c_void_p),
+    ("instrument", CbInstrumentation), ("lefttree", C.POINTER(CbPlanState)), ("righttree", C.POINTER(CbPlanState)),
+    ("ps_ResultTupleSlot", C.POINTER(CbTupleTableSlot)), ("squelched", C.c_bool), ("priv", C.c_void_p),
+]
+
+
+class CbEState(C.Structure):
+    _fields_ = [("es_ctx", C.c_void_p), ("es_nrels", C.c_int32), ("es_range_table", C.POINTER(C.c_void_p)),
+                ("es_segindex", C.c_int32), ("es_numsegments", C.c_int32), ("es_interconnect", C.c_void_p),
+                ("es_errcode", C.c_int32), ("es_errmsg", C.c_char * 512), ("es_error_hook", C.c_void_p),
+                ("es_force_generic", C.c_int32), ("es_processed", C.c_int64), ("es_cluster", C.c_void_p)]
+
+
+def header_symbols(header):
+    """Function names declared in a C header (used by the not-gpu export test)."""
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set()
+    for m in re.finditer(r"\b((?:cbgpu|cb)_[A-Za-z0-9_]+)\s*\(", text):
+        name = m.group(1)
+        if name.startswith(("cb_type_width",)):
+            continue
+        names.add(name)
+    return sorted(names)
+
+
+def build():
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc"), "-j8", "all"])
+
+
+def gpu():
+    global _GPU
+    if _GPU is None:
+        so = os.path.join(HERE, "libcbgpu.so")
+        if not os.path.exists(so):
+            raise CbgpuError(-1, "libcbgpu.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(so, mode=C.RTLD_GLOBAL)
+        vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+        sig = {
+            "cbgpu_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+            "cbgpu_ctx_destroy": (None, [vp]),
+            "cbgpu_last_error": (C.c_char_p, [vp]),
+            "cbgpu_sync": (C.c_int, [vp]),
+            "cbgpu_check_status": (C.c_int, [vp]),
+            "cbgpu_device_count": (C.c_int, []),
+            "cbgpu_sm_count": (C.c_int, [vp]),
+            "cbgpu_kernel_launches": (i64, [vp]),
+            "cbgpu_timer_start": (C.c_int, [vp]),
+            "cbgpu_timer_stop_ms": (C.c_int, [vp, C.POINTER(dbl)]),
+            "cbgpu_last_kernel_ms": (dbl, [vp]),
+            "cbgpu_last_kernel_name": (C.c_char_p, [vp]),
+            "cbgpu_flush_l2": (C.c_int, [vp]),
+            "cbgpu_host_alloc": (vp, [C.c_size_t]),
+            "cbgpu_host_free": (None, [vp]),
+            "cbgpu_hashbpchar": (C.c_uint32, [C.c_char_p, i32]),
+            "cbgpu_rel_create": (C.c_int, [vp, i64, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(vp)]),
+            "cbgpu_rel_free": (None, [vp]),
+            "cbgpu_rel_nrows": (i64, [vp]),
+            "cbgpu_rel_ncols": (i32, [vp]),
+            "cbgpu_rel_col_type": (i32, [vp, i32]),
+            "cbgpu_rel_col_dscale": (i32, [vp, i32]),
+            "cbgpu_rel_load_column": (C.c_int, [vp, i32, vp, vp]),
+            "cbgpu_rel_read_column": (C.c_int, [vp, i32, i64, i64, vp, vp]),
+            "cbgpu_rel_set_visimap": (C.c_int, [vp, vp]),
+            "cbgpu_rel_set_dict_hash": (C.c_int, [vp, i32, vp, i32]),
+            "cbgpu_rel_set_nrows": (C.c_int, [vp, i64]),
+            "cbgpu_rel_col_devptr": (vp, [vp, i32]),
+            "cbgpu_rel_nbytes": (C.c_size_t, [vp]),
+            "cbgpu_ht_build": (C.c_int, [vp, vp, C.POINTER(i32), i32, C.POINTER(vp)]),
+            "cbgpu_ht_free": (None, [vp]),
+            "cbgpu_ht_nrows": (i64, [vp]),
+            "cbgpu_ht_has_duplicates": (C.c_int, [vp]),
+            "cbgpu_ht_probe_pairs": (C.c_int, [vp, vp, vp, C.POINTER(i32), i32, vp, i64, vp]),
+            "cbgpu_pairs_free": (None, [vp]),
+            "cbgpu_read_u32": (C.c_int, [vp, vp, i64, vp]),
+            "cbgpu_gen_lineitem": (C.c_int, [vp, vp, u64, i64, i64, i64]),
+            "cbgpu_gen_orders": (C.c_int, [vp, vp, u64, i64, i64]),
+            "cbgpu_gen_customer": (C.c_int, [vp, vp, u64]),
+            "cbgpu_gen_supplier": (C.c_int, [vp, vp, u64]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _GPU = L
+    return _GPU
+
+
+def ex():
+    global _EXEC
+    if _EXEC is None:
+        gpu()
+        so = os.path.join(HERE, "libcbexec.so")
+        if not os.path.exists(so):
+            raise CbgpuError(-1, "libcbexec.so is not built (run __graft_entry__.build())")
+        L = C.CDLL(so)
+        vp = C.c_void_p
+        L.cb_CreateExecutorState.restype = C.POINTER(CbEState)
+        L.cb_CreateExecutorState.argtypes = [vp, C.POINTER(vp), C.c_int32]
+        L.cb_FreeExecutorState.argtypes = [C.POINTER(CbEState)]
+        L.cb_estate_error.restype = C.c_char_p
+        L.cb_estate_error.argtypes = [C.POINTER(CbEState)]
+        L.cb_ExecInitNode.restype = C.POINTER(CbPlanState)
+        L.cb_ExecInitNode.argtypes = [C.POINTER(P.CbPlan), C.POINTER(CbEState), C.c_int]
+        L.cb_ExecProcNode.restype = C.POINTER(CbTupleTableSlot)
+        L.cb_ExecProcNode.argtypes = [C.POINTER(CbPlanState)]
+        L.cb_MultiExecProcNode.restype = vp
+        L.cb_MultiExecProcNode.argtypes = [C.POINTER(CbPlanState)]
+        for n in ("cb_ExecEndNode", "cb_ExecReScan", "cb_ExecSquelchNode"):
+            getattr(L, n).restype = None
+            getattr(L, n).argtypes = [C.POINTER(CbPlanState)]
+        L.cb_slot_text.restype = C.c_int
+        L.cb_slot_text.argtypes = [C.POINTER(CbTupleTableSlot), C.c_int, C.c_char_p, C.c_int]
+        L.cb_slot_float8.restype = C.c_double
+        L.cb_slot_float8.argtypes = [C.POINTER(CbTupleTableSlot), C.c_int]
+        L.cb_numeric_sum_text.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_char_p, C.c_int32]
+        L.cb_numeric_avg_text.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_char_p, C.c_int32]
+        L.cb_cluster_create.restype = vp
+        L.cb_cluster_create.argtypes = [vp, C.c_int32]
+        L.cb_cluster_set_range_table.restype = C.c_int
+        L.cb_cluster_set_range_table.argtypes = [vp, C.c_int32, C.POINTER(vp), C.c_int32]
+        L.cb_cluster_estate.restype = C.POINTER(CbEState)
+        L.cb_cluster_estate.argtypes = [vp, C.c_int32]
+        L.cb_cluster_init_plan.restype = C.c_int
+        L.cb_cluster_init_plan.argtypes = [vp, C.POINTER(P.CbPlan)]
+        L.cb_cluster_next.restype = C.POINTER(CbTupleTableSlot)
+        L.cb_cluster_next.argtypes = [vp]
+        L.cb_cluster_current_segment.restype = C.c_int32
+        L.cb_cluster_current_segment.argtypes = [vp]
+        L.cb_cluster_end.argtypes = [vp]
+        L.cb_cluster_destroy.argtypes = [vp]
+        L.cb_cluster_error.restype = C.c_char_p
+        L.cb_cluster_error.argtypes = [vp]
+        _EXEC = L
+    return _EXEC
+
+
+def hashbpchar(text):
+    b = text.encode() if isinstance(text, str) else text
+    return int(gpu().cbgpu_hashbpchar(b, len(b)))
+
+
+class Context:
+    def __init__(self, device=0):
+        self.L = gpu()
+        h = C.c_void_p()
+        rc = self.L.cbgpu_ctx_create(device, C.byref(h))
+        self.h = h
+        if rc:
+            raise CbgpuError(rc, self.error())
+
+    def error(self):
+        return (self.L.cbgpu_last_error(self.h) or b"").decode()
+
+    def check(self, rc):
+        if rc:
+            raise CbgpuError(rc, self.error())
+
+    def sync(self):
+        self.check(self.L.cbgpu_sync(self.h))
+
+    def launches(self):
+        return int(self.L.cbgpu_kernel_launches(self.h))
+
+    def timer_start(self):
+        self.check(self.L.cbgpu_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_double()
+        self.check(self.L.cbgpu_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def last_kernel(self):
+        return (self.L.cbgpu_last_kernel_name(self.h) or b"").decode(), float(self.L.cbgpu_last_kernel_ms(self.h))
+
+    def flush_l2(self):
+        self.check(self.L.cbgpu_flush_l2(self.h))
+
+    def sm_count(self):
+        return int(self.L.cbgpu_sm_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.cbgpu_ctx_destroy(self.h)
+            self.h = None
+
+
+class DeviceRelation:
+    """An HBM-resident relation (the decoded, projected form of an AOCS table)."""
+
+    def __init__(self, ctx, nrows, types, dscales=None, name="rel"):
+        self.ctx = ctx
+        self.name = name
+        self.types = list(types)
+        self.dscales = list(dscales) if dscales is not None else [2 if t == P.NUMERIC else 0 for t in types]
+        n = len(types)
+        h = C.c_void_p()
+        ctx.check(ctx.L.cbgpu_rel_create(ctx.h, nrows, n, (C.c_int32 * n)(*self.types), (C.c_int32 * n)(*self.dscales),
+                                         C.byref(h)))
+        self.h = h
+        self.nrows = nrows
+
+    @classmethod
+    def from_host(cls, ctx, rel: HostRelation):
+        d = cls(ctx, rel.nrows, rel.types, rel.dscales, rel.name)
+        d.load(rel)
+        return d
+
+    def load(self, rel: HostRelation, sync=True):
+        """Host -> device copy of every column (cbgpu_rel_load_column)."""
+        L = self.ctx.L
+        for i, col in enumerate(rel.columns):
+            nl = rel.nulls[i]
+            if nl is not None:
+                nl = np.ascontiguousarray(nl, dtype=np.uint8)
+            self.ctx.check(L.cbgpu_rel_load_column(self.h, i, col.ctypes.data, nl.ctypes.data if nl is not None else None))
+            if rel.dict_hashes[i] is not None:
+                dh = np.ascontiguousarray(rel.dict_hashes[i], dtype=np.uint32)
+                self.ctx.check(L.cbgpu_rel_set_dict_hash(self.h, i, dh.ctypes.data, len(dh)))
+        if rel.visimap is not None:
+            vm = np.ascontiguousarray(rel.visimap, dtype=np.uint8)
+            self.ctx.check(L.cbgpu_rel_set_visimap(self.h, vm.ctypes.data))
+        if sync:
+            self.ctx.sync()
+
+    def load_column_ptr(self, col, host_ptr):
+        self.ctx.check(self.ctx.L.cbgpu_rel_load_column(self.h, col, host_ptr, None))
+
+    def set_dict_hash(self, col, hashes):
+        dh = np.ascontiguousarray(hashes, dtype=np.uint32)
+        self.ctx.check(self.ctx.L.cbgpu_rel_set_dict_hash(self.h, col, dh.ctypes.data, len(dh)))
+
+    def read_column(self, col, lo=0, hi=None):
+        hi = self.rows() if hi is None else hi
+        out = np.empty(hi - lo, dtype=NP_DTYPE[self.types[col]])
+        nulls = np.zeros(hi - lo, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.cbgpu_rel_read_column(self.h, col, lo, hi, out.ctypes.data, nulls.ctypes.data))
+        return out, nulls
+
+    def rows(self):
+        return int(self.ctx.L.cbgpu_rel_nrows(self.h))
+
+    def nbytes(self):
+        return int(self.ctx.L.cbgpu_rel_nbytes(self.h))
+
+    def free(self):
+        if self.h:
+            self.ctx.L.cbgpu_rel_free(self.h)
+            self.h = None
+
+
+def _slot_row(E, slot):
+    s = slot.contents
+    row, states = [], []
+    buf = C.create_string_buffer(160)
+    for i in range(s.tts_nvalid):
+        states.append((s.tts_state_n[i], ((s.tts_state_hi[i] << 64) | (s.tts_state_lo[i] & (2 ** 64 - 1)))))
+        if s.tts_isnull[i]:
+            row.append(None)
+            continue
+        t = s.tts_types[i]
+        if t == P.FLOAT8:
+            row.append(E.cb_slot_float8(slot, i + 1))
+        elif t in (P.NUMERIC, P.NUMERIC128):
+            E.cb_slot_text(slot, i + 1, buf, 160)
+            row.append(buf.value.decode())
+        else:
+            row.append(int(s.tts_values[i]))
+    return row, states
+
+
+class Result:
+    def __init__(self):
+        self.rows = []
+        self.states = []
+        self.segments = []
+        self.instrument = {}
+
+
+def _collect_instrument(ps, out):
+    if not ps:
+        return
+    n = ps.contents
+    ins = n.instrument
+    out[n.plan.contents.plan_node_id] = {"node": n.type, "ntuples": ins.ntuples, "kernels": ins.kernels,
+                                         "device_ms": ins.device_ms, "rows_in": ins.rows_in}
+    _collect_instrument(n.lefttree, out)
+    _collect_instrument(n.righttree, out)
+
+
+class Executor:
+    """ExecutorStart / ExecutorRun / ExecutorEnd for one segment (one GPU)."""
+
+    def __init__(self, ctx, range_table, force_generic=False):
+        self.ctx = ctx
+        self.E = ex()
+        n = len(range_table)
+        arr = (C.c_void_p * max(n, 1))(*[r.h for r in range_table])
+        self.estate = self.E.cb_CreateExecutorState(ctx.h, arr, n)
+        self.estate.contents.es_force_generic = 1 if force_generic else 0
+        self._keep = [arr, range_table]
+
+    def run(self, plan_node):
+        """Pull every tuple through cb_ExecProcNode, as ExecutePlan does (execMain.c:2772)."""
+        E = self.E
+        es = self.estate
+        es.contents.es_errcode = 0
+        ps = E.cb_ExecInitNode(P.plan_ptr(plan_node), es, 0)
+        if not ps:
+            raise CbgpuError(es.contents.es_errcode, E.cb_estate_error(es).decode())
+        res = Result()
+        try:
+            while True:
+                slot = E.cb_ExecProcNode(ps)
+                if es.contents.es_errcode:
+                    raise CbgpuError(es.contents.es_errcode, E.cb_estate_error(es).decode())
+                if not slot or slot.contents.tts_empty:
+                    break
+                row, st = _slot_row(E, slot)
+                res.rows.append(row)
+                res.states.append(st)
+                res.segments.append(0)
+            _collect_instrument(ps, res.instrument)
+        finally:
+            E.cb_ExecEndNode(ps)
+        return res
+
+    def close(self):
+        if self.estate:
+            self.E.cb_FreeExecutorState(self.estate)
+            self.estate = None
+
+
+class Cluster:
+    """N segment executors in one process over one GPU (the reference's gpdemo, on a device)."""
+
+    def __init__(self, ctx, segment_range_tables, force_generic=False):
+        self.ctx = ctx
+        self.E = ex()
+        self.nsegs = len(segment_range_tables)
+        self.h = self.E.cb_cluster_create(ctx.h, self.nsegs)
+        self._keep = []
+        for s, rt in enumerate(segment_range_tables):
+            arr = (C.c_void_p * max(len(rt), 1))(*[r.h for r in rt])
+            self._keep += [arr, rt]
+            rc = self.E.cb_cluster_set_range_table(self.h, s, arr, len(rt))
+            if rc:
+                raise CbgpuError(rc, "bad range table")
+            self.E.cb_cluster_estate(self.h, s).contents.es_force_generic = 1 if force_generic else 0
+
+    def run(self, plan_node):
+        E = self.E
+        rc = E.cb_cluster_init_plan(self.h, P.plan_ptr(plan_node))
+        if rc:
+            msg = E.cb_cluster_error(self.h).decode()
+            E.cb_cluster_end(self.h)
+            raise CbgpuError(rc, msg)
+        res = Result()
+        try:
+            while True:
+                slot = E.cb_cluster_next(self.h)
+                err = E.cb_cluster_error(self.h)
+                if err:
+                    raise CbgpuError(-1, err.decode())
+                if not slot or slot.contents.tts_empty:
+                    break
+                row, st = _slot_row(E, slot)
+                res.rows.append(row)
+                res.states.append(st)
+                res.segments.append(int(E.cb_cluster_current_segment(self.h)))
+        finally:
+            E.cb_cluster_end(self.h)
+        return res
+
+    def close(self):
+        if self.h:
+            self.E.cb_cluster_destroy(self.h)
+            self.h = None

@@ -1,0 +1,499 @@
+/*
+ * agg.cu - aggregate hash tables (allocation, read-back, conversion to a relation) and device top-N.
+ *
+ * The table stands in for the reference's TupleHashTable of AggStatePerGroupData
+ * (backend/executor/execGrouping.c:317, backend/executor/nodeAgg.c:2220-2319).  Per group it holds
+ * the grouping keys and, per accumulator, (N, 128-bit exact sum) - the same content as the
+ * reference's Int128AggState / NumericAggState{N, sumX} (backend/utils/adt/numeric.c:5340, 4602)
+ * or float8 {N, Sx} - so partial states can be redistributed and combined (two-stage aggregation,
+ * nodes/nodes.h:977-1000 AggSplit) and finalised exactly on the host.
+ */
+#include "common.cuh"
+
+#include <stdlib.h>
+
+static int64_t
+next_pow2(int64_t v)
+{
+	int64_t		p = 1;
+
+	while (p < v)
+		p <<= 1;
+	return p;
+}
+
+__global__ void
+k_agg_init(AggDev t, const int32_t *kinds)
+{
+	size_t		cap = (size_t) t.mask + 1;
+	size_t		i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	size_t		stride = (size_t) gridDim.x * blockDim.x;
+
+	for (; i < cap; i += stride)
+	{
+		t.state[i] = 0;
+		for (int a = 0; a < t.naccs; a++)
+		{
+			unsigned long long lo = 0;
+
+			if (kinds[a] == CBP_ACC_MIN || kinds[a] == CBP_ACC_MERGE_MIN)
+				lo = 0x7fffffffffffffffull;
+			else if (kinds[a] == CBP_ACC_MAX || kinds[a] == CBP_ACC_MERGE_MAX)
+				lo = 0x8000000000000000ull;
+			t.n[i * t.naccs + a] = 0;
+			t.sum[(i * t.naccs + a) * 2] = lo;
+			t.sum[(i * t.naccs + a) * 2 + 1] = 0;
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		*t.ngroups = 0;
+		*t.full = 0;
+	}
+}
+
+extern "C" int
+cbgpu_agg_reset(cbgpu_aggtable *t)
+{
+	cbgpu_ctx  *ctx = t->ctx;
+	int32_t    *dk;
+
+	CB_CUDA(ctx, cudaMallocAsync(&dk, sizeof(int32_t) * CBP_MAX_AGGS, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(dk, t->kinds, sizeof(int32_t) * CBP_MAX_AGGS, cudaMemcpyHostToDevice, ctx->stream));
+	int			blocks = (int) ((t->capacity + 255) / 256);
+
+	if (blocks > ctx->sm_count * 8)
+		blocks = ctx->sm_count * 8;
+	k_agg_init<<<blocks, 256, 0, ctx->stream>>>(t->d, dk);
+	CB_LAUNCHED(ctx, "k_agg_init");
+	CB_CUDA(ctx, cudaFreeAsync(dk, ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_agg_create(cbgpu_ctx *ctx, int32_t nkeys, int32_t naccs, const int32_t *acc_kinds, int64_t capacity_groups,
+				 cbgpu_aggtable **out)
+{
+	cbgpu_aggtable *t;
+	int64_t		cap;
+
+	if (nkeys < 0 || nkeys > CBP_MAX_KEYS || naccs < 0 || naccs > CBP_MAX_AGGS)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "aggregate with %s%lld keys/accumulators is beyond the GPU path's limits", "", (long long) (nkeys * 100 + naccs));
+	t = (cbgpu_aggtable *) calloc(1, sizeof(cbgpu_aggtable));
+	if (!t)
+		return CBGPU_ERR_NOMEM;
+	cap = next_pow2((capacity_groups < 16 ? 16 : capacity_groups) * 2);
+	if (cap > (1ll << 31))
+	{
+		free(t);
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "aggregate table of %s%lld slots exceeds the GPU path's limit", "", cap);
+	}
+	t->ctx = ctx;
+	t->capacity = cap;
+	t->d.mask = (uint32_t) (cap - 1);
+	t->d.nkeys = nkeys;
+	t->d.naccs = naccs;
+	for (int a = 0; a < naccs; a++)
+		t->kinds[a] = acc_kinds ? acc_kinds[a] : CBP_ACC_SUM_INT;
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	CB_CUDA(ctx, cudaMalloc(&t->d.state, cap * sizeof(int32_t)));
+	CB_CUDA(ctx, cudaMalloc(&t->d.hash, cap * sizeof(uint32_t)));
+	CB_CUDA(ctx, cudaMalloc(&t->d.keys, cap * sizeof(int64_t) * (nkeys ? nkeys : 1)));
+	CB_CUDA(ctx, cudaMalloc(&t->d.keynull, cap * sizeof(uint32_t)));
+	CB_CUDA(ctx, cudaMalloc(&t->d.n, cap * sizeof(int64_t) * (naccs ? naccs : 1)));
+	CB_CUDA(ctx, cudaMalloc(&t->d.sum, cap * 2 * sizeof(unsigned long long) * (naccs ? naccs : 1)));
+	CB_CUDA(ctx, cudaMalloc(&t->d.ngroups, sizeof(int32_t) * 2));
+	t->d.full = t->d.ngroups + 1;
+	*out = t;
+	return cbgpu_agg_reset(t);
+}
+
+extern "C" void
+cbgpu_agg_free(cbgpu_aggtable *t)
+{
+	if (!t)
+		return;
+	cudaSetDevice(t->ctx->device);
+	cudaStreamSynchronize(t->ctx->stream);
+	cudaFree(t->d.state);
+	cudaFree(t->d.hash);
+	cudaFree(t->d.keys);
+	cudaFree(t->d.keynull);
+	cudaFree(t->d.n);
+	cudaFree(t->d.sum);
+	cudaFree(t->d.ngroups);
+	free(t);
+}
+
+extern "C" int
+cbgpu_agg_ngroups(cbgpu_aggtable *t, int64_t *ngroups)
+{
+	cbgpu_ctx  *ctx = t->ctx;
+	int32_t		h[2];
+
+	CB_CUDA(ctx, cudaMemcpyAsync(h, t->d.ngroups, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (h[1])
+		return cb_fail(ctx, CBGPU_ERR_NOMEM, "aggregate hash table overflow (%s capacity %lld slots)", "", t->capacity);
+	*ngroups = h[0];
+	return CBGPU_OK;
+}
+
+/* compaction: slots in `ready` state -> dense rows (agg_retrieve_hash_table's table walk,
+ * backend/executor/nodeAgg.c:3014) */
+struct AggOut
+{
+	int64_t    *keys;
+	uint32_t   *keynull;
+	int64_t    *n;
+	int64_t    *lo;
+	int64_t    *hi;
+	int32_t    *counter;
+	int64_t		maxgroups;
+};
+
+__global__ void
+k_agg_compact(AggDev t, AggOut o)
+{
+	size_t		cap = (size_t) t.mask + 1;
+	size_t		i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	size_t		stride = (size_t) gridDim.x * blockDim.x;
+
+	for (; i < cap; i += stride)
+	{
+		if (t.state[i] != 2)
+			continue;
+		int			g = atomicAdd(o.counter, 1);
+
+		if (g >= o.maxgroups)
+			continue;
+		for (int k = 0; k < t.nkeys; k++)
+			o.keys[(size_t) g * t.nkeys + k] = t.keys[i * t.nkeys + k];
+		o.keynull[g] = t.keynull[i];
+		for (int a = 0; a < t.naccs; a++)
+		{
+			o.n[(size_t) g * t.naccs + a] = t.n[i * t.naccs + a];
+			o.lo[(size_t) g * t.naccs + a] = (int64_t) t.sum[(i * t.naccs + a) * 2];
+			o.hi[(size_t) g * t.naccs + a] = (int64_t) t.sum[(i * t.naccs + a) * 2 + 1];
+		}
+	}
+}
+
+extern "C" int
+cbgpu_agg_read(cbgpu_aggtable *t, int64_t maxgroups, int64_t *keys, uint32_t *keynull, int64_t *n, int64_t *sum_lo,
+			   int64_t *sum_hi, int64_t *ngroups)
+{
+	cbgpu_ctx  *ctx = t->ctx;
+	int64_t		ng;
+	int			rc = cbgpu_agg_ngroups(t, &ng);
+	AggOut		o;
+	int			nk = t->d.nkeys ? t->d.nkeys : 1;
+	int			na = t->d.naccs ? t->d.naccs : 1;
+
+	if (rc)
+		return rc;
+	*ngroups = ng;
+	if (ng > maxgroups)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_agg_read: %s%lld groups exceed the caller's buffer", "", ng);
+	if (ng == 0)
+		return CBGPU_OK;
+	o.maxgroups = ng;
+	CB_CUDA(ctx, cudaMallocAsync(&o.keys, sizeof(int64_t) * ng * nk, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&o.keynull, sizeof(uint32_t) * ng, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&o.n, sizeof(int64_t) * ng * na, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&o.lo, sizeof(int64_t) * ng * na, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&o.hi, sizeof(int64_t) * ng * na, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&o.counter, sizeof(int32_t), ctx->stream));
+	CB_CUDA(ctx, cudaMemsetAsync(o.counter, 0, sizeof(int32_t), ctx->stream));
+	int			blocks = (int) ((t->capacity + 255) / 256);
+
+	if (blocks > ctx->sm_count * 8)
+		blocks = ctx->sm_count * 8;
+	k_agg_compact<<<blocks, 256, 0, ctx->stream>>>(t->d, o);
+	CB_LAUNCHED(ctx, "k_agg_compact");
+	if (t->d.nkeys)
+		CB_CUDA(ctx, cudaMemcpyAsync(keys, o.keys, sizeof(int64_t) * ng * t->d.nkeys, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(keynull, o.keynull, sizeof(uint32_t) * ng, cudaMemcpyDeviceToHost, ctx->stream));
+	if (t->d.naccs)
+	{
+		CB_CUDA(ctx, cudaMemcpyAsync(n, o.n, sizeof(int64_t) * ng * t->d.naccs, cudaMemcpyDeviceToHost, ctx->stream));
+		CB_CUDA(ctx, cudaMemcpyAsync(sum_lo, o.lo, sizeof(int64_t) * ng * t->d.naccs, cudaMemcpyDeviceToHost, ctx->stream));
+		CB_CUDA(ctx, cudaMemcpyAsync(sum_hi, o.hi, sizeof(int64_t) * ng * t->d.naccs, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFreeAsync(o.keys, ctx->stream);
+	cudaFreeAsync(o.keynull, ctx->stream);
+	cudaFreeAsync(o.n, ctx->stream);
+	cudaFreeAsync(o.lo, ctx->stream);
+	cudaFreeAsync(o.hi, ctx->stream);
+	cudaFreeAsync(o.counter, ctx->stream);
+	return CBGPU_OK;
+}
+
+/* groups -> relation: key columns (typed), then per accumulator N, sum.lo, sum.hi (int8 each) */
+struct AggRelOut
+{
+	void	   *key[CBP_MAX_KEYS];
+	uint8_t    *keynulls[CBP_MAX_KEYS];
+	int32_t		keytype[CBP_MAX_KEYS];
+	int64_t    *acc[CBP_MAX_AGGS * 3];
+	int32_t    *counter;
+};
+
+__global__ void
+k_agg_to_rel(AggDev t, AggRelOut o)
+{
+	size_t		cap = (size_t) t.mask + 1;
+	size_t		i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	size_t		stride = (size_t) gridDim.x * blockDim.x;
+
+	for (; i < cap; i += stride)
+	{
+		if (t.state[i] != 2)
+			continue;
+		int			g = atomicAdd(o.counter, 1);
+		uint32_t	nm = t.keynull[i];
+
+		for (int k = 0; k < t.nkeys; k++)
+		{
+			int64_t		v = t.keys[i * t.nkeys + k];
+
+			switch (o.keytype[k])
+			{
+				case CB_INT4: case CB_DATE: case CB_DICT32:
+					((int32_t *) o.key[k])[g] = (int32_t) v;
+					break;
+				case CB_INT8: case CB_NUMERIC: case CB_FLOAT8:
+					((int64_t *) o.key[k])[g] = v;
+					break;
+				default:
+					((uint8_t *) o.key[k])[g] = (uint8_t) v;
+			}
+			if (o.keynulls[k])
+				o.keynulls[k][g] = (nm >> k) & 1;
+		}
+		for (int a = 0; a < t.naccs; a++)
+		{
+			o.acc[a * 3][g] = t.n[i * t.naccs + a];
+			o.acc[a * 3 + 1][g] = (int64_t) t.sum[(i * t.naccs + a) * 2];
+			o.acc[a * 3 + 2][g] = (int64_t) t.sum[(i * t.naccs + a) * 2 + 1];
+		}
+	}
+}
+
+__global__ void
+k_agg_anynull(AggDev t, int *flag)
+{
+	size_t		cap = (size_t) t.mask + 1;
+	size_t		i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	size_t		stride = (size_t) gridDim.x * blockDim.x;
+
+	for (; i < cap; i += stride)
+		if (t.state[i] == 2 && t.keynull[i])
+			*flag = 1;
+}
+
+extern "C" int
+cbgpu_agg_to_rel(cbgpu_aggtable *t, const int32_t *keytypes, cbgpu_rel **out)
+{
+	cbgpu_ctx  *ctx = t->ctx;
+	int64_t		ng;
+	int			rc = cbgpu_agg_ngroups(t, &ng);
+	int32_t		types[CBP_MAX_KEYS + CBP_MAX_AGGS * 3];
+	int			ncols = t->d.nkeys + t->d.naccs * 3;
+	cbgpu_rel  *rel;
+	AggRelOut	o;
+	int		   *d_flag;
+	int			h_flag = 0;
+
+	if (rc)
+		return rc;
+	for (int k = 0; k < t->d.nkeys; k++)
+		types[k] = keytypes[k];
+	for (int a = 0; a < t->d.naccs * 3; a++)
+		types[t->d.nkeys + a] = CB_INT8;
+	rc = cbgpu_rel_create(ctx, ng, ncols, types, NULL, &rel);
+	if (rc)
+		return rc;
+	memset(&o, 0, sizeof(o));
+	int			blocks = (int) ((t->capacity + 255) / 256);
+
+	if (blocks > ctx->sm_count * 8)
+		blocks = ctx->sm_count * 8;
+	/* NULL group keys need null byte-maps on the key columns */
+	CB_CUDA(ctx, cudaMallocAsync(&d_flag, sizeof(int), ctx->stream));
+	CB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+	k_agg_anynull<<<blocks, 256, 0, ctx->stream>>>(t->d, d_flag);
+	CB_LAUNCHED(ctx, "k_agg_anynull");
+	CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	CB_CUDA(ctx, cudaFreeAsync(d_flag, ctx->stream));
+	for (int k = 0; k < t->d.nkeys; k++)
+	{
+		o.key[k] = rel->data[k];
+		o.keytype[k] = keytypes[k];
+		if (h_flag && ng > 0)
+		{
+			CB_CUDA(ctx, cudaMalloc(&rel->nulls[k], (size_t) ng));
+			o.keynulls[k] = rel->nulls[k];
+		}
+	}
+	for (int a = 0; a < t->d.naccs * 3; a++)
+		o.acc[a] = (int64_t *) rel->data[t->d.nkeys + a];
+	CB_CUDA(ctx, cudaMallocAsync(&o.counter, sizeof(int32_t), ctx->stream));
+	CB_CUDA(ctx, cudaMemsetAsync(o.counter, 0, sizeof(int32_t), ctx->stream));
+	if (ng > 0)
+	{
+		k_agg_to_rel<<<blocks, 256, 0, ctx->stream>>>(t->d, o);
+		CB_LAUNCHED(ctx, "k_agg_to_rel");
+	}
+	CB_CUDA(ctx, cudaFreeAsync(o.counter, ctx->stream));
+	*out = rel;
+	return CBGPU_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * top-N: ORDER BY keys LIMIT n over a relation (bounded sort above the Agg)
+ * --------------------------------------------------------------------------------------------- */
+#define TOPN_MAXK 64
+#define TOPN_MAXKEYS 4
+
+struct TopnParams
+{
+	const void *key[TOPN_MAXKEYS];
+	int32_t		keytype[TOPN_MAXKEYS];
+	int32_t		desc[TOPN_MAXKEYS];
+	int32_t		uns[TOPN_MAXKEYS];
+	int32_t		nkeys;
+	int32_t		k;
+	const uint32_t *in_idx;		/* NULL = identity over nrows                                         */
+	int64_t		nin;
+	uint32_t   *out_idx;		/* [nthreads * k], padded with 0xFFFFFFFF                             */
+};
+
+/* true when row a sorts strictly before row b */
+__device__ __forceinline__ bool
+topn_before(const TopnParams &p, const int64_t *ka, uint32_t ra, const int64_t *kb, uint32_t rb)
+{
+	for (int i = 0; i < p.nkeys; i++)
+	{
+		int64_t		x = ka[i],
+					y = kb[i];
+
+		if (x == y)
+			continue;
+		bool		lt = p.uns[i] ? ((uint64_t) x < (uint64_t) y) : (x < y);
+
+		return p.desc[i] ? !lt : lt;
+	}
+	return ra < rb;
+}
+
+__global__ void
+k_topn(TopnParams p)
+{
+	uint32_t	best_row[TOPN_MAXK];
+	int64_t		best_key[TOPN_MAXK][TOPN_MAXKEYS];
+	int			nbest = 0;
+	int64_t		tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t		stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (int64_t i = tid; i < p.nin; i += stride)
+	{
+		uint32_t	row = p.in_idx ? p.in_idx[i] : (uint32_t) i;
+		int64_t		key[TOPN_MAXKEYS];
+
+		if (row == 0xFFFFFFFFu)
+			continue;
+		for (int k = 0; k < p.nkeys; k++)
+			key[k] = cb_load_widen(p.key[k], p.keytype[k], row);
+		if (nbest == p.k && !topn_before(p, key, row, best_key[nbest - 1], best_row[nbest - 1]))
+			continue;
+		/* insertion into the sorted local list */
+		int			pos = nbest < p.k ? nbest : p.k - 1;
+
+		while (pos > 0 && topn_before(p, key, row, best_key[pos - 1], best_row[pos - 1]))
+		{
+			best_row[pos] = best_row[pos - 1];
+			for (int k = 0; k < p.nkeys; k++)
+				best_key[pos][k] = best_key[pos - 1][k];
+			pos--;
+		}
+		best_row[pos] = row;
+		for (int k = 0; k < p.nkeys; k++)
+			best_key[pos][k] = key[k];
+		if (nbest < p.k)
+			nbest++;
+	}
+	for (int j = 0; j < p.k; j++)
+		p.out_idx[tid * p.k + j] = j < nbest ? best_row[j] : 0xFFFFFFFFu;
+}
+
+extern "C" int
+cbgpu_topn(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const int32_t *descending, const int32_t *unsigned_cmp,
+		   int32_t nkeys, int64_t limit, uint32_t *host_idx, int64_t *nout)
+{
+	TopnParams	p;
+	uint32_t   *cand1 = NULL,
+			   *cand2 = NULL;
+	int64_t		n1,
+				n2;
+
+	if (nkeys < 1 || nkeys > TOPN_MAXKEYS || limit < 1 || limit > TOPN_MAXK)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "device top-N supports 1..4 sort keys and LIMIT <= 64 (%s got %lld)", "", limit);
+	memset(&p, 0, sizeof(p));
+	for (int i = 0; i < nkeys; i++)
+	{
+		if (keycols[i] < 0 || keycols[i] >= rel->ncols)
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_topn: bad key column%s %lld", "", keycols[i]);
+		if (rel->nulls[keycols[i]])
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "device top-N over a nullable sort key (%s column %lld)", "", keycols[i]);
+		p.key[i] = rel->data[keycols[i]];
+		p.keytype[i] = rel->types[keycols[i]];
+		p.desc[i] = descending[i];
+		p.uns[i] = unsigned_cmp ? unsigned_cmp[i] : 0;
+		if (p.keytype[i] == CB_FLOAT8)
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "device top-N over a float8 key%s", "", 0);
+	}
+	p.nkeys = nkeys;
+	p.k = (int32_t) limit;
+	*nout = 0;
+	if (rel->nrows == 0)
+		return CBGPU_OK;
+	/* pass 1: every thread keeps its own best k; pass 2: one CTA over the candidates */
+	int			blocks1 = ctx->sm_count * 2,
+				threads = 128;
+
+	if ((int64_t) blocks1 * threads > rel->nrows)
+		blocks1 = (int) ((rel->nrows + threads - 1) / threads);
+	n1 = (int64_t) blocks1 * threads * limit;
+	CB_CUDA(ctx, cudaMallocAsync(&cand1, n1 * sizeof(uint32_t), ctx->stream));
+	p.in_idx = NULL;
+	p.nin = rel->nrows;
+	p.out_idx = cand1;
+	k_topn<<<blocks1, threads, 0, ctx->stream>>>(p);
+	CB_LAUNCHED(ctx, "k_topn");
+	n2 = (int64_t) threads * limit;
+	CB_CUDA(ctx, cudaMallocAsync(&cand2, n2 * sizeof(uint32_t), ctx->stream));
+	p.in_idx = cand1;
+	p.nin = n1;
+	p.out_idx = cand2;
+	k_topn<<<1, threads, 0, ctx->stream>>>(p);
+	CB_LAUNCHED(ctx, "k_topn");
+	/* final: one thread */
+	p.in_idx = cand2;
+	p.nin = n2;
+	p.out_idx = cand1;
+	k_topn<<<1, 1, 0, ctx->stream>>>(p);
+	CB_LAUNCHED(ctx, "k_topn");
+	CB_CUDA(ctx, cudaMemcpyAsync(host_idx, cand1, limit * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFreeAsync(cand1, ctx->stream);
+	cudaFreeAsync(cand2, ctx->stream);
+	int64_t		n = 0;
+
+	while (n < limit && host_idx[n] != 0xFFFFFFFFu)
+		n++;
+	*nout = n;
+	return CBGPU_OK;
+}

@@ -1,0 +1,431 @@
+/*
+ * common.cuh - shared internals of libcbgpu.so: context / relation structs, error plumbing, the
+ * reference's hash functions as device code, and the 128-bit accumulate primitives.
+ *
+ * Hashing must be bit-exact with the reference (parity gate): each device function cites the
+ * reference function it restates (paths under /root/reference/src).
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cbgpu.h"
+
+#define CB_MAX_COLS_REL 64
+
+struct cbgpu_ctx
+{
+	int			device;
+	cudaStream_t stream;
+	char		err[512];
+	int			sm_count;
+	int64_t		launches;
+	cudaEvent_t ev_t0, ev_t1, ev_k0, ev_k1;
+	double		last_kernel_ms;
+	const char *last_kernel_name;
+	bool		kernel_timed;
+	void	   *flush_buf;
+	size_t		flush_bytes;
+	int		   *d_status;		/* device status word: nonzero = CBGPU error code raised by a kernel */
+	int		   *h_status;		/* pinned mirror                                                      */
+};
+
+struct cbgpu_rel
+{
+	cbgpu_ctx  *ctx;
+	int64_t		nrows;
+	int64_t		capacity;
+	int32_t		ncols;
+	int32_t		types[CB_MAX_COLS_REL];
+	int32_t		dscales[CB_MAX_COLS_REL];
+	void	   *data[CB_MAX_COLS_REL];
+	uint8_t	   *nulls[CB_MAX_COLS_REL];
+	uint32_t   *dict_hash[CB_MAX_COLS_REL];
+	int32_t		dict_n[CB_MAX_COLS_REL];
+	uint8_t	   *visimap;
+	bool		owns[CB_MAX_COLS_REL];
+};
+
+/* agg table, device view (struct of arrays; open addressing, linear probing) */
+struct AggDev
+{
+	uint32_t	mask;			/* capacity - 1                                                       */
+	int32_t		nkeys;
+	int32_t		naccs;
+	int32_t    *state;			/* [cap] 0 empty, 1 being written, 2 ready                            */
+	uint32_t   *hash;			/* [cap]                                                              */
+	int64_t    *keys;			/* [cap][nkeys]                                                       */
+	uint32_t   *keynull;		/* [cap] bit k = key k is NULL                                        */
+	int64_t    *n;				/* [cap][naccs]                                                       */
+	unsigned long long *sum;	/* [cap][naccs][2] lo, hi (float8 state: bits in lo)                  */
+	int32_t    *ngroups;
+	int32_t    *full;			/* set when an insert found no free slot                              */
+};
+
+struct cbgpu_aggtable
+{
+	cbgpu_ctx  *ctx;
+	AggDev		d;
+	int64_t		capacity;
+	int32_t		kinds[CBP_MAX_AGGS];
+};
+
+/* join hash table, device view: slot = hash32 << 32 | rowid32, EMPTY = ~0 */
+#define HT_EMPTY 0xFFFFFFFFFFFFFFFFull
+struct HtDev
+{
+	unsigned long long *slots;
+	uint32_t	mask;
+	int32_t		nkeys;
+	const void *keydata[CBP_MAX_KEYS];	/* inner key columns, for match verification                  */
+	const uint8_t *keynulls[CBP_MAX_KEYS];
+	const uint32_t *keydict[CBP_MAX_KEYS];
+	int32_t		keytype[CBP_MAX_KEYS];
+};
+
+struct cbgpu_hashtable
+{
+	cbgpu_ctx  *ctx;
+	HtDev		d;
+	cbgpu_rel  *inner;
+	int64_t		nslots;
+	int64_t		ninserted;
+	int		   *d_flags;		/* [0] duplicates seen, [1] inserted count                            */
+	int			has_dups;
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * error plumbing
+ * --------------------------------------------------------------------------------------------- */
+static inline int
+cb_fail(cbgpu_ctx *ctx, int code, const char *fmt, const char *a = "", long long b = 0)
+{
+	if (ctx)
+		snprintf(ctx->err, sizeof(ctx->err), fmt, a, b);
+	return code;
+}
+
+#define CB_CUDA(ctx, call) \
+	do { \
+		cudaError_t e__ = (call); \
+		if (e__ != cudaSuccess) \
+		{ \
+			if (ctx) \
+				snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+			return CBGPU_ERR_CUDA; \
+		} \
+	} while (0)
+
+/* kernel launch bookkeeping (every kernel of ours goes through this) */
+#define CB_LAUNCHED(ctx, name) \
+	do { \
+		(ctx)->launches++; \
+		cudaError_t e__ = cudaGetLastError(); \
+		if (e__ != cudaSuccess) \
+		{ \
+			snprintf((ctx)->err, sizeof((ctx)->err), "launch %s: %s", name, cudaGetErrorString(e__)); \
+			return CBGPU_ERR_CUDA; \
+		} \
+	} while (0)
+
+int			cb_check_status(cbgpu_ctx *ctx, const char *what);	/* sync + read device status word */
+
+static inline int
+cb_type_w(int t)
+{
+	return cb_type_width((CbTypeId) t);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * the reference's hash functions, device + host
+ * --------------------------------------------------------------------------------------------- */
+#define CB_HD __host__ __device__ __forceinline__
+
+CB_HD uint32_t
+pg_rot(uint32_t x, int k)
+{
+	return (x << k) | (x >> (32 - k));
+}
+
+/* final() of common/hashfn.c:133-142 */
+#define PG_FINAL(a, b, c) \
+	do { \
+		c ^= b; c -= pg_rot(b, 14); \
+		a ^= c; a -= pg_rot(c, 11); \
+		b ^= a; b -= pg_rot(a, 25); \
+		c ^= b; c -= pg_rot(b, 16); \
+		a ^= c; a -= pg_rot(c, 4); \
+		b ^= a; b -= pg_rot(a, 14); \
+		c ^= b; c -= pg_rot(b, 24); \
+	} while (0)
+
+/* mix() of common/hashfn.c:99-107 */
+#define PG_MIX(a, b, c) \
+	do { \
+		a -= c; a ^= pg_rot(c, 4); c += b; \
+		b -= a; b ^= pg_rot(a, 6); a += c; \
+		c -= b; c ^= pg_rot(b, 8); b += a; \
+		a -= c; a ^= pg_rot(c, 16); c += b; \
+		b -= a; b ^= pg_rot(a, 19); a += c; \
+		c -= b; c ^= pg_rot(b, 4); b += a; \
+	} while (0)
+
+/* hash_bytes_uint32 (common/hashfn.c:627-640) = hashint4 (access/hash/hashfunc.c:72); dates hash
+ * as int4 (catalog/pg_amproc.dat:310) */
+CB_HD uint32_t
+pg_hash_uint32(uint32_t k)
+{
+	uint32_t	a, b, c;
+
+	a = b = c = 0x9e3779b9u + (uint32_t) sizeof(uint32_t) + 3923095u;
+	a += k;
+	PG_FINAL(a, b, c);
+	return c;
+}
+
+/* hashint8 (access/hash/hashfunc.c:84-102) */
+CB_HD uint32_t
+pg_hashint8(int64_t val)
+{
+	uint32_t	lohalf = (uint32_t) val;
+	uint32_t	hihalf = (uint32_t) ((uint64_t) val >> 32);
+
+	lohalf ^= (val >= 0) ? hihalf : ~hihalf;
+	return pg_hash_uint32(lohalf);
+}
+
+/* hash_bytes (common/hashfn.c:146-360) over exactly 8 bytes given as two little-endian words */
+CB_HD uint32_t
+pg_hash_bytes8(uint32_t w0, uint32_t w1)
+{
+	uint32_t	a, b, c;
+
+	a = b = c = 0x9e3779b9u + 8u + 3923095u;
+	b += w1;
+	a += w0;
+	PG_FINAL(a, b, c);
+	return c;
+}
+
+/* hash_bytes over 0 or 1 byte: hashbpchar of a character(1) value (utils/adt/varchar.c:981-1004,
+ * bcTruelen strips a trailing blank so ' ' hashes zero bytes) */
+CB_HD uint32_t
+pg_hash_bpchar1(uint8_t ch)
+{
+	uint32_t	a, b, c;
+	uint32_t	len = (ch == (uint8_t) ' ') ? 0u : 1u;
+
+	a = b = c = 0x9e3779b9u + len + 3923095u;
+	if (len)
+		a += ch;
+	PG_FINAL(a, b, c);
+	return c;
+}
+
+/* hashfloat8 (access/hash/hashfunc.c:194-216) */
+CB_HD uint32_t
+pg_hashfloat8(uint64_t bits)
+{
+	if ((bits << 1) == 0)
+		return 0;				/* +0 and -0 */
+	if (((bits >> 52) & 0x7ff) == 0x7ff && (bits & 0xfffffffffffffull) != 0)
+		bits = 0x7ff8000000000000ull;	/* get_float8_nan() */
+	return pg_hash_bytes8((uint32_t) bits, (uint32_t) (bits >> 32));
+}
+
+/* general hash_bytes for the host side (dictionary strings) */
+static inline uint32_t
+pg_hash_bytes_host(const unsigned char *k, int keylen)
+{
+	uint32_t	a, b, c;
+	int			len = keylen;
+
+	a = b = c = 0x9e3779b9u + (uint32_t) len + 3923095u;
+	while (len >= 12)
+	{
+		a += (k[0] + ((uint32_t) k[1] << 8) + ((uint32_t) k[2] << 16) + ((uint32_t) k[3] << 24));
+		b += (k[4] + ((uint32_t) k[5] << 8) + ((uint32_t) k[6] << 16) + ((uint32_t) k[7] << 24));
+		c += (k[8] + ((uint32_t) k[9] << 8) + ((uint32_t) k[10] << 16) + ((uint32_t) k[11] << 24));
+		PG_MIX(a, b, c);
+		k += 12;
+		len -= 12;
+	}
+	switch (len)
+	{
+		case 11: c += ((uint32_t) k[10] << 24);
+		case 10: c += ((uint32_t) k[9] << 16);
+		case 9:  c += ((uint32_t) k[8] << 8);
+		case 8:  b += ((uint32_t) k[7] << 24);
+		case 7:  b += ((uint32_t) k[6] << 16);
+		case 6:  b += ((uint32_t) k[5] << 8);
+		case 5:  b += k[4];
+		case 4:  a += ((uint32_t) k[3] << 24);
+		case 3:  a += ((uint32_t) k[2] << 16);
+		case 2:  a += ((uint32_t) k[1] << 8);
+		case 1:  a += k[0];
+	}
+	PG_FINAL(a, b, c);
+	return c;
+}
+
+/* murmurhash32 (include/common/hashfn.h:93-103): finaliser of TupleHashTableHash_internal
+ * (executor/execGrouping.c:495) */
+CB_HD uint32_t
+pg_murmurhash32(uint32_t h)
+{
+	h ^= h >> 16;
+	h *= 0x85ebca6bu;
+	h ^= h >> 13;
+	h *= 0xc2b2ae35u;
+	h ^= h >> 16;
+	return h;
+}
+
+/* per-key combine: rotate left 1 then XOR (NULL contributes nothing): executor/nodeHash.c:2134,
+ * executor/execGrouping.c:474, cdb/cdbhash.c:196 */
+CB_HD uint32_t
+pg_hash_combine(uint32_t acc, uint32_t h, bool isnull)
+{
+	acc = (acc << 1) | (acc >> 31);
+	return isnull ? acc : (acc ^ h);
+}
+
+/* jump_consistent_hash (cdb/cdbhash.c:530-541).  The double-precision divide and the
+ * int64 * double product must round as on the host: plain IEEE ops, no fma contraction. */
+CB_HD int32_t
+pg_jump_consistent_hash(uint64_t key, int32_t num_segments)
+{
+	int64_t		b = -1;
+	int64_t		j = 0;
+
+	while (j < num_segments)
+	{
+		b = j;
+		key = key * 2862933555777941757ULL + 1;
+#ifdef __CUDA_ARCH__
+		double		q = __ddiv_rn((double) (1LL << 31), (double) ((key >> 33) + 1));
+
+		j = (int64_t) __dmul_rn((double) (b + 1), q);
+#else
+		double		q = (double) (1LL << 31) / (double) ((key >> 33) + 1);
+
+		j = (int64_t) ((double) (b + 1) * q);
+#endif
+	}
+	return (int32_t) b;
+}
+
+/* hash function of one key datum by type (pg_amproc: hashint4, hashint8, hashfloat8, hashbpchar,
+ * hashchar for bool) on the 64-bit widened value */
+__device__ __forceinline__ uint32_t
+pg_hash_datum(int type, int64_t v, const uint32_t *dict)
+{
+	switch (type)
+	{
+		case CB_INT4: case CB_DATE:
+			return pg_hash_uint32((uint32_t) (int32_t) v);
+		case CB_INT8:
+			return pg_hashint8(v);
+		case CB_FLOAT8:
+			return pg_hashfloat8((uint64_t) v);
+		case CB_BPCHAR1:
+			return pg_hash_bpchar1((uint8_t) v);
+		case CB_DICT8: case CB_DICT32:
+			return dict ? __ldg(dict + v) : 0u;
+		case CB_BOOL:
+			return pg_hash_uint32((uint32_t) (int32_t) (int8_t) v);
+		default:
+			return 0u;
+	}
+}
+
+/* widen a column element to 64 bits (float8: raw bits) */
+__device__ __forceinline__ int64_t
+cb_load_widen(const void *data, int type, uint32_t row)
+{
+	switch (type)
+	{
+		case CB_INT4: case CB_DATE: case CB_DICT32:
+			return (int64_t) __ldg((const int32_t *) data + row);
+		case CB_INT8: case CB_NUMERIC: case CB_FLOAT8:
+			return __ldg((const long long *) data + row);
+		default:
+			return (int64_t) __ldg((const uint8_t *) data + row);
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * exact 128-bit accumulate built from 64-bit atomics.  Additions commute, so the final (hi, lo)
+ * pair is exact once all adds have landed: lo wraps, each wrap carries into hi.
+ * (The reference keeps int8 sums in an Int128AggState, utils/adt/numeric.c:5340.)
+ * --------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void
+atomic_add128(unsigned long long *acc, unsigned long long lo, unsigned long long hi)
+{
+	if (lo)
+	{
+		unsigned long long old = atomicAdd(acc, lo);
+
+		if (old + lo < old)
+			hi += 1;
+	}
+	if (hi)
+		atomicAdd(acc + 1, hi);
+}
+
+__device__ __forceinline__ void
+atomic_add128_signed(unsigned long long *acc, long long v)
+{
+	atomic_add128(acc, (unsigned long long) v, v < 0 ? ~0ull : 0ull);
+}
+
+/* group lookup / insert in an agg table.  Returns the slot, or -1 when the table is full. */
+__device__ __forceinline__ int
+agg_find_or_insert(const AggDev &t, uint32_t hash, const int64_t *keys, uint32_t nullmask)
+{
+	uint32_t	pos = hash & t.mask;
+
+	for (uint32_t probes = 0; probes <= t.mask; probes++)
+	{
+		int			s = *((volatile int *) (t.state + pos));
+
+		if (s == 0)
+		{
+			int			old = atomicCAS(t.state + pos, 0, 1);
+
+			if (old == 0)
+			{
+				/* initialize_hash_entry (executor/nodeAgg.c:2220): copy the grouping keys */
+				for (int k = 0; k < t.nkeys; k++)
+					t.keys[(size_t) pos * t.nkeys + k] = keys[k];
+				t.keynull[pos] = nullmask;
+				t.hash[pos] = hash;
+				__threadfence();
+				*((volatile int *) (t.state + pos)) = 2;
+				atomicAdd(t.ngroups, 1);
+				return (int) pos;
+			}
+			s = old;
+		}
+		while (s == 1)
+			s = *((volatile int *) (t.state + pos));
+		__threadfence();
+		if (*((volatile uint32_t *) (t.hash + pos)) == hash && *((volatile uint32_t *) (t.keynull + pos)) == nullmask)
+		{
+			/* TupleHashTableMatch (executor/execGrouping.c:548): NULLs group together */
+			bool		same = true;
+
+			for (int k = 0; k < t.nkeys; k++)
+				if (!((nullmask >> k) & 1) && *((volatile long long *) (t.keys + (size_t) pos * t.nkeys + k)) != keys[k])
+					same = false;
+			if (same)
+				return (int) pos;
+		}
+		pos = (pos + 1) & t.mask;
+	}
+	atomicExch(t.full, 1);
+	return -1;
+}

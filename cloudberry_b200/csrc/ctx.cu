@@ -1,0 +1,526 @@
+/*
+ * ctx.cu - context, HBM-resident relations, timing helpers.
+ *
+ * A relation here is the decoded, projected form of an AOCS table: what aocs_beginscan
+ * (backend/access/aocs/aocsam.c:549) + the datum-stream block cursor (include/utils/
+ * datumstreamblock.h:1220-1614) hand the executor one Datum at a time, laid out instead as one
+ * contiguous fixed-width array per projected column (DESIGN.md "data layout in HBM").
+ */
+#include "common.cuh"
+
+#include <stdlib.h>
+
+extern "C" int
+cbgpu_device_count(void)
+{
+	int			n = 0;
+
+	if (cudaGetDeviceCount(&n) != cudaSuccess)
+		return 0;
+	return n;
+}
+
+extern "C" int
+cbgpu_ctx_create(int device, cbgpu_ctx **out)
+{
+	cbgpu_ctx  *ctx = (cbgpu_ctx *) calloc(1, sizeof(cbgpu_ctx));
+	cudaDeviceProp prop;
+
+	if (!ctx)
+		return CBGPU_ERR_NOMEM;
+	*out = ctx;
+	ctx->device = device;
+	CB_CUDA(ctx, cudaSetDevice(device));
+	CB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+	ctx->sm_count = prop.multiProcessorCount;
+	CB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	CB_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
+	CB_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
+	CB_CUDA(ctx, cudaEventCreate(&ctx->ev_k0));
+	CB_CUDA(ctx, cudaEventCreate(&ctx->ev_k1));
+	CB_CUDA(ctx, cudaMalloc(&ctx->d_status, sizeof(int)));
+	CB_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+	CB_CUDA(ctx, cudaMallocHost(&ctx->h_status, sizeof(int)));
+	*ctx->h_status = 0;
+	/* L2 is 126 MB on B200: flush buffer comfortably larger */
+	ctx->flush_bytes = (size_t) 512 << 20;
+	ctx->flush_buf = NULL;
+	return CBGPU_OK;
+}
+
+extern "C" void
+cbgpu_ctx_destroy(cbgpu_ctx *ctx)
+{
+	if (!ctx)
+		return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->flush_buf)
+		cudaFree(ctx->flush_buf);
+	cudaFree(ctx->d_status);
+	cudaFreeHost(ctx->h_status);
+	cudaEventDestroy(ctx->ev_t0);
+	cudaEventDestroy(ctx->ev_t1);
+	cudaEventDestroy(ctx->ev_k0);
+	cudaEventDestroy(ctx->ev_k1);
+	cudaStreamDestroy(ctx->stream);
+	free(ctx);
+}
+
+extern "C" const char *
+cbgpu_last_error(cbgpu_ctx *ctx)
+{
+	return ctx ? ctx->err : "no context";
+}
+
+extern "C" int
+cbgpu_sync(cbgpu_ctx *ctx)
+{
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return CBGPU_OK;
+}
+
+int
+cb_check_status(cbgpu_ctx *ctx, const char *what)
+{
+	CB_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (*ctx->h_status != 0)
+	{
+		int			code = *ctx->h_status;
+
+		CB_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+		snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what,
+				 code == CBGPU_ERR_OVERFLOW ? "value out of range (integer/numeric overflow)" :
+				 code == CBGPU_ERR_NOMEM ? "device table or output buffer full" : "device-side error");
+		return code;
+	}
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_check_status(cbgpu_ctx *ctx)
+{
+	return cb_check_status(ctx, "GPU pipeline");
+}
+
+extern "C" int
+cbgpu_sm_count(cbgpu_ctx *ctx)
+{
+	return ctx->sm_count;
+}
+
+extern "C" int64_t
+cbgpu_kernel_launches(cbgpu_ctx *ctx)
+{
+	return ctx->launches;
+}
+
+extern "C" int
+cbgpu_timer_start(cbgpu_ctx *ctx)
+{
+	CB_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_timer_stop_ms(cbgpu_ctx *ctx, double *ms)
+{
+	float		f = 0;
+
+	CB_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+	CB_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+	CB_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev_t0, ctx->ev_t1));
+	*ms = f;
+	return CBGPU_OK;
+}
+
+extern "C" double
+cbgpu_last_kernel_ms(cbgpu_ctx *ctx)
+{
+	float		f = 0;
+
+	if (!ctx->kernel_timed)
+		return -1.0;
+	if (cudaEventSynchronize(ctx->ev_k1) != cudaSuccess)
+		return -1.0;
+	if (cudaEventElapsedTime(&f, ctx->ev_k0, ctx->ev_k1) != cudaSuccess)
+		return -1.0;
+	return f;
+}
+
+extern "C" const char *
+cbgpu_last_kernel_name(cbgpu_ctx *ctx)
+{
+	return ctx->last_kernel_name ? ctx->last_kernel_name : "";
+}
+
+__global__ void
+k_flush_fill(uint4 *p, size_t n, uint32_t v)
+{
+	size_t		i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	size_t		stride = (size_t) gridDim.x * blockDim.x;
+
+	for (; i < n; i += stride)
+		p[i] = make_uint4(v, v, v, v);
+}
+
+extern "C" int
+cbgpu_flush_l2(cbgpu_ctx *ctx)
+{
+	static uint32_t gen = 0;
+
+	if (!ctx->flush_buf)
+		CB_CUDA(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+	k_flush_fill<<<ctx->sm_count * 4, 512, 0, ctx->stream>>>((uint4 *) ctx->flush_buf, ctx->flush_bytes / 16, ++gen);
+	CB_LAUNCHED(ctx, "k_flush_fill");
+	return CBGPU_OK;
+}
+
+extern "C" void *
+cbgpu_host_alloc(size_t bytes)
+{
+	void	   *p = NULL;
+
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess)
+		return NULL;
+	return p;
+}
+
+extern "C" void
+cbgpu_host_free(void *p)
+{
+	if (p)
+		cudaFreeHost(p);
+}
+
+extern "C" uint32_t
+cbgpu_hashbpchar(const char *s, int32_t len)
+{
+	/* bcTruelen (utils/adt/varchar.c:704): ignore trailing blanks */
+	while (len > 0 && s[len - 1] == ' ')
+		len--;
+	return pg_hash_bytes_host((const unsigned char *) s, len);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * relations
+ * --------------------------------------------------------------------------------------------- */
+extern "C" int
+cbgpu_rel_create(cbgpu_ctx *ctx, int64_t nrows, int32_t ncols, const int32_t *types, const int32_t *dscales,
+				 cbgpu_rel **out)
+{
+	cbgpu_rel  *r;
+
+	if (ncols < 0 || ncols > CB_MAX_COLS_REL || nrows < 0 || nrows > 0xFFFFFFF0ll)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_create: bad shape (%s nrows=%lld)", "", nrows);
+	r = (cbgpu_rel *) calloc(1, sizeof(cbgpu_rel));
+	if (!r)
+		return CBGPU_ERR_NOMEM;
+	r->ctx = ctx;
+	r->nrows = nrows;
+	r->capacity = nrows;
+	r->ncols = ncols;
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	for (int i = 0; i < ncols; i++)
+	{
+		size_t		bytes = (size_t) (nrows ? nrows : 1) * cb_type_w(types[i]);
+
+		if (cb_type_w(types[i]) == 0)
+		{
+			free(r);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_create: bad column type%s %lld", "", types[i]);
+		}
+		r->types[i] = types[i];
+		r->dscales[i] = dscales ? dscales[i] : 0;
+		/* pad so 16-byte vector loads and TMA bulk copies may read a whole final vector */
+		bytes = (bytes + 255) & ~(size_t) 255;
+		CB_CUDA(ctx, cudaMalloc(&r->data[i], bytes));
+		r->owns[i] = true;
+	}
+	*out = r;
+	return CBGPU_OK;
+}
+
+extern "C" void
+cbgpu_rel_free(cbgpu_rel *rel)
+{
+	if (!rel)
+		return;
+	cudaSetDevice(rel->ctx->device);
+	cudaStreamSynchronize(rel->ctx->stream);
+	for (int i = 0; i < rel->ncols; i++)
+	{
+		if (rel->owns[i] && rel->data[i])
+			cudaFree(rel->data[i]);
+		if (rel->nulls[i])
+			cudaFree(rel->nulls[i]);
+		if (rel->dict_hash[i] && rel->dict_n[i] >= 0)
+			cudaFree(rel->dict_hash[i]);
+	}
+	if (rel->visimap)
+		cudaFree(rel->visimap);
+	free(rel);
+}
+
+extern "C" int64_t
+cbgpu_rel_nrows(const cbgpu_rel *rel)
+{
+	return rel->nrows;
+}
+
+extern "C" int32_t
+cbgpu_rel_ncols(const cbgpu_rel *rel)
+{
+	return rel->ncols;
+}
+
+extern "C" int32_t
+cbgpu_rel_col_type(const cbgpu_rel *rel, int32_t col)
+{
+	return (col >= 0 && col < rel->ncols) ? rel->types[col] : 0;
+}
+
+extern "C" int32_t
+cbgpu_rel_col_dscale(const cbgpu_rel *rel, int32_t col)
+{
+	return (col >= 0 && col < rel->ncols) ? rel->dscales[col] : 0;
+}
+
+extern "C" int
+cbgpu_rel_load_column(cbgpu_rel *rel, int32_t col, const void *host, const uint8_t *nulls)
+{
+	cbgpu_ctx  *ctx = rel->ctx;
+
+	if (col < 0 || col >= rel->ncols)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_load_column: bad column%s %lld", "", col);
+	if (rel->nrows == 0)
+		return CBGPU_OK;
+	CB_CUDA(ctx, cudaMemcpyAsync(rel->data[col], host, (size_t) rel->nrows * cb_type_w(rel->types[col]),
+								 cudaMemcpyHostToDevice, ctx->stream));
+	if (nulls)
+	{
+		if (!rel->nulls[col])
+			CB_CUDA(ctx, cudaMalloc(&rel->nulls[col], (size_t) rel->capacity));
+		CB_CUDA(ctx, cudaMemcpyAsync(rel->nulls[col], nulls, (size_t) rel->nrows, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	else if (rel->nulls[col])
+	{
+		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(rel->nulls[col]);
+		rel->nulls[col] = NULL;
+	}
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_rel_read_column(cbgpu_rel *rel, int32_t col, int64_t lo, int64_t hi, void *host, uint8_t *nulls)
+{
+	cbgpu_ctx  *ctx = rel->ctx;
+	int			w;
+
+	if (col < 0 || col >= rel->ncols || lo < 0 || hi > rel->nrows || lo > hi)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_read_column: bad range%s %lld", "", lo);
+	w = cb_type_w(rel->types[col]);
+	if (hi > lo)
+	{
+		CB_CUDA(ctx, cudaMemcpyAsync(host, (char *) rel->data[col] + (size_t) lo * w, (size_t) (hi - lo) * w,
+									 cudaMemcpyDeviceToHost, ctx->stream));
+		if (nulls)
+		{
+			if (rel->nulls[col])
+				CB_CUDA(ctx, cudaMemcpyAsync(nulls, rel->nulls[col] + lo, (size_t) (hi - lo), cudaMemcpyDeviceToHost, ctx->stream));
+			else
+				memset(nulls, 0, (size_t) (hi - lo));
+		}
+	}
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_rel_set_visimap(cbgpu_rel *rel, const uint8_t *bits)
+{
+	cbgpu_ctx  *ctx = rel->ctx;
+	size_t		bytes = (size_t) ((rel->nrows + 7) / 8);
+
+	if (!bits)
+	{
+		if (rel->visimap)
+		{
+			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			cudaFree(rel->visimap);
+			rel->visimap = NULL;
+		}
+		return CBGPU_OK;
+	}
+	if (!rel->visimap)
+		CB_CUDA(ctx, cudaMalloc(&rel->visimap, ((bytes + 255) & ~(size_t) 255) + 256));
+	CB_CUDA(ctx, cudaMemcpyAsync(rel->visimap, bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_rel_set_dict_hash(cbgpu_rel *rel, int32_t col, const uint32_t *hashes, int32_t n)
+{
+	cbgpu_ctx  *ctx = rel->ctx;
+
+	if (col < 0 || col >= rel->ncols || n <= 0)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_set_dict_hash: bad argument%s %lld", "", col);
+	if (rel->dict_hash[col])
+	{
+		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(rel->dict_hash[col]);
+	}
+	CB_CUDA(ctx, cudaMalloc(&rel->dict_hash[col], (size_t) n * sizeof(uint32_t)));
+	CB_CUDA(ctx, cudaMemcpyAsync(rel->dict_hash[col], hashes, (size_t) n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	rel->dict_n[col] = n;
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_rel_set_nrows(cbgpu_rel *rel, int64_t nrows)
+{
+	if (nrows < 0 || nrows > rel->capacity)
+		return cb_fail(rel->ctx, CBGPU_ERR_INVALID, "cbgpu_rel_set_nrows: beyond capacity%s %lld", "", nrows);
+	rel->nrows = nrows;
+	return CBGPU_OK;
+}
+
+extern "C" void *
+cbgpu_rel_col_devptr(cbgpu_rel *rel, int32_t col)
+{
+	return (col >= 0 && col < rel->ncols) ? rel->data[col] : NULL;
+}
+
+extern "C" size_t
+cbgpu_rel_nbytes(const cbgpu_rel *rel)
+{
+	size_t		b = 0;
+
+	for (int i = 0; i < rel->ncols; i++)
+		b += (size_t) rel->nrows * cb_type_w(rel->types[i]);
+	return b;
+}
+
+extern "C" int
+cbgpu_read_u32(cbgpu_ctx *ctx, const uint32_t *dev, int64_t n, uint32_t *host)
+{
+	if (n > 0)
+		CB_CUDA(ctx, cudaMemcpyAsync(host, dev, (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_dev_alloc(cbgpu_ctx *ctx, size_t bytes, void **dev)
+{
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	CB_CUDA(ctx, cudaMalloc(dev, bytes ? bytes : 8));
+	CB_CUDA(ctx, cudaMemsetAsync(*dev, 0, bytes ? bytes : 8, ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_dev_read(cbgpu_ctx *ctx, const void *dev, size_t bytes, void *host)
+{
+	CB_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_dev_write(cbgpu_ctx *ctx, void *dev, size_t bytes, const void *host)
+{
+	CB_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" void
+cbgpu_dev_free(cbgpu_ctx *ctx, void *dev)
+{
+	if (!dev)
+		return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(dev);
+}
+
+extern "C" int
+cbgpu_rel_add_nullmap(cbgpu_rel *rel, int32_t col)
+{
+	cbgpu_ctx  *ctx = rel->ctx;
+
+	if (col < 0 || col >= rel->ncols)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_add_nullmap: bad column%s %lld", "", col);
+	if (rel->nulls[col])
+		return CBGPU_OK;
+	CB_CUDA(ctx, cudaMalloc(&rel->nulls[col], (size_t) (rel->capacity ? rel->capacity : 1)));
+	CB_CUDA(ctx, cudaMemsetAsync(rel->nulls[col], 0, (size_t) (rel->capacity ? rel->capacity : 1), ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_rel_copy_rows(cbgpu_rel *dst, int64_t dst_lo, cbgpu_rel *src, int64_t src_lo, int64_t n)
+{
+	cbgpu_ctx  *ctx = dst->ctx;
+
+	if (dst->ncols != src->ncols || dst_lo < 0 || src_lo < 0 || dst_lo + n > dst->capacity || src_lo + n > src->capacity)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_copy_rows: shape / range mismatch%s (%lld rows)", "", n);
+	if (n == 0)
+		return CBGPU_OK;
+	for (int c = 0; c < dst->ncols; c++)
+	{
+		int			w = cb_type_w(dst->types[c]);
+
+		if (dst->types[c] != src->types[c])
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_copy_rows: column %s%lld type mismatch", "", c);
+		CB_CUDA(ctx, cudaMemcpyAsync((char *) dst->data[c] + (size_t) dst_lo * w, (char *) src->data[c] + (size_t) src_lo * w,
+									 (size_t) n * w, cudaMemcpyDeviceToDevice, ctx->stream));
+		if (src->nulls[c])
+		{
+			int			rc = cbgpu_rel_add_nullmap(dst, c);
+
+			if (rc)
+				return rc;
+			CB_CUDA(ctx, cudaMemcpyAsync(dst->nulls[c] + dst_lo, src->nulls[c] + src_lo, (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+		}
+	}
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_rel_has_nulls(const cbgpu_rel *rel, int32_t col)
+{
+	return (col >= 0 && col < rel->ncols && rel->nulls[col]) ? 1 : 0;
+}
+
+extern "C" const uint32_t *
+cbgpu_rel_dict_hash_dev(const cbgpu_rel *rel, int32_t col)
+{
+	return (col >= 0 && col < rel->ncols) ? rel->dict_hash[col] : NULL;
+}
+
+extern "C" const uint8_t *
+cbgpu_rel_nulls_dev(const cbgpu_rel *rel, int32_t col)
+{
+	return (col >= 0 && col < rel->ncols) ? rel->nulls[col] : NULL;
+}
+
+extern "C" const uint8_t *
+cbgpu_rel_visimap_dev(const cbgpu_rel *rel)
+{
+	return rel->visimap;
+}
+
+extern "C" int
+cbgpu_rel_share_dict_hash(cbgpu_rel *dst, int32_t dcol, const cbgpu_rel *src, int32_t scol)
+{
+	if (dcol < 0 || dcol >= dst->ncols || scol < 0 || scol >= src->ncols)
+		return cb_fail(dst->ctx, CBGPU_ERR_INVALID, "cbgpu_rel_share_dict_hash: bad column%s %lld", "", dcol);
+	dst->dict_hash[dcol] = src->dict_hash[scol];
+	dst->dict_n[dcol] = -src->dict_n[scol];	/* negative: borrowed, not freed with dst */
+	return CBGPU_OK;
+}

@@ -1,0 +1,409 @@
+/*
+ * hashtable.cu - hash join build (K2) and the stand-alone pair-emitting probe (K3).
+ *
+ * Build restates MultiExecPrivateHash -> ExecHashGetHashValue -> ExecHashTableInsert
+ * (backend/executor/nodeHash.c:167, 2089, 1877): per inner row hash = rotl1-xor of the per-key
+ * hash functions (no finaliser), rows with a NULL key are not inserted (strict operators, :2161).
+ * The reference chains MinimalTuples off nbuckets = pow2(ntuples / 5) bucket heads; the device
+ * table is open addressing with linear probing over slots = hash32 << 32 | inner row id, at load
+ * factor <= 0.5, and late-materialises: the inner payload stays in its column arrays and is
+ * gathered by row id only for surviving rows.  The slot position uses the same 32-bit hash value
+ * the reference computes (bucketno = hashvalue & (nbuckets - 1), nodeHash.c:2233).
+ *
+ * Probe restates ExecScanHashBucket (nodeHash.c:2255-2308): compare the stored hash value first,
+ * then the key equality (hashqualclauses).
+ */
+#include "common.cuh"
+
+#include <stdlib.h>
+
+struct BuildParams
+{
+	HtDev		ht;
+	int64_t		nrows;
+	int		   *flags;			/* [0] duplicate key seen, [1] rows inserted                          */
+};
+
+__device__ __forceinline__ bool
+ht_row_hash(const HtDev &ht, uint32_t row, uint32_t *hash)
+{
+	uint32_t	h = 0;
+
+	for (int k = 0; k < ht.nkeys; k++)
+	{
+		if (ht.keynulls[k] && ht.keynulls[k][row])
+			return false;
+		int64_t		v = cb_load_widen(ht.keydata[k], ht.keytype[k], row);
+
+		h = pg_hash_combine(h, pg_hash_datum(ht.keytype[k], v, ht.keydict[k]), false);
+	}
+	*hash = h;
+	return true;
+}
+
+__device__ __forceinline__ bool
+ht_keys_equal_rows(const HtDev &ht, uint32_t ra, uint32_t rb)
+{
+	for (int k = 0; k < ht.nkeys; k++)
+		if (cb_load_widen(ht.keydata[k], ht.keytype[k], ra) != cb_load_widen(ht.keydata[k], ht.keytype[k], rb))
+			return false;
+	return true;
+}
+
+__global__ void
+k_ht_clear(unsigned long long *slots, size_t n)
+{
+	size_t		i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	size_t		stride = (size_t) gridDim.x * blockDim.x;
+
+	for (; i < n; i += stride)
+		slots[i] = HT_EMPTY;
+}
+
+__global__ void __launch_bounds__(256)
+k_ht_build(BuildParams p)
+{
+	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t		stride = (int64_t) gridDim.x * blockDim.x;
+	int			inserted = 0;
+	bool		dup = false;
+
+	for (; i < p.nrows; i += stride)
+	{
+		uint32_t	row = (uint32_t) i;
+		uint32_t	h;
+
+		if (!ht_row_hash(p.ht, row, &h))
+			continue;
+		unsigned long long e = ((unsigned long long) h << 32) | row;
+		uint32_t	pos = h & p.ht.mask;
+
+		for (;;)
+		{
+			unsigned long long cur = p.ht.slots[pos];
+
+			if (cur == HT_EMPTY)
+			{
+				cur = atomicCAS(p.ht.slots + pos, HT_EMPTY, e);
+				if (cur == HT_EMPTY)
+					break;
+			}
+			/* occupied: same hash value -> maybe the same key (a duplicate on the build side) */
+			if ((uint32_t) (cur >> 32) == h && !dup && ht_keys_equal_rows(p.ht, (uint32_t) cur, row))
+				dup = true;
+			pos = (pos + 1) & p.ht.mask;
+		}
+		inserted++;
+	}
+	if (dup)
+		atomicExch(p.flags, 1);
+	/* one atomic per warp for the inserted count */
+	for (int o = 16; o; o >>= 1)
+		inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
+	if ((threadIdx.x & 31) == 0 && inserted)
+		atomicAdd(p.flags + 1, inserted);
+}
+
+extern "C" int
+cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t nkeys, cbgpu_hashtable **out)
+{
+	cbgpu_hashtable *ht;
+	int64_t		nslots = 64;
+	BuildParams p;
+	int			h_flags[2];
+
+	if (nkeys < 1 || nkeys > CBP_MAX_KEYS)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "hash join with %s%lld key columns is beyond the GPU path's limit (4)", "", nkeys);
+	while (nslots < inner->nrows * 2)
+		nslots <<= 1;
+	if (nslots > (1ll << 32))
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "hash join build side too large for 32-bit slots%s (%lld rows)", "", inner->nrows);
+	ht = (cbgpu_hashtable *) calloc(1, sizeof(cbgpu_hashtable));
+	if (!ht)
+		return CBGPU_ERR_NOMEM;
+	ht->ctx = ctx;
+	ht->inner = inner;
+	ht->nslots = nslots;
+	ht->d.mask = (uint32_t) (nslots - 1);
+	ht->d.nkeys = nkeys;
+	for (int k = 0; k < nkeys; k++)
+	{
+		int			c = keycols[k];
+
+		if (c < 0 || c >= inner->ncols)
+		{
+			free(ht);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_ht_build: bad key column%s %lld", "", c);
+		}
+		if (inner->types[c] == CB_NUMERIC)
+		{
+			free(ht);
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "numeric hash join keys (hash_numeric) are not on the GPU path%s", "", 0);
+		}
+		if ((inner->types[c] == CB_DICT8 || inner->types[c] == CB_DICT32) && !inner->dict_hash[c])
+		{
+			free(ht);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "dictionary column %s%lld used as a join key without dict hashes", "", c);
+		}
+		ht->d.keydata[k] = inner->data[c];
+		ht->d.keynulls[k] = inner->nulls[c];
+		ht->d.keydict[k] = inner->dict_hash[c];
+		ht->d.keytype[k] = inner->types[c];
+	}
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	CB_CUDA(ctx, cudaMalloc(&ht->d.slots, (size_t) nslots * sizeof(unsigned long long)));
+	CB_CUDA(ctx, cudaMalloc(&ht->d_flags, 2 * sizeof(int)));
+	CB_CUDA(ctx, cudaMemsetAsync(ht->d_flags, 0, 2 * sizeof(int), ctx->stream));
+	int			blocks = (int) ((nslots + 255) / 256);
+
+	if (blocks > ctx->sm_count * 8)
+		blocks = ctx->sm_count * 8;
+	k_ht_clear<<<blocks, 256, 0, ctx->stream>>>(ht->d.slots, (size_t) nslots);
+	CB_LAUNCHED(ctx, "k_ht_clear");
+	p.ht = ht->d;
+	p.nrows = inner->nrows;
+	p.flags = ht->d_flags;
+	if (inner->nrows > 0)
+	{
+		blocks = (int) ((inner->nrows + 255) / 256);
+		if (blocks > ctx->sm_count * 8)
+			blocks = ctx->sm_count * 8;
+		k_ht_build<<<blocks, 256, 0, ctx->stream>>>(p);
+		CB_LAUNCHED(ctx, "k_ht_build");
+	}
+	CB_CUDA(ctx, cudaMemcpyAsync(h_flags, ht->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ht->has_dups = h_flags[0];
+	ht->ninserted = h_flags[1];
+	*out = ht;
+	return CBGPU_OK;
+}
+
+extern "C" void
+cbgpu_ht_free(cbgpu_hashtable *ht)
+{
+	if (!ht)
+		return;
+	cudaSetDevice(ht->ctx->device);
+	cudaStreamSynchronize(ht->ctx->stream);
+	cudaFree(ht->d.slots);
+	cudaFree(ht->d_flags);
+	free(ht);
+}
+
+extern "C" int64_t
+cbgpu_ht_nrows(const cbgpu_hashtable *ht)
+{
+	return ht->ninserted;
+}
+
+extern "C" int
+cbgpu_ht_has_duplicates(const cbgpu_hashtable *ht)
+{
+	return ht->has_dups;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * K3 stand-alone: (outer_idx, inner_idx) pairs for every match (INNER join), two passes:
+ * count matches per outer row -> exclusive scan -> write pairs.  Output order is outer-row major,
+ * so the pair list is deterministic.
+ * --------------------------------------------------------------------------------------------- */
+struct ProbeParams
+{
+	HtDev		ht;
+	const void *okey[CBP_MAX_KEYS];
+	const uint8_t *onulls[CBP_MAX_KEYS];
+	const uint32_t *odict[CBP_MAX_KEYS];
+	int32_t		otype[CBP_MAX_KEYS];
+	const uint32_t *sel;
+	int64_t		n;
+	unsigned long long *counts;	/* [n + 1] match counts, then their exclusive scan                    */
+	uint32_t   *out_outer;
+	uint32_t   *out_inner;
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256)
+k_ht_probe_pairs(ProbeParams p)
+{
+	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t		stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; i < p.n; i += stride)
+	{
+		uint32_t	row = p.sel ? p.sel[i] : (uint32_t) i;
+		uint32_t	h = 0;
+		int64_t		key[CBP_MAX_KEYS];
+		bool		isnull = false;
+		unsigned long long cnt = 0;
+		unsigned long long base = WRITE ? p.counts[i] : 0;
+
+		for (int k = 0; k < p.ht.nkeys; k++)
+		{
+			if (p.onulls[k] && p.onulls[k][row])
+				isnull = true;
+			key[k] = cb_load_widen(p.okey[k], p.otype[k], row);
+			h = pg_hash_combine(h, pg_hash_datum(p.otype[k], key[k], p.odict[k]), false);
+		}
+		if (!isnull)
+		{
+			uint32_t	pos = h & p.ht.mask;
+
+			for (;;)
+			{
+				unsigned long long e = p.ht.slots[pos];
+
+				if (e == HT_EMPTY)
+					break;
+				if ((uint32_t) (e >> 32) == h)
+				{
+					uint32_t	irow = (uint32_t) e;
+					bool		eq = true;
+
+					for (int k = 0; k < p.ht.nkeys; k++)
+						if (cb_load_widen(p.ht.keydata[k], p.ht.keytype[k], irow) != key[k])
+							eq = false;
+					if (eq)
+					{
+						if (WRITE)
+						{
+							p.out_outer[base + cnt] = row;
+							p.out_inner[base + cnt] = irow;
+						}
+						cnt++;
+					}
+				}
+				pos = (pos + 1) & p.ht.mask;
+			}
+		}
+		if (!WRITE)
+			p.counts[i] = cnt;
+	}
+}
+
+/* single-CTA chained exclusive scan (the pair-emitting probe is the general N:M fallback, not a
+ * hot kernel; correctness and determinism matter here, not speed) */
+__global__ void
+k_exclusive_scan_u64(unsigned long long *a, int64_t n)
+{
+	__shared__ unsigned long long carry;
+	__shared__ unsigned long long warp_tot[32];
+
+	if (threadIdx.x == 0)
+		carry = 0;
+	__syncthreads();
+	for (int64_t base = 0; base < n; base += blockDim.x)
+	{
+		int64_t		i = base + threadIdx.x;
+		unsigned long long v = i < n ? a[i] : 0;
+		unsigned long long x = v;
+		int			lane = threadIdx.x & 31,
+					w = threadIdx.x >> 5;
+
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+
+			if (lane >= o)
+				x += y;
+		}
+		if (lane == 31)
+			warp_tot[w] = x;
+		__syncthreads();
+		if (w == 0)
+		{
+			unsigned long long t = lane < (int) (blockDim.x >> 5) ? warp_tot[lane] : 0;
+
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				unsigned long long y = __shfl_up_sync(0xffffffffu, t, o);
+
+				if (lane >= o)
+					t += y;
+			}
+			warp_tot[lane] = t;
+		}
+		__syncthreads();
+		unsigned long long prev = (w ? warp_tot[w - 1] : 0) + carry;
+
+		if (i < n)
+			a[i] = prev + x - v;
+		__syncthreads();
+		if (threadIdx.x == blockDim.x - 1)
+			carry = prev + x;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+		a[n] = carry;
+}
+
+extern "C" int
+cbgpu_ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
+					 const uint32_t *sel, int64_t nsel, cbgpu_pairs *out)
+{
+	ProbeParams p;
+	int64_t		n = sel ? nsel : outer->nrows;
+	unsigned long long total = 0;
+
+	memset(out, 0, sizeof(*out));
+	if (nkeys != ht->d.nkeys)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_ht_probe_pairs: key count mismatch%s %lld", "", nkeys);
+	memset(&p, 0, sizeof(p));
+	p.ht = ht->d;
+	for (int k = 0; k < nkeys; k++)
+	{
+		int			c = keycols[k];
+
+		if (c < 0 || c >= outer->ncols)
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_ht_probe_pairs: bad key column%s %lld", "", c);
+		p.okey[k] = outer->data[c];
+		p.onulls[k] = outer->nulls[c];
+		p.odict[k] = outer->dict_hash[c];
+		p.otype[k] = outer->types[c];
+	}
+	p.sel = sel;
+	p.n = n;
+	if (n == 0)
+		return CBGPU_OK;
+	CB_CUDA(ctx, cudaMallocAsync(&p.counts, (size_t) (n + 1) * sizeof(unsigned long long), ctx->stream));
+	int			blocks = (int) ((n + 255) / 256);
+
+	if (blocks > ctx->sm_count * 8)
+		blocks = ctx->sm_count * 8;
+	k_ht_probe_pairs<false><<<blocks, 256, 0, ctx->stream>>>(p);
+	CB_LAUNCHED(ctx, "k_ht_probe_pairs<count>");
+	k_exclusive_scan_u64<<<1, 1024, 0, ctx->stream>>>(p.counts, n);
+	CB_LAUNCHED(ctx, "k_exclusive_scan_u64");
+	CB_CUDA(ctx, cudaMemcpyAsync(&total, p.counts + n, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (total > 0xFFFFFFF0ull)
+	{
+		cudaFreeAsync(p.counts, ctx->stream);
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "join result of %s%lld pairs exceeds the GPU path's 32-bit row ids", "", (long long) total);
+	}
+	out->npairs = (int64_t) total;
+	if (total)
+	{
+		CB_CUDA(ctx, cudaMalloc(&out->outer_idx, (size_t) total * sizeof(uint32_t)));
+		CB_CUDA(ctx, cudaMalloc(&out->inner_idx, (size_t) total * sizeof(uint32_t)));
+		p.out_outer = out->outer_idx;
+		p.out_inner = out->inner_idx;
+		k_ht_probe_pairs<true><<<blocks, 256, 0, ctx->stream>>>(p);
+		CB_LAUNCHED(ctx, "k_ht_probe_pairs<write>");
+	}
+	CB_CUDA(ctx, cudaFreeAsync(p.counts, ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" void
+cbgpu_pairs_free(cbgpu_pairs *p)
+{
+	if (!p)
+		return;
+	if (p->outer_idx)
+		cudaFree(p->outer_idx);
+	if (p->inner_idx)
+		cudaFree(p->inner_idx);
+	p->outer_idx = p->inner_idx = NULL;
+	p->npairs = 0;
+}

@@ -1,0 +1,588 @@
+/*
+ * pipeline.cu - cbgpu_pipeline_run: descriptor validation, dispatch, and the generic pipeline kernel.
+ *
+ * A pipeline is the GPU form of one slice-internal chain of the reference's pull executor between
+ * two pipeline breakers: the driving scan (aocs_getnext, backend/access/aocs/aocsam.c:1418), its
+ * quals (ExecScan -> ExecQual, backend/executor/execScan.c:162), zero or more hash-join probes
+ * (ExecHashJoinImpl HJ_NEED_NEW_OUTER / HJ_SCAN_BUCKET, backend/executor/nodeHashjoin.c:476,575)
+ * and one sink: hash aggregation (agg_fill_hash_table, backend/executor/nodeAgg.c:2726),
+ * materialisation for a Hash build side (MultiExecPrivateHash, nodeHash.c:167) or the sending half
+ * of a Redistribute Motion (execMotionSender + evalHashKey, backend/executor/nodeMotion.c:203,1088).
+ *
+ * The generic kernel interprets the descriptor's postfix program one row per thread, warp
+ * synchronously (all lanes step the same program counter; dead rows are masked), with late
+ * materialisation: a column is read only when an expression needs it, and only for rows still
+ * alive.  Pattern-specialised kernels (scan_agg.cu, ...) take over when the descriptor matches a
+ * shape they fuse by hand; results are identical (tests run both).
+ */
+#include "pipeline.cuh"
+
+#include <stdlib.h>
+
+/* ---------------------------------------------------------------------------------------------
+ * host: descriptor -> device form
+ * --------------------------------------------------------------------------------------------- */
+int
+cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
+{
+	memset(d, 0, sizeof(*d));
+	if (p->nrows < 0 || p->nrows > 0xFFFFFFF0ll)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "pipeline over %s%lld rows exceeds 32-bit row ids", "", p->nrows);
+	if (p->ncols < 0 || p->ncols > CBP_MAX_COLS || p->nops < 1 || p->nops > CBP_MAX_OPS ||
+		p->nprobes < 0 || p->nprobes > CBP_MAX_SRC - 1 || p->drv_nsrc < 0 || p->drv_nsrc > CBP_MAX_SRC)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "pipeline descriptor exceeds the GPU path's limits%s (%lld ops)", "", p->nops);
+	d->nrows = p->nrows;
+	d->visimap = p->visimap;
+	d->drv_nsrc = p->drv_nsrc;
+	for (int s = 0; s < CBP_MAX_SRC; s++)
+		d->drv_idx[s] = s < p->drv_nsrc ? p->drv_idx[s] : NULL;
+	d->ncols = p->ncols;
+	for (int c = 0; c < p->ncols; c++)
+	{
+		d->cols[c] = p->cols[c];
+		if (p->cols[c].src < 0 || p->cols[c].src >= CBP_MAX_SRC || cb_type_w(p->cols[c].type) == 0)
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline column %s%lld malformed", "", c);
+	}
+	d->nops = p->nops;
+	/* validate the program by simulating its stack depth */
+	int			depth = 0;
+
+	for (int i = 0; i < p->nops; i++)
+	{
+		const CbpOp *op = &p->ops[i];
+
+		d->ops[i] = *op;
+		switch (op->code)
+		{
+			case CBP_LOAD:
+				if (op->a < 0 || op->a >= p->ncols)
+					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld loads a missing column", "", i);
+				depth++;
+				break;
+			case CBP_CONST:
+				depth++;
+				break;
+			case CBP_DUP:
+				if (op->a < 0 || op->a >= depth)
+					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld: DUP out of range", "", i);
+				depth++;
+				break;
+			case CBP_ADD: case CBP_SUB: case CBP_MUL: case CBP_FADD: case CBP_FSUB: case CBP_FMUL:
+			case CBP_EQ: case CBP_NE: case CBP_LT: case CBP_LE: case CBP_GT: case CBP_GE:
+			case CBP_FEQ: case CBP_FNE: case CBP_FLT: case CBP_FLE: case CBP_FGT: case CBP_FGE:
+			case CBP_AND: case CBP_OR:
+				if (depth < 2)
+					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld underflows the stack", "", i);
+				depth--;
+				break;
+			case CBP_NOT: case CBP_I2F:
+				if (depth < 1)
+					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld underflows the stack", "", i);
+				break;
+			case CBP_FILTER: case CBP_POP:
+				if (depth < 1)
+					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld underflows the stack", "", i);
+				depth--;
+				break;
+			case CBP_PROBE:
+				if (op->a < 0 || op->a >= p->nprobes || depth < p->probes[op->a].nkeys)
+					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld: bad PROBE", "", i);
+				depth -= p->probes[op->a].nkeys;
+				break;
+			case CBP_END:
+				if (i != p->nops - 1)
+					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld: END before the last op", "", i);
+				break;
+			default:
+				return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld: unknown opcode", "", i);
+		}
+		if (depth > CBP_STACK)
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "pipeline expression stack deeper than %s%lld", "", CBP_STACK);
+	}
+	if (p->ops[p->nops - 1].code != CBP_END)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline program does not end with END%s", "", 0);
+	d->nprobes = p->nprobes;
+	d->src_base = p->drv_nsrc > 1 ? p->drv_nsrc : 1;
+	if (d->src_base + p->nprobes > CBP_MAX_SRC)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "pipeline joins more than %s%lld sources", "", CBP_MAX_SRC);
+	for (int j = 0; j < p->nprobes; j++)
+	{
+		const CbpProbe *pp = &p->probes[j];
+
+		if (!pp->ht || pp->nkeys != pp->ht->d.nkeys)
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline probe %s%lld: hash table / key count mismatch", "", j);
+		if (pp->jointype != CB_JOIN_INNER && pp->jointype != CB_JOIN_LEFT && pp->jointype != CB_JOIN_SEMI && pp->jointype != CB_JOIN_ANTI)
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "join type %s%lld is not implemented on the GPU path", "", pp->jointype);
+		if (pp->ht->has_dups && (pp->jointype == CB_JOIN_INNER || pp->jointype == CB_JOIN_LEFT))
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "fused probe %s%lld needs unique build keys; use cbgpu_ht_probe_pairs", "", j);
+		d->probes[j].ht = pp->ht->d;
+		d->probes[j].jointype = pp->jointype;
+		d->probes[j].nkeys = pp->nkeys;
+		for (int k = 0; k < pp->nkeys; k++)
+		{
+			d->probes[j].keytype[k] = pp->keytype[k];
+			d->probes[j].keydict[k] = pp->key_dict_hash[k];
+		}
+	}
+	const CbpSink *s = &p->sink;
+	DSink	   *ds = &d->sink;
+
+	ds->kind = s->kind;
+	switch (s->kind)
+	{
+		case CBP_SINK_AGG:
+			if (!s->agg || s->nkeys != s->agg->d.nkeys || s->naccs != s->agg->d.naccs)
+				return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: agg table shape mismatch%s", "", 0);
+			ds->agg = s->agg->d;
+			ds->nkeys = s->nkeys;
+			ds->naccs = s->naccs;
+			for (int k = 0; k < s->nkeys; k++)
+			{
+				ds->keytype[k] = s->keytype[k];
+				ds->keydict[k] = s->key_dict_hash[k];
+				if (s->keytype[k] == CB_NUMERIC)
+					return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "numeric GROUP BY keys (hash_numeric) are not on the GPU path%s", "", 0);
+			}
+			{
+				int			nargs = depth - s->nkeys;
+
+				for (int a = 0; a < s->naccs; a++)
+				{
+					int			need = s->accs[a].kind == CBP_ACC_MERGE_INT ? 3 : (s->accs[a].kind == CBP_ACC_MERGE_FLOAT || s->accs[a].kind == CBP_ACC_MERGE_MIN || s->accs[a].kind == CBP_ACC_MERGE_MAX) ? 2 : 1;
+
+					ds->accs[a] = s->accs[a];
+					if (s->accs[a].arg >= 0 && s->accs[a].arg + need > nargs)
+						return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: accumulator %s%lld argument beyond the stack", "", a);
+					if (s->accs[a].arg < 0 && s->accs[a].kind != CBP_ACC_COUNT)
+						return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: accumulator %s%lld needs an argument", "", a);
+				}
+				if (nargs < 0)
+					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: fewer stack values than keys%s", "", 0);
+			}
+			break;
+		case CBP_SINK_MATERIALIZE:
+		case CBP_SINK_PARTITION:
+			if (!s->out || s->nout != depth || s->nout > CBP_MAX_OUT || s->nout > s->out->ncols || !s->out_count)
+				return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: output shape mismatch%s (%lld values)", "", depth);
+			ds->nout = s->nout;
+			for (int c = 0; c < s->nout; c++)
+			{
+				ds->outcol[c] = s->out->data[c];
+				ds->outnull[c] = s->out->nulls[c];
+				ds->outtype[c] = s->out->types[c];
+			}
+			ds->out_count = (unsigned long long *) s->out_count;
+			ds->out_capacity = s->out->capacity;
+			if (s->kind == CBP_SINK_PARTITION)
+			{
+				if (s->nsegs < 1 || s->nhash < 1 || s->nhash > CBP_MAX_KEYS || s->nhash > s->nout ||
+					s->seg_capacity * s->nsegs > s->out->capacity)
+					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: bad partition description%s", "", 0);
+				ds->nhash = s->nhash;
+				ds->nsegs = s->nsegs;
+				ds->seg_capacity = s->seg_capacity;
+				for (int k = 0; k < s->nhash; k++)
+				{
+					ds->hashtype[k] = s->hashtype[k];
+					ds->hashdict[k] = s->hash_dict_hash[k];
+				}
+			}
+			break;
+		default:
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink kind %s%lld unknown", "", s->kind);
+	}
+	d->status = ctx->d_status;
+	return CBGPU_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * generic kernel
+ * --------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ int
+fcmp_pg(double x, double y)
+{
+	/* float8_cmp_internal (include/utils/float.h): NaN equals NaN and sorts above everything */
+	if (x != x)
+		return (y != y) ? 0 : 1;
+	if (y != y)
+		return -1;
+	return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(256)
+k_pipeline_generic(const __grid_constant__ PipeDev P)
+{
+	const int64_t nwarp_rows = (P.nrows + 31) & ~31ll;
+	int64_t		base = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x);
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	const int	lane = threadIdx.x & 31;
+
+	for (; base < nwarp_rows; base += stride)
+	{
+		bool		alive = base < P.nrows;
+		uint32_t	ridx[CBP_MAX_SRC];
+		uint32_t	rnull = 0;		/* bit s: source s is NULL-extended (left join miss)              */
+		int64_t		st[CBP_STACK];
+		uint32_t	snull = 0;
+		int			sp = 0;
+
+#pragma unroll
+		for (int s = 0; s < CBP_MAX_SRC; s++)
+			ridx[s] = 0;
+		if (alive)
+		{
+			if (P.drv_nsrc == 0)
+				ridx[0] = (uint32_t) base;
+			else
+				for (int s = 0; s < P.drv_nsrc; s++)
+					ridx[s] = P.drv_idx[s] ? P.drv_idx[s][base] : (uint32_t) base;
+			/* AppendOnlyVisimap_IsVisible (backend/access/appendonly/appendonly_visimap.c:198) */
+			if (P.visimap && !((P.visimap[ridx[0] >> 3] >> (ridx[0] & 7)) & 1))
+				alive = false;
+		}
+		for (int pc = 0; pc < P.nops; pc++)
+		{
+			if (!__any_sync(0xffffffffu, alive))
+				break;
+			const int	code = P.ops[pc].code;
+			const int	a = P.ops[pc].a;
+
+			if (code == CBP_END)
+				break;
+			if (code == CBP_PROBE)
+			{
+				const DProbe &pr = P.probes[a];
+				uint32_t	h = 0;
+				bool		knull = false;
+				int64_t		key[CBP_MAX_KEYS];
+				bool		found = false;
+				uint32_t	irow = 0;
+
+				sp -= pr.nkeys;
+				for (int k = 0; k < pr.nkeys; k++)
+				{
+					key[k] = st[sp + k];
+					if ((snull >> (sp + k)) & 1)
+						knull = true;
+					h = pg_hash_combine(h, pg_hash_datum(pr.keytype[k], key[k], pr.keydict[k]), false);
+				}
+				snull &= (1u << sp) - 1;
+				if (alive && !knull)
+				{
+					uint32_t	pos = h & pr.ht.mask;
+
+					for (;;)
+					{
+						unsigned long long e = pr.ht.slots[pos];
+
+						if (e == HT_EMPTY)
+							break;
+						if ((uint32_t) (e >> 32) == h)
+						{
+							bool		eq = true;
+
+							irow = (uint32_t) e;
+							for (int k = 0; k < pr.nkeys; k++)
+								if (cb_load_widen(pr.ht.keydata[k], pr.ht.keytype[k], irow) != key[k])
+									eq = false;
+							if (eq)
+							{
+								found = true;
+								break;
+							}
+						}
+						pos = (pos + 1) & pr.ht.mask;
+					}
+				}
+				/* join-type handling of the probe states (nodeHashjoin.c:583-713) */
+				switch (pr.jointype)
+				{
+					case CB_JOIN_INNER:
+					case CB_JOIN_SEMI:
+						if (!found)
+							alive = false;
+						break;
+					case CB_JOIN_ANTI:
+						if (found)
+							alive = false;
+						break;
+					case CB_JOIN_LEFT:
+						if (!found)
+							rnull |= 1u << (P.src_base + a);
+						break;
+				}
+				ridx[P.src_base + a] = irow;
+				continue;
+			}
+			switch (code)
+			{
+				case CBP_LOAD:
+					{
+						const CbpColumn &c = P.cols[a];
+						bool		isnull = (rnull >> c.src) & 1;
+						int64_t		v = 0;
+
+						if (alive && !isnull)
+						{
+							uint32_t	r = ridx[c.src];
+
+							if (c.nulls && c.nulls[r])
+								isnull = true;
+							else
+								v = cb_load_widen(c.data, c.type, r);
+						}
+						st[sp] = v;
+						snull = isnull ? (snull | (1u << sp)) : (snull & ~(1u << sp));
+						sp++;
+						break;
+					}
+				case CBP_CONST:
+					st[sp] = P.ops[pc].imm;
+					snull &= ~(1u << sp);
+					sp++;
+					break;
+				case CBP_DUP:
+					st[sp] = st[a];
+					snull = ((snull >> a) & 1) ? (snull | (1u << sp)) : (snull & ~(1u << sp));
+					sp++;
+					break;
+				case CBP_POP:
+					sp--;
+					break;
+				case CBP_ADD: case CBP_SUB: case CBP_MUL:
+					{
+						int64_t		y = st[sp - 1],
+									x = st[sp - 2];
+						bool		n = ((snull >> (sp - 1)) | (snull >> (sp - 2))) & 1;
+						int64_t		r;
+						bool		ovf;
+
+						/* int8pl / int8mi / int8mul report "bigint out of range" (utils/adt/int8.c);
+						 * scaled numerics share the check: a product that leaves 64 bits is refused,
+						 * never wrapped */
+						if (code == CBP_ADD)
+						{
+							r = (int64_t) ((uint64_t) x + (uint64_t) y);
+							ovf = ((x ^ r) & (y ^ r)) < 0;
+						}
+						else if (code == CBP_SUB)
+						{
+							r = (int64_t) ((uint64_t) x - (uint64_t) y);
+							ovf = ((x ^ y) & (x ^ r)) < 0;
+						}
+						else
+						{
+							r = (int64_t) ((uint64_t) x * (uint64_t) y);
+							ovf = __mul64hi(x, y) != (r >> 63);
+						}
+						if (alive && !n && ovf)
+							atomicExch(P.status, CBGPU_ERR_OVERFLOW);
+						sp--;
+						st[sp - 1] = r;
+						snull = n ? (snull | (1u << (sp - 1))) : (snull & ~(1u << (sp - 1)));
+						break;
+					}
+				case CBP_FADD: case CBP_FSUB: case CBP_FMUL:
+					{
+						double		y = __longlong_as_double(st[sp - 1]),
+									x = __longlong_as_double(st[sp - 2]);
+						bool		n = ((snull >> (sp - 1)) | (snull >> (sp - 2))) & 1;
+						double		r = code == CBP_FADD ? __dadd_rn(x, y) : code == CBP_FSUB ? __dsub_rn(x, y) : __dmul_rn(x, y);
+
+						sp--;
+						st[sp - 1] = __double_as_longlong(r);
+						snull = n ? (snull | (1u << (sp - 1))) : (snull & ~(1u << (sp - 1)));
+						break;
+					}
+				case CBP_I2F:
+					{
+						double		scale = 1.0;
+
+						for (int k = 0; k < a; k++)
+							scale *= 10.0;
+						st[sp - 1] = __double_as_longlong(__ddiv_rn((double) st[sp - 1], scale));
+						break;
+					}
+				case CBP_EQ: case CBP_NE: case CBP_LT: case CBP_LE: case CBP_GT: case CBP_GE:
+				case CBP_FEQ: case CBP_FNE: case CBP_FLT: case CBP_FLE: case CBP_FGT: case CBP_FGE:
+					{
+						int64_t		y = st[sp - 1],
+									x = st[sp - 2];
+						bool		n = ((snull >> (sp - 1)) | (snull >> (sp - 2))) & 1;
+						int			c;
+						bool		r;
+
+						if (code >= CBP_FEQ)
+							c = fcmp_pg(__longlong_as_double(x), __longlong_as_double(y));
+						else
+							c = x < y ? -1 : (x > y ? 1 : 0);
+						switch (code)
+						{
+							case CBP_EQ: case CBP_FEQ: r = c == 0; break;
+							case CBP_NE: case CBP_FNE: r = c != 0; break;
+							case CBP_LT: case CBP_FLT: r = c < 0; break;
+							case CBP_LE: case CBP_FLE: r = c <= 0; break;
+							case CBP_GT: case CBP_FGT: r = c > 0; break;
+							default: r = c >= 0; break;
+						}
+						sp--;
+						st[sp - 1] = r;
+						snull = n ? (snull | (1u << (sp - 1))) : (snull & ~(1u << (sp - 1)));
+						break;
+					}
+				case CBP_AND: case CBP_OR:
+					{
+						/* three-valued logic of ExecEvalBoolAnd/OrStep (execExprInterp.c) */
+						bool		yn = (snull >> (sp - 1)) & 1,
+									xn = (snull >> (sp - 2)) & 1;
+						bool		y = st[sp - 1] != 0,
+									x = st[sp - 2] != 0;
+						bool		r,
+									n;
+
+						if (code == CBP_AND)
+						{
+							bool		anyfalse = (!xn && !x) || (!yn && !y);
+
+							r = !anyfalse;
+							n = !anyfalse && (xn || yn);
+						}
+						else
+						{
+							bool		anytrue = (!xn && x) || (!yn && y);
+
+							r = anytrue;
+							n = !anytrue && (xn || yn);
+						}
+						sp--;
+						st[sp - 1] = r;
+						snull = n ? (snull | (1u << (sp - 1))) : (snull & ~(1u << (sp - 1)));
+						break;
+					}
+				case CBP_NOT:
+					st[sp - 1] = !st[sp - 1];
+					break;
+				case CBP_FILTER:
+					sp--;
+					/* ExecQual: NULL counts as false */
+					if (((snull >> sp) & 1) || !st[sp])
+						alive = false;
+					snull &= ~(1u << sp);
+					break;
+			}
+		}
+		/* ---- sink ---- */
+		const DSink &S = P.sink;
+
+		if (S.kind == CBP_SINK_AGG)
+		{
+			if (alive)
+			{
+				/* TupleHashTableHash_internal (executor/execGrouping.c:437-495): hash_iv 0,
+				 * rotate-xor per key (NULL -> 0), then murmurhash32 */
+				uint32_t	h = 0;
+				uint32_t	knull = snull & ((1u << S.nkeys) - 1);
+
+				for (int k = 0; k < S.nkeys; k++)
+				{
+					bool		isn = (knull >> k) & 1;
+
+					if (isn)
+						st[k] = 0;
+					h = pg_hash_combine(h, isn ? 0u : pg_hash_datum(S.keytype[k], st[k], S.keydict[k]), isn);
+				}
+				h = pg_murmurhash32(h);
+				int			slot = agg_find_or_insert(S.agg, h, st, knull);
+
+				if (slot >= 0)
+					for (int a = 0; a < S.naccs; a++)
+						sink_acc_update(S.agg, slot, a, S.accs[a], st + S.nkeys, snull >> S.nkeys);
+			}
+		}
+		else
+		{
+			/* one output position per surviving row; positions handed out per warp and per
+			 * destination so the counters see one atomic per (warp, destination) */
+			int			seg = 0;
+
+			if (S.kind == CBP_SINK_PARTITION && alive)
+			{
+				/* cdbhashinit / cdbhash / cdbhashreduce (cdb/cdbhash.c:171,189,253) */
+				uint32_t	h = 0;
+
+				for (int k = 0; k < S.nhash; k++)
+				{
+					bool		isn = (snull >> k) & 1;
+
+					h = pg_hash_combine(h, isn ? 0u : pg_hash_datum(S.hashtype[k], st[k], S.hashdict[k]), isn);
+				}
+				seg = pg_jump_consistent_hash(h, S.nsegs);
+			}
+			uint32_t	amask = __ballot_sync(0xffffffffu, alive);
+
+			if (alive)
+			{
+				uint32_t	peers = __match_any_sync(amask, seg);
+				int			leader = __ffs(peers) - 1;
+				unsigned long long pos = 0;
+
+				if (lane == leader)
+					pos = atomicAdd(S.out_count + seg, (unsigned long long) __popc(peers));
+				pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1));
+				int64_t		cap = S.kind == CBP_SINK_PARTITION ? S.seg_capacity : S.out_capacity;
+
+				if ((int64_t) pos >= cap)
+					atomicExch(P.status, CBGPU_ERR_NOMEM);
+				else
+				{
+					uint64_t	dst = (uint64_t) seg * (uint64_t) S.seg_capacity + pos;
+
+					for (int c = 0; c < S.nout; c++)
+					{
+						sink_store(S.outcol[c], S.outtype[c], dst, st[c]);
+						if (S.outnull[c])
+							S.outnull[c][dst] = (snull >> c) & 1;
+						else if ((snull >> c) & 1)
+							atomicExch(P.status, CBGPU_ERR_INVALID);
+					}
+				}
+			}
+		}
+	}
+}
+
+extern "C" int
+cbgpu_pipeline_run(cbgpu_ctx *ctx, const CbPipeline *p)
+{
+	static PipeDev d;			/* large: keep it off the stack (single-threaded callers, as a backend is) */
+	int			rc = cb_pipeline_to_dev(ctx, p, &d);
+	bool		handled = false;
+
+	if (rc)
+		return rc;
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	ctx->kernel_timed = false;
+	if (p->nrows == 0)
+		return CBGPU_OK;
+	if (!p->force_generic)
+	{
+		rc = cb_try_specialised(ctx, p, &d, &handled);
+		if (rc)
+			return rc;
+	}
+	if (!handled)
+	{
+		int64_t		warps = (p->nrows + 31) / 32;
+		int64_t		blocks = (warps + 7) / 8;
+
+		if (blocks > (int64_t) ctx->sm_count * 8)
+			blocks = (int64_t) ctx->sm_count * 8;
+		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
+		k_pipeline_generic<<<(int) blocks, 256, 0, ctx->stream>>>(d);
+		CB_LAUNCHED(ctx, "k_pipeline_generic");
+		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
+		ctx->kernel_timed = true;
+		ctx->last_kernel_name = "k_pipeline_generic";
+	}
+	return CBGPU_OK;
+}

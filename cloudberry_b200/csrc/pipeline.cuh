@@ -1,0 +1,147 @@
+/*
+ * pipeline.cuh - device-side form of a pipeline descriptor and the sink primitives shared by the
+ * generic and the pattern-specialised pipeline kernels.
+ */
+#pragma once
+#include "common.cuh"
+
+struct DProbe
+{
+	HtDev		ht;
+	int32_t		jointype;
+	int32_t		nkeys;
+	int32_t		keytype[CBP_MAX_KEYS];
+	const uint32_t *keydict[CBP_MAX_KEYS];
+};
+
+struct DSink
+{
+	int32_t		kind;
+	AggDev		agg;
+	int32_t		nkeys;
+	int32_t		keytype[CBP_MAX_KEYS];
+	const uint32_t *keydict[CBP_MAX_KEYS];
+	int32_t		naccs;
+	CbpAcc		accs[CBP_MAX_AGGS];
+	int32_t		nout;
+	void	   *outcol[CBP_MAX_OUT];
+	uint8_t    *outnull[CBP_MAX_OUT];
+	int32_t		outtype[CBP_MAX_OUT];
+	unsigned long long *out_count;
+	int64_t		out_capacity;
+	int32_t		nhash;
+	int32_t		hashtype[CBP_MAX_KEYS];
+	const uint32_t *hashdict[CBP_MAX_KEYS];
+	int32_t		nsegs;
+	int64_t		seg_capacity;
+};
+
+struct PipeDev
+{
+	int64_t		nrows;
+	const uint8_t *visimap;
+	int32_t		drv_nsrc;
+	const uint32_t *drv_idx[CBP_MAX_SRC];
+	int32_t		ncols;
+	CbpColumn	cols[CBP_MAX_COLS];
+	int32_t		nops;
+	CbpOp		ops[CBP_MAX_OPS];
+	int32_t		nprobes;
+	int32_t		src_base;		/* probe j's inner rows are source src_base + j                      */
+	DProbe		probes[CBP_MAX_SRC - 1];
+	DSink		sink;
+	int		   *status;
+};
+
+/* one accumulator update of advance_aggregates (backend/executor/nodeAgg.c:856).  `args` are the
+ * stack values after the keys; argnull their NULL bits. */
+__device__ __forceinline__ void
+sink_acc_update(const AggDev &t, int slot, int a, const CbpAcc &acc, const int64_t *args, uint32_t argnull)
+{
+	int64_t    *np = t.n + (size_t) slot * t.naccs + a;
+	unsigned long long *sp = t.sum + ((size_t) slot * t.naccs + a) * 2;
+
+	switch (acc.kind)
+	{
+		case CBP_ACC_COUNT:		/* int8inc / int8inc_any (utils/adt/int8.c:805) */
+			if (acc.arg < 0 || !((argnull >> acc.arg) & 1))
+				atomicAdd((unsigned long long *) np, 1ull);
+			break;
+		case CBP_ACC_SUM_INT:	/* int4_sum / int8_avg_accum / numeric_avg_accum: N += 1, sumX += v */
+			if (!((argnull >> acc.arg) & 1))
+			{
+				atomicAdd((unsigned long long *) np, 1ull);
+				atomic_add128_signed(sp, args[acc.arg]);
+			}
+			break;
+		case CBP_ACC_SUM_FLOAT:	/* float8pl / float8_accum Sx (tree order here: tolerance, not bit-exact) */
+			if (!((argnull >> acc.arg) & 1))
+			{
+				atomicAdd((unsigned long long *) np, 1ull);
+				atomicAdd((double *) sp, __longlong_as_double(args[acc.arg]));
+			}
+			break;
+		case CBP_ACC_MIN:
+			if (!((argnull >> acc.arg) & 1))
+			{
+				atomicAdd((unsigned long long *) np, 1ull);
+				atomicMin((long long *) sp, (long long) args[acc.arg]);
+			}
+			break;
+		case CBP_ACC_MAX:
+			if (!((argnull >> acc.arg) & 1))
+			{
+				atomicAdd((unsigned long long *) np, 1ull);
+				atomicMax((long long *) sp, (long long) args[acc.arg]);
+			}
+			break;
+		case CBP_ACC_MERGE_COUNT:	/* int8pl over partial counts */
+			if (!((argnull >> acc.arg) & 1))
+				atomicAdd((unsigned long long *) np, (unsigned long long) args[acc.arg]);
+			break;
+		case CBP_ACC_MERGE_INT:	/* int8_avg_combine / numeric_avg_combine (numeric.c:5726, 4946) */
+			if (!((argnull >> acc.arg) & 1))
+			{
+				atomicAdd((unsigned long long *) np, (unsigned long long) args[acc.arg]);
+				atomic_add128(sp, (unsigned long long) args[acc.arg + 1], (unsigned long long) args[acc.arg + 2]);
+			}
+			break;
+		case CBP_ACC_MERGE_MIN:
+		case CBP_ACC_MERGE_MAX:
+			if (!((argnull >> acc.arg) & 1) && args[acc.arg] > 0)
+			{
+				atomicAdd((unsigned long long *) np, (unsigned long long) args[acc.arg]);
+				if (acc.kind == CBP_ACC_MERGE_MIN)
+					atomicMin((long long *) sp, (long long) args[acc.arg + 1]);
+				else
+					atomicMax((long long *) sp, (long long) args[acc.arg + 1]);
+			}
+			break;
+		case CBP_ACC_MERGE_FLOAT:	/* float8_combine (float.c:2886): N and Sx add */
+			if (!((argnull >> acc.arg) & 1))
+			{
+				atomicAdd((unsigned long long *) np, (unsigned long long) args[acc.arg]);
+				atomicAdd((double *) sp, __longlong_as_double(args[acc.arg + 1]));
+			}
+			break;
+	}
+}
+
+__device__ __forceinline__ void
+sink_store(void *col, int type, uint64_t pos, int64_t v)
+{
+	switch (type)
+	{
+		case CB_INT4: case CB_DATE: case CB_DICT32:
+			((int32_t *) col)[pos] = (int32_t) v;
+			break;
+		case CB_INT8: case CB_NUMERIC: case CB_FLOAT8:
+			((int64_t *) col)[pos] = v;
+			break;
+		default:
+			((uint8_t *) col)[pos] = (uint8_t) v;
+	}
+}
+
+int			cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d);
+int			cb_try_specialised(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handled);

@@ -1,0 +1,178 @@
+/*
+ * cb_exec.h - the host executor: the reference's PlanState / ExecProcNode operator API for the
+ * scan -> hash join -> hash aggregate (+ Motion) path, in plain C over the CUDA C ABI (cbgpu.h).
+ *
+ * Names, argument meaning and life cycle follow the reference (paths under /root/reference/src):
+ *
+ *   cb_ExecInitNode      ExecInitNode            backend/executor/execProcnode.c:190
+ *   cb_ExecProcNode      ExecProcNode            include/executor/executor.h (-> ps->ExecProcNode,
+ *                                                typedef ExecProcNodeMtd include/nodes/execnodes.h:1056)
+ *   cb_MultiExecProcNode MultiExecProcNode       backend/executor/execProcnode.c:718 (Hash build)
+ *   cb_ExecEndNode       ExecEndNode             backend/executor/execProcnode.c:791
+ *   cb_ExecReScan        ExecReScan              backend/executor/execAmi.c
+ *   cb_ExecSquelchNode   ExecSquelchNode         backend/executor/execAmi.c:763
+ *   CbPlanState          PlanState               include/nodes/execnodes.h:1065-1164
+ *   CbTupleTableSlot     TupleTableSlot (virtual) include/executor/tuptable.h:115-132
+ *   CbEState             EState                  include/nodes/execnodes.h
+ *   CbInterconnect       MotionIPCLayer          include/cdb/ml_ipc.h:36-210
+ *
+ * Contract kept: ExecProcNode returns one tuple per call in the node's result slot and NULL (or an
+ * empty slot) at end of data; a parent pulls its children through the same entry point.  Inside,
+ * operators exchange device column batches and whole sub-trees (scan + joins + aggregate) are
+ * fused into one kernel, so only post-aggregation rows are ever materialised one by one.
+ *
+ * Errors: the reference ereport(ERROR)s, i.e. siglongjmp (utils/elog.h:185).  Here every entry
+ * point records (code, message) in the EState and returns NULL / a negative code; a backend shim
+ * calls ereport after cb_ExecEndNode has released device memory.  If es_error_hook is set it is
+ * called with the same (code, message) at the point of failure.
+ */
+#ifndef CB_EXEC_H
+#define CB_EXEC_H
+
+#include "cbgpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct CbPlanState;
+struct CbEState;
+struct CbInterconnect;
+
+/* a numeric result Datum (by reference, like the reference's Numeric varlena) */
+typedef struct CbNumericDatum
+{
+	int64_t		lo, hi;			/* unscaled 128-bit value (two's complement) when it fits           */
+	int32_t		dscale;
+	char		text[84];		/* exact decimal text, as numeric_out() prints it                   */
+} CbNumericDatum;
+
+typedef struct CbTupleTableSlot
+{
+	bool		tts_empty;		/* TTS_FLAG_EMPTY                                                    */
+	int32_t		tts_nvalid;
+	int32_t	   *tts_types;		/* CbTypeId per attribute                                            */
+	int64_t    *tts_values;		/* Datum: by value (ints, date, codes, float8 bits) or a pointer
+								 * to a CbNumericDatum for CB_NUMERIC / CB_NUMERIC128                */
+	bool	   *tts_isnull;
+	/* partial aggregate states (AGGSPLIT_INITIAL_SERIAL outputs): N and the 128-bit sum per column */
+	int64_t    *tts_state_n;
+	int64_t    *tts_state_lo;
+	int64_t    *tts_state_hi;
+} CbTupleTableSlot;
+
+typedef CbTupleTableSlot *(*CbExecProcNodeMtd) (struct CbPlanState *pstate);
+
+typedef struct CbInstrumentation
+{
+	double		ntuples;		/* tuples emitted through ExecProcNode                               */
+	double		nloops;
+	int64_t		kernels;		/* device kernels launched on behalf of this node                    */
+	double		device_ms;		/* CUDA-event time of this node's pipelines                          */
+	int64_t		rows_in;		/* rows of the driving relation(s) this node's pipelines scanned     */
+} CbInstrumentation;
+
+typedef struct CbPlanState
+{
+	CbNodeTag	type;
+	CbPlan	   *plan;
+	struct CbEState *state;
+	CbExecProcNodeMtd ExecProcNode;
+	CbInstrumentation instrument;
+	struct CbPlanState *lefttree;
+	struct CbPlanState *righttree;
+	CbTupleTableSlot *ps_ResultTupleSlot;
+	bool		squelched;
+	void	   *priv;			/* node-private state                                                */
+} CbPlanState;
+
+typedef void (*CbErrorHook) (struct CbEState *estate, int code, const char *message);
+
+typedef struct CbEState
+{
+	cbgpu_ctx  *es_ctx;
+	int32_t		es_nrels;
+	cbgpu_rel **es_range_table;	/* scanrelid - 1 -> relation                                         */
+	int32_t		es_segindex;	/* GpIdentity.segindex                                               */
+	int32_t		es_numsegments;
+	struct CbInterconnect *es_interconnect;	/* NULL when es_numsegments == 1                         */
+	int32_t		es_errcode;
+	char		es_errmsg[512];
+	CbErrorHook es_error_hook;
+	int32_t		es_force_generic;	/* tests: never use the pattern-specialised kernels              */
+	int64_t		es_processed;
+	void	   *es_cluster;		/* in-process multi-segment runs: the owning CbCluster               */
+} CbEState;
+
+CbEState   *cb_CreateExecutorState(cbgpu_ctx *ctx, cbgpu_rel **range_table, int32_t nrels);
+void		cb_FreeExecutorState(CbEState *estate);
+const char *cb_estate_error(CbEState *estate);
+
+CbPlanState *cb_ExecInitNode(CbPlan *node, CbEState *estate, int eflags);
+CbTupleTableSlot *cb_ExecProcNode(CbPlanState *node);
+/* Hash nodes only: runs the build (MultiExecHash, nodeHash.c:130); returns the hash table */
+cbgpu_hashtable *cb_MultiExecProcNode(CbPlanState *node);
+void		cb_ExecEndNode(CbPlanState *node);
+void		cb_ExecReScan(CbPlanState *node);
+void		cb_ExecSquelchNode(CbPlanState *node);
+
+/* slot accessors (slot_getattr, executor/tuptable.h) */
+#define CbTupIsNull(slot) ((slot) == NULL || (slot)->tts_empty)
+int			cb_slot_natts(const CbTupleTableSlot *slot);
+int			cb_slot_isnull(const CbTupleTableSlot *slot, int attno);
+int64_t		cb_slot_int64(const CbTupleTableSlot *slot, int attno);
+double		cb_slot_float8(const CbTupleTableSlot *slot, int attno);
+/* value as text the way the reference prints it (numeric_out, int8out, float8out %.17g) */
+int			cb_slot_text(const CbTupleTableSlot *slot, int attno, char *buf, int buflen);
+
+/* numeric finalisation helpers (numeric_sum / numeric_avg, utils/adt/numeric.c:6091,6056 with
+ * select_div_scale :9194): exact text from (sum, dscale[, N]) */
+void		cb_numeric_sum_text(int64_t lo, int64_t hi, int32_t dscale, char *out, int32_t outlen);
+void		cb_numeric_avg_text(int64_t lo, int64_t hi, int32_t dscale, int64_t n, char *out, int32_t outlen);
+
+/* ------------------------------------------------------------------------------------------
+ * interconnect: what the reference reaches through MotionIPCLayer (include/cdb/ml_ipc.h:36)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct CbInterconnect
+{
+	const char *name;
+	int32_t		nsegs;
+	int32_t		segindex;
+	/* Redistribute: `send` holds this segment's rows grouped by destination (destination d's rows
+	 * start at d * seg_capacity, counts[d] of them).  Returns the rows addressed to this segment. */
+	int			(*redistribute) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id,
+								 cbgpu_rel *send, const int64_t *counts, int64_t seg_capacity, cbgpu_rel **recv);
+	/* Gather: every segment's rows to segment `root`; other segments get an empty relation */
+	int			(*gather) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id, int32_t root,
+						   cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
+	/* Broadcast: every segment receives every segment's rows */
+	int			(*broadcast) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id,
+							  cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
+	void		(*teardown) (struct CbInterconnect *ic);
+	void	   *priv;
+} CbInterconnect;
+
+/*
+ * In-process cluster: N segment executors over one context (the reference tests "multi-node" the
+ * same way: gpdemo runs every segment on one host, gpAux/gpdemo/demo_cluster.sh).  Each segment has
+ * its own range table; Motion nodes exchange device batches through the local interconnect.
+ */
+typedef struct CbCluster CbCluster;
+CbCluster  *cb_cluster_create(cbgpu_ctx *ctx, int32_t nsegs);
+/* range table of one segment (pointers are borrowed) */
+int			cb_cluster_set_range_table(CbCluster *c, int32_t seg, cbgpu_rel **range_table, int32_t nrels);
+CbEState   *cb_cluster_estate(CbCluster *c, int32_t seg);
+/* ExecInitNode on every segment; returns the root PlanState of segment 0's copy */
+int			cb_cluster_init_plan(CbCluster *c, CbPlan *plan);
+/* pull the next tuple of the whole query: the top slice of each segment in turn (a slice that
+ * receives from a Gather Motion runs on segment 0 only) */
+CbTupleTableSlot *cb_cluster_next(CbCluster *c);
+int32_t		cb_cluster_current_segment(CbCluster *c);
+void		cb_cluster_end(CbCluster *c);
+void		cb_cluster_destroy(CbCluster *c);
+const char *cb_cluster_error(CbCluster *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif							/* CB_EXEC_H */

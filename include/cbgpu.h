@@ -1,0 +1,315 @@
+/*
+ * cbgpu.h - thin C ABI over the sm_100a CUDA kernels (libcbgpu.so).
+ *
+ * Plain C: pointers, sizes and POD structs only; no CUDA or torch types cross this boundary.
+ * The host executor (include/cb_exec.h, cloudberry_b200/csrc/exec/ *.c, plain C) is the only
+ * caller on the product path; a Cloudberry backend shim would bind the same entry points
+ * (INTEGRATION.md).  Every function returns CBGPU_OK or a negative error code and leaves a
+ * message in cbgpu_last_error(ctx); nothing longjmps or throws across the boundary
+ * (the reference reports errors with ereport(ERROR) = siglongjmp, utils/elog.h:185; the shim turns
+ * a status code into ereport only after the stream is drained and device memory released).
+ *
+ * What each group of entry points replaces in the reference (paths under /root/reference/src):
+ *
+ *   relations / columns   the decoded form of an AOCS scan: aocs_beginscan (backend/access/aocs/
+ *                         aocsam.c:549) chooses projected columns, datumstreamread_block + the
+ *                         block cursor (backend/utils/datumstream/datumstream.c:1364,
+ *                         include/utils/datumstreamblock.h:1220-1614) decode them.  Here a column
+ *                         is one HBM-resident fixed-width array.
+ *   cbgpu_pipeline_run    the per-row inner loops: aocs_getnext (aocsam.c:1418) + ExecScan qual /
+ *                         projection (backend/executor/execScan.c:162) + ExecHashJoin probe
+ *                         (backend/executor/nodeHashjoin.c:203, nodeHash.c:2089,2255) +
+ *                         agg_fill_hash_table / advance_aggregates (backend/executor/nodeAgg.c:2726,
+ *                         856) + execMotionSender's evalHashKey (backend/executor/nodeMotion.c:1088),
+ *                         fused into one late-materialising kernel per pipeline.
+ *   cbgpu_ht_*            MultiExecPrivateHash / ExecHashTableInsert (backend/executor/nodeHash.c:
+ *                         167,1877) and ExecScanHashBucket (:2255).
+ *   cbgpu_agg_*           TupleHashTable + per-group transition states (backend/executor/
+ *                         execGrouping.c:317, nodeAgg.c:2220-2319) and agg_retrieve_hash_table
+ *                         (nodeAgg.c:2952).
+ *   cbgpu_topn            Limit <- Sort above the Agg (bounded tuplesort), device side so ~1.2M
+ *                         Q3 groups are not drained through slots.
+ *   cbgpu_motion_*        cdbmotion SendTuple / RecvTupleFrom over a MotionIPCLayer
+ *                         (backend/cdb/motion/cdbmotion.c:425,549; include/cdb/ml_ipc.h:36-210),
+ *                         replaced by a hash-partition kernel + NCCL grouped send/recv.
+ */
+#ifndef CBGPU_H
+#define CBGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include "cb_plan.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBGPU_OK 0
+#define CBGPU_ERR_CUDA (-1)			/* a CUDA runtime / NCCL call failed                              */
+#define CBGPU_ERR_INVALID (-2)		/* bad argument / malformed descriptor                             */
+#define CBGPU_ERR_UNSUPPORTED (-3)	/* valid plan shape the GPU path does not implement: fail loudly,
+									 * there is no CPU fallback                                        */
+#define CBGPU_ERR_OVERFLOW (-4)		/* integer / numeric value out of range during execution           */
+#define CBGPU_ERR_NOMEM (-5)
+
+typedef struct cbgpu_ctx cbgpu_ctx;
+typedef struct cbgpu_rel cbgpu_rel;
+typedef struct cbgpu_hashtable cbgpu_hashtable;
+typedef struct cbgpu_aggtable cbgpu_aggtable;
+typedef struct cbgpu_motion cbgpu_motion;
+
+/* ------------------------------------------------------------------------------------------
+ * context
+ * ------------------------------------------------------------------------------------------ */
+int			cbgpu_ctx_create(int device, cbgpu_ctx **out);	/* lazily initialises CUDA: call after fork */
+void		cbgpu_ctx_destroy(cbgpu_ctx *ctx);
+const char *cbgpu_last_error(cbgpu_ctx *ctx);
+int			cbgpu_sync(cbgpu_ctx *ctx);						/* drain the context's stream              */
+/* drain the stream and report (then clear) an error a kernel raised: overflow, full table / buffer */
+int			cbgpu_check_status(cbgpu_ctx *ctx);
+int			cbgpu_device_count(void);
+int			cbgpu_sm_count(cbgpu_ctx *ctx);
+int64_t		cbgpu_kernel_launches(cbgpu_ctx *ctx);			/* kernels launched so far on this ctx     */
+/* device-side timing on the context's stream (CUDA events) */
+int			cbgpu_timer_start(cbgpu_ctx *ctx);
+int			cbgpu_timer_stop_ms(cbgpu_ctx *ctx, double *ms);
+/* last pipeline kernel's own duration (events around that launch only) and its name */
+double		cbgpu_last_kernel_ms(cbgpu_ctx *ctx);
+const char *cbgpu_last_kernel_name(cbgpu_ctx *ctx);
+/* write `bytes` of HBM so the next timed kernel starts with a cold L2 */
+int			cbgpu_flush_l2(cbgpu_ctx *ctx);
+/* pinned host memory for the end-to-end (host buffers) path */
+void	   *cbgpu_host_alloc(size_t bytes);
+void		cbgpu_host_free(void *p);
+
+/* hashbpchar (backend/utils/adt/varchar.c:981) on the host, for dictionary columns */
+uint32_t	cbgpu_hashbpchar(const char *s, int32_t len);
+
+/* ------------------------------------------------------------------------------------------
+ * relations: HBM-resident column batches
+ * ------------------------------------------------------------------------------------------ */
+int			cbgpu_rel_create(cbgpu_ctx *ctx, int64_t nrows, int32_t ncols, const int32_t *types,
+							 const int32_t *dscales, cbgpu_rel **out);
+void		cbgpu_rel_free(cbgpu_rel *rel);
+int64_t		cbgpu_rel_nrows(const cbgpu_rel *rel);
+int32_t		cbgpu_rel_ncols(const cbgpu_rel *rel);
+int32_t		cbgpu_rel_col_type(const cbgpu_rel *rel, int32_t col);
+int32_t		cbgpu_rel_col_dscale(const cbgpu_rel *rel, int32_t col);
+/* host -> device copy of one whole column (asynchronous on the context stream when `host` is
+ * pinned); nulls: NULL or one byte per row (1 = NULL) */
+int			cbgpu_rel_load_column(cbgpu_rel *rel, int32_t col, const void *host, const uint8_t *nulls);
+/* device -> host copy of rows [lo, hi) of a column (blocking) */
+int			cbgpu_rel_read_column(cbgpu_rel *rel, int32_t col, int64_t lo, int64_t hi, void *host, uint8_t *nulls);
+/* visibility bitmap, one bit per row, 1 = visible (appendonly_visimap.c:198); NULL clears it */
+int			cbgpu_rel_set_visimap(cbgpu_rel *rel, const uint8_t *bits);
+/* per-code hashbpchar values of a dictionary column (so it can be a hash key) */
+int			cbgpu_rel_set_dict_hash(cbgpu_rel *rel, int32_t col, const uint32_t *hashes, int32_t n);
+/* shrink the logical row count (relations allocated at an upper bound, e.g. Motion receive) */
+int			cbgpu_rel_set_nrows(cbgpu_rel *rel, int64_t nrows);
+/* raw device pointer of a column (for harness-side generators / NCCL); not dereferenceable on host */
+void	   *cbgpu_rel_col_devptr(cbgpu_rel *rel, int32_t col);
+size_t		cbgpu_rel_nbytes(const cbgpu_rel *rel);
+
+/* ------------------------------------------------------------------------------------------
+ * pipelines: driving source -> [filter | probe]* -> sink, one fused kernel
+ * ------------------------------------------------------------------------------------------ */
+#define CBP_MAX_SRC 8
+#define CBP_MAX_COLS 40
+#define CBP_MAX_OPS 128
+#define CBP_MAX_KEYS 4
+#define CBP_MAX_AGGS 16
+#define CBP_MAX_OUT 24
+#define CBP_STACK 24
+
+typedef enum CbpOpCode
+{
+	CBP_END = 0,
+	CBP_LOAD,			/* a = column index; push value widened to 64 bits (float8: raw bits)        */
+	CBP_CONST,			/* push imm                                                                   */
+	CBP_ADD, CBP_SUB, CBP_MUL,		/* int64 (ints, dates, scaled numerics); overflow -> error        */
+	CBP_FADD, CBP_FSUB, CBP_FMUL,	/* float8                                                         */
+	CBP_I2F,			/* int64 scaled by 10^a -> float8                                             */
+	CBP_EQ, CBP_NE, CBP_LT, CBP_LE, CBP_GT, CBP_GE,			/* int64 compare -> bool                  */
+	CBP_FEQ, CBP_FNE, CBP_FLT, CBP_FLE, CBP_FGT, CBP_FGE,	/* float8 compare (PG NaN ordering)       */
+	CBP_AND, CBP_OR, CBP_NOT,		/* three-valued                                                   */
+	CBP_FILTER,			/* pop; the row survives only if the value is true (not NULL)                 */
+	CBP_PROBE,			/* a = probe index; pops that probe's key values (pushed in key order)        */
+	CBP_DUP,			/* push a copy of stack[a] (common sub-expressions)                           */
+	CBP_POP
+} CbpOpCode;
+
+typedef struct CbpOp
+{
+	int32_t		code;
+	int32_t		a;
+	int64_t		imm;
+} CbpOp;
+
+typedef struct CbpColumn
+{
+	const void *data;			/* device pointer                                                     */
+	const uint8_t *nulls;		/* device pointer, one byte per row, or NULL                          */
+	const uint32_t *dict_hash;	/* device pointer: per-code hash for CB_DICT*, or NULL                */
+	int32_t		type;			/* CbTypeId                                                           */
+	int32_t		src;			/* which source's row index addresses it: 0 = driving relation,
+								 * 1 + j = inner side of probe j                                      */
+} CbpColumn;
+
+typedef struct CbpProbe
+{
+	const cbgpu_hashtable *ht;
+	int32_t		jointype;		/* CbJoinType: INNER, LEFT, SEMI, ANTI                                */
+	int32_t		nkeys;
+	int32_t		keytype[CBP_MAX_KEYS];	/* CbTypeId of each outer key value (for its hash function)   */
+	const uint32_t *key_dict_hash[CBP_MAX_KEYS];
+} CbpProbe;
+
+typedef enum CbpSinkKind
+{
+	CBP_SINK_AGG = 1,			/* hash aggregate into an agg table                                   */
+	CBP_SINK_MATERIALIZE,		/* append the stack values as rows of an output relation              */
+	CBP_SINK_PARTITION			/* like MATERIALIZE, rows grouped by destination segment (Motion)     */
+} CbpSinkKind;
+
+typedef enum CbpAggKind
+{
+	CBP_ACC_COUNT = 1,			/* N += 1 (count(*)) or N += (arg not null)                           */
+	CBP_ACC_SUM_INT,			/* N, 128-bit exact sum: int4_sum / int8_avg_accum / numeric_avg_accum */
+	CBP_ACC_SUM_FLOAT,			/* N, float8 Sx: float8pl / float8_accum                              */
+	CBP_ACC_MIN, CBP_ACC_MAX,	/* int64 ordering (ints, dates, scaled numerics)                      */
+	CBP_ACC_MERGE_INT,			/* combine: arg pair (N, 128-bit sum) from a partial state            */
+	CBP_ACC_MERGE_FLOAT,		/* arg pair (N, Sx bits)                                              */
+	CBP_ACC_MERGE_COUNT,		/* arg N                                                              */
+	CBP_ACC_MERGE_MIN,			/* arg pair (N, value): ignored when N = 0                            */
+	CBP_ACC_MERGE_MAX
+} CbpAggKind;
+
+typedef struct CbpAcc
+{
+	int32_t		kind;			/* CbpAggKind                                                         */
+	int32_t		arg;			/* stack position (0-based, after the keys) of the argument, -1 none;
+								 * MERGE_INT takes 3 consecutive values: N, sum.lo, sum.hi            */
+} CbpAcc;
+
+typedef struct CbpSink
+{
+	int32_t		kind;
+	/* AGG */
+	cbgpu_aggtable *agg;
+	int32_t		nkeys;
+	int32_t		keytype[CBP_MAX_KEYS];
+	const uint32_t *key_dict_hash[CBP_MAX_KEYS];
+	int32_t		naccs;
+	CbpAcc		accs[CBP_MAX_AGGS];
+	/* MATERIALIZE / PARTITION: the top `nout` stack values become one output row */
+	int32_t		nout;
+	cbgpu_rel  *out;			/* preallocated with capacity >= possible rows                        */
+	int64_t	   *out_count;		/* device counter(s): [1] or [nsegs]                                  */
+	/* PARTITION: cdbhash over the first nhash output values */
+	int32_t		nhash;
+	int32_t		hashtype[CBP_MAX_KEYS];
+	const uint32_t *hash_dict_hash[CBP_MAX_KEYS];
+	int32_t		nsegs;
+	int64_t		seg_capacity;	/* rows reserved per destination inside `out`                         */
+} CbpSink;
+
+typedef struct CbPipeline
+{
+	int64_t		nrows;			/* rows of the driving source                                         */
+	const uint8_t *visimap;		/* driving relation's visibility bits or NULL                         */
+	/* optional driver index vectors: row i addresses source s at drv_idx[s][i] (identity if NULL).
+	 * Used to continue from join pairs (outer_idx, inner_idx) or a selection vector. */
+	int32_t		drv_nsrc;
+	const uint32_t *drv_idx[CBP_MAX_SRC];
+	int32_t		ncols;
+	CbpColumn	cols[CBP_MAX_COLS];
+	int32_t		nops;
+	CbpOp		ops[CBP_MAX_OPS];
+	int32_t		nprobes;
+	CbpProbe	probes[CBP_MAX_SRC - 1];
+	CbpSink		sink;
+	int32_t		force_generic;	/* tests: bypass the pattern-specialised kernels                      */
+} CbPipeline;
+
+int			cbgpu_pipeline_run(cbgpu_ctx *ctx, const CbPipeline *p);
+
+/* ------------------------------------------------------------------------------------------
+ * hash join tables
+ * ------------------------------------------------------------------------------------------ */
+/* build over rows of `inner` (all rows, or those listed in sel[0..nsel)); key columns by index.
+ * NULL keys are not inserted (strict hash operators, nodeHash.c:2161). */
+int			cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t nkeys,
+						   cbgpu_hashtable **out);
+void		cbgpu_ht_free(cbgpu_hashtable *ht);
+int64_t		cbgpu_ht_nrows(const cbgpu_hashtable *ht);
+int			cbgpu_ht_has_duplicates(const cbgpu_hashtable *ht);
+/* stand-alone probe emitting (outer_idx, inner_idx) pairs for an INNER join (all matches);
+ * outer key columns by index.  pairs are written to two device arrays owned by the call result. */
+typedef struct cbgpu_pairs
+{
+	int64_t		npairs;
+	uint32_t   *outer_idx;		/* device                                                             */
+	uint32_t   *inner_idx;		/* device                                                             */
+} cbgpu_pairs;
+int			cbgpu_ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer,
+								 const int32_t *keycols, int32_t nkeys, const uint32_t *sel, int64_t nsel,
+								 cbgpu_pairs *out);
+void		cbgpu_pairs_free(cbgpu_pairs *p);
+int			cbgpu_read_u32(cbgpu_ctx *ctx, const uint32_t *dev, int64_t n, uint32_t *host);
+/* small device scratch (sink row counters, index vectors): zero-filled allocation, read-back, free */
+int			cbgpu_dev_alloc(cbgpu_ctx *ctx, size_t bytes, void **dev);
+int			cbgpu_dev_read(cbgpu_ctx *ctx, const void *dev, size_t bytes, void *host);
+int			cbgpu_dev_write(cbgpu_ctx *ctx, void *dev, size_t bytes, const void *host);
+void		cbgpu_dev_free(cbgpu_ctx *ctx, void *dev);
+/* give column `col` of an output relation a NULL byte-map (zero-filled) so sinks may store NULLs */
+int			cbgpu_rel_add_nullmap(cbgpu_rel *rel, int32_t col);
+/* device -> device copy of rows [src_lo, src_lo + n) of every column of `src` to row dst_lo of `dst`
+ * (same column types); the local interconnect and Motion receive buffers use it */
+int			cbgpu_rel_copy_rows(cbgpu_rel *dst, int64_t dst_lo, cbgpu_rel *src, int64_t src_lo, int64_t n);
+int			cbgpu_rel_has_nulls(const cbgpu_rel *rel, int32_t col);
+const uint32_t *cbgpu_rel_dict_hash_dev(const cbgpu_rel *rel, int32_t col);
+const uint8_t *cbgpu_rel_nulls_dev(const cbgpu_rel *rel, int32_t col);
+const uint8_t *cbgpu_rel_visimap_dev(const cbgpu_rel *rel);
+/* share a dictionary hash table between relations (device pointer copy; `dst` does not own it) */
+int			cbgpu_rel_share_dict_hash(cbgpu_rel *dst, int32_t dcol, const cbgpu_rel *src, int32_t scol);
+
+/* ------------------------------------------------------------------------------------------
+ * aggregate tables
+ * ------------------------------------------------------------------------------------------ */
+/* acc_kinds[a] (CbpAggKind) fixes each accumulator's initial value (MIN / MAX need one) */
+int			cbgpu_agg_create(cbgpu_ctx *ctx, int32_t nkeys, int32_t naccs, const int32_t *acc_kinds,
+							 int64_t capacity_groups, cbgpu_aggtable **out);
+void		cbgpu_agg_free(cbgpu_aggtable *t);
+int			cbgpu_agg_reset(cbgpu_aggtable *t);
+/* number of groups present (blocking) */
+int			cbgpu_agg_ngroups(cbgpu_aggtable *t, int64_t *ngroups);
+/* copy the groups out, compacted, in table order: keys[g*nkeys+k] (64-bit widened),
+ * keynull[g] bit k, n[g*naccs+a], sum_lo/sum_hi[g*naccs+a] (float8 states: bits in sum_lo) */
+int			cbgpu_agg_read(cbgpu_aggtable *t, int64_t maxgroups, int64_t *keys, uint32_t *keynull,
+						   int64_t *n, int64_t *sum_lo, int64_t *sum_hi, int64_t *ngroups);
+/* groups as a device relation: columns = keys (typed), then per accumulator N (int8) and the
+ * 128-bit sum as two int8 columns (lo, hi); used as the source of the next pipeline (Motion,
+ * final aggregation) and by top-N */
+int			cbgpu_agg_to_rel(cbgpu_aggtable *t, const int32_t *keytypes, cbgpu_rel **out);
+
+/* device top-N over a relation: ORDER BY up to 4 (column, descending) keys LIMIT n; 128-bit
+ * values are ordered through (hi, lo) column pairs: pass hi as the key and lo as the next key.
+ * Returns the chosen row indices in order. */
+int			cbgpu_topn(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const int32_t *descending,
+					   const int32_t *unsigned_cmp, int32_t nkeys, int64_t limit, uint32_t *host_idx,
+					   int64_t *nout);
+
+/* ------------------------------------------------------------------------------------------
+ * synthetic TPC-H shaped generator (harness; same counter-based formulas as
+ * cloudberry_b200/tpch.py so host and device tables are identical)
+ * ------------------------------------------------------------------------------------------ */
+int			cbgpu_gen_lineitem(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed, int64_t row_lo,
+							   int64_t n_supp, int64_t n_part);
+int			cbgpu_gen_orders(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed, int64_t row_lo, int64_t n_cust);
+int			cbgpu_gen_customer(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed);
+int			cbgpu_gen_supplier(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif							/* CBGPU_H */
