@@ -1,0 +1,309 @@
+#!/usr/bin/env python3
+"""bench.py - TPC-H SF100 Q1 (AOCS scan -> hash aggregate) rows/sec on N GPU-segments.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
+  value      whole-job rows/sec with the projected lineitem columns already resident in HBM
+             (a "step" = one full pass of Q1 over the rank's lineitem shard through the ExecProcNode-style
+             executor and the C ABI; weak scaling: every GPU-segment holds a full SF100-sized shard)
+  e2e        the same query with HOST (pinned) buffers: every step copies the projected columns host->device,
+             runs the query, and reads the result rows back
+  roofline   algorithmic bytes (38 B/row: SURVEY.md 8d) / CUDA-event duration of the scan+agg kernel, against the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (row-at-a-time restatement of the reference path) on a bounded sample, rank 0, N=1
+`--impl reference` times that CPU restatement on all host cores (the reference server itself cannot be built
+here: no bison/flex) with the same metric / config keys.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+Q1_BYTES_PER_ROW = 38       # qty 8 + extendedprice 8 + discount 8 + tax 8 + shipdate 4 + returnflag 1 + linestatus 1
+Q1_COLS = ["l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.p:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        clocks, reasons, mx = [], set(), None
+        for line in open(self.f.name):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9 or parts[0] != str(self.gpu):
+                continue
+            try:
+                clocks.append(float(parts[1]))
+                mx = float(parts[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if clocks:
+            clocks.sort()
+            out.update({"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons),
+                        "samples": len(clocks)})
+        return out
+
+
+def cpu_q1_sample(nthreads, rows_total, seed=42):
+    """Run the oracle's Q1 on a bounded sample of the same synthetic lineitem; returns (rows/s, rows, seconds)."""
+    from cloudberry_b200 import tpch
+    from oracle import oracle as O
+    sz = tpch.sizes(100)
+    per = max(1, rows_total // nthreads)
+    segs = []
+    nation, region = tpch.gen_nation_region()
+    for s in range(nthreads):
+        cols = tpch.gen_lineitem(seed, sz["lineitem"], sz["supplier"], sz["part"], lo=s * per, hi=(s + 1) * per)
+        segs.append([tpch._rel("lineitem", cols)])
+    plan = tpch.q1_plan(nthreads) if nthreads > 1 else tpch.q1_plan(1)
+    O.lib()
+    t0 = time.perf_counter()
+    res = O.execute(plan, segs, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    assert len(res.rows) >= 1
+    return per * nthreads / dt, per * nthreads, dt
+
+
+def run_reference(args):
+    """CPU arm: the restated reference path (oracle) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    nthreads = min(cores, 64)
+    rows = min(64_000_000, 2_000_000 * nthreads)
+    # generate once, time K steps after W warm-ups
+    from cloudberry_b200 import tpch
+    from oracle import oracle as O
+    sz = tpch.sizes(100)
+    per = rows // nthreads
+    segs = [[tpch._rel("lineitem", tpch.gen_lineitem(42, sz["lineitem"], sz["supplier"], sz["part"], lo=s * per, hi=(s + 1) * per))]
+            for s in range(nthreads)]
+    plan = tpch.q1_plan(nthreads) if nthreads > 1 else tpch.q1_plan(1)
+    O.lib()
+    for _ in range(args.warmup):
+        O.execute(plan, segs, nthreads=nthreads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.execute(plan, segs, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    value = per * nthreads * args.steps / dt
+    sample = "Q1 over %d synthetic lineitem rows per step (%d CPU segments x %d rows, two-stage aggregation)" % (per * nthreads, nthreads, per)
+    line = {
+        "impl": "reference", "metric": "TPC-H SF100 Q1 rows/sec", "value": value, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "TPC-H SF100 Q1 on 1 GPU-segment (scan + hash-agg kernel, no Motion)", "rows_per_gpu": sz["lineitem"],
+                   "note": "CPU restatement of the reference path (oracle/); the reference server needs bison/flex and cannot be built here"},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--sf", type=float, default=100.0, help="scale factor of each GPU-segment's shard (default: the BASELINE config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    from cloudberry_b200 import capi, tpch
+    import numpy as np
+
+    ctx = capi.Context(local_rank)
+    G = ctx.L
+    sz = tpch.sizes(int(args.sf) if float(args.sf).is_integer() else args.sf)
+    nrows = sz["lineitem"]
+    li_types = [t for _, t in tpch.SCHEMA["lineitem"]]
+    li = capi.DeviceRelation(ctx, nrows, li_types, name="lineitem")
+    # rank r holds rows [r * nrows, (r + 1) * nrows) of an (N x SF)-sized table: a valid (random) distribution for Q1
+    ctx.check(G.cbgpu_gen_lineitem(ctx.h, li.h, 42, rank * nrows, sz["supplier"], sz["part"]))
+    ctx.sync()
+    rt = [li]
+    ex = capi.Executor(ctx, rt)
+    plan1 = tpch.q1_plan(1)
+
+    def barrier():
+        ctx.sync()
+        if dist:
+            dist.barrier()
+        ctx.sync()
+
+    def combine(rows_states):
+        return rows_states
+
+    # ---- device-resident: warm-up, then K timed steps ----
+    for _ in range(args.warmup):
+        res = ex.run(plan1)
+    sampler = ClockSampler(local_rank)
+    kernel_ms = []
+    barrier()
+    sampler.start()
+    l0 = ctx.launches()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        res = ex.run(plan1)
+        kernel_ms.append(ctx.last_kernel()[1])
+    ms = ctx.timer_stop_ms()
+    l1 = ctx.launches()
+    barrier()
+    clocks = sampler.stop()
+    kname = ctx.last_kernel()[0]
+    if dist:
+        import torch
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_rows = nrows * world
+    value = total_rows * args.steps / (ms / 1e3)
+    peak, peak_src = measured_peak()
+    kms = sorted(kernel_ms)[len(kernel_ms) // 2]
+    achieved = nrows * Q1_BYTES_PER_ROW / (kms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "q1_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- end to end: host (pinned) buffers -> H2D -> query -> rows back ----
+    e2e = None
+    if not args.no_e2e:
+        cols = [tpch.SCHEMA["lineitem"].index(next(c for c in tpch.SCHEMA["lineitem"] if c[0] == n)) for n in Q1_COLS]
+        e2e_rows = nrows
+        host = {}
+        ok = True
+        for c in cols:
+            w = capi.P.TYPE_WIDTH[li_types[c]]
+            p = G.cbgpu_host_alloc(e2e_rows * w)
+            if not p:
+                ok = False
+                break
+            host[c] = p
+            ctx.check(G.cbgpu_rel_read_column(li.h, c, 0, e2e_rows, p, None))
+        if ok:
+            h2d = sum(e2e_rows * capi.P.TYPE_WIDTH[li_types[c]] for c in cols)
+            d2h = 0
+
+            def e2e_step():
+                for c in cols:
+                    li.load_column_ptr(c, host[c])
+                r = ex.run(plan1)
+                return r
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            ctx.timer_start()
+            for _ in range(args.e2e_steps):
+                r = e2e_step()
+            e_ms = ctx.timer_stop_ms()
+            wall = time.perf_counter() - t0
+            barrier()
+            d2h = sum(8 * len(row) for row in r.rows)
+            e_ms = max(e_ms, wall * 1e3)
+            if dist:
+                import torch
+                t = torch.tensor([e_ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e_ms = float(t.item())
+            e2e = {"value": e2e_rows * world * args.e2e_steps / (e_ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d * world,
+                   "d2h_bytes_per_step": d2h * world, "steps": args.e2e_steps, "ms_per_step": e_ms / args.e2e_steps}
+        for p in host.values():
+            G.cbgpu_host_free(p)
+
+    # ---- CPU baseline (rank 0, N = 1): the oracle, scalar, on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, rows, secs = cpu_q1_sample(1, 24_000_000)
+        cpu = {"value": rate, "unit": "rows/s", "cores": 1, "kind": "port",
+               "sample": "Q1 over the first %d rows of the same synthetic lineitem, %.1f s, one thread (row-at-a-time oracle)" % (rows, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": "TPC-H SF100 Q1 rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "TPC-H SF%g Q1 on %d GPU-segment(s) (scan + hash-agg kernel%s)" % (args.sf, world, ", two-stage agg over Redistribute Motion" if world > 1 else ", no Motion"),
+                       "rows_per_gpu": nrows, "groups": len(res.rows), "l2": "inputs (%.1f GB per GPU) larger than L2" % (nrows * Q1_BYTES_PER_ROW / 1e9),
+                       "timing": "CUDA events on the executor's stream, max over ranks"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": kname, "kernel_ms": kms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": nrows * Q1_BYTES_PER_ROW},
+            "clocks": clocks, "gpu_launches": l1 - l0,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ex.close()
+    li.free()
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -223,7 +223,7 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 		uint32_t	ridx[CBP_MAX_SRC];
 		uint32_t	rnull = 0;		/* bit s: source s is NULL-extended (left join miss)              */
 		int64_t		st[CBP_STACK];
-		uint32_t	snull = 0;
+		uint64_t	snull = 0;
 		int			sp = 0;
 
 #pragma unroll
@@ -266,7 +266,7 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 						knull = true;
 					h = pg_hash_combine(h, pg_hash_datum(pr.keytype[k], key[k], pr.keydict[k]), false);
 				}
-				snull &= (1u << sp) - 1;
+				snull &= (1ull << sp) - 1;
 				if (alive && !knull)
 				{
 					uint32_t	pos = h & pr.ht.mask;
@@ -332,18 +332,18 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 								v = cb_load_widen(c.data, c.type, r);
 						}
 						st[sp] = v;
-						snull = isnull ? (snull | (1u << sp)) : (snull & ~(1u << sp));
+						snull = isnull ? (snull | (1ull << sp)) : (snull & ~(1ull << sp));
 						sp++;
 						break;
 					}
 				case CBP_CONST:
 					st[sp] = P.ops[pc].imm;
-					snull &= ~(1u << sp);
+					snull &= ~(1ull << sp);
 					sp++;
 					break;
 				case CBP_DUP:
 					st[sp] = st[a];
-					snull = ((snull >> a) & 1) ? (snull | (1u << sp)) : (snull & ~(1u << sp));
+					snull = ((snull >> a) & 1) ? (snull | (1ull << sp)) : (snull & ~(1ull << sp));
 					sp++;
 					break;
 				case CBP_POP:
@@ -379,7 +379,7 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 							atomicExch(P.status, CBGPU_ERR_OVERFLOW);
 						sp--;
 						st[sp - 1] = r;
-						snull = n ? (snull | (1u << (sp - 1))) : (snull & ~(1u << (sp - 1)));
+						snull = n ? (snull | (1ull << (sp - 1))) : (snull & ~(1ull << (sp - 1)));
 						break;
 					}
 				case CBP_FADD: case CBP_FSUB: case CBP_FMUL:
@@ -391,7 +391,7 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 
 						sp--;
 						st[sp - 1] = __double_as_longlong(r);
-						snull = n ? (snull | (1u << (sp - 1))) : (snull & ~(1u << (sp - 1)));
+						snull = n ? (snull | (1ull << (sp - 1))) : (snull & ~(1ull << (sp - 1)));
 						break;
 					}
 				case CBP_I2F:
@@ -427,7 +427,7 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 						}
 						sp--;
 						st[sp - 1] = r;
-						snull = n ? (snull | (1u << (sp - 1))) : (snull & ~(1u << (sp - 1)));
+						snull = n ? (snull | (1ull << (sp - 1))) : (snull & ~(1ull << (sp - 1)));
 						break;
 					}
 				case CBP_AND: case CBP_OR:
@@ -456,7 +456,7 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 						}
 						sp--;
 						st[sp - 1] = r;
-						snull = n ? (snull | (1u << (sp - 1))) : (snull & ~(1u << (sp - 1)));
+						snull = n ? (snull | (1ull << (sp - 1))) : (snull & ~(1ull << (sp - 1)));
 						break;
 					}
 				case CBP_NOT:
@@ -467,7 +467,7 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 					/* ExecQual: NULL counts as false */
 					if (((snull >> sp) & 1) || !st[sp])
 						alive = false;
-					snull &= ~(1u << sp);
+					snull &= ~(1ull << sp);
 					break;
 			}
 		}
@@ -481,7 +481,7 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 				/* TupleHashTableHash_internal (executor/execGrouping.c:437-495): hash_iv 0,
 				 * rotate-xor per key (NULL -> 0), then murmurhash32 */
 				uint32_t	h = 0;
-				uint32_t	knull = snull & ((1u << S.nkeys) - 1);
+				uint32_t	knull = (uint32_t) (snull & ((1ull << S.nkeys) - 1));
 
 				for (int k = 0; k < S.nkeys; k++)
 				{

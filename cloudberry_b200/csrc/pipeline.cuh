@@ -56,7 +56,7 @@ struct PipeDev
 /* one accumulator update of advance_aggregates (backend/executor/nodeAgg.c:856).  `args` are the
  * stack values after the keys; argnull their NULL bits. */
 __device__ __forceinline__ void
-sink_acc_update(const AggDev &t, int slot, int a, const CbpAcc &acc, const int64_t *args, uint32_t argnull)
+sink_acc_update(const AggDev &t, int slot, int a, const CbpAcc &acc, const int64_t *args, uint64_t argnull)
 {
 	int64_t    *np = t.n + (size_t) slot * t.naccs + a;
 	unsigned long long *sp = t.sum + ((size_t) slot * t.naccs + a) * 2;

@@ -118,8 +118,8 @@ size_t		cbgpu_rel_nbytes(const cbgpu_rel *rel);
 #define CBP_MAX_OPS 128
 #define CBP_MAX_KEYS 4
 #define CBP_MAX_AGGS 16
-#define CBP_MAX_OUT 24
-#define CBP_STACK 24
+#define CBP_MAX_OUT 48
+#define CBP_STACK 48
 
 typedef enum CbpOpCode
 {
