@@ -50,7 +50,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -145,7 +145,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--sf", type=float, default=100.0, help="scale factor of each GPU-segment's shard (default: the BASELINE config)")
@@ -196,12 +196,12 @@ def main():
         return rows_states
 
     # ---- device-resident: warm-up, then K timed steps ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()         # covers warm-up and the timed region: both are the same load
     for _ in range(args.warmup):
         res = ex.run(plan1)
-    sampler = ClockSampler(local_rank)
     kernel_ms = []
     barrier()
-    sampler.start()
     l0 = ctx.launches()
     ctx.timer_start()
     for _ in range(args.steps):

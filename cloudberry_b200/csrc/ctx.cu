@@ -521,6 +521,7 @@ cbgpu_rel_share_dict_hash(cbgpu_rel *dst, int32_t dcol, const cbgpu_rel *src, in
 	if (dcol < 0 || dcol >= dst->ncols || scol < 0 || scol >= src->ncols)
 		return cb_fail(dst->ctx, CBGPU_ERR_INVALID, "cbgpu_rel_share_dict_hash: bad column%s %lld", "", dcol);
 	dst->dict_hash[dcol] = src->dict_hash[scol];
-	dst->dict_n[dcol] = -src->dict_n[scol];	/* negative: borrowed, not freed with dst */
+	/* negative count: borrowed, not freed with dst (the source may itself be a borrower) */
+	dst->dict_n[dcol] = src->dict_n[scol] > 0 ? -src->dict_n[scol] : (src->dict_n[scol] < 0 ? src->dict_n[scol] : -1);
 	return CBGPU_OK;
 }

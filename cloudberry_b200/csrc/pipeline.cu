@@ -561,6 +561,13 @@ cbgpu_pipeline_run(cbgpu_ctx *ctx, const CbPipeline *p)
 	if (rc)
 		return rc;
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	{
+		/* an earlier asynchronous failure must not be blamed on (or hidden by) this launch */
+		cudaError_t stale = cudaGetLastError();
+
+		if (stale != cudaSuccess)
+			return cb_fail(ctx, CBGPU_ERR_CUDA, "CUDA error pending before the pipeline launch: %s", cudaGetErrorString(stale));
+	}
 	ctx->kernel_timed = false;
 	if (p->nrows == 0)
 		return CBGPU_OK;

@@ -22,7 +22,6 @@
 #include "pipeline.cuh"
 #include "xmatch.h"
 
-#define SA_THREADS 256
 #define SA_NSUM 6				/* sA sB sC sD sREV sCHG */
 
 struct SmallAggParams
@@ -35,8 +34,8 @@ struct SmallAggParams
 	long long	k,
 				k2;
 	const int32_t *fcol;		/* optional filter column (int4/date)                                 */
-	int32_t		fcode;			/* CbpOpCode comparison                                               */
-	int32_t		fconst;
+	int32_t		flo;			/* the qual folded to a closed range: flo <= value <= flo + fspan     */
+	uint32_t	fspan;
 	const uint8_t *key0;		/* optional group key columns (char(1) / dictionary code)             */
 	const uint8_t *key1;
 	const uint8_t *visimap;
@@ -50,36 +49,11 @@ struct SmallAggParams
 	int32_t		want_chg;		/* the b*(k-c)*(k2+d) sum is requested                                */
 	int		   *status;
 	int		   *retry;			/* set when a CTA saw more than G distinct groups                     */
+	int		   *audit;			/* set when the 64-bit fast arithmetic could have overflowed          */
 	/* per-CTA partial results, committed by k_small_commit once no CTA asked for a retry */
 	unsigned long long *scratch;	/* [grid][G][SA_NSUM + 1][2]                                      */
 	unsigned   *skeys;			/* [grid][G]                                                          */
 };
-
-__device__ __forceinline__ bool
-sa_cmp(int code, int32_t x, int32_t y)
-{
-	switch (code)
-	{
-		case CBP_EQ: return x == y;
-		case CBP_NE: return x != y;
-		case CBP_LT: return x < y;
-		case CBP_LE: return x <= y;
-		case CBP_GT: return x > y;
-		default: return x >= y;
-	}
-}
-
-__device__ __forceinline__ void
-ld_nc_v2(const long long *p, long long &a, long long &b)
-{
-	asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-}
-
-__device__ __forceinline__ long long
-sa_abs(long long v)
-{
-	return v < 0 ? -v : v;
-}
 
 template <int G>
 struct SaAcc
@@ -88,63 +62,148 @@ struct SaAcc
 	long long	s[G][SA_NSUM];
 };
 
-/* accumulate one row into the register accumulators of its group slot */
-template <int G>
+/*
+ * acc += hit * v with hit in {0, 1}: one IMAD.WIDE.U32 (hit * v.lo + acc, 64-bit add with carry)
+ * and one IMAD (hit * v.hi + acc.hi).  Two fma-pipe instructions per 64-bit accumulator and row,
+ * no compare / select / predicate per accumulator; two's complement makes it exact for negative v.
+ */
 __device__ __forceinline__ void
-sa_accumulate(SaAcc<G> &acc, int slot, bool pass, long long a, long long b, long long c, long long d, long long rev, long long chg)
+sa_madd(long long &acc, unsigned hit, long long v)
 {
-#pragma unroll
-	for (int g = 0; g < G; g++)
-	{
-		bool		hit = pass && slot == g;
-
-		acc.cnt[g] += hit ? 1u : 0u;
-		acc.s[g][0] += hit ? a : 0;
-		acc.s[g][1] += hit ? b : 0;
-		acc.s[g][2] += hit ? c : 0;
-		acc.s[g][3] += hit ? d : 0;
-		acc.s[g][4] += hit ? rev : 0;
-		acc.s[g][5] += hit ? chg : 0;
-	}
+	asm("{\n\t"
+		".reg .b32 vlo, vhi, tlo, thi;\n\t"
+		".reg .b64 t;\n\t"
+		"mov.b64 {vlo, vhi}, %2;\n\t"
+		"mad.wide.u32 t, %1, vlo, %0;\n\t"
+		"mov.b64 {tlo, thi}, t;\n\t"
+		"mad.lo.u32 thi, %1, vhi, thi;\n\t"
+		"mov.b64 %0, {tlo, thi};\n\t"
+		"}"
+		: "+l"(acc) : "r"(hit), "l"(v));
 }
 
-/* find (or claim) the slot of a group key in the CTA's shared key table */
+/* slow path, once per new group per thread: claim a slot in the CTA's shared key table */
 template <int G>
-__device__ __forceinline__ int
-sa_slot(unsigned *gkeys, unsigned key, int *retry)
+__device__ __noinline__ void
+sa_insert_key(unsigned *gkeys, unsigned key, int *retry)
 {
-#pragma unroll
-	for (int g = 0; g < G; g++)
+	bool		placed = false;
+
+	for (int g = 0; g < G && !placed; g++)
 	{
 		unsigned	cur = ((volatile unsigned *) gkeys)[g];
 
-		if (cur == key)
-			return g;
 		if (cur == 0)
-		{
-			unsigned	old = atomicCAS(gkeys + g, 0u, key);
-
-			if (old == 0 || old == key)
-				return g;
-		}
+			cur = atomicCAS(gkeys + g, 0u, key);
+		if (cur == 0 || cur == key)
+			placed = true;
 	}
-	atomicExch(retry, 1);
-	return -1;
+	if (!placed)
+		atomicExch(retry, 1);	/* more distinct groups than register slots */
 }
 
+/* ---- TMA bulk-copy pipeline primitives (sm_90+ PTX; SASS: UBLKCP / SYNCS) ---- */
+__device__ __forceinline__ uint32_t
+smem_u32(const void *p)
+{
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void
+mbar_init(uint64_t *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void
+mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_wait(uint64_t *bar, unsigned parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+/* one contiguous global -> shared bulk copy, completion counted in bytes on `bar` */
+__device__ __forceinline__ void
+tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+#define SA_TILE 896				/* rows per pipeline stage                                            */
+#define SA_STAGES 5
+/* consumer threads (one extra warp produces): 448 + 32 threads leave 128 registers per thread for
+ * the 4-group kernel; the 8-group kernel needs twice the accumulators and runs half the threads */
+#define SA_NCONS(G) ((G) <= 4 ? 448 : 224)
+
+struct __align__(128) SaStage
+{
+	long long	a[SA_TILE];
+	long long	b[SA_TILE];
+	long long	c[SA_TILE];
+	long long	d[SA_TILE];
+	int32_t		f[SA_TILE];
+	uint8_t		k0[SA_TILE];
+	uint8_t		k1[SA_TILE];
+};
+
+/*
+ * One persistent CTA per SM.  Warp 0 is the producer: for each tile it arms the stage's "full"
+ * mbarrier with the byte count and issues one TMA bulk copy per projected column
+ * (cp.async.bulk global -> shared), up to SA_STAGES tiles ahead, so ~150 KB of loads are in flight
+ * per SM regardless of what the consumers are doing.  The 16 consumer warps wait on "full", read
+ * their rows from shared memory (row-per-thread, conflict free), evaluate the qual and the
+ * arithmetic, accumulate per group in registers, and release the stage through "empty".
+ */
 template <int G>
-__global__ void __launch_bounds__(SA_THREADS, (G <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(SA_NCONS(G) + 32, 1)
 k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	SaStage    *stages = (SaStage *) smem_raw;
+	__shared__ uint64_t full_bar[SA_STAGES];
+	__shared__ uint64_t empty_bar[SA_STAGES];
 	__shared__ unsigned gkeys[G];
 	__shared__ unsigned long long red[G][SA_NSUM + 1][2];	/* 128-bit CTA totals                     */
 	SaAcc<G>	acc;
-	unsigned long long magB = 0,
-				magKC = 0,
-				magKD = 0,
-				magAcc = 0;
-	long long	rows_seen = 0;
+	unsigned long long magAB = 0,	/* OR of the raw a / b, c and d values seen (sign bits included)  */
+				magC = 0,
+				magD = 0;
+	unsigned	rows_seen = 0;
+	unsigned	gk[G];			/* this thread's cached copy of the CTA's group key table             */
+	constexpr int NCONS = SA_NCONS(G);
+	const int	warp = threadIdx.x >> 5;
+	const int	lane = threadIdx.x & 31;
+	const int64_t ntiles = (P.nrows + SA_TILE - 1) / SA_TILE;
 
+	if (threadIdx.x == 0)
+	{
+		for (int s = 0; s < SA_STAGES; s++)
+		{
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], NCONS / 32);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
 	if (threadIdx.x < G)
 		gkeys[threadIdx.x] = 0;
 	for (int i = threadIdx.x; i < G * (SA_NSUM + 1) * 2; i += blockDim.x)
@@ -153,131 +212,164 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 	for (int g = 0; g < G; g++)
 	{
 		acc.cnt[g] = 0;
+		gk[g] = 0;
 #pragma unroll
 		for (int s = 0; s < SA_NSUM; s++)
 			acc.s[g][s] = 0;
 	}
 	__syncthreads();
 
-	/* tiles of 2 * SA_THREADS rows: thread t owns rows base + 2t, base + 2t + 1 */
-	const int64_t tile = 2 * SA_THREADS;
-	const int64_t ntiles = (P.nrows + tile - 1) / tile;
-
-	for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+	if (warp == 0)
 	{
-		const int64_t r0 = t * tile + 2 * threadIdx.x;
-		long long	a[2] = {0, 0},
-					b[2],
-					c[2],
-					d[2] = {0, 0};
-		int32_t		f[2] = {0, 0};
-		unsigned	k0[2] = {0, 0},
-					k1[2] = {0, 0};
-		bool		ok[2];
-
-		ok[0] = r0 < P.nrows;
-		ok[1] = r0 + 1 < P.nrows;
-		if (ok[1])
+		/* ---- producer ---- */
+		if (lane == 0)
 		{
-			/* full pair: 16-byte loads, streaming (no L1 allocation: each byte is used once) */
-			ld_nc_v2(P.colB + r0, b[0], b[1]);
-			ld_nc_v2(P.colC + r0, c[0], c[1]);
-			if (P.colA)
-				ld_nc_v2(P.colA + r0, a[0], a[1]);
-			if (P.colD)
-				ld_nc_v2(P.colD + r0, d[0], d[1]);
-			if (P.fcol)
-			{
-				int2		fv = __ldg((const int2 *) (P.fcol + r0));
+			int			it = 0;
 
-				f[0] = fv.x;
-				f[1] = fv.y;
-			}
-			if (P.key0)
+			for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
 			{
-				unsigned short kv = __ldg((const unsigned short *) (P.key0 + r0));
+				const int	s = it % SA_STAGES;
+				const unsigned ph = (it / SA_STAGES) & 1;
+				const int64_t r0 = t * SA_TILE;
+				const int64_t rows = P.nrows - r0 < SA_TILE ? P.nrows - r0 : SA_TILE;
+				/* bulk copies move multiples of 16 bytes; relations are allocated padded, so the
+				 * few bytes past the last row are readable and simply ignored */
+				const unsigned b8 = (unsigned) (rows * 8 + 15) & ~15u;
+				const unsigned b4 = (unsigned) (rows * 4 + 15) & ~15u;
+				const unsigned b1 = (unsigned) (rows + 15) & ~15u;
+				unsigned	total = 2 * b8 + (P.colA ? b8 : 0) + (P.colD ? b8 : 0) + (P.fcol ? b4 : 0) +
+					(P.key0 ? b1 : 0) + (P.key1 ? b1 : 0);
+				SaStage    *st = &stages[s];
 
-				k0[0] = kv & 0xff;
-				k0[1] = kv >> 8;
-			}
-			if (P.key1)
-			{
-				unsigned short kv = __ldg((const unsigned short *) (P.key1 + r0));
-
-				k1[0] = kv & 0xff;
-				k1[1] = kv >> 8;
+				mbar_wait(&empty_bar[s], ph ^ 1);
+				mbar_expect_tx(&full_bar[s], total);
+				tma_load_1d(st->b, P.colB + r0, b8, &full_bar[s]);
+				tma_load_1d(st->c, P.colC + r0, b8, &full_bar[s]);
+				if (P.colA)
+					tma_load_1d(st->a, P.colA + r0, b8, &full_bar[s]);
+				if (P.colD)
+					tma_load_1d(st->d, P.colD + r0, b8, &full_bar[s]);
+				if (P.fcol)
+					tma_load_1d(st->f, P.fcol + r0, b4, &full_bar[s]);
+				if (P.key0)
+					tma_load_1d(st->k0, P.key0 + r0, b1, &full_bar[s]);
+				if (P.key1)
+					tma_load_1d(st->k1, P.key1 + r0, b1, &full_bar[s]);
 			}
 		}
-		else if (ok[0])
-		{
-			b[0] = __ldg(P.colB + r0);
-			c[0] = __ldg(P.colC + r0);
-			b[1] = c[1] = 0;
-			if (P.colA)
-				a[0] = __ldg(P.colA + r0);
-			if (P.colD)
-				d[0] = __ldg(P.colD + r0);
-			if (P.fcol)
-				f[0] = __ldg(P.fcol + r0);
-			if (P.key0)
-				k0[0] = __ldg(P.key0 + r0);
-			if (P.key1)
-				k1[0] = __ldg(P.key1 + r0);
-		}
-		else
-		{
-			b[0] = b[1] = c[0] = c[1] = 0;
-		}
-		if (P.visimap && ok[0])
-		{
-			/* AppendOnlyVisimap_IsVisible: both rows of the pair share a byte (r0 is even) */
-			unsigned	vb = __ldg(P.visimap + (r0 >> 3)) >> (r0 & 7);
+	}
+	else
+	{
+		/* ---- consumers ---- */
+		const int	ct = threadIdx.x - 32;
+		int			it = 0;
 
-			ok[0] = ok[0] && (vb & 1);
-			ok[1] = ok[1] && ((vb >> 1) & 1);
-		}
+		for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
+		{
+			const int	s = it % SA_STAGES;
+			const unsigned ph = (it / SA_STAGES) & 1;
+			const int64_t r0 = t * SA_TILE;
+			const int	rows = (int) (P.nrows - r0 < SA_TILE ? P.nrows - r0 : SA_TILE);
+			const SaStage *st = &stages[s];
+
+			mbar_wait(&full_bar[s], ph);
 #pragma unroll
-		for (int j = 0; j < 2; j++)
-		{
-			bool		pass = ok[j] && (!P.fcol || sa_cmp(P.fcode, f[j], P.fconst));
-			long long	kc = P.k - c[j];
-			long long	kd = P.k2 + d[j];
-			long long	rev = b[j] * kc;
-			long long	chg = P.want_chg ? rev * kd : 0;
-			/* slot lookup: the key carries a valid bit so 0 means "empty slot" */
-			unsigned	key = 0x10000u | k0[j] | (k1[j] << 8);
-			int			slot = 0;
-
-			if (pass)
+			for (int j = 0; j < SA_TILE / NCONS; j++)
 			{
-				slot = sa_slot<G>(gkeys, key, P.retry);
-				magB |= (unsigned long long) sa_abs(b[j]);
-				magKC |= (unsigned long long) sa_abs(kc);
-				if (P.want_chg)
-					magKD |= (unsigned long long) sa_abs(kd);
-				magAcc |= (unsigned long long) (sa_abs(a[j]) | sa_abs(b[j]) | sa_abs(c[j]) | sa_abs(d[j]) | sa_abs(rev) | sa_abs(chg));
-				rows_seen++;
+				const int	r = ct + j * NCONS;
+				bool		pass = r < rows;
+				long long	a = P.colA ? st->a[r] : 0;
+				long long	b = st->b[r];
+				long long	c = st->c[r];
+				long long	d = P.colD ? st->d[r] : 0;
+				int32_t		f = P.fcol ? st->f[r] : P.flo;
+				unsigned	k0 = P.key0 ? st->k0[r] : 0;
+				unsigned	k1 = P.key1 ? st->k1[r] : 0;
+
+				if (P.visimap && pass)
+				{
+					/* AppendOnlyVisimap_IsVisible (access/appendonly/appendonly_visimap.c:198) */
+					const int64_t gr = r0 + r;
+
+					pass = (__ldg(P.visimap + (gr >> 3)) >> (gr & 7)) & 1;
+				}
+				/* the qual as a closed range (EQ/LT/LE/GT/GE folded by the host): one unsigned compare */
+				pass = pass && ((unsigned) (f - P.flo) <= P.fspan);
+				long long	kc = P.k - c;
+				long long	rev = b * kc;
+				long long	chg = P.want_chg ? rev * (P.k2 + d) : 0;
+				/* the key carries a valid bit (0 = empty slot); a row that fails the qual gets a key
+				 * no slot can hold */
+				unsigned	key = pass ? (0x10000u | k0 | (k1 << 8)) : 0xFFFFFFFFu;
+				unsigned	hit[G];
+				unsigned	known = 0;
+
+#pragma unroll
+				for (int g = 0; g < G; g++)
+				{
+					hit[g] = key == gk[g] ? 1u : 0u;
+					known |= hit[g];
+				}
+				if (pass && !known)
+				{
+					sa_insert_key<G>(gkeys, key, P.retry);
+#pragma unroll
+					for (int g = 0; g < G; g++)
+					{
+						gk[g] = ((volatile unsigned *) gkeys)[g];
+						hit[g] = key == gk[g] ? 1u : 0u;
+					}
+				}
+				magAB |= pass ? (unsigned long long) (a | b) : 0ull;
+				magC |= pass ? (unsigned long long) c : 0ull;
+				magD |= pass ? (unsigned long long) d : 0ull;
+				rows_seen += pass ? 1u : 0u;
+#pragma unroll
+				for (int g = 0; g < G; g++)
+				{
+					acc.cnt[g] += hit[g];
+					sa_madd(acc.s[g][0], hit[g], a);
+					sa_madd(acc.s[g][1], hit[g], b);
+					sa_madd(acc.s[g][2], hit[g], c);
+					sa_madd(acc.s[g][3], hit[g], d);
+					sa_madd(acc.s[g][4], hit[g], rev);
+					sa_madd(acc.s[g][5], hit[g], chg);
+				}
 			}
-			sa_accumulate<G>(acc, slot, pass && slot >= 0, a[j], b[j], c[j], d[j], rev, chg);
+			/* this warp is done with the stage: one arrival per consumer warp frees it */
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(&empty_bar[s]);
 		}
 	}
 
-	/* overflow audit: bits(b) + bits(k-c) + bits(k2+d) must stay below 63, and so must
-	 * bits(largest accumulated value) + bits(rows this thread accumulated) */
+	/* overflow audit.  The masks OR every raw input of their column (a negative value sets bit 63,
+	 * fails the audit, and the host re-runs the pipeline on the generic kernel with its
+	 * per-operation checks).  |k - c| < 2^(max(bits c, bits k) + 1), likewise k2 + d; a product has
+	 * at most the sum of its factors' bit counts, and a thread's partial sum at most bits(value) +
+	 * bits(rows accumulated).  Everything must stay below 63 bits. */
 	{
-		int			bb = 64 - __clzll(magB),
-					bkc = 64 - __clzll(magKC),
-					bkd = 64 - __clzll(magKD);
-		int			bacc = 64 - __clzll(magAcc),
-					brows = 64 - __clzll((unsigned long long) rows_seen);
+		int			bab = 64 - __clzll(magAB),
+					bc = 64 - __clzll(magC),
+					bd = 64 - __clzll(magD);
+		unsigned long long ak = (unsigned long long) (P.k < 0 ? -P.k : P.k),
+					ak2 = (unsigned long long) (P.k2 < 0 ? -P.k2 : P.k2);
+		int			bk = 64 - __clzll(ak),
+					bk2 = 64 - __clzll(ak2);
+		int			brev = bab + (bc > bk ? bc : bk) + 1;
+		int			bchg = P.want_chg ? brev + (bd > bk2 ? bd : bk2) + 1 : 0;
+		int			brows = 32 - __clz(rows_seen);
+		int			worst = brev > bchg ? brev : bchg;
 
-		if (bb + bkc + bkd >= 63 || bacc + brows >= 63)
-			atomicExch(P.status, CBGPU_ERR_OVERFLOW);
+		if (bc > worst)
+			worst = bc;
+		if (bd > worst)
+			worst = bd;
+		if (worst + brows >= 63)
+			atomicExch(P.audit, 1);
 	}
 
 	/* CTA reduction: warp shuffle, then one 128-bit shared add per warp, group and sum */
-	const int	lane = threadIdx.x & 31;
-
 #pragma unroll
 	for (int g = 0; g < G; g++)
 	{
@@ -323,7 +415,7 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 __global__ void
 k_small_commit(const __grid_constant__ SmallAggParams P, int G, int nblocks)
 {
-	if (*P.retry)
+	if (*P.retry || *P.audit)
 		return;
 	for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nblocks * G; e += gridDim.x * blockDim.x)
 	{
@@ -385,6 +477,7 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 	if (!xm_decompile(p, &x) || x.depth < s->nkeys)
 		return CBGPU_OK;
 	memset(&P, 0, sizeof(P));
+	P.fspan = 0xFFFFFFFFu;		/* no qual: every value is inside the range */
 	/* quals: at most one CMP(int32 column, const) */
 	if (x.nsections > 1)
 		return CBGPU_OK;
@@ -397,9 +490,26 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 		if (x.sections[0].kind != 0 || !xm_is_cmp_const(&x, x.sections[0].node, &code, &col, &v) ||
 			!col_plain(p, col, 4) || v < INT32_MIN || v > INT32_MAX)
 			return CBGPU_OK;
+		/* fold the comparison into a closed int32 range (NE is not a range: generic kernel) */
+		int64_t		lo = INT32_MIN,
+					hi = INT32_MAX;
+
+		switch (code)
+		{
+			case CBP_EQ: lo = hi = v; break;
+			case CBP_LT: hi = v - 1; break;
+			case CBP_LE: hi = v; break;
+			case CBP_GT: lo = v + 1; break;
+			case CBP_GE: lo = v; break;
+			default: return CBGPU_OK;
+		}
+		if (lo > hi)
+			lo = hi = (int64_t) INT32_MAX + 1;	/* empty range: handled below */
+		if (lo > INT32_MAX || hi < INT32_MIN)
+			return CBGPU_OK;
 		P.fcol = (const int32_t *) p->cols[col].data;
-		P.fcode = code;
-		P.fconst = (int32_t) v;
+		P.flo = (int32_t) lo;
+		P.fspan = (uint32_t) (hi - lo);
 	}
 	/* keys: one-byte columns */
 	for (int i = 0; i < s->nkeys; i++)
@@ -514,35 +624,45 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 
 	/* retry flag: more distinct groups in one CTA than register slots -> wider kernel, then generic */
 	int		   *d_retry;
-	int			h_retry = 0;
-	int64_t		ntiles = (p->nrows + 2 * SA_THREADS - 1) / (2 * SA_THREADS);
-	int			blocks = ctx->sm_count * 2;
+	int			h_retry[2] = {0, 0};
+	int64_t		ntiles = (p->nrows + SA_TILE - 1) / SA_TILE;
+	int			blocks = ctx->sm_count;
+	const size_t smem = sizeof(SaStage) * SA_STAGES;
 
 	if (blocks > ntiles)
 		blocks = (int) ntiles;
-	CB_CUDA(ctx, cudaMallocAsync(&d_retry, sizeof(int), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&d_retry, 2 * sizeof(int), ctx->stream));
 	CB_CUDA(ctx, cudaMallocAsync(&P.scratch, (size_t) blocks * 8 * (SA_NSUM + 1) * 2 * sizeof(unsigned long long), ctx->stream));
 	CB_CUDA(ctx, cudaMallocAsync(&P.skeys, (size_t) blocks * 8 * sizeof(unsigned), ctx->stream));
 	P.retry = d_retry;
+	P.audit = d_retry + 1;
 	for (int attempt = 0; attempt < 2; attempt++)
 	{
 		int			G = attempt == 0 ? 4 : 8;
 
-		CB_CUDA(ctx, cudaMemsetAsync(d_retry, 0, sizeof(int), ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(d_retry, 0, 2 * sizeof(int), ctx->stream));
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
 		if (attempt == 0)
-			k_scan_agg_small<4><<<blocks, SA_THREADS, 0, ctx->stream>>>(P);
+		{
+			CB_CUDA(ctx, cudaFuncSetAttribute(k_scan_agg_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			k_scan_agg_small<4><<<blocks, SA_NCONS(4) + 32, smem, ctx->stream>>>(P);
+		}
 		else
-			k_scan_agg_small<8><<<blocks, SA_THREADS, 0, ctx->stream>>>(P);
+		{
+			CB_CUDA(ctx, cudaFuncSetAttribute(k_scan_agg_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			k_scan_agg_small<8><<<blocks, SA_NCONS(8) + 32, smem, ctx->stream>>>(P);
+		}
 		CB_LAUNCHED(ctx, "k_scan_agg_small");
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
 		ctx->kernel_timed = true;
 		ctx->last_kernel_name = attempt == 0 ? "k_scan_agg_small<4>" : "k_scan_agg_small<8>";
 		k_small_commit<<<1, 256, 0, ctx->stream>>>(P, G, blocks);
 		CB_LAUNCHED(ctx, "k_small_commit");
-		CB_CUDA(ctx, cudaMemcpyAsync(&h_retry, d_retry, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		CB_CUDA(ctx, cudaMemcpyAsync(h_retry, d_retry, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		if (!h_retry)
+		if (h_retry[1])
+			break;				/* values too wide for the 64-bit fast path: generic kernel, nothing was committed */
+		if (!h_retry[0])
 		{
 			*handled = true;
 			break;
