@@ -96,13 +96,13 @@ cbgpu_agg_create(cbgpu_ctx *ctx, int32_t nkeys, int32_t naccs, const int32_t *ac
 	for (int a = 0; a < naccs; a++)
 		t->kinds[a] = acc_kinds ? acc_kinds[a] : CBP_ACC_SUM_INT;
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
-	CB_CUDA(ctx, cudaMalloc(&t->d.state, cap * sizeof(int32_t)));
-	CB_CUDA(ctx, cudaMalloc(&t->d.hash, cap * sizeof(uint32_t)));
-	CB_CUDA(ctx, cudaMalloc(&t->d.keys, cap * sizeof(int64_t) * (nkeys ? nkeys : 1)));
-	CB_CUDA(ctx, cudaMalloc(&t->d.keynull, cap * sizeof(uint32_t)));
-	CB_CUDA(ctx, cudaMalloc(&t->d.n, cap * sizeof(int64_t) * (naccs ? naccs : 1)));
-	CB_CUDA(ctx, cudaMalloc(&t->d.sum, cap * 2 * sizeof(unsigned long long) * (naccs ? naccs : 1)));
-	CB_CUDA(ctx, cudaMalloc(&t->d.ngroups, sizeof(int32_t) * 2));
+	CB_CUDA(ctx, cudaMallocAsync(&t->d.state, cap * sizeof(int32_t), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&t->d.hash, cap * sizeof(uint32_t), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&t->d.keys, cap * sizeof(int64_t) * (nkeys ? nkeys : 1), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&t->d.keynull, cap * sizeof(uint32_t), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&t->d.n, cap * sizeof(int64_t) * (naccs ? naccs : 1), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&t->d.sum, cap * 2 * sizeof(unsigned long long) * (naccs ? naccs : 1), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&t->d.ngroups, sizeof(int32_t) * 2, ctx->stream));
 	t->d.full = t->d.ngroups + 1;
 	*out = t;
 	return cbgpu_agg_reset(t);
@@ -114,14 +114,13 @@ cbgpu_agg_free(cbgpu_aggtable *t)
 	if (!t)
 		return;
 	cudaSetDevice(t->ctx->device);
-	cudaStreamSynchronize(t->ctx->stream);
-	cudaFree(t->d.state);
-	cudaFree(t->d.hash);
-	cudaFree(t->d.keys);
-	cudaFree(t->d.keynull);
-	cudaFree(t->d.n);
-	cudaFree(t->d.sum);
-	cudaFree(t->d.ngroups);
+	cudaFreeAsync(t->d.state, t->ctx->stream);
+	cudaFreeAsync(t->d.hash, t->ctx->stream);
+	cudaFreeAsync(t->d.keys, t->ctx->stream);
+	cudaFreeAsync(t->d.keynull, t->ctx->stream);
+	cudaFreeAsync(t->d.n, t->ctx->stream);
+	cudaFreeAsync(t->d.sum, t->ctx->stream);
+	cudaFreeAsync(t->d.ngroups, t->ctx->stream);
 	free(t);
 }
 
@@ -334,7 +333,7 @@ cbgpu_agg_to_rel(cbgpu_aggtable *t, const int32_t *keytypes, cbgpu_rel **out)
 		o.keytype[k] = keytypes[k];
 		if (h_flag && ng > 0)
 		{
-			CB_CUDA(ctx, cudaMalloc(&rel->nulls[k], (size_t) ng));
+			CB_CUDA(ctx, cudaMallocAsync(&rel->nulls[k], (size_t) ng, ctx->stream));
 			o.keynulls[k] = rel->nulls[k];
 		}
 	}

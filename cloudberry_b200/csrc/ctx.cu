@@ -34,6 +34,15 @@ cbgpu_ctx_create(int device, cbgpu_ctx **out)
 	CB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
 	ctx->sm_count = prop.multiProcessorCount;
 	CB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	{
+		/* every device allocation of the library is stream-ordered (cudaMallocAsync); keep freed
+		 * blocks cached in the pool so per-query hash tables / result buffers cost no driver call */
+		cudaMemPool_t pool;
+		unsigned long long keep = ~0ull;
+
+		CB_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
+		CB_CUDA(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	}
 	CB_CUDA(ctx, cudaEventCreate(&ctx->ev_t0));
 	CB_CUDA(ctx, cudaEventCreate(&ctx->ev_t1));
 	CB_CUDA(ctx, cudaEventCreate(&ctx->ev_k0));
@@ -235,7 +244,7 @@ cbgpu_rel_create(cbgpu_ctx *ctx, int64_t nrows, int32_t ncols, const int32_t *ty
 		r->dscales[i] = dscales ? dscales[i] : 0;
 		/* pad so 16-byte vector loads and TMA bulk copies may read a whole final vector */
 		bytes = (bytes + 255) & ~(size_t) 255;
-		CB_CUDA(ctx, cudaMalloc(&r->data[i], bytes));
+		CB_CUDA(ctx, cudaMallocAsync(&r->data[i], bytes, ctx->stream));
 		r->owns[i] = true;
 	}
 	*out = r;
@@ -247,19 +256,20 @@ cbgpu_rel_free(cbgpu_rel *rel)
 {
 	if (!rel)
 		return;
+	/* stream-ordered frees: memory returns to the context's pool once the work queued before this
+	 * point has drained; no host synchronisation */
 	cudaSetDevice(rel->ctx->device);
-	cudaStreamSynchronize(rel->ctx->stream);
 	for (int i = 0; i < rel->ncols; i++)
 	{
 		if (rel->owns[i] && rel->data[i])
-			cudaFree(rel->data[i]);
+			cudaFreeAsync(rel->data[i], rel->ctx->stream);
 		if (rel->nulls[i])
-			cudaFree(rel->nulls[i]);
+			cudaFreeAsync(rel->nulls[i], rel->ctx->stream);
 		if (rel->dict_hash[i] && rel->dict_n[i] >= 0)
-			cudaFree(rel->dict_hash[i]);
+			cudaFreeAsync(rel->dict_hash[i], rel->ctx->stream);
 	}
 	if (rel->visimap)
-		cudaFree(rel->visimap);
+		cudaFreeAsync(rel->visimap, rel->ctx->stream);
 	free(rel);
 }
 
@@ -301,13 +311,12 @@ cbgpu_rel_load_column(cbgpu_rel *rel, int32_t col, const void *host, const uint8
 	if (nulls)
 	{
 		if (!rel->nulls[col])
-			CB_CUDA(ctx, cudaMalloc(&rel->nulls[col], (size_t) rel->capacity));
+			CB_CUDA(ctx, cudaMallocAsync(&rel->nulls[col], (size_t) rel->capacity, ctx->stream));
 		CB_CUDA(ctx, cudaMemcpyAsync(rel->nulls[col], nulls, (size_t) rel->nrows, cudaMemcpyHostToDevice, ctx->stream));
 	}
 	else if (rel->nulls[col])
 	{
-		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		cudaFree(rel->nulls[col]);
+		cudaFreeAsync(rel->nulls[col], ctx->stream);
 		rel->nulls[col] = NULL;
 	}
 	return CBGPU_OK;
@@ -348,14 +357,13 @@ cbgpu_rel_set_visimap(cbgpu_rel *rel, const uint8_t *bits)
 	{
 		if (rel->visimap)
 		{
-			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-			cudaFree(rel->visimap);
+			cudaFreeAsync(rel->visimap, ctx->stream);
 			rel->visimap = NULL;
 		}
 		return CBGPU_OK;
 	}
 	if (!rel->visimap)
-		CB_CUDA(ctx, cudaMalloc(&rel->visimap, ((bytes + 255) & ~(size_t) 255) + 256));
+		CB_CUDA(ctx, cudaMallocAsync(&rel->visimap, ((bytes + 255) & ~(size_t) 255) + 256, ctx->stream));
 	CB_CUDA(ctx, cudaMemcpyAsync(rel->visimap, bits, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	return CBGPU_OK;
 }
@@ -369,10 +377,9 @@ cbgpu_rel_set_dict_hash(cbgpu_rel *rel, int32_t col, const uint32_t *hashes, int
 		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_set_dict_hash: bad argument%s %lld", "", col);
 	if (rel->dict_hash[col])
 	{
-		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		cudaFree(rel->dict_hash[col]);
+		cudaFreeAsync(rel->dict_hash[col], ctx->stream);
 	}
-	CB_CUDA(ctx, cudaMalloc(&rel->dict_hash[col], (size_t) n * sizeof(uint32_t)));
+	CB_CUDA(ctx, cudaMallocAsync(&rel->dict_hash[col], (size_t) n * sizeof(uint32_t), ctx->stream));
 	CB_CUDA(ctx, cudaMemcpyAsync(rel->dict_hash[col], hashes, (size_t) n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	rel->dict_n[col] = n;
@@ -417,7 +424,7 @@ extern "C" int
 cbgpu_dev_alloc(cbgpu_ctx *ctx, size_t bytes, void **dev)
 {
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
-	CB_CUDA(ctx, cudaMalloc(dev, bytes ? bytes : 8));
+	CB_CUDA(ctx, cudaMallocAsync(dev, bytes ? bytes : 8, ctx->stream));
 	CB_CUDA(ctx, cudaMemsetAsync(*dev, 0, bytes ? bytes : 8, ctx->stream));
 	return CBGPU_OK;
 }
@@ -444,8 +451,7 @@ cbgpu_dev_free(cbgpu_ctx *ctx, void *dev)
 	if (!dev)
 		return;
 	cudaSetDevice(ctx->device);
-	cudaStreamSynchronize(ctx->stream);
-	cudaFree(dev);
+	cudaFreeAsync(dev, ctx->stream);
 }
 
 extern "C" int
@@ -457,7 +463,7 @@ cbgpu_rel_add_nullmap(cbgpu_rel *rel, int32_t col)
 		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_add_nullmap: bad column%s %lld", "", col);
 	if (rel->nulls[col])
 		return CBGPU_OK;
-	CB_CUDA(ctx, cudaMalloc(&rel->nulls[col], (size_t) (rel->capacity ? rel->capacity : 1)));
+	CB_CUDA(ctx, cudaMallocAsync(&rel->nulls[col], (size_t) (rel->capacity ? rel->capacity : 1), ctx->stream));
 	CB_CUDA(ctx, cudaMemsetAsync(rel->nulls[col], 0, (size_t) (rel->capacity ? rel->capacity : 1), ctx->stream));
 	return CBGPU_OK;
 }

@@ -151,8 +151,8 @@ cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t
 		ht->d.keytype[k] = inner->types[c];
 	}
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
-	CB_CUDA(ctx, cudaMalloc(&ht->d.slots, (size_t) nslots * sizeof(unsigned long long)));
-	CB_CUDA(ctx, cudaMalloc(&ht->d_flags, 2 * sizeof(int)));
+	CB_CUDA(ctx, cudaMallocAsync(&ht->d.slots, (size_t) nslots * sizeof(unsigned long long), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&ht->d_flags, 2 * sizeof(int), ctx->stream));
 	CB_CUDA(ctx, cudaMemsetAsync(ht->d_flags, 0, 2 * sizeof(int), ctx->stream));
 	int			blocks = (int) ((nslots + 255) / 256);
 
@@ -185,9 +185,8 @@ cbgpu_ht_free(cbgpu_hashtable *ht)
 	if (!ht)
 		return;
 	cudaSetDevice(ht->ctx->device);
-	cudaStreamSynchronize(ht->ctx->stream);
-	cudaFree(ht->d.slots);
-	cudaFree(ht->d_flags);
+	cudaFreeAsync(ht->d.slots, ht->ctx->stream);
+	cudaFreeAsync(ht->d_flags, ht->ctx->stream);
 	free(ht);
 }
 

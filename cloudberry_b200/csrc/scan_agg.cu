@@ -9,15 +9,20 @@
  * 2645,2567 - here exact scaled-integer products), LookupTupleHashEntry (backend/executor/
  * execGrouping.c:317) and the transition functions (numeric_avg_accum, int8inc: nodeAgg.c:856).
  *
- * Shape: persistent grid (a multiple of the SM count), each thread streams rows with 16-byte
- * vectorised loads (two rows per load), keeps per-group accumulators in registers (G <= 4 or 8
- * groups, slot ids from a per-CTA shared-memory key table), reduces per CTA with warp shuffles and
- * commits each group once per CTA into the global aggregate table with 128-bit exact adds.
- * HBM-bound: algorithmic bytes/row = sum of the projected column widths (Q1: 38 B/row).
+ * Shape: one persistent CTA per SM.  A producer warp streams the projected columns into a
+ * shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP / SYNCS), several
+ * tiles ahead of the consumers, so the HBM pipe stays full whatever the consumers do.  Consumer
+ * warps read rows from shared memory, evaluate the qual and the arithmetic, and accumulate per
+ * group in registers (G <= 4 or 8 slots; slot keys live in a per-CTA shared table, cached in
+ * registers).  Per-CTA totals are reduced with shuffles and committed once per CTA and group into
+ * the global aggregate table with exact 128-bit adds.
+ * HBM-bound by design: algorithmic bytes/row = sum of the projected column widths (Q1: 38 B/row).
  *
- * Exactness: per-row products are 64-bit; the kernel ORs the magnitudes of the factors it
- * multiplies and of the values it accumulates, and reports CBGPU_ERR_OVERFLOW (never a wrapped
- * sum) if a product or a per-thread partial sum could have left 63 bits.  Group totals are 128-bit.
+ * Exactness: per-row products and per-thread partial sums are 64-bit.  The kernel ORs the raw
+ * input magnitudes per column and audits, from those bit counts, that no product or partial sum
+ * could have left 63 bits (and, in the NARROW variant, that the 32-bit multiply-accumulate form was
+ * valid).  A failed audit commits nothing; the host re-runs the next wider variant and finally the
+ * generic kernel, whose every operation is overflow-checked.  Group totals are 128-bit.
  */
 #include "pipeline.cuh"
 #include "xmatch.h"
@@ -30,7 +35,7 @@ struct SmallAggParams
 	const long long *colA;		/* optional plain column                                              */
 	const long long *colB;		/* b of b*(k-c)                                                       */
 	const long long *colC;
-	const long long *colD;		/* optional: d of (k2+d)                                              */
+	const long long *colD;		/* optional: d of (k2+d), or a second plain column                    */
 	long long	k,
 				k2;
 	const int32_t *fcol;		/* optional filter column (int4/date)                                 */
@@ -49,8 +54,8 @@ struct SmallAggParams
 	int32_t		want_chg;		/* the b*(k-c)*(k2+d) sum is requested                                */
 	int		   *status;
 	int		   *retry;			/* set when a CTA saw more than G distinct groups                     */
-	int		   *audit;			/* set when the 64-bit fast arithmetic could have overflowed          */
-	/* per-CTA partial results, committed by k_small_commit once no CTA asked for a retry */
+	int		   *audit;			/* set when this variant's arithmetic could have overflowed           */
+	/* per-CTA partial results, committed by k_small_commit once no CTA raised retry / audit */
 	unsigned long long *scratch;	/* [grid][G][SA_NSUM + 1][2]                                      */
 	unsigned   *skeys;			/* [grid][G]                                                          */
 };
@@ -63,23 +68,29 @@ struct SaAcc
 };
 
 /*
- * acc += hit * v with hit in {0, 1}: one IMAD.WIDE.U32 (hit * v.lo + acc, 64-bit add with carry)
- * and one IMAD (hit * v.hi + acc.hi).  Two fma-pipe instructions per 64-bit accumulator and row,
- * no compare / select / predicate per accumulator; two's complement makes it exact for negative v.
+ * acc += hit * v with hit in {0, 1}.
+ * Wide form: IMAD.WIDE.U32 (hit * v.lo + acc, a 64-bit add with carry) + IMAD (hit * v.hi + acc.hi):
+ * two fma-pipe instructions per accumulator and row, no compare / select per accumulator; two's
+ * complement makes it exact for negative v.  Narrow form (v known to fit 32 unsigned bits, audited
+ * after the fact): the IMAD.WIDE.U32 alone.
  */
+template <bool NARROW>
 __device__ __forceinline__ void
 sa_madd(long long &acc, unsigned hit, long long v)
 {
-	asm("{\n\t"
-		".reg .b32 vlo, vhi, tlo, thi;\n\t"
-		".reg .b64 t;\n\t"
-		"mov.b64 {vlo, vhi}, %2;\n\t"
-		"mad.wide.u32 t, %1, vlo, %0;\n\t"
-		"mov.b64 {tlo, thi}, t;\n\t"
-		"mad.lo.u32 thi, %1, vhi, thi;\n\t"
-		"mov.b64 %0, {tlo, thi};\n\t"
-		"}"
-		: "+l"(acc) : "r"(hit), "l"(v));
+	if (NARROW)
+		asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(hit), "r"((unsigned) v));
+	else
+		asm("{\n\t"
+			".reg .b32 vlo, vhi, tlo, thi;\n\t"
+			".reg .b64 t;\n\t"
+			"mov.b64 {vlo, vhi}, %2;\n\t"
+			"mad.wide.u32 t, %1, vlo, %0;\n\t"
+			"mov.b64 {tlo, thi}, t;\n\t"
+			"mad.lo.u32 thi, %1, vhi, thi;\n\t"
+			"mov.b64 %0, {tlo, thi};\n\t"
+			"}"
+			: "+l"(acc) : "r"(hit), "l"(v));
 }
 
 /* slow path, once per new group per thread: claim a slot in the CTA's shared key table */
@@ -166,15 +177,112 @@ struct __align__(128) SaStage
 	uint8_t		k1[SA_TILE];
 };
 
+/* per-thread consumer state */
+template <int G>
+struct SaState
+{
+	SaAcc<G>	acc;
+	unsigned	gk[G];			/* cached copy of the CTA's group key table                           */
+	unsigned long long magAB,	/* OR of the raw a / b, c and d values seen (sign bits included)      */
+				magC, magD;
+	unsigned	rows_seen;
+};
+
+/*
+ * one row.  MASK: which of the six sums are wanted (bit s = sum s; the host sets bit 0 / bits 3,5
+ * only when column a / d exists).  SHAPE: which optional inputs exist, fixed at compile time so
+ * the row loop carries no per-row presence tests: 1 = qual column + two key columns (the Q1 shape),
+ * 2 = qual column, no keys (Q6 shape), 0 = decided at run time.  CHECK: bounds / visimap tests
+ * (last tile, relations with a visibility map).
+ */
+template <int G, int MASK, bool NARROW, int SHAPE, bool CHECK>
+__device__ __forceinline__ void
+sa_row(const SmallAggParams &P, SaState<G> &S, unsigned *gkeys, const SaStage *st, int r, int rows, int64_t r0)
+{
+	const bool	hasF = SHAPE ? true : P.fcol != NULL;
+	const bool	hasK0 = SHAPE == 1 ? true : (SHAPE == 2 ? false : P.key0 != NULL);
+	const bool	hasK1 = SHAPE == 1 ? true : (SHAPE == 2 ? false : P.key1 != NULL);
+	bool		pass = true;
+	long long	a = (MASK & 1) ? st->a[r] : 0;
+	long long	b = st->b[r];
+	long long	c = st->c[r];
+	long long	d = (MASK & 0x28) ? st->d[r] : 0;
+	int32_t		f = hasF ? st->f[r] : P.flo;
+	unsigned	k0 = hasK0 ? st->k0[r] : 0;
+	unsigned	k1 = hasK1 ? st->k1[r] : 0;
+
+	if (CHECK)
+	{
+		pass = r < rows;
+		if (!pass)
+			a = b = c = d = 0;	/* stale shared memory must not reach the audit masks */
+		if (P.visimap && pass)
+		{
+			/* AppendOnlyVisimap_IsVisible (access/appendonly/appendonly_visimap.c:198) */
+			const int64_t gr = r0 + r;
+
+			pass = (__ldg(P.visimap + (gr >> 3)) >> (gr & 7)) & 1;
+		}
+	}
+	/* the qual as a closed range (EQ/LT/LE/GT/GE folded by the host): one unsigned compare */
+	pass = pass && ((unsigned) (f - P.flo) <= P.fspan);
+	long long	kc = P.k - c;
+	long long	rev = b * kc;
+	long long	chg = (MASK & 0x20) ? rev * (P.k2 + d) : 0;
+	/* the key carries a valid bit (0 = empty slot); a row that fails the qual gets a key no slot holds */
+	unsigned	key = pass ? (0x10000u | k0 | (k1 << 8)) : 0xFFFFFFFFu;
+	unsigned	hit[G];
+	unsigned	known = 0;
+
+#pragma unroll
+	for (int g = 0; g < G; g++)
+	{
+		hit[g] = key == S.gk[g] ? 1u : 0u;
+		known |= hit[g];
+	}
+	if (pass && !known)
+	{
+		sa_insert_key<G>(gkeys, key, P.retry);
+#pragma unroll
+		for (int g = 0; g < G; g++)
+		{
+			S.gk[g] = ((volatile unsigned *) gkeys)[g];
+			hit[g] = key == S.gk[g] ? 1u : 0u;
+		}
+	}
+	/* audit masks take every in-range row (also rows the qual rejects: only more conservative) */
+	S.magAB |= (unsigned long long) (a | b);
+	S.magC |= (unsigned long long) c;
+	S.magD |= (unsigned long long) d;
+	S.rows_seen += pass ? 1u : 0u;
+#pragma unroll
+	for (int g = 0; g < G; g++)
+	{
+		S.acc.cnt[g] += hit[g];
+		if (MASK & 0x01)
+			sa_madd<NARROW>(S.acc.s[g][0], hit[g], a);
+		if (MASK & 0x02)
+			sa_madd<NARROW>(S.acc.s[g][1], hit[g], b);
+		if (MASK & 0x04)
+			sa_madd<NARROW>(S.acc.s[g][2], hit[g], c);
+		if (MASK & 0x08)
+			sa_madd<NARROW>(S.acc.s[g][3], hit[g], d);
+		if (MASK & 0x10)
+			sa_madd<NARROW>(S.acc.s[g][4], hit[g], rev);
+		if (MASK & 0x20)
+			sa_madd<false>(S.acc.s[g][5], hit[g], chg);
+	}
+}
+
 /*
  * One persistent CTA per SM.  Warp 0 is the producer: for each tile it arms the stage's "full"
  * mbarrier with the byte count and issues one TMA bulk copy per projected column
- * (cp.async.bulk global -> shared), up to SA_STAGES tiles ahead, so ~150 KB of loads are in flight
- * per SM regardless of what the consumers are doing.  The 16 consumer warps wait on "full", read
+ * (cp.async.bulk global -> shared), up to SA_STAGES tiles ahead, so ~170 KB of loads are in flight
+ * per SM regardless of what the consumers are doing.  The consumer warps wait on "full", read
  * their rows from shared memory (row-per-thread, conflict free), evaluate the qual and the
  * arithmetic, accumulate per group in registers, and release the stage through "empty".
  */
-template <int G>
+template <int G, int MASK, bool NARROW, int SHAPE>
 __global__ void __launch_bounds__(SA_NCONS(G) + 32, 1)
 k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 {
@@ -184,13 +292,8 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 	__shared__ uint64_t empty_bar[SA_STAGES];
 	__shared__ unsigned gkeys[G];
 	__shared__ unsigned long long red[G][SA_NSUM + 1][2];	/* 128-bit CTA totals                     */
-	SaAcc<G>	acc;
-	unsigned long long magAB = 0,	/* OR of the raw a / b, c and d values seen (sign bits included)  */
-				magC = 0,
-				magD = 0;
-	unsigned	rows_seen = 0;
-	unsigned	gk[G];			/* this thread's cached copy of the CTA's group key table             */
 	constexpr int NCONS = SA_NCONS(G);
+	SaState<G>	S;
 	const int	warp = threadIdx.x >> 5;
 	const int	lane = threadIdx.x & 31;
 	const int64_t ntiles = (P.nrows + SA_TILE - 1) / SA_TILE;
@@ -208,14 +311,16 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 		gkeys[threadIdx.x] = 0;
 	for (int i = threadIdx.x; i < G * (SA_NSUM + 1) * 2; i += blockDim.x)
 		(&red[0][0][0])[i] = 0;
+	S.magAB = S.magC = S.magD = 0;
+	S.rows_seen = 0;
 #pragma unroll
 	for (int g = 0; g < G; g++)
 	{
-		acc.cnt[g] = 0;
-		gk[g] = 0;
+		S.acc.cnt[g] = 0;
+		S.gk[g] = 0;
 #pragma unroll
 		for (int s = 0; s < SA_NSUM; s++)
-			acc.s[g][s] = 0;
+			S.acc.s[g][s] = 0;
 	}
 	__syncthreads();
 
@@ -237,7 +342,9 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 				const unsigned b8 = (unsigned) (rows * 8 + 15) & ~15u;
 				const unsigned b4 = (unsigned) (rows * 4 + 15) & ~15u;
 				const unsigned b1 = (unsigned) (rows + 15) & ~15u;
-				unsigned	total = 2 * b8 + (P.colA ? b8 : 0) + (P.colD ? b8 : 0) + (P.fcol ? b4 : 0) +
+				const bool	wantA = (MASK & 1) != 0;
+				const bool	wantD = (MASK & 0x28) != 0;
+				unsigned	total = 2 * b8 + (wantA ? b8 : 0) + (wantD ? b8 : 0) + (P.fcol ? b4 : 0) +
 					(P.key0 ? b1 : 0) + (P.key1 ? b1 : 0);
 				SaStage    *st = &stages[s];
 
@@ -245,9 +352,9 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 				mbar_expect_tx(&full_bar[s], total);
 				tma_load_1d(st->b, P.colB + r0, b8, &full_bar[s]);
 				tma_load_1d(st->c, P.colC + r0, b8, &full_bar[s]);
-				if (P.colA)
+				if (wantA)
 					tma_load_1d(st->a, P.colA + r0, b8, &full_bar[s]);
-				if (P.colD)
+				if (wantD)
 					tma_load_1d(st->d, P.colD + r0, b8, &full_bar[s]);
 				if (P.fcol)
 					tma_load_1d(st->f, P.fcol + r0, b4, &full_bar[s]);
@@ -273,68 +380,17 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 			const SaStage *st = &stages[s];
 
 			mbar_wait(&full_bar[s], ph);
-#pragma unroll
-			for (int j = 0; j < SA_TILE / NCONS; j++)
+			if (rows == SA_TILE && !P.visimap)
 			{
-				const int	r = ct + j * NCONS;
-				bool		pass = r < rows;
-				long long	a = P.colA ? st->a[r] : 0;
-				long long	b = st->b[r];
-				long long	c = st->c[r];
-				long long	d = P.colD ? st->d[r] : 0;
-				int32_t		f = P.fcol ? st->f[r] : P.flo;
-				unsigned	k0 = P.key0 ? st->k0[r] : 0;
-				unsigned	k1 = P.key1 ? st->k1[r] : 0;
-
-				if (P.visimap && pass)
-				{
-					/* AppendOnlyVisimap_IsVisible (access/appendonly/appendonly_visimap.c:198) */
-					const int64_t gr = r0 + r;
-
-					pass = (__ldg(P.visimap + (gr >> 3)) >> (gr & 7)) & 1;
-				}
-				/* the qual as a closed range (EQ/LT/LE/GT/GE folded by the host): one unsigned compare */
-				pass = pass && ((unsigned) (f - P.flo) <= P.fspan);
-				long long	kc = P.k - c;
-				long long	rev = b * kc;
-				long long	chg = P.want_chg ? rev * (P.k2 + d) : 0;
-				/* the key carries a valid bit (0 = empty slot); a row that fails the qual gets a key
-				 * no slot can hold */
-				unsigned	key = pass ? (0x10000u | k0 | (k1 << 8)) : 0xFFFFFFFFu;
-				unsigned	hit[G];
-				unsigned	known = 0;
-
 #pragma unroll
-				for (int g = 0; g < G; g++)
-				{
-					hit[g] = key == gk[g] ? 1u : 0u;
-					known |= hit[g];
-				}
-				if (pass && !known)
-				{
-					sa_insert_key<G>(gkeys, key, P.retry);
+				for (int j = 0; j < SA_TILE / NCONS; j++)
+					sa_row<G, MASK, NARROW, SHAPE, false>(P, S, gkeys, st, ct + j * NCONS, rows, r0);
+			}
+			else
+			{
 #pragma unroll
-					for (int g = 0; g < G; g++)
-					{
-						gk[g] = ((volatile unsigned *) gkeys)[g];
-						hit[g] = key == gk[g] ? 1u : 0u;
-					}
-				}
-				magAB |= pass ? (unsigned long long) (a | b) : 0ull;
-				magC |= pass ? (unsigned long long) c : 0ull;
-				magD |= pass ? (unsigned long long) d : 0ull;
-				rows_seen += pass ? 1u : 0u;
-#pragma unroll
-				for (int g = 0; g < G; g++)
-				{
-					acc.cnt[g] += hit[g];
-					sa_madd(acc.s[g][0], hit[g], a);
-					sa_madd(acc.s[g][1], hit[g], b);
-					sa_madd(acc.s[g][2], hit[g], c);
-					sa_madd(acc.s[g][3], hit[g], d);
-					sa_madd(acc.s[g][4], hit[g], rev);
-					sa_madd(acc.s[g][5], hit[g], chg);
-				}
+				for (int j = 0; j < SA_TILE / NCONS; j++)
+					sa_row<G, MASK, NARROW, SHAPE, true>(P, S, gkeys, st, ct + j * NCONS, rows, r0);
 			}
 			/* this warp is done with the stage: one arrival per consumer warp frees it */
 			__syncwarp();
@@ -343,22 +399,22 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 		}
 	}
 
-	/* overflow audit.  The masks OR every raw input of their column (a negative value sets bit 63,
-	 * fails the audit, and the host re-runs the pipeline on the generic kernel with its
-	 * per-operation checks).  |k - c| < 2^(max(bits c, bits k) + 1), likewise k2 + d; a product has
-	 * at most the sum of its factors' bit counts, and a thread's partial sum at most bits(value) +
-	 * bits(rows accumulated).  Everything must stay below 63 bits. */
+	/* overflow audit.  The masks OR every raw input of their column (a negative value sets bit 63 and
+	 * fails the audit).  |k - c| < 2^(max(bits c, bits k) + 1), likewise k2 + d; a product has at most
+	 * the sum of its factors' bit counts, a thread's partial sum at most bits(value) + bits(rows
+	 * accumulated); all must stay below 63 bits.  NARROW additionally needs every single-IMAD
+	 * operand (a, b, c, d, b*(k-c)) below 2^32. */
 	{
-		int			bab = 64 - __clzll(magAB),
-					bc = 64 - __clzll(magC),
-					bd = 64 - __clzll(magD);
+		int			bab = 64 - __clzll(S.magAB),
+					bc = 64 - __clzll(S.magC),
+					bd = 64 - __clzll(S.magD);
 		unsigned long long ak = (unsigned long long) (P.k < 0 ? -P.k : P.k),
 					ak2 = (unsigned long long) (P.k2 < 0 ? -P.k2 : P.k2);
 		int			bk = 64 - __clzll(ak),
 					bk2 = 64 - __clzll(ak2);
 		int			brev = bab + (bc > bk ? bc : bk) + 1;
-		int			bchg = P.want_chg ? brev + (bd > bk2 ? bd : bk2) + 1 : 0;
-		int			brows = 32 - __clz(rows_seen);
+		int			bchg = (MASK & 0x20) ? brev + (bd > bk2 ? bd : bk2) + 1 : 0;
+		int			brows = 32 - __clz(S.rows_seen);
 		int			worst = brev > bchg ? brev : bchg;
 
 		if (bc > worst)
@@ -366,6 +422,11 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 		if (bd > worst)
 			worst = bd;
 		if (worst + brows >= 63)
+			atomicExch(P.audit, 1);
+		if (NARROW && (bab > 32 || bc > 32 || bd > 32 || ((MASK & 0x10) && brev > 32)))
+			atomicExch(P.audit, 1);
+		/* negative inputs: the unsigned narrow form and the bit-count bounds do not hold */
+		if ((long long) (S.magAB | S.magC | S.magD) < 0)
 			atomicExch(P.audit, 1);
 	}
 
@@ -376,8 +437,10 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 #pragma unroll
 		for (int s = 0; s <= SA_NSUM; s++)
 		{
-			long long	v = s < SA_NSUM ? acc.s[g][s < SA_NSUM ? s : 0] : (long long) acc.cnt[g];
+			long long	v = s < SA_NSUM ? S.acc.s[g][s < SA_NSUM ? s : 0] : (long long) S.acc.cnt[g];
 
+			if (s < SA_NSUM && !((MASK >> s) & 1))
+				continue;
 			/* per-thread partials fit 63 bits (audited above); 32 of them need up to 68 bits, so
 			 * reduce (lo, hi) pairs */
 			unsigned long long lo = (unsigned long long) v;
@@ -622,53 +685,107 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 
 	P.want_chg = have_chg;
 
-	/* retry flag: more distinct groups in one CTA than register slots -> wider kernel, then generic */
-	int		   *d_retry;
-	int			h_retry[2] = {0, 0};
+	/* which of the six sums does the plan need? */
+	int			need = 0;
+
+	for (int a = 0; a < s->naccs; a++)
+		if (P.accsum[a] >= 0)
+			need |= 1 << P.accsum[a];
+	if (have_chg)
+		need |= 0x20;
+
+	/* instantiated sum masks, cheapest first: b*(k-c) alone (Q3/Q5/Q10-style revenue), the Q1 set
+	 * (a, b, c, rev, chg), everything.  A mask that reads column a / d needs that column. */
+	static const int masks[3] = {0x10, 0x37, 0x3f};
+	int			mask = -1;
+
+	for (int i = 0; i < 3 && mask < 0; i++)
+		if ((need & ~masks[i]) == 0 && (!(masks[i] & 0x01) || P.colA) && (!(masks[i] & 0x28) || P.colD))
+			mask = masks[i];
+	if (mask < 0)
+		return CBGPU_OK;		/* e.g. a and d both absent but a plain sum wanted elsewhere: generic kernel */
+	const int	shape = (P.fcol && P.key0 && P.key1) ? 1 : ((P.fcol && !P.key0 && !P.key1) ? 2 : 0);
+
+	int		   *d_flags;
+	int			h_flags[2] = {0, 0};
 	int64_t		ntiles = (p->nrows + SA_TILE - 1) / SA_TILE;
 	int			blocks = ctx->sm_count;
 	const size_t smem = sizeof(SaStage) * SA_STAGES;
+	int			G = 4;
+	bool		narrow = true;
 
 	if (blocks > ntiles)
 		blocks = (int) ntiles;
-	CB_CUDA(ctx, cudaMallocAsync(&d_retry, 2 * sizeof(int), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&d_flags, 2 * sizeof(int), ctx->stream));
 	CB_CUDA(ctx, cudaMallocAsync(&P.scratch, (size_t) blocks * 8 * (SA_NSUM + 1) * 2 * sizeof(unsigned long long), ctx->stream));
 	CB_CUDA(ctx, cudaMallocAsync(&P.skeys, (size_t) blocks * 8 * sizeof(unsigned), ctx->stream));
-	P.retry = d_retry;
-	P.audit = d_retry + 1;
-	for (int attempt = 0; attempt < 2; attempt++)
+	P.retry = d_flags;
+	P.audit = d_flags + 1;
+	/* ladder: (4 groups, narrow) -> wider arithmetic on a failed audit, 8 groups when a CTA saw more
+	 * than 4 keys -> the generic kernel.  A failed attempt commits nothing. */
+	for (;;)
 	{
-		int			G = attempt == 0 ? 4 : 8;
-
-		CB_CUDA(ctx, cudaMemsetAsync(d_retry, 0, 2 * sizeof(int), ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream));
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
-		if (attempt == 0)
+#define SA_LAUNCH(GG, MM, NN, SS) \
+		do { \
+			static bool attr_done = false; \
+			if (!attr_done) \
+			{ \
+				CB_CUDA(ctx, cudaFuncSetAttribute(k_scan_agg_small<GG, MM, NN, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+				attr_done = true; \
+			} \
+			k_scan_agg_small<GG, MM, NN, SS><<<blocks, SA_NCONS(GG) + 32, smem, ctx->stream>>>(P); \
+			ctx->last_kernel_name = "k_scan_agg_small<" #GG "," #MM "," #NN "," #SS ">"; \
+		} while (0)
+#define SA_PICK_SHAPE(MM, NN) \
+		do { \
+			if (shape == 1) SA_LAUNCH(4, MM, NN, 1); \
+			else if (shape == 2) SA_LAUNCH(4, MM, NN, 2); \
+			else SA_LAUNCH(4, MM, NN, 0); \
+		} while (0)
+#define SA_PICK(NN) \
+		do { \
+			if (mask == 0x10) SA_PICK_SHAPE(0x10, NN); \
+			else if (mask == 0x37) SA_PICK_SHAPE(0x37, NN); \
+			else SA_PICK_SHAPE(0x3f, NN); \
+		} while (0)
+		if (G == 8)
 		{
-			CB_CUDA(ctx, cudaFuncSetAttribute(k_scan_agg_small<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-			k_scan_agg_small<4><<<blocks, SA_NCONS(4) + 32, smem, ctx->stream>>>(P);
+			/* rare: 5..8 groups per CTA.  One instantiation: all sums, wide arithmetic. */
+			if (!P.colA || !P.colD)
+				break;
+			SA_LAUNCH(8, 0x3f, false, 0);
 		}
+		else if (narrow)
+			SA_PICK(true);
 		else
-		{
-			CB_CUDA(ctx, cudaFuncSetAttribute(k_scan_agg_small<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-			k_scan_agg_small<8><<<blocks, SA_NCONS(8) + 32, smem, ctx->stream>>>(P);
-		}
+			SA_PICK(false);
 		CB_LAUNCHED(ctx, "k_scan_agg_small");
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
 		ctx->kernel_timed = true;
-		ctx->last_kernel_name = attempt == 0 ? "k_scan_agg_small<4>" : "k_scan_agg_small<8>";
 		k_small_commit<<<1, 256, 0, ctx->stream>>>(P, G, blocks);
 		CB_LAUNCHED(ctx, "k_small_commit");
-		CB_CUDA(ctx, cudaMemcpyAsync(h_retry, d_retry, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		CB_CUDA(ctx, cudaMemcpyAsync(h_flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-		if (h_retry[1])
-			break;				/* values too wide for the 64-bit fast path: generic kernel, nothing was committed */
-		if (!h_retry[0])
+		if (h_flags[1])
 		{
-			*handled = true;
-			break;
+			if (!narrow || G == 8)
+				break;			/* too wide even for 64-bit partials: generic kernel */
+			narrow = false;
+			continue;
 		}
+		if (h_flags[0])
+		{
+			if (G == 8)
+				break;			/* more than 8 groups in one CTA: generic kernel */
+			G = 8;
+			continue;
+		}
+		*handled = true;
+		break;
 	}
-	CB_CUDA(ctx, cudaFreeAsync(d_retry, ctx->stream));
+	CB_CUDA(ctx, cudaFreeAsync(d_flags, ctx->stream));
 	CB_CUDA(ctx, cudaFreeAsync(P.scratch, ctx->stream));
 	CB_CUDA(ctx, cudaFreeAsync(P.skeys, ctx->stream));
 	return CBGPU_OK;
