@@ -122,6 +122,10 @@ def gpu():
             "cbgpu_ht_probe_pairs": (C.c_int, [vp, vp, vp, C.POINTER(i32), i32, vp, i64, vp]),
             "cbgpu_pairs_free": (None, [vp]),
             "cbgpu_read_u32": (C.c_int, [vp, vp, i64, vp]),
+            "cbgpu_motion_unique_id": (C.c_int, [vp]),
+            "cbgpu_motion_create": (C.c_int, [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]),
+            "cbgpu_motion_destroy": (None, [vp]),
+            "cbgpu_motion_bytes_sent": (i64, [vp]),
             "cbgpu_gen_lineitem": (C.c_int, [vp, vp, u64, i64, i64, i64]),
             "cbgpu_gen_orders": (C.c_int, [vp, vp, u64, i64, i64]),
             "cbgpu_gen_customer": (C.c_int, [vp, vp, u64]),
@@ -164,6 +168,9 @@ def ex():
         L.cb_slot_float8.argtypes = [C.POINTER(CbTupleTableSlot), C.c_int]
         L.cb_numeric_sum_text.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_char_p, C.c_int32]
         L.cb_numeric_avg_text.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_char_p, C.c_int32]
+        L.cb_interconnect_nccl_create.restype = vp
+        L.cb_interconnect_nccl_create.argtypes = [vp]
+        L.cb_interconnect_destroy.argtypes = [vp]
         L.cb_cluster_create.restype = vp
         L.cb_cluster_create.argtypes = [vp, C.c_int32]
         L.cb_cluster_set_range_table.restype = C.c_int
@@ -231,6 +238,35 @@ class Context:
     def close(self):
         if self.h:
             self.L.cbgpu_ctx_destroy(self.h)
+            self.h = None
+
+
+class Motion:
+    """NCCL interconnect endpoint of one GPU-segment (one process per GPU)."""
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        rc = gpu().cbgpu_motion_unique_id(buf)
+        if rc:
+            raise CbgpuError(rc, "ncclGetUniqueId failed")
+        return buf.raw
+
+    def __init__(self, ctx, rank, nranks, unique_id):
+        self.ctx = ctx
+        self.rank = rank
+        self.nranks = nranks
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        ctx.check(ctx.L.cbgpu_motion_create(ctx.h, rank, nranks, buf, C.byref(h)))
+        self.h = h
+
+    def bytes_sent(self):
+        return int(self.ctx.L.cbgpu_motion_bytes_sent(self.h))
+
+    def close(self):
+        if self.h:
+            self.ctx.L.cbgpu_motion_destroy(self.h)
             self.h = None
 
 
@@ -340,7 +376,7 @@ def _collect_instrument(ps, out):
 class Executor:
     """ExecutorStart / ExecutorRun / ExecutorEnd for one segment (one GPU)."""
 
-    def __init__(self, ctx, range_table, force_generic=False):
+    def __init__(self, ctx, range_table, force_generic=False, motion=None):
         self.ctx = ctx
         self.E = ex()
         n = len(range_table)
@@ -348,6 +384,14 @@ class Executor:
         self.estate = self.E.cb_CreateExecutorState(ctx.h, arr, n)
         self.estate.contents.es_force_generic = 1 if force_generic else 0
         self._keep = [arr, range_table]
+        self.ic = None
+        if motion is not None:
+            # SetupInterconnect (executor/execMain.c:531): this process is segment `rank` of `nranks`
+            self.ic = self.E.cb_interconnect_nccl_create(motion.h)
+            self.estate.contents.es_interconnect = self.ic
+            self.estate.contents.es_segindex = motion.rank
+            self.estate.contents.es_numsegments = motion.nranks
+            self._keep.append(motion)
 
     def run(self, plan_node):
         """Pull every tuple through cb_ExecProcNode, as ExecutePlan does (execMain.c:2772)."""
@@ -378,6 +422,9 @@ class Executor:
         if self.estate:
             self.E.cb_FreeExecutorState(self.estate)
             self.estate = None
+        if self.ic:
+            self.E.cb_interconnect_destroy(self.ic)
+            self.ic = None
 
 
 class Cluster:

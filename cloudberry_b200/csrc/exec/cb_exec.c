@@ -2389,6 +2389,55 @@ cb_slot_text(const CbTupleTableSlot *slot, int attno, char *buf, int buflen)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * NCCL interconnect: the MotionIPCLayer-shaped vtable over cbgpu_motion_*
+ * ------------------------------------------------------------------------------------------ */
+static int
+ic_nccl_redistribute(CbInterconnect *ic, CbEState *es, int32_t motion_id, cbgpu_rel *send, const int64_t *counts,
+					 int64_t seg_capacity, cbgpu_rel **recv)
+{
+	(void) motion_id;
+	GPU(es, cbgpu_motion_redistribute((cbgpu_motion *) ic->priv, send, counts, seg_capacity, recv));
+	return CBGPU_OK;
+}
+
+static int
+ic_nccl_gather(CbInterconnect *ic, CbEState *es, int32_t motion_id, int32_t root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv)
+{
+	(void) motion_id;
+	GPU(es, cbgpu_motion_gather((cbgpu_motion *) ic->priv, root, send, nrows, recv));
+	return CBGPU_OK;
+}
+
+static int
+ic_nccl_broadcast(CbInterconnect *ic, CbEState *es, int32_t motion_id, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv)
+{
+	(void) motion_id;
+	GPU(es, cbgpu_motion_broadcast((cbgpu_motion *) ic->priv, send, nrows, recv));
+	return CBGPU_OK;
+}
+
+CbInterconnect *
+cb_interconnect_nccl_create(cbgpu_motion *motion)
+{
+	CbInterconnect *ic = calloc(1, sizeof(CbInterconnect));
+
+	ic->name = "nccl";
+	ic->nsegs = cbgpu_motion_nranks(motion);
+	ic->segindex = cbgpu_motion_rank(motion);
+	ic->redistribute = ic_nccl_redistribute;
+	ic->gather = ic_nccl_gather;
+	ic->broadcast = ic_nccl_broadcast;
+	ic->priv = motion;
+	return ic;
+}
+
+void
+cb_interconnect_destroy(CbInterconnect *ic)
+{
+	free(ic);
+}
+
+/* ------------------------------------------------------------------------------------------
  * in-process cluster + local interconnect
  * ------------------------------------------------------------------------------------------ */
 struct CbCluster

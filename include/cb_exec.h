@@ -152,6 +152,12 @@ typedef struct CbInterconnect
 	void	   *priv;
 } CbInterconnect;
 
+/* interconnect over NCCL (cbgpu_motion_*): one process per GPU-segment.  SetupInterconnect
+ * (executor/execMain.c:531) equivalent: attach the result to CbEState.es_interconnect and set
+ * es_segindex / es_numsegments. */
+CbInterconnect *cb_interconnect_nccl_create(cbgpu_motion *motion);
+void		cb_interconnect_destroy(CbInterconnect *ic);
+
 /*
  * In-process cluster: N segment executors over one context (the reference tests "multi-node" the
  * same way: gpdemo runs every segment on one host, gpAux/gpdemo/demo_cluster.sh).  Each segment has

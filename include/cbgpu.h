@@ -300,6 +300,26 @@ int			cbgpu_topn(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const i
 					   int64_t *nout);
 
 /* ------------------------------------------------------------------------------------------
+ * interconnect over NCCL: one process per GPU-segment (backend/cdb/motion/cdbmotion.c:425,549 and
+ * the MotionIPCLayer implementations under contrib/interconnect are what this replaces)
+ * ------------------------------------------------------------------------------------------ */
+/* 128-byte rendezvous token created on one rank and handed to all (the harness broadcasts it) */
+int			cbgpu_motion_unique_id(void *out128);
+int			cbgpu_motion_create(cbgpu_ctx *ctx, int rank, int nranks, const void *unique_id128, cbgpu_motion **out);
+void		cbgpu_motion_destroy(cbgpu_motion *m);
+int			cbgpu_motion_rank(const cbgpu_motion *m);
+int			cbgpu_motion_nranks(const cbgpu_motion *m);
+int64_t		cbgpu_motion_bytes_sent(const cbgpu_motion *m);
+/* Redistribute: `send` holds this rank's rows grouped by destination (destination d at row
+ * d * seg_capacity, counts[d] rows); returns the rows addressed to this rank, sender by sender */
+int			cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *counts, int64_t seg_capacity,
+									  cbgpu_rel **recv);
+/* Gather: the first nrows rows of every rank's `send` to rank `root` (others receive 0 rows) */
+int			cbgpu_motion_gather(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
+/* Broadcast: every rank receives every rank's first nrows rows */
+int			cbgpu_motion_broadcast(cbgpu_motion *m, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
+
+/* ------------------------------------------------------------------------------------------
  * synthetic TPC-H shaped generator (harness; same counter-based formulas as
  * cloudberry_b200/tpch.py so host and device tables are identical)
  * ------------------------------------------------------------------------------------------ */

@@ -1,0 +1,67 @@
+"""Worker for the multi-GPU parity test: run under torchrun, one rank per GPU-segment.
+
+Every rank holds its cdbhash shard of the reference's regression fixture (placement computed by the
+oracle, the GPU path never sees the other shards), joins the NCCL interconnect, and runs the
+two-stage Q1 and the Motion-bearing Q3 / Q5 plans through the executor.  Rank 0 (the Gather Motion's
+receiver) checks the rows against the reference's expected output."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from cloudberry_b200 import capi, tpch
+    from oracle import oracle as O
+    from gpu_util import shard, to_device
+
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rels, exp = tpch.load_golden(capi.hashbpchar)
+    replicated = os.environ.get("CB_REPLICATED", "1") == "1"
+    dist_keys = dict(tpch.DIST_KEY)
+    if not replicated:
+        dist_keys["customer"] = "c_custkey"
+        dist_keys["supplier"] = "s_suppkey"
+    mine = shard(O, rels, world, dist_keys)[rank]
+    ctx = capi.Context(local)
+    dev = to_device(ctx, mine)
+    ids = [capi.Motion.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    motion = capi.Motion(ctx, rank, world, ids[0])
+    ex = capi.Executor(ctx, dev, motion=motion)
+    seg = exp["dict"]["c_mktsegment_dict"].index("MACHINERY")
+    reg = exp["dict"]["r_name_dict"].index("AMERICA")
+    ok = True
+    r1 = ex.run(tpch.q1_plan(world))
+    r3 = ex.run(tpch.q3_plan(seg, world, customer_replicated=replicated))
+    r5 = ex.run(tpch.q5_plan(reg, world, replicated=replicated))
+    if rank == 0:
+        ok = ok and tpch.format_q1(r1.rows) == exp["q1"]
+        ok = ok and tpch.format_q3(r3.rows) == exp["q3"]
+        ok = ok and tpch.format_q5(r5.rows, exp["dict"]["n_name_dict"]) == exp["q5"]
+        print("MULTIRANK", "PASS" if ok else "FAIL", "world", world, "replicated", replicated, "nccl bytes sent by rank 0", motion.bytes_sent())
+        if not ok:
+            print(tpch.format_q1(r1.rows), tpch.format_q3(r3.rows), tpch.format_q5(r5.rows, exp["dict"]["n_name_dict"]))
+    else:
+        ok = len(r1.rows) == 0 and len(r3.rows) == 0 and len(r5.rows) == 0     # only the gather receiver emits
+        if not ok:
+            print("MULTIRANK FAIL: non-root rank emitted rows")
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    ex.close()
+    motion.close()
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()
