@@ -212,14 +212,18 @@ def main():
     barrier()
     l0 = ctx.launches()
     ctx.timer_start()
+    knames = []
     for _ in range(args.steps):
+        ctx.kernel_log_reset()
         res = ex.run(plan1)
-        kernel_ms.append(ctx.last_kernel()[1])
+        kn, km = ctx.longest_kernel()     # the step's dominant kernel, timed by its own CUDA events
+        kernel_ms.append(km)
+        knames.append(kn)
     ms = ctx.timer_stop_ms()
     l1 = ctx.launches()
     barrier()
     clocks = sampler.stop()
-    kname = ctx.last_kernel()[0]
+    kname = knames[-1]
     ngroups = len(res.rows)
     if dist:
         import torch

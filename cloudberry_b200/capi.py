@@ -98,6 +98,8 @@ def gpu():
             "cbgpu_timer_stop_ms": (C.c_int, [vp, C.POINTER(dbl)]),
             "cbgpu_last_kernel_ms": (dbl, [vp]),
             "cbgpu_last_kernel_name": (C.c_char_p, [vp]),
+            "cbgpu_kernel_log_reset": (None, [vp]),
+            "cbgpu_kernel_log_longest": (C.c_int, [vp, C.c_char_p, C.c_int, C.POINTER(dbl)]),
             "cbgpu_flush_l2": (C.c_int, [vp]),
             "cbgpu_host_alloc": (vp, [C.c_size_t]),
             "cbgpu_host_free": (None, [vp]),
@@ -228,6 +230,16 @@ class Context:
 
     def last_kernel(self):
         return (self.L.cbgpu_last_kernel_name(self.h) or b"").decode(), float(self.L.cbgpu_last_kernel_ms(self.h))
+
+    def kernel_log_reset(self):
+        self.L.cbgpu_kernel_log_reset(self.h)
+
+    def longest_kernel(self):
+        """(name, ms) of the longest pipeline kernel since kernel_log_reset(); syncs the stream."""
+        buf = C.create_string_buffer(128)
+        ms = C.c_double()
+        self.check(self.L.cbgpu_kernel_log_longest(self.h, buf, 128, C.byref(ms)))
+        return buf.value.decode(), ms.value
 
     def flush_l2(self):
         self.check(self.L.cbgpu_flush_l2(self.h))

@@ -27,6 +27,12 @@ struct cbgpu_ctx
 	double		last_kernel_ms;
 	const char *last_kernel_name;
 	bool		kernel_timed;
+	/* log of the pipeline kernels since cbgpu_kernel_log_reset(): own event pair per entry */
+#define CB_KLOG 32
+	cudaEvent_t klog_ev[CB_KLOG][2];
+	const char *klog_name[CB_KLOG];
+	int			klog_n;
+	bool		klog_ready;
 	void	   *flush_buf;
 	size_t		flush_bytes;
 	int		   *d_status;		/* device status word: nonzero = CBGPU error code raised by a kernel */

@@ -158,6 +158,65 @@ cbgpu_last_kernel_ms(cbgpu_ctx *ctx)
 	return f;
 }
 
+/* pipeline-kernel log: every pipeline launch brackets itself with its own event pair */
+int
+cb_klog_begin(cbgpu_ctx *ctx, const char *name)
+{
+	int			i = ctx->klog_n;
+
+	if (i >= CB_KLOG)
+		return -1;
+	if (!ctx->klog_ready)
+	{
+		for (int k = 0; k < CB_KLOG; k++)
+		{
+			cudaEventCreate(&ctx->klog_ev[k][0]);
+			cudaEventCreate(&ctx->klog_ev[k][1]);
+		}
+		ctx->klog_ready = true;
+	}
+	ctx->klog_name[i] = name;
+	cudaEventRecord(ctx->klog_ev[i][0], ctx->stream);
+	ctx->klog_n = i + 1;
+	return i;
+}
+
+void
+cb_klog_end(cbgpu_ctx *ctx, int i)
+{
+	if (i >= 0)
+		cudaEventRecord(ctx->klog_ev[i][1], ctx->stream);
+}
+
+extern "C" void
+cbgpu_kernel_log_reset(cbgpu_ctx *ctx)
+{
+	ctx->klog_n = 0;
+}
+
+extern "C" int
+cbgpu_kernel_log_longest(cbgpu_ctx *ctx, char *name, int namelen, double *ms)
+{
+	float		best = -1.f;
+	int			bi = -1;
+
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (int i = 0; i < ctx->klog_n; i++)
+	{
+		float		f = 0;
+
+		if (cudaEventElapsedTime(&f, ctx->klog_ev[i][0], ctx->klog_ev[i][1]) == cudaSuccess && f > best)
+		{
+			best = f;
+			bi = i;
+		}
+	}
+	*ms = best;
+	if (name && namelen > 0)
+		snprintf(name, (size_t) namelen, "%s", bi >= 0 ? ctx->klog_name[bi] : "");
+	return CBGPU_OK;
+}
+
 extern "C" const char *
 cbgpu_last_kernel_name(cbgpu_ctx *ctx)
 {

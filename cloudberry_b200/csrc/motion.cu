@@ -149,6 +149,9 @@ exchange_rows(cbgpu_motion *m, cbgpu_rel *send, cbgpu_rel *recv, const int64_t *
 	cbgpu_ctx  *ctx = m->ctx;
 	int			n = m->nranks;
 
+	/* one NCCL group for the whole exchange: every column's sends and receives fuse into a single
+	 * launch */
+	CB_NCCL(ctx, ncclGroupStart());
 	for (int c = 0; c < send->ncols; c++)
 	{
 		size_t		w = (size_t) cb_type_w(send->types[c]);
@@ -159,7 +162,6 @@ exchange_rows(cbgpu_motion *m, cbgpu_rel *send, cbgpu_rel *recv, const int64_t *
 			char	   *rp = pass ? (char *) recv->nulls[c] : (char *) recv->data[c];
 			size_t		ww = pass ? 1 : w;
 
-			CB_NCCL(ctx, ncclGroupStart());
 			for (int peer = 0; peer < n; peer++)
 			{
 				if (peer == m->rank)
@@ -172,13 +174,22 @@ exchange_rows(cbgpu_motion *m, cbgpu_rel *send, cbgpu_rel *recv, const int64_t *
 				if (recv_cnt[peer] > 0)
 					CB_NCCL(ctx, ncclRecv(rp + (size_t) recv_off[peer] * ww, (size_t) recv_cnt[peer] * ww, ncclInt8, peer, m->comm, ctx->stream));
 			}
-			CB_NCCL(ctx, ncclGroupEnd());
-			/* rows that stay on this segment never leave the device */
-			if (send_cnt[m->rank] > 0)
-				CB_CUDA(ctx, cudaMemcpyAsync(rp + (size_t) recv_off[m->rank] * ww, sp + (size_t) send_off[m->rank] * ww,
-											 (size_t) send_cnt[m->rank] * ww, cudaMemcpyDeviceToDevice, ctx->stream));
 		}
 	}
+	CB_NCCL(ctx, ncclGroupEnd());
+	/* rows that stay on this segment never leave the device */
+	if (send_cnt[m->rank] > 0)
+		for (int c = 0; c < send->ncols; c++)
+		{
+			size_t		w = (size_t) cb_type_w(send->types[c]);
+
+			CB_CUDA(ctx, cudaMemcpyAsync((char *) recv->data[c] + (size_t) recv_off[m->rank] * w,
+										 (char *) send->data[c] + (size_t) send_off[m->rank] * w,
+										 (size_t) send_cnt[m->rank] * w, cudaMemcpyDeviceToDevice, ctx->stream));
+			if (send->nulls[c])
+				CB_CUDA(ctx, cudaMemcpyAsync(recv->nulls[c] + recv_off[m->rank], send->nulls[c] + send_off[m->rank],
+											 (size_t) send_cnt[m->rank], cudaMemcpyDeviceToDevice, ctx->stream));
+		}
 	m->exchanges++;
 	return CBGPU_OK;
 }

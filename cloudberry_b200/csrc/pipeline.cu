@@ -585,8 +585,11 @@ cbgpu_pipeline_run(cbgpu_ctx *ctx, const CbPipeline *p)
 		if (blocks > (int64_t) ctx->sm_count * 8)
 			blocks = (int64_t) ctx->sm_count * 8;
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
+		int			kl = cb_klog_begin(ctx, "k_pipeline_generic");
+
 		k_pipeline_generic<<<(int) blocks, 256, 0, ctx->stream>>>(d);
 		CB_LAUNCHED(ctx, "k_pipeline_generic");
+		cb_klog_end(ctx, kl);
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
 		ctx->kernel_timed = true;
 		ctx->last_kernel_name = "k_pipeline_generic";

@@ -143,5 +143,7 @@ sink_store(void *col, int type, uint64_t pos, int64_t v)
 	}
 }
 
+int			cb_klog_begin(cbgpu_ctx *ctx, const char *name);
+void		cb_klog_end(cbgpu_ctx *ctx, int i);
 int			cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d);
 int			cb_try_specialised(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handled);

@@ -727,6 +727,7 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 	{
 		CB_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), ctx->stream));
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
+		int			kl = cb_klog_begin(ctx, "k_scan_agg_small");
 #define SA_LAUNCH(GG, MM, NN, SS) \
 		do { \
 			static bool attr_done = false; \
@@ -737,6 +738,8 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 			} \
 			k_scan_agg_small<GG, MM, NN, SS><<<blocks, SA_NCONS(GG) + 32, smem, ctx->stream>>>(P); \
 			ctx->last_kernel_name = "k_scan_agg_small<" #GG "," #MM "," #NN "," #SS ">"; \
+			if (kl >= 0) \
+				ctx->klog_name[kl] = ctx->last_kernel_name; \
 		} while (0)
 #define SA_PICK_SHAPE(MM, NN) \
 		do { \
@@ -762,6 +765,7 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 		else
 			SA_PICK(false);
 		CB_LAUNCHED(ctx, "k_scan_agg_small");
+		cb_klog_end(ctx, kl);
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
 		ctx->kernel_timed = true;
 		k_small_commit<<<1, 256, 0, ctx->stream>>>(P, G, blocks);

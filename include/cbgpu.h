@@ -75,6 +75,9 @@ int			cbgpu_timer_start(cbgpu_ctx *ctx);
 int			cbgpu_timer_stop_ms(cbgpu_ctx *ctx, double *ms);
 /* last pipeline kernel's own duration (events around that launch only) and its name */
 double		cbgpu_last_kernel_ms(cbgpu_ctx *ctx);
+/* log of pipeline kernels launched since the last reset; the longest one's name and duration */
+void		cbgpu_kernel_log_reset(cbgpu_ctx *ctx);
+int			cbgpu_kernel_log_longest(cbgpu_ctx *ctx, char *name, int namelen, double *ms);
 const char *cbgpu_last_kernel_name(cbgpu_ctx *ctx);
 /* write `bytes` of HBM so the next timed kernel starts with a cold L2 */
 int			cbgpu_flush_l2(cbgpu_ctx *ctx);

@@ -1,0 +1,72 @@
+#!/usr/bin/env python3
+"""Run TPC-H Q1 / Q3 / Q5 over device-generated synthetic tables on one GPU and print timings
+(harness / profiling aid; bench.py is the contract benchmark)."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from cloudberry_b200 import capi, tpch  # noqa: E402
+
+
+def device_tables(ctx, sf, seed=42):
+    sz = tpch.sizes(int(sf) if float(sf).is_integer() else sf)
+    G = ctx.L
+    rels = {}
+    for name in tpch.RT:
+        types = [t for _, t in tpch.SCHEMA[name]]
+        rels[name] = capi.DeviceRelation(ctx, sz[name], types, name=name)
+    ctx.check(G.cbgpu_gen_lineitem(ctx.h, rels["lineitem"].h, seed, 0, sz["supplier"], sz["part"]))
+    ctx.check(G.cbgpu_gen_orders(ctx.h, rels["orders"].h, seed, 0, sz["customer"]))
+    ctx.check(G.cbgpu_gen_customer(ctx.h, rels["customer"].h, seed))
+    ctx.check(G.cbgpu_gen_supplier(ctx.h, rels["supplier"].h, seed))
+    nation, region = tpch.gen_nation_region()
+    hn = tpch._rel("nation", nation, {"n_name": tpch.NATIONS}).set_dict_hashes(capi.hashbpchar)
+    hr = tpch._rel("region", region, {"r_name": tpch.REGIONS}).set_dict_hashes(capi.hashbpchar)
+    rels["nation"].load(hn)
+    rels["region"].load(hr)
+    import numpy as np
+    rels["customer"].set_dict_hash(2, np.array([capi.hashbpchar(s) for s in tpch.SEGMENTS], dtype=np.uint32))
+    ctx.sync()
+    return [rels[n] for n in tpch.RT], sz
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sf", type=float, default=1.0)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--queries", default="q1,q3,q5")
+    ap.add_argument("--generic", action="store_true")
+    args = ap.parse_args()
+    ctx = capi.Context(0)
+    rt, sz = device_tables(ctx, args.sf)
+    ex = capi.Executor(ctx, rt, force_generic=args.generic)
+    plans = {"q1": lambda: tpch.q1_plan(1), "q3": lambda: tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), 1),
+             "q5": lambda: tpch.q5_plan(tpch.REGIONS.index("AMERICA"), 1)}
+    rows_in = {"q1": sz["lineitem"], "q3": sz["lineitem"] + sz["orders"] + sz["customer"],
+               "q5": sz["lineitem"] + sz["orders"] + sz["customer"] + sz["supplier"] + 30}
+    for q in args.queries.split(","):
+        plan = plans[q]()
+        res = ex.run(plan)       # warm-up
+        times = []
+        for _ in range(args.steps):
+            ctx.kernel_log_reset()
+            ctx.timer_start()
+            res = ex.run(plan)
+            times.append(ctx.timer_stop_ms())
+        kn, km = ctx.longest_kernel()
+        ms = sorted(times)[len(times) // 2]
+        print(json.dumps({"query": q, "sf": args.sf, "ms": ms, "rows_per_s": rows_in[q] / (ms / 1e3), "result_rows": len(res.rows),
+                          "longest_kernel": kn, "longest_kernel_ms": km,
+                          "nodes": {k: {"node": v["node"], "kernels": v["kernels"], "device_ms": round(v["device_ms"], 3),
+                                        "ntuples": v["ntuples"]} for k, v in res.instrument.items()},
+                          "first_rows": res.rows[:3]}))
+    ex.close()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
