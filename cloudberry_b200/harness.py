@@ -1,0 +1,87 @@
+"""Multi-process harness pieces shared by bench.py, the multi-GPU worker and the CPU (gloo) tests.
+
+One process per GPU-segment, launched by torchrun.  torch.distributed is plumbing only (rendezvous,
+barrier, max-over-ranks of timings, handing the NCCL rendezvous token around); the data path's
+collectives live in csrc/motion.cu.  `exchange_by_destination` is the reference implementation of
+the Redistribute protocol (count exchange, then payload all-to-all) on host tensors: the CPU tests
+run it over gloo to pin the protocol the CUDA side follows."""
+import os
+
+import numpy as np
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def init_dist(backend, local_rank=0):
+    import torch
+    import torch.distributed as dist
+    if backend == "nccl":
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist.init_process_group(backend)
+    return dist
+
+
+def broadcast_token(dist, make_token, rank):
+    """Rank 0 makes the interconnect's rendezvous token (cbgpu_motion_unique_id), everyone gets it."""
+    box = [make_token() if rank == 0 else None]
+    if dist is not None:
+        dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def shard_rows(rank, nrows_per_rank):
+    """Weak-scaling shard of a counter-generated table: rank r owns rows [r * n, (r + 1) * n)."""
+    return rank * nrows_per_rank, (rank + 1) * nrows_per_rank
+
+
+def max_over_ranks(dist, values, device="cpu"):
+    import torch
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def exchange_by_destination(dist, rank, world, dest, columns):
+    """Redistribute rows to their destination ranks.
+    dest: int array (nrows) of destination ranks; columns: list of numpy arrays (nrows each).
+    Protocol = csrc/motion.cu: (1) every rank learns every rank's per-destination counts (all-gather),
+    (2) one all-to-all per column of exactly those row ranges, sender-major on the receiver.
+    Returns the received columns."""
+    import torch
+    order = np.argsort(dest, kind="stable")
+    counts = np.bincount(dest, minlength=world).astype(np.int64)
+    mine = torch.from_numpy(counts.copy())
+    gathered = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    matrix = torch.stack(gathered).numpy()            # matrix[s][d]
+    recv_counts = matrix[:, rank]
+    out = []
+    for col in columns:
+        col = np.ascontiguousarray(col[order])
+        send = torch.from_numpy(col.view(np.uint8).reshape(len(col), -1).copy()) if len(col) else torch.zeros((0, col.dtype.itemsize), dtype=torch.uint8)
+        w = col.dtype.itemsize
+        send_list = list(torch.split(send.reshape(-1), [int(c) * w for c in counts]))
+        recv_list = [torch.zeros(int(c) * w, dtype=torch.uint8) for c in recv_counts]
+        dist.all_to_all(recv_list, send_list) if dist.get_backend() != "gloo" else _gloo_all_to_all(dist, rank, world, recv_list, send_list)
+        out.append(torch.cat(recv_list).numpy().view(col.dtype) if recv_counts.sum() else np.zeros(0, dtype=col.dtype))
+    return out, matrix
+
+
+def _gloo_all_to_all(dist, rank, world, recv_list, send_list):
+    """gloo has no all_to_all for uneven splits on every build: pairwise isend/irecv."""
+    reqs = []
+    for peer in range(world):
+        if peer == rank:
+            recv_list[peer].copy_(send_list[peer])
+            continue
+        if send_list[peer].numel():
+            reqs.append(dist.isend(send_list[peer].contiguous(), dst=peer))
+        if recv_list[peer].numel():
+            reqs.append(dist.irecv(recv_list[peer], src=peer))
+    for r in reqs:
+        r.wait()
