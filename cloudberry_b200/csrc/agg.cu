@@ -459,32 +459,48 @@ cbgpu_topn(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const int32_t
 	*nout = 0;
 	if (rel->nrows == 0)
 		return CBGPU_OK;
-	/* pass 1: every thread keeps its own best k; pass 2: one CTA over the candidates */
-	int			blocks1 = ctx->sm_count * 2,
-				threads = 128;
+	/* tournament: every pass gives each thread ~64 candidates and keeps its best k, until one thread
+	 * holds the answer; passes shrink the candidate list by ~64 / k each */
+	{
+		const int	threads = 128;
+		const int64_t per_thread = 64;
+		const uint32_t *in = NULL;
+		int64_t		nin = rel->nrows;
+		int			which = 0;
+		int64_t		cap = ((rel->nrows + per_thread - 1) / per_thread + threads) * limit;
 
-	if ((int64_t) blocks1 * threads > rel->nrows)
-		blocks1 = (int) ((rel->nrows + threads - 1) / threads);
-	n1 = (int64_t) blocks1 * threads * limit;
-	CB_CUDA(ctx, cudaMallocAsync(&cand1, n1 * sizeof(uint32_t), ctx->stream));
-	p.in_idx = NULL;
-	p.nin = rel->nrows;
-	p.out_idx = cand1;
-	k_topn<<<blocks1, threads, 0, ctx->stream>>>(p);
-	CB_LAUNCHED(ctx, "k_topn");
-	n2 = (int64_t) threads * limit;
-	CB_CUDA(ctx, cudaMallocAsync(&cand2, n2 * sizeof(uint32_t), ctx->stream));
-	p.in_idx = cand1;
-	p.nin = n1;
-	p.out_idx = cand2;
-	k_topn<<<1, threads, 0, ctx->stream>>>(p);
-	CB_LAUNCHED(ctx, "k_topn");
-	/* final: one thread */
-	p.in_idx = cand2;
-	p.nin = n2;
-	p.out_idx = cand1;
-	k_topn<<<1, 1, 0, ctx->stream>>>(p);
-	CB_LAUNCHED(ctx, "k_topn");
+		CB_CUDA(ctx, cudaMallocAsync(&cand1, cap * sizeof(uint32_t), ctx->stream));
+		CB_CUDA(ctx, cudaMallocAsync(&cand2, cap * sizeof(uint32_t), ctx->stream));
+		for (;;)
+		{
+			int64_t		nthreads = (nin + per_thread - 1) / per_thread;
+			int			blocks = (int) ((nthreads + threads - 1) / threads);
+			int			tpb = nthreads < threads ? (int) nthreads : threads;
+			uint32_t   *outbuf = which ? cand2 : cand1;
+
+			if (nthreads <= 1)
+			{
+				blocks = 1;
+				tpb = 1;
+			}
+			p.in_idx = in;
+			p.nin = nin;
+			p.out_idx = outbuf;
+			k_topn<<<blocks, tpb, 0, ctx->stream>>>(p);
+			CB_LAUNCHED(ctx, "k_topn");
+			n1 = (int64_t) blocks * tpb * limit;
+			if (blocks == 1 && tpb == 1)
+			{
+				if (outbuf != cand1)
+					CB_CUDA(ctx, cudaMemcpyAsync(cand1, outbuf, limit * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+				break;
+			}
+			in = outbuf;
+			nin = n1;
+			which ^= 1;
+		}
+		(void) n2;
+	}
 	CB_CUDA(ctx, cudaMemcpyAsync(host_idx, cand1, limit * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	cudaFreeAsync(cand1, ctx->stream);

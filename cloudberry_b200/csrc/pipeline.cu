@@ -191,6 +191,31 @@ cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
 		default:
 			return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink kind %s%lld unknown", "", s->kind);
 	}
+	/* stage boundaries: after every FILTER / PROBE (the stack is empty there) */
+	{
+		int			ns = 0,
+					dep = 0;
+
+		d->stage_pc[ns++] = 0;
+		for (int i = 0; i < p->nops; i++)
+		{
+			int			c = p->ops[i].code;
+
+			if (c == CBP_LOAD || c == CBP_CONST || c == CBP_DUP)
+				dep++;
+			else if (c == CBP_FILTER || c == CBP_POP)
+				dep--;
+			else if (c == CBP_PROBE)
+				dep -= p->probes[p->ops[i].a].nkeys;
+			else if (c != CBP_NOT && c != CBP_I2F && c != CBP_END)
+				dep--;
+			if ((c == CBP_FILTER || c == CBP_PROBE) && dep == 0 && ns < CBP_MAX_STAGES && i + 1 < p->nops)
+				d->stage_pc[ns++] = i + 1;
+		}
+		d->nstages = ns;
+		d->stage_pc[ns] = p->nops;
+		d->nsrc = d->src_base + p->nprobes;
+	}
 	d->status = ctx->d_status;
 	return CBGPU_OK;
 }
@@ -209,17 +234,70 @@ fcmp_pg(double x, double y)
 	return x < y ? -1 : (x > y ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(256)
+#define GEN_THREADS 256
+#define GEN_QCAP 64				/* entries per inter-stage queue (a stage runs as soon as 32 are waiting) */
+
+/*
+ * Staged execution.  The program is cut into stages at the points where rows can die and the
+ * expression stack is empty (after every FILTER / PROBE).  Each warp owns one small queue per stage
+ * boundary in shared memory, holding the source row ids of the rows that survived so far.  The warp
+ * always runs the deepest stage that has a full warp's worth (32) of rows waiting, else feeds
+ * stage 0 with the next 32 driving rows, and drains partial queues at the end.  So the ops behind a
+ * selective qual or join probe execute with (nearly) full warps instead of once per original warp:
+ * the device-side form of the row-at-a-time late materialisation of aocs_getnext_withqual
+ * (backend/access/aocs/aocsam.c:1269,1359) and of probing only tuples that passed the scan qual.
+ */
+__global__ void __launch_bounds__(GEN_THREADS)
 k_pipeline_generic(const __grid_constant__ PipeDev P)
 {
-	const int64_t nwarp_rows = (P.nrows + 31) & ~31ll;
-	int64_t		base = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x);
-	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	extern __shared__ uint32_t gen_smem[];
 	const int	lane = threadIdx.x & 31;
+	const int	warp_in_cta = threadIdx.x >> 5;
+	const int	nq = P.nstages - 1;			/* queues per warp */
+	const int	ew = P.nsrc + 1;			/* words per queue entry: row ids + NULL-extension mask */
+	uint32_t   *myq = gen_smem + (size_t) warp_in_cta * nq * GEN_QCAP * ew;
+	int			qcnt[CBP_MAX_STAGES];		/* warp-uniform */
+	const int64_t nchunks = (P.nrows + 31) / 32;
+	int64_t		chunk = (int64_t) blockIdx.x * (GEN_THREADS / 32) + warp_in_cta;
+	const int64_t chunk_stride = (int64_t) gridDim.x * (GEN_THREADS / 32);
 
-	for (; base < nwarp_rows; base += stride)
+#pragma unroll
+	for (int s = 0; s < CBP_MAX_STAGES; s++)
+		qcnt[s] = 0;
+
+	for (;;)
 	{
-		bool		alive = base < P.nrows;
+		/* ---- choose a stage ---- */
+		int			stage = -1;
+		int			navail = 0;
+
+		for (int s = nq; s >= 1; s--)
+			if (qcnt[s - 1] >= 32)
+			{
+				stage = s;
+				navail = 32;
+				break;
+			}
+		if (stage < 0)
+		{
+			if (chunk < nchunks)
+				stage = 0;
+			else
+			{
+				for (int s = 1; s <= nq; s++)
+					if (qcnt[s - 1] > 0)
+					{
+						stage = s;
+						navail = qcnt[s - 1];
+						break;
+					}
+				if (stage < 0)
+					break;
+			}
+		}
+
+		/* ---- fetch this lane's row ---- */
+		bool		alive;
 		uint32_t	ridx[CBP_MAX_SRC];
 		uint32_t	rnull = 0;		/* bit s: source s is NULL-extended (left join miss)              */
 		int64_t		st[CBP_STACK];
@@ -229,18 +307,47 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 #pragma unroll
 		for (int s = 0; s < CBP_MAX_SRC; s++)
 			ridx[s] = 0;
-		if (alive)
+		if (stage == 0)
 		{
-			if (P.drv_nsrc == 0)
-				ridx[0] = (uint32_t) base;
-			else
-				for (int s = 0; s < P.drv_nsrc; s++)
-					ridx[s] = P.drv_idx[s] ? P.drv_idx[s][base] : (uint32_t) base;
-			/* AppendOnlyVisimap_IsVisible (backend/access/appendonly/appendonly_visimap.c:198) */
-			if (P.visimap && !((P.visimap[ridx[0] >> 3] >> (ridx[0] & 7)) & 1))
-				alive = false;
+			const int64_t base = chunk * 32 + lane;
+
+			chunk += chunk_stride;
+			alive = base < P.nrows;
+			if (alive)
+			{
+				if (P.drv_nsrc == 0)
+					ridx[0] = (uint32_t) base;
+				else
+					for (int s = 0; s < P.drv_nsrc; s++)
+						ridx[s] = P.drv_idx[s] ? P.drv_idx[s][base] : (uint32_t) base;
+				/* AppendOnlyVisimap_IsVisible (backend/access/appendonly/appendonly_visimap.c:198) */
+				if (P.visimap && !((P.visimap[ridx[0] >> 3] >> (ridx[0] & 7)) & 1))
+					alive = false;
+			}
 		}
-		for (int pc = 0; pc < P.nops; pc++)
+		else
+		{
+			/* pop the newest `navail` entries of the queue feeding this stage */
+			uint32_t   *q = myq + (size_t) (stage - 1) * GEN_QCAP * ew;
+			const int	first = qcnt[stage - 1] - navail;
+
+			alive = lane < navail;
+			if (alive)
+			{
+				const uint32_t *e = q + (size_t) (first + lane) * ew;
+
+				for (int s = 0; s < P.nsrc; s++)
+					ridx[s] = e[s];
+				rnull = e[P.nsrc];
+			}
+			qcnt[stage - 1] = first;
+			__syncwarp();
+		}
+
+		/* ---- run the stage's ops ---- */
+		const int	pc_end = P.stage_pc[stage + 1];
+
+		for (int pc = P.stage_pc[stage]; pc < pc_end; pc++)
 		{
 			if (!__any_sync(0xffffffffu, alive))
 				break;
@@ -471,6 +578,25 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 					break;
 			}
 		}
+
+		if (stage < nq)
+		{
+			/* survivors wait in the next queue (there is room: it held < 32 entries) */
+			uint32_t   *q = myq + (size_t) stage * GEN_QCAP * ew;
+			const uint32_t m = __ballot_sync(0xffffffffu, alive);
+
+			if (alive)
+			{
+				uint32_t   *e = q + (size_t) (qcnt[stage] + __popc(m & ((1u << lane) - 1))) * ew;
+
+				for (int s = 0; s < P.nsrc; s++)
+					e[s] = ridx[s];
+				e[P.nsrc] = rnull;
+			}
+			qcnt[stage] += __popc(m);
+			__syncwarp();
+			continue;
+		}
 		/* ---- sink ---- */
 		const DSink &S = P.sink;
 
@@ -581,13 +707,20 @@ cbgpu_pipeline_run(cbgpu_ctx *ctx, const CbPipeline *p)
 	{
 		int64_t		warps = (p->nrows + 31) / 32;
 		int64_t		blocks = (warps + 7) / 8;
+		size_t		smem = (size_t) (GEN_THREADS / 32) * (size_t) (d.nstages - 1) * GEN_QCAP * (size_t) (d.nsrc + 1) * sizeof(uint32_t);
+		static bool attr_done = false;
 
 		if (blocks > (int64_t) ctx->sm_count * 8)
 			blocks = (int64_t) ctx->sm_count * 8;
+		if (!attr_done)
+		{
+			CB_CUDA(ctx, cudaFuncSetAttribute(k_pipeline_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+			attr_done = true;
+		}
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
 		int			kl = cb_klog_begin(ctx, "k_pipeline_generic");
 
-		k_pipeline_generic<<<(int) blocks, 256, 0, ctx->stream>>>(d);
+		k_pipeline_generic<<<(int) blocks, GEN_THREADS, smem, ctx->stream>>>(d);
 		CB_LAUNCHED(ctx, "k_pipeline_generic");
 		cb_klog_end(ctx, kl);
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));

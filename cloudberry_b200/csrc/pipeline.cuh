@@ -5,6 +5,8 @@
 #pragma once
 #include "common.cuh"
 
+#define CBP_MAX_STAGES 12
+
 struct DProbe
 {
 	HtDev		ht;
@@ -48,6 +50,9 @@ struct PipeDev
 	CbpOp		ops[CBP_MAX_OPS];
 	int32_t		nprobes;
 	int32_t		src_base;		/* probe j's inner rows are source src_base + j                      */
+	int32_t		nsrc;			/* sources in use                                                    */
+	int32_t		nstages;		/* program stages (cut after every FILTER / PROBE)                   */
+	int32_t		stage_pc[CBP_MAX_STAGES + 2];
 	DProbe		probes[CBP_MAX_SRC - 1];
 	DSink		sink;
 	int		   *status;
