@@ -100,6 +100,9 @@ def gpu():
             "cbgpu_last_kernel_name": (C.c_char_p, [vp]),
             "cbgpu_kernel_log_reset": (None, [vp]),
             "cbgpu_kernel_log_longest": (C.c_int, [vp, C.c_char_p, C.c_int, C.POINTER(dbl)]),
+            "cbgpu_trace_begin": (C.c_int, [vp]),
+            "cbgpu_trace_end": (C.c_int, [vp]),
+            "cbgpu_trace_get": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(dbl)]),
             "cbgpu_flush_l2": (C.c_int, [vp]),
             "cbgpu_host_alloc": (vp, [C.c_size_t]),
             "cbgpu_host_free": (None, [vp]),
@@ -240,6 +243,20 @@ class Context:
         ms = C.c_double()
         self.check(self.L.cbgpu_kernel_log_longest(self.h, buf, 128, C.byref(ms)))
         return buf.value.decode(), ms.value
+
+    def trace_begin(self):
+        self.check(self.L.cbgpu_trace_begin(self.h))
+
+    def trace_end(self):
+        """[(kernel name, ms)] for every launch since trace_begin(); ms runs from the previous launch's end."""
+        n = self.L.cbgpu_trace_end(self.h)
+        out = []
+        buf = C.create_string_buffer(128)
+        ms = C.c_double()
+        for i in range(n):
+            self.check(self.L.cbgpu_trace_get(self.h, i, buf, 128, C.byref(ms)))
+            out.append((buf.value.decode(), ms.value))
+        return out
 
     def flush_l2(self):
         self.check(self.L.cbgpu_flush_l2(self.h))

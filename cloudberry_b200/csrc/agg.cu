@@ -124,12 +124,39 @@ cbgpu_agg_free(cbgpu_aggtable *t)
 	free(t);
 }
 
+/* number of published groups (TupleHashTable's `members`) */
+__global__ void
+k_agg_count(AggDev t)
+{
+	size_t		cap = (size_t) t.mask + 1;
+	size_t		i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	size_t		stride = (size_t) gridDim.x * blockDim.x;
+	int			c = 0;
+
+	for (; i < cap; i += stride)
+		c += t.state[i] == 2;
+	for (int o = 16; o > 0; o >>= 1)
+		c += __shfl_xor_sync(0xffffffffu, c, o);
+	if ((threadIdx.x & 31) == 0 && c)
+		atomicAdd(t.ngroups, c);
+}
+
 extern "C" int
 cbgpu_agg_ngroups(cbgpu_aggtable *t, int64_t *ngroups)
 {
 	cbgpu_ctx  *ctx = t->ctx;
 	int32_t		h[2];
 
+	/* groups are counted here, once, rather than with one same-address atomic per new group */
+	CB_CUDA(ctx, cudaMemsetAsync(t->d.ngroups, 0, sizeof(int32_t), ctx->stream));
+	{
+		int			blocks = (int) ((t->capacity + 1023) / 1024);
+
+		if (blocks > ctx->sm_count * 8)
+			blocks = ctx->sm_count * 8;
+		k_agg_count<<<blocks, 256, 0, ctx->stream>>>(t->d);
+		CB_LAUNCHED(ctx, "k_agg_count");
+	}
 	CB_CUDA(ctx, cudaMemcpyAsync(h, t->d.ngroups, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	if (h[1])

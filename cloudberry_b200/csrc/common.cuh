@@ -33,6 +33,12 @@ struct cbgpu_ctx
 	const char *klog_name[CB_KLOG];
 	int			klog_n;
 	bool		klog_ready;
+	/* launch trace (cbgpu_trace_begin): one event after every kernel launch */
+#define CB_TRACE 1024
+	bool		trace_on;
+	int			trace_n;
+	cudaEvent_t *trace_ev;		/* CB_TRACE + 1 events, created on first use                         */
+	const char *trace_name[CB_TRACE];
 	void	   *flush_buf;
 	size_t		flush_bytes;
 	int		   *d_status;		/* device status word: nonzero = CBGPU error code raised by a kernel */
@@ -85,6 +91,12 @@ struct HtDev
 {
 	unsigned long long *slots;
 	uint32_t	mask;
+	/* blocked Bloom filter over the build keys' hash values: 2 bits in one 32-bit word, ~16 bits per
+	 * key, small enough to stay L2-resident.  A probe that fails it skips the table (DRAM) access:
+	 * the reference's runtime filter (PassByBloomFilter, executor/nodeSeqscan.c:413; built from the
+	 * build side in executor/nodeHash.c:4321-4432, lib/bloomfilter.c) applied at the probe. */
+	uint32_t   *bloom;
+	uint32_t	bloom_mask;
 	int32_t		nkeys;
 	const void *keydata[CBP_MAX_KEYS];	/* inner key columns, for match verification                  */
 	const uint8_t *keynulls[CBP_MAX_KEYS];
@@ -126,9 +138,12 @@ cb_fail(cbgpu_ctx *ctx, int code, const char *fmt, const char *a = "", long long
 	} while (0)
 
 /* kernel launch bookkeeping (every kernel of ours goes through this) */
+void		cb_trace_mark(cbgpu_ctx *ctx, const char *name);
 #define CB_LAUNCHED(ctx, name) \
 	do { \
 		(ctx)->launches++; \
+		if ((ctx)->trace_on) \
+			cb_trace_mark(ctx, name); \
 		cudaError_t e__ = cudaGetLastError(); \
 		if (e__ != cudaSuccess) \
 		{ \
@@ -348,6 +363,16 @@ pg_hash_datum(int type, int64_t v, const uint32_t *dict)
 	}
 }
 
+/* Bloom word index and bit pattern of a 32-bit key hash (bits independent of the slot index) */
+CB_HD uint32_t
+ht_bloom_bits(uint32_t h, uint32_t *word, uint32_t bloom_mask)
+{
+	uint32_t	m = pg_murmurhash32(h ^ 0x9e3779b9u);
+
+	*word = m & bloom_mask;
+	return (1u << ((m >> 22) & 31)) | (1u << ((m >> 27) & 31));
+}
+
 /* widen a column element to 64 bits (float8: raw bits) */
 __device__ __forceinline__ int64_t
 cb_load_widen(const void *data, int type, uint32_t row)
@@ -388,21 +413,27 @@ atomic_add128_signed(unsigned long long *acc, long long v)
 	atomic_add128(acc, (unsigned long long) v, v < 0 ? ~0ull : 0ull);
 }
 
-/* group lookup / insert in an agg table.  Returns the slot, or -1 when the table is full. */
+/* group lookup / insert in an agg table.  Returns the slot, or -1 when the table is full.
+ *
+ * A slot is claimed with one CAS (0 -> 1), filled, then published (state 2).  A lane that meets a
+ * slot in state 1 re-reads it on the NEXT trip of the same loop instead of spinning in a loop of
+ * its own: the claiming lane may sit in the same warp (adjacent rows of one group), and it can only
+ * finish its store if the divergent paths reconverge at the bottom of every trip. */
 __device__ __forceinline__ int
 agg_find_or_insert(const AggDev &t, uint32_t hash, const int64_t *keys, uint32_t nullmask)
 {
 	uint32_t	pos = hash & t.mask;
+	uint32_t	probes = 0;
+	int			result = -2;
 
-	for (uint32_t probes = 0; probes <= t.mask; probes++)
+	while (result == -2)
 	{
 		int			s = *((volatile int *) (t.state + pos));
 
 		if (s == 0)
 		{
-			int			old = atomicCAS(t.state + pos, 0, 1);
-
-			if (old == 0)
+			s = atomicCAS(t.state + pos, 0, 1);
+			if (s == 0)
 			{
 				/* initialize_hash_entry (executor/nodeAgg.c:2220): copy the grouping keys */
 				for (int k = 0; k < t.nkeys; k++)
@@ -411,27 +442,33 @@ agg_find_or_insert(const AggDev &t, uint32_t hash, const int64_t *keys, uint32_t
 				t.hash[pos] = hash;
 				__threadfence();
 				*((volatile int *) (t.state + pos)) = 2;
-				atomicAdd(t.ngroups, 1);
-				return (int) pos;
+				result = (int) pos;
 			}
-			s = old;
 		}
-		while (s == 1)
-			s = *((volatile int *) (t.state + pos));
-		__threadfence();
-		if (*((volatile uint32_t *) (t.hash + pos)) == hash && *((volatile uint32_t *) (t.keynull + pos)) == nullmask)
+		if (result == -2 && s == 2)
 		{
-			/* TupleHashTableMatch (executor/execGrouping.c:548): NULLs group together */
-			bool		same = true;
+			bool		same = false;
 
-			for (int k = 0; k < t.nkeys; k++)
-				if (!((nullmask >> k) & 1) && *((volatile long long *) (t.keys + (size_t) pos * t.nkeys + k)) != keys[k])
-					same = false;
+			__threadfence();
+			if (*((volatile uint32_t *) (t.hash + pos)) == hash && *((volatile uint32_t *) (t.keynull + pos)) == nullmask)
+			{
+				/* TupleHashTableMatch (executor/execGrouping.c:548): NULLs group together */
+				same = true;
+				for (int k = 0; k < t.nkeys; k++)
+					if (!((nullmask >> k) & 1) && *((volatile long long *) (t.keys + (size_t) pos * t.nkeys + k)) != keys[k])
+						same = false;
+			}
 			if (same)
-				return (int) pos;
+				result = (int) pos;
+			else if (++probes > t.mask)
+			{
+				atomicExch(t.full, 1);
+				result = -1;
+			}
+			else
+				pos = (pos + 1) & t.mask;
 		}
-		pos = (pos + 1) & t.mask;
+		/* s == 1: the owner is filling the slot; look again */
 	}
-	atomicExch(t.full, 1);
-	return -1;
+	return result;
 }

@@ -188,6 +188,57 @@ cb_klog_end(cbgpu_ctx *ctx, int i)
 		cudaEventRecord(ctx->klog_ev[i][1], ctx->stream);
 }
 
+/* launch trace: an event after every launch; entry i's time = event i -> event i + 1, i.e. the
+ * kernel plus whatever idle gap preceded it on the stream */
+void
+cb_trace_mark(cbgpu_ctx *ctx, const char *name)
+{
+	if (ctx->trace_n >= CB_TRACE)
+		return;
+	ctx->trace_name[ctx->trace_n] = name;
+	cudaEventRecord(ctx->trace_ev[ctx->trace_n + 1], ctx->stream);
+	ctx->trace_n++;
+}
+
+extern "C" int
+cbgpu_trace_begin(cbgpu_ctx *ctx)
+{
+	if (!ctx->trace_ev)
+	{
+		ctx->trace_ev = (cudaEvent_t *) calloc(CB_TRACE + 1, sizeof(cudaEvent_t));
+		if (!ctx->trace_ev)
+			return CBGPU_ERR_NOMEM;
+		for (int i = 0; i <= CB_TRACE; i++)
+			CB_CUDA(ctx, cudaEventCreate(&ctx->trace_ev[i]));
+	}
+	ctx->trace_n = 0;
+	ctx->trace_on = true;
+	CB_CUDA(ctx, cudaEventRecord(ctx->trace_ev[0], ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_trace_end(cbgpu_ctx *ctx)
+{
+	ctx->trace_on = false;
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return ctx->trace_n;
+}
+
+extern "C" int
+cbgpu_trace_get(cbgpu_ctx *ctx, int i, char *name, int namelen, double *ms)
+{
+	float		f = 0;
+
+	if (i < 0 || i >= ctx->trace_n)
+		return CBGPU_ERR_INVALID;
+	CB_CUDA(ctx, cudaEventElapsedTime(&f, ctx->trace_ev[i], ctx->trace_ev[i + 1]));
+	*ms = f;
+	if (name && namelen > 0)
+		snprintf(name, (size_t) namelen, "%s", ctx->trace_name[i]);
+	return CBGPU_OK;
+}
+
 extern "C" void
 cbgpu_kernel_log_reset(cbgpu_ctx *ctx)
 {

@@ -78,6 +78,15 @@ k_ht_build(BuildParams p)
 		unsigned long long e = ((unsigned long long) h << 32) | row;
 		uint32_t	pos = h & p.ht.mask;
 
+		if (p.ht.bloom)
+		{
+			uint32_t	w;
+			uint32_t	bits = ht_bloom_bits(h, &w, p.ht.bloom_mask);
+
+			if ((p.ht.bloom[w] & bits) != bits)
+				atomicOr(p.ht.bloom + w, bits);
+		}
+
 		for (;;)
 		{
 			unsigned long long cur = p.ht.slots[pos];
@@ -153,6 +162,16 @@ cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
 	CB_CUDA(ctx, cudaMallocAsync(&ht->d.slots, (size_t) nslots * sizeof(unsigned long long), ctx->stream));
 	CB_CUDA(ctx, cudaMallocAsync(&ht->d_flags, 2 * sizeof(int), ctx->stream));
+	{
+		/* ~16 filter bits per build row, at least one cache line */
+		int64_t		words = 32;
+
+		while (words < inner->nrows / 2)
+			words <<= 1;
+		CB_CUDA(ctx, cudaMallocAsync(&ht->d.bloom, (size_t) words * sizeof(uint32_t), ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(ht->d.bloom, 0, (size_t) words * sizeof(uint32_t), ctx->stream));
+		ht->d.bloom_mask = (uint32_t) (words - 1);
+	}
 	CB_CUDA(ctx, cudaMemsetAsync(ht->d_flags, 0, 2 * sizeof(int), ctx->stream));
 	int			blocks = (int) ((nslots + 255) / 256);
 
@@ -186,6 +205,8 @@ cbgpu_ht_free(cbgpu_hashtable *ht)
 		return;
 	cudaSetDevice(ht->ctx->device);
 	cudaFreeAsync(ht->d.slots, ht->ctx->stream);
+	if (ht->d.bloom)
+		cudaFreeAsync(ht->d.bloom, ht->ctx->stream);
 	cudaFreeAsync(ht->d_flags, ht->ctx->stream);
 	free(ht);
 }
@@ -243,6 +264,14 @@ k_ht_probe_pairs(ProbeParams p)
 				isnull = true;
 			key[k] = cb_load_widen(p.okey[k], p.otype[k], row);
 			h = pg_hash_combine(h, pg_hash_datum(p.otype[k], key[k], p.odict[k]), false);
+		}
+		if (!isnull && p.ht.bloom)
+		{
+			uint32_t	w;
+			uint32_t	bits = ht_bloom_bits(h, &w, p.ht.bloom_mask);
+
+			if ((__ldg(p.ht.bloom + w) & bits) != bits)
+				isnull = true;		/* certainly absent */
 		}
 		if (!isnull)
 		{

@@ -191,30 +191,114 @@ cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
 		default:
 			return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink kind %s%lld unknown", "", s->kind);
 	}
-	/* stage boundaries: after every FILTER / PROBE (the stack is empty there) */
+	/* peephole: the three shapes nearly every plan on this path contains run as single fused ops
+	 * (no stack traffic): `col CMP const` quals, probes keyed by plain columns, a * (k - b) */
+	{
+		static CbpOp x[CBP_MAX_OPS];
+		int			n = 0;
+		int			i = 0;
+
+		while (i < p->nops)
+		{
+			const CbpOp *o = &d->ops[i];
+
+			if (i + 3 < p->nops && o[0].code == CBP_LOAD && o[1].code == CBP_CONST && o[2].code >= CBP_EQ && o[2].code <= CBP_GE &&
+				o[3].code == CBP_FILTER && d->cols[o[0].a].type != CB_FLOAT8 && o[0].a < 0x10000)
+			{
+				x[n].code = XOP_FILTER_COL;
+				x[n].a = o[0].a | (o[2].code << 16);
+				x[n].imm = o[1].imm;
+				n++;
+				i += 4;
+				continue;
+			}
+			if (i + 4 < p->nops && o[0].code == CBP_LOAD && o[1].code == CBP_CONST && o[2].code == CBP_LOAD && o[3].code == CBP_SUB &&
+				o[4].code == CBP_MUL && o[0].a < 0x8000 && o[2].a < 0x8000)
+			{
+				x[n].code = XOP_MULCSUB;
+				x[n].a = o[0].a | (o[2].a << 16);
+				x[n].imm = o[1].imm;
+				n++;
+				i += 5;
+				continue;
+			}
+			if (o[0].code == CBP_LOAD)
+			{
+				/* LOAD x nkeys then PROBE */
+				int			k = 0;
+
+				while (i + k < p->nops && d->ops[i + k].code == CBP_LOAD && k < CBP_MAX_KEYS && d->ops[i + k].a < 256)
+					k++;
+				if (i + k < p->nops && d->ops[i + k].code == CBP_PROBE && p->probes[d->ops[i + k].a].nkeys <= k)
+				{
+					int			nk = p->probes[d->ops[i + k].a].nkeys;
+					int			skip = k - nk;	/* leading LOADs that are not keys stay as they are */
+					uint64_t	cols = 0;
+
+					for (int j = 0; j < skip; j++)
+						x[n++] = d->ops[i + j];
+					for (int j = 0; j < nk; j++)
+						cols |= (uint64_t) d->ops[i + skip + j].a << (8 * j);
+					x[n].code = XOP_PROBE_COLS;
+					x[n].a = d->ops[i + k].a;
+					x[n].imm = (int64_t) cols;
+					n++;
+					i += k + 1;
+					continue;
+				}
+			}
+			x[n++] = *o;
+			i++;
+		}
+		memcpy(d->ops, x, sizeof(CbpOp) * (size_t) n);
+		d->nops = n;
+	}
+	/* stage boundaries: after every PROBE (rows die there and the stack is empty) */
 	{
 		int			ns = 0,
 					dep = 0;
 
 		d->stage_pc[ns++] = 0;
-		for (int i = 0; i < p->nops; i++)
+		for (int i = 0; i < d->nops; i++)
 		{
-			int			c = p->ops[i].code;
+			int			c = d->ops[i].code;
 
-			if (c == CBP_LOAD || c == CBP_CONST || c == CBP_DUP)
+			if (c == CBP_LOAD || c == CBP_CONST || c == CBP_DUP || c == XOP_MULCSUB)
 				dep++;
 			else if (c == CBP_FILTER || c == CBP_POP)
 				dep--;
 			else if (c == CBP_PROBE)
-				dep -= p->probes[p->ops[i].a].nkeys;
-			else if (c != CBP_NOT && c != CBP_I2F && c != CBP_END)
+				dep -= p->probes[d->ops[i].a].nkeys;
+			else if (c != CBP_NOT && c != CBP_I2F && c != CBP_END && c != XOP_FILTER_COL && c != XOP_PROBE_COLS)
 				dep--;
-			if ((c == CBP_FILTER || c == CBP_PROBE) && dep == 0 && ns < CBP_MAX_STAGES && i + 1 < p->nops)
+			if ((c == CBP_PROBE || c == XOP_PROBE_COLS) && dep == 0 && ns < CBP_MAX_STAGES && i + 1 < d->nops)
 				d->stage_pc[ns++] = i + 1;
 		}
-		d->nstages = ns;
-		d->stage_pc[ns] = p->nops;
 		d->nsrc = d->src_base + p->nprobes;
+		/* queue shapes; keep the per-CTA queue area within 24 KB so 8 CTAs (64 warps) stay resident:
+		 * the deepest cuts see the fewest rows and are dropped first */
+		for (;;)
+		{
+			int			words = 0,
+						probes = 0,
+						pc = 0;
+
+			for (int b = 0; b + 1 < ns; b++)
+			{
+				for (; pc < d->stage_pc[b + 1]; pc++)
+					if (d->ops[pc].code == CBP_PROBE || d->ops[pc].code == XOP_PROBE_COLS)
+						probes++;
+				d->q_off[b] = words;
+				d->q_ew[b] = d->src_base + probes + 1;
+				words += 64 * d->q_ew[b];
+			}
+			d->q_words = words;
+			if (words * 4 * 8 <= 24 * 1024 || ns <= 1)
+				break;
+			ns--;
+		}
+		d->nstages = ns;
+		d->stage_pc[ns] = d->nops;
 	}
 	d->status = ctx->d_status;
 	return CBGPU_OK;
@@ -232,6 +316,27 @@ fcmp_pg(double x, double y)
 	if (y != y)
 		return -1;
 	return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* fetch column `ci` for this lane's row: value widened to 64 bits, NULL flag */
+__device__ __forceinline__ int64_t
+gen_load_col(const PipeDev &P, int ci, const uint32_t *ridx, uint32_t rnull, bool alive, bool *isnull)
+{
+	const CbpColumn &c = P.cols[ci];
+	bool		n = (rnull >> c.src) & 1;
+	int64_t		v = 0;
+
+	if (alive && !n)
+	{
+		uint32_t	r = ridx[c.src];
+
+		if (c.nulls && c.nulls[r])
+			n = true;
+		else
+			v = cb_load_widen(c.data, c.type, r);
+	}
+	*isnull = n;
+	return v;
 }
 
 #define GEN_THREADS 256
@@ -254,8 +359,9 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 	const int	lane = threadIdx.x & 31;
 	const int	warp_in_cta = threadIdx.x >> 5;
 	const int	nq = P.nstages - 1;			/* queues per warp */
-	const int	ew = P.nsrc + 1;			/* words per queue entry: row ids + NULL-extension mask */
-	uint32_t   *myq = gen_smem + (size_t) warp_in_cta * nq * GEN_QCAP * ew;
+	/* queue b's entries hold the row ids of the sources known after stage b, plus the NULL-extension
+	 * mask: q_ew[b] words each, at word offset q_off[b] of the warp's area */
+	uint32_t   *myq = gen_smem + (size_t) warp_in_cta * P.q_words;
 	int			qcnt[CBP_MAX_STAGES];		/* warp-uniform */
 	const int64_t nchunks = (P.nrows + 31) / 32;
 	int64_t		chunk = (int64_t) blockIdx.x * (GEN_THREADS / 32) + warp_in_cta;
@@ -328,7 +434,8 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 		else
 		{
 			/* pop the newest `navail` entries of the queue feeding this stage */
-			uint32_t   *q = myq + (size_t) (stage - 1) * GEN_QCAP * ew;
+			uint32_t   *q = myq + P.q_off[stage - 1];
+			const int	ew = P.q_ew[stage - 1];
 			const int	first = qcnt[stage - 1] - navail;
 
 			alive = lane < navail;
@@ -336,9 +443,9 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 			{
 				const uint32_t *e = q + (size_t) (first + lane) * ew;
 
-				for (int s = 0; s < P.nsrc; s++)
+				for (int s = 0; s < ew - 1; s++)
 					ridx[s] = e[s];
-				rnull = e[P.nsrc];
+				rnull = e[ew - 1];
 			}
 			qcnt[stage - 1] = first;
 			__syncwarp();
@@ -356,7 +463,47 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 
 			if (code == CBP_END)
 				break;
-			if (code == CBP_PROBE)
+			if (code == XOP_FILTER_COL)
+			{
+				/* fused LOAD col; CONST v; CMP; FILTER */
+				bool		isn;
+				int64_t		x = gen_load_col(P, a & 0xffff, ridx, rnull, alive, &isn);
+				int64_t		y = P.ops[pc].imm;
+				bool		r;
+
+				switch (a >> 16)
+				{
+					case CBP_EQ: r = x == y; break;
+					case CBP_NE: r = x != y; break;
+					case CBP_LT: r = x < y; break;
+					case CBP_LE: r = x <= y; break;
+					case CBP_GT: r = x > y; break;
+					default: r = x >= y; break;
+				}
+				if (isn || !r)
+					alive = false;
+				continue;
+			}
+			if (code == XOP_MULCSUB)
+			{
+				/* fused LOAD a; CONST k; LOAD b; SUB; MUL  ->  a * (k - b), overflow refused */
+				bool		an,
+							bn;
+				int64_t		x = gen_load_col(P, a & 0xffff, ridx, rnull, alive, &an);
+				int64_t		b = gen_load_col(P, a >> 16, ridx, rnull, alive, &bn);
+				int64_t		k = P.ops[pc].imm;
+				int64_t		d = (int64_t) ((uint64_t) k - (uint64_t) b);
+				int64_t		r = (int64_t) ((uint64_t) x * (uint64_t) d);
+				bool		ovf = (((k ^ b) & (k ^ d)) < 0) || (__mul64hi(x, d) != (r >> 63));
+
+				if (alive && !an && !bn && ovf)
+					atomicExch(P.status, CBGPU_ERR_OVERFLOW);
+				st[sp] = r;
+				snull = (an || bn) ? (snull | (1ull << sp)) : (snull & ~(1ull << sp));
+				sp++;
+				continue;
+			}
+			if (code == CBP_PROBE || code == XOP_PROBE_COLS)
 			{
 				const DProbe &pr = P.probes[a];
 				uint32_t	h = 0;
@@ -365,16 +512,44 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 				bool		found = false;
 				uint32_t	irow = 0;
 
-				sp -= pr.nkeys;
-				for (int k = 0; k < pr.nkeys; k++)
+				if (code == CBP_PROBE)
 				{
-					key[k] = st[sp + k];
-					if ((snull >> (sp + k)) & 1)
-						knull = true;
-					h = pg_hash_combine(h, pg_hash_datum(pr.keytype[k], key[k], pr.keydict[k]), false);
+					sp -= pr.nkeys;
+					for (int k = 0; k < pr.nkeys; k++)
+					{
+						key[k] = st[sp + k];
+						if ((snull >> (sp + k)) & 1)
+							knull = true;
+					}
+					snull &= (1ull << sp) - 1;
 				}
-				snull &= (1ull << sp) - 1;
-				if (alive && !knull)
+				else
+				{
+					/* fused LOAD key columns; PROBE: the column indexes ride in imm, 8 bits each */
+					const uint64_t kc = (uint64_t) P.ops[pc].imm;
+
+					for (int k = 0; k < pr.nkeys; k++)
+					{
+						bool		isn;
+
+						key[k] = gen_load_col(P, (int) ((kc >> (8 * k)) & 0xff), ridx, rnull, alive, &isn);
+						if (isn)
+							knull = true;
+					}
+				}
+				for (int k = 0; k < pr.nkeys; k++)
+					h = pg_hash_combine(h, pg_hash_datum(pr.keytype[k], key[k], pr.keydict[k]), false);
+				bool		maybe = alive && !knull;
+
+				if (maybe && pr.ht.bloom)
+				{
+					/* runtime Bloom filter first: it is L2-resident, the table is not */
+					uint32_t	w;
+					uint32_t	bits = ht_bloom_bits(h, &w, pr.ht.bloom_mask);
+
+					maybe = (__ldg(pr.ht.bloom + w) & bits) == bits;
+				}
+				if (maybe)
 				{
 					uint32_t	pos = h & pr.ht.mask;
 
@@ -582,16 +757,17 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 		if (stage < nq)
 		{
 			/* survivors wait in the next queue (there is room: it held < 32 entries) */
-			uint32_t   *q = myq + (size_t) stage * GEN_QCAP * ew;
+			uint32_t   *q = myq + P.q_off[stage];
+			const int	ew = P.q_ew[stage];
 			const uint32_t m = __ballot_sync(0xffffffffu, alive);
 
 			if (alive)
 			{
 				uint32_t   *e = q + (size_t) (qcnt[stage] + __popc(m & ((1u << lane) - 1))) * ew;
 
-				for (int s = 0; s < P.nsrc; s++)
+				for (int s = 0; s < ew - 1; s++)
 					e[s] = ridx[s];
-				e[P.nsrc] = rnull;
+				e[ew - 1] = rnull;
 			}
 			qcnt[stage] += __popc(m);
 			__syncwarp();
@@ -707,7 +883,7 @@ cbgpu_pipeline_run(cbgpu_ctx *ctx, const CbPipeline *p)
 	{
 		int64_t		warps = (p->nrows + 31) / 32;
 		int64_t		blocks = (warps + 7) / 8;
-		size_t		smem = (size_t) (GEN_THREADS / 32) * (size_t) (d.nstages - 1) * GEN_QCAP * (size_t) (d.nsrc + 1) * sizeof(uint32_t);
+		size_t		smem = (size_t) (GEN_THREADS / 32) * (size_t) d.q_words * sizeof(uint32_t);
 		static bool attr_done = false;
 
 		if (blocks > (int64_t) ctx->sm_count * 8)

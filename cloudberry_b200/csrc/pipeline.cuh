@@ -7,6 +7,11 @@
 
 #define CBP_MAX_STAGES 12
 
+/* internal fused opcodes produced by the host-side peephole pass (never part of the C ABI) */
+#define XOP_FILTER_COL 100		/* a = col | cmp << 16, imm = constant                               */
+#define XOP_PROBE_COLS 101		/* a = probe, imm = key column indexes, 8 bits each                  */
+#define XOP_MULCSUB 102			/* a = colA | colB << 16, imm = k: push colA * (k - colB)            */
+
 struct DProbe
 {
 	HtDev		ht;
@@ -53,6 +58,9 @@ struct PipeDev
 	int32_t		nsrc;			/* sources in use                                                    */
 	int32_t		nstages;		/* program stages (cut after every FILTER / PROBE)                   */
 	int32_t		stage_pc[CBP_MAX_STAGES + 2];
+	int32_t		q_off[CBP_MAX_STAGES];	/* per-warp queue b: word offset and words per entry               */
+	int32_t		q_ew[CBP_MAX_STAGES];
+	int32_t		q_words;		/* words of queue space per warp                                     */
 	DProbe		probes[CBP_MAX_SRC - 1];
 	DSink		sink;
 	int		   *status;
@@ -151,4 +159,5 @@ sink_store(void *col, int type, uint64_t pos, int64_t v)
 int			cb_klog_begin(cbgpu_ctx *ctx, const char *name);
 void		cb_klog_end(cbgpu_ctx *ctx, int i);
 int			cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d);
+int			cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handled);
 int			cb_try_specialised(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handled);

@@ -1,0 +1,747 @@
+/*
+ * probe_chain.cu - K3 fused: scan -> range quals -> up to four N:1 hash-join probes -> sink, compiled
+ * (not interpreted), one persistent kernel whose stages run on full batches.
+ *
+ * Restates the outer side of ExecHashJoinImpl (backend/executor/nodeHashjoin.c:203-738):
+ * HJ_NEED_NEW_OUTER fetches the next outer tuple (here: the next row of the driving scan that
+ * passes its quals, ExecScan execScan.c:162), ExecHashGetHashValue hashes the join keys
+ * (nodeHash.c:2089), ExecScanHashBucket finds the match (nodeHash.c:2255), and the joined tuple
+ * feeds the next join's outer side - for the whole chain of joins at once, then the sink:
+ * hash aggregation (agg_fill_hash_table, nodeAgg.c:2726) or materialisation for a parent Hash /
+ * Motion.  Shapes covered: TPC-H Q3 / Q5 / Q10-style star and chain joins on integer keys.
+ *
+ * Design.  The pipeline is a chain of stages joined by queues of row-id tuples:
+ *
+ *     F      quals (+ visimap) over a tile of driving rows           -> queue 0 (shared memory)
+ *     B_j    Bloom filter of build side j (L2-resident)              -> queue 2j+1 (+ key hash)
+ *     H_j    hash table j (HBM), stored hash, key verification       -> queue 2j+2 (+ inner row id)
+ *     sink   aggregate / materialise
+ *
+ * A persistent CTA (4 per SM) schedules them itself: the deepest stage with a full batch
+ * (PC_BATCH entries, PC_U per thread) runs; otherwise the next tile is scanned; at the end the
+ * queues drain front to back.  So every stage always runs with full warps over rows that are still
+ * alive, a probe behind a selective qual, filter or join costs only its survivors (late
+ * materialisation: key and payload columns are gathered by row id in the stage that needs them),
+ * and inside a stage each thread issues the loads of its PC_U rows back to back before using any -
+ * the memory-level parallelism a row-at-a-time loop over dependent (column -> filter word -> slot ->
+ * key) loads lacks.  Queue 0 carries most rows and lives in shared memory; the deeper queues see
+ * few rows and live in a per-CTA slice of global memory that stays in L2.
+ */
+#include "pipeline.cuh"
+#include "xmatch.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#define PC_THREADS 256
+#define PC_TILE 2048			/* driving rows per run of stage F                                    */
+#define PC_BATCH 1024			/* queue entries per run of any other stage                           */
+#define PC_U (PC_BATCH / PC_THREADS)
+#define PC_Q0CAP (PC_BATCH + PC_TILE)
+#define PC_QCAP (2 * PC_BATCH)	/* a consumer runs at PC_BATCH, a producer adds at most PC_BATCH      */
+#define PC_MAXP 4
+#define PC_MAXOUT 8
+#define PC_NQ (2 * PC_MAXP + 1)
+
+struct PcCol
+{
+	const void *data;
+	const uint32_t *dict;
+	int32_t		type;
+	int32_t		src;			/* 0 = driving relation, 1 + j = inner side of probe j                */
+};
+
+struct PcFilter
+{
+	const int32_t *col;
+	int32_t		lo;
+	uint32_t	span;
+};
+
+struct PcProbe
+{
+	HtDev		ht;
+	int32_t		nkeys;
+	int32_t		jointype;
+	int32_t		kind;			/* 0: one int32 key, hashint4; 1: one int64 key, hashint8; 2: general */
+	PcCol		key[2];
+	int32_t		keytype[2];		/* hash function by the OUTER key's type (cross-type int4/int8 joins) */
+};
+
+struct PcParams
+{
+	int64_t		nrows;
+	const uint8_t *visimap;
+	int32_t		nfilters;
+	int32_t		np;
+	PcFilter	filt[2];
+	PcProbe		probe[PC_MAXP];
+	uint32_t   *qmem;			/* global queues: [CTA][q_cta_words]                                  */
+	int64_t		q_cta_words;
+	int32_t		q_off[PC_NQ];	/* queue k >= 1: word offset inside the CTA's slice                   */
+	/* sink */
+	int32_t		sink_kind;		/* CBP_SINK_AGG or CBP_SINK_MATERIALIZE                               */
+	AggDev		agg;
+	int32_t		nkeys;
+	PcCol		key[CBP_MAX_KEYS];
+	int32_t		naccs;
+	int32_t		acc_term[CBP_MAX_AGGS];	/* -1 = count, else index of the value term               */
+	int32_t		nterms;
+	int32_t		term_kind[2];	/* 0 = column a, 1 = a * (k - b)                                      */
+	PcCol		term_a[2], term_b[2];
+	long long	term_k[2];
+	int32_t		nout;
+	PcCol		out[PC_MAXOUT];
+	void	   *outcol[PC_MAXOUT];
+	int32_t		outtype[PC_MAXOUT];
+	unsigned long long *out_count;
+	int64_t		out_capacity;
+	int		   *status;
+};
+
+/* a queue as a stage sees it: word w of entry e at q[w * cap + e]; words 0 .. = row ids by source */
+struct PcQ
+{
+	const uint32_t *q;
+	uint32_t	cap;
+	uint32_t	iota_base;		/* q == NULL: entry e is driving row iota_base + e (no quals)         */
+};
+
+__device__ __forceinline__ uint32_t
+pc_row(const PcQ &Q, int src, uint32_t e)
+{
+	return Q.q ? Q.q[(size_t) src * Q.cap + e] : Q.iota_base + e;
+}
+
+__device__ __forceinline__ int64_t
+pc_load(const PcCol &c, const PcQ &Q, uint32_t e)
+{
+	return cb_load_widen(c.data, c.type, pc_row(Q, c.src, e));
+}
+
+/* reserve one output position per surviving lane: one shared-memory atomic per warp; every lane of
+ * the warp calls (full-mask ballot: the warp is converged afterwards) */
+__device__ __forceinline__ uint32_t
+pc_reserve(unsigned *cnt, bool alive)
+{
+	const unsigned m = __ballot_sync(0xffffffffu, alive);
+	const int	lane = threadIdx.x & 31;
+	unsigned	base = 0;
+
+	if (m == 0)
+		return 0;
+	if (lane == (__ffs(m) - 1))
+		base = atomicAdd(cnt, (unsigned) __popc(m));
+	base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+	return base + __popc(m & ((1u << lane) - 1));
+}
+
+template <int KIND>
+__device__ __forceinline__ uint32_t
+pc_key_hash(const PcProbe &pr, int64_t k0, int64_t k1)
+{
+	if (KIND == 0)
+		return pg_hash_combine(0u, pg_hash_uint32((uint32_t) (int32_t) k0), false);
+	if (KIND == 1)
+		return pg_hash_combine(0u, pg_hashint8(k0), false);
+	uint32_t	h = pg_hash_combine(0u, pg_hash_datum(pr.keytype[0], k0, pr.key[0].dict), false);
+
+	if (pr.nkeys > 1)
+		h = pg_hash_combine(h, pg_hash_datum(pr.keytype[1], k1, pr.key[1].dict), false);
+	return h;
+}
+
+template <int KIND>
+__device__ __forceinline__ int64_t
+pc_load_key0(const PcProbe &pr, uint32_t row)
+{
+	if (KIND == 0)
+		return (int64_t) __ldg((const int32_t *) pr.key[0].data + row);
+	if (KIND == 1)
+		return __ldg((const long long *) pr.key[0].data + row);
+	return cb_load_widen(pr.key[0].data, pr.key[0].type, row);
+}
+
+/* stage B_j: hash the join keys (ExecHashGetHashValue, nodeHash.c:2089) and test the build side's
+ * Bloom filter.  in: entries [base, base + n) of Q (j + 1 row ids); out: the same row ids + hash. */
+template <int KIND>
+__device__ __noinline__ void
+pc_stage_bloom(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t *out, unsigned *ocnt)
+{
+	/* an anti join keeps the rows WITHOUT a match: the filter cannot drop anything */
+	const bool	use_bloom = pr.ht.bloom != NULL && pr.jointype != CB_JOIN_ANTI;
+	uint32_t	e[PC_U], h[PC_U], w[PC_U], bits[PC_U], word[PC_U];
+	int64_t		k0[PC_U], k1[PC_U];
+	bool		v[PC_U];
+
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		const unsigned i = u * PC_THREADS + threadIdx.x;
+		uint32_t	r0;
+
+		v[u] = i < n;
+		e[u] = base + (v[u] ? i : 0u);
+		r0 = pc_row(Q, pr.key[0].src, e[u]);
+		k0[u] = pc_load_key0<KIND>(pr, r0);
+		k1[u] = (KIND == 2 && pr.nkeys > 1) ? pc_load(pr.key[1], Q, e[u]) : 0;
+	}
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		h[u] = pc_key_hash<KIND>(pr, k0[u], k1[u]);
+		bits[u] = ht_bloom_bits(h[u], &w[u], pr.ht.bloom_mask);
+	}
+	if (use_bloom)
+	{
+#pragma unroll
+		for (int u = 0; u < PC_U; u++)
+			word[u] = __ldg(pr.ht.bloom + w[u]);
+	}
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		const bool	pass = v[u] && (!use_bloom || (word[u] & bits[u]) == bits[u]);
+		const uint32_t pos = pc_reserve(ocnt, pass);
+
+		if (pass)
+		{
+			for (int s = 0; s <= j; s++)
+				out[(size_t) s * PC_QCAP + pos] = pc_row(Q, s, e[u]);
+			out[(size_t) (j + 1) * PC_QCAP + pos] = h[u];
+		}
+	}
+}
+
+/* stage H_j: ExecScanHashBucket (nodeHash.c:2255) for the rows that passed the filter: linear
+ * probing from hash & mask, stored hash compared first, then the key itself.
+ * in: j + 1 row ids + hash; out: j + 2 row ids. */
+template <int KIND>
+__device__ __noinline__ void
+pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t *out, unsigned *ocnt)
+{
+	uint32_t	e[PC_U], h[PC_U], pos[PC_U];
+	unsigned long long slot[PC_U];
+	bool		v[PC_U];
+
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		const unsigned i = u * PC_THREADS + threadIdx.x;
+
+		v[u] = i < n;
+		e[u] = base + (v[u] ? i : 0u);
+		h[u] = Q.q[(size_t) (j + 1) * Q.cap + e[u]];
+		pos[u] = h[u] & pr.ht.mask;
+	}
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+		slot[u] = v[u] ? __ldg(pr.ht.slots + pos[u]) : HT_EMPTY;
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		bool		found = false;
+		uint32_t	irow = 0;
+
+		if (slot[u] != HT_EMPTY)
+		{
+			const int64_t k0 = pc_load_key0<KIND>(pr, pc_row(Q, pr.key[0].src, e[u]));
+			const int64_t k1 = (KIND == 2 && pr.nkeys > 1) ? pc_load(pr.key[1], Q, e[u]) : 0;
+			unsigned long long x = slot[u];
+			uint32_t	p = pos[u];
+
+			while (x != HT_EMPTY)
+			{
+				if ((uint32_t) (x >> 32) == h[u])
+				{
+					const uint32_t r = (uint32_t) x;
+
+					if (cb_load_widen(pr.ht.keydata[0], pr.ht.keytype[0], r) == k0 &&
+						(KIND != 2 || pr.nkeys < 2 || cb_load_widen(pr.ht.keydata[1], pr.ht.keytype[1], r) == k1))
+					{
+						found = true;
+						irow = r;
+						break;
+					}
+				}
+				p = (p + 1) & pr.ht.mask;
+				x = __ldg(pr.ht.slots + p);
+			}
+		}
+		const bool	alive = v[u] && (pr.jointype == CB_JOIN_ANTI ? !found : found);
+		const uint32_t opos = pc_reserve(ocnt, alive);
+
+		if (alive)
+		{
+			for (int s = 0; s <= j; s++)
+				out[(size_t) s * PC_QCAP + opos] = pc_row(Q, s, e[u]);
+			out[(size_t) (j + 1) * PC_QCAP + opos] = irow;
+		}
+	}
+}
+
+/* sink over entries [base, base + n) of the last queue (np + 1 row ids) */
+__device__ __noinline__ void
+pc_stage_sink(const PcParams &P, PcQ Q, unsigned base, unsigned n, unsigned long long *s_obase)
+{
+	if (P.sink_kind == CBP_SINK_AGG)
+	{
+		for (unsigned b = 0; b < n; b += PC_THREADS)
+		{
+			const unsigned i = b + threadIdx.x;
+
+			if (i < n)
+			{
+				const uint32_t e = base + i;
+				int64_t		kv[CBP_MAX_KEYS];
+				uint32_t	h = 0;
+
+				/* TupleHashTableHash_internal (executor/execGrouping.c:437-495) */
+				for (int k = 0; k < P.nkeys; k++)
+				{
+					kv[k] = pc_load(P.key[k], Q, e);
+					h = pg_hash_combine(h, pg_hash_datum(P.key[k].type, kv[k], P.key[k].dict), false);
+				}
+				h = pg_murmurhash32(h);
+				int64_t		tv[2] = {0, 0};
+
+				for (int t = 0; t < P.nterms; t++)
+				{
+					int64_t		a = pc_load(P.term_a[t], Q, e);
+
+					if (P.term_kind[t] == 1)
+					{
+						int64_t		bb = pc_load(P.term_b[t], Q, e);
+						int64_t		k = P.term_k[t];
+						int64_t		d = (int64_t) ((uint64_t) k - (uint64_t) bb);
+						int64_t		r = (int64_t) ((uint64_t) a * (uint64_t) d);
+
+						/* numeric_mul / numeric_sub are exact; a product that leaves 64 bits is refused */
+						if ((((k ^ bb) & (k ^ d)) < 0) || (__mul64hi(a, d) != (r >> 63)))
+							atomicExch(P.status, CBGPU_ERR_OVERFLOW);
+						tv[t] = r;
+					}
+					else
+						tv[t] = a;
+				}
+				int			slot = agg_find_or_insert(P.agg, h, kv, 0);
+
+				if (slot >= 0)
+					for (int a = 0; a < P.naccs; a++)
+					{
+						atomicAdd((unsigned long long *) (P.agg.n + (size_t) slot * P.agg.naccs + a), 1ull);
+						if (P.acc_term[a] >= 0)
+							atomic_add128_signed(P.agg.sum + ((size_t) slot * P.agg.naccs + a) * 2, tv[P.acc_term[a]]);
+					}
+			}
+			__syncwarp();		/* lanes that waited on a group being created rejoin before the next trip */
+		}
+	}
+	else
+	{
+		/* one reservation of n output rows per run, then coalesced stores */
+		if (threadIdx.x == 0)
+			*s_obase = atomicAdd(P.out_count, (unsigned long long) n);
+		__syncthreads();
+		const unsigned long long ob = *s_obase;
+
+		if ((int64_t) (ob + n) > P.out_capacity)
+		{
+			if (threadIdx.x == 0)
+				atomicExch(P.status, CBGPU_ERR_NOMEM);
+		}
+		else
+			for (unsigned i = threadIdx.x; i < n; i += PC_THREADS)
+				for (int c = 0; c < P.nout; c++)
+					sink_store(P.outcol[c], P.outtype[c], ob + i, pc_load(P.out[c], Q, base + i));
+	}
+}
+
+__global__ void __launch_bounds__(PC_THREADS, 4)
+k_probe_chain(const __grid_constant__ PcParams P)
+{
+	__shared__ uint32_t q0[PC_Q0CAP];
+	__shared__ PcProbe sprobe[PC_MAXP];	/* the stages read their probe through a pointer: keep it near */
+	__shared__ unsigned cnt[PC_NQ];		/* entries waiting in queue k                                 */
+	__shared__ int s_stage;
+	__shared__ unsigned s_n, s_base;
+	__shared__ long long s_tile;
+	__shared__ unsigned long long s_obase;
+	const int	np = P.np;
+	const int	last = 2 * np + 1;		/* the sink's stage number; stage s reads queue s - 1         */
+	const bool	iota = P.nfilters == 0 && P.visimap == NULL;
+	const int64_t tile_rows = iota ? PC_BATCH : PC_TILE;
+	const int64_t ntiles = (P.nrows + tile_rows - 1) / tile_rows;
+	uint32_t   *const qg = P.qmem + (size_t) blockIdx.x * (size_t) P.q_cta_words;
+	int64_t		next_tile = blockIdx.x;	/* thread 0's */
+
+	if (threadIdx.x < PC_NQ)
+		cnt[threadIdx.x] = 0;
+	for (int i = threadIdx.x; i < (int) (np * sizeof(PcProbe) / sizeof(uint32_t)); i += PC_THREADS)
+		((uint32_t *) sprobe)[i] = ((const uint32_t *) P.probe)[i];
+	for (;;)
+	{
+		__syncthreads();				/* the previous run's pushes are in */
+		if (threadIdx.x == 0)
+		{
+			int			s = -1;
+			bool		from_tile = false;
+
+			/* the deepest stage with a full batch; else scan on; else drain front to back */
+			for (int k = last; k >= 1; k--)
+				if (cnt[k - 1] >= PC_BATCH)
+				{
+					s = k;
+					break;
+				}
+			if (s < 0)
+			{
+				if (next_tile < ntiles)
+				{
+					s = iota ? 1 : 0;
+					from_tile = true;
+					s_tile = next_tile;
+					next_tile += gridDim.x;
+				}
+				else
+					for (int k = 1; k <= last; k++)
+						if (cnt[k - 1] > 0)
+						{
+							s = k;
+							break;
+						}
+			}
+			if (s >= 1 && !from_tile)
+			{
+				const unsigned c = cnt[s - 1];
+				const unsigned n = c < PC_BATCH ? c : PC_BATCH;
+
+				s_n = n;
+				s_base = c - n;			/* the newest n entries */
+				cnt[s - 1] = c - n;
+			}
+			s_stage = from_tile ? -2 - s : s;	/* -2: F, -3: B_0 straight from the tile */
+		}
+		__syncthreads();
+		const int	code = s_stage;
+
+		if (code == -1)
+			break;
+		if (code == -2)
+		{
+			/* stage F: ExecQual on a tile of driving rows; all of a thread's loads first */
+			const int64_t base = s_tile * PC_TILE;
+			const unsigned nvalid = (unsigned) (P.nrows - base < PC_TILE ? P.nrows - base : PC_TILE);
+			int32_t		f0[PC_TILE / PC_THREADS], f1[PC_TILE / PC_THREADS];
+			uint8_t		vm[PC_TILE / PC_THREADS];
+
+#pragma unroll
+			for (int u = 0; u < PC_TILE / PC_THREADS; u++)
+			{
+				const unsigned o = u * PC_THREADS + threadIdx.x;
+				const bool	ok = o < nvalid;
+
+				f0[u] = (ok && P.nfilters > 0) ? __ldg(P.filt[0].col + base + o) : 0;
+				f1[u] = (ok && P.nfilters > 1) ? __ldg(P.filt[1].col + base + o) : 0;
+				vm[u] = (ok && P.visimap) ? __ldg(P.visimap + ((base + o) >> 3)) : (uint8_t) 0xff;
+			}
+#pragma unroll
+			for (int u = 0; u < PC_TILE / PC_THREADS; u++)
+			{
+				const unsigned o = u * PC_THREADS + threadIdx.x;
+				bool		alive = o < nvalid;
+
+				if (P.visimap)
+					alive = alive && ((vm[u] >> ((base + o) & 7)) & 1);
+				if (P.nfilters > 0)
+					alive = alive && (unsigned) (f0[u] - P.filt[0].lo) <= P.filt[0].span;
+				if (P.nfilters > 1)
+					alive = alive && (unsigned) (f1[u] - P.filt[1].lo) <= P.filt[1].span;
+				const uint32_t pos = pc_reserve(&cnt[0], alive);
+
+				if (alive)
+					q0[pos] = (uint32_t) (base + o);
+			}
+			continue;
+		}
+		int			s = code;
+		PcQ			Q;
+		unsigned	n = s_n,
+					base = s_base;
+
+		if (code == -3)
+		{
+			const int64_t tb = s_tile * PC_BATCH;
+
+			s = 1;
+			Q.q = NULL;
+			Q.cap = 0;
+			Q.iota_base = (uint32_t) tb;
+			n = (unsigned) (P.nrows - tb < PC_BATCH ? P.nrows - tb : PC_BATCH);
+			base = 0;
+		}
+		else if (s == 1)
+		{
+			Q.q = q0;
+			Q.cap = PC_Q0CAP;
+			Q.iota_base = 0;
+		}
+		else
+		{
+			Q.q = qg + P.q_off[s - 1];
+			Q.cap = PC_QCAP;
+			Q.iota_base = 0;
+		}
+		if (s == last)
+			pc_stage_sink(P, Q, base, n, &s_obase);
+		else
+		{
+			const int	j = (s - 1) >> 1;
+			const PcProbe &pr = sprobe[j];
+			uint32_t   *out = qg + P.q_off[s];
+
+			if (s & 1)
+			{
+				if (pr.kind == 0)
+					pc_stage_bloom<0>(pr, j, Q, base, n, out, &cnt[s]);
+				else if (pr.kind == 1)
+					pc_stage_bloom<1>(pr, j, Q, base, n, out, &cnt[s]);
+				else
+					pc_stage_bloom<2>(pr, j, Q, base, n, out, &cnt[s]);
+			}
+			else
+			{
+				if (pr.kind == 0)
+					pc_stage_ht<0>(pr, j, Q, base, n, out, &cnt[s]);
+				else if (pr.kind == 1)
+					pc_stage_ht<1>(pr, j, Q, base, n, out, &cnt[s]);
+				else
+					pc_stage_ht<2>(pr, j, Q, base, n, out, &cnt[s]);
+			}
+		}
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * matcher
+ * --------------------------------------------------------------------------------------------- */
+static bool
+pc_col(const CbPipeline *p, int c, PcCol *out, int base)
+{
+	if (p->cols[c].nulls != NULL || p->cols[c].type == CB_FLOAT8 || p->cols[c].type == CB_NUMERIC128)
+		return false;
+	out->data = p->cols[c].data;
+	out->dict = p->cols[c].dict_hash;
+	out->type = p->cols[c].type;
+	out->src = p->cols[c].src == 0 ? 0 : p->cols[c].src - base + 1;
+	return true;
+}
+
+int
+cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handled)
+{
+	static XProg x;
+	static PcParams P;
+	const CbpSink *s = &p->sink;
+	int			np = 0;
+	int			base = 1;
+	int			term_node[2] = {-1, -1};
+
+	*handled = false;
+	if (p->nprobes < 1 || p->nprobes > PC_MAXP || p->drv_nsrc != 0)
+		return CBGPU_OK;
+	if (s->kind != CBP_SINK_AGG && s->kind != CBP_SINK_MATERIALIZE)
+		return CBGPU_OK;
+	if (!xm_decompile(p, &x))
+		return CBGPU_OK;
+	memset(&P, 0, sizeof(P));
+	/* sections: quals (before the first probe only), then the probes in program order */
+	for (int i = 0; i < x.nsections; i++)
+	{
+		XSection   *sec = &x.sections[i];
+
+		if (sec->kind == 0)
+		{
+			int			code, col;
+			int64_t		v, lo = INT32_MIN, hi = INT32_MAX;
+
+			if (np > 0 || P.nfilters >= 2)
+				return CBGPU_OK;	/* a qual behind a join: generic kernel */
+			if (!xm_is_cmp_const(&x, sec->node, &code, &col, &v) || p->cols[col].src != 0 || p->cols[col].nulls ||
+				cb_type_w(p->cols[col].type) != 4)
+				return CBGPU_OK;
+			switch (code)
+			{
+				case CBP_EQ: lo = hi = v; break;
+				case CBP_LT: hi = v - 1; break;
+				case CBP_LE: hi = v; break;
+				case CBP_GT: lo = v + 1; break;
+				case CBP_GE: lo = v; break;
+				default: return CBGPU_OK;
+			}
+			if (lo > INT32_MAX || hi < INT32_MIN || lo > hi)
+				return CBGPU_OK;
+			P.filt[P.nfilters].col = (const int32_t *) p->cols[col].data;
+			P.filt[P.nfilters].lo = (int32_t) lo;
+			P.filt[P.nfilters].span = (uint32_t) (hi - lo);
+			P.nfilters++;
+		}
+		else
+		{
+			const CbpProbe *pp = &p->probes[sec->probe];
+			PcProbe    *q = &P.probe[np];
+
+			if (sec->probe != np || pp->nkeys > 2)
+				return CBGPU_OK;
+			if (pp->jointype != CB_JOIN_INNER && pp->jointype != CB_JOIN_SEMI && pp->jointype != CB_JOIN_ANTI)
+				return CBGPU_OK;
+			if ((pp->jointype != CB_JOIN_INNER) && np != p->nprobes - 1)
+				return CBGPU_OK;	/* semi / anti only as the last probe (its inner side has no columns) */
+			q->ht = d->probes[np].ht;
+			q->nkeys = pp->nkeys;
+			q->jointype = pp->jointype;
+			if (!q->ht.bloom)
+				return CBGPU_OK;
+			for (int k = 0; k < pp->nkeys; k++)
+			{
+				int			col;
+
+				if (!xm_is_load(&x, sec->keys[k], &col) || !pc_col(p, col, &q->key[k], base))
+					return CBGPU_OK;
+				if (q->key[k].src > np)
+					return CBGPU_OK;
+				q->keytype[k] = pp->keytype[k];
+				q->key[k].type = p->cols[col].type;
+				if (q->ht.keynulls[k])
+					return CBGPU_OK;
+			}
+			if (pp->nkeys == 1 && (q->key[0].type == CB_INT4 || q->key[0].type == CB_DATE) &&
+				(q->keytype[0] == CB_INT4 || q->keytype[0] == CB_DATE))
+				q->kind = 0;
+			else if (pp->nkeys == 1 && q->key[0].type == CB_INT8 && q->keytype[0] == CB_INT8)
+				q->kind = 1;
+			else
+				q->kind = 2;
+			np++;
+		}
+	}
+	if (np != p->nprobes)
+		return CBGPU_OK;
+	P.np = np;
+	P.nrows = p->nrows;
+	P.visimap = p->visimap;
+	P.status = ctx->d_status;
+	P.sink_kind = s->kind;
+	if (s->kind == CBP_SINK_AGG)
+	{
+		if (x.depth < s->nkeys)
+			return CBGPU_OK;
+		P.agg = d->sink.agg;
+		P.nkeys = s->nkeys;
+		for (int k = 0; k < s->nkeys; k++)
+		{
+			int			col;
+
+			if (!xm_is_load(&x, x.stack[k], &col) || !pc_col(p, col, &P.key[k], base))
+				return CBGPU_OK;
+			P.key[k].type = s->keytype[k];
+			P.key[k].dict = s->key_dict_hash[k];
+		}
+		P.naccs = s->naccs;
+		for (int a = 0; a < s->naccs; a++)
+		{
+			int			node, col, b, c;
+			int64_t		k;
+			int			t = -1;
+
+			if (s->accs[a].kind == CBP_ACC_COUNT && s->accs[a].arg < 0)
+			{
+				P.acc_term[a] = -1;
+				continue;
+			}
+			if (s->accs[a].kind != CBP_ACC_SUM_INT)
+				return CBGPU_OK;
+			node = x.stack[s->nkeys + s->accs[a].arg];
+			for (int u = 0; u < P.nterms; u++)
+				if (term_node[u] == node)
+					t = u;
+			if (t >= 0)
+			{
+				P.acc_term[a] = t;	/* aggregates over the same expression share the value */
+				continue;
+			}
+			if (P.nterms >= 2)
+				return CBGPU_OK;
+			t = P.nterms;
+			term_node[t] = node;
+			if (xm_is_rev(&x, node, &b, &k, &c))
+			{
+				P.term_kind[t] = 1;
+				P.term_k[t] = k;
+				if (!pc_col(p, b, &P.term_a[t], base) || !pc_col(p, c, &P.term_b[t], base))
+					return CBGPU_OK;
+			}
+			else if (xm_is_load(&x, node, &col))
+			{
+				P.term_kind[t] = 0;
+				if (!pc_col(p, col, &P.term_a[t], base))
+					return CBGPU_OK;
+			}
+			else
+				return CBGPU_OK;
+			P.nterms++;
+			P.acc_term[a] = t;
+		}
+	}
+	else
+	{
+		if (s->nout > PC_MAXOUT || x.depth != s->nout)
+			return CBGPU_OK;
+		P.nout = s->nout;
+		for (int c = 0; c < s->nout; c++)
+		{
+			int			col;
+
+			if (!xm_is_load(&x, x.stack[c], &col) || !pc_col(p, col, &P.out[c], base) || d->sink.outnull[c])
+				return CBGPU_OK;
+			P.outcol[c] = d->sink.outcol[c];
+			P.outtype[c] = d->sink.outtype[c];
+		}
+		P.out_count = d->sink.out_count;
+		P.out_capacity = d->sink.out_capacity;
+	}
+
+	/* persistent grid: 4 CTAs per SM; queue k >= 1 holds (k + 3) / 2 words per entry */
+	const bool	iota = P.nfilters == 0 && P.visimap == NULL;
+	const int64_t ntiles = (p->nrows + (iota ? PC_BATCH : PC_TILE) - 1) / (iota ? PC_BATCH : PC_TILE);
+	int			blocks = ctx->sm_count * 4;
+	int64_t		words = 0;
+
+	if (blocks > ntiles)
+		blocks = (int) ntiles;
+	for (int k = 1; k <= 2 * np; k++)
+	{
+		P.q_off[k] = (int32_t) words;
+		words += (int64_t) PC_QCAP * ((k + 3) / 2);
+	}
+	P.q_cta_words = words;
+	CB_CUDA(ctx, cudaMallocAsync(&P.qmem, (size_t) blocks * (size_t) words * sizeof(uint32_t), ctx->stream));
+	if (getenv("CBGPU_DEBUG"))
+		fprintf(stderr, "k_probe_chain: np %d nrows %lld tiles %lld blocks %d queue words/CTA %lld filters %d sink %d kinds %d %d %d %d\n", np,
+				(long long) P.nrows, (long long) ntiles, blocks, (long long) words, P.nfilters, P.sink_kind, P.probe[0].kind,
+				P.probe[1].kind, P.probe[2].kind, P.probe[3].kind);
+	CB_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
+	int			kl = cb_klog_begin(ctx, "k_probe_chain");
+
+	k_probe_chain<<<blocks, PC_THREADS, 0, ctx->stream>>>(P);
+	ctx->last_kernel_name = "k_probe_chain";
+	if (kl >= 0)
+		ctx->klog_name[kl] = ctx->last_kernel_name;
+	CB_LAUNCHED(ctx, "k_probe_chain");
+	cb_klog_end(ctx, kl);
+	CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
+	CB_CUDA(ctx, cudaFreeAsync(P.qmem, ctx->stream));
+	ctx->kernel_timed = true;
+	*handled = true;
+	return CBGPU_OK;
+}

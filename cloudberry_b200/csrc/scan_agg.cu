@@ -798,5 +798,9 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 int
 cb_try_specialised(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handled)
 {
-	return try_small_agg(ctx, p, d, handled);
+	int			rc = try_small_agg(ctx, p, d, handled);
+
+	if (rc != CBGPU_OK || *handled)
+		return rc;
+	return cb_try_probe_chain(ctx, p, d, handled);
 }

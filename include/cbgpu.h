@@ -79,6 +79,11 @@ double		cbgpu_last_kernel_ms(cbgpu_ctx *ctx);
 void		cbgpu_kernel_log_reset(cbgpu_ctx *ctx);
 int			cbgpu_kernel_log_longest(cbgpu_ctx *ctx, char *name, int namelen, double *ms);
 const char *cbgpu_last_kernel_name(cbgpu_ctx *ctx);
+/* launch trace (profiling aid): an event after every kernel launch between begin and end; end
+ * returns the number of entries, get returns entry i's name and its event-to-event time */
+int			cbgpu_trace_begin(cbgpu_ctx *ctx);
+int			cbgpu_trace_end(cbgpu_ctx *ctx);
+int			cbgpu_trace_get(cbgpu_ctx *ctx, int i, char *name, int namelen, double *ms);
 /* write `bytes` of HBM so the next timed kernel starts with a cold L2 */
 int			cbgpu_flush_l2(cbgpu_ctx *ctx);
 /* pinned host memory for the end-to-end (host buffers) path */

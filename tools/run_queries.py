@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--queries", default="q1,q3,q5")
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="print every kernel launch of one extra run with its time")
     args = ap.parse_args()
     ctx = capi.Context(0)
     rt, sz = device_tables(ctx, args.sf)
@@ -58,6 +59,13 @@ def main():
             res = ex.run(plan)
             times.append(ctx.timer_stop_ms())
         kn, km = ctx.longest_kernel()
+        if args.trace:
+            ctx.trace_begin()
+            ex.run(plan)
+            tr = ctx.trace_end()
+            print("trace %s: %d launches, %.3f ms" % (q, len(tr), sum(m for _, m in tr)))
+            for name, m in tr:
+                print("   %-28s %9.3f ms" % (name, m))
         ms = sorted(times)[len(times) // 2]
         print(json.dumps({"query": q, "sf": args.sf, "ms": ms, "rows_per_s": rows_in[q] / (ms / 1e3), "result_rows": len(res.rows),
                           "longest_kernel": kn, "longest_kernel_ms": km,
