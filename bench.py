@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-joins", action="store_true", help="skip the Q3 / Q5 join pipelines (extra keys q3, q5)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -287,6 +288,36 @@ def main():
         for p in host.values():
             G.cbgpu_host_free(p)
 
+    # ---- the join queries of the metric (Q3, Q5) on the same resident tables: N = 1 ----
+    joins = {}
+    if world == 1 and not args.no_joins:
+        from cloudberry_b200 import harness
+        rt_all, _ = harness.device_tables(ctx, args.sf, lineitem=li)
+        exj = capi.Executor(ctx, rt_all)
+        plans = {"q3": tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), 1), "q5": tpch.q5_plan(tpch.REGIONS.index("AMERICA"), 1)}
+        jsteps = max(3, min(args.steps, 10))
+        for q, plan in plans.items():
+            for _ in range(args.warmup):
+                r = exj.run(plan)
+            ctx.sync()
+            l0j = ctx.launches()
+            ctx.timer_start()
+            for _ in range(jsteps):
+                ctx.kernel_log_reset()
+                r = exj.run(plan)
+            qms = ctx.timer_stop_ms() / jsteps
+            kn, km = ctx.longest_kernel()
+            rows_in, nbytes = harness.query_rows_bytes(q, sz)
+            joins[q] = {"value": rows_in / (qms / 1e3), "unit": "rows/s", "ms_per_step": qms, "steps": jsteps, "rows_scanned": rows_in,
+                        "result_rows": len(r.rows), "gpu_launches_per_step": (ctx.launches() - l0j) // jsteps,
+                        "longest_kernel": kn, "longest_kernel_ms": km,
+                        "roofline": {"bound": "hbm", "achieved": nbytes / (qms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": nbytes / (qms / 1e3) / 1e9 / peak, "algorithmic_bytes": nbytes,
+                                     "note": "whole query (all pipelines, builds, top-N, host glue) against the projected base columns"}}
+        exj.close()
+        for r_ in rt_all[1:]:
+            r_.free()
+
     # ---- CPU baseline (rank 0, N = 1): the oracle, scalar, on a bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -311,6 +342,7 @@ def main():
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        line.update(joins)
         print(json.dumps(line))
     ex.close()
     li.free()

@@ -363,15 +363,85 @@ pg_hash_datum(int type, int64_t v, const uint32_t *dict)
 	}
 }
 
-/* Bloom word index and bit pattern of a 32-bit key hash (bits independent of the slot index) */
+/* Bloom word index and bit pattern of a 32-bit key hash: two multiplicative remixes, the word from
+ * the top bits of one, the two bit positions from the top bits of the other */
 CB_HD uint32_t
 ht_bloom_bits(uint32_t h, uint32_t *word, uint32_t bloom_mask)
 {
-	uint32_t	m = pg_murmurhash32(h ^ 0x9e3779b9u);
+	const uint32_t m1 = h * 0x9e3779b1u;
+	const uint32_t m2 = h * 0x85ebca6bu;
 
-	*word = m & bloom_mask;
-	return (1u << ((m >> 22) & 31)) | (1u << ((m >> 27) & 31));
+	*word = (m1 >> 4) & bloom_mask;
+	return (1u << (m2 >> 27)) | (1u << ((m2 >> 22) & 31));
 }
+
+#ifdef __CUDACC__
+/* L2 eviction-priority policies for per-load cache hints: columns streamed once should not push
+ * out the structures every row consults (Bloom filters, inter-stage queues) */
+__device__ __forceinline__ uint64_t
+l2_policy_evict_first(void)
+{
+	uint64_t	p;
+
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+
+__device__ __forceinline__ uint64_t
+l2_policy_evict_last(void)
+{
+	uint64_t	p;
+
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+
+__device__ __forceinline__ uint32_t
+ldg_hint_u32(const uint32_t *a, uint64_t pol)
+{
+	uint32_t	v;
+
+	asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+	return v;
+}
+
+__device__ __forceinline__ int32_t
+ldg_stream_s32(const int32_t *a, uint64_t pol)
+{
+	int32_t		v;
+
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+	return v;
+}
+
+__device__ __forceinline__ int64_t
+ldg_stream_s64(const long long *a, uint64_t pol)
+{
+	long long	v;
+
+	asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
+	return v;
+}
+
+__device__ __forceinline__ int4
+ldg_stream_v4(const int4 *a, uint64_t pol)
+{
+	int4		v;
+
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+				 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol));
+	return v;
+}
+
+__device__ __forceinline__ unsigned long long
+ldg_stream_u64(const unsigned long long *a, uint64_t pol)
+{
+	unsigned long long v;
+
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
+	return v;
+}
+#endif
 
 /* widen a column element to 64 bits (float8: raw bits) */
 __device__ __forceinline__ int64_t

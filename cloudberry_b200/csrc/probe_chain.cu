@@ -153,12 +153,15 @@ pc_key_hash(const PcProbe &pr, int64_t k0, int64_t k1)
 
 template <int KIND>
 __device__ __forceinline__ int64_t
-pc_load_key0(const PcProbe &pr, uint32_t row)
+pc_load_key0(const PcProbe &pr, uint32_t row, uint64_t pol_stream)
 {
+	/* a key column of the driving relation is read once, front to back: first in line for eviction */
 	if (KIND == 0)
-		return (int64_t) __ldg((const int32_t *) pr.key[0].data + row);
+		return pr.key[0].src == 0 ? (int64_t) ldg_stream_s32((const int32_t *) pr.key[0].data + row, pol_stream)
+			: (int64_t) __ldg((const int32_t *) pr.key[0].data + row);
 	if (KIND == 1)
-		return __ldg((const long long *) pr.key[0].data + row);
+		return pr.key[0].src == 0 ? ldg_stream_s64((const long long *) pr.key[0].data + row, pol_stream)
+			: __ldg((const long long *) pr.key[0].data + row);
 	return cb_load_widen(pr.key[0].data, pr.key[0].type, row);
 }
 
@@ -170,7 +173,10 @@ pc_stage_bloom(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint3
 {
 	/* an anti join keeps the rows WITHOUT a match: the filter cannot drop anything */
 	const bool	use_bloom = pr.ht.bloom != NULL && pr.jointype != CB_JOIN_ANTI;
-	uint32_t	e[PC_U], h[PC_U], w[PC_U], bits[PC_U], word[PC_U];
+	const uint64_t pol_stream = l2_policy_evict_first();
+	const uint64_t pol_keep = l2_policy_evict_last();
+	const int	lane = threadIdx.x & 31;
+	uint32_t	e[PC_U], h[PC_U], w[PC_U], bits[PC_U], word[PC_U], bal[PC_U];
 	int64_t		k0[PC_U], k1[PC_U];
 	bool		v[PC_U];
 
@@ -183,7 +189,7 @@ pc_stage_bloom(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint3
 		v[u] = i < n;
 		e[u] = base + (v[u] ? i : 0u);
 		r0 = pc_row(Q, pr.key[0].src, e[u]);
-		k0[u] = pc_load_key0<KIND>(pr, r0);
+		k0[u] = pc_load_key0<KIND>(pr, r0, pol_stream);
 		k1[u] = (KIND == 2 && pr.nkeys > 1) ? pc_load(pr.key[1], Q, e[u]) : 0;
 	}
 #pragma unroll
@@ -194,22 +200,40 @@ pc_stage_bloom(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint3
 	}
 	if (use_bloom)
 	{
+		/* the filter is consulted by every row: last in line for eviction from L2 */
 #pragma unroll
 		for (int u = 0; u < PC_U; u++)
-			word[u] = __ldg(pr.ht.bloom + w[u]);
+			word[u] = ldg_hint_u32(pr.ht.bloom + w[u], pol_keep);
 	}
+	/* one reservation per warp for all PC_U rows of every lane; entries stay in row order */
+	unsigned	tot = 0,
+				wb = 0;
+
 #pragma unroll
 	for (int u = 0; u < PC_U; u++)
 	{
 		const bool	pass = v[u] && (!use_bloom || (word[u] & bits[u]) == bits[u]);
-		const uint32_t pos = pc_reserve(ocnt, pass);
 
-		if (pass)
+		bal[u] = __ballot_sync(0xffffffffu, pass);
+		tot += __popc(bal[u]);
+	}
+	if (tot == 0)
+		return;
+	if (lane == 0)
+		wb = atomicAdd(ocnt, tot);
+	wb = __shfl_sync(0xffffffffu, wb, 0);
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		if ((bal[u] >> lane) & 1)
 		{
+			const uint32_t pos = wb + __popc(bal[u] & ((1u << lane) - 1));
+
 			for (int s = 0; s <= j; s++)
 				out[(size_t) s * PC_QCAP + pos] = pc_row(Q, s, e[u]);
 			out[(size_t) (j + 1) * PC_QCAP + pos] = h[u];
 		}
+		wb += __popc(bal[u]);
 	}
 }
 
@@ -220,7 +244,9 @@ template <int KIND>
 __device__ __noinline__ void
 pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t *out, unsigned *ocnt)
 {
-	uint32_t	e[PC_U], h[PC_U], pos[PC_U];
+	const uint64_t pol_stream = l2_policy_evict_first();
+	const int	lane = threadIdx.x & 31;
+	uint32_t	e[PC_U], h[PC_U], pos[PC_U], irow[PC_U], bal[PC_U];
 	unsigned long long slot[PC_U];
 	bool		v[PC_U];
 
@@ -237,15 +263,18 @@ pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t
 #pragma unroll
 	for (int u = 0; u < PC_U; u++)
 		slot[u] = v[u] ? __ldg(pr.ht.slots + pos[u]) : HT_EMPTY;
+	unsigned	tot = 0,
+				wb = 0;
+
 #pragma unroll
 	for (int u = 0; u < PC_U; u++)
 	{
 		bool		found = false;
-		uint32_t	irow = 0;
 
+		irow[u] = 0;
 		if (slot[u] != HT_EMPTY)
 		{
-			const int64_t k0 = pc_load_key0<KIND>(pr, pc_row(Q, pr.key[0].src, e[u]));
+			const int64_t k0 = pc_load_key0<KIND>(pr, pc_row(Q, pr.key[0].src, e[u]), pol_stream);
 			const int64_t k1 = (KIND == 2 && pr.nkeys > 1) ? pc_load(pr.key[1], Q, e[u]) : 0;
 			unsigned long long x = slot[u];
 			uint32_t	p = pos[u];
@@ -260,7 +289,7 @@ pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t
 						(KIND != 2 || pr.nkeys < 2 || cb_load_widen(pr.ht.keydata[1], pr.ht.keytype[1], r) == k1))
 					{
 						found = true;
-						irow = r;
+						irow[u] = r;
 						break;
 					}
 				}
@@ -268,15 +297,27 @@ pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t
 				x = __ldg(pr.ht.slots + p);
 			}
 		}
-		const bool	alive = v[u] && (pr.jointype == CB_JOIN_ANTI ? !found : found);
-		const uint32_t opos = pc_reserve(ocnt, alive);
-
-		if (alive)
+		/* full-mask ballot: the warp reconverges here */
+		bal[u] = __ballot_sync(0xffffffffu, v[u] && (pr.jointype == CB_JOIN_ANTI ? !found : found));
+		tot += __popc(bal[u]);
+	}
+	if (tot == 0)
+		return;
+	if (lane == 0)
+		wb = atomicAdd(ocnt, tot);
+	wb = __shfl_sync(0xffffffffu, wb, 0);
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		if ((bal[u] >> lane) & 1)
 		{
+			const uint32_t opos = wb + __popc(bal[u] & ((1u << lane) - 1));
+
 			for (int s = 0; s <= j; s++)
 				out[(size_t) s * PC_QCAP + opos] = pc_row(Q, s, e[u]);
-			out[(size_t) (j + 1) * PC_QCAP + opos] = irow;
+			out[(size_t) (j + 1) * PC_QCAP + opos] = irow[u];
 		}
+		wb += __popc(bal[u]);
 	}
 }
 
@@ -357,6 +398,16 @@ pc_stage_sink(const PcParams &P, PcQ Q, unsigned base, unsigned n, unsigned long
 	}
 }
 
+/* bit u set when row u of the eight (a.x .. b.w) lies in [lo, lo + span] */
+__device__ __forceinline__ unsigned
+pc_range8(int4 a, int4 b, int32_t lo, uint32_t span)
+{
+	return ((unsigned) ((unsigned) (a.x - lo) <= span) << 0) | ((unsigned) ((unsigned) (a.y - lo) <= span) << 1) |
+		((unsigned) ((unsigned) (a.z - lo) <= span) << 2) | ((unsigned) ((unsigned) (a.w - lo) <= span) << 3) |
+		((unsigned) ((unsigned) (b.x - lo) <= span) << 4) | ((unsigned) ((unsigned) (b.y - lo) <= span) << 5) |
+		((unsigned) ((unsigned) (b.z - lo) <= span) << 6) | ((unsigned) ((unsigned) (b.w - lo) <= span) << 7);
+}
+
 __global__ void __launch_bounds__(PC_THREADS, 4)
 k_probe_chain(const __grid_constant__ PcParams P)
 {
@@ -429,39 +480,76 @@ k_probe_chain(const __grid_constant__ PcParams P)
 			break;
 		if (code == -2)
 		{
-			/* stage F: ExecQual on a tile of driving rows; all of a thread's loads first */
+			/* stage F: ExecQual on a tile of driving rows.  A thread owns 8 consecutive rows: its qual
+			 * columns arrive as two 16-byte loads each, issued before any is used; the survivors of
+			 * a warp's 256 rows go to queue 0 in row order with one warp scan and one atomic. */
 			const int64_t base = s_tile * PC_TILE;
 			const unsigned nvalid = (unsigned) (P.nrows - base < PC_TILE ? P.nrows - base : PC_TILE);
-			int32_t		f0[PC_TILE / PC_THREADS], f1[PC_TILE / PC_THREADS];
-			uint8_t		vm[PC_TILE / PC_THREADS];
+			const unsigned o0 = threadIdx.x * 8;
+			const int	lane = threadIdx.x & 31;
+			const uint64_t pol_stream = l2_policy_evict_first();
+			unsigned	am = 0;
 
-#pragma unroll
-			for (int u = 0; u < PC_TILE / PC_THREADS; u++)
+			if (o0 + 8 <= nvalid)
 			{
-				const unsigned o = u * PC_THREADS + threadIdx.x;
-				const bool	ok = o < nvalid;
+				int4		a0 = make_int4(0, 0, 0, 0), b0 = a0, a1 = a0, b1 = a0;
+				unsigned	vm = 0xff;
 
-				f0[u] = (ok && P.nfilters > 0) ? __ldg(P.filt[0].col + base + o) : 0;
-				f1[u] = (ok && P.nfilters > 1) ? __ldg(P.filt[1].col + base + o) : 0;
-				vm[u] = (ok && P.visimap) ? __ldg(P.visimap + ((base + o) >> 3)) : (uint8_t) 0xff;
-			}
-#pragma unroll
-			for (int u = 0; u < PC_TILE / PC_THREADS; u++)
-			{
-				const unsigned o = u * PC_THREADS + threadIdx.x;
-				bool		alive = o < nvalid;
-
-				if (P.visimap)
-					alive = alive && ((vm[u] >> ((base + o) & 7)) & 1);
 				if (P.nfilters > 0)
-					alive = alive && (unsigned) (f0[u] - P.filt[0].lo) <= P.filt[0].span;
+				{
+					a0 = ldg_stream_v4((const int4 *) (P.filt[0].col + base + o0), pol_stream);
+					b0 = ldg_stream_v4((const int4 *) (P.filt[0].col + base + o0) + 1, pol_stream);
+				}
 				if (P.nfilters > 1)
-					alive = alive && (unsigned) (f1[u] - P.filt[1].lo) <= P.filt[1].span;
-				const uint32_t pos = pc_reserve(&cnt[0], alive);
-
-				if (alive)
-					q0[pos] = (uint32_t) (base + o);
+				{
+					a1 = ldg_stream_v4((const int4 *) (P.filt[1].col + base + o0), pol_stream);
+					b1 = ldg_stream_v4((const int4 *) (P.filt[1].col + base + o0) + 1, pol_stream);
+				}
+				if (P.visimap)
+					vm = __ldg(P.visimap + ((base + o0) >> 3));
+				am = vm;
+				if (P.nfilters > 0)
+					am &= pc_range8(a0, b0, P.filt[0].lo, P.filt[0].span);
+				if (P.nfilters > 1)
+					am &= pc_range8(a1, b1, P.filt[1].lo, P.filt[1].span);
 			}
+			else
+				for (int u = 0; u < 8; u++)
+				{
+					const int64_t r = base + o0 + u;
+					bool		alive = o0 + u < nvalid;
+
+					if (alive && P.visimap)
+						alive = (__ldg(P.visimap + (r >> 3)) >> (r & 7)) & 1;
+					if (alive && P.nfilters > 0)
+						alive = (unsigned) (__ldg(P.filt[0].col + r) - P.filt[0].lo) <= P.filt[0].span;
+					if (alive && P.nfilters > 1)
+						alive = (unsigned) (__ldg(P.filt[1].col + r) - P.filt[1].lo) <= P.filt[1].span;
+					am |= (unsigned) alive << u;
+				}
+			const unsigned c = __popc(am);
+			unsigned	x = c;
+
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const unsigned y = __shfl_up_sync(0xffffffffu, x, d);
+
+				if (lane >= d)
+					x += y;
+			}
+			const unsigned total = __shfl_sync(0xffffffffu, x, 31);
+			unsigned	wb = 0;
+
+			if (lane == 31 && total)
+				wb = atomicAdd(&cnt[0], total);
+			wb = __shfl_sync(0xffffffffu, wb, 31);
+			unsigned	pos = wb + x - c;
+
+#pragma unroll
+			for (int u = 0; u < 8; u++)
+				if ((am >> u) & 1)
+					q0[pos++] = (uint32_t) (base + o0 + u);
 			continue;
 		}
 		int			s = code;
@@ -537,6 +625,13 @@ pc_col(const CbPipeline *p, int c, PcCol *out, int base)
 	return true;
 }
 
+#define PC_REJECT(n) \
+	do { \
+		if (getenv("CBGPU_DEBUG")) \
+			fprintf(stderr, "k_probe_chain: pipeline not matched (reason %d, line %d)\n", n, __LINE__); \
+		return CBGPU_OK; \
+	} while (0)
+
 int
 cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handled)
 {
@@ -548,12 +643,12 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 	int			term_node[2] = {-1, -1};
 
 	*handled = false;
-	if (p->nprobes < 1 || p->nprobes > PC_MAXP || p->drv_nsrc != 0)
-		return CBGPU_OK;
+	if (p->nprobes < 0 || p->nprobes > PC_MAXP || p->drv_nsrc != 0)
+		PC_REJECT(1);		/* no probes at all is fine: quals -> sink (a filtered scan feeding a Hash or a Motion) */
 	if (s->kind != CBP_SINK_AGG && s->kind != CBP_SINK_MATERIALIZE)
-		return CBGPU_OK;
+		PC_REJECT(2);
 	if (!xm_decompile(p, &x))
-		return CBGPU_OK;
+		PC_REJECT(3);
 	memset(&P, 0, sizeof(P));
 	/* sections: quals (before the first probe only), then the probes in program order */
 	for (int i = 0; i < x.nsections; i++)
@@ -565,11 +660,11 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 			int			code, col;
 			int64_t		v, lo = INT32_MIN, hi = INT32_MAX;
 
-			if (np > 0 || P.nfilters >= 2)
-				return CBGPU_OK;	/* a qual behind a join: generic kernel */
+			if (np > 0)
+				PC_REJECT(4);	/* a qual behind a join: generic kernel */
 			if (!xm_is_cmp_const(&x, sec->node, &code, &col, &v) || p->cols[col].src != 0 || p->cols[col].nulls ||
 				cb_type_w(p->cols[col].type) != 4)
-				return CBGPU_OK;
+				PC_REJECT(5);
 			switch (code)
 			{
 				case CBP_EQ: lo = hi = v; break;
@@ -577,14 +672,40 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 				case CBP_LE: hi = v; break;
 				case CBP_GT: lo = v + 1; break;
 				case CBP_GE: lo = v; break;
-				default: return CBGPU_OK;
+				default: PC_REJECT(6);
 			}
 			if (lo > INT32_MAX || hi < INT32_MIN || lo > hi)
-				return CBGPU_OK;
-			P.filt[P.nfilters].col = (const int32_t *) p->cols[col].data;
-			P.filt[P.nfilters].lo = (int32_t) lo;
-			P.filt[P.nfilters].span = (uint32_t) (hi - lo);
-			P.nfilters++;
+				PC_REJECT(7);
+			if (hi > INT32_MAX)
+				hi = INT32_MAX;
+			if (lo < INT32_MIN)
+				lo = INT32_MIN;
+			if (((uintptr_t) p->cols[col].data & 15) != 0)
+				PC_REJECT(100);		/* stage F reads the qual columns 16 bytes at a time */
+			{
+				int			f = P.nfilters;
+
+				/* a second qual on the same column narrows the first one's range (date BETWEEN) */
+				for (int g = 0; g < P.nfilters; g++)
+					if (P.filt[g].col == (const int32_t *) p->cols[col].data)
+					{
+						const int64_t olo = P.filt[g].lo,
+									ohi = olo + (int64_t) P.filt[g].span;
+
+						lo = lo > olo ? lo : olo;
+						hi = hi < ohi ? hi : ohi;
+						f = g;
+					}
+				if (lo > hi)
+					PC_REJECT(7);
+				if (f == P.nfilters && P.nfilters >= 2)
+					PC_REJECT(4);
+				P.filt[f].col = (const int32_t *) p->cols[col].data;
+				P.filt[f].lo = (int32_t) lo;
+				P.filt[f].span = (uint32_t) (hi - lo);
+				if (f == P.nfilters)
+					P.nfilters++;
+			}
 		}
 		else
 		{
@@ -592,28 +713,28 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 			PcProbe    *q = &P.probe[np];
 
 			if (sec->probe != np || pp->nkeys > 2)
-				return CBGPU_OK;
+				PC_REJECT(8);
 			if (pp->jointype != CB_JOIN_INNER && pp->jointype != CB_JOIN_SEMI && pp->jointype != CB_JOIN_ANTI)
-				return CBGPU_OK;
+				PC_REJECT(9);
 			if ((pp->jointype != CB_JOIN_INNER) && np != p->nprobes - 1)
-				return CBGPU_OK;	/* semi / anti only as the last probe (its inner side has no columns) */
+				PC_REJECT(10);	/* semi / anti only as the last probe (its inner side has no columns) */
 			q->ht = d->probes[np].ht;
 			q->nkeys = pp->nkeys;
 			q->jointype = pp->jointype;
 			if (!q->ht.bloom)
-				return CBGPU_OK;
+				PC_REJECT(11);
 			for (int k = 0; k < pp->nkeys; k++)
 			{
 				int			col;
 
 				if (!xm_is_load(&x, sec->keys[k], &col) || !pc_col(p, col, &q->key[k], base))
-					return CBGPU_OK;
+					PC_REJECT(12);
 				if (q->key[k].src > np)
-					return CBGPU_OK;
+					PC_REJECT(13);
 				q->keytype[k] = pp->keytype[k];
 				q->key[k].type = p->cols[col].type;
 				if (q->ht.keynulls[k])
-					return CBGPU_OK;
+					PC_REJECT(14);
 			}
 			if (pp->nkeys == 1 && (q->key[0].type == CB_INT4 || q->key[0].type == CB_DATE) &&
 				(q->keytype[0] == CB_INT4 || q->keytype[0] == CB_DATE))
@@ -626,7 +747,7 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 		}
 	}
 	if (np != p->nprobes)
-		return CBGPU_OK;
+		PC_REJECT(15);
 	P.np = np;
 	P.nrows = p->nrows;
 	P.visimap = p->visimap;
@@ -635,7 +756,7 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 	if (s->kind == CBP_SINK_AGG)
 	{
 		if (x.depth < s->nkeys)
-			return CBGPU_OK;
+			PC_REJECT(16);
 		P.agg = d->sink.agg;
 		P.nkeys = s->nkeys;
 		for (int k = 0; k < s->nkeys; k++)
@@ -643,7 +764,7 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 			int			col;
 
 			if (!xm_is_load(&x, x.stack[k], &col) || !pc_col(p, col, &P.key[k], base))
-				return CBGPU_OK;
+				PC_REJECT(17);
 			P.key[k].type = s->keytype[k];
 			P.key[k].dict = s->key_dict_hash[k];
 		}
@@ -660,7 +781,7 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 				continue;
 			}
 			if (s->accs[a].kind != CBP_ACC_SUM_INT)
-				return CBGPU_OK;
+				PC_REJECT(18);
 			node = x.stack[s->nkeys + s->accs[a].arg];
 			for (int u = 0; u < P.nterms; u++)
 				if (term_node[u] == node)
@@ -671,7 +792,7 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 				continue;
 			}
 			if (P.nterms >= 2)
-				return CBGPU_OK;
+				PC_REJECT(19);
 			t = P.nterms;
 			term_node[t] = node;
 			if (xm_is_rev(&x, node, &b, &k, &c))
@@ -679,16 +800,16 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 				P.term_kind[t] = 1;
 				P.term_k[t] = k;
 				if (!pc_col(p, b, &P.term_a[t], base) || !pc_col(p, c, &P.term_b[t], base))
-					return CBGPU_OK;
+					PC_REJECT(20);
 			}
 			else if (xm_is_load(&x, node, &col))
 			{
 				P.term_kind[t] = 0;
 				if (!pc_col(p, col, &P.term_a[t], base))
-					return CBGPU_OK;
+					PC_REJECT(21);
 			}
 			else
-				return CBGPU_OK;
+				PC_REJECT(22);
 			P.nterms++;
 			P.acc_term[a] = t;
 		}
@@ -696,14 +817,14 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 	else
 	{
 		if (s->nout > PC_MAXOUT || x.depth != s->nout)
-			return CBGPU_OK;
+			PC_REJECT(23);
 		P.nout = s->nout;
 		for (int c = 0; c < s->nout; c++)
 		{
 			int			col;
 
 			if (!xm_is_load(&x, x.stack[c], &col) || !pc_col(p, col, &P.out[c], base) || d->sink.outnull[c])
-				return CBGPU_OK;
+				PC_REJECT(24);
 			P.outcol[c] = d->sink.outcol[c];
 			P.outtype[c] = d->sink.outtype[c];
 		}
@@ -725,7 +846,7 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 		words += (int64_t) PC_QCAP * ((k + 3) / 2);
 	}
 	P.q_cta_words = words;
-	CB_CUDA(ctx, cudaMallocAsync(&P.qmem, (size_t) blocks * (size_t) words * sizeof(uint32_t), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&P.qmem, (size_t) blocks * (size_t) (words ? words : 1) * sizeof(uint32_t), ctx->stream));
 	if (getenv("CBGPU_DEBUG"))
 		fprintf(stderr, "k_probe_chain: np %d nrows %lld tiles %lld blocks %d queue words/CTA %lld filters %d sink %d kinds %d %d %d %d\n", np,
 				(long long) P.nrows, (long long) ntiles, blocks, (long long) words, P.nfilters, P.sink_kind, P.probe[0].kind,

@@ -85,3 +85,42 @@ def _gloo_all_to_all(dist, rank, world, recv_list, send_list):
             reqs.append(dist.irecv(recv_list[peer], src=peer))
     for r in reqs:
         r.wait()
+
+
+def device_tables(ctx, sf, seed=42, lineitem=None):
+    """All six TPC-H relations of the queries on this path, generated on the device (csrc/gen.cu: the same
+    counter-based formulas as tpch.py) in range-table order; `lineitem` reuses an existing relation."""
+    from . import capi, tpch
+    sz = tpch.sizes(int(sf) if float(sf).is_integer() else sf)
+    G = ctx.L
+    rels = {}
+    for name in tpch.RT:
+        if name == "lineitem" and lineitem is not None:
+            rels[name] = lineitem
+            continue
+        types = [t for _, t in tpch.SCHEMA[name]]
+        rels[name] = capi.DeviceRelation(ctx, sz[name], types, name=name)
+    if lineitem is None:
+        ctx.check(G.cbgpu_gen_lineitem(ctx.h, rels["lineitem"].h, seed, 0, sz["supplier"], sz["part"]))
+    ctx.check(G.cbgpu_gen_orders(ctx.h, rels["orders"].h, seed, 0, sz["customer"]))
+    ctx.check(G.cbgpu_gen_customer(ctx.h, rels["customer"].h, seed))
+    ctx.check(G.cbgpu_gen_supplier(ctx.h, rels["supplier"].h, seed))
+    nation, region = tpch.gen_nation_region()
+    rels["nation"].load(tpch._rel("nation", nation, {"n_name": tpch.NATIONS}).set_dict_hashes(capi.hashbpchar))
+    rels["region"].load(tpch._rel("region", region, {"r_name": tpch.REGIONS}).set_dict_hashes(capi.hashbpchar))
+    rels["customer"].set_dict_hash(2, np.array([capi.hashbpchar(s) for s in tpch.SEGMENTS], dtype=np.uint32))
+    ctx.sync()
+    return [rels[n] for n in tpch.RT], sz
+
+
+# projected bytes per row of every base table a query scans (SURVEY.md 8d: each projected column once)
+QUERY_BYTES = {
+    "q3": {"lineitem": 28, "orders": 20, "customer": 5},
+    "q5": {"lineitem": 28, "orders": 16, "customer": 8, "supplier": 8, "nation": 9, "region": 5},
+}
+
+
+def query_rows_bytes(q, sz):
+    rows = sum(sz[t] for t in QUERY_BYTES[q])
+    nbytes = sum(sz[t] * w for t, w in QUERY_BYTES[q].items())
+    return rows, nbytes

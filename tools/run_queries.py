@@ -12,26 +12,7 @@ sys.path.insert(0, ROOT)
 from cloudberry_b200 import capi, tpch  # noqa: E402
 
 
-def device_tables(ctx, sf, seed=42):
-    sz = tpch.sizes(int(sf) if float(sf).is_integer() else sf)
-    G = ctx.L
-    rels = {}
-    for name in tpch.RT:
-        types = [t for _, t in tpch.SCHEMA[name]]
-        rels[name] = capi.DeviceRelation(ctx, sz[name], types, name=name)
-    ctx.check(G.cbgpu_gen_lineitem(ctx.h, rels["lineitem"].h, seed, 0, sz["supplier"], sz["part"]))
-    ctx.check(G.cbgpu_gen_orders(ctx.h, rels["orders"].h, seed, 0, sz["customer"]))
-    ctx.check(G.cbgpu_gen_customer(ctx.h, rels["customer"].h, seed))
-    ctx.check(G.cbgpu_gen_supplier(ctx.h, rels["supplier"].h, seed))
-    nation, region = tpch.gen_nation_region()
-    hn = tpch._rel("nation", nation, {"n_name": tpch.NATIONS}).set_dict_hashes(capi.hashbpchar)
-    hr = tpch._rel("region", region, {"r_name": tpch.REGIONS}).set_dict_hashes(capi.hashbpchar)
-    rels["nation"].load(hn)
-    rels["region"].load(hr)
-    import numpy as np
-    rels["customer"].set_dict_hash(2, np.array([capi.hashbpchar(s) for s in tpch.SEGMENTS], dtype=np.uint32))
-    ctx.sync()
-    return [rels[n] for n in tpch.RT], sz
+from cloudberry_b200.harness import device_tables  # noqa: E402
 
 
 def main():
