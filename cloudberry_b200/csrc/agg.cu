@@ -455,6 +455,158 @@ k_topn(TopnParams p)
 		p.out_idx[tid * p.k + j] = j < nbest ? best_row[j] : 0xFFFFFFFFu;
 }
 
+/* --- threshold selection: the usual case (n >> k) costs two streaming passes over ONE key column ---
+ * A: per-CTA minimum of the leading non-constant sort key, mapped so that smaller = sorts first;
+ * K: the k-th smallest CTA minimum T bounds the answer (k rows - those minima - are <= T);
+ * B: rows with key <= T become candidates (a few dozen when the key is not heavily tied);
+ * C: one CTA ranks the candidates with the full comparator. */
+#define TOPN_BLOCKS 1024
+#define TOPN_CAND 4096
+
+__device__ __forceinline__ unsigned long long
+topn_ukey(const TopnParams &p, int i, uint32_t row)
+{
+	unsigned long long u = (unsigned long long) cb_load_widen(p.key[i], p.keytype[i], row);
+
+	if (!p.uns[i])
+		u ^= 0x8000000000000000ull;
+	return p.desc[i] ? ~u : u;
+}
+
+__global__ void __launch_bounds__(256)
+k_topn_min(TopnParams p, int keyi, unsigned long long *bmin, unsigned long long *bmax)
+{
+	__shared__ unsigned long long smin[8], smax[8];
+	unsigned long long lo = ~0ull,
+				hi = 0;
+
+	for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < p.nin; i += (int64_t) gridDim.x * blockDim.x)
+	{
+		const unsigned long long u = topn_ukey(p, keyi, (uint32_t) i);
+
+		lo = u < lo ? u : lo;
+		hi = u > hi ? u : hi;
+	}
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		const unsigned long long a = __shfl_xor_sync(0xffffffffu, lo, o);
+		const unsigned long long b = __shfl_xor_sync(0xffffffffu, hi, o);
+
+		lo = a < lo ? a : lo;
+		hi = b > hi ? b : hi;
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		smin[threadIdx.x >> 5] = lo;
+		smax[threadIdx.x >> 5] = hi;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		for (int w = 1; w < 8; w++)
+		{
+			lo = smin[w] < lo ? smin[w] : lo;
+			hi = smax[w] > hi ? smax[w] : hi;
+		}
+		bmin[blockIdx.x] = lo;
+		bmax[blockIdx.x] = hi;
+	}
+}
+
+/* out[0] = k-th smallest block minimum (or the maximum when there are fewer than k blocks),
+ * out[1] = global minimum, out[2] = global maximum */
+__global__ void __launch_bounds__(TOPN_BLOCKS)
+k_topn_kth(const unsigned long long *bmin, const unsigned long long *bmax, int nblocks, int k, unsigned long long *out)
+{
+	__shared__ unsigned long long v[TOPN_BLOCKS];
+	__shared__ unsigned long long gmax;
+	const int	t = threadIdx.x;
+
+	v[t] = t < nblocks ? bmin[t] : ~0ull;
+	if (t == 0)
+	{
+		unsigned long long m = 0;
+
+		for (int i = 0; i < nblocks; i++)
+			m = bmax[i] > m ? bmax[i] : m;
+		gmax = m;
+	}
+	__syncthreads();
+	for (int size = 2; size <= TOPN_BLOCKS; size <<= 1)
+		for (int stride = size >> 1; stride > 0; stride >>= 1)
+		{
+			const int	partner = t ^ stride;
+
+			if (partner > t)
+			{
+				const bool	up = (t & size) == 0;
+				const unsigned long long a = v[t],
+							b = v[partner];
+
+				if ((a > b) == up)
+				{
+					v[t] = b;
+					v[partner] = a;
+				}
+			}
+			__syncthreads();
+		}
+	if (t == 0)
+	{
+		out[0] = nblocks >= k ? v[k - 1] : gmax;
+		out[1] = v[0];
+		out[2] = gmax;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_topn_filter(TopnParams p, int keyi, const unsigned long long *thr, uint32_t *cand, int *ncand)
+{
+	const unsigned long long T = thr[0];
+
+	for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < p.nin; i += (int64_t) gridDim.x * blockDim.x)
+		if (topn_ukey(p, keyi, (uint32_t) i) <= T)
+		{
+			const int	pos = atomicAdd(ncand, 1);
+
+			if (pos < TOPN_CAND)
+				cand[pos] = (uint32_t) i;
+		}
+}
+
+/* rank every candidate among the candidates with the full comparator; ranks < k are the answer */
+__global__ void __launch_bounds__(1024)
+k_topn_final(TopnParams p, const uint32_t *cand, const int *ncand, int64_t nall, uint32_t *out)
+{
+	const int	m = cand ? (*ncand < TOPN_CAND ? *ncand : TOPN_CAND) : (int) nall;
+
+	for (int j = threadIdx.x; j < p.k; j += blockDim.x)
+		out[j] = 0xFFFFFFFFu;
+	__syncthreads();
+	for (int i = threadIdx.x; i < m; i += blockDim.x)
+	{
+		const uint32_t ri = cand ? cand[i] : (uint32_t) i;
+		int64_t		ki[TOPN_MAXKEYS];
+		int			rank = 0;
+
+		for (int k = 0; k < p.nkeys; k++)
+			ki[k] = cb_load_widen(p.key[k], p.keytype[k], ri);
+		for (int j = 0; j < m && rank < p.k; j++)
+		{
+			const uint32_t rj = cand ? cand[j] : (uint32_t) j;
+			int64_t		kj[TOPN_MAXKEYS];
+
+			if (j == i)
+				continue;
+			for (int k = 0; k < p.nkeys; k++)
+				kj[k] = cb_load_widen(p.key[k], p.keytype[k], rj);
+			rank += topn_before(p, kj, rj, ki, ri);
+		}
+		if (rank < p.k)
+			out[rank] = ri;
+	}
+}
+
 extern "C" int
 cbgpu_topn(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const int32_t *descending, const int32_t *unsigned_cmp,
 		   int32_t nkeys, int64_t limit, uint32_t *host_idx, int64_t *nout)
@@ -486,6 +638,65 @@ cbgpu_topn(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const int32_t
 	*nout = 0;
 	if (rel->nrows == 0)
 		return CBGPU_OK;
+	{
+		/* threshold selection first (see above); the tournament below only when it cannot decide */
+		unsigned long long *scratch = NULL;		/* [TOPN_BLOCKS] minima, [TOPN_BLOCKS] maxima, [3] threshold / min / max */
+		uint32_t   *cand = NULL;
+		int		   *ncand = NULL;
+		unsigned long long h3[3];
+		int			hn = 0;
+		bool		done = false;
+
+		p.in_idx = NULL;
+		p.nin = rel->nrows;
+		CB_CUDA(ctx, cudaMallocAsync(&cand1, (TOPN_MAXK + 1) * sizeof(uint32_t), ctx->stream));
+		if (rel->nrows <= TOPN_CAND)
+		{
+			k_topn_final<<<1, 1024, 0, ctx->stream>>>(p, NULL, NULL, rel->nrows, cand1);
+			CB_LAUNCHED(ctx, "k_topn_final");
+			done = true;
+		}
+		else
+		{
+			int			nblocks = (int) ((rel->nrows + 63) / 64);	/* > TOPN_CAND rows: at least TOPN_MAXK blocks */
+
+			if (nblocks > TOPN_BLOCKS)
+				nblocks = TOPN_BLOCKS;
+			CB_CUDA(ctx, cudaMallocAsync(&scratch, (2 * TOPN_BLOCKS + 3) * sizeof(unsigned long long), ctx->stream));
+			CB_CUDA(ctx, cudaMallocAsync(&cand, TOPN_CAND * sizeof(uint32_t), ctx->stream));
+			CB_CUDA(ctx, cudaMallocAsync(&ncand, sizeof(int), ctx->stream));
+			for (int keyi = 0; keyi < nkeys && !done; keyi++)
+			{
+				k_topn_min<<<nblocks, 256, 0, ctx->stream>>>(p, keyi, scratch, scratch + TOPN_BLOCKS);
+				CB_LAUNCHED(ctx, "k_topn_min");
+				k_topn_kth<<<1, TOPN_BLOCKS, 0, ctx->stream>>>(scratch, scratch + TOPN_BLOCKS, nblocks, p.k, scratch + 2 * TOPN_BLOCKS);
+				CB_LAUNCHED(ctx, "k_topn_kth");
+				CB_CUDA(ctx, cudaMemcpyAsync(h3, scratch + 2 * TOPN_BLOCKS, sizeof(h3), cudaMemcpyDeviceToHost, ctx->stream));
+				CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				if (h3[1] == h3[2])
+					continue;	/* a constant key (e.g. the high half of small 128-bit sums) decides nothing */
+				CB_CUDA(ctx, cudaMemsetAsync(ncand, 0, sizeof(int), ctx->stream));
+				k_topn_filter<<<nblocks, 256, 0, ctx->stream>>>(p, keyi, scratch + 2 * TOPN_BLOCKS, cand, ncand);
+				CB_LAUNCHED(ctx, "k_topn_filter");
+				CB_CUDA(ctx, cudaMemcpyAsync(&hn, ncand, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+				CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				if (hn <= TOPN_CAND)
+				{
+					k_topn_final<<<1, 1024, 0, ctx->stream>>>(p, cand, ncand, 0, cand1);
+					CB_LAUNCHED(ctx, "k_topn_final");
+					done = true;
+				}
+				break;			/* heavily tied key: the tournament sorts it out */
+			}
+			CB_CUDA(ctx, cudaFreeAsync(scratch, ctx->stream));
+			CB_CUDA(ctx, cudaFreeAsync(cand, ctx->stream));
+			CB_CUDA(ctx, cudaFreeAsync(ncand, ctx->stream));
+		}
+		if (done)
+			goto fetch;
+		CB_CUDA(ctx, cudaFreeAsync(cand1, ctx->stream));
+		cand1 = NULL;
+	}
 	/* tournament: every pass gives each thread ~64 candidates and keeps its best k, until one thread
 	 * holds the answer; passes shrink the candidate list by ~64 / k each */
 	{
@@ -528,6 +739,7 @@ cbgpu_topn(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const int32_t
 		}
 		(void) n2;
 	}
+fetch:
 	CB_CUDA(ctx, cudaMemcpyAsync(host_idx, cand1, limit * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	cudaFreeAsync(cand1, ctx->stream);

@@ -53,7 +53,8 @@ struct PcCol
 
 struct PcFilter
 {
-	const int32_t *col;
+	const void *col;			/* int32 / date column, or a 1-byte one (dictionary code, char(1), bool) */
+	int32_t		width;			/* 4 or 1                                                             */
 	int32_t		lo;
 	uint32_t	span;
 };
@@ -398,6 +399,23 @@ pc_stage_sink(const PcParams &P, PcQ Q, unsigned base, unsigned n, unsigned long
 	}
 }
 
+__device__ __forceinline__ int32_t
+pc_filter_value(const PcFilter &f, int64_t row)
+{
+	return f.width == 4 ? __ldg((const int32_t *) f.col + row) : (int32_t) __ldg((const uint8_t *) f.col + row);
+}
+
+/* eight consecutive 1-byte values as eight ints */
+__device__ __forceinline__ void
+pc_unpack8(unsigned long long v, int4 *a, int4 *b)
+{
+	const unsigned lo = (unsigned) v,
+				hi = (unsigned) (v >> 32);
+
+	*a = make_int4((int) (lo & 0xff), (int) ((lo >> 8) & 0xff), (int) ((lo >> 16) & 0xff), (int) (lo >> 24));
+	*b = make_int4((int) (hi & 0xff), (int) ((hi >> 8) & 0xff), (int) ((hi >> 16) & 0xff), (int) (hi >> 24));
+}
+
 /* bit u set when row u of the eight (a.x .. b.w) lies in [lo, lo + span] */
 __device__ __forceinline__ unsigned
 pc_range8(int4 a, int4 b, int32_t lo, uint32_t span)
@@ -495,15 +513,26 @@ k_probe_chain(const __grid_constant__ PcParams P)
 				int4		a0 = make_int4(0, 0, 0, 0), b0 = a0, a1 = a0, b1 = a0;
 				unsigned	vm = 0xff;
 
+				/* 8 rows of a 4-byte column are two 16-byte loads, of a 1-byte column one 8-byte load */
 				if (P.nfilters > 0)
 				{
-					a0 = ldg_stream_v4((const int4 *) (P.filt[0].col + base + o0), pol_stream);
-					b0 = ldg_stream_v4((const int4 *) (P.filt[0].col + base + o0) + 1, pol_stream);
+					if (P.filt[0].width == 4)
+					{
+						a0 = ldg_stream_v4((const int4 *) ((const int32_t *) P.filt[0].col + base + o0), pol_stream);
+						b0 = ldg_stream_v4((const int4 *) ((const int32_t *) P.filt[0].col + base + o0) + 1, pol_stream);
+					}
+					else
+						pc_unpack8(ldg_stream_u64((const unsigned long long *) ((const uint8_t *) P.filt[0].col + base + o0), pol_stream), &a0, &b0);
 				}
 				if (P.nfilters > 1)
 				{
-					a1 = ldg_stream_v4((const int4 *) (P.filt[1].col + base + o0), pol_stream);
-					b1 = ldg_stream_v4((const int4 *) (P.filt[1].col + base + o0) + 1, pol_stream);
+					if (P.filt[1].width == 4)
+					{
+						a1 = ldg_stream_v4((const int4 *) ((const int32_t *) P.filt[1].col + base + o0), pol_stream);
+						b1 = ldg_stream_v4((const int4 *) ((const int32_t *) P.filt[1].col + base + o0) + 1, pol_stream);
+					}
+					else
+						pc_unpack8(ldg_stream_u64((const unsigned long long *) ((const uint8_t *) P.filt[1].col + base + o0), pol_stream), &a1, &b1);
 				}
 				if (P.visimap)
 					vm = __ldg(P.visimap + ((base + o0) >> 3));
@@ -522,9 +551,9 @@ k_probe_chain(const __grid_constant__ PcParams P)
 					if (alive && P.visimap)
 						alive = (__ldg(P.visimap + (r >> 3)) >> (r & 7)) & 1;
 					if (alive && P.nfilters > 0)
-						alive = (unsigned) (__ldg(P.filt[0].col + r) - P.filt[0].lo) <= P.filt[0].span;
+						alive = (unsigned) (pc_filter_value(P.filt[0], r) - P.filt[0].lo) <= P.filt[0].span;
 					if (alive && P.nfilters > 1)
-						alive = (unsigned) (__ldg(P.filt[1].col + r) - P.filt[1].lo) <= P.filt[1].span;
+						alive = (unsigned) (pc_filter_value(P.filt[1], r) - P.filt[1].lo) <= P.filt[1].span;
 					am |= (unsigned) alive << u;
 				}
 			const unsigned c = __popc(am);
@@ -663,8 +692,14 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 			if (np > 0)
 				PC_REJECT(4);	/* a qual behind a join: generic kernel */
 			if (!xm_is_cmp_const(&x, sec->node, &code, &col, &v) || p->cols[col].src != 0 || p->cols[col].nulls ||
-				cb_type_w(p->cols[col].type) != 4)
+				(cb_type_w(p->cols[col].type) != 4 && cb_type_w(p->cols[col].type) != 1))
 				PC_REJECT(5);
+			if (cb_type_w(p->cols[col].type) == 1)
+			{
+				/* 1-byte columns hold unsigned values (cb_load_widen): clamp the range to them */
+				lo = 0;
+				hi = 255;
+			}
 			switch (code)
 			{
 				case CBP_EQ: lo = hi = v; break;
@@ -687,7 +722,7 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 
 				/* a second qual on the same column narrows the first one's range (date BETWEEN) */
 				for (int g = 0; g < P.nfilters; g++)
-					if (P.filt[g].col == (const int32_t *) p->cols[col].data)
+					if (P.filt[g].col == p->cols[col].data)
 					{
 						const int64_t olo = P.filt[g].lo,
 									ohi = olo + (int64_t) P.filt[g].span;
@@ -700,7 +735,8 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 					PC_REJECT(7);
 				if (f == P.nfilters && P.nfilters >= 2)
 					PC_REJECT(4);
-				P.filt[f].col = (const int32_t *) p->cols[col].data;
+				P.filt[f].col = p->cols[col].data;
+				P.filt[f].width = cb_type_w(p->cols[col].type);
 				P.filt[f].lo = (int32_t) lo;
 				P.filt[f].span = (uint32_t) (hi - lo);
 				if (f == P.nfilters)
