@@ -88,7 +88,7 @@ struct PcParams
 	int32_t		naccs;
 	int32_t		acc_term[CBP_MAX_AGGS];	/* -1 = count, else index of the value term               */
 	int32_t		nterms;
-	int32_t		term_kind[2];	/* 0 = column a, 1 = a * (k - b)                                      */
+	int32_t		term_kind[2];	/* 0 = column a, 1 = a * (k - b), 2 = a - b, 3 = a + b                */
 	PcCol		term_a[2], term_b[2];
 	long long	term_k[2];
 	int32_t		nout;
@@ -360,6 +360,16 @@ pc_stage_sink(const PcParams &P, PcQ Q, unsigned base, unsigned n, unsigned long
 
 						/* numeric_mul / numeric_sub are exact; a product that leaves 64 bits is refused */
 						if ((((k ^ bb) & (k ^ d)) < 0) || (__mul64hi(a, d) != (r >> 63)))
+							atomicExch(P.status, CBGPU_ERR_OVERFLOW);
+						tv[t] = r;
+					}
+					else if (P.term_kind[t] >= 2)
+					{
+						const int64_t bb = pc_load(P.term_b[t], Q, e);
+						const int64_t r = P.term_kind[t] == 2 ? (int64_t) ((uint64_t) a - (uint64_t) bb) : (int64_t) ((uint64_t) a + (uint64_t) bb);
+
+						/* int8mi / int8pl raise "bigint out of range" (utils/adt/int8.c:448,427): refused */
+						if (P.term_kind[t] == 2 ? (((a ^ bb) & (a ^ r)) < 0) : ((~(a ^ bb) & (a ^ r)) < 0))
 							atomicExch(P.status, CBGPU_ERR_OVERFLOW);
 						tv[t] = r;
 					}
@@ -837,6 +847,13 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 				P.term_k[t] = k;
 				if (!pc_col(p, b, &P.term_a[t], base) || !pc_col(p, c, &P.term_b[t], base))
 					PC_REJECT(20);
+			}
+			else if ((x.nodes[node].code == CBP_SUB || x.nodes[node].code == CBP_ADD) && xm_is_load(&x, x.nodes[node].l, &b) &&
+					 xm_is_load(&x, x.nodes[node].r, &c))
+			{
+				P.term_kind[t] = x.nodes[node].code == CBP_SUB ? 2 : 3;
+				if (!pc_col(p, b, &P.term_a[t], base) || !pc_col(p, c, &P.term_b[t], base))
+					PC_REJECT(30);
 			}
 			else if (xm_is_load(&x, node, &col))
 			{
