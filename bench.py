@@ -288,34 +288,61 @@ def main():
         for p in host.values():
             G.cbgpu_host_free(p)
 
-    # ---- the join queries of the metric (Q3, Q5) on the same resident tables: N = 1 ----
+    # ---- the join queries of the metric (Q3, Q5).  N = 1: on the same resident tables.  N > 1: the BASELINE
+    # configs "TPC-H SF100 Q3 / Q5 on N GPU-segments": ONE SF-sized database distributed over the segments as the
+    # reference's DDL would (lineitem / orders by orderkey, customer by c_custkey, supplier by s_suppkey, nation
+    # and region replicated), plans with Redistribute Motions over NCCL; strong scaling ----
     joins = {}
-    if world == 1 and not args.no_joins:
+    if not args.no_joins:
         from cloudberry_b200 import harness
-        rt_all, _ = harness.device_tables(ctx, args.sf, lineitem=li)
-        exj = capi.Executor(ctx, rt_all)
-        plans = {"q3": tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), 1), "q5": tpch.q5_plan(tpch.REGIONS.index("AMERICA"), 1)}
+        if world == 1:
+            rt_all, _ = harness.device_tables(ctx, args.sf, lineitem=li)
+            exj = capi.Executor(ctx, rt_all)
+            owned = rt_all[1:]
+        else:
+            ex.close()
+            ex = None
+            li.free()           # the weak-scaling Q1 shard makes room for the distributed database
+            li = None
+            rt_all, _ = harness.distributed_tables(ctx, motion, args.sf, rank, world)
+            exj = capi.Executor(ctx, rt_all, motion=motion)
+            owned = rt_all
+        plans = {"q3": tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), world, customer_replicated=False),
+                 "q5": tpch.q5_plan(tpch.REGIONS.index("AMERICA"), world, replicated=False)}
         jsteps = max(3, min(args.steps, 10))
         for q, plan in plans.items():
             for _ in range(args.warmup):
                 r = exj.run(plan)
-            ctx.sync()
+            barrier()
             l0j = ctx.launches()
+            sent0 = motion.bytes_sent() if motion else 0
             ctx.timer_start()
             for _ in range(jsteps):
                 ctx.kernel_log_reset()
                 r = exj.run(plan)
             qms = ctx.timer_stop_ms() / jsteps
             kn, km = ctx.longest_kernel()
+            nres = len(r.rows)
+            sent = (motion.bytes_sent() - sent0) / jsteps if motion else 0
+            barrier()
+            if dist:
+                import torch
+                t = torch.tensor([qms, float(nres), float(sent)], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                qms, nres = float(t[0].item()), int(t[1].item())
+                t2 = torch.tensor([float(sent)], device="cuda")
+                dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+                sent = float(t2.item())
             rows_in, nbytes = harness.query_rows_bytes(q, sz)
             joins[q] = {"value": rows_in / (qms / 1e3), "unit": "rows/s", "ms_per_step": qms, "steps": jsteps, "rows_scanned": rows_in,
-                        "result_rows": len(r.rows), "gpu_launches_per_step": (ctx.launches() - l0j) // jsteps,
-                        "longest_kernel": kn, "longest_kernel_ms": km,
-                        "roofline": {"bound": "hbm", "achieved": nbytes / (qms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                     "frac": nbytes / (qms / 1e3) / 1e9 / peak, "algorithmic_bytes": nbytes,
-                                     "note": "whole query (all pipelines, builds, top-N, host glue) against the projected base columns"}}
+                        "scaling": "strong" if world > 1 else "n/a", "result_rows": nres,
+                        "gpu_launches_per_step": (ctx.launches() - l0j) // jsteps,
+                        "longest_kernel": kn, "longest_kernel_ms": km, "motion_bytes_per_step": int(sent),
+                        "roofline": {"bound": "hbm", "achieved": nbytes / (qms / 1e3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                                     "frac": nbytes / (qms / 1e3) / 1e9 / (peak * world), "algorithmic_bytes": nbytes,
+                                     "note": "whole query (all pipelines, builds, Motions, top-N, host glue) against the projected base columns"}}
         exj.close()
-        for r_ in rt_all[1:]:
+        for r_ in owned:
             r_.free()
 
     # ---- CPU baseline (rank 0, N = 1): the oracle, scalar, on a bounded sample ----
@@ -344,8 +371,10 @@ def main():
             line["cpu_baseline"] = cpu
         line.update(joins)
         print(json.dumps(line))
-    ex.close()
-    li.free()
+    if ex:
+        ex.close()
+    if li:
+        li.free()
     if motion:
         motion.close()
     ctx.close()

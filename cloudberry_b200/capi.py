@@ -135,6 +135,8 @@ def gpu():
             "cbgpu_gen_orders": (C.c_int, [vp, vp, u64, i64, i64]),
             "cbgpu_gen_customer": (C.c_int, [vp, vp, u64]),
             "cbgpu_gen_supplier": (C.c_int, [vp, vp, u64]),
+            "cbgpu_gen_customer_range": (C.c_int, [vp, vp, u64, i64]),
+            "cbgpu_gen_supplier_range": (C.c_int, [vp, vp, u64, i64]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -164,6 +166,8 @@ def ex():
         L.cb_ExecProcNode.argtypes = [C.POINTER(CbPlanState)]
         L.cb_MultiExecProcNode.restype = vp
         L.cb_MultiExecProcNode.argtypes = [C.POINTER(CbPlanState)]
+        L.cb_ExecProcNodeBatch.restype = C.c_int
+        L.cb_ExecProcNodeBatch.argtypes = [C.POINTER(CbPlanState), C.POINTER(vp)]
         for n in ("cb_ExecEndNode", "cb_ExecReScan", "cb_ExecSquelchNode"):
             getattr(L, n).restype = None
             getattr(L, n).argtypes = [C.POINTER(CbPlanState)]
@@ -315,6 +319,20 @@ class DeviceRelation:
         self.nrows = nrows
 
     @classmethod
+    def adopt(cls, ctx, handle, name="batch"):
+        """Wrap a cbgpu_rel the library handed over (cb_ExecProcNodeBatch); this object now owns it."""
+        L = ctx.L
+        d = cls.__new__(cls)
+        d.ctx = ctx
+        d.name = name
+        d.h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+        n = int(L.cbgpu_rel_ncols(d.h))
+        d.types = [int(L.cbgpu_rel_col_type(d.h, i)) for i in range(n)]
+        d.dscales = [int(L.cbgpu_rel_col_dscale(d.h, i)) for i in range(n)]
+        d.nrows = int(L.cbgpu_rel_nrows(d.h))
+        return d
+
+    @classmethod
     def from_host(cls, ctx, rel: HostRelation):
         d = cls(ctx, rel.nrows, rel.types, rel.dscales, rel.name)
         d.load(rel)
@@ -446,6 +464,23 @@ class Executor:
         finally:
             E.cb_ExecEndNode(ps)
         return res
+
+    def run_batch(self, plan_node, name="batch"):
+        """The plan's whole output as one device-resident relation (cb_ExecProcNodeBatch)."""
+        E = self.E
+        es = self.estate
+        es.contents.es_errcode = 0
+        ps = E.cb_ExecInitNode(P.plan_ptr(plan_node), es, 0)
+        if not ps:
+            raise CbgpuError(es.contents.es_errcode, E.cb_estate_error(es).decode())
+        try:
+            h = C.c_void_p()
+            rc = E.cb_ExecProcNodeBatch(ps, C.byref(h))
+            if rc or es.contents.es_errcode:
+                raise CbgpuError(rc or es.contents.es_errcode, E.cb_estate_error(es).decode())
+            return DeviceRelation.adopt(self.ctx, h, name)
+        finally:
+            E.cb_ExecEndNode(ps)
 
     def close(self):
         if self.estate:

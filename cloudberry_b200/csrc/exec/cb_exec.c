@@ -2223,6 +2223,41 @@ exec_generic(CbPlanState *ps)
 	return slot;
 }
 
+/* Batch-oriented twin of ExecProcNode ("new native entry points are batch-oriented"):
+ * the node's whole output as ONE device-resident column batch instead of a slot per call.  The
+ * relation holds one column per scalar output (three per transition state: N, sum lo, sum hi) and
+ * becomes the caller's (cbgpu_rel_free).  For parents that can consume a batch - another GPU
+ * operator, a Motion sender, a loader distributing a table with `DISTRIBUTED BY`. */
+int
+cb_ExecProcNodeBatch(CbPlanState *ps, cbgpu_rel **out)
+{
+	CbEState   *es = ps->state;
+	NodePriv   *p = np(ps);
+	CbStream   *s;
+	cbgpu_rel  *rel = NULL;
+	PExpr		shape[MAX_OUT];
+	int			nshape;
+	int			found = -1;
+
+	*out = NULL;
+	if (ps->squelched || es->es_errcode)
+		return es->es_errcode ? es->es_errcode : CBGPU_ERR_INVALID;
+	if (ps->type == T_CbHash || ps->type == T_CbAgg || ps->type == T_CbLimitSort)
+		return es_fail(es, CBGPU_ERR_UNSUPPORTED, "batch output of node type %d (its result is finalised on the host)", (int) ps->type);
+	TRY(node_open(ps, &s));
+	TRY(stream_materialize(es, ps, s, &p->owned, &rel, shape, &nshape));
+	for (int i = 0; i < p->owned.nrels; i++)
+		if (p->owned.rels[i] == rel)
+			found = i;
+	if (found < 0)
+		return es_fail(es, CBGPU_ERR_INVALID, "batch output lost track of its relation");
+	p->owned.rels[found] = p->owned.rels[--p->owned.nrels];
+	ps->instrument.ntuples += (double) cbgpu_rel_nrows(rel);
+	ps->instrument.nloops += 1;
+	*out = rel;
+	return CBGPU_OK;
+}
+
 CbPlanState *
 cb_ExecInitNode(CbPlan *node, CbEState *estate, int eflags)
 {

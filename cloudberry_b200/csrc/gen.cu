@@ -165,22 +165,37 @@ cbgpu_gen_orders(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed, int64_t row_lo, 
 }
 
 __global__ void
-k_gen_keyed(int32_t *key, int32_t *nation, uint8_t *seg, int64_t n, uint64_t seed, uint64_t col_nation, uint64_t col_seg)
+k_gen_keyed(int32_t *key, int32_t *nation, uint8_t *seg, int64_t n, int64_t row_lo, uint64_t seed, uint64_t col_nation,
+			uint64_t col_seg)
 {
 	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	int64_t		stride = (int64_t) gridDim.x * blockDim.x;
 
 	for (; i < n; i += stride)
 	{
-		key[i] = (int32_t) (i + 1);
-		nation[i] = (int32_t) (gen_u(seed, col_nation, (uint64_t) i) % 25);
+		const int64_t r = row_lo + i;
+
+		key[i] = (int32_t) (r + 1);
+		nation[i] = (int32_t) (gen_u(seed, col_nation, (uint64_t) r) % 25);
 		if (seg)
-			seg[i] = (uint8_t) (gen_u(seed, col_seg, (uint64_t) i) % 5);
+			seg[i] = (uint8_t) (gen_u(seed, col_seg, (uint64_t) r) % 5);
 	}
 }
 
 extern "C" int
 cbgpu_gen_customer(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed)
+{
+	return cbgpu_gen_customer_range(ctx, rel, seed, 0);
+}
+
+extern "C" int
+cbgpu_gen_supplier(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed)
+{
+	return cbgpu_gen_supplier_range(ctx, rel, seed, 0);
+}
+
+extern "C" int
+cbgpu_gen_customer_range(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed, int64_t row_lo)
 {
 	const int	types[3] = {CB_INT4, CB_INT4, CB_DICT8};
 	int			rc = gen_check(ctx, rel, types, 3, "customer");
@@ -190,13 +205,13 @@ cbgpu_gen_customer(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed)
 	if (rel->nrows == 0)
 		return CBGPU_OK;
 	k_gen_keyed<<<gen_blocks(ctx, rel->nrows), 256, 0, ctx->stream>>>((int32_t *) rel->data[0], (int32_t *) rel->data[1],
-																		 (uint8_t *) rel->data[2], rel->nrows, seed, 31, 32);
+																		 (uint8_t *) rel->data[2], rel->nrows, row_lo, seed, 31, 32);
 	CB_LAUNCHED(ctx, "k_gen_keyed");
 	return CBGPU_OK;
 }
 
 extern "C" int
-cbgpu_gen_supplier(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed)
+cbgpu_gen_supplier_range(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed, int64_t row_lo)
 {
 	const int	types[2] = {CB_INT4, CB_INT4};
 	int			rc = gen_check(ctx, rel, types, 2, "supplier");
@@ -206,7 +221,7 @@ cbgpu_gen_supplier(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed)
 	if (rel->nrows == 0)
 		return CBGPU_OK;
 	k_gen_keyed<<<gen_blocks(ctx, rel->nrows), 256, 0, ctx->stream>>>((int32_t *) rel->data[0], (int32_t *) rel->data[1],
-																		 NULL, rel->nrows, seed, 41, 0);
+																		 NULL, rel->nrows, row_lo, seed, 41, 0);
 	CB_LAUNCHED(ctx, "k_gen_keyed");
 	return CBGPU_OK;
 }

@@ -124,3 +124,56 @@ def query_rows_bytes(q, sz):
     rows = sum(sz[t] for t in QUERY_BYTES[q])
     nbytes = sum(sz[t] * w for t, w in QUERY_BYTES[q].items())
     return rows, nbytes
+
+
+def distribute_by_hash(ctx, motion, rel, keycol, name):
+    """`DISTRIBUTED BY (key)` at load time: every rank holds a row-range slice `rel` of the table; a
+    Redistribute Motion (cdbhash + jump consistent hash of the key, NCCL all-to-all) leaves each rank with
+    the rows the reference would store on that segment.  Returns the shard as a device relation."""
+    from . import capi
+    from . import plan as P
+    ex = capi.Executor(ctx, [rel], motion=motion)
+    tl = [("c%d" % i, P.Var(1, i + 1, t, rel.dscales[i])) for i, t in enumerate(rel.types)]
+    scan = P.SeqScan(1, tl)
+    m = P.Motion(scan, P.MOTIONTYPE_HASH, [P.out_var(scan, keycol + 1)], motion.nranks)
+    out = ex.run_batch(m, name)
+    ex.close()
+    return out
+
+
+def distributed_tables(ctx, motion, sf, rank, world, seed=42):
+    """The six relations of an SF-sized database spread over `world` GPU-segments the way the reference's
+    DDL would: lineitem and orders by orderkey, customer by c_custkey, supplier by s_suppkey, nation and
+    region replicated.  Each rank generates a 1/world row range of every distributed table, then the
+    load-time Redistribute moves the rows to their segments."""
+    from . import capi, tpch
+    sz = tpch.sizes(int(sf) if float(sf).is_integer() else sf)
+    G = ctx.L
+    keys = {"lineitem": 0, "orders": 0, "customer": 0, "supplier": 0}
+    shards = {}
+    seg_hash = np.array([capi.hashbpchar(s) for s in tpch.SEGMENTS], dtype=np.uint32)
+    for name in ("lineitem", "orders", "customer", "supplier"):
+        n = sz[name]
+        lo, hi = rank * n // world, (rank + 1) * n // world
+        types = [t for _, t in tpch.SCHEMA[name]]
+        sl = capi.DeviceRelation(ctx, hi - lo, types, name=name + "_slice")
+        if name == "lineitem":
+            ctx.check(G.cbgpu_gen_lineitem(ctx.h, sl.h, seed, lo, sz["supplier"], sz["part"]))
+        elif name == "orders":
+            ctx.check(G.cbgpu_gen_orders(ctx.h, sl.h, seed, lo, sz["customer"]))
+        elif name == "customer":
+            ctx.check(G.cbgpu_gen_customer_range(ctx.h, sl.h, seed, lo))
+            sl.set_dict_hash(2, seg_hash)
+        else:
+            ctx.check(G.cbgpu_gen_supplier_range(ctx.h, sl.h, seed, lo))
+        ctx.sync()
+        shards[name] = distribute_by_hash(ctx, motion, sl, keys[name], name)
+        sl.free()
+    nation, region = tpch.gen_nation_region()
+    for name, cols, texts in (("nation", nation, {"n_name": tpch.NATIONS}), ("region", region, {"r_name": tpch.REGIONS})):
+        types = [t for _, t in tpch.SCHEMA[name]]
+        r = capi.DeviceRelation(ctx, sz[name], types, name=name)
+        r.load(tpch._rel(name, cols, texts).set_dict_hashes(capi.hashbpchar))
+        shards[name] = r
+    ctx.sync()
+    return [shards[n] for n in tpch.RT], sz

@@ -112,6 +112,11 @@ CbPlanState *cb_ExecInitNode(CbPlan *node, CbEState *estate, int eflags);
 CbTupleTableSlot *cb_ExecProcNode(CbPlanState *node);
 /* Hash nodes only: runs the build (MultiExecHash, nodeHash.c:130); returns the hash table */
 cbgpu_hashtable *cb_MultiExecProcNode(CbPlanState *node);
+/* batch-oriented twin of cb_ExecProcNode: the node's whole output as one device-resident column
+ * batch (one column per scalar output, N / sum-lo / sum-hi per transition state); the relation
+ * becomes the caller's.  Scan, HashJoin and Motion sub-trees; Agg / LimitSort finalise on the host
+ * and return CBGPU_ERR_UNSUPPORTED. */
+int			cb_ExecProcNodeBatch(CbPlanState *node, cbgpu_rel **out);
 void		cb_ExecEndNode(CbPlanState *node);
 void		cb_ExecReScan(CbPlanState *node);
 void		cb_ExecSquelchNode(CbPlanState *node);

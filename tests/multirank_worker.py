@@ -40,6 +40,21 @@ def main():
     seg = exp["dict"]["c_mktsegment_dict"].index("MACHINERY")
     reg = exp["dict"]["r_name_dict"].index("AMERICA")
     ok = True
+    # load-time DISTRIBUTED BY: every rank starts from a row-range slice of lineitem, the Redistribute Motion
+    # (batch output, cb_ExecProcNodeBatch) must leave it with exactly the oracle's cdbhash shard
+    import numpy as np
+    from cloudberry_b200 import harness
+    li = rels[0]
+    lo, hi = rank * li.nrows // world, (rank + 1) * li.nrows // world
+    sl = capi.DeviceRelation.from_host(ctx, li.take(np.arange(lo, hi)))
+    mine_li = harness.distribute_by_hash(ctx, motion, sl, li.attno("l_orderkey") - 1, "lineitem")
+    got = sorted(zip(*[mine_li.read_column(c)[0].tolist() for c in range(len(li.names))]))
+    want = sorted(zip(*[c.tolist() for c in mine[0].columns]))
+    if got != want:
+        ok = False
+        print("MULTIRANK FAIL: distribute_by_hash gave %d rows, the oracle's shard has %d" % (len(got), len(want)))
+    mine_li.free()
+    sl.free()
     r1 = ex.run(tpch.q1_plan(world))
     r3 = ex.run(tpch.q3_plan(seg, world, customer_replicated=replicated))
     r5 = ex.run(tpch.q5_plan(reg, world, replicated=replicated))
@@ -51,7 +66,7 @@ def main():
         if not ok:
             print(tpch.format_q1(r1.rows), tpch.format_q3(r3.rows), tpch.format_q5(r5.rows, exp["dict"]["n_name_dict"]))
     else:
-        ok = len(r1.rows) == 0 and len(r3.rows) == 0 and len(r5.rows) == 0     # only the gather receiver emits
+        ok = ok and len(r1.rows) == 0 and len(r3.rows) == 0 and len(r5.rows) == 0     # only the gather receiver emits
         if not ok:
             print("MULTIRANK FAIL: non-root rank emitted rows")
     flag = torch.tensor([0 if ok else 1], device="cuda")

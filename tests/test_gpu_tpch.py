@@ -134,3 +134,34 @@ def test_synthetic_vs_oracle(ctx, oracle, generic):
     ex.close()
     for d in dev:
         d.free()
+
+
+def test_exec_proc_node_batch(ctx, oracle, golden):
+    """cb_ExecProcNodeBatch: a sub-tree's output as one device-resident column batch (here the lower join of
+    Q3: orders (date qual) x customer (segment qual)), equal to the oracle's rows for the same plan node."""
+    rels, exp = golden
+    dev = to_device(ctx, rels)
+    ex = capi.Executor(ctx, dev)
+    seg = exp["dict"]["c_mktsegment_dict"].index("MACHINERY")
+    cutoff = tpch.date_to_days(1995, 3, 15)
+    cust = tpch._scan("customer", ["c_custkey"], [P.OpExpr(P.OP_EQ, tpch._svar("customer", "c_mktsegment"), P.Const(P.DICT8, seg))])
+    orders = tpch._scan("orders", ["o_orderkey", "o_custkey", "o_orderdate", "o_shippriority"],
+                        [P.OpExpr(P.OP_LT, tpch._svar("orders", "o_orderdate"), P.Const(P.DATE, cutoff))])
+    hc = P.Hash(cust, [P.out_var(cust, 1)])
+    j1 = P.HashJoin(P.JOIN_INNER, orders, hc, [P.out_var(orders, 2)],
+                    [("o_orderkey", P.out_var(orders, 1)), ("o_orderdate", P.out_var(orders, 3)),
+                     ("o_shippriority", P.out_var(orders, 4))])
+    batch = ex.run_batch(j1)
+    want = oracle.execute(j1, [rels])
+    assert batch.rows() == len(want.rows) > 0
+    got = list(zip(*[batch.read_column(c)[0].tolist() for c in range(3)]))
+    assert sorted(got) == sorted(tuple(r) for r in want.rows)
+    # and a filtered scan with no join at all
+    b2 = ex.run_batch(orders)
+    w2 = oracle.execute(orders, [rels])
+    assert sorted(zip(*[b2.read_column(c)[0].tolist() for c in range(4)])) == sorted(tuple(r) for r in w2.rows)
+    batch.free()
+    b2.free()
+    ex.close()
+    for d in dev:
+        d.free()
