@@ -338,6 +338,8 @@ def main():
                         "scaling": "strong" if world > 1 else "n/a", "result_rows": nres,
                         "gpu_launches_per_step": (ctx.launches() - l0j) // jsteps,
                         "longest_kernel": kn, "longest_kernel_ms": km, "motion_bytes_per_step": int(sent),
+                        "motion": ("fused partition + exchange over peer memory (CUDA IPC windows, NVLink stores)" if motion and motion.direct()
+                                   else "staged partition + NCCL send/recv") if motion else "none",
                         "roofline": {"bound": "hbm", "achieved": nbytes / (qms / 1e3) / 1e9, "peak": peak * world, "unit": "GB/s",
                                      "frac": nbytes / (qms / 1e3) / 1e9 / (peak * world), "algorithmic_bytes": nbytes,
                                      "note": "whole query (all pipelines, builds, Motions, top-N, host glue) against the projected base columns"}}

@@ -77,12 +77,29 @@ def build():
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "csrc"), "-j8", "all"])
 
 
+def _preload_bundled_nccl():
+    """libcbgpu.so needs libnccl.so.2.  When the harness also imports torch (rendezvous, barrier), both must
+    share ONE NCCL: load the copy bundled with torch's wheels first, so the dynamic loader resolves the
+    SONAME to it whichever of the two libraries is imported first.  No such wheel: the system library is used."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def gpu():
     global _GPU
     if _GPU is None:
         so = os.path.join(HERE, "libcbgpu.so")
         if not os.path.exists(so):
             raise CbgpuError(-1, "libcbgpu.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        _preload_bundled_nccl()
         L = C.CDLL(so, mode=C.RTLD_GLOBAL)
         vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
         sig = {
@@ -131,6 +148,8 @@ def gpu():
             "cbgpu_motion_create": (C.c_int, [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]),
             "cbgpu_motion_destroy": (None, [vp]),
             "cbgpu_motion_bytes_sent": (i64, [vp]),
+            "cbgpu_motion_direct_bytes": (i64, [vp]),
+            "cbgpu_motion_direct_available": (C.c_int, [vp]),
             "cbgpu_gen_lineitem": (C.c_int, [vp, vp, u64, i64, i64, i64]),
             "cbgpu_gen_orders": (C.c_int, [vp, vp, u64, i64, i64]),
             "cbgpu_gen_customer": (C.c_int, [vp, vp, u64]),
@@ -295,7 +314,13 @@ class Motion:
         self.h = h
 
     def bytes_sent(self):
-        return int(self.ctx.L.cbgpu_motion_bytes_sent(self.h))
+        """payload bytes this rank moved to other segments: through NCCL (staged path) + stored into peers'
+        windows (direct path)"""
+        return int(self.ctx.L.cbgpu_motion_bytes_sent(self.h)) + int(self.ctx.L.cbgpu_motion_direct_bytes(self.h))
+
+    def direct(self):
+        """True when Redistribute runs fused over peer memory (CUDA IPC windows), False: staged over NCCL"""
+        return bool(self.ctx.L.cbgpu_motion_direct_available(self.h))
 
     def close(self):
         if self.h:

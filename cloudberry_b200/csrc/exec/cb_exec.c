@@ -1560,6 +1560,9 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 		VarCtx		vc;
 		void	   *counter;
 		cbgpu_rel  *rel;
+		int			direct = 0;
+		void *const *part_cols = NULL;
+		unsigned long long *const *part_counts = NULL;
 
 		if (m->nhashExprs < 1 || m->nhashExprs > CBP_MAX_KEYS)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "hash Motion with %d keys is beyond the GPU path's limit", m->nhashExprs);
@@ -1635,7 +1638,26 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 			if (*seg_capacity > pl->nrows)
 				*seg_capacity = pl->nrows;
 		}
-		GPU(es, cbgpu_rel_create(es->es_ctx, *seg_capacity * nsegs, ncols, types, dscales, &rel));
+		/* direct Motion (interconnects with peer memory): the PARTITION sink stores every row straight
+		 * into its destination segment's receive buffer - no send buffer, no separate exchange */
+		{
+			CbInterconnect *ic = es->es_cluster ? NULL : es->es_interconnect;
+			int			anynull = 0;
+
+			for (int c = 0; c < ncols; c++)
+				anynull |= nullable[c];
+			if (ic && ic->direct_begin && !anynull)
+			{
+				int64_t		cap = 0;
+
+				if (ic->direct_begin(ic, es, m->motionID, ncols, types, dscales, pl->nrows, &cap, &part_cols, &part_counts) == CBGPU_OK)
+				{
+					direct = 1;
+					*seg_capacity = cap;
+				}
+			}
+		}
+		GPU(es, cbgpu_rel_create(es->es_ctx, direct ? 0 : *seg_capacity * nsegs, ncols, types, dscales, &rel));
 		p->owned.rels[p->owned.nrels++] = rel;
 		for (int c = 0; c < ncols; c++)
 			if (nullable[c])
@@ -1666,6 +1688,8 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 		pl->sink.nhash = m->nhashExprs;
 		pl->sink.nsegs = m->numHashSegments > 0 ? m->numHashSegments : nsegs;
 		pl->sink.seg_capacity = *seg_capacity;
+		pl->sink.part_cols = direct ? part_cols : NULL;
+		pl->sink.part_counts = direct ? part_counts : NULL;
 		pl->force_generic = es->es_force_generic;
 		if (pl->sink.nsegs != nsegs)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "Motion to %d hash segments on a %d-segment cluster", pl->sink.nsegs, nsegs);
@@ -1674,7 +1698,7 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 
 			GPU(es, cbgpu_pipeline_run(es->es_ctx, pl));
 			GPU(es, cbgpu_dev_read(es->es_ctx, counter, sizeof(int64_t) * (size_t) nsegs, counts));
-			for (int d = 0; d < nsegs; d++)
+			for (int d = 0; d < nsegs && !direct; d++)
 				if (counts[d] > *seg_capacity)
 					return es_fail(es, CBGPU_ERR_NOMEM, "Motion send buffer for segment %d overflowed (%lld rows, capacity %lld): data skew beyond the reserved allowance",
 								   d, (long long) counts[d], (long long) *seg_capacity);
@@ -1684,12 +1708,49 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 			if (cbgpu_last_kernel_ms(es->es_ctx) > 0)
 				ps->instrument.device_ms += cbgpu_last_kernel_ms(es->es_ctx);
 		}
-		for (int d = 0; d < nsegs; d++)
+		for (int d = 0; d < nsegs && !direct; d++)
 			if (counts[d] > *seg_capacity)
 				return es_fail(es, CBGPU_ERR_NOMEM, "Motion send buffer for segment %d overflowed (%lld rows, capacity %lld): data skew beyond the reserved allowance",
 							   d, (long long) counts[d], (long long) *seg_capacity);
 		pl->nops = saved_nops;
 		*send = rel;
+		if (direct)
+		{
+			/* RecvTupleFrom for the whole stream: wait for every sender, take delivery */
+			CbInterconnect *ic = es->es_interconnect;
+			cbgpu_rel  *recv = NULL;
+			int64_t		elsewhere = 0;
+			int			c = m->nhashExprs;
+
+			for (int d = 0; d < nsegs; d++)
+				if (d != es->es_segindex)
+					elsewhere += counts[d];
+			if (ic->direct_end(ic, es, m->motionID, elsewhere, &recv) != CBGPU_OK)
+				return es->es_errcode ? es->es_errcode : es_fail(es, CBGPU_ERR_CUDA, "%s", cbgpu_last_error(es->es_ctx));
+			p->owned.rels[p->owned.nrels++] = recv;
+			for (int k = 0; k < m->nhashExprs; k++)
+			{
+				PExpr	   *kx = &s->pe[hashpe[k]];
+
+				if (kx->kind == PE_COL && (kx->type == CB_DICT8 || kx->type == CB_DICT32) && pl->cols[kx->col].dict_hash)
+					GPU(es, cbgpu_rel_share_dict_hash(recv, k, s->col_rel[kx->col], s->col_idx[kx->col]));
+			}
+			for (int i = 0; i < s->nout; i++)
+			{
+				PExpr	   *x = &s->pe[s->out[i]];
+
+				if (x->kind == PE_STATE)
+				{
+					c += 3;
+					continue;
+				}
+				if (x->kind == PE_COL && (x->type == CB_DICT8 || x->type == CB_DICT32) && pl->cols[x->col].dict_hash)
+					GPU(es, cbgpu_rel_share_dict_hash(recv, c, s->col_rel[x->col], s->col_idx[x->col]));
+				c++;
+			}
+			p->recv = recv;
+			p->recv_ready = 1;
+		}
 	}
 	return CBGPU_OK;
 }
@@ -1767,6 +1828,8 @@ open_motion(CbPlanState *ps, CbStream **out)
 		if (es->es_numsegments > 64)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "more than 64 segments");
 		TRY(motion_send_side(ps, &send, counts, &segcap));
+		if (p->recv_ready)		/* direct Motion: the sender slice's kernel already delivered */
+			return motion_recv_stream(ps, p->recv, out);
 		switch (m->motionType)
 		{
 			case CB_MOTIONTYPE_HASH:
@@ -2451,11 +2514,35 @@ ic_nccl_broadcast(CbInterconnect *ic, CbEState *es, int32_t motion_id, cbgpu_rel
 	return CBGPU_OK;
 }
 
+static int
+ic_nccl_direct_begin(CbInterconnect *ic, CbEState *es, int32_t motion_id, int32_t ncols, const int32_t *types, const int32_t *dscales,
+					 int64_t input_rows, int64_t *capacity, void *const **dest_cols, unsigned long long *const **dest_counts)
+{
+	(void) motion_id;
+	(void) es;
+	/* not an error for the query: CBGPU_ERR_UNSUPPORTED / CBGPU_ERR_NOMEM here (the same on every
+	 * segment) sends this Motion down the staged path */
+	return cbgpu_motion_direct_begin((cbgpu_motion *) ic->priv, ncols, types, dscales, input_rows, capacity, dest_cols, dest_counts);
+}
+
+static int
+ic_nccl_direct_end(CbInterconnect *ic, CbEState *es, int32_t motion_id, int64_t rows_sent_elsewhere, cbgpu_rel **recv)
+{
+	(void) motion_id;
+	GPU(es, cbgpu_motion_direct_end((cbgpu_motion *) ic->priv, rows_sent_elsewhere, recv));
+	return CBGPU_OK;
+}
+
 CbInterconnect *
 cb_interconnect_nccl_create(cbgpu_motion *motion)
 {
 	CbInterconnect *ic = calloc(1, sizeof(CbInterconnect));
 
+	if (cbgpu_motion_direct_available(motion))
+	{
+		ic->direct_begin = ic_nccl_direct_begin;
+		ic->direct_end = ic_nccl_direct_end;
+	}
 	ic->name = "nccl";
 	ic->nsegs = cbgpu_motion_nranks(motion);
 	ic->segindex = cbgpu_motion_rank(motion);

@@ -17,6 +17,7 @@
 
 #include <nccl.h>
 #include <stdlib.h>
+#include <string.h>
 
 struct cbgpu_motion
 {
@@ -27,7 +28,27 @@ struct cbgpu_motion
 	long long  *d_counts;		/* [nranks * nranks] scratch for the count exchange                   */
 	int64_t		bytes_sent;		/* payload bytes this rank handed to NCCL (diagnostics / bench)       */
 	int64_t		exchanges;
+	/* peer-memory window: one cudaMalloc'ed arena per rank, mapped into every other rank's process
+	 * (CUDA IPC), so a sender slice's PARTITION sink stores rows straight into the receiver's HBM
+	 * over NVLink - no staging buffer, no payload through NCCL (direct Redistribute, below) */
+	char	   *win;
+	size_t		win_bytes;		/* the smallest window of all ranks                                   */
+	char	   *peer_win[64];	/* peer_win[rank] == win                                              */
+	bool		direct_ok;
+	void	  **d_tab;			/* device table handed to the sink: [64 * CBP_MAX_OUT] column bases, [64] counters */
+	void	  **h_tab;			/* pinned host copy                                                   */
+	/* the direct exchange in flight */
+	int32_t		dx_ncols;
+	int32_t		dx_types[CBP_MAX_OUT];
+	int32_t		dx_dscales[CBP_MAX_OUT];
+	int64_t		dx_cap;
+	size_t		dx_off[CBP_MAX_OUT];
+	int64_t		direct_bytes;	/* payload bytes stored into peers' windows (diagnostics / bench)      */
+	int64_t		direct_exchanges;
 };
+
+#define DX_TAB_COLS (64 * CBP_MAX_OUT)
+#define DX_ALIGN 256
 
 #define CB_NCCL(ctx, call) \
 	do { \
@@ -52,6 +73,9 @@ cbgpu_motion_unique_id(void *out128)
 	return CBGPU_OK;
 }
 
+static int	motion_window_setup(cbgpu_motion *m);
+static void motion_window_teardown(cbgpu_motion *m);
+
 extern "C" int
 cbgpu_motion_create(cbgpu_ctx *ctx, int rank, int nranks, const void *unique_id128, cbgpu_motion **out)
 {
@@ -68,7 +92,125 @@ cbgpu_motion_create(cbgpu_ctx *ctx, int rank, int nranks, const void *unique_id1
 	CB_NCCL(ctx, ncclCommInitRank(&m->comm, nranks, id, rank));
 	CB_CUDA(ctx, cudaMalloc(&m->d_counts, sizeof(long long) * (size_t) nranks * (size_t) (nranks + 1)));
 	*out = m;
+	return motion_window_setup(m);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * peer-memory window
+ * --------------------------------------------------------------------------------------------- */
+struct WinHello
+{
+	cudaIpcMemHandle_t handle;
+	unsigned long long bytes;
+	int			ok;
+	char		pad[128 - sizeof(cudaIpcMemHandle_t) - sizeof(unsigned long long) - sizeof(int)];
+};
+
+/* allocate this rank's window, swap IPC handles through the communicator, map every peer's.
+ * Any rank failing at any step turns the direct path off on ALL ranks (the decision is all-reduced):
+ * Redistribute then takes the staged NCCL path - both are device paths. */
+static int
+motion_window_setup(cbgpu_motion *m)
+{
+	cbgpu_ctx  *ctx = m->ctx;
+	const int	n = m->nranks;
+	WinHello   *h_all = (WinHello *) calloc((size_t) n, sizeof(WinHello));
+	WinHello   *d_all = NULL;
+	WinHello	mine;
+	size_t		want = (size_t) 16384 << 20;	/* of 180 GB: room for a Motion of ~500 M narrow rows per receiver */
+	const char *env = getenv("CBGPU_MOTION_WINDOW_MB");
+	int			ok = 1;
+	int		   *d_ok = NULL;
+	int			h_ok = 0;
+
+	m->direct_ok = false;
+	if (!h_all)
+		return CBGPU_ERR_NOMEM;
+	if (n > 64 || (getenv("CBGPU_MOTION") && strcmp(getenv("CBGPU_MOTION"), "nccl") == 0))
+		ok = 0;
+	if (env && atoll(env) > 0)
+		want = (size_t) atoll(env) << 20;
+	memset(&mine, 0, sizeof(mine));
+	if (ok)
+	{
+		size_t		freeb = 0, total = 0;
+
+		cudaMemGetInfo(&freeb, &total);
+		while (want > freeb / 2 && want > ((size_t) 64 << 20))
+			want >>= 1;
+		if (cudaMalloc(&m->win, want) != cudaSuccess || cudaIpcGetMemHandle(&mine.handle, m->win) != cudaSuccess)
+		{
+			cudaGetLastError();
+			ok = 0;
+		}
+	}
+	mine.bytes = want;
+	mine.ok = ok;
+	CB_CUDA(ctx, cudaMalloc(&d_all, sizeof(WinHello) * (size_t) (n + 1)));
+	CB_CUDA(ctx, cudaMemcpyAsync(d_all + n, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+	CB_NCCL(ctx, ncclAllGather(d_all + n, d_all, sizeof(WinHello), ncclInt8, m->comm, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(h_all, d_all, sizeof(WinHello) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	m->win_bytes = want;
+	for (int p = 0; p < n; p++)
+	{
+		if (!h_all[p].ok)
+			ok = 0;
+		if (h_all[p].bytes < m->win_bytes)
+			m->win_bytes = (size_t) h_all[p].bytes;
+	}
+	for (int p = 0; p < n && ok; p++)
+	{
+		if (p == m->rank)
+		{
+			m->peer_win[p] = m->win;
+			continue;
+		}
+		if (cudaIpcOpenMemHandle((void **) &m->peer_win[p], h_all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+		{
+			cudaGetLastError();
+			m->peer_win[p] = NULL;
+			ok = 0;
+		}
+	}
+	/* everyone or no one */
+	CB_CUDA(ctx, cudaMalloc(&d_ok, sizeof(int)));
+	CB_CUDA(ctx, cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+	CB_NCCL(ctx, ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, m->comm, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(d_ok);
+	cudaFree(d_all);
+	free(h_all);
+	if (h_ok)
+	{
+		CB_CUDA(ctx, cudaMalloc(&m->d_tab, sizeof(void *) * (DX_TAB_COLS + 64)));
+		CB_CUDA(ctx, cudaMallocHost(&m->h_tab, sizeof(void *) * (DX_TAB_COLS + 64)));
+		m->direct_ok = true;
+	}
+	else
+		motion_window_teardown(m);
 	return CBGPU_OK;
+}
+
+static void
+motion_window_teardown(cbgpu_motion *m)
+{
+	for (int p = 0; p < m->nranks && p < 64; p++)
+		if (p != m->rank && m->peer_win[p])
+		{
+			cudaIpcCloseMemHandle(m->peer_win[p]);
+			m->peer_win[p] = NULL;
+		}
+	if (m->win)
+		cudaFree(m->win);
+	m->win = NULL;
+	if (m->d_tab)
+		cudaFree(m->d_tab);
+	if (m->h_tab)
+		cudaFreeHost(m->h_tab);
+	m->d_tab = m->h_tab = NULL;
+	m->direct_ok = false;
 }
 
 extern "C" void
@@ -78,6 +220,19 @@ cbgpu_motion_destroy(cbgpu_motion *m)
 		return;
 	cudaSetDevice(m->ctx->device);
 	cudaStreamSynchronize(m->ctx->stream);
+	{
+		/* nobody unmaps a window a peer may still be storing into */
+		int		   *d = NULL;
+
+		if (m->direct_ok && cudaMalloc(&d, sizeof(int)) == cudaSuccess)
+		{
+			cudaMemsetAsync(d, 0, sizeof(int), m->ctx->stream);
+			ncclAllReduce(d, d, 1, ncclInt32, ncclMin, m->comm, m->ctx->stream);
+			cudaStreamSynchronize(m->ctx->stream);
+			cudaFree(d);
+		}
+		motion_window_teardown(m);
+	}
 	ncclCommDestroy(m->comm);
 	cudaFree(m->d_counts);
 	free(m);
@@ -112,6 +267,8 @@ exchange_counts(cbgpu_motion *m, const int64_t *mine, int64_t *matrix)
 	CB_CUDA(ctx, cudaMemcpyAsync(d_mine, mine, sizeof(long long) * n, cudaMemcpyHostToDevice, ctx->stream));
 	CB_NCCL(ctx, ncclAllGather(d_mine, m->d_counts, (size_t) n, ncclInt64, m->comm, ctx->stream));
 	CB_CUDA(ctx, cudaMemcpyAsync(matrix, m->d_counts, sizeof(long long) * (size_t) n * n, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, "nccl:counts");
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return CBGPU_OK;
 }
@@ -190,6 +347,8 @@ exchange_rows(cbgpu_motion *m, cbgpu_rel *send, cbgpu_rel *recv, const int64_t *
 				CB_CUDA(ctx, cudaMemcpyAsync(recv->nulls[c] + recv_off[m->rank], send->nulls[c] + send_off[m->rank],
 											 (size_t) send_cnt[m->rank], cudaMemcpyDeviceToDevice, ctx->stream));
 		}
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, "nccl:rows");
 	m->exchanges++;
 	return CBGPU_OK;
 }
@@ -222,6 +381,132 @@ cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *count
 		rc = exchange_rows(m, send, *recv, send_off, send_cnt, recv_off, recv_cnt);
 	free(matrix);
 	return rc;
+}
+
+
+/* ---------------------------------------------------------------------------------------------
+ * direct Redistribute: partition + exchange as ONE kernel over peer memory.
+ *
+ *   begin   (collective) every rank announces how many rows enter its sender slice; all derive the
+ *           same per-receiver capacity and the same layout of the exchange inside every window
+ *           ([row counter][column 0][column 1]...); each rank zeroes ITS counter BEFORE the
+ *           announcement all-gather, so no peer can store before the counter is clean; the caller
+ *           gets device tables of every destination's column bases and counter
+ *   kernel  the sender slice's pipeline runs with its PARTITION sink in direct mode: destination =
+ *           cdbhashreduce(keys); a CTA reserves a slice of the DESTINATION's buffer with one
+ *           system-scope atomic per destination and run, and stores the rows there over NVLink
+ *   end     (collective) one 4-byte all-reduce = "every sender's kernel has finished"; the receiver
+ *           reads its counter and moves the rows out of the window into a relation of its own, so
+ *           the window is free again when the next Motion's announcement completes
+ * --------------------------------------------------------------------------------------------- */
+extern "C" int
+cbgpu_motion_direct_available(const cbgpu_motion *m)
+{
+	return m->direct_ok ? 1 : 0;
+}
+
+extern "C" int64_t
+cbgpu_motion_direct_bytes(const cbgpu_motion *m)
+{
+	return m->direct_bytes;
+}
+
+extern "C" int
+cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, const int32_t *dscales, int64_t input_rows,
+						  int64_t *capacity, void *const **dest_cols, unsigned long long *const **dest_counts)
+{
+	cbgpu_ctx  *ctx = m->ctx;
+	const int	n = m->nranks;
+	long long  *d_mine = m->d_counts + (size_t) n * n;
+	long long	h_rows[64];
+	int64_t		cap = 0,
+				total = 0;
+	size_t		off = DX_ALIGN;
+
+	if (!m->direct_ok)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "direct Redistribute is not available%s (no peer-memory window)", "", 0);
+	if (ncols < 1 || ncols > CBP_MAX_OUT)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "direct Redistribute of %s%lld columns", "", ncols);
+	/* my counter is clean before anyone can learn that the exchange has started */
+	CB_CUDA(ctx, cudaMemsetAsync(m->win, 0, DX_ALIGN, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(d_mine, &input_rows, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+	CB_NCCL(ctx, ncclAllGather(d_mine, m->d_counts, 1, ncclInt64, m->comm, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(h_rows, m->d_counts, sizeof(long long) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, "p2p:announce");
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	/* the same arithmetic on every rank: even share + 25 % skew allowance + slack per sender */
+	for (int s = 0; s < n; s++)
+	{
+		total += h_rows[s];
+		cap += h_rows[s] / n + h_rows[s] / (4 * n) + 65536;
+	}
+	if (cap > total)
+		cap = total;
+	if (cap < 1)
+		cap = 1;
+	for (int c = 0; c < ncols; c++)
+	{
+		m->dx_types[c] = types[c];
+		m->dx_dscales[c] = dscales ? dscales[c] : 0;
+		m->dx_off[c] = off;
+		off += (((size_t) cap * (size_t) cb_type_w(types[c])) + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
+	}
+	if (off > m->win_bytes)
+		return cb_fail(ctx, CBGPU_ERR_NOMEM, "direct Redistribute needs %s%lld bytes of window (raise CBGPU_MOTION_WINDOW_MB)", "", (long long) off);
+	m->dx_ncols = ncols;
+	m->dx_cap = cap;
+	for (int d = 0; d < n; d++)
+	{
+		for (int c = 0; c < ncols; c++)
+			m->h_tab[(size_t) d * ncols + c] = m->peer_win[d] + m->dx_off[c];
+		m->h_tab[DX_TAB_COLS + d] = m->peer_win[d];
+	}
+	CB_CUDA(ctx, cudaMemcpyAsync(m->d_tab, m->h_tab, sizeof(void *) * (DX_TAB_COLS + 64), cudaMemcpyHostToDevice, ctx->stream));
+	*capacity = cap;
+	*dest_cols = (void *const *) m->d_tab;
+	*dest_counts = (unsigned long long *const *) (m->d_tab + DX_TAB_COLS);
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_motion_direct_end(cbgpu_motion *m, int64_t rows_sent_elsewhere, cbgpu_rel **recv)
+{
+	cbgpu_ctx  *ctx = m->ctx;
+	int		   *d_flag = (int *) (m->d_counts + (size_t) m->nranks * m->nranks);
+	unsigned long long got = 0;
+	int			rc;
+
+	*recv = NULL;
+	if (!m->direct_ok || m->dx_ncols < 1)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_motion_direct_end without a begin%s", "", 0);
+	/* stream order puts this after my kernel; its completion anywhere means every kernel is done */
+	CB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+	CB_NCCL(ctx, ncclAllReduce(d_flag, d_flag, 1, ncclInt32, ncclMax, m->comm, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(&got, m->win, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, "p2p:complete");
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if ((int64_t) got > m->dx_cap)
+		return cb_fail(ctx, CBGPU_ERR_NOMEM, "Motion receive buffer overflowed (%s%lld rows): data skew beyond the reserved allowance", "", (long long) got);
+	rc = cbgpu_rel_create(ctx, (int64_t) got, m->dx_ncols, m->dx_types, m->dx_dscales, recv);
+	if (rc)
+		return rc;
+	for (int c = 0; c < m->dx_ncols && got > 0; c++)
+		CB_CUDA(ctx, cudaMemcpyAsync((*recv)->data[c], m->win + m->dx_off[c], (size_t) got * (size_t) cb_type_w(m->dx_types[c]),
+									 cudaMemcpyDeviceToDevice, ctx->stream));
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, "p2p:copy-out");
+	{
+		int64_t		roww = 0;
+
+		for (int c = 0; c < m->dx_ncols; c++)
+			roww += cb_type_w(m->dx_types[c]);
+		m->direct_bytes += rows_sent_elsewhere * roww;
+	}
+	m->direct_exchanges++;
+	m->dx_ncols = 0;
+	return CBGPU_OK;
 }
 
 extern "C" int

@@ -176,8 +176,14 @@ cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
 			if (s->kind == CBP_SINK_PARTITION)
 			{
 				if (s->nsegs < 1 || s->nhash < 1 || s->nhash > CBP_MAX_KEYS || s->nhash > s->nout ||
-					s->seg_capacity * s->nsegs > s->out->capacity)
+					(!s->part_cols && s->seg_capacity * s->nsegs > s->out->capacity) || (s->part_cols && !s->part_counts))
 					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: bad partition description%s", "", 0);
+				ds->part_cols = s->part_cols;
+				ds->part_counts = s->part_counts;
+				if (s->part_cols)
+					for (int c = 0; c < s->nout; c++)
+						if (s->out->nulls[c])
+							return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "direct Motion of a nullable column%s", "", 0);
 				ds->nhash = s->nhash;
 				ds->nsegs = s->nsegs;
 				ds->seg_capacity = s->seg_capacity;
@@ -828,13 +834,28 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 				int			leader = __ffs(peers) - 1;
 				unsigned long long pos = 0;
 
+				const bool	direct = S.kind == CBP_SINK_PARTITION && S.part_cols != NULL;
+
 				if (lane == leader)
+				{
 					pos = atomicAdd(S.out_count + seg, (unsigned long long) __popc(peers));
+					if (direct)		/* the slice of the DESTINATION's buffer; the local count stays as a statistic */
+						pos = atomicAdd_system(S.part_counts[seg], (unsigned long long) __popc(peers));
+				}
 				pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1));
 				int64_t		cap = S.kind == CBP_SINK_PARTITION ? S.seg_capacity : S.out_capacity;
 
 				if ((int64_t) pos >= cap)
 					atomicExch(P.status, CBGPU_ERR_NOMEM);
+				else if (direct)
+				{
+					for (int c = 0; c < S.nout; c++)
+					{
+						sink_store(S.part_cols[seg * S.nout + c], S.outtype[c], pos, st[c]);
+						if ((snull >> c) & 1)
+							atomicExch(P.status, CBGPU_ERR_INVALID);
+					}
+				}
 				else
 				{
 					uint64_t	dst = (uint64_t) seg * (uint64_t) S.seg_capacity + pos;

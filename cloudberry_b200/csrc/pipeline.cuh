@@ -41,6 +41,8 @@ struct DSink
 	const uint32_t *hashdict[CBP_MAX_KEYS];
 	int32_t		nsegs;
 	int64_t		seg_capacity;
+	void *const *part_cols;		/* direct Motion: destination d's column c at part_cols[d * nout + c]  */
+	unsigned long long *const *part_counts;	/* ... and its row counter (peer memory)               */
 };
 
 struct PipeDev

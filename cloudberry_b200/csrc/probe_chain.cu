@@ -97,7 +97,24 @@ struct PcParams
 	int32_t		outtype[PC_MAXOUT];
 	unsigned long long *out_count;
 	int64_t		out_capacity;
+	/* PARTITION: cdbhash over the first nhash output columns picks the destination segment */
+	int32_t		nhash;
+	int32_t		hashtype[CBP_MAX_KEYS];
+	const uint32_t *hashdict[CBP_MAX_KEYS];
+	int32_t		nsegs;
+	int64_t		seg_capacity;
+	void *const *part_cols;		/* direct Motion: destination d's column c at part_cols[d * nout + c]  */
+	unsigned long long *const *part_counts;
 	int		   *status;
+};
+
+/* shared scratch of the PARTITION sink: destination and rank within it for every entry of a run */
+struct PcPart
+{
+	unsigned	count[64];
+	unsigned long long base[64];
+	uint8_t		seg[PC_BATCH];
+	uint16_t	rank[PC_BATCH];
 };
 
 /* a queue as a stage sees it: word w of entry e at q[w * cap + e]; words 0 .. = row ids by source */
@@ -324,7 +341,7 @@ pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t
 
 /* sink over entries [base, base + n) of the last queue (np + 1 row ids) */
 __device__ __noinline__ void
-pc_stage_sink(const PcParams &P, PcQ Q, unsigned base, unsigned n, unsigned long long *s_obase)
+pc_stage_sink(const PcParams &P, PcQ Q, unsigned base, unsigned n, unsigned long long *s_obase, PcPart *part)
 {
 	if (P.sink_kind == CBP_SINK_AGG)
 	{
@@ -389,6 +406,52 @@ pc_stage_sink(const PcParams &P, PcQ Q, unsigned base, unsigned n, unsigned long
 			__syncwarp();		/* lanes that waited on a group being created rejoin before the next trip */
 		}
 	}
+	else if (P.sink_kind == CBP_SINK_PARTITION)
+	{
+		/* execMotionSender / evalHashKey (nodeMotion.c:203,1088): destination = cdbhashreduce of the hash
+		 * keys (cdb/cdbhash.c:189,253).  Rows are counted per destination in shared memory, the run
+		 * takes one slice per destination from the send buffer, then every row is stored. */
+		if (threadIdx.x < 64)
+			part->count[threadIdx.x] = 0;
+		__syncthreads();
+		for (unsigned i = threadIdx.x; i < n; i += PC_THREADS)
+		{
+			uint32_t	h = 0;
+
+			for (int k = 0; k < P.nhash; k++)
+				h = pg_hash_combine(h, pg_hash_datum(P.hashtype[k], pc_load(P.out[k], Q, base + i), P.hashdict[k]), false);
+			const int	seg = pg_jump_consistent_hash(h, P.nsegs);
+
+			part->seg[i] = (uint8_t) seg;
+			part->rank[i] = (uint16_t) atomicAdd(&part->count[seg], 1u);
+		}
+		__syncthreads();
+		if (threadIdx.x < P.nsegs && part->count[threadIdx.x])
+		{
+			unsigned long long b = atomicAdd(P.out_count + threadIdx.x, (unsigned long long) part->count[threadIdx.x]);
+
+			/* direct Motion: the slice is reserved in the DESTINATION segment's buffer, over NVLink */
+			if (P.part_cols)
+				b = atomicAdd_system(P.part_counts[threadIdx.x], (unsigned long long) part->count[threadIdx.x]);
+			part->base[threadIdx.x] = b;
+			if ((int64_t) (b + part->count[threadIdx.x]) > P.seg_capacity)
+				atomicExch(P.status, CBGPU_ERR_NOMEM);
+		}
+		__syncthreads();
+		for (unsigned i = threadIdx.x; i < n; i += PC_THREADS)
+		{
+			const int	seg = part->seg[i];
+			const unsigned long long pos = part->base[seg] + part->rank[i];
+
+			if ((int64_t) pos < P.seg_capacity)
+			{
+				const uint64_t dst = P.part_cols ? pos : (uint64_t) seg * (uint64_t) P.seg_capacity + pos;
+
+				for (int c = 0; c < P.nout; c++)
+					sink_store(P.part_cols ? P.part_cols[seg * P.nout + c] : P.outcol[c], P.outtype[c], dst, pc_load(P.out[c], Q, base + i));
+			}
+		}
+	}
 	else
 	{
 		/* one reservation of n output rows per run, then coalesced stores */
@@ -446,6 +509,7 @@ k_probe_chain(const __grid_constant__ PcParams P)
 	__shared__ unsigned s_n, s_base;
 	__shared__ long long s_tile;
 	__shared__ unsigned long long s_obase;
+	__shared__ PcPart part;
 	const int	np = P.np;
 	const int	last = 2 * np + 1;		/* the sink's stage number; stage s reads queue s - 1         */
 	const bool	iota = P.nfilters == 0 && P.visimap == NULL;
@@ -620,7 +684,7 @@ k_probe_chain(const __grid_constant__ PcParams P)
 			Q.iota_base = 0;
 		}
 		if (s == last)
-			pc_stage_sink(P, Q, base, n, &s_obase);
+			pc_stage_sink(P, Q, base, n, &s_obase, &part);
 		else
 		{
 			const int	j = (s - 1) >> 1;
@@ -684,7 +748,9 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 	*handled = false;
 	if (p->nprobes < 0 || p->nprobes > PC_MAXP || p->drv_nsrc != 0)
 		PC_REJECT(1);		/* no probes at all is fine: quals -> sink (a filtered scan feeding a Hash or a Motion) */
-	if (s->kind != CBP_SINK_AGG && s->kind != CBP_SINK_MATERIALIZE)
+	if (s->kind != CBP_SINK_AGG && s->kind != CBP_SINK_MATERIALIZE && s->kind != CBP_SINK_PARTITION)
+		PC_REJECT(2);
+	if (s->kind == CBP_SINK_PARTITION && s->nsegs > 64)
 		PC_REJECT(2);
 	if (!xm_decompile(p, &x))
 		PC_REJECT(3);
@@ -883,6 +949,19 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 		}
 		P.out_count = d->sink.out_count;
 		P.out_capacity = d->sink.out_capacity;
+		if (s->kind == CBP_SINK_PARTITION)
+		{
+			P.nhash = d->sink.nhash;
+			P.nsegs = d->sink.nsegs;
+			P.seg_capacity = d->sink.seg_capacity;
+			P.part_cols = d->sink.part_cols;
+			P.part_counts = d->sink.part_counts;
+			for (int k = 0; k < P.nhash; k++)
+			{
+				P.hashtype[k] = d->sink.hashtype[k];
+				P.hashdict[k] = d->sink.hashdict[k];
+			}
+		}
 	}
 
 	/* persistent grid: 4 CTAs per SM; queue k >= 1 holds (k + 3) / 2 words per entry */

@@ -155,6 +155,16 @@ typedef struct CbInterconnect
 							  cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
 	void		(*teardown) (struct CbInterconnect *ic);
 	void	   *priv;
+	/* optional (NULL when the interconnect has no peer memory): Redistribute fused into the sender
+	 * slice's kernel.  begin is collective and returns the PARTITION sink's destination tables
+	 * (CbpSink.part_cols / part_counts) and the per-receiver capacity; a non-zero return means "use
+	 * redistribute() for this Motion" and must be the same on every segment.  end is collective and
+	 * returns the rows delivered to this segment. */
+	int			(*direct_begin) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id, int32_t ncols,
+								 const int32_t *types, const int32_t *dscales, int64_t input_rows, int64_t *capacity,
+								 void *const **dest_cols, unsigned long long *const **dest_counts);
+	int			(*direct_end) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id,
+							   int64_t rows_sent_elsewhere, cbgpu_rel **recv);
 } CbInterconnect;
 
 /* interconnect over NCCL (cbgpu_motion_*): one process per GPU-segment.  SetupInterconnect

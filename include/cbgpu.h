@@ -219,6 +219,11 @@ typedef struct CbpSink
 	const uint32_t *hash_dict_hash[CBP_MAX_KEYS];
 	int32_t		nsegs;
 	int64_t		seg_capacity;	/* rows reserved per destination inside `out`                         */
+	/* PARTITION, direct mode (cbgpu_motion_direct_begin): rows are stored into the destinations' own
+	 * buffers instead of `out` (which then only describes the column types): part_cols[d * nout + c],
+	 * part_counts[d]; seg_capacity = rows every destination can take */
+	void *const *part_cols;
+	unsigned long long *const *part_counts;
 } CbpSink;
 
 typedef struct CbPipeline
@@ -322,6 +327,20 @@ int64_t		cbgpu_motion_bytes_sent(const cbgpu_motion *m);
  * d * seg_capacity, counts[d] rows); returns the rows addressed to this rank, sender by sender */
 int			cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *counts, int64_t seg_capacity,
 									  cbgpu_rel **recv);
+/* Direct Redistribute: partition + exchange fused into the sender slice's own kernel, over peer memory
+ * (every rank's receive window is mapped into every other rank through CUDA IPC at create time; rows
+ * are stored straight into the destination's HBM over NVLink).  begin and end are collective.
+ *   begin: announce this rank's sender input rows; returns the per-receiver row capacity and two device
+ *          tables for the PARTITION sink: dest_cols[d * ncols + c] = base of column c in segment d's
+ *          window, dest_counts[d] = segment d's row counter (CbpSink.part_cols / part_counts)
+ *   end:   after the pipeline ran: wait for every sender, return the rows addressed to this rank.
+ * cbgpu_motion_direct_available() == 0 (no P2P / IPC, or CBGPU_MOTION=nccl): use cbgpu_motion_redistribute. */
+int			cbgpu_motion_direct_available(const cbgpu_motion *m);
+int			cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, const int32_t *dscales,
+									  int64_t input_rows, int64_t *capacity, void *const **dest_cols,
+									  unsigned long long *const **dest_counts);
+int			cbgpu_motion_direct_end(cbgpu_motion *m, int64_t rows_sent_elsewhere, cbgpu_rel **recv);
+int64_t		cbgpu_motion_direct_bytes(const cbgpu_motion *m);
 /* Gather: the first nrows rows of every rank's `send` to rank `root` (others receive 0 rows) */
 int			cbgpu_motion_gather(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
 /* Broadcast: every rank receives every rank's first nrows rows */

@@ -62,7 +62,7 @@ def main():
         ok = ok and tpch.format_q1(r1.rows) == exp["q1"]
         ok = ok and tpch.format_q3(r3.rows) == exp["q3"]
         ok = ok and tpch.format_q5(r5.rows, exp["dict"]["n_name_dict"]) == exp["q5"]
-        print("MULTIRANK", "PASS" if ok else "FAIL", "world", world, "replicated", replicated, "nccl bytes sent by rank 0", motion.bytes_sent())
+        print("MULTIRANK", "PASS" if ok else "FAIL", "world", world, "replicated", replicated, "direct" if motion.direct() else "staged", "motion bytes sent by rank 0", motion.bytes_sent())
         if not ok:
             print(tpch.format_q1(r1.rows), tpch.format_q3(r3.rows), tpch.format_q5(r5.rows, exp["dict"]["n_name_dict"]))
     else:

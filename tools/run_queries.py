@@ -23,11 +23,25 @@ def main():
     ap.add_argument("--generic", action="store_true")
     ap.add_argument("--trace", action="store_true", help="print every kernel launch of one extra run with its time")
     args = ap.parse_args()
-    ctx = capi.Context(0)
-    rt, sz = device_tables(ctx, args.sf)
-    ex = capi.Executor(ctx, rt, force_generic=args.generic)
-    plans = {"q1": lambda: tpch.q1_plan(1), "q3": lambda: tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), 1),
-             "q5": lambda: tpch.q5_plan(tpch.REGIONS.index("AMERICA"), 1)}
+    rank, local, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    ctx = capi.Context(local)
+    motion = None
+    if world > 1:
+        # under torchrun: one SF-sized database distributed over the ranks, plans with Motions over NCCL
+        import torch
+        import torch.distributed as dist
+        from cloudberry_b200 import harness
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ids = [capi.Motion.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        motion = capi.Motion(ctx, rank, world, ids[0])
+        rt, sz = harness.distributed_tables(ctx, motion, args.sf, rank, world)
+    else:
+        rt, sz = device_tables(ctx, args.sf)
+    ex = capi.Executor(ctx, rt, force_generic=args.generic, motion=motion)
+    plans = {"q1": lambda: tpch.q1_plan(world), "q3": lambda: tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), world, customer_replicated=False),
+             "q5": lambda: tpch.q5_plan(tpch.REGIONS.index("AMERICA"), world, replicated=False)}
     rows_in = {"q1": sz["lineitem"], "q3": sz["lineitem"] + sz["orders"] + sz["customer"],
                "q5": sz["lineitem"] + sz["orders"] + sz["customer"] + sz["supplier"] + 30}
     for q in args.queries.split(","):
@@ -44,10 +58,14 @@ def main():
             ctx.trace_begin()
             ex.run(plan)
             tr = ctx.trace_end()
+            if rank != 0:
+                continue
             print("trace %s: %d launches, %.3f ms" % (q, len(tr), sum(m for _, m in tr)))
             for name, m in tr:
                 print("   %-28s %9.3f ms" % (name, m))
         ms = sorted(times)[len(times) // 2]
+        if rank != 0:
+            continue
         print(json.dumps({"query": q, "sf": args.sf, "ms": ms, "rows_per_s": rows_in[q] / (ms / 1e3), "result_rows": len(res.rows),
                           "longest_kernel": kn, "longest_kernel_ms": km,
                           "nodes": {k: {"node": v["node"], "kernels": v["kernels"], "device_ms": round(v["device_ms"], 3),
