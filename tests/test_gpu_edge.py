@@ -1,0 +1,183 @@
+"""Edge cases of the scan / join / aggregate path, CUDA executor vs the CPU oracle, exact (-m gpu).
+
+What the reference's own regression tests exercise around these operators (src/test/regress/sql/join.sql,
+aggregates.sql, appendonly / uao visibility tests): empty inputs on either side, ragged row counts around the
+kernels' tile sizes, NULL join keys (never match: strict hash operators, nodeHash.c:2161) and NULL group keys
+(group together, execGrouping.c:548), invisible rows (visimap), build-side duplicates (N:M), LEFT / SEMI / ANTI
+joins, count/min/max/avg over NULLs, float8 sums (tolerance), and arithmetic that leaves 64 bits
+(refused loudly, never wrapped)."""
+import math
+
+import numpy as np
+import pytest
+
+from cloudberry_b200 import capi
+from cloudberry_b200 import plan as P
+from cloudberry_b200.relation import HostRelation
+from gpu_util import canon, to_device
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _nulls(rng, n, frac):
+    return (rng.random(n) < frac).astype(np.uint8) if frac else None
+
+
+def fact(n, seed=1, null_frac=0.0, visible_frac=1.0, kmax=50):
+    rng = np.random.default_rng(seed)
+    cols = [rng.integers(0, kmax, n), rng.integers(-10**6, 10**6, n), rng.integers(0, 10**9, n), rng.random(n) * 1000.0,
+            rng.integers(0, 7, n), rng.integers(0, 3000, n)]
+    nulls = [_nulls(rng, n, null_frac), _nulls(rng, n, null_frac), None, None, _nulls(rng, n, null_frac), None]
+    vis = None
+    if visible_frac < 1.0:
+        bits = (rng.random(n) < visible_frac).astype(np.uint8)
+        vis = np.packbits(bits, bitorder="little")
+    return HostRelation("fact", ["k", "v", "amt", "x", "g", "d"], [P.INT4, P.INT8, P.NUMERIC, P.FLOAT8, P.DICT8, P.DATE], cols,
+                        nulls=nulls, visimap=vis, dict_texts=[None, None, None, None, ["g%d" % i for i in range(7)], None])
+
+
+def dim(n, seed=2, null_frac=0.0, dup=1, kmax=50):
+    rng = np.random.default_rng(seed)
+    keys = np.repeat(rng.permutation(kmax)[:max(n // dup, 0)], dup)[:n] if n else np.zeros(0, dtype=np.int64)
+    n = len(keys)
+    cols = [keys, rng.integers(0, 100, n), rng.integers(0, 5, n)]
+    return HostRelation("dim", ["dk", "w", "c"], [P.INT4, P.INT8, P.DICT8], cols, nulls=[_nulls(rng, n, null_frac), None, None],
+                        dict_texts=[None, None, ["c%d" % i for i in range(5)]])
+
+
+def scan(relid, rel, names, quals=()):
+    tl = []
+    for nme in names:
+        a, t, ds = rel.var(nme)
+        tl.append((nme, P.Var(relid, a, t, ds)))
+    return P.SeqScan(relid, tl, quals)
+
+
+def run_both(ctx, oracle, plan, rels_o, rels_p, generic):
+    dev = to_device(ctx, rels_p)
+    ex = capi.Executor(ctx, dev, force_generic=generic)
+    try:
+        got = ex.run(plan)
+    finally:
+        ex.close()
+        for d in dev:
+            d.free()
+    want = oracle.execute(plan, [rels_o])
+    return got.rows, want.rows
+
+
+def make(fn, *a, **k):
+    """the same table twice: dictionary hashes through the oracle's and through the product's hashbpchar"""
+    from oracle import oracle as O
+    return fn(*a, **k).set_dict_hashes(O.hashbpchar), fn(*a, **k).set_dict_hashes(capi.hashbpchar)
+
+
+def agg_over(child, names, keys, aggs):
+    from cloudberry_b200.tpch import _child_var
+    v = _child_var(child)
+    targets = [(k, v(k)) for k in keys] + [(n, P.Aggref(op, None if arg is None else v(arg))) for n, op, arg in aggs]
+    return P.Agg(child, P.AGG_HASHED, P.AGGSPLIT_SIMPLE, [names.index(k) + 1 for k in keys], targets, num_groups=64)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("n", [0, 1, 31, 33, 255, 257, 2047, 2049, 4097, 100003])
+def test_ragged_and_empty_scan_agg(ctx, oracle, n, generic):
+    fo, fp = make(fact, n)
+    names = ["g", "amt", "v", "d"]
+    sc = scan(1, fo, names, [P.OpExpr(P.OP_LT, P.Var(1, fo.attno("d"), P.DATE), P.Const(P.DATE, 2000))])
+    plan = agg_over(sc, names, ["g"], [("s", P.AGG_SUM, "amt"), ("c", P.AGG_COUNT_STAR, None), ("a", P.AGG_AVG, "amt"),
+                                       ("mn", P.AGG_MIN, "v"), ("mx", P.AGG_MAX, "v")])
+    got, want = run_both(ctx, oracle, plan, [fo], [fp], generic)
+    assert canon(got) == canon(want)
+    assert len(want) == 0 if n == 0 else True
+
+
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("jointype", [P.JOIN_INNER, P.JOIN_LEFT, P.JOIN_SEMI, P.JOIN_ANTI])
+@pytest.mark.parametrize("nf,nd", [(0, 40), (5000, 0), (5000, 40), (2049, 1)])
+def test_join_types_and_empty_sides(ctx, oracle, jointype, nf, nd, generic):
+    fo, fp = make(fact, nf, seed=3)
+    do, dp = make(dim, nd, seed=4)
+    sf = scan(1, fo, ["k", "amt", "g"])
+    sd = scan(2, do, ["dk", "w", "c"])
+    h = P.Hash(sd, [P.out_var(sd, 1)])
+    targets = [("k", P.out_var(sf, 1)), ("amt", P.out_var(sf, 2)), ("g", P.out_var(sf, 3))]
+    if jointype in (P.JOIN_INNER, P.JOIN_LEFT):
+        targets += [("w", P.InnerVar(2, P.INT8)), ("c", P.InnerVar(3, P.DICT8))]
+    j = P.HashJoin(jointype, sf, h, [P.out_var(sf, 1)], targets)
+    names = [t[0] for t in targets]
+    aggs = [("s", P.AGG_SUM, "amt"), ("n", P.AGG_COUNT_STAR, None)]
+    if "w" in names:
+        aggs += [("sw", P.AGG_SUM, "w"), ("cw", P.AGG_COUNT, "w")]
+    plan = agg_over(j, names, ["g"] + (["c"] if "c" in names else []), aggs)
+    got, want = run_both(ctx, oracle, plan, [fo, do], [fp, dp], generic)
+    assert canon(got) == canon(want)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_null_keys_visimap_and_duplicates(ctx, oracle, generic):
+    """NULL join keys match nothing, NULL group keys form one group, invisible rows do not exist, a build side with
+    duplicate keys multiplies the matches (N:M)."""
+    fo, fp = make(fact, 20011, seed=5, null_frac=0.1, visible_frac=0.8)
+    do, dp = make(dim, 90, seed=6, null_frac=0.1, dup=3)
+    sf = scan(1, fo, ["k", "v", "amt", "g"])
+    sd = scan(2, do, ["dk", "w", "c"])
+    h = P.Hash(sd, [P.out_var(sd, 1)])
+    j = P.HashJoin(P.JOIN_INNER, sf, h, [P.out_var(sf, 1)],
+                   [("g", P.out_var(sf, 4)), ("v", P.out_var(sf, 2)), ("amt", P.out_var(sf, 3)), ("w", P.InnerVar(2, P.INT8)),
+                    ("c", P.InnerVar(3, P.DICT8))])
+    plan = agg_over(j, ["g", "v", "amt", "w", "c"], ["g", "c"],
+                    [("s", P.AGG_SUM, "amt"), ("n", P.AGG_COUNT_STAR, None), ("cv", P.AGG_COUNT, "v"), ("av", P.AGG_AVG, "v"),
+                     ("mn", P.AGG_MIN, "v"), ("mx", P.AGG_MAX, "w")])
+    got, want = run_both(ctx, oracle, plan, [fo, do], [fp, dp], generic)
+    assert len(want) > 5
+    assert canon(got) == canon(want)
+    # the NULL group exists on both sides
+    assert any(r[0] is None for r in want) and any(r[0] is None for r in got)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_float8_sum_avg_tolerance(ctx, oracle, generic):
+    """float8 SUM / AVG accumulate in a different order than float8pl's sequential sum: relative tolerance
+    1e-12 * sqrt(N); group keys and counts stay exact."""
+    n = 200003
+    fo, fp = make(fact, n, seed=7)
+    sc = scan(1, fo, ["g", "x"])
+    plan = agg_over(sc, ["g", "x"], ["g"], [("sx", P.AGG_SUM, "x"), ("ax", P.AGG_AVG, "x"), ("n", P.AGG_COUNT_STAR, None)])
+    got, want = run_both(ctx, oracle, plan, [fo], [fp], generic)
+    g = {r[0]: r for r in got}
+    w = {r[0]: r for r in want}
+    assert set(g) == set(w)
+    tol = 1e-12 * math.sqrt(n)
+    for k in w:
+        assert g[k][3] == w[k][3]
+        assert abs(float(g[k][1]) - float(w[k][1])) <= tol * abs(float(w[k][1]))
+        assert abs(float(g[k][2]) - float(w[k][2])) <= tol * abs(float(w[k][2]))
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_overflow_is_refused(ctx, oracle, generic):
+    """numeric_mul is exact in the reference; the 64-bit scaled form here must refuse a product that leaves
+    64 bits instead of wrapping (CBGPU_ERR_OVERFLOW), on every kernel"""
+    n = 5000
+    fo, fp = make(fact, n, seed=8)
+    fp.columns[2][:] = 4 * 10**18          # amt
+    sc = scan(1, fp, ["g", "amt"])
+    from cloudberry_b200.tpch import _child_var
+    v = _child_var(sc)
+    big = P.OpExpr(P.OP_MUL, v("amt"), P.OpExpr(P.OP_SUB, P.NumericConst("100.00"), v("amt")))
+    plan = P.Agg(sc, P.AGG_HASHED, P.AGGSPLIT_SIMPLE, [1], [("g", v("g")), ("s", P.Aggref(P.AGG_SUM, big))], num_groups=16)
+    dev = to_device(ctx, [fp])
+    ex = capi.Executor(ctx, dev, force_generic=generic)
+    with pytest.raises(capi.CbgpuError):
+        ex.run(plan)
+    ex.close()
+    for d in dev:
+        d.free()
