@@ -1,0 +1,252 @@
+"""AOCS column-file format: CPU restatement of the READER (test infrastructure) + access to the reference's WRITER.
+
+TEST INFRASTRUCTURE ONLY (tests/, tests/golden/make_aocs_golden.py).
+
+Reader restated here, in numpy / plain Python, from:
+  storage block header    include/cdb/cdbappendonlystorage_int.h:64-147 (AOSmallContentHeader bit fields),
+                          cdb/cdbappendonlystorageformat.c:81-113 (header length: 8 + 2 x CRC + firstRowNum),
+                          include/cdb/cdbappendonlystorage.h:37-42 (content rounded up to 8 bytes)
+  datum stream block      include/utils/datumstreamblock.h:74-83 (DatumStreamBlock_Orig), flags :202-208,
+                          utils/datumstream/datumstreamblock.c:153-354 (GetReadyOrig: header, MAXALIGNed NULL bitmap,
+                          MAXALIGNed datum area), datumstreamblock.h:1442-1540 (AdvanceOrig: NULLs take no datum space;
+                          fixed width: += datumlen; varlena: += VARSIZE_ANY, then skip zero pad bytes to typalign)
+  varlena headers         include/postgres.h VARATT_IS_1B / VARSIZE_1B / VARSIZE_4B (little endian)
+  numeric                 include/utils/numeric.h:103-189 (short / long headers, base-10000 digits, weight, dscale)
+Pinned by tests/test_aocs_format.py against column files written by the reference's own code (oracle/ref_aocs.c).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# (typid, attlen, byval, align, storage) as pg_type has them
+TYPEINFO = {
+    "int4": (23, 4, 1, "i", "p"), "int8": (20, 8, 1, "d", "p"), "date": (1082, 4, 1, "i", "p"),
+    "float8": (701, 8, 1, "d", "p"), "bool": (16, 1, 1, "c", "p"), "int2": (21, 2, 1, "s", "p"),
+    "numeric": (1700, -1, 0, "i", "m"), "bpchar": (1042, -1, 0, "i", "x"),
+}
+NBASE = 10000
+
+
+# ------------------------------------------------------------------------------------------------
+# numeric <-> scaled integer
+# ------------------------------------------------------------------------------------------------
+def numeric_digits(scaled, dscale):
+    """(sign, weight, digits) of scaled * 10^-dscale in base 10000 with leading / trailing zero digits stripped
+    (make_result / strip_var, utils/adt/numeric.c)."""
+    sign = scaled < 0
+    v = -scaled if sign else scaled
+    groups_after = (dscale + 3) // 4
+    v *= 10 ** (4 * groups_after - dscale)
+    digits = []
+    while v:
+        digits.append(v % NBASE)
+        v //= NBASE
+    digits.reverse()
+    weight = len(digits) - groups_after - 1
+    while digits and digits[0] == 0:
+        digits.pop(0)
+        weight -= 1
+    while digits and digits[-1] == 0:
+        digits.pop()
+    if not digits:
+        weight, sign = 0, False
+    return sign, weight, digits
+
+
+def numeric_varlena(scaled, dscale):
+    """4-byte-header varlena of a numeric datum as numeric_in would hand it to the insert path: short numeric
+    header when dscale <= 63 and -64 <= weight <= 63 (NUMERIC_CAN_BE_SHORT), else the long header."""
+    sign, weight, digits = numeric_digits(int(scaled), dscale)
+    if dscale <= 0x3F and -64 <= weight <= 63:
+        hdr = 0x8000 | (0x2000 if sign else 0) | (dscale << 7) | (0x0040 if weight < 0 else 0) | (weight & 0x003F)
+        body = int(hdr).to_bytes(2, "little")
+    else:
+        body = int((0x4000 if sign else 0) | (dscale & 0x3FFF)).to_bytes(2, "little") + int(weight & 0xFFFF).to_bytes(2, "little")
+    body += b"".join(int(d).to_bytes(2, "little") for d in digits)
+    total = 4 + len(body)
+    return int(total << 2).to_bytes(4, "little") + body
+
+
+def numeric_from_bytes(data, dscale_out):
+    """numeric datum body (after the varlena header) -> integer scaled by 10^dscale_out (exact, else ValueError)"""
+    h = int.from_bytes(data[0:2], "little")
+    if (h & 0xC000) == 0x8000:
+        sign = bool(h & 0x2000)
+        weight = h & 0x003F
+        if h & 0x0040:
+            weight -= 64
+        off = 2
+    elif (h & 0xC000) == 0xC000:
+        raise ValueError("NaN / infinity")
+    else:
+        sign = (h & 0xC000) == 0x4000
+        weight = int.from_bytes(data[2:4], "little", signed=True)
+        off = 4
+    nd = (len(data) - off) // 2
+    acc = 0
+    for i in range(nd):
+        acc = acc * NBASE + int.from_bytes(data[off + 2 * i:off + 2 * i + 2], "little")
+    e10 = 4 * (weight - nd + 1) + dscale_out
+    if nd == 0:
+        return 0
+    if e10 >= 0:
+        acc *= 10 ** e10
+    else:
+        q, r = divmod(acc, 10 ** (-e10))
+        if r:
+            raise ValueError("numeric has more fractional digits than the column's scale")
+        acc = q
+    return -acc if sign else acc
+
+
+def bpchar_varlena(text):
+    b = text.encode()
+    return int((4 + len(b)) << 2).to_bytes(4, "little") + b
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's writer (oracle/_ref/libaocs_ref.so, built from the reference's sources where present)
+# ------------------------------------------------------------------------------------------------
+_REF = None
+
+
+def ref_lib():
+    global _REF
+    if _REF is None:
+        so = os.path.join(HERE, "_ref", "libaocs_ref.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        L.ref_aocs_write_column.restype = C.c_int64
+        L.ref_aocs_write_column.argtypes = [C.c_int] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                                            C.POINTER(C.c_int64)]
+        L.ref_aocs_last_error.restype = C.c_char_p
+        L.ref_numeric_inspect.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.c_void_p, C.c_int]
+        L.ref_aocs_block_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.ref_aocs_verify_block.argtypes = [C.c_void_p, C.c_int]
+        _REF = L
+    return _REF
+
+
+def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768, dscale=0):
+    """Column file bytes as the reference's insert path writes them.  values: ints / floats (by-value types), scaled
+    ints (numeric) or str (bpchar)."""
+    L = ref_lib()
+    typid, attlen, byval, align, storage = TYPEINFO[typname]
+    n = len(values)
+    nl = None if nulls is None else np.ascontiguousarray(nulls, dtype=np.uint8)
+    varbuf = b""
+    if attlen == -1:
+        offs = np.zeros(n, dtype=np.int64)
+        parts = []
+        pos = 0
+        for i, v in enumerate(values):
+            if nl is not None and nl[i]:
+                continue
+            b = numeric_varlena(v, dscale) if typname == "numeric" else bpchar_varlena(v)
+            b += b"\0" * ((-len(b)) % 4)            # datums handed in are int-aligned palloc chunks
+            offs[i] = pos
+            parts.append(b)
+            pos += len(b)
+        varbuf = b"".join(parts) + b"\0" * 8
+        vals = offs
+    elif typname == "float8":
+        vals = np.ascontiguousarray(values, dtype=np.float64).view(np.int64)
+    else:
+        vals = np.ascontiguousarray(values, dtype=np.int64)
+        if attlen < 8:
+            vals = vals & ((1 << (8 * attlen)) - 1)  # a by-value Datum holds the zero-extended low bytes
+    cap = n * 24 + (n // 100 + 4) * 64 + 4096
+    out = (C.c_ubyte * cap)()
+    nb = C.c_int64()
+    vb = (C.c_ubyte * max(len(varbuf), 1)).from_buffer_copy(varbuf or b"\0")
+    r = L.ref_aocs_write_column(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize,
+                                vals.ctypes.data, C.addressof(vb), nl.ctypes.data if nl is not None else None, n,
+                                C.addressof(out), cap, C.byref(nb))
+    if r < 0:
+        raise RuntimeError("reference writer: " + L.ref_aocs_last_error().decode())
+    return bytes(out[:r]), int(nb.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# the restated reader
+# ------------------------------------------------------------------------------------------------
+def walk_blocks(raw, checksum):
+    """[(content offset, content length, row count, first row number)] of a column file"""
+    out = []
+    pos = 0
+    n = len(raw)
+    while pos < n:
+        w0 = int.from_bytes(raw[pos:pos + 4], "little")
+        w1 = int.from_bytes(raw[pos + 4:pos + 8], "little")
+        kind = (w0 & 0x70000000) >> 28
+        if kind != 1:
+            raise ValueError("block at %d: header kind %d is not SmallContent" % (pos, kind))
+        has_first = (w0 & 0x08000000) >> 27
+        rows = (w0 & 0x00FFFC00) >> 10
+        dlen = ((w0 & 0x3FF) << 11) | ((w1 & 0xFFE00000) >> 21)
+        clen = w1 & 0x001FFFFF
+        if clen:
+            raise ValueError("compressed block")
+        hlen = 8 + (8 if checksum else 0)
+        first = -1
+        if has_first:
+            first = int.from_bytes(raw[pos + hlen:pos + hlen + 8], "little", signed=True)
+            hlen += 8
+        out.append((pos + hlen, dlen, rows, first))
+        pos += hlen + (dlen + 7) // 8 * 8
+    return out
+
+
+def decode_column(raw, typname, checksum, dscale=0):
+    """(values, nulls): numeric -> scaled int64, bpchar -> first byte, fixed width -> the value"""
+    typid, attlen, byval, align, storage = TYPEINFO[typname]
+    alignto = {"c": 1, "s": 2, "i": 4, "d": 8}[align]
+    vals, nulls = [], []
+    for off, dlen, rows, first in walk_blocks(raw, checksum):
+        blk = raw[off:off + dlen]
+        version, flags, ndatum = (int.from_bytes(blk[0:2], "little", signed=True), int.from_bytes(blk[2:4], "little"),
+                                  int.from_bytes(blk[4:6], "little", signed=True))
+        nullsz = int.from_bytes(blk[8:12], "little")
+        sz = int.from_bytes(blk[12:16], "little")
+        if version != 0 or ndatum != rows:
+            raise ValueError("not an Original datum stream block, or row counts disagree")
+        p = 16
+        bitmap = None
+        if flags & 1:
+            bitmap = blk[p:p + nullsz]
+            p += nullsz
+        p = (p + 7) // 8 * 8
+        end = p + sz
+        for r in range(rows):
+            if bitmap is not None and (bitmap[r >> 3] >> (r & 7)) & 1:
+                vals.append(0)
+                nulls.append(1)
+                continue
+            nulls.append(0)
+            if attlen > 0:
+                v = int.from_bytes(blk[p:p + attlen], "little", signed=typname != "bool")
+                p += attlen
+            else:
+                b0 = blk[p]
+                if b0 & 1:
+                    size = b0 >> 1
+                    body = blk[p + 1:p + size]
+                else:
+                    size = (int.from_bytes(blk[p:p + 4], "little") >> 2) & 0x3FFFFFFF
+                    body = blk[p + 4:p + size]
+                v = numeric_from_bytes(body, dscale) if typname == "numeric" else (body[0] if len(body) else 32)
+                p += size
+                if p < end and blk[p] == 0:
+                    p = (p + alignto - 1) // alignto * alignto
+            vals.append(v)
+        if p > end + alignto:
+            raise ValueError("datum area overrun")
+    if typname == "float8":
+        return np.array(vals, dtype=np.int64).view(np.float64), np.array(nulls, dtype=np.uint8)
+    return np.array(vals, dtype=np.int64), np.array(nulls, dtype=np.uint8)

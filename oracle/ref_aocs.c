@@ -1,0 +1,342 @@
+/*
+ * oracle/ref_aocs.c - drives the REFERENCE's own AOCS block writer to produce golden column files.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Built by oracle/Makefile (only where /root/reference exists) into
+ * oracle/_ref/libaocs_ref.so together with three reference sources compiled where they lie:
+ *     src/backend/utils/datumstream/datumstreamblock.c    datum stream blocks (Orig / Dense / RLE / delta)
+ *     src/backend/cdb/cdbappendonlystorageformat.c        Append-Only storage block headers + checksums
+ *     src/port/pg_crc32c_sb8.c                            CRC-32C
+ * with the stand-in generated headers under oracle/ref_shim/ (the reference's configure / genbki
+ * are not run).  No reference source is copied: this file only
+ *   - stubs the backend services those sources call (palloc, ereport, a few GUC flags, encryption
+ *     hooks) so that they link outside a backend, and
+ *   - replays the put / flush loop of aocs_insert_values (access/aocs/aocsam.c:1583-1640) ->
+ *     datumstreamwrite_put / datumstreamwrite_block_orig (utils/datumstream/datumstream.c:300,880-923)
+ *     -> AppendOnlyStorageWrite_FinishBuffer (cdb/cdbappendonlystoragewrite.c:1183-1300, the
+ *     uncompressed small-content branch) for one column,
+ * so the bytes in the golden fixtures are what the reference writes into a column's segment file.
+ * tests/golden/make_aocs_golden.py calls it; the fixtures it writes are what travels.
+ */
+#include "postgres.h"
+
+#include <setjmp.h>
+#include <stdarg.h>
+
+#include "catalog/pg_appendonly.h"
+#include "cdb/cdbappendonlystorage.h"
+#include "cdb/cdbappendonlystorageformat.h"
+#include "utils/datumstreamblock.h"
+#include "utils/numeric.h"
+
+/* port.h routes the printf family to the reference's own src/port implementations, which are not linked here */
+#undef vsnprintf
+#undef snprintf
+#undef vsprintf
+#undef sprintf
+#undef printf
+#undef fprintf
+#undef vfprintf
+
+/* ---- backend services the three sources reach for ---- */
+MemoryContext CurrentMemoryContext = NULL;
+bool		Debug_appendonly_print_insert = false;
+bool		Debug_appendonly_print_insert_tuple = false;
+bool		Debug_appendonly_print_scan = false;
+bool		Debug_appendonly_print_scan_tuple = false;
+bool		Debug_appendonly_print_storage_headers = false;
+bool		Debug_appendonly_print_verify_write_block = false;
+bool		Debug_datumstream_block_read_check_integrity = true;
+bool		Debug_datumstream_block_write_check_integrity = true;
+bool		Debug_datumstream_write_print_small_varlena_info = false;
+bool		Debug_datumstream_write_use_small_initial_buffers = false;
+bool		Debug_datumstream_read_check_large_varlena_integrity = false;
+bool		Debug_datumstream_read_print_varlena_info = false;
+bool		FileEncryptionEnabled = false;
+
+static jmp_buf ref_jmp;
+static char ref_errbuf[512];
+static int	ref_elevel;
+
+void	   *palloc(Size size) { return malloc(size ? size : 1); }
+void	   *palloc0(Size size) { return calloc(1, size ? size : 1); }
+void	   *repalloc(void *p, Size size) { return realloc(p, size ? size : 1); }
+void		pfree(void *p) { free(p); }
+
+bool
+errstart(int elevel, const char *domain)
+{
+	(void) domain;
+	ref_elevel = elevel;
+	return elevel >= ERROR;		/* LOG / DEBUG chatter is dropped */
+}
+
+bool
+errstart_cold(int elevel, const char *domain)
+{
+	return errstart(elevel, domain);
+}
+
+void
+errfinish(const char *filename, int lineno, const char *funcname)
+{
+	(void) funcname;
+	if (ref_elevel >= ERROR)
+	{
+		size_t		n = strlen(ref_errbuf);
+
+		snprintf(ref_errbuf + n, sizeof(ref_errbuf) - n, " (%s:%d)", filename, lineno);
+		longjmp(ref_jmp, 1);
+	}
+}
+
+void
+errmsg(const char *fmt,...)
+{
+	va_list		ap;
+
+	va_start(ap, fmt);
+	vsnprintf(ref_errbuf, sizeof(ref_errbuf), fmt, ap);
+	va_end(ap);
+}
+
+void
+errmsg_internal(const char *fmt,...)
+{
+	va_list		ap;
+
+	va_start(ap, fmt);
+	vsnprintf(ref_errbuf, sizeof(ref_errbuf), fmt, ap);
+	va_end(ap);
+}
+
+void		errdetail(const char *fmt,...) { (void) fmt; }
+void		errdetail_internal(const char *fmt,...) { (void) fmt; }
+void		errcode(int sqlerrcode) { (void) sqlerrcode; }
+int			errprintstack(bool printstack) { (void) printstack; return 0; }
+
+int
+pg_sprintf(char *str, const char *fmt,...)
+{
+	va_list		ap;
+	int			n;
+
+	va_start(ap, fmt);
+	n = vsprintf(str, fmt, ap);
+	va_end(ap);
+	return n;
+}
+
+int
+pg_snprintf(char *str, size_t count, const char *fmt,...)
+{
+	va_list		ap;
+	int			n;
+
+	va_start(ap, fmt);
+	n = vsnprintf(str, count, fmt, ap);
+	va_end(ap);
+	return n;
+}
+
+char *
+psprintf(const char *fmt,...)
+{
+	char	   *buf = malloc(1024);
+	va_list		ap;
+
+	va_start(ap, fmt);
+	vsnprintf(buf, 1024, fmt, ap);
+	va_end(ap);
+	return buf;
+}
+
+void		EncryptAOBLock(unsigned char *data_buf, const int buf_len, RelFileNode *file_node) { (void) data_buf; (void) buf_len; (void) file_node; }
+void		DecryptAOBlock(unsigned char *data_buf, const int buf_len, RelFileNode *file_node) { (void) data_buf; (void) buf_len; (void) file_node; }
+
+/* access/common/detoast.c:652 for the plain (never toasted, never compressed) datums the fixtures hold */
+void
+varattrib_untoast_ptr_len(Datum d, char **datastart, int *len, void **tofree)
+{
+	struct varlena *va = (struct varlena *) DatumGetPointer(d);
+
+	*tofree = NULL;
+	if (VARATT_IS_SHORT(va))
+	{
+		*len = VARSIZE_SHORT(va) - VARHDRSZ_SHORT;
+		*datastart = VARDATA_SHORT(va);
+	}
+	else
+	{
+		*len = VARSIZE(va) - VARHDRSZ;
+		*datastart = VARDATA(va);
+	}
+}
+
+const char *
+ref_aocs_last_error(void)
+{
+	return ref_errbuf;
+}
+
+/* ---- numeric varlena datums (by reference) through the reference's own header macros ---- */
+
+/* read back a numeric datum with utils/numeric.h's accessors: sign, dscale, weight, digits */
+int
+ref_numeric_inspect(const unsigned char *varlena4, int *sign, int *dscale, int *weight, int *ndigits, int16 *digits, int maxdigits)
+{
+	Numeric		num = (Numeric) varlena4;
+	int			n = NUMERIC_NDIGITS(num);
+
+	if (NUMERIC_IS_SPECIAL(num))
+		return -1;
+	*sign = NUMERIC_SIGN(num) == NUMERIC_NEG;
+	*dscale = NUMERIC_DSCALE(num);
+	*weight = NUMERIC_WEIGHT(num);
+	*ndigits = n;
+	for (int i = 0; i < n && i < maxdigits; i++)
+		digits[i] = NUMERIC_DIGITS(num)[i];
+	return NUMERIC_HEADER_IS_SHORT(num) ? 1 : 0;
+}
+
+/*
+ * Write one column.  `values`: by-value datums (attlen 1/2/4/8), or for attlen -1 offsets into
+ * `varbuf` of 4-byte-header varlenas.  Returns bytes written into out (the column's segment-file
+ * content: storage blocks back to back), -1 on error (ref_aocs_last_error).
+ */
+int64
+ref_aocs_write_column(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize,
+					  const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
+					  unsigned char *out, int64 outcap, int64 *nblocks_out)
+{
+	DatumStreamBlockWrite dsw;
+	DatumStreamTypeInfo ti;
+	RelFileNode node;
+	const int	version = AOSegfileFormatVersion_GetLatest();
+	const int	hdrlen = AppendOnlyStorageFormat_RegularHeaderLenNeeded(checksum != 0) + (int) sizeof(int64);	/* + firstRowNum */
+	int64		pos = 0;
+	int64		first_row = 1;
+	int64		nblocks = 0;
+	unsigned char *blockbuf = malloc((size_t) blocksize + 64);
+
+	memset(&node, 0, sizeof(node));
+	memset(&dsw, 0, sizeof(dsw));
+	ti.datumlen = attlen;
+	ti.typid = typid;
+	ti.typstorage = (char) storage;
+	ti.align = (char) align;
+	ti.byval = byval != 0;
+	ref_errbuf[0] = 0;
+	if (setjmp(ref_jmp))
+	{
+		free(blockbuf);
+		return -1;
+	}
+	/* create_datumstreamwrite (datumstream.c:588-632), DatumStreamVersion_Original */
+	DatumStreamBlockWrite_Init(&dsw, &ti, DatumStreamVersion_Original, false, false,
+							   AOSmallContentHeader_MaxRowCount, AOSmallContentHeader_MaxRowCount, blocksize - hdrlen,
+							   NULL, NULL, NULL, NULL, &node);
+
+#define FLUSH() \
+	do { \
+		int			rowCount = DatumStreamBlockWrite_Nth(&dsw); \
+		int64		contentLen; \
+		int32		rounded; \
+		if (rowCount > 0) \
+		{ \
+			memset(blockbuf, 0, (size_t) blocksize + 64); \
+			contentLen = DatumStreamBlockWrite_Block(&dsw, blockbuf + hdrlen, &node); \
+			rounded = AOStorage_RoundUp((int32) contentLen, version); \
+			AppendOnlyStorageFormat_MakeSmallContentHeader(blockbuf, checksum != 0, true, version, first_row, 1 /* AOCSBK_BLOCK */, \
+														   rowCount, (int32) contentLen, 0); \
+			if (pos + hdrlen + rounded > outcap) \
+			{ \
+				snprintf(ref_errbuf, sizeof(ref_errbuf), "output buffer too small"); \
+				free(blockbuf); \
+				return -1; \
+			} \
+			memcpy(out + pos, blockbuf, (size_t) hdrlen + (size_t) rounded); \
+			pos += hdrlen + rounded; \
+			first_row += rowCount; \
+			nblocks++; \
+			DatumStreamBlockWrite_GetReady(&dsw); \
+		} \
+	} while (0)
+
+	for (int64 i = 0; i < n; i++)
+	{
+		bool		isnull = nulls && nulls[i];
+		Datum		d = 0;
+		void	   *toFree = NULL;
+		int			err;
+
+		if (!isnull)
+			d = attlen == -1 ? PointerGetDatum(varbuf + values[i]) : (Datum) values[i];
+		err = DatumStreamBlockWrite_Put(&dsw, d, isnull, &toFree);
+		if (err < 0)
+		{
+			FLUSH();
+			err = DatumStreamBlockWrite_Put(&dsw, d, isnull, &toFree);
+			if (err < 0)
+			{
+				snprintf(ref_errbuf, sizeof(ref_errbuf), "datum %lld does not fit an empty block", (long long) i);
+				free(blockbuf);
+				return -1;
+			}
+		}
+	}
+	FLUSH();
+	DatumStreamBlockWrite_Finish(&dsw);
+	free(blockbuf);
+	if (nblocks_out)
+		*nblocks_out = nblocks;
+	return pos;
+}
+
+/* parse one storage block header with the reference's own accessor (for cross-checking a walker) */
+int
+ref_aocs_block_info(const unsigned char *hdr, int checksum, int *header_len, int *row_count, int *data_len, int64 *first_row,
+					int *header_kind)
+{
+	const int	version = AOSegfileFormatVersion_GetLatest();
+	AOHeaderCheckError e;
+	int32		overall = 0,
+				offset = 0,
+				uncompressed = 0,
+				compressed = 0;
+	int			exec_kind = 0;
+	bool		has_first = false;
+	int64		fr = -1;
+	int			rc = 0;
+	int32		hlen = 0;
+
+	if (setjmp(ref_jmp))
+		return -1;
+	e = AppendOnlyStorageFormat_GetHeaderInfo((uint8 *) hdr, checksum != 0, header_kind, &hlen);
+	if (e != AOHeaderCheckOk)
+		return -2;
+	e = AppendOnlyStorageFormat_GetSmallContentHeaderInfo((uint8 *) hdr, hlen, checksum != 0, 1 << 21, &overall, &offset, &uncompressed,
+														  &exec_kind, &has_first, version, &fr, &rc, (bool *) &compressed, &compressed);
+	if (e != AOHeaderCheckOk)
+		return -3;
+	*header_len = offset;
+	*row_count = rc;
+	*data_len = uncompressed;
+	*first_row = fr;
+	return 0;
+}
+
+/* verify the checksums of one block with the reference's routines: 0 = both good */
+int
+ref_aocs_verify_block(const unsigned char *hdr, int overall_len)
+{
+	pg_crc32	stored = 0,
+				computed = 0;
+
+	if (setjmp(ref_jmp))
+		return -1;
+	if (!AppendOnlyStorageFormat_VerifyHeaderChecksum((uint8 *) hdr, &stored, &computed))
+		return 1;
+	if (!AppendOnlyStorageFormat_VerifyBlockChecksum((uint8 *) hdr, overall_len, &stored, &computed))
+		return 2;
+	return 0;
+}

@@ -1,0 +1,1 @@
+/* stand-in for the genbki-generated catalog/pg_appendonly_d.h: nothing from it is needed by the block-format sources */

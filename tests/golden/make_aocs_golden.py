@@ -1,0 +1,62 @@
+#!/usr/bin/env python3
+"""Write tests/golden/aocs_columns.npz: AOCS column files produced by the REFERENCE's own block writer
+(oracle/_ref/libaocs_ref.so = the reference's datumstreamblock.c + cdbappendonlystorageformat.c + pg_crc32c_sb8.c,
+driven by oracle/ref_aocs.c; run `make -C oracle` first) together with the values that went in.
+
+Runs only where /root/reference exists; the .npz is what travels and what the parity tests read."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import aocs_format as A  # noqa: E402
+
+
+def main():
+    if A.ref_lib() is None:
+        sys.exit("oracle/_ref/libaocs_ref.so missing: run `make -C oracle` where /root/reference exists")
+    rng = np.random.default_rng(20260922)
+    out = {}
+    cases = []
+
+    def add(name, typname, values, nulls, checksum, blocksize, dscale=0):
+        raw, nblocks = A.ref_write_column(typname, values, nulls, checksum, blocksize, dscale)
+        out[name + "__raw"] = np.frombuffer(raw, dtype=np.uint8)
+        if typname == "bpchar":
+            out[name + "__values"] = np.array([ord(v[0]) if v else 32 for v in values], dtype=np.int64)
+        elif typname == "float8":
+            out[name + "__values"] = np.asarray(values, dtype=np.float64)
+        else:
+            out[name + "__values"] = np.asarray(values, dtype=np.int64)
+        out[name + "__nulls"] = np.zeros(len(values), dtype=np.uint8) if nulls is None else np.asarray(nulls, dtype=np.uint8)
+        cases.append("%s|%s|%d|%d|%d|%d" % (name, typname, 1 if checksum else 0, blocksize, dscale, nblocks))
+
+    n = 20011
+    nul = (rng.random(n) < 0.07).astype(np.uint8)
+    add("int4_plain", "int4", rng.integers(-2**31, 2**31 - 1, n), None, True, 32768)
+    add("int4_nulls_8k", "int4", rng.integers(-10**6, 10**6, n), nul, False, 8192)
+    add("int8_nulls", "int8", rng.integers(-2**62, 2**62, n), nul, True, 32768)
+    add("date_plain", "date", rng.integers(-3000, 9000, n), None, True, 32768)
+    add("float8_nulls", "float8", rng.normal(0, 1e6, n), nul, True, 32768)
+    add("bool_plain", "bool", rng.integers(0, 2, n), None, True, 8192)
+    # numeric(15,2): TPC-H-like prices, quantities, discounts; zero, negatives, 15-digit extremes
+    price = rng.integers(90000, 10500000, n)
+    price[:8] = [0, 1, -1, 99, 100, 10**15 - 1, -(10**15 - 1), 10000]
+    add("numeric_price", "numeric", price, None, True, 32768, dscale=2)
+    add("numeric_disc_nulls_8k", "numeric", rng.integers(0, 11, n), nul, False, 8192, dscale=2)
+    add("numeric_scale6", "numeric", rng.integers(-10**12, 10**12, 5003), None, True, 32768, dscale=6)
+    add("bpchar1_flags", "bpchar", [("A", "N", "R", "F", "O")[i] for i in rng.integers(0, 5, n)], nul, True, 32768)
+    add("int4_tiny", "int4", [7], None, True, 32768)
+    add("int4_allnull", "int4", [0] * 100, [1] * 100, True, 32768)
+    out["cases"] = np.array(cases)
+    path = os.path.join(ROOT, "tests", "golden", "aocs_columns.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(cases), "columns")
+    for c in cases:
+        print("  ", c)
+
+
+if __name__ == "__main__":
+    main()
