@@ -1,0 +1,372 @@
+/*
+ * aocs.cu - the storage side of aocs_getnext on the device: one column's segment-file bytes in, one
+ * decoded column of a relation out.
+ *
+ * Restates, for a whole column at once, what the reference does per row and per block:
+ *   datumstreamread_block -> AppendOnlyStorageRead_GetBlockInfo / _Content
+ *       (utils/datumstream/datumstream.c:1364; cdb/cdbappendonlystorageread.c:954,1136): walk the
+ *       Append-Only storage blocks of the column file; header layout
+ *       include/cdb/cdbappendonlystorage_int.h:64-147 (AOSmallContentHeader bit fields), length =
+ *       8 + 2 x CRC-32C (if checksummed) + 8 (firstRowNum), cdb/cdbappendonlystorageformat.c:81-113;
+ *       content rounded up to 8 bytes (include/cdb/cdbappendonlystorage.h:37-42)
+ *   DatumStreamBlockRead_GetReadyOrig (utils/datumstream/datumstreamblock.c:153-354): 16-byte
+ *       DatumStreamBlock_Orig header (include/utils/datumstreamblock.h:74-83), NULL bitmap of
+ *       `nullsz` bytes when DSB_HAS_NULLBITMAP, datum area at the next MAXALIGN boundary
+ *   DatumStreamBlockRead_AdvanceOrig / _Get (include/utils/datumstreamblock.h:1442-1540,1220-1440):
+ *       NULL rows take no datum space; fixed width: next = cur + datumlen; varlena: next = cur +
+ *       VARSIZE_ANY, then zero pad bytes are skipped up to the type's alignment
+ *   numeric datums (include/utils/numeric.h:103-189: short / long header, base-10000 digits) become
+ *       int64 scaled by the column's display scale, char(1) datums their byte - the same decoded form
+ *       the rest of the path works on (DESIGN.md "data layout in HBM").
+ *
+ * The host walks the block headers (16 bytes read per block) into a directory; the file is copied to
+ * the device as it lies; one warp decodes one block: NULL bitmap -> ballot / popcount gives every
+ * row its physical datum index; fixed-width datums are then gathered in parallel; varlena datums are
+ * located by lane 0 walking 32 lengths at a time, and decoded by all lanes.
+ *
+ * Supported: uncompressed SmallContent blocks holding Original datum stream blocks (what an AOCS
+ * table without compresstype / rle_type writes).  Bulk-compressed, large-content and Dense (RLE /
+ * delta) blocks are refused with CBGPU_ERR_UNSUPPORTED, never guessed at.
+ */
+#include "common.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+struct AocsDir
+{
+	long long	off;			/* content offset in the file                                         */
+	long long	rowbase;		/* first output row of the block                                      */
+	int32_t		rows;
+	int32_t		dlen;
+};
+
+struct AocsParams
+{
+	const uint8_t *raw;
+	const AocsDir *dir;
+	int32_t		nblocks;
+	int32_t		attlen;			/* 1 / 2 / 4 / 8, or -1 varlena                                       */
+	int32_t		varkind;		/* CBGPU_AOCS_VAR_NUMERIC / _BPCHAR1                                  */
+	int32_t		typalign;		/* 1 / 2 / 4 / 8                                                      */
+	int32_t		dscale;			/* numeric: scale of the output integers                              */
+	void	   *out;
+	uint8_t    *outnull;		/* NULL when no block of the file has a NULL bitmap                   */
+	int		   *status;
+};
+
+#define AOCS_WARPS 4
+
+__device__ __forceinline__ uint32_t
+aocs_le32(const uint8_t *p)
+{
+	return (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24);
+}
+
+/* numeric datum body -> integer scaled by 10^dscale; false when it does not fit or is not exact */
+__device__ __forceinline__ bool
+aocs_numeric(const uint8_t *body, int len, int dscale, int64_t *out)
+{
+	const uint32_t h = (uint32_t) body[0] | ((uint32_t) body[1] << 8);
+	bool		neg;
+	int			weight,
+				off;
+
+	if ((h & 0xC000u) == 0x8000u)
+	{
+		/* NUMERIC_SHORT: sign 0x2000, dscale 0x1F80 >> 7, weight sign 0x0040, weight 0x003F */
+		neg = (h & 0x2000u) != 0;
+		weight = (int) (h & 0x003Fu);
+		if (h & 0x0040u)
+			weight -= 64;
+		off = 2;
+	}
+	else if ((h & 0xC000u) == 0xC000u)
+		return false;			/* NaN / infinity have no integer form */
+	else
+	{
+		neg = (h & 0xC000u) == 0x4000u;
+		weight = (int) (int16_t) ((uint32_t) body[2] | ((uint32_t) body[3] << 8));
+		off = 4;
+	}
+	const int	nd = (len - off) / 2;
+	uint64_t	acc = 0;
+
+	for (int i = 0; i < nd; i++)
+	{
+		const uint32_t d = (uint32_t) body[off + 2 * i] | ((uint32_t) body[off + 2 * i + 1] << 8);
+
+		if (acc > (0x7fffffffffffffffull - d) / 10000ull)
+			return false;
+		acc = acc * 10000ull + d;
+	}
+	int			e10 = 4 * (weight - nd + 1) + dscale;
+
+	if (nd == 0)
+		acc = 0;
+	else if (e10 >= 0)
+	{
+		for (; e10 > 0; e10--)
+		{
+			if (acc > 0x7fffffffffffffffull / 10ull)
+				return false;
+			acc *= 10ull;
+		}
+	}
+	else
+	{
+		for (; e10 < 0; e10++)
+		{
+			if (acc % 10ull)
+				return false;	/* more fractional digits than the column's scale */
+			acc /= 10ull;
+		}
+	}
+	*out = neg ? -(int64_t) acc : (int64_t) acc;
+	return true;
+}
+
+__global__ void __launch_bounds__(AOCS_WARPS * 32)
+k_aocs_decode(AocsParams P)
+{
+	__shared__ uint32_t s_off[AOCS_WARPS][32];
+	const int	lane = threadIdx.x & 31;
+	const int	w = threadIdx.x >> 5;
+	const int	nwarps = gridDim.x * AOCS_WARPS;
+
+	for (int b = blockIdx.x * AOCS_WARPS + w; b < P.nblocks; b += nwarps)
+	{
+		const AocsDir D = P.dir[b];
+		const uint8_t *blk = P.raw + D.off;
+		/* DatumStreamBlock_Orig */
+		const int	version = (int) (int16_t) ((uint32_t) blk[0] | ((uint32_t) blk[1] << 8));
+		const uint32_t flags = (uint32_t) blk[2] | ((uint32_t) blk[3] << 8);
+		const int	ndatum = (int) (int16_t) ((uint32_t) blk[4] | ((uint32_t) blk[5] << 8));
+		const uint32_t nullsz = aocs_le32(blk + 8);
+		const uint32_t sz = aocs_le32(blk + 12);
+		const uint8_t *bitmap = (flags & 1u) ? blk + 16 : NULL;
+		uint32_t	p0 = 16 + ((flags & 1u) ? nullsz : 0u);
+
+		p0 = (p0 + 7u) & ~7u;
+		if (version != 0 || ndatum != D.rows || (flags & ~1u) != 0 || (int64_t) p0 + sz > D.dlen + 8)
+		{
+			if (lane == 0)
+				atomicExch(P.status, CBGPU_ERR_INVALID);
+			continue;
+		}
+		const uint8_t *data = blk + p0;
+		uint32_t	phys = 0,		/* physical datums before this trip (fixed width) */
+					cur = 0;		/* byte offset of the next datum (varlena) */
+
+		for (int r0 = 0; r0 < D.rows; r0 += 32)
+		{
+			const int	r = r0 + lane;
+			const bool	inr = r < D.rows;
+			const bool	isnull = inr && bitmap && ((bitmap[r >> 3] >> (r & 7)) & 1);
+			const unsigned nn = __ballot_sync(0xffffffffu, inr && !isnull);
+			const int	k = __popc(nn & ((1u << lane) - 1));
+			const int	cnt = __popc(nn);
+			const int64_t orow = D.rowbase + r;
+
+			if (P.attlen < 0)
+			{
+				/* lane 0 finds where this trip's datums start: VARSIZE_ANY + zero-pad skipping */
+				if (lane == 0)
+				{
+					uint32_t	c = cur;
+
+					for (int i = 0; i < cnt; i++)
+					{
+						s_off[w][i] = c;
+						const uint32_t b0 = data[c];
+						const uint32_t size = (b0 & 1u) ? (b0 >> 1) : ((aocs_le32(data + c) >> 2) & 0x3FFFFFFFu);
+
+						if (size == 0 || c + size > sz)
+						{
+							atomicExch(P.status, CBGPU_ERR_INVALID);
+							c = sz;
+							break;
+						}
+						c += size;
+						if (c < sz && data[c] == 0)
+							c = (c + (uint32_t) P.typalign - 1u) & ~((uint32_t) P.typalign - 1u);
+					}
+					cur = c;
+				}
+				cur = __shfl_sync(0xffffffffu, cur, 0);
+				__syncwarp();
+			}
+			if (inr)
+			{
+				int64_t		v = 0;
+
+				if (!isnull)
+				{
+					if (P.attlen > 0)
+					{
+						const uint8_t *d = data + (size_t) (phys + k) * P.attlen;
+
+						switch (P.attlen)
+						{
+							case 1: v = (int64_t) *d; break;
+							case 2: v = (int64_t) *(const int16_t *) d; break;
+							case 4: v = (int64_t) *(const int32_t *) d; break;
+							default: v = *(const long long *) d; break;
+						}
+					}
+					else
+					{
+						const uint8_t *d = data + s_off[w][k];
+						const uint32_t b0 = d[0];
+						const int	hdr = (b0 & 1u) ? 1 : 4;
+						const int	size = (b0 & 1u) ? (int) (b0 >> 1) : (int) ((aocs_le32(d) >> 2) & 0x3FFFFFFFu);
+
+						if (P.varkind == CBGPU_AOCS_VAR_NUMERIC)
+						{
+							if (size - hdr < 2 || !aocs_numeric(d + hdr, size - hdr, P.dscale, &v))
+								atomicExch(P.status, CBGPU_ERR_OVERFLOW);
+						}
+						else
+							v = size - hdr > 0 ? (int64_t) d[hdr] : (int64_t) ' ';
+					}
+				}
+				switch (P.attlen > 0 ? P.attlen : (P.varkind == CBGPU_AOCS_VAR_NUMERIC ? 8 : 1))
+				{
+					case 1: ((uint8_t *) P.out)[orow] = (uint8_t) v; break;
+					case 2: ((int16_t *) P.out)[orow] = (int16_t) v; break;
+					case 4: ((int32_t *) P.out)[orow] = (int32_t) v; break;
+					default: ((int64_t *) P.out)[orow] = v; break;
+				}
+				if (P.outnull)
+					P.outnull[orow] = isnull ? 1 : 0;
+			}
+			phys += (uint32_t) cnt;
+			__syncwarp();
+		}
+	}
+}
+
+extern "C" int
+cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t attlen, int32_t varkind,
+						 int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows_out)
+{
+	const uint8_t *raw = (const uint8_t *) file_bytes;
+	AocsDir    *dir = NULL;
+	int64_t		ndir = 0,
+				capdir = 0,
+				pos = 0,
+				rows = 0;
+	bool		anynull = false;
+	AocsParams	P;
+	uint8_t    *d_raw = NULL;
+	AocsDir    *d_dir = NULL;
+	int			outw;
+
+	*nrows_out = 0;
+	if (col < 0 || col >= rel->ncols)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_aocs_decode_column: bad column%s %lld", "", col);
+	outw = cb_type_w(rel->types[col]);
+	if (attlen > 0 ? (attlen != outw || (attlen != 1 && attlen != 2 && attlen != 4 && attlen != 8))
+		: !((varkind == CBGPU_AOCS_VAR_NUMERIC && rel->types[col] == CB_NUMERIC) || (varkind == CBGPU_AOCS_VAR_BPCHAR1 && outw == 1)))
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "AOCS column of length %s%lld does not decode into this relation column", "", attlen);
+	if (typalign != 1 && typalign != 2 && typalign != 4 && typalign != 8)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "type alignment %s%lld", "", typalign);
+	/* AppendOnlyStorageRead_GetBlockInfo for every block of the file */
+	while (pos < nbytes)
+	{
+		uint32_t	w0, w1;
+		int			kind, has_first, nrow, dlen, clen, hlen;
+
+		if (pos + 8 > nbytes)
+		{
+			free(dir);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "AOCS column file ends inside a block header%s (offset %lld)", "", pos);
+		}
+		memcpy(&w0, raw + pos, 4);
+		memcpy(&w1, raw + pos + 4, 4);
+		kind = (int) ((w0 & 0x70000000u) >> 28);
+		has_first = (int) ((w0 & 0x08000000u) >> 27);
+		nrow = (int) ((w0 & 0x00FFFC00u) >> 10);
+		dlen = (int) (((w0 & 0x000003FFu) << 11) | ((w1 & 0xFFE00000u) >> 21));
+		clen = (int) (w1 & 0x001FFFFFu);
+		if ((w0 >> 31) != 0 || kind != 1 /* AoHeaderKind_SmallContent */ || clen != 0)
+		{
+			free(dir);
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED,
+						   "AOCS block at offset %s%lld is not an uncompressed SmallContent block (bulk-compressed, large-content and dense blocks are not decoded on the device)",
+						   "", pos);
+		}
+		hlen = 8 + (checksum ? 8 : 0) + (has_first ? 8 : 0);
+		if (pos + hlen + dlen > nbytes || dlen < 16)
+		{
+			free(dir);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "AOCS block at offset %s%lld runs past the end of the file", "", pos);
+		}
+		if (ndir == capdir)
+		{
+			capdir = capdir ? capdir * 2 : 1024;
+			dir = (AocsDir *) realloc(dir, sizeof(AocsDir) * (size_t) capdir);
+			if (!dir)
+				return CBGPU_ERR_NOMEM;
+		}
+		dir[ndir].off = pos + hlen;
+		dir[ndir].rowbase = row_offset + rows;
+		dir[ndir].rows = nrow;
+		dir[ndir].dlen = dlen;
+		ndir++;
+		if (raw[pos + hlen + 2] & 1)	/* DSB_HAS_NULLBITMAP */
+			anynull = true;
+		rows += nrow;
+		pos += hlen + ((int64_t) dlen + 7) / 8 * 8;
+	}
+	if (row_offset < 0 || row_offset + rows > rel->capacity)
+	{
+		free(dir);
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "AOCS column file holds %s%lld rows: more than the relation has room for", "", rows);
+	}
+	if (ndir == 0)
+	{
+		free(dir);
+		return CBGPU_OK;
+	}
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (anynull && !rel->nulls[col])
+	{
+		int			rc = cbgpu_rel_add_nullmap(rel, col);
+
+		if (rc)
+		{
+			free(dir);
+			return rc;
+		}
+	}
+	CB_CUDA(ctx, cudaMallocAsync(&d_raw, (size_t) nbytes + 16, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&d_dir, sizeof(AocsDir) * (size_t) ndir, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, (size_t) nbytes, cudaMemcpyHostToDevice, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(d_dir, dir, sizeof(AocsDir) * (size_t) ndir, cudaMemcpyHostToDevice, ctx->stream));
+	memset(&P, 0, sizeof(P));
+	P.raw = d_raw;
+	P.dir = d_dir;
+	P.nblocks = (int32_t) ndir;
+	P.attlen = attlen;
+	P.varkind = varkind;
+	P.typalign = typalign;
+	P.dscale = rel->dscales[col];
+	P.out = rel->data[col];
+	P.outnull = rel->nulls[col];
+	P.status = ctx->d_status;
+	{
+		int			blocks = (int) ((ndir + AOCS_WARPS - 1) / AOCS_WARPS);
+
+		if (blocks > ctx->sm_count * 16)
+			blocks = ctx->sm_count * 16;
+		k_aocs_decode<<<blocks, AOCS_WARPS * 32, 0, ctx->stream>>>(P);
+		CB_LAUNCHED(ctx, "k_aocs_decode");
+	}
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));	/* the caller's file buffer and `dir` are free again */
+	CB_CUDA(ctx, cudaFreeAsync(d_raw, ctx->stream));
+	CB_CUDA(ctx, cudaFreeAsync(d_dir, ctx->stream));
+	free(dir);
+	*nrows_out = rows;
+	return cbgpu_check_status(ctx);
+}

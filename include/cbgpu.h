@@ -347,6 +347,22 @@ int			cbgpu_motion_gather(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nr
 int			cbgpu_motion_broadcast(cbgpu_motion *m, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
 
 /* ------------------------------------------------------------------------------------------
+ * AOCS column files decoded on the device (the storage side of aocs_getnext, access/aocs/aocsam.c:1418:
+ * datumstreamread_block utils/datumstream/datumstream.c:1364, AppendOnlyStorageRead_GetBlockInfo
+ * cdb/cdbappendonlystorageread.c:954, DatumStreamBlockRead_GetReadyOrig / _AdvanceOrig / _Get
+ * utils/datumstream/datumstreamblock.c:153, include/utils/datumstreamblock.h:1442,1220)
+ * ------------------------------------------------------------------------------------------ */
+#define CBGPU_AOCS_VAR_NUMERIC 1	/* numeric varlena -> int64 scaled by the column's dscale             */
+#define CBGPU_AOCS_VAR_BPCHAR1 2	/* character(1) varlena -> its byte                                   */
+/* file_bytes: one column's segment file (<relfilenode>.<n>) as it lies on disk, in host memory:
+ * uncompressed SmallContent storage blocks holding Original datum stream blocks.  attlen = pg_type
+ * typlen (1/2/4/8, or -1 with varkind), typalign in bytes.  Decodes into rows [row_offset, +nrows) of
+ * column `col` (NULL bitmaps become the column's null map).  Other block kinds: CBGPU_ERR_UNSUPPORTED. */
+int			cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum,
+									 int32_t attlen, int32_t varkind, int32_t typalign, cbgpu_rel *rel, int32_t col,
+									 int64_t row_offset, int64_t *nrows);
+
+/* ------------------------------------------------------------------------------------------
  * synthetic TPC-H shaped generator (harness; same counter-based formulas as
  * cloudberry_b200/tpch.py so host and device tables are identical)
  * ------------------------------------------------------------------------------------------ */

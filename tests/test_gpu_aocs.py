@@ -1,0 +1,76 @@
+"""AOCS column files decoded ON THE DEVICE (cbgpu_aocs_decode_column) == the values the reference's own block writer
+was given (tests/golden/aocs_columns.npz, see tests/test_aocs_format.py), then a query straight off decoded files."""
+import numpy as np
+import pytest
+
+from cloudberry_b200 import capi
+from cloudberry_b200 import plan as P
+from test_aocs_format import CASES
+
+pytestmark = pytest.mark.gpu
+
+# typname -> (relation column type, attlen, varkind, typalign)
+DECODE = {"int4": (P.INT4, 4, 0, 4), "int8": (P.INT8, 8, 0, 8), "date": (P.DATE, 4, 0, 4), "float8": (P.FLOAT8, 8, 0, 8),
+          "bool": (P.BOOL, 1, 0, 1), "numeric": (P.NUMERIC, -1, 1, 4), "bpchar": (P.BPCHAR1, -1, 2, 4)}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_device_decode_matches_reference_written_values(ctx, case):
+    name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = case
+    ctype, attlen, varkind, align = DECODE[typname]
+    rel = capi.DeviceRelation(ctx, len(values), [ctype], dscales=[dscale])
+    n = rel.load_aocs_column(0, raw, checksum, attlen, varkind, align)
+    assert n == len(values)
+    got, gotnull = rel.read_column(0)
+    assert np.array_equal(gotnull.astype(np.uint8), nulls)
+    keep = nulls == 0
+    if typname == "float8":
+        assert np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64))
+    else:
+        assert np.array_equal(got[keep].astype(np.int64), values[keep])
+    rel.free()
+
+
+def test_refuses_what_it_does_not_decode(ctx):
+    name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = CASES[0]
+    rel = capi.DeviceRelation(ctx, len(values), [P.INT4])
+    bad = bytearray(raw)
+    bad[3] = (bad[3] & 0x8F) | 0x20          # header kind 2 = LargeContent
+    with pytest.raises(capi.CbgpuError):
+        rel.load_aocs_column(0, bytes(bad), checksum, 4, 0, 4)
+    with pytest.raises(capi.CbgpuError):
+        rel.load_aocs_column(0, raw[:len(raw) - 24], checksum, 4, 0, 4)      # truncated file
+    with pytest.raises(capi.CbgpuError):
+        rel.load_aocs_column(0, raw, checksum, 8, 0, 8)                      # wrong width for the column
+    rel.free()
+
+
+def test_query_over_decoded_files(ctx, oracle):
+    """scan + aggregate over a relation whose columns came from reference-written column files"""
+    by = {c[0]: c for c in CASES}
+    price, flags = by["numeric_price"], by["bpchar1_flags"]
+    n = len(price[7])
+    from cloudberry_b200.relation import HostRelation
+    from gpu_util import canon
+    rel = capi.DeviceRelation(ctx, n, [P.BPCHAR1, P.NUMERIC])
+    assert rel.load_aocs_column(0, flags[6], flags[2], -1, 2, 4) == n
+    assert rel.load_aocs_column(1, price[6], price[2], -1, 1, 4) == n
+    host = HostRelation("t", ["f", "p"], [P.BPCHAR1, P.NUMERIC], [flags[7].astype(np.uint8), price[7]], nulls=[flags[8], None])
+    sc = P.SeqScan(1, [("f", P.Var(1, 1, P.BPCHAR1)), ("p", P.Var(1, 2, P.NUMERIC, 2))])
+    from cloudberry_b200.tpch import _child_var
+    v = _child_var(sc)
+    plan = P.Agg(sc, P.AGG_HASHED, P.AGGSPLIT_SIMPLE, [1], [("f", v("f")), ("s", P.Aggref(P.AGG_SUM, v("p"))), ("n", P.Aggref(P.AGG_COUNT_STAR))],
+                 num_groups=8)
+    ex = capi.Executor(ctx, [rel])
+    got = ex.run(plan)
+    want = oracle.execute(plan, [[host]])
+    assert canon(got.rows) == canon(want.rows) and len(want.rows) == 6     # five flags + the NULL group
+    ex.close()
+    rel.free()
