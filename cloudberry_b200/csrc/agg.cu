@@ -58,6 +58,8 @@ cbgpu_agg_reset(cbgpu_aggtable *t)
 	cbgpu_ctx  *ctx = t->ctx;
 	int32_t    *dk;
 
+	t->counted = false;
+
 	CB_CUDA(ctx, cudaMallocAsync(&dk, sizeof(int32_t) * CBP_MAX_AGGS, ctx->stream));
 	CB_CUDA(ctx, cudaMemcpyAsync(dk, t->kinds, sizeof(int32_t) * CBP_MAX_AGGS, cudaMemcpyHostToDevice, ctx->stream));
 	int			blocks = (int) ((t->capacity + 255) / 256);
@@ -102,7 +104,7 @@ cbgpu_agg_create(cbgpu_ctx *ctx, int32_t nkeys, int32_t naccs, const int32_t *ac
 	CB_CUDA(ctx, cudaMallocAsync(&t->d.keynull, cap * sizeof(uint32_t), ctx->stream));
 	CB_CUDA(ctx, cudaMallocAsync(&t->d.n, cap * sizeof(int64_t) * (naccs ? naccs : 1), ctx->stream));
 	CB_CUDA(ctx, cudaMallocAsync(&t->d.sum, cap * 2 * sizeof(unsigned long long) * (naccs ? naccs : 1), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&t->d.ngroups, sizeof(int32_t) * 2, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&t->d.ngroups, sizeof(int32_t) * 4, ctx->stream));
 	t->d.full = t->d.ngroups + 1;
 	*out = t;
 	return cbgpu_agg_reset(t);
@@ -124,45 +126,73 @@ cbgpu_agg_free(cbgpu_aggtable *t)
 	free(t);
 }
 
-/* number of published groups (TupleHashTable's `members`) */
+/* number of published groups (TupleHashTable's `members`), and whether any group key is NULL */
 __global__ void
-k_agg_count(AggDev t)
+k_agg_count(AggDev t, int *anynull)
 {
 	size_t		cap = (size_t) t.mask + 1;
 	size_t		i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
 	size_t		stride = (size_t) gridDim.x * blockDim.x;
 	int			c = 0;
+	int			an = 0;
 
 	for (; i < cap; i += stride)
-		c += t.state[i] == 2;
+		if (t.state[i] == 2)
+		{
+			c++;
+			an |= t.keynull[i] != 0;
+		}
 	for (int o = 16; o > 0; o >>= 1)
+	{
 		c += __shfl_xor_sync(0xffffffffu, c, o);
-	if ((threadIdx.x & 31) == 0 && c)
-		atomicAdd(t.ngroups, c);
+		an |= __shfl_xor_sync(0xffffffffu, an, o);
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		if (c)
+			atomicAdd(t.ngroups, c);
+		if (an)
+			*anynull = 1;
+	}
 }
 
 extern "C" int
 cbgpu_agg_ngroups(cbgpu_aggtable *t, int64_t *ngroups)
 {
 	cbgpu_ctx  *ctx = t->ctx;
-	int32_t		h[2];
+	int32_t		h[3];
 
-	/* groups are counted here, once, rather than with one same-address atomic per new group */
-	CB_CUDA(ctx, cudaMemsetAsync(t->d.ngroups, 0, sizeof(int32_t), ctx->stream));
+	if (!t->counted)
 	{
-		int			blocks = (int) ((t->capacity + 1023) / 1024);
+		/* groups are counted here, once per fill, rather than with one same-address atomic per new
+		 * group; d.ngroups = {count, table-full flag, any-NULL-key flag} */
+		CB_CUDA(ctx, cudaMemsetAsync(t->d.ngroups, 0, sizeof(int32_t), ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(t->d.ngroups + 2, 0, sizeof(int32_t), ctx->stream));
+		{
+			int			blocks = (int) ((t->capacity + 1023) / 1024);
 
-		if (blocks > ctx->sm_count * 8)
-			blocks = ctx->sm_count * 8;
-		k_agg_count<<<blocks, 256, 0, ctx->stream>>>(t->d);
-		CB_LAUNCHED(ctx, "k_agg_count");
+			if (blocks > ctx->sm_count * 8)
+				blocks = ctx->sm_count * 8;
+			k_agg_count<<<blocks, 256, 0, ctx->stream>>>(t->d, t->d.ngroups + 2);
+			CB_LAUNCHED(ctx, "k_agg_count");
+		}
+		CB_CUDA(ctx, cudaMemcpyAsync(h, t->d.ngroups, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if (h[1])
+			return cb_fail(ctx, CBGPU_ERR_NOMEM, "aggregate hash table overflow (%s capacity %lld slots)", "", t->capacity);
+		t->ngroups = h[0];
+		t->anynull = h[2];
+		t->counted = true;
 	}
-	CB_CUDA(ctx, cudaMemcpyAsync(h, t->d.ngroups, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	if (h[1])
-		return cb_fail(ctx, CBGPU_ERR_NOMEM, "aggregate hash table overflow (%s capacity %lld slots)", "", t->capacity);
-	*ngroups = h[0];
+	*ngroups = t->ngroups;
 	return CBGPU_OK;
+}
+
+/* the table is about to be written (a pipeline's AGG sink, a reset): forget the cached count */
+void
+cb_agg_touch(cbgpu_aggtable *t)
+{
+	t->counted = false;
 }
 
 /* compaction: slots in `ready` state -> dense rows (agg_retrieve_hash_table's table walk,
@@ -329,7 +359,6 @@ cbgpu_agg_to_rel(cbgpu_aggtable *t, const int32_t *keytypes, cbgpu_rel **out)
 	int			ncols = t->d.nkeys + t->d.naccs * 3;
 	cbgpu_rel  *rel;
 	AggRelOut	o;
-	int		   *d_flag;
 	int			h_flag = 0;
 
 	if (rc)
@@ -346,14 +375,8 @@ cbgpu_agg_to_rel(cbgpu_aggtable *t, const int32_t *keytypes, cbgpu_rel **out)
 
 	if (blocks > ctx->sm_count * 8)
 		blocks = ctx->sm_count * 8;
-	/* NULL group keys need null byte-maps on the key columns */
-	CB_CUDA(ctx, cudaMallocAsync(&d_flag, sizeof(int), ctx->stream));
-	CB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
-	k_agg_anynull<<<blocks, 256, 0, ctx->stream>>>(t->d, d_flag);
-	CB_LAUNCHED(ctx, "k_agg_anynull");
-	CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	CB_CUDA(ctx, cudaFreeAsync(d_flag, ctx->stream));
+	/* NULL group keys need null byte-maps on the key columns (flag gathered with the group count) */
+	h_flag = t->anynull;
 	for (int k = 0; k < t->d.nkeys; k++)
 	{
 		o.key[k] = rel->data[k];

@@ -83,6 +83,10 @@ struct cbgpu_aggtable
 	AggDev		d;
 	int64_t		capacity;
 	int32_t		kinds[CBP_MAX_AGGS];
+	/* group count / "some group key is NULL", valid until the table is written again */
+	bool		counted;
+	int64_t		ngroups;
+	int32_t		anynull;
 };
 
 /* join hash table, device view: slot = hash32 << 32 | rowid32, EMPTY = ~0 */

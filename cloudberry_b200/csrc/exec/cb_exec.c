@@ -1646,11 +1646,14 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 
 			for (int c = 0; c < ncols; c++)
 				anynull |= nullable[c];
-			if (ic && ic->direct_begin && !anynull)
+			if (ic && ic->direct_begin)
 			{
 				int64_t		cap = 0;
 
-				if (ic->direct_begin(ic, es, m->motionID, ncols, types, dscales, pl->nrows, &cap, &part_cols, &part_counts) == CBGPU_OK)
+				/* every segment calls begin (it is collective); one whose data rules the direct path out
+				 * here - a nullable column exists on this segment only - announces -1 rows and all of
+				 * them take the staged path together */
+				if (ic->direct_begin(ic, es, m->motionID, ncols, types, dscales, anynull ? -1 : pl->nrows, &cap, &part_cols, &part_counts) == CBGPU_OK)
 				{
 					direct = 1;
 					*seg_capacity = cap;

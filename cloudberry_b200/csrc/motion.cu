@@ -45,10 +45,15 @@ struct cbgpu_motion
 	size_t		dx_off[CBP_MAX_OUT];
 	int64_t		direct_bytes;	/* payload bytes stored into peers' windows (diagnostics / bench)      */
 	int64_t		direct_exchanges;
+	int64_t		gather_seq;		/* direct Gathers so far: picks the buffer                            */
 };
 
 #define DX_TAB_COLS (64 * CBP_MAX_OUT)
 #define DX_ALIGN 256
+/* the tail of every window: two alternating Gather buffers; each holds [64 row counts] + one payload
+ * slot per sender */
+#define GX_BYTES ((size_t) 32 << 20)
+#define GX_HDR 1024
 
 #define CB_NCCL(ctx, call) \
 	do { \
@@ -90,7 +95,7 @@ cbgpu_motion_create(cbgpu_ctx *ctx, int rank, int nranks, const void *unique_id1
 	m->nranks = nranks;
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
 	CB_NCCL(ctx, ncclCommInitRank(&m->comm, nranks, id, rank));
-	CB_CUDA(ctx, cudaMalloc(&m->d_counts, sizeof(long long) * (size_t) nranks * (size_t) (nranks + 1)));
+	CB_CUDA(ctx, cudaMalloc(&m->d_counts, sizeof(long long) * (size_t) (nranks + 2) * (size_t) (nranks + 2)));
 	*out = m;
 	return motion_window_setup(m);
 }
@@ -186,9 +191,9 @@ motion_window_setup(cbgpu_motion *m)
 	{
 		CB_CUDA(ctx, cudaMalloc(&m->d_tab, sizeof(void *) * (DX_TAB_COLS + 64)));
 		CB_CUDA(ctx, cudaMallocHost(&m->h_tab, sizeof(void *) * (DX_TAB_COLS + 64)));
-		m->direct_ok = true;
+		m->direct_ok = m->win_bytes >= 4 * GX_BYTES;
 	}
-	else
+	if (!m->direct_ok)
 		motion_window_teardown(m);
 	return CBGPU_OK;
 }
@@ -256,20 +261,47 @@ cbgpu_motion_bytes_sent(const cbgpu_motion *m)
 	return m->bytes_sent;
 }
 
-/* every rank learns every rank's per-destination row counts: matrix[s * nranks + d] */
+/* every rank learns every rank's per-destination row counts: matrix[s * nranks + d].  The same
+ * all-gather carries which columns of `send` have a NULL map on each rank: a map may exist on one
+ * segment only (it follows the data), but sender and receiver must post the same transfers, so every
+ * rank gives `send` (zeroed) maps for the union before the rows move. */
 static int
-exchange_counts(cbgpu_motion *m, const int64_t *mine, int64_t *matrix)
+exchange_counts(cbgpu_motion *m, cbgpu_rel *send, const int64_t *mine, int64_t *matrix)
 {
 	cbgpu_ctx  *ctx = m->ctx;
-	int			n = m->nranks;
-	long long  *d_mine = m->d_counts + (size_t) n * n;
+	const int	n = m->nranks;
+	long long  *d_all = m->d_counts;
+	long long  *d_mine = m->d_counts + (size_t) (n + 1) * n;
+	long long	h_mine[65], h_all[65 * 64];
+	unsigned long long mask = 0,
+				all = 0;
 
-	CB_CUDA(ctx, cudaMemcpyAsync(d_mine, mine, sizeof(long long) * n, cudaMemcpyHostToDevice, ctx->stream));
-	CB_NCCL(ctx, ncclAllGather(d_mine, m->d_counts, (size_t) n, ncclInt64, m->comm, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(matrix, m->d_counts, sizeof(long long) * (size_t) n * n, cudaMemcpyDeviceToHost, ctx->stream));
+	for (int c = 0; c < send->ncols && c < 64; c++)
+		if (send->nulls[c])
+			mask |= 1ull << c;
+	for (int d = 0; d < n; d++)
+		h_mine[d] = mine[d];
+	h_mine[n] = (long long) mask;
+	CB_CUDA(ctx, cudaMemcpyAsync(d_mine, h_mine, sizeof(long long) * (size_t) (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+	CB_NCCL(ctx, ncclAllGather(d_mine, d_all, (size_t) (n + 1), ncclInt64, m->comm, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(h_all, d_all, sizeof(long long) * (size_t) (n + 1) * n, cudaMemcpyDeviceToHost, ctx->stream));
 	if (ctx->trace_on)
 		cb_trace_mark(ctx, "nccl:counts");
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (int s = 0; s < n; s++)
+	{
+		for (int d = 0; d < n; d++)
+			matrix[(size_t) s * n + d] = h_all[(size_t) s * (n + 1) + d];
+		all |= (unsigned long long) h_all[(size_t) s * (n + 1) + n];
+	}
+	for (int c = 0; c < send->ncols && c < 64; c++)
+		if (((all >> c) & 1) && !send->nulls[c])
+		{
+			int			rc = cbgpu_rel_add_nullmap(send, c);
+
+			if (rc)
+				return rc;
+		}
 	return CBGPU_OK;
 }
 
@@ -364,7 +396,7 @@ cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *count
 
 	if (n > 64)
 		return cb_fail(m->ctx, CBGPU_ERR_UNSUPPORTED, "more than 64 segments%s", "", 0);
-	rc = exchange_counts(m, counts, matrix);
+	rc = exchange_counts(m, send, counts, matrix);
 	if (rc == CBGPU_OK)
 	{
 		for (int s = 0; s < n; s++)
@@ -399,6 +431,25 @@ cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *count
  *           reads its counter and moves the rows out of the window into a relation of its own, so
  *           the window is free again when the next Motion's announcement completes
  * --------------------------------------------------------------------------------------------- */
+struct CopyCols
+{
+	void	   *dst[CBP_MAX_OUT];
+	const void *src[CBP_MAX_OUT];
+	size_t		bytes[CBP_MAX_OUT];
+};
+
+__global__ void
+k_copy_cols(CopyCols cc)
+{
+	const int	c = blockIdx.x;
+	const size_t n = cc.bytes[c];
+	unsigned char *d = (unsigned char *) cc.dst[c];
+	const unsigned char *s = (const unsigned char *) cc.src[c];
+
+	for (size_t i = threadIdx.x; i < n; i += blockDim.x)
+		d[i] = s[i];
+}
+
 extern "C" int
 cbgpu_motion_direct_available(const cbgpu_motion *m)
 {
@@ -435,6 +486,10 @@ cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, 
 	if (ctx->trace_on)
 		cb_trace_mark(ctx, "p2p:announce");
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	/* a rank that cannot take part (input_rows < 0: e.g. a nullable column there) vetoes for everyone */
+	for (int s = 0; s < n; s++)
+		if (h_rows[s] < 0)
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "direct Redistribute vetoed by segment %s%lld", "", s);
 	/* the same arithmetic on every rank: even share + 25 % skew allowance + slack per sender */
 	for (int s = 0; s < n; s++)
 	{
@@ -452,7 +507,7 @@ cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, 
 		m->dx_off[c] = off;
 		off += (((size_t) cap * (size_t) cb_type_w(types[c])) + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
 	}
-	if (off > m->win_bytes)
+	if (off + 2 * GX_BYTES > m->win_bytes)
 		return cb_fail(ctx, CBGPU_ERR_NOMEM, "direct Redistribute needs %s%lld bytes of window (raise CBGPU_MOTION_WINDOW_MB)", "", (long long) off);
 	m->dx_ncols = ncols;
 	m->dx_cap = cap;
@@ -492,9 +547,24 @@ cbgpu_motion_direct_end(cbgpu_motion *m, int64_t rows_sent_elsewhere, cbgpu_rel 
 	rc = cbgpu_rel_create(ctx, (int64_t) got, m->dx_ncols, m->dx_types, m->dx_dscales, recv);
 	if (rc)
 		return rc;
-	for (int c = 0; c < m->dx_ncols && got > 0; c++)
-		CB_CUDA(ctx, cudaMemcpyAsync((*recv)->data[c], m->win + m->dx_off[c], (size_t) got * (size_t) cb_type_w(m->dx_types[c]),
-									 cudaMemcpyDeviceToDevice, ctx->stream));
+	if (got > 0 && got <= 65536)
+	{
+		/* a few rows (partial aggregate states, top-N candidates): one launch for all columns */
+		CopyCols	cc;
+
+		for (int c = 0; c < m->dx_ncols; c++)
+		{
+			cc.dst[c] = (*recv)->data[c];
+			cc.src[c] = m->win + m->dx_off[c];
+			cc.bytes[c] = (size_t) got * (size_t) cb_type_w(m->dx_types[c]);
+		}
+		k_copy_cols<<<m->dx_ncols, 256, 0, ctx->stream>>>(cc);
+		CB_LAUNCHED(ctx, "k_copy_cols");
+	}
+	else
+		for (int c = 0; c < m->dx_ncols && got > 0; c++)
+			CB_CUDA(ctx, cudaMemcpyAsync((*recv)->data[c], m->win + m->dx_off[c], (size_t) got * (size_t) cb_type_w(m->dx_types[c]),
+										 cudaMemcpyDeviceToDevice, ctx->stream));
 	if (ctx->trace_on)
 		cb_trace_mark(ctx, "p2p:copy-out");
 	{
@@ -509,6 +579,141 @@ cbgpu_motion_direct_end(cbgpu_motion *m, int64_t rows_sent_elsewhere, cbgpu_rel 
 	return CBGPU_OK;
 }
 
+/* direct Gather (a handful of rows per sender: final aggregates, top-N candidates): every sender
+ * stores its row count and its rows into ITS slot of the root's Gather buffer, one 4-byte all-reduce
+ * says "all stored" (and carries "somebody's rows did not fit": then everyone takes the NCCL path),
+ * the root assembles.  Two buffers alternate, so the all-reduce of Gather k + 1 is also the proof that
+ * the root has emptied the buffer Gather k + 2 will overwrite. */
+struct GatherPut
+{
+	long long  *hdr;			/* root's count slot for this sender                                  */
+	long long	nrows;
+	CopyCols	cc;
+	int			ncols;
+};
+
+__global__ void
+k_gather_put(GatherPut g)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		*g.hdr = g.nrows;
+	if ((int) blockIdx.x < g.ncols)
+	{
+		const size_t n = g.cc.bytes[blockIdx.x];
+		unsigned char *d = (unsigned char *) g.cc.dst[blockIdx.x];
+		const unsigned char *s = (const unsigned char *) g.cc.src[blockIdx.x];
+
+		for (size_t i = threadIdx.x; i < n; i += blockDim.x)
+			d[i] = s[i];
+	}
+}
+
+/* returns 1 when done directly, 0 when the caller must take the staged path, < 0 on error */
+static int
+gather_direct(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv)
+{
+	cbgpu_ctx  *ctx = m->ctx;
+	const int	n = m->nranks;
+	const size_t slot = ((GX_BYTES - GX_HDR) / (size_t) n) / DX_ALIGN * DX_ALIGN;
+	const size_t buf = m->win_bytes - 2 * GX_BYTES + (size_t) (m->gather_seq & 1) * GX_BYTES;
+	int		   *d_flag = (int *) (m->d_counts + (size_t) n * n);
+	size_t		off[CBP_MAX_OUT];
+	size_t		need = 0;
+	int			fits = 1;
+	int			h_flag = 0;
+	long long	h_cnt[64];
+
+	if (!m->direct_ok || n > 64 || send->ncols > CBP_MAX_OUT)
+		return 0;
+	for (int c = 0; c < send->ncols; c++)
+	{
+		if (send->nulls[c])
+			fits = 0;			/* a null map may exist on one rank only: the decision rides on the all-reduce */
+		off[c] = need;
+		need += ((size_t) nrows * (size_t) cb_type_w(send->types[c]) + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
+	}
+	if (need > slot)
+		fits = 0;
+	m->gather_seq++;
+	if (fits)
+	{
+		GatherPut	g;
+		char	   *base = m->peer_win[root] + buf;
+
+		memset(&g, 0, sizeof(g));
+		g.hdr = (long long *) base + m->rank;
+		g.nrows = nrows;
+		g.ncols = send->ncols;
+		for (int c = 0; c < send->ncols; c++)
+		{
+			g.cc.dst[c] = base + GX_HDR + (size_t) m->rank * slot + off[c];
+			g.cc.src[c] = send->data[c];
+			g.cc.bytes[c] = (size_t) nrows * (size_t) cb_type_w(send->types[c]);
+		}
+		k_gather_put<<<send->ncols > 0 ? send->ncols : 1, 256, 0, ctx->stream>>>(g);
+		CB_LAUNCHED(ctx, "k_gather_put");
+	}
+	h_flag = fits ? 0 : 1;
+	CB_CUDA(ctx, cudaMemcpyAsync(d_flag, &h_flag, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+	CB_NCCL(ctx, ncclAllReduce(d_flag, d_flag, 1, ncclInt32, ncclMax, m->comm, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	if (m->rank == root)
+		CB_CUDA(ctx, cudaMemcpyAsync(h_cnt, m->win + buf, sizeof(long long) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, "p2p:gather");
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (h_flag)
+		return 0;				/* somebody's rows were too many for a slot: nothing was consumed, go staged */
+	{
+		int64_t		total = 0;
+		int			rc;
+
+		if (m->rank == root)
+			for (int s = 0; s < n; s++)
+				total += h_cnt[s];
+		rc = make_recv(m, send, total, recv);
+		if (rc)
+			return -rc;
+		if (m->rank == root && total > 0)
+		{
+			int64_t		at = 0;
+
+			for (int s = 0; s < n; s++)
+			{
+				CopyCols	cc;
+
+				if (h_cnt[s] == 0)
+					continue;
+				for (int c = 0; c < send->ncols; c++)
+				{
+					const size_t w = (size_t) cb_type_w(send->types[c]);
+					/* every sender laid its columns out with ITS row count */
+					size_t		o = 0;
+
+					for (int cc2 = 0; cc2 < c; cc2++)
+						o += ((size_t) h_cnt[s] * (size_t) cb_type_w(send->types[cc2]) + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
+					cc.dst[c] = (char *) (*recv)->data[c] + (size_t) at * w;
+					cc.src[c] = m->win + buf + GX_HDR + (size_t) s * slot + o;
+					cc.bytes[c] = (size_t) h_cnt[s] * w;
+				}
+				k_copy_cols<<<send->ncols, 256, 0, ctx->stream>>>(cc);
+				CB_LAUNCHED(ctx, "k_copy_cols");
+				at += h_cnt[s];
+			}
+		}
+		if (m->rank != root)
+		{
+			int64_t		roww = 0;
+
+			for (int c = 0; c < send->ncols; c++)
+				roww += cb_type_w(send->types[c]);
+			m->direct_bytes += nrows * roww;
+		}
+	}
+	m->direct_exchanges++;
+	return 1;
+}
+
 extern "C" int
 cbgpu_motion_gather(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv)
 {
@@ -520,9 +725,15 @@ cbgpu_motion_gather(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, c
 
 	if (n > 64)
 		return cb_fail(m->ctx, CBGPU_ERR_UNSUPPORTED, "more than 64 segments%s", "", 0);
+	rc = gather_direct(m, root, send, nrows, recv);
+	if (rc != 0)
+	{
+		free(matrix);
+		return rc > 0 ? CBGPU_OK : -rc;
+	}
 	for (int d = 0; d < n; d++)
 		mine[d] = d == root ? nrows : 0;
-	rc = exchange_counts(m, mine, matrix);
+	rc = exchange_counts(m, send, mine, matrix);
 	if (rc == CBGPU_OK)
 	{
 		for (int s = 0; s < n; s++)
@@ -554,7 +765,7 @@ cbgpu_motion_broadcast(cbgpu_motion *m, cbgpu_rel *send, int64_t nrows, cbgpu_re
 		return cb_fail(m->ctx, CBGPU_ERR_UNSUPPORTED, "more than 64 segments%s", "", 0);
 	for (int d = 0; d < n; d++)
 		mine[d] = nrows;
-	rc = exchange_counts(m, mine, matrix);
+	rc = exchange_counts(m, send, mine, matrix);
 	if (rc == CBGPU_OK)
 	{
 		for (int s = 0; s < n; s++)

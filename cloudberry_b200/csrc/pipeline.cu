@@ -134,6 +134,7 @@ cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
 			if (!s->agg || s->nkeys != s->agg->d.nkeys || s->naccs != s->agg->d.naccs)
 				return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: agg table shape mismatch%s", "", 0);
 			ds->agg = s->agg->d;
+			cb_agg_touch(s->agg);
 			ds->nkeys = s->nkeys;
 			ds->naccs = s->naccs;
 			for (int k = 0; k < s->nkeys; k++)

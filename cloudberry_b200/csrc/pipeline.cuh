@@ -158,6 +158,7 @@ sink_store(void *col, int type, uint64_t pos, int64_t v)
 	}
 }
 
+void		cb_agg_touch(cbgpu_aggtable *t);
 int			cb_klog_begin(cbgpu_ctx *ctx, const char *name);
 void		cb_klog_end(cbgpu_ctx *ctx, int i);
 int			cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d);

@@ -330,7 +330,8 @@ int			cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t 
 /* Direct Redistribute: partition + exchange fused into the sender slice's own kernel, over peer memory
  * (every rank's receive window is mapped into every other rank through CUDA IPC at create time; rows
  * are stored straight into the destination's HBM over NVLink).  begin and end are collective.
- *   begin: announce this rank's sender input rows; returns the per-receiver row capacity and two device
+ *   begin: announce this rank's sender input rows (-1 = this rank cannot go direct, e.g. a nullable
+ *          column: then begin fails on EVERY rank and all take cbgpu_motion_redistribute); returns the per-receiver row capacity and two device
  *          tables for the PARTITION sink: dest_cols[d * ncols + c] = base of column c in segment d's
  *          window, dest_counts[d] = segment d's row counter (CbpSink.part_cols / part_counts)
  *   end:   after the pipeline ran: wait for every sender, return the rows addressed to this rank.

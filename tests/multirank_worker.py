@@ -55,6 +55,30 @@ def main():
         print("MULTIRANK FAIL: distribute_by_hash gave %d rows, the oracle's shard has %d" % (len(got), len(want)))
     mine_li.free()
     sl.free()
+    # a null map that exists on ONE segment only: the direct-or-staged decision of every Motion must still be taken
+    # by all segments together (Redistribute: veto in the announcement; Gather: flag in the all-reduce)
+    from cloudberry_b200 import plan as P
+    from cloudberry_b200.relation import HostRelation
+    kk = np.arange(100, dtype=np.int64) + 1000 * rank
+    nl = (np.arange(100) % 10 == 0).astype(np.uint8) if rank == 0 else None
+    t = HostRelation("t", ["k", "v"], [P.INT4, P.INT8], [kk, kk * 2], nulls=[nl, None])
+    dt = capi.DeviceRelation.from_host(ctx, t)
+    ext = capi.Executor(ctx, [dt], motion=motion)
+    sc = P.SeqScan(1, [("k", P.Var(1, 1, P.INT4)), ("v", P.Var(1, 2, P.INT8))])
+    mh = P.Motion(sc, P.MOTIONTYPE_HASH, [P.out_var(sc, 1)], world)
+    rt = ext.run(P.Motion(mh, P.MOTIONTYPE_GATHER))
+    if rank == 0:
+        want_t = []
+        for r in range(world):
+            for i in range(100):
+                k = i + 1000 * r
+                want_t.append((None if (r == 0 and i % 10 == 0) else k, 2 * k))
+        got_t = sorted(((-1 if a is None else a), b) for a, b in (tuple(x) for x in rt.rows))
+        if got_t != sorted(((-1 if a is None else a), b) for a, b in want_t):
+            ok = False
+            print("MULTIRANK FAIL: asymmetric null map through Redistribute + Gather: %d rows" % len(rt.rows))
+    ext.close()
+    dt.free()
     r1 = ex.run(tpch.q1_plan(world))
     r3 = ex.run(tpch.q3_plan(seg, world, customer_replicated=replicated))
     r5 = ex.run(tpch.q5_plan(reg, world, replicated=replicated))
