@@ -445,20 +445,6 @@ translate_plan(Plan *p, EState *estate, List **rels)
 /* ------------------------------------------------------------------------------------------
  * the replaced ExecProcNode
  * ------------------------------------------------------------------------------------------ */
-static void
-shim_release(void *arg)
-{
-	CbgpuShim  *shim = (CbgpuShim *) arg;
-
-	if (shim->cbps)
-		cb_ExecEndNode(shim->cbps);
-	shim->cbps = NULL;
-	if (shim->cbestate)
-		cb_FreeExecutorState(shim->cbestate);
-	shim->cbestate = NULL;
-	shim_list = NULL;			/* the entries live in the query context that is going away */
-}
-
 /* PlanState -> shim: a short list in the query context (a core patch would add one pointer to PlanState) */
 typedef struct ShimEntry
 {
@@ -476,6 +462,20 @@ shim_of(PlanState *ps)
 			return e->shim;
 	elog(ERROR, "cbgpu: no shim registered for plan node %d", ps->plan->plan_node_id);
 	return NULL;
+}
+
+static void
+shim_release(void *arg)
+{
+	CbgpuShim  *shim = (CbgpuShim *) arg;
+
+	if (shim->cbps)
+		cb_ExecEndNode(shim->cbps);
+	shim->cbps = NULL;
+	if (shim->cbestate)
+		cb_FreeExecutorState(shim->cbestate);
+	shim->cbestate = NULL;
+	shim_list = NULL;			/* the entries live in the query context that is going away */
 }
 
 static TupleTableSlot *
