@@ -49,10 +49,18 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+            # only this rank's GPU: querying all eight per sample is too slow for a timed region of ~100 ms
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                       "-lms", "10"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def ready(self):
+        """has nvidia-smi written its first sample yet?"""
+        try:
+            return self.p is None or os.path.getsize(self.f.name) > 0
+        except OSError:
+            return True
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -209,6 +217,15 @@ def main():
     sampler.start()         # covers warm-up and the timed region: both are the same load
     for _ in range(args.warmup):
         res = ex.run(plan1)
+    # keep the same load up (untimed) until the clock sampler is actually sampling; with several ranks the number of
+    # extra steps must be the same everywhere (every step holds collectives), so it is fixed there
+    if dist:
+        for _ in range(80):
+            res = ex.run(plan1)
+    else:
+        t_wait = time.perf_counter()
+        while not sampler.ready() and time.perf_counter() - t_wait < 3.0:
+            res = ex.run(plan1)
     kernel_ms = []
     barrier()
     l0 = ctx.launches()
