@@ -35,7 +35,12 @@
 
 #define PC_THREADS 256
 #define PC_TILE 2048			/* driving rows per run of stage F                                    */
+#ifndef PC_BATCH
 #define PC_BATCH 1024			/* queue entries per run of any other stage                           */
+#endif
+#ifndef PC_OCC
+#define PC_OCC 4				/* resident CTAs per SM the register budget is set for                */
+#endif
 #define PC_U (PC_BATCH / PC_THREADS)
 #define PC_Q0CAP (PC_BATCH + PC_TILE)
 #define PC_QCAP (2 * PC_BATCH)	/* a consumer runs at PC_BATCH, a producer adds at most PC_BATCH      */
@@ -499,7 +504,7 @@ pc_range8(int4 a, int4 b, int32_t lo, uint32_t span)
 		((unsigned) ((unsigned) (b.z - lo) <= span) << 6) | ((unsigned) ((unsigned) (b.w - lo) <= span) << 7);
 }
 
-__global__ void __launch_bounds__(PC_THREADS, 4)
+__global__ void __launch_bounds__(PC_THREADS, PC_OCC)
 k_probe_chain(const __grid_constant__ PcParams P)
 {
 	__shared__ uint32_t q0[PC_Q0CAP];
@@ -967,7 +972,7 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 	/* persistent grid: 4 CTAs per SM; queue k >= 1 holds (k + 3) / 2 words per entry */
 	const bool	iota = P.nfilters == 0 && P.visimap == NULL;
 	const int64_t ntiles = (p->nrows + (iota ? PC_BATCH : PC_TILE) - 1) / (iota ? PC_BATCH : PC_TILE);
-	int			blocks = ctx->sm_count * 4;
+	int			blocks = ctx->sm_count * PC_OCC;
 	int64_t		words = 0;
 
 	if (blocks > ntiles)
