@@ -24,9 +24,18 @@
  * row its physical datum index; fixed-width datums are then gathered in parallel; varlena datums are
  * located by lane 0 walking 32 lengths at a time, and decoded by all lanes.
  *
- * Supported: uncompressed SmallContent blocks holding Original datum stream blocks (what an AOCS
- * table without compresstype / rle_type writes).  Bulk-compressed, large-content and Dense (RLE /
- * delta) blocks are refused with CBGPU_ERR_UNSUPPORTED, never guessed at.
+ *   Dense blocks (compresstype = rle_type, compresslevel 1: DatumStreamBlock_Dense + Rle_Extension,
+ *       include/utils/datumstreamblock.h:86-170; GetReadyDense datumstreamblock.c:627-1010; AdvanceDense
+ *       datumstreamblock.h:1725-1960): the NULL bitmap has one bit per NON-REPEATED position, the
+ *       compress bitmap one bit per physical datum, a set bit = "repeats `count` more times", counts in
+ *       the 1-4 byte codec of datumstreamblock.h:617-730.  A warp takes 32 positions at a time: lane 0
+ *       decodes their repeat counts (and varlena offsets), a warp scan of the run lengths gives every
+ *       position its first output row, short runs are written by their lane, long runs by the warp.
+ *
+ * Supported: uncompressed SmallContent / NonBulkDenseContent storage blocks holding Original or Dense
+ * (RLE) datum stream blocks.  Bulk-compressed and large-content blocks, and Dense blocks with delta
+ * range encoding (rle_type on int4 / int8 / date / time columns), are refused with
+ * CBGPU_ERR_UNSUPPORTED, never guessed at.
  */
 #include "common.cuh"
 
@@ -126,10 +135,223 @@ aocs_numeric(const uint8_t *body, int len, int dscale, int64_t *out)
 	return true;
 }
 
+/* value of the datum at d (fixed width: the value; numeric: scaled integer; char(1): the byte) */
+__device__ __forceinline__ int64_t
+aocs_value(const AocsParams &P, const uint8_t *d)
+{
+	int64_t		v = 0;
+
+	if (P.attlen > 0)
+	{
+		switch (P.attlen)
+		{
+			case 1: v = (int64_t) *d; break;
+			case 2: v = (int64_t) *(const int16_t *) d; break;
+			case 4: v = (int64_t) *(const int32_t *) d; break;
+			default: v = *(const long long *) d; break;
+		}
+		return v;
+	}
+	const uint32_t b0 = d[0];
+	const int	hdr = (b0 & 1u) ? 1 : 4;
+	const int	size = (b0 & 1u) ? (int) (b0 >> 1) : (int) ((aocs_le32(d) >> 2) & 0x3FFFFFFFu);
+
+	if (P.varkind == CBGPU_AOCS_VAR_NUMERIC)
+	{
+		if (size - hdr < 2 || !aocs_numeric(d + hdr, size - hdr, P.dscale, &v))
+			atomicExch(P.status, CBGPU_ERR_OVERFLOW);
+	}
+	else
+		v = size - hdr > 0 ? (int64_t) d[hdr] : (int64_t) ' ';
+	return v;
+}
+
+__device__ __forceinline__ void
+aocs_store(const AocsParams &P, int64_t orow, int64_t v, bool isnull)
+{
+	switch (P.attlen > 0 ? P.attlen : (P.varkind == CBGPU_AOCS_VAR_NUMERIC ? 8 : 1))
+	{
+		case 1: ((uint8_t *) P.out)[orow] = (uint8_t) v; break;
+		case 2: ((int16_t *) P.out)[orow] = (int16_t) v; break;
+		case 4: ((int32_t *) P.out)[orow] = (int32_t) v; break;
+		default: ((int64_t *) P.out)[orow] = v; break;
+	}
+	if (P.outnull)
+		P.outnull[orow] = isnull ? 1 : 0;
+}
+
+/* one Dense (optionally RLE) datum stream block, by one warp */
+__device__ __forceinline__ void
+aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uint32_t *s_off, uint32_t *s_rep)
+{
+	const int	lane = threadIdx.x & 31;
+	const uint32_t flags = (uint32_t) blk[2] | ((uint32_t) blk[3] << 8);
+	const int32_t logical = (int32_t) aocs_le32(blk + 4);
+	const int32_t physical = (int32_t) aocs_le32(blk + 8);
+	const uint32_t psize = aocs_le32(blk + 12);
+	const bool	rle = (flags & 2u) != 0;
+	uint32_t	p = 16;
+	uint32_t	nn_count = 0,
+				c_count = 0,
+				rc_size = 0;
+	const uint8_t *bitmap = NULL,
+			   *cbitmap = NULL,
+			   *rc = NULL;
+
+	if (logical != D.rows || (flags & 4u) || (flags & ~7u))
+	{
+		/* DSB_HAS_DELTA_COMPRESSION: not decoded here */
+		if (lane == 0)
+			atomicExch(P.status, (flags & 4u) ? CBGPU_ERR_UNSUPPORTED : CBGPU_ERR_INVALID);
+		return;
+	}
+	if (rle)
+	{
+		nn_count = aocs_le32(blk + p);
+		c_count = aocs_le32(blk + p + 4);
+		rc_size = aocs_le32(blk + p + 12);
+		p += 16;
+	}
+	if (flags & 1u)
+	{
+		const uint32_t nb = rle ? nn_count : (uint32_t) logical;
+
+		bitmap = blk + p;
+		p += (nb + 7u) >> 3;
+	}
+	if (rle)
+	{
+		cbitmap = blk + p;
+		p += (c_count + 7u) >> 3;
+		rc = blk + p;
+		p += rc_size;
+	}
+	p = (p + 7u) & ~7u;
+	if ((int64_t) p + psize > D.dlen + 8)
+	{
+		if (lane == 0)
+			atomicExch(P.status, CBGPU_ERR_INVALID);
+		return;
+	}
+	const uint8_t *data = blk + p;
+	/* positions = the items the NULL bitmap counts: NULLs and non-repeated datums */
+	const uint32_t npos = bitmap ? (rle ? nn_count : (uint32_t) logical) : (uint32_t) physical;
+	uint32_t	dbase = 0,		/* physical datums before this trip */
+				cur = 0,		/* byte offset of the next varlena datum */
+				rcp = 0;		/* byte offset of the next repeat count */
+	int64_t		rowbase = 0;	/* logical rows before this trip */
+
+	for (uint32_t p0 = 0; p0 < npos; p0 += 32)
+	{
+		const uint32_t pos = p0 + lane;
+		const bool	inr = pos < npos;
+		const bool	isnull = inr && bitmap && ((bitmap[pos >> 3] >> (pos & 7)) & 1);
+		const unsigned nn = __ballot_sync(0xffffffffu, inr && !isnull);
+		const int	k = __popc(nn & ((1u << lane) - 1));
+		const int	cnt = __popc(nn);
+		const uint32_t di = dbase + (uint32_t) k;
+		const bool	cb = inr && !isnull && rle && ((cbitmap[di >> 3] >> (di & 7)) & 1);
+		const unsigned cm = __ballot_sync(0xffffffffu, cb);
+
+		if (lane == 0)
+		{
+			/* repeat counts of this trip's compressed datums (DatumStreamInt32Compress_Decode) ... */
+			uint32_t	r = rcp;
+			const int	nc = __popc(cm);
+
+			for (int i = 0; i < nc; i++)
+			{
+				const uint32_t b0 = rc[r];
+				const int	len = (int) (b0 >> 6) + 1;
+				uint32_t	v = b0 & 0x3Fu;
+
+				for (int j = 1; j < len; j++)
+					v = (v << 8) | rc[r + j];
+				s_rep[i] = v;
+				r += (uint32_t) len;
+			}
+			rcp = r;
+			/* ... and, for varlena columns, where its datums start */
+			if (P.attlen < 0)
+			{
+				uint32_t	c = cur;
+
+				for (int i = 0; i < cnt; i++)
+				{
+					s_off[i] = c;
+					const uint32_t b0 = data[c];
+					const uint32_t size = (b0 & 1u) ? (b0 >> 1) : ((aocs_le32(data + c) >> 2) & 0x3FFFFFFFu);
+
+					if (size == 0 || c + size > psize)
+					{
+						atomicExch(P.status, CBGPU_ERR_INVALID);
+						c = psize;
+						break;
+					}
+					c += size;
+					if (c < psize && data[c] == 0)
+						c = (c + (uint32_t) P.typalign - 1u) & ~((uint32_t) P.typalign - 1u);
+				}
+				cur = c;
+			}
+		}
+		rcp = __shfl_sync(0xffffffffu, rcp, 0);
+		cur = __shfl_sync(0xffffffffu, cur, 0);
+		__syncwarp();
+		/* run length of every position, its first output row by a warp scan */
+		const uint32_t len = !inr ? 0u : (isnull ? 1u : 1u + (cb ? s_rep[__popc(cm & ((1u << lane) - 1))] : 0u));
+		uint32_t	x = len;
+
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+
+			if (lane >= d)
+				x += y;
+		}
+		const uint32_t total = __shfl_sync(0xffffffffu, x, 31);
+		const int64_t first = rowbase + (int64_t) (x - len);
+		int64_t		v = 0;
+
+		if (inr && !isnull)
+			v = aocs_value(P, P.attlen > 0 ? data + (size_t) di * P.attlen : data + s_off[k]);
+		if (__any_sync(0xffffffffu, first + (int64_t) len > D.rows))
+		{
+			if (lane == 0)
+				atomicExch(P.status, CBGPU_ERR_INVALID);	/* repeat counts run past the block's row count */
+			return;
+		}
+		/* short runs by their own lane, long runs by the whole warp */
+		if (len > 0 && len <= 8)
+			for (uint32_t i = 0; i < len; i++)
+				aocs_store(P, D.rowbase + first + i, v, isnull);
+		unsigned	longm = __ballot_sync(0xffffffffu, len > 8);
+
+		while (longm)
+		{
+			const int	src = __ffs(longm) - 1;
+			const int64_t f = __shfl_sync(0xffffffffu, first, src);
+			const uint32_t l = __shfl_sync(0xffffffffu, len, src);
+			const int64_t vv = __shfl_sync(0xffffffffu, v, src);
+
+			longm &= longm - 1;
+			for (uint32_t i = lane; i < l; i += 32)
+				aocs_store(P, D.rowbase + f + i, vv, false);
+		}
+		dbase += (uint32_t) cnt;
+		rowbase += total;
+		__syncwarp();
+	}
+	if (rowbase != D.rows && lane == 0)
+		atomicExch(P.status, CBGPU_ERR_INVALID);
+}
+
 __global__ void __launch_bounds__(AOCS_WARPS * 32)
 k_aocs_decode(AocsParams P)
 {
 	__shared__ uint32_t s_off[AOCS_WARPS][32];
+	__shared__ uint32_t s_rep[AOCS_WARPS][32];
 	const int	lane = threadIdx.x & 31;
 	const int	w = threadIdx.x >> 5;
 	const int	nwarps = gridDim.x * AOCS_WARPS;
@@ -148,6 +370,11 @@ k_aocs_decode(AocsParams P)
 		uint32_t	p0 = 16 + ((flags & 1u) ? nullsz : 0u);
 
 		p0 = (p0 + 7u) & ~7u;
+		if (version == 1 || version == 2)
+		{
+			aocs_decode_dense(P, D, blk, s_off[w], s_rep[w]);
+			continue;
+		}
 		if (version != 0 || ndatum != D.rows || (flags & ~1u) != 0 || (int64_t) p0 + sz > D.dlen + 8)
 		{
 			if (lane == 0)
@@ -286,14 +513,24 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 		memcpy(&w1, raw + pos + 4, 4);
 		kind = (int) ((w0 & 0x70000000u) >> 28);
 		has_first = (int) ((w0 & 0x08000000u) >> 27);
-		nrow = (int) ((w0 & 0x00FFFC00u) >> 10);
-		dlen = (int) (((w0 & 0x000003FFu) << 11) | ((w1 & 0xFFE00000u) >> 21));
-		clen = (int) (w1 & 0x001FFFFFu);
-		if ((w0 >> 31) != 0 || kind != 1 /* AoHeaderKind_SmallContent */ || clen != 0)
+		if (kind == 3)
+		{
+			/* AoHeaderKind_NonBulkDenseContent (cdbappendonlystorage_int.h:259-325): 30-bit row count */
+			nrow = (int) (w1 & 0x3FFFFFFFu);
+			dlen = (int) (w0 & 0x001FFFFFu);
+			clen = 0;
+		}
+		else
+		{
+			nrow = (int) ((w0 & 0x00FFFC00u) >> 10);
+			dlen = (int) (((w0 & 0x000003FFu) << 11) | ((w1 & 0xFFE00000u) >> 21));
+			clen = (int) (w1 & 0x001FFFFFu);
+		}
+		if ((w0 >> 31) != 0 || (kind != 1 /* AoHeaderKind_SmallContent */ && kind != 3) || clen != 0)
 		{
 			free(dir);
 			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED,
-						   "AOCS block at offset %s%lld is not an uncompressed SmallContent block (bulk-compressed, large-content and dense blocks are not decoded on the device)",
+						   "AOCS block at offset %s%lld is not an uncompressed SmallContent / NonBulkDenseContent block (bulk-compressed and large-content blocks are not decoded on the device)",
 						   "", pos);
 		}
 		hlen = 8 + (checksum ? 8 : 0) + (has_first ? 8 : 0);

@@ -10,6 +10,10 @@ Reader restated here, in numpy / plain Python, from:
                           utils/datumstream/datumstreamblock.c:153-354 (GetReadyOrig: header, MAXALIGNed NULL bitmap,
                           MAXALIGNed datum area), datumstreamblock.h:1442-1540 (AdvanceOrig: NULLs take no datum space;
                           fixed width: += datumlen; varlena: += VARSIZE_ANY, then skip zero pad bytes to typalign)
+  dense blocks (rle_type) include/utils/datumstreamblock.h:86-170 (Dense header, RLE extension), :617-730 (repeat count
+                          codec), :1725-1960 (AdvanceDense: a set compress bit = the datum repeats `count` more times; the
+                          NULL bitmap has one bit per non-repeated position), datumstreamblock.c:627-1010 (GetReadyDense);
+                          NonBulkDenseContent storage header include/cdb/cdbappendonlystorage_int.h:259-325
   varlena headers         include/postgres.h VARATT_IS_1B / VARSIZE_1B / VARSIZE_4B (little endian)
   numeric                 include/utils/numeric.h:103-189 (short / long headers, base-10000 digits, weight, dscale)
 Pinned by tests/test_aocs_format.py against column files written by the reference's own code (oracle/ref_aocs.c).
@@ -123,6 +127,9 @@ def ref_lib():
         L.ref_aocs_write_column.restype = C.c_int64
         L.ref_aocs_write_column.argtypes = [C.c_int] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                                             C.POINTER(C.c_int64)]
+        L.ref_aocs_write_column_ex.restype = C.c_int64
+        L.ref_aocs_write_column_ex.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                                               C.POINTER(C.c_int64)]
         L.ref_aocs_last_error.restype = C.c_char_p
         L.ref_numeric_inspect.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.c_void_p, C.c_int]
@@ -133,7 +140,7 @@ def ref_lib():
     return _REF
 
 
-def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768, dscale=0):
+def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768, dscale=0, rle=False):
     """Column file bytes as the reference's insert path writes them.  values: ints / floats (by-value types), scaled
     ints (numeric) or str (bpchar)."""
     L = ref_lib()
@@ -165,9 +172,9 @@ def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768
     out = (C.c_ubyte * cap)()
     nb = C.c_int64()
     vb = (C.c_ubyte * max(len(varbuf), 1)).from_buffer_copy(varbuf or b"\0")
-    r = L.ref_aocs_write_column(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize,
-                                vals.ctypes.data, C.addressof(vb), nl.ctypes.data if nl is not None else None, n,
-                                C.addressof(out), cap, C.byref(nb))
+    r = L.ref_aocs_write_column_ex(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize, 1 if rle else 0,
+                                   vals.ctypes.data, C.addressof(vb), nl.ctypes.data if nl is not None else None, n,
+                                   C.addressof(out), cap, C.byref(nb))
     if r < 0:
         raise RuntimeError("reference writer: " + L.ref_aocs_last_error().decode())
     return bytes(out[:r]), int(nb.value)
@@ -185,14 +192,17 @@ def walk_blocks(raw, checksum):
         w0 = int.from_bytes(raw[pos:pos + 4], "little")
         w1 = int.from_bytes(raw[pos + 4:pos + 8], "little")
         kind = (w0 & 0x70000000) >> 28
-        if kind != 1:
-            raise ValueError("block at %d: header kind %d is not SmallContent" % (pos, kind))
         has_first = (w0 & 0x08000000) >> 27
-        rows = (w0 & 0x00FFFC00) >> 10
-        dlen = ((w0 & 0x3FF) << 11) | ((w1 & 0xFFE00000) >> 21)
-        clen = w1 & 0x001FFFFF
-        if clen:
-            raise ValueError("compressed block")
+        if kind == 1:           # SmallContent
+            rows = (w0 & 0x00FFFC00) >> 10
+            dlen = ((w0 & 0x3FF) << 11) | ((w1 & 0xFFE00000) >> 21)
+            if w1 & 0x001FFFFF:
+                raise ValueError("compressed block")
+        elif kind == 3:         # NonBulkDenseContent: 30-bit row count
+            dlen = w0 & 0x001FFFFF
+            rows = w1 & 0x3FFFFFFF
+        else:
+            raise ValueError("block at %d: header kind %d is neither SmallContent nor NonBulkDenseContent" % (pos, kind))
         hlen = 8 + (8 if checksum else 0)
         first = -1
         if has_first:
@@ -203,50 +213,121 @@ def walk_blocks(raw, checksum):
     return out
 
 
+def _varint(buf, p):
+    """DatumStreamInt32Compress_Decode: top two bits of the first byte = length - 1, big endian"""
+    n = (buf[p] >> 6) + 1
+    v = buf[p] & 0x3F
+    for i in range(1, n):
+        v = (v << 8) | buf[p + i]
+    return v, n
+
+
+class _Datums:
+    """the datum area of one block, read front to back (AdvanceOrig / AdvanceDense pointer rules)"""
+
+    def __init__(self, blk, p, end, typname, dscale):
+        self.blk, self.p, self.end, self.typname, self.dscale = blk, p, end, typname, dscale
+        self.typid, self.attlen, _, align, _ = TYPEINFO[typname]
+        self.alignto = {"c": 1, "s": 2, "i": 4, "d": 8}[align]
+
+    def next(self):
+        blk, p = self.blk, self.p
+        if self.attlen > 0:
+            v = int.from_bytes(blk[p:p + self.attlen], "little", signed=self.typname != "bool")
+            self.p = p + self.attlen
+            return v
+        b0 = blk[p]
+        if b0 & 1:
+            size = b0 >> 1
+            body = blk[p + 1:p + size]
+        else:
+            size = (int.from_bytes(blk[p:p + 4], "little") >> 2) & 0x3FFFFFFF
+            body = blk[p + 4:p + size]
+        v = numeric_from_bytes(body, self.dscale) if self.typname == "numeric" else (body[0] if len(body) else 32)
+        p += size
+        if p < self.end and blk[p] == 0:
+            p = (p + self.alignto - 1) // self.alignto * self.alignto
+        self.p = p
+        return v
+
+
 def decode_column(raw, typname, checksum, dscale=0):
     """(values, nulls): numeric -> scaled int64, bpchar -> first byte, fixed width -> the value"""
-    typid, attlen, byval, align, storage = TYPEINFO[typname]
-    alignto = {"c": 1, "s": 2, "i": 4, "d": 8}[align]
     vals, nulls = [], []
     for off, dlen, rows, first in walk_blocks(raw, checksum):
         blk = raw[off:off + dlen]
-        version, flags, ndatum = (int.from_bytes(blk[0:2], "little", signed=True), int.from_bytes(blk[2:4], "little"),
-                                  int.from_bytes(blk[4:6], "little", signed=True))
-        nullsz = int.from_bytes(blk[8:12], "little")
-        sz = int.from_bytes(blk[12:16], "little")
-        if version != 0 or ndatum != rows:
-            raise ValueError("not an Original datum stream block, or row counts disagree")
+        version, flags = int.from_bytes(blk[0:2], "little", signed=True), int.from_bytes(blk[2:4], "little")
+        if version == 0:
+            # DatumStreamBlock_Orig
+            ndatum = int.from_bytes(blk[4:6], "little", signed=True)
+            nullsz = int.from_bytes(blk[8:12], "little")
+            sz = int.from_bytes(blk[12:16], "little")
+            if ndatum != rows:
+                raise ValueError("row counts disagree")
+            p = 16
+            bitmap = None
+            if flags & 1:
+                bitmap = blk[p:p + nullsz]
+                p += nullsz
+            p = (p + 7) // 8 * 8
+            d = _Datums(blk, p, p + sz, typname, dscale)
+            for r in range(rows):
+                if bitmap is not None and (bitmap[r >> 3] >> (r & 7)) & 1:
+                    vals.append(0)
+                    nulls.append(1)
+                else:
+                    vals.append(d.next())
+                    nulls.append(0)
+            if d.p > d.end + d.alignto:
+                raise ValueError("datum area overrun")
+            continue
+        if version not in (1, 2):
+            raise ValueError("unknown datum stream block version %d" % version)
+        # DatumStreamBlock_Dense (+ Rle_Extension)
+        logical = int.from_bytes(blk[4:8], "little", signed=True)
+        psize = int.from_bytes(blk[12:16], "little", signed=True)
+        if logical != rows:
+            raise ValueError("row counts disagree")
+        if flags & 4:
+            raise ValueError("delta range compression")
         p = 16
+        rle = bool(flags & 2)
+        if rle:
+            nn_count, c_count, rc_count, rc_size = [int.from_bytes(blk[p + 4 * i:p + 4 * i + 4], "little") for i in range(4)]
+            p += 16
         bitmap = None
         if flags & 1:
-            bitmap = blk[p:p + nullsz]
-            p += nullsz
+            nb = nn_count if rle else logical
+            bitmap = blk[p:p + (nb + 7) // 8]
+            p += (nb + 7) // 8
+        if rle:
+            cbitmap = blk[p:p + (c_count + 7) // 8]
+            p += (c_count + 7) // 8
+            rc = blk[p:p + rc_size]
+            p += rc_size
         p = (p + 7) // 8 * 8
-        end = p + sz
-        for r in range(rows):
-            if bitmap is not None and (bitmap[r >> 3] >> (r & 7)) & 1:
-                vals.append(0)
-                nulls.append(1)
-                continue
-            nulls.append(0)
-            if attlen > 0:
-                v = int.from_bytes(blk[p:p + attlen], "little", signed=typname != "bool")
-                p += attlen
-            else:
-                b0 = blk[p]
-                if b0 & 1:
-                    size = b0 >> 1
-                    body = blk[p + 1:p + size]
-                else:
-                    size = (int.from_bytes(blk[p:p + 4], "little") >> 2) & 0x3FFFFFFF
-                    body = blk[p + 4:p + size]
-                v = numeric_from_bytes(body, dscale) if typname == "numeric" else (body[0] if len(body) else 32)
-                p += size
-                if p < end and blk[p] == 0:
-                    p = (p + alignto - 1) // alignto * alignto
-            vals.append(v)
-        if p > end + alignto:
-            raise ValueError("datum area overrun")
+        d = _Datums(blk, p, p + psize, typname, dscale)
+        produced = pos = di = rcp = 0
+        while produced < logical:
+            if bitmap is not None:
+                isnull = (bitmap[pos >> 3] >> (pos & 7)) & 1
+                pos += 1
+                if isnull:
+                    vals.append(0)
+                    nulls.append(1)
+                    produced += 1
+                    continue
+            rep = 0
+            if rle and (cbitmap[di >> 3] >> (di & 7)) & 1:
+                rep, n = _varint(rc, rcp)
+                rcp += n
+            v = d.next()
+            di += 1
+            vals.extend([v] * (1 + rep))
+            nulls.extend([0] * (1 + rep))
+            produced += 1 + rep
+        if produced != logical:
+            raise ValueError("repeat counts overrun the block")
     if typname == "float8":
         return np.array(vals, dtype=np.int64).view(np.float64), np.array(nulls, dtype=np.uint8)
     return np.array(vals, dtype=np.int64), np.array(nulls, dtype=np.uint8)

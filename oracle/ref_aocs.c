@@ -198,6 +198,10 @@ ref_numeric_inspect(const unsigned char *varlena4, int *sign, int *dscale, int *
 	return NUMERIC_HEADER_IS_SHORT(num) ? 1 : 0;
 }
 
+int64		ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle,
+									 const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
+									 unsigned char *out, int64 outcap, int64 *nblocks_out);
+
 /*
  * Write one column.  `values`: by-value datums (attlen 1/2/4/8), or for attlen -1 offsets into
  * `varbuf` of 4-byte-header varlenas.  Returns bytes written into out (the column's segment-file
@@ -207,6 +211,19 @@ int64
 ref_aocs_write_column(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize,
 					  const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
 					  unsigned char *out, int64 outcap, int64 *nblocks_out)
+{
+	return ref_aocs_write_column_ex(typid, attlen, byval, align, storage, checksum, blocksize, 0, values, varbuf, nulls, n, out, outcap,
+									nblocks_out);
+}
+
+/* rle != 0: compresstype = rle_type, compresslevel 1 (init_datumstream_info, datumstream.c:396-419):
+ * DatumStreamVersion_Dense_Enhanced blocks with RLE done by the datum stream layer, no bulk compression;
+ * blocks of more than 16383 rows get the NonBulkDenseContent storage header (datumstreamwrite_block_dense,
+ * datumstream.c:925-978).  Delta range encoding (int4 / int8 / date / time types only) is left off. */
+int64
+ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle,
+						 const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
+						 unsigned char *out, int64 outcap, int64 *nblocks_out)
 {
 	DatumStreamBlockWrite dsw;
 	DatumStreamTypeInfo ti;
@@ -231,10 +248,16 @@ ref_aocs_write_column(int typid, int attlen, int byval, int align, int storage, 
 		free(blockbuf);
 		return -1;
 	}
-	/* create_datumstreamwrite (datumstream.c:588-632), DatumStreamVersion_Original */
-	DatumStreamBlockWrite_Init(&dsw, &ti, DatumStreamVersion_Original, false, false,
-							   AOSmallContentHeader_MaxRowCount, AOSmallContentHeader_MaxRowCount, blocksize - hdrlen,
-							   NULL, NULL, NULL, NULL, &node);
+	/* create_datumstreamwrite (datumstream.c:588-632) */
+	if (rle)
+		DatumStreamBlockWrite_Init(&dsw, &ti, DatumStreamVersion_Dense_Enhanced, true, false,
+								   AOSmallContentHeader_MaxRowCount, AONonBulkDenseContentHeader_MaxLargeRowCount,
+								   blocksize - (AoHeader_LongSize + (checksum ? 8 : 0) + 8),
+								   NULL, NULL, NULL, NULL, &node);
+	else
+		DatumStreamBlockWrite_Init(&dsw, &ti, DatumStreamVersion_Original, false, false,
+								   AOSmallContentHeader_MaxRowCount, AOSmallContentHeader_MaxRowCount, blocksize - hdrlen,
+								   NULL, NULL, NULL, NULL, &node);
 
 #define FLUSH() \
 	do { \
@@ -246,8 +269,12 @@ ref_aocs_write_column(int typid, int attlen, int byval, int align, int storage, 
 			memset(blockbuf, 0, (size_t) blocksize + 64); \
 			contentLen = DatumStreamBlockWrite_Block(&dsw, blockbuf + hdrlen, &node); \
 			rounded = AOStorage_RoundUp((int32) contentLen, version); \
-			AppendOnlyStorageFormat_MakeSmallContentHeader(blockbuf, checksum != 0, true, version, first_row, 1 /* AOCSBK_BLOCK */, \
-														   rowCount, (int32) contentLen, 0); \
+			if (rowCount <= AOSmallContentHeader_MaxRowCount) \
+				AppendOnlyStorageFormat_MakeSmallContentHeader(blockbuf, checksum != 0, true, version, first_row, 1 /* AOCSBK_BLOCK */, \
+															   rowCount, (int32) contentLen, 0); \
+			else \
+				AppendOnlyStorageFormat_MakeNonBulkDenseContentHeader(blockbuf, checksum != 0, true, version, first_row, 1, \
+																	  rowCount, (int32) contentLen); \
 			if (pos + hdrlen + rounded > outcap) \
 			{ \
 				snprintf(ref_errbuf, sizeof(ref_errbuf), "output buffer too small"); \

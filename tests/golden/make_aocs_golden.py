@@ -21,8 +21,8 @@ def main():
     out = {}
     cases = []
 
-    def add(name, typname, values, nulls, checksum, blocksize, dscale=0):
-        raw, nblocks = A.ref_write_column(typname, values, nulls, checksum, blocksize, dscale)
+    def add(name, typname, values, nulls, checksum, blocksize, dscale=0, rle=False):
+        raw, nblocks = A.ref_write_column(typname, values, nulls, checksum, blocksize, dscale, rle=rle)
         out[name + "__raw"] = np.frombuffer(raw, dtype=np.uint8)
         if typname == "bpchar":
             out[name + "__values"] = np.array([ord(v[0]) if v else 32 for v in values], dtype=np.int64)
@@ -48,6 +48,19 @@ def main():
     add("numeric_disc_nulls_8k", "numeric", rng.integers(0, 11, n), nul, False, 8192, dscale=2)
     add("numeric_scale6", "numeric", rng.integers(-10**12, 10**12, 5003), None, True, 32768, dscale=6)
     add("bpchar1_flags", "bpchar", [("A", "N", "R", "F", "O")[i] for i in rng.integers(0, 5, n)], nul, True, 32768)
+    # compresstype = rle_type (Dense blocks with repeat counts); runs, NULLs inside and between runs, one run longer
+    # than a SmallContent header can count (-> NonBulkDenseContent header), values that do not repeat at all
+    runs = np.repeat(rng.integers(0, 5, 300), rng.integers(1, 120, 300))
+    nr = len(runs)
+    nulr = (rng.random(nr) < 0.04).astype(np.uint8)
+    add("rle_bpchar1_runs_nulls", "bpchar", [("A", "N", "R", "F", "O")[i] for i in runs], nulr, True, 32768, rle=True)
+    add("rle_numeric_long_run", "numeric", np.concatenate([np.full(40000, 12345), rng.integers(100, 10**7, 3000), np.full(20000, -5),
+                                                              np.repeat(rng.integers(0, 11, 500), rng.integers(1, 9, 500))]),
+        None, True, 32768, dscale=2, rle=True)
+    add("rle_float8_runs_8k", "float8", np.repeat(rng.normal(0, 1e3, 700), rng.integers(1, 40, 700)), None, False, 8192, rle=True)
+    add("rle_bool_norepeat", "bool", rng.integers(0, 2, 3000) * 0 + np.arange(3000) % 2, None, True, 8192, rle=True)
+    mixed = np.where(rng.random(9000) < 0.5, np.repeat(rng.normal(0, 10, 900), 10), rng.normal(0, 1e6, 9000))
+    add("rle_float8_many_blocks_nulls", "float8", mixed, (rng.random(9000) < 0.05).astype(np.uint8), True, 8192, rle=True)
     add("int4_tiny", "int4", [7], None, True, 32768)
     add("int4_allnull", "int4", [0] * 100, [1] * 100, True, 32768)
     out["cases"] = np.array(cases)
