@@ -33,9 +33,11 @@
  *       position its first output row, short runs are written by their lane, long runs by the warp.
  *
  * Supported: uncompressed SmallContent / NonBulkDenseContent storage blocks holding Original or Dense
- * (RLE) datum stream blocks.  Bulk-compressed and large-content blocks, and Dense blocks with delta
- * range encoding (rle_type on int4 / int8 / date / time columns), are refused with
- * CBGPU_ERR_UNSUPPORTED, never guessed at.
+ * (RLE and / or delta range) datum stream blocks - everything `compresstype=rle_type,
+ * compresslevel=1` writes.  Delta range encoding (int4 / int8 / date columns; AdvanceDenseDelta,
+ * datumstreamblock.h:1625-1723: a set delta bit = "previous value +/- a 29-bit delta", codec :779-900)
+ * is a running sum: per trip an affine-map scan across the warp.  Bulk-compressed (zlib / zstd) and
+ * large-content blocks are refused with CBGPU_ERR_UNSUPPORTED, never guessed at.
  */
 #include "common.cuh"
 
@@ -182,7 +184,7 @@ aocs_store(const AocsParams &P, int64_t orow, int64_t v, bool isnull)
 
 /* one Dense (optionally RLE) datum stream block, by one warp */
 __device__ __forceinline__ void
-aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uint32_t *s_off, uint32_t *s_rep)
+aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uint32_t *s_off, uint32_t *s_rep, int32_t *s_del)
 {
 	const int	lane = threadIdx.x & 31;
 	const uint32_t flags = (uint32_t) blk[2] | ((uint32_t) blk[3] << 8);
@@ -190,19 +192,23 @@ aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uin
 	const int32_t physical = (int32_t) aocs_le32(blk + 8);
 	const uint32_t psize = aocs_le32(blk + 12);
 	const bool	rle = (flags & 2u) != 0;
+	const bool	delta = (flags & 4u) != 0;
 	uint32_t	p = 16;
 	uint32_t	nn_count = 0,
 				c_count = 0,
-				rc_size = 0;
+				rc_size = 0,
+				d_count = 0,
+				d_size = 0;
 	const uint8_t *bitmap = NULL,
 			   *cbitmap = NULL,
-			   *rc = NULL;
+			   *rc = NULL,
+			   *dbitmap = NULL,
+			   *dl = NULL;
 
-	if (logical != D.rows || (flags & 4u) || (flags & ~7u))
+	if (logical != D.rows || (flags & ~7u) || (delta && P.attlen != 4 && P.attlen != 8))
 	{
-		/* DSB_HAS_DELTA_COMPRESSION: not decoded here */
 		if (lane == 0)
-			atomicExch(P.status, (flags & 4u) ? CBGPU_ERR_UNSUPPORTED : CBGPU_ERR_INVALID);
+			atomicExch(P.status, CBGPU_ERR_INVALID);
 		return;
 	}
 	if (rle)
@@ -211,6 +217,13 @@ aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uin
 		c_count = aocs_le32(blk + p + 4);
 		rc_size = aocs_le32(blk + p + 12);
 		p += 16;
+	}
+	if (delta)
+	{
+		/* DatumStreamBlock_Delta_Extension (datumstreamblock.h:172-195) */
+		d_count = aocs_le32(blk + p);
+		d_size = aocs_le32(blk + p + 8);
+		p += 12;
 	}
 	if (flags & 1u)
 	{
@@ -226,6 +239,13 @@ aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uin
 		rc = blk + p;
 		p += rc_size;
 	}
+	if (delta)
+	{
+		dbitmap = blk + p;
+		p += (d_count + 7u) >> 3;
+		dl = blk + p;
+		p += d_size;
+	}
 	p = (p + 7u) & ~7u;
 	if ((int64_t) p + psize > D.dlen + 8)
 	{
@@ -235,11 +255,15 @@ aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uin
 	}
 	const uint8_t *data = blk + p;
 	/* positions = the items the NULL bitmap counts: NULLs and non-repeated datums */
-	const uint32_t npos = bitmap ? (rle ? nn_count : (uint32_t) logical) : (uint32_t) physical;
-	uint32_t	dbase = 0,		/* physical datums before this trip */
+	/* without a NULL bitmap every position is a value: compress / delta bitmaps count them when present */
+	const uint32_t npos = bitmap ? (rle ? nn_count : (uint32_t) logical) : (rle ? c_count : (delta ? d_count : (uint32_t) physical));
+	uint32_t	dbase = 0,		/* non-NULL positions before this trip */
+				pbase = 0,		/* physical datums before this trip */
 				cur = 0,		/* byte offset of the next varlena datum */
-				rcp = 0;		/* byte offset of the next repeat count */
+				rcp = 0,		/* byte offset of the next repeat count */
+				dlp = 0;		/* byte offset of the next delta */
 	int64_t		rowbase = 0;	/* logical rows before this trip */
+	unsigned long long running = 0;	/* the value deltas apply to (AdvanceDenseDelta's delta_datum_p) */
 
 	for (uint32_t p0 = 0; p0 < npos; p0 += 32)
 	{
@@ -252,6 +276,9 @@ aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uin
 		const uint32_t di = dbase + (uint32_t) k;
 		const bool	cb = inr && !isnull && rle && ((cbitmap[di >> 3] >> (di & 7)) & 1);
 		const unsigned cm = __ballot_sync(0xffffffffu, cb);
+		const bool	isdelta = inr && !isnull && delta && ((dbitmap[di >> 3] >> (di & 7)) & 1);
+		const unsigned dm = __ballot_sync(0xffffffffu, isdelta);
+		const unsigned pm = nn & ~dm;		/* positions holding a physical datum */
 
 		if (lane == 0)
 		{
@@ -271,6 +298,24 @@ aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uin
 				r += (uint32_t) len;
 			}
 			rcp = r;
+			/* ... its deltas (DatumStreamInt32CompressReserved3_Decode: 2 length bits, "positive" bit, 29 bits) ... */
+			{
+				uint32_t	q = dlp;
+				const int	nd = __popc(dm);
+
+				for (int i = 0; i < nd; i++)
+				{
+					const uint32_t b0 = dl[q];
+					const int	len = (int) (b0 >> 6) + 1;
+					uint32_t	v = b0 & 0x1Fu;
+
+					for (int j = 1; j < len; j++)
+						v = (v << 8) | dl[q + j];
+					s_del[i] = (b0 & 0x20u) ? (int32_t) v : -(int32_t) v;
+					q += (uint32_t) len;
+				}
+				dlp = q;
+			}
 			/* ... and, for varlena columns, where its datums start */
 			if (P.attlen < 0)
 			{
@@ -296,6 +341,7 @@ aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uin
 			}
 		}
 		rcp = __shfl_sync(0xffffffffu, rcp, 0);
+		dlp = __shfl_sync(0xffffffffu, dlp, 0);
 		cur = __shfl_sync(0xffffffffu, cur, 0);
 		__syncwarp();
 		/* run length of every position, its first output row by a warp scan */
@@ -314,8 +360,39 @@ aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uin
 		const int64_t first = rowbase + (int64_t) (x - len);
 		int64_t		v = 0;
 
-		if (inr && !isnull)
-			v = aocs_value(P, P.attlen > 0 ? data + (size_t) di * P.attlen : data + s_off[k]);
+		if (inr && !isnull && !isdelta)
+		{
+			const uint32_t ph = pbase + (uint32_t) __popc(pm & ((1u << lane) - 1));
+
+			v = aocs_value(P, P.attlen > 0 ? data + (size_t) ph * P.attlen : data + s_off[k]);
+		}
+		if (delta)
+		{
+			/* value = previous value + delta: an affine map per position (physical datum: x -> v; delta:
+			 * x -> x + d; NULL / idle lane: x -> x), composed across the warp by a scan, applied to the
+			 * value the previous trip ended on.  4-byte types wrap like the reference's uint32 arithmetic. */
+			unsigned long long a = (inr && !isnull && !isdelta) ? 0ull : 1ull;
+			unsigned long long b = (inr && !isnull) ? (isdelta ? (unsigned long long) (long long) s_del[__popc(dm & ((1u << lane) - 1))]
+													   : (unsigned long long) v) : 0ull;
+
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const unsigned long long a1 = __shfl_up_sync(0xffffffffu, a, d);
+				const unsigned long long b1 = __shfl_up_sync(0xffffffffu, b, d);
+
+				if (lane >= d)
+				{
+					b = a * b1 + b;
+					a = a * a1;
+				}
+			}
+			const unsigned long long val = a * running + b;
+
+			running = __shfl_sync(0xffffffffu, val, 31);
+			if (inr && !isnull)
+				v = P.attlen == 4 ? (int64_t) (int32_t) (uint32_t) val : (int64_t) val;
+		}
 		if (__any_sync(0xffffffffu, first + (int64_t) len > D.rows))
 		{
 			if (lane == 0)
@@ -340,6 +417,7 @@ aocs_decode_dense(const AocsParams &P, const AocsDir &D, const uint8_t *blk, uin
 				aocs_store(P, D.rowbase + f + i, vv, false);
 		}
 		dbase += (uint32_t) cnt;
+		pbase += (uint32_t) __popc(pm);
 		rowbase += total;
 		__syncwarp();
 	}
@@ -352,6 +430,7 @@ k_aocs_decode(AocsParams P)
 {
 	__shared__ uint32_t s_off[AOCS_WARPS][32];
 	__shared__ uint32_t s_rep[AOCS_WARPS][32];
+	__shared__ int32_t s_del[AOCS_WARPS][32];
 	const int	lane = threadIdx.x & 31;
 	const int	w = threadIdx.x >> 5;
 	const int	nwarps = gridDim.x * AOCS_WARPS;
@@ -372,7 +451,7 @@ k_aocs_decode(AocsParams P)
 		p0 = (p0 + 7u) & ~7u;
 		if (version == 1 || version == 2)
 		{
-			aocs_decode_dense(P, D, blk, s_off[w], s_rep[w]);
+			aocs_decode_dense(P, D, blk, s_off[w], s_rep[w], s_del[w]);
 			continue;
 		}
 		if (version != 0 || ndatum != D.rows || (flags & ~1u) != 0 || (int64_t) p0 + sz > D.dlen + 8)

@@ -141,6 +141,8 @@ def ref_lib():
 
 
 def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768, dscale=0, rle=False):
+    # rle: False / 0 plain, True / 1 rle_type, 2 rle_type with delta range encoding (what the reference picks for
+    # int4 / int8 / date columns under rle_type)
     """Column file bytes as the reference's insert path writes them.  values: ints / floats (by-value types), scaled
     ints (numeric) or str (bpchar)."""
     L = ref_lib()
@@ -172,7 +174,7 @@ def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768
     out = (C.c_ubyte * cap)()
     nb = C.c_int64()
     vb = (C.c_ubyte * max(len(varbuf), 1)).from_buffer_copy(varbuf or b"\0")
-    r = L.ref_aocs_write_column_ex(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize, 1 if rle else 0,
+    r = L.ref_aocs_write_column_ex(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize, int(rle),
                                    vals.ctypes.data, C.addressof(vb), nl.ctypes.data if nl is not None else None, n,
                                    C.addressof(out), cap, C.byref(nb))
     if r < 0:
@@ -288,13 +290,15 @@ def decode_column(raw, typname, checksum, dscale=0):
         psize = int.from_bytes(blk[12:16], "little", signed=True)
         if logical != rows:
             raise ValueError("row counts disagree")
-        if flags & 4:
-            raise ValueError("delta range compression")
         p = 16
         rle = bool(flags & 2)
+        delta = bool(flags & 4)
         if rle:
             nn_count, c_count, rc_count, rc_size = [int.from_bytes(blk[p + 4 * i:p + 4 * i + 4], "little") for i in range(4)]
             p += 16
+        if delta:
+            d_count, d_items, d_size = [int.from_bytes(blk[p + 4 * i:p + 4 * i + 4], "little") for i in range(3)]
+            p += 12
         bitmap = None
         if flags & 1:
             nb = nn_count if rle else logical
@@ -305,9 +309,16 @@ def decode_column(raw, typname, checksum, dscale=0):
             p += (c_count + 7) // 8
             rc = blk[p:p + rc_size]
             p += rc_size
+        if delta:
+            dbitmap = blk[p:p + (d_count + 7) // 8]
+            p += (d_count + 7) // 8
+            deltas = blk[p:p + d_size]
+            p += d_size
         p = (p + 7) // 8 * 8
         d = _Datums(blk, p, p + psize, typname, dscale)
-        produced = pos = di = rcp = 0
+        produced = pos = di = rcp = dp = 0
+        running = 0
+        width = TYPEINFO[typname][1]
         while produced < logical:
             if bitmap is not None:
                 isnull = (bitmap[pos >> 3] >> (pos & 7)) & 1
@@ -321,7 +332,20 @@ def decode_column(raw, typname, checksum, dscale=0):
             if rle and (cbitmap[di >> 3] >> (di & 7)) & 1:
                 rep, n = _varint(rc, rcp)
                 rcp += n
-            v = d.next()
+            if delta and (dbitmap[di >> 3] >> (di & 7)) & 1:
+                # DatumStreamInt32CompressReserved3_Decode: 2 length bits, 1 "positive" bit, 29 value bits, big endian
+                nb = (deltas[dp] >> 6) + 1
+                mag = deltas[dp] & 0x1F
+                for i in range(1, nb):
+                    mag = (mag << 8) | deltas[dp + i]
+                running = running + mag if deltas[dp] & 0x20 else running - mag
+                dp += nb
+                bits = 8 * width
+                running &= (1 << bits) - 1
+                v = running - (1 << bits) if running >> (bits - 1) else running
+            else:
+                v = d.next()
+                running = v & ((1 << (8 * width)) - 1) if width > 0 else 0
             di += 1
             vals.extend([v] * (1 + rep))
             nulls.extend([0] * (1 + rep))

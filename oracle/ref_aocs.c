@@ -219,7 +219,8 @@ ref_aocs_write_column(int typid, int attlen, int byval, int align, int storage, 
 /* rle != 0: compresstype = rle_type, compresslevel 1 (init_datumstream_info, datumstream.c:396-419):
  * DatumStreamVersion_Dense_Enhanced blocks with RLE done by the datum stream layer, no bulk compression;
  * blocks of more than 16383 rows get the NonBulkDenseContent storage header (datumstreamwrite_block_dense,
- * datumstream.c:925-978).  Delta range encoding (int4 / int8 / date / time types only) is left off. */
+ * datumstream.c:925-978).  rle == 2 adds delta range encoding, which init_datumstream_info turns on for
+ * int4 / int8 / date / time / timestamp columns (is_deltarange_compression_supported, datumstream.c:330-360). */
 int64
 ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle,
 						 const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
@@ -250,7 +251,7 @@ ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storag
 	}
 	/* create_datumstreamwrite (datumstream.c:588-632) */
 	if (rle)
-		DatumStreamBlockWrite_Init(&dsw, &ti, DatumStreamVersion_Dense_Enhanced, true, false,
+		DatumStreamBlockWrite_Init(&dsw, &ti, DatumStreamVersion_Dense_Enhanced, true, rle >= 2,
 								   AOSmallContentHeader_MaxRowCount, AONonBulkDenseContentHeader_MaxLargeRowCount,
 								   blocksize - (AoHeader_LongSize + (checksum ? 8 : 0) + 8),
 								   NULL, NULL, NULL, NULL, &node);

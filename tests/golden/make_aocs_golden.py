@@ -61,6 +61,16 @@ def main():
     add("rle_bool_norepeat", "bool", rng.integers(0, 2, 3000) * 0 + np.arange(3000) % 2, None, True, 8192, rle=True)
     mixed = np.where(rng.random(9000) < 0.5, np.repeat(rng.normal(0, 10, 900), 10), rng.normal(0, 1e6, 9000))
     add("rle_float8_many_blocks_nulls", "float8", mixed, (rng.random(9000) < 0.05).astype(np.uint8), True, 8192, rle=True)
+    # rle_type on integer / date columns also turns delta range encoding on (init_datumstream_info): sorted dates with
+    # repeats and NULLs, growing keys with large jumps in both directions, random int4 (deltas too big to encode)
+    nd = 30000
+    dates = np.cumsum(rng.integers(0, 3, nd)) - 500
+    add("delta_date_sorted_nulls", "date", dates, (rng.random(nd) < 0.03).astype(np.uint8), True, 32768, rle=2)
+    keys = np.cumsum(rng.integers(-40, 1000, nd)).astype(np.int64) * 7 + 2**40
+    keys[100], keys[101], keys[5000] = -2**62, 2**62, 0
+    add("delta_int8_keys_8k", "int8", keys, None, False, 8192, rle=2)
+    add("delta_int4_random", "int4", rng.integers(-2**31, 2**31 - 1, 5000), None, True, 8192, rle=2)
+    add("delta_int4_wrap", "int4", np.array([2**31 - 1, -2**31, -2**31 + 5, 2**31 - 3, 0, 1, 1, 1, 2, 2**29, 2**29 + 2**29 - 1]), None, True, 8192, rle=2)
     add("int4_tiny", "int4", [7], None, True, 32768)
     add("int4_allnull", "int4", [0] * 100, [1] * 100, True, 32768)
     out["cases"] = np.array(cases)
