@@ -660,6 +660,8 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 	CB_CUDA(ctx, cudaMallocAsync(&d_dir, sizeof(AocsDir) * (size_t) ndir, ctx->stream));
 	CB_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, (size_t) nbytes, cudaMemcpyHostToDevice, ctx->stream));
 	CB_CUDA(ctx, cudaMemcpyAsync(d_dir, dir, sizeof(AocsDir) * (size_t) ndir, cudaMemcpyHostToDevice, ctx->stream));
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, "aocs:h2d");
 	memset(&P, 0, sizeof(P));
 	P.raw = d_raw;
 	P.dir = d_dir;

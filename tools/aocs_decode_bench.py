@@ -1,0 +1,43 @@
+#!/usr/bin/env python3
+"""Throughput of the on-device AOCS decoder (k_aocs_decode): tiles the reference-written golden column files
+(tests/golden/aocs_columns.npz) to a few hundred MB each and reports the kernel's own time (launch trace), file bytes/s
+and rows/s per column kind.  Profiling aid; the H2D copy of the file (pageable host memory here) is not in the number."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from cloudberry_b200 import capi  # noqa: E402
+from test_aocs_format import CASES  # noqa: E402
+from test_gpu_aocs import DECODE  # noqa: E402
+
+
+def main():
+    ctx = capi.Context(0)
+    target = 256 << 20
+    for name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls in CASES:
+        if len(values) < 1000:
+            continue
+        k = max(1, target // len(raw))
+        big = raw * k
+        n = len(values) * k
+        ctype, attlen, varkind, align = DECODE[typname]
+        rel = capi.DeviceRelation(ctx, n, [ctype], dscales=[dscale])
+        rel.load_aocs_column(0, big, checksum, attlen, varkind, align)      # warm-up
+        ctx.trace_begin()
+        got = rel.load_aocs_column(0, big, checksum, attlen, varkind, align)
+        tr = ctx.trace_end()
+        ms = sum(m for nme, m in tr if nme == "k_aocs_decode")
+        assert got == n
+        print("%-30s %8.1f MB file  %10d rows  kernel %7.3f ms  %7.1f GB/s of file  %7.2f G rows/s  (%d blocks)" %
+              (name, len(big) / 1e6, n, ms, len(big) / ms / 1e6, n / ms / 1e6, nblocks * k))
+        rel.free()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
