@@ -165,8 +165,10 @@ cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t
 	{
 		/* ~16 filter bits per build row, at least one cache line */
 		int64_t		words = 32;
+		const char *env = getenv("CBGPU_BLOOM_DIV");	/* rows per 32-bit filter word (tuning aid), default 2 */
+		int			div = env && atoi(env) > 0 ? atoi(env) : 2;
 
-		while (words < inner->nrows / 2)
+		while (words < inner->nrows / div)
 			words <<= 1;
 		CB_CUDA(ctx, cudaMallocAsync(&ht->d.bloom, (size_t) words * sizeof(uint32_t), ctx->stream));
 		CB_CUDA(ctx, cudaMemsetAsync(ht->d.bloom, 0, (size_t) words * sizeof(uint32_t), ctx->stream));
