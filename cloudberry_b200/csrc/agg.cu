@@ -177,7 +177,9 @@ cbgpu_agg_ngroups(cbgpu_aggtable *t, int64_t *ngroups)
 			CB_LAUNCHED(ctx, "k_agg_count");
 		}
 		CB_CUDA(ctx, cudaMemcpyAsync(h, t->d.ngroups, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+		CB_CUDA(ctx, CB_STATUS_RIDE(ctx));
 		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		CB_STATUS_FETCHED(ctx);
 		if (h[1])
 			return cb_fail(ctx, CBGPU_ERR_NOMEM, "aggregate hash table overflow (%s capacity %lld slots)", "", t->capacity);
 		t->ngroups = h[0];

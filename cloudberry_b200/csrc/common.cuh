@@ -43,6 +43,9 @@ struct cbgpu_ctx
 	size_t		flush_bytes;
 	int		   *d_status;		/* device status word: nonzero = CBGPU error code raised by a kernel */
 	int		   *h_status;		/* pinned mirror                                                      */
+	int64_t		status_seen_at;	/* ctx->launches when h_status was last fetched (-1: never): every
+								 * synchronising read-back fetches the status word too, so the check
+								 * after it costs no second round trip                                 */
 };
 
 struct cbgpu_rel
@@ -157,6 +160,9 @@ void		cb_trace_mark(cbgpu_ctx *ctx, const char *name);
 	} while (0)
 
 int			cb_check_status(cbgpu_ctx *ctx, const char *what);	/* sync + read device status word */
+/* enqueue the status word's copy next to another device-to-host copy; call cb_status_fetched after the sync */
+#define CB_STATUS_RIDE(ctx) cudaMemcpyAsync((ctx)->h_status, (ctx)->d_status, sizeof(int), cudaMemcpyDeviceToHost, (ctx)->stream)
+#define CB_STATUS_FETCHED(ctx) ((ctx)->status_seen_at = (ctx)->launches)
 
 static inline int
 cb_type_w(int t)

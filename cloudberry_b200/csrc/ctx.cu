@@ -92,13 +92,19 @@ cbgpu_sync(cbgpu_ctx *ctx)
 int
 cb_check_status(cbgpu_ctx *ctx, const char *what)
 {
-	CB_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (ctx->status_seen_at != ctx->launches)
+	{
+		/* no read-back has fetched the word since the last launch: do it now */
+		CB_CUDA(ctx, CB_STATUS_RIDE(ctx));
+		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		CB_STATUS_FETCHED(ctx);
+	}
 	if (*ctx->h_status != 0)
 	{
 		int			code = *ctx->h_status;
 
 		CB_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+		*ctx->h_status = 0;
 		snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what,
 				 code == CBGPU_ERR_OVERFLOW ? "value out of range (integer/numeric overflow)" :
 				 code == CBGPU_ERR_NOMEM ? "device table or output buffer full" : "device-side error");
@@ -543,7 +549,9 @@ extern "C" int
 cbgpu_dev_read(cbgpu_ctx *ctx, const void *dev, size_t bytes, void *host)
 {
 	CB_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, CB_STATUS_RIDE(ctx));
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	CB_STATUS_FETCHED(ctx);
 	return CBGPU_OK;
 }
 

@@ -694,8 +694,8 @@ stream_materialize(CbEState *es, CbPlanState *ps, CbStream *s, Owned *own, cbgpu
 		int64_t		before = cbgpu_kernel_launches(es->es_ctx);
 
 		GPU(es, cbgpu_pipeline_run(es->es_ctx, p));
+		GPU(es, cbgpu_dev_read(es->es_ctx, counter, sizeof(int64_t), &count));	/* the status word rides along */
 		GPU(es, cbgpu_check_status(es->es_ctx));
-		GPU(es, cbgpu_dev_read(es->es_ctx, counter, sizeof(int64_t), &count));
 		ps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
 		ps->instrument.rows_in += s->rows_in;
 		if (cbgpu_last_kernel_ms(es->es_ctx) > 0)
@@ -1253,9 +1253,15 @@ agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream
 		pl->sink.agg = t;
 		rc = cbgpu_pipeline_run(es->es_ctx, pl);
 		if (rc == CBGPU_OK)
+		{
+			/* the group count's read-back fetches the status word too: one round trip for both.  A full
+			 * table (NOMEM from ngroups) must not hide an overflow raised by the same kernel. */
+			int			rc2 = cbgpu_agg_ngroups(t, &ng);
+
 			rc = cbgpu_check_status(es->es_ctx);
-		if (rc == CBGPU_OK)
-			rc = cbgpu_agg_ngroups(t, &ng);
+			if (rc == CBGPU_OK)
+				rc = rc2;
+		}
 		ps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
 		ps->instrument.rows_in += s->rows_in;
 		if (cbgpu_last_kernel_ms(es->es_ctx) > 0)
