@@ -463,6 +463,90 @@ cbgpu_rel_read_column(cbgpu_rel *rel, int32_t col, int64_t lo, int64_t hi, void 
 	return CBGPU_OK;
 }
 
+/* a few rows of every column in ONE round trip: result sets above an aggregate or a top-N are a handful of
+ * rows, and one synchronising copy per row and column is what their delivery would otherwise cost */
+struct ReadRows
+{
+	const void *data[CB_MAX_COLS_REL];
+	const uint8_t *nulls[CB_MAX_COLS_REL];
+	int32_t		types[CB_MAX_COLS_REL];
+	int32_t		ncols;
+	const uint32_t *idx;
+	int64_t		n;
+	long long  *out;
+	uint8_t    *outnull;
+};
+
+__global__ void
+k_read_rows(ReadRows p)
+{
+	const int64_t total = p.n * p.ncols;
+
+	for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x)
+	{
+		const int64_t r = i / p.ncols;
+		const int	c = (int) (i % p.ncols);
+		const uint32_t row = p.idx ? p.idx[r] : (uint32_t) r;
+
+		p.out[i] = cb_load_widen(p.data[c], p.types[c], row);
+		p.outnull[i] = p.nulls[c] ? p.nulls[c][row] : (uint8_t) 0;
+	}
+}
+
+extern "C" int
+cbgpu_rel_read_rows(cbgpu_rel *rel, const uint32_t *host_idx, int64_t n, int64_t *out, uint8_t *outnull)
+{
+	cbgpu_ctx  *ctx = rel->ctx;
+	ReadRows	p;
+	uint32_t   *d_idx = NULL;
+	char	   *d_buf = NULL;
+	const int64_t total = n * rel->ncols;
+
+	if (n < 0 || (!host_idx && n > rel->nrows) || rel->ncols > CB_MAX_COLS_REL)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_read_rows: bad row count%s %lld", "", n);
+	if (total == 0)
+		return CBGPU_OK;
+	for (int64_t r = 0; host_idx && r < n; r++)
+		if ((int64_t) host_idx[r] >= rel->nrows)
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_read_rows: row %s%lld out of range", "", (long long) host_idx[r]);
+	memset(&p, 0, sizeof(p));
+	for (int c = 0; c < rel->ncols; c++)
+	{
+		p.data[c] = rel->data[c];
+		p.nulls[c] = rel->nulls[c];
+		p.types[c] = rel->types[c];
+	}
+	p.ncols = rel->ncols;
+	p.n = n;
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	CB_CUDA(ctx, cudaMallocAsync(&d_buf, (size_t) total * 9, ctx->stream));
+	p.out = (long long *) d_buf;
+	p.outnull = (uint8_t *) (d_buf + (size_t) total * 8);
+	if (host_idx)
+	{
+		CB_CUDA(ctx, cudaMallocAsync(&d_idx, (size_t) n * sizeof(uint32_t), ctx->stream));
+		CB_CUDA(ctx, cudaMemcpyAsync(d_idx, host_idx, (size_t) n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		p.idx = d_idx;
+	}
+	{
+		int			blocks = (int) ((total + 255) / 256);
+
+		if (blocks > ctx->sm_count * 8)
+			blocks = ctx->sm_count * 8;
+		k_read_rows<<<blocks, 256, 0, ctx->stream>>>(p);
+		CB_LAUNCHED(ctx, "k_read_rows");
+	}
+	CB_CUDA(ctx, cudaMemcpyAsync(out, p.out, (size_t) total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(outnull, p.outnull, (size_t) total, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, CB_STATUS_RIDE(ctx));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	CB_STATUS_FETCHED(ctx);
+	CB_CUDA(ctx, cudaFreeAsync(d_buf, ctx->stream));
+	if (d_idx)
+		CB_CUDA(ctx, cudaFreeAsync(d_idx, ctx->stream));
+	return CBGPU_OK;
+}
+
 extern "C" int
 cbgpu_rel_set_visimap(cbgpu_rel *rel, const uint8_t *bits)
 {

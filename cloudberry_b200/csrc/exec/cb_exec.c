@@ -1706,12 +1706,14 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 			int64_t		before = cbgpu_kernel_launches(es->es_ctx);
 
 			GPU(es, cbgpu_pipeline_run(es->es_ctx, pl));
-			GPU(es, cbgpu_dev_read(es->es_ctx, counter, sizeof(int64_t) * (size_t) nsegs, counts));
+			if (!direct)			/* direct: the counts come back with direct_end's own round trip */
+				GPU(es, cbgpu_dev_read(es->es_ctx, counter, sizeof(int64_t) * (size_t) nsegs, counts));
 			for (int d = 0; d < nsegs && !direct; d++)
 				if (counts[d] > *seg_capacity)
 					return es_fail(es, CBGPU_ERR_NOMEM, "Motion send buffer for segment %d overflowed (%lld rows, capacity %lld): data skew beyond the reserved allowance",
 								   d, (long long) counts[d], (long long) *seg_capacity);
-			GPU(es, cbgpu_check_status(es->es_ctx));
+			if (!direct)
+				GPU(es, cbgpu_check_status(es->es_ctx));
 			ps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
 			ps->instrument.rows_in += s->rows_in;
 			if (cbgpu_last_kernel_ms(es->es_ctx) > 0)
@@ -1728,14 +1730,11 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 			/* RecvTupleFrom for the whole stream: wait for every sender, take delivery */
 			CbInterconnect *ic = es->es_interconnect;
 			cbgpu_rel  *recv = NULL;
-			int64_t		elsewhere = 0;
 			int			c = m->nhashExprs;
 
-			for (int d = 0; d < nsegs; d++)
-				if (d != es->es_segindex)
-					elsewhere += counts[d];
-			if (ic->direct_end(ic, es, m->motionID, elsewhere, &recv) != CBGPU_OK)
+			if (ic->direct_end(ic, es, m->motionID, (const int64_t *) counter, counts, &recv) != CBGPU_OK)
 				return es->es_errcode ? es->es_errcode : es_fail(es, CBGPU_ERR_CUDA, "%s", cbgpu_last_error(es->es_ctx));
+			GPU(es, cbgpu_check_status(es->es_ctx));	/* fetched with the completion: no extra round trip */
 			p->owned.rels[p->owned.nrels++] = recv;
 			for (int k = 0; k < m->nhashExprs; k++)
 			{
@@ -1916,6 +1915,27 @@ rel_to_result(CbEState *es, cbgpu_rel *rel, const PExpr *shape, int nshape, cons
 	uint8_t   **coln = calloc((size_t) ncols, sizeof(uint8_t *));
 	int			rc = CBGPU_OK;
 
+	/* small result sets (groups, top-N rows): every column's rows in one round trip */
+	if (nrows > 0 && nrows * ncols <= (1 << 20))
+	{
+		int64_t    *vals = calloc((size_t) (nrows * ncols), sizeof(int64_t));
+		uint8_t    *nls = calloc((size_t) (nrows * ncols), 1);
+
+		rc = cbgpu_rel_read_rows(rel, rowidx, nrows, vals, nls);
+		for (int c = 0; c < ncols; c++)
+		{
+			colv[c] = calloc((size_t) nrows, sizeof(int64_t));
+			coln[c] = calloc((size_t) nrows, 1);
+			for (int64_t r = 0; r < nrows && rc == CBGPU_OK; r++)
+			{
+				colv[c][r] = vals[(size_t) r * ncols + c];
+				coln[c][r] = nls[(size_t) r * ncols + c];
+			}
+		}
+		free(vals);
+		free(nls);
+	}
+	else
 	/* read every column (whole, or the selected rows one by one when an index list is given) */
 	for (int c = 0; c < ncols && rc == CBGPU_OK; c++)
 	{
@@ -2535,10 +2555,11 @@ ic_nccl_direct_begin(CbInterconnect *ic, CbEState *es, int32_t motion_id, int32_
 }
 
 static int
-ic_nccl_direct_end(CbInterconnect *ic, CbEState *es, int32_t motion_id, int64_t rows_sent_elsewhere, cbgpu_rel **recv)
+ic_nccl_direct_end(CbInterconnect *ic, CbEState *es, int32_t motion_id, const int64_t *dev_sent_counts, int64_t *sent_counts,
+				   cbgpu_rel **recv)
 {
 	(void) motion_id;
-	GPU(es, cbgpu_motion_direct_end((cbgpu_motion *) ic->priv, rows_sent_elsewhere, recv));
+	GPU(es, cbgpu_motion_direct_end((cbgpu_motion *) ic->priv, dev_sent_counts, sent_counts, recv));
 	return CBGPU_OK;
 }
 

@@ -525,8 +525,10 @@ cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, 
 }
 
 extern "C" int
-cbgpu_motion_direct_end(cbgpu_motion *m, int64_t rows_sent_elsewhere, cbgpu_rel **recv)
+cbgpu_motion_direct_end(cbgpu_motion *m, const int64_t *dev_sent_counts, int64_t *sent_counts, cbgpu_rel **recv)
 {
+	int64_t		rows_sent_elsewhere = 0;
+
 	cbgpu_ctx  *ctx = m->ctx;
 	int		   *d_flag = (int *) (m->d_counts + (size_t) m->nranks * m->nranks);
 	unsigned long long got = 0;
@@ -539,9 +541,17 @@ cbgpu_motion_direct_end(cbgpu_motion *m, int64_t rows_sent_elsewhere, cbgpu_rel 
 	CB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
 	CB_NCCL(ctx, ncclAllReduce(d_flag, d_flag, 1, ncclInt32, ncclMax, m->comm, ctx->stream));
 	CB_CUDA(ctx, cudaMemcpyAsync(&got, m->win, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream));
+	/* the sender slice's own per-destination counts (a statistic) and the status word ride in the same round trip */
+	if (dev_sent_counts && sent_counts)
+		CB_CUDA(ctx, cudaMemcpyAsync(sent_counts, dev_sent_counts, sizeof(int64_t) * (size_t) m->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, CB_STATUS_RIDE(ctx));
 	if (ctx->trace_on)
 		cb_trace_mark(ctx, "p2p:complete");
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	CB_STATUS_FETCHED(ctx);
+	for (int d = 0; d < m->nranks && dev_sent_counts && sent_counts; d++)
+		if (d != m->rank)
+			rows_sent_elsewhere += sent_counts[d];
 	if ((int64_t) got > m->dx_cap)
 		return cb_fail(ctx, CBGPU_ERR_NOMEM, "Motion receive buffer overflowed (%s%lld rows): data skew beyond the reserved allowance", "", (long long) got);
 	rc = cbgpu_rel_create(ctx, (int64_t) got, m->dx_ncols, m->dx_types, m->dx_dscales, recv);

@@ -164,7 +164,7 @@ typedef struct CbInterconnect
 								 const int32_t *types, const int32_t *dscales, int64_t input_rows, int64_t *capacity,
 								 void *const **dest_cols, unsigned long long *const **dest_counts);
 	int			(*direct_end) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id,
-							   int64_t rows_sent_elsewhere, cbgpu_rel **recv);
+							   const int64_t *dev_sent_counts, int64_t *sent_counts, cbgpu_rel **recv);
 } CbInterconnect;
 
 /* interconnect over NCCL (cbgpu_motion_*): one process per GPU-segment.  SetupInterconnect

@@ -114,6 +114,9 @@ int			cbgpu_rel_set_visimap(cbgpu_rel *rel, const uint8_t *bits);
 int			cbgpu_rel_set_dict_hash(cbgpu_rel *rel, int32_t col, const uint32_t *hashes, int32_t n);
 /* shrink the logical row count (relations allocated at an upper bound, e.g. Motion receive) */
 int			cbgpu_rel_set_nrows(cbgpu_rel *rel, int64_t nrows);
+/* n rows (host_idx[0..n), or the first n when host_idx is NULL) of EVERY column in one round trip: values widened
+ * to int64 (float8: raw bits), row-major out[r * ncols + c], outnull likewise.  For small result sets. */
+int			cbgpu_rel_read_rows(cbgpu_rel *rel, const uint32_t *host_idx, int64_t n, int64_t *out, uint8_t *outnull);
 /* raw device pointer of a column (for harness-side generators / NCCL); not dereferenceable on host */
 void	   *cbgpu_rel_col_devptr(cbgpu_rel *rel, int32_t col);
 size_t		cbgpu_rel_nbytes(const cbgpu_rel *rel);
@@ -334,13 +337,14 @@ int			cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t 
  *          column: then begin fails on EVERY rank and all take cbgpu_motion_redistribute); returns the per-receiver row capacity and two device
  *          tables for the PARTITION sink: dest_cols[d * ncols + c] = base of column c in segment d's
  *          window, dest_counts[d] = segment d's row counter (CbpSink.part_cols / part_counts)
- *   end:   after the pipeline ran: wait for every sender, return the rows addressed to this rank.
+ *   end:   after the pipeline ran: wait for every sender, return the rows addressed to this rank; the sink's own
+ *          per-destination counters (dev_sent_counts, device) are copied to sent_counts in the same round trip.
  * cbgpu_motion_direct_available() == 0 (no P2P / IPC, or CBGPU_MOTION=nccl): use cbgpu_motion_redistribute. */
 int			cbgpu_motion_direct_available(const cbgpu_motion *m);
 int			cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, const int32_t *dscales,
 									  int64_t input_rows, int64_t *capacity, void *const **dest_cols,
 									  unsigned long long *const **dest_counts);
-int			cbgpu_motion_direct_end(cbgpu_motion *m, int64_t rows_sent_elsewhere, cbgpu_rel **recv);
+int			cbgpu_motion_direct_end(cbgpu_motion *m, const int64_t *dev_sent_counts, int64_t *sent_counts, cbgpu_rel **recv);
 int64_t		cbgpu_motion_direct_bytes(const cbgpu_motion *m);
 /* Gather: the first nrows rows of every rank's `send` to rank `root` (others receive 0 rows) */
 int			cbgpu_motion_gather(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
