@@ -74,6 +74,16 @@ struct PcProbe
 	int32_t		keytype[2];		/* hash function by the OUTER key's type (cross-type int4/int8 joins) */
 };
 
+#define PC_MAXEARLY 2
+struct PcEarly
+{
+	const void *col;			/* driving-relation column (4 or 8 bytes wide)                         */
+	int32_t		width;
+	int32_t		hashtype;		/* CbTypeId whose hash function keys the filter                       */
+	const uint32_t *bloom;
+	uint32_t	mask;
+};
+
 struct PcParams
 {
 	int64_t		nrows;
@@ -82,6 +92,11 @@ struct PcParams
 	int32_t		np;
 	PcFilter	filt[2];
 	PcProbe		probe[PC_MAXP];
+	/* scan-level runtime filters (the reference's PassByBloomFilter in the SeqScan, executor/nodeSeqscan.c:413,
+	 * built by CreateRuntimeFilter executor/nodeHashjoin.c:2217 per hash-clause column that traces down to the
+	 * scan): a Bloom filter over ONE key column of a later probe's build side, checked in stage F */
+	int32_t		nearly;
+	PcEarly		early[PC_MAXEARLY];
 	uint32_t   *qmem;			/* global queues: [CTA][q_cta_words]                                  */
 	int64_t		q_cta_words;
 	int32_t		q_off[PC_NQ];	/* queue k >= 1: word offset inside the CTA's slice                   */
@@ -517,7 +532,7 @@ k_probe_chain(const __grid_constant__ PcParams P)
 	__shared__ PcPart part;
 	const int	np = P.np;
 	const int	last = 2 * np + 1;		/* the sink's stage number; stage s reads queue s - 1         */
-	const bool	iota = P.nfilters == 0 && P.visimap == NULL;
+	const bool	iota = P.nfilters == 0 && P.visimap == NULL && P.nearly == 0;
 	const int64_t tile_rows = iota ? PC_BATCH : PC_TILE;
 	const int64_t ntiles = (P.nrows + tile_rows - 1) / tile_rows;
 	uint32_t   *const qg = P.qmem + (size_t) blockIdx.x * (size_t) P.q_cta_words;
@@ -635,6 +650,29 @@ k_probe_chain(const __grid_constant__ PcParams P)
 						alive = (unsigned) (pc_filter_value(P.filt[1], r) - P.filt[1].lo) <= P.filt[1].span;
 					am |= (unsigned) alive << u;
 				}
+			/* scan-level runtime filters: the key columns of the rows still alive, 8 filter words in flight */
+			for (int f = 0; f < P.nearly && __any_sync(0xffffffffu, am != 0); f++)
+			{
+				const PcEarly &E = P.early[f];
+				uint32_t	bits[8], word[8];
+
+#pragma unroll
+				for (int u = 0; u < 8; u++)
+				{
+					const int64_t r = base + o0 + u;
+					int64_t		kv = 0;
+					uint32_t	w = 0;
+
+					if ((am >> u) & 1)
+						kv = E.width == 4 ? (int64_t) __ldg((const int32_t *) E.col + r) : __ldg((const long long *) E.col + r);
+					bits[u] = ht_bloom_bits(pg_hash_combine(0u, pg_hash_datum(E.hashtype, kv, NULL), false), &w, E.mask);
+					word[u] = ((am >> u) & 1) ? __ldg(E.bloom + w) : 0u;
+				}
+#pragma unroll
+				for (int u = 0; u < 8; u++)
+					if ((word[u] & bits[u]) != bits[u])
+						am &= ~(1u << u);
+			}
 			const unsigned c = __popc(am);
 			unsigned	x = c;
 
@@ -731,6 +769,83 @@ pc_col(const CbPipeline *p, int c, PcCol *out, int base)
 	out->type = p->cols[c].type;
 	out->src = p->cols[c].src == 0 ? 0 : p->cols[c].src - base + 1;
 	return true;
+}
+
+/* Bloom filter over key column `kc` of probe k's build side, restricted to the build rows that can still find a
+ * partner in every later INNER probe whose keys all come from that same build side (`red`): a row of the driving scan
+ * whose key misses it can never reach the sink - probe k would drop it, or a later probe would */
+struct PcEarlyBuild
+{
+	int64_t		nrows;			/* rows of probe k's inner relation                                   */
+	HtDev		self;			/* probe k's table: key columns / NULL maps of the build side         */
+	int32_t		kc;
+	int32_t		hashtype;
+	int32_t		nred;
+	HtDev		red[PC_MAXP];
+	int32_t		red_nkeys[PC_MAXP];
+	PcCol		red_key[PC_MAXP][2];	/* columns of the build relation (indexed by its row)             */
+	int32_t		red_keytype[PC_MAXP][2];
+	uint32_t   *bloom;			/* NULL: only count the rows that would go in                         */
+	uint32_t	mask;
+	unsigned long long *passed;
+};
+
+__global__ void
+k_pc_early_build(PcEarlyBuild B)
+{
+	for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; r < B.nrows; r += (int64_t) gridDim.x * blockDim.x)
+	{
+		bool		ok = true;
+
+		for (int k = 0; k < B.self.nkeys; k++)
+			if (B.self.keynulls[k] && B.self.keynulls[k][r])
+				ok = false;		/* never inserted into probe k's table (nodeHash.c:2161) */
+		for (int m = 0; m < B.nred && ok; m++)
+		{
+			const HtDev &T = B.red[m];
+			int64_t		kv[2] = {0, 0};
+			uint32_t	h = 0;
+			bool		found = false;
+
+			for (int i = 0; i < B.red_nkeys[m]; i++)
+			{
+				kv[i] = cb_load_widen(B.red_key[m][i].data, B.red_key[m][i].type, (uint32_t) r);
+				h = pg_hash_combine(h, pg_hash_datum(B.red_keytype[m][i], kv[i], B.red_key[m][i].dict), false);
+			}
+			uint32_t	pos = h & T.mask;
+
+			for (;;)
+			{
+				const unsigned long long e = T.slots[pos];
+
+				if (e == HT_EMPTY)
+					break;
+				if ((uint32_t) (e >> 32) == h)
+				{
+					const uint32_t ir = (uint32_t) e;
+
+					if (cb_load_widen(T.keydata[0], T.keytype[0], ir) == kv[0] &&
+						(B.red_nkeys[m] < 2 || cb_load_widen(T.keydata[1], T.keytype[1], ir) == kv[1]))
+					{
+						found = true;
+						break;
+					}
+				}
+				pos = (pos + 1) & T.mask;
+			}
+			ok = found;
+		}
+		if (ok && !B.bloom)
+			atomicAdd(B.passed, 1ull);
+		if (ok && B.bloom)
+		{
+			uint32_t	w;
+			const int64_t kv = cb_load_widen(B.self.keydata[B.kc], B.self.keytype[B.kc], (uint32_t) r);
+			const uint32_t bits = ht_bloom_bits(pg_hash_combine(0u, pg_hash_datum(B.hashtype, kv, NULL), false), &w, B.mask);
+
+			atomicOr(B.bloom + w, bits);
+		}
+	}
 }
 
 #define PC_REJECT(n) \
@@ -969,8 +1084,99 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 		}
 	}
 
+	/* scan-level runtime filters.  The reference pushes a Bloom filter per integer hash-clause column down to the
+	 * SeqScan the column comes from (CreateRuntimeFilter / FindTargetNodes, nodeHashjoin.c:2217,2407).  Probe k's own
+	 * filter is consulted in stage B_k anyway; what stage F can add is a filter that knows MORE than probe k's build
+	 * side: the build rows that also survive the later probes keyed only by that build side's columns (a dimension
+	 * joined to its sub-dimension further up the plan).  Rows of the scan that miss it are dropped before the first
+	 * hash-table access instead of after several. */
+	void	   *early_mem[PC_MAXEARLY] = {NULL, NULL};
+
+	for (int k = 0; k < np && P.nearly < PC_MAXEARLY && !getenv("CBGPU_NO_EARLY_FILTER"); k++)
+	{
+		static PcEarlyBuild B;
+		PcProbe    *q = &P.probe[k];
+		const cbgpu_rel *inner = p->probes[k].ht->inner;
+		int			kc = -1;
+		int64_t		words = 32;
+
+		memset(&B, 0, sizeof(B));
+		if (q->jointype != CB_JOIN_INNER || !inner || inner->nrows < 1)
+			continue;
+		for (int m = k + 1; m < np; m++)
+		{
+			bool		all = P.probe[m].jointype == CB_JOIN_INNER;
+
+			for (int i = 0; i < P.probe[m].nkeys; i++)
+				if (P.probe[m].key[i].src != k + 1)
+					all = false;
+			if (!all)
+				continue;
+			B.red[B.nred] = P.probe[m].ht;
+			B.red_nkeys[B.nred] = P.probe[m].nkeys;
+			for (int i = 0; i < P.probe[m].nkeys; i++)
+			{
+				B.red_key[B.nred][i] = P.probe[m].key[i];
+				B.red_keytype[B.nred][i] = P.probe[m].keytype[i];
+			}
+			B.nred++;
+		}
+		if (B.nred == 0)
+			continue;
+		for (int i = 0; i < q->nkeys && kc < 0; i++)
+			if (q->key[i].src == 0 && (q->key[i].type == CB_INT4 || q->key[i].type == CB_DATE || q->key[i].type == CB_INT8))
+				kc = i;
+		if (kc < 0)
+			continue;
+		{
+			/* worth it only if the later probes thin the build side out: try the first 64 K build rows */
+			unsigned long long *d_passed,
+						h_passed = 0;
+			const int64_t sample = inner->nrows < 65536 ? inner->nrows : 65536;
+
+			CB_CUDA(ctx, cudaMallocAsync(&d_passed, sizeof(*d_passed), ctx->stream));
+			CB_CUDA(ctx, cudaMemsetAsync(d_passed, 0, sizeof(*d_passed), ctx->stream));
+			B.nrows = sample;
+			B.self = q->ht;
+			B.kc = kc;
+			B.hashtype = q->keytype[kc];
+			B.bloom = NULL;
+			B.passed = d_passed;
+			k_pc_early_build<<<(int) ((sample + 255) / 256), 256, 0, ctx->stream>>>(B);
+			CB_LAUNCHED(ctx, "k_pc_early_build");
+			CB_CUDA(ctx, cudaMemcpyAsync(&h_passed, d_passed, sizeof(h_passed), cudaMemcpyDeviceToHost, ctx->stream));
+			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			CB_CUDA(ctx, cudaFreeAsync(d_passed, ctx->stream));
+			if ((int64_t) h_passed * 2 > sample)
+				continue;
+		}
+		while (words < inner->nrows / 2)
+			words <<= 1;
+		CB_CUDA(ctx, cudaMallocAsync(&early_mem[P.nearly], (size_t) words * sizeof(uint32_t), ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(early_mem[P.nearly], 0, (size_t) words * sizeof(uint32_t), ctx->stream));
+		B.nrows = inner->nrows;
+		B.self = q->ht;
+		B.kc = kc;
+		B.hashtype = q->keytype[kc];
+		B.bloom = (uint32_t *) early_mem[P.nearly];
+		B.mask = (uint32_t) (words - 1);
+		{
+			int			eb = (int) ((inner->nrows + 255) / 256);
+
+			if (eb > ctx->sm_count * 8)
+				eb = ctx->sm_count * 8;
+			k_pc_early_build<<<eb, 256, 0, ctx->stream>>>(B);
+			CB_LAUNCHED(ctx, "k_pc_early_build");
+		}
+		P.early[P.nearly].col = q->key[kc].data;
+		P.early[P.nearly].width = cb_type_w(q->key[kc].type);
+		P.early[P.nearly].hashtype = q->keytype[kc];
+		P.early[P.nearly].bloom = B.bloom;
+		P.early[P.nearly].mask = B.mask;
+		P.nearly++;
+	}
 	/* persistent grid: 4 CTAs per SM; queue k >= 1 holds (k + 3) / 2 words per entry */
-	const bool	iota = P.nfilters == 0 && P.visimap == NULL;
+	const bool	iota = P.nfilters == 0 && P.visimap == NULL && P.nearly == 0;
 	const int64_t ntiles = (p->nrows + (iota ? PC_BATCH : PC_TILE) - 1) / (iota ? PC_BATCH : PC_TILE);
 	int			blocks = ctx->sm_count * PC_OCC;
 	int64_t		words = 0;
@@ -988,6 +1194,8 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 		fprintf(stderr, "k_probe_chain: np %d nrows %lld tiles %lld blocks %d queue words/CTA %lld filters %d sink %d kinds %d %d %d %d\n", np,
 				(long long) P.nrows, (long long) ntiles, blocks, (long long) words, P.nfilters, P.sink_kind, P.probe[0].kind,
 				P.probe[1].kind, P.probe[2].kind, P.probe[3].kind);
+	if (getenv("CBGPU_DEBUG") && P.nearly)
+		fprintf(stderr, "k_probe_chain: %d scan-level runtime filter(s)\n", P.nearly);
 	CB_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
 	int			kl = cb_klog_begin(ctx, "k_probe_chain");
 
@@ -999,6 +1207,9 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 	cb_klog_end(ctx, kl);
 	CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
 	CB_CUDA(ctx, cudaFreeAsync(P.qmem, ctx->stream));
+	for (int f = 0; f < PC_MAXEARLY; f++)
+		if (early_mem[f])
+			CB_CUDA(ctx, cudaFreeAsync(early_mem[f], ctx->stream));
 	ctx->kernel_timed = true;
 	*handled = true;
 	return CBGPU_OK;
