@@ -46,6 +46,9 @@
 
 struct AocsDir
 {
+	long long	hoff;			/* storage block header offset in the file                            */
+	int32_t		overall;		/* header + firstRowNum + content rounded up                          */
+	int32_t		pad;
 	long long	off;			/* content offset in the file                                         */
 	long long	rowbase;		/* first output row of the block                                      */
 	int32_t		rows;
@@ -135,6 +138,111 @@ aocs_numeric(const uint8_t *body, int len, int dscale, int64_t *out)
 	}
 	*out = neg ? -(int64_t) acc : (int64_t) acc;
 	return true;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * CRC-32C (Castagnoli, reflected polynomial 0x82F63B78), as src/port/pg_crc32c_sb8.c computes it.
+ * Append-only blocks store it WITHOUT the final inversion (cdbappendonlystorageformat.c:41-46,71-76):
+ *   block checksum  (bytes 8..11)  = crc over bytes [16, overall block length)
+ *   header checksum (bytes 12..15) = crc over bytes [0, 12)
+ * (AppendOnlyStorageFormat_ComputeBlockChecksum / _ComputeHeaderChecksum :27-78, layout :125-190).
+ * One warp per block: every lane runs the byte-wise table recurrence over its slice starting from 0,
+ * then lane 0 stitches the slices: crc(A || B) = crc(A) * x^(8|B|) mod P  xor  crc0(B)  over GF(2).
+ * --------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t
+crc32c_mulmod(uint32_t a, uint32_t b)
+{
+	/* a * b mod P in the reflected representation (bit 31 = x^0) */
+	uint32_t	r = 0;
+
+	for (int i = 0; i < 32; i++)
+	{
+		if (a & 0x80000000u)
+			r ^= b;
+		a <<= 1;
+		b = (b >> 1) ^ ((b & 1u) ? 0x82F63B78u : 0u);
+	}
+	return r;
+}
+
+/* x^(8 n) mod P */
+__device__ __forceinline__ uint32_t
+crc32c_xpow8n(uint32_t n)
+{
+	uint32_t	result = 0x80000000u;	/* 1 */
+	uint32_t	sq = 0x00800000u;		/* x^8 */
+
+	while (n)
+	{
+		if (n & 1u)
+			result = crc32c_mulmod(result, sq);
+		sq = crc32c_mulmod(sq, sq);
+		n >>= 1;
+	}
+	return result;
+}
+
+__global__ void __launch_bounds__(AOCS_WARPS * 32)
+k_aocs_verify(const uint8_t *raw, const AocsDir *dir, int nblocks, int *status)
+{
+	__shared__ uint32_t tab[256];
+	const int	lane = threadIdx.x & 31;
+	const int	w = threadIdx.x >> 5;
+	const int	nwarps = gridDim.x * AOCS_WARPS;
+
+	for (int i = threadIdx.x; i < 256; i += blockDim.x)
+	{
+		uint32_t	c = (uint32_t) i;
+
+		for (int k = 0; k < 8; k++)
+			c = (c >> 1) ^ ((c & 1u) ? 0x82F63B78u : 0u);
+		tab[i] = c;
+	}
+	__syncthreads();
+	for (int b = blockIdx.x * AOCS_WARPS + w; b < nblocks; b += nwarps)
+	{
+		const uint8_t *h = raw + dir[b].hoff;
+		const uint32_t len = (uint32_t) dir[b].overall - 16u;
+		const uint8_t *d = h + 16;
+		const uint32_t per = ((len + 31u) / 32u + 3u) & ~3u;	/* bytes per lane */
+		const uint32_t lo = (uint32_t) lane * per < len ? (uint32_t) lane * per : len;
+		const uint32_t hi = lo + per < len ? lo + per : len;
+		uint32_t	c = 0;
+
+		/* blocks are 8-byte aligned and padded to 8 bytes, slices are whole words */
+		for (uint32_t i = lo; i < hi; i += 4)
+		{
+			c ^= *(const uint32_t *) (d + i);
+			c = tab[c & 0xffu] ^ (c >> 8);
+			c = tab[c & 0xffu] ^ (c >> 8);
+			c = tab[c & 0xffu] ^ (c >> 8);
+			c = tab[c & 0xffu] ^ (c >> 8);
+		}
+		/* stitch: start from the init value, advance it over each slice's length, add the slice's own crc */
+		uint32_t	crc = 0xFFFFFFFFu;
+		const uint32_t mfull = crc32c_xpow8n(per);
+
+		for (int l = 0; l < 32; l++)
+		{
+			const uint32_t cl = __shfl_sync(0xffffffffu, c, l);
+			const uint32_t nl = __shfl_sync(0xffffffffu, hi - lo, l);
+
+			if (nl == 0)
+				continue;
+			crc = crc32c_mulmod(crc, nl == per ? mfull : crc32c_xpow8n(nl)) ^ cl;
+		}
+		if (lane == 0)
+		{
+			uint32_t	hc = 0xFFFFFFFFu;
+			const uint32_t stored_block = aocs_le32(h + 8);
+			const uint32_t stored_header = aocs_le32(h + 12);
+
+			for (int i = 0; i < 12; i++)
+				hc = tab[(hc ^ h[i]) & 0xffu] ^ (hc >> 8);
+			if (hc != stored_header || crc != stored_block)
+				atomicExch(status, CBGPU_ERR_CORRUPT);
+		}
+	}
 }
 
 /* value of the datum at d (fixed width: the value; numeric: scaled integer; char(1): the byte) */
@@ -435,6 +543,8 @@ k_aocs_decode(AocsParams P)
 	const int	w = threadIdx.x >> 5;
 	const int	nwarps = gridDim.x * AOCS_WARPS;
 
+	if (*P.status == CBGPU_ERR_CORRUPT)
+		return;					/* k_aocs_verify (same stream, just before) rejected a block: decode nothing */
 	for (int b = blockIdx.x * AOCS_WARPS + w; b < P.nblocks; b += nwarps)
 	{
 		const AocsDir D = P.dir[b];
@@ -625,6 +735,8 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 			if (!dir)
 				return CBGPU_ERR_NOMEM;
 		}
+		dir[ndir].hoff = pos;
+		dir[ndir].overall = (int32_t) (hlen + ((int64_t) dlen + 7) / 8 * 8);
 		dir[ndir].off = pos + hlen;
 		dir[ndir].rowbase = row_offset + rows;
 		dir[ndir].rows = nrow;
@@ -678,6 +790,12 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 
 		if (blocks > ctx->sm_count * 16)
 			blocks = ctx->sm_count * 16;
+		if (checksum)
+		{
+			/* AppendOnlyStorageRead verifies header and block checksums before handing a block on */
+			k_aocs_verify<<<blocks, AOCS_WARPS * 32, 0, ctx->stream>>>(d_raw, d_dir, (int) ndir, ctx->d_status);
+			CB_LAUNCHED(ctx, "k_aocs_verify");
+		}
 		k_aocs_decode<<<blocks, AOCS_WARPS * 32, 0, ctx->stream>>>(P);
 		CB_LAUNCHED(ctx, "k_aocs_decode");
 	}

@@ -107,7 +107,8 @@ cb_check_status(cbgpu_ctx *ctx, const char *what)
 		*ctx->h_status = 0;
 		snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what,
 				 code == CBGPU_ERR_OVERFLOW ? "value out of range (integer/numeric overflow)" :
-				 code == CBGPU_ERR_NOMEM ? "device table or output buffer full" : "device-side error");
+				 code == CBGPU_ERR_NOMEM ? "device table or output buffer full" :
+				 code == CBGPU_ERR_CORRUPT ? "stored block fails its checksum" : "device-side error");
 		return code;
 	}
 	return CBGPU_OK;

@@ -51,6 +51,7 @@ extern "C" {
 									 * there is no CPU fallback                                        */
 #define CBGPU_ERR_OVERFLOW (-4)		/* integer / numeric value out of range during execution           */
 #define CBGPU_ERR_NOMEM (-5)
+#define CBGPU_ERR_CORRUPT (-6)		/* stored data fails its checksum (AOCS block CRC-32C)              */
 
 typedef struct cbgpu_ctx cbgpu_ctx;
 typedef struct cbgpu_rel cbgpu_rel;
@@ -362,7 +363,9 @@ int			cbgpu_motion_broadcast(cbgpu_motion *m, cbgpu_rel *send, int64_t nrows, cb
 /* file_bytes: one column's segment file (<relfilenode>.<n>) as it lies on disk, in host memory:
  * uncompressed SmallContent storage blocks holding Original datum stream blocks.  attlen = pg_type
  * typlen (1/2/4/8, or -1 with varkind), typalign in bytes.  Decodes into rows [row_offset, +nrows) of
- * column `col` (NULL bitmaps become the column's null map).  Other block kinds: CBGPU_ERR_UNSUPPORTED. */
+ * column `col` (NULL bitmaps become the column's null map).  With checksum != 0 every block's header and
+ * block CRC-32C are verified on the device first (CBGPU_ERR_CORRUPT), as the reference does on read
+ * (AppendOnlyStorageFormat_VerifyHeaderChecksum / _VerifyBlockChecksum).  Other block kinds: CBGPU_ERR_UNSUPPORTED. */
 int			cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum,
 									 int32_t attlen, int32_t varkind, int32_t typalign, cbgpu_rel *rel, int32_t col,
 									 int64_t row_offset, int64_t *nrows);

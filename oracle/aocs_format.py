@@ -185,7 +185,36 @@ def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768
 # ------------------------------------------------------------------------------------------------
 # the restated reader
 # ------------------------------------------------------------------------------------------------
-def walk_blocks(raw, checksum):
+_CRC32C_TABLE = []
+
+
+def crc32c_raw(data, crc=0xFFFFFFFF):
+    """CRC-32C (reflected 0x82F63B78) WITHOUT the final inversion: INIT_CRC32C + COMP_CRC32C only, which is what
+    append-only block headers store (cdbappendonlystorageformat.c:41-46, 71-76; src/port/pg_crc32c_sb8.c)."""
+    if not _CRC32C_TABLE:
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ (0x82F63B78 if c & 1 else 0)
+            _CRC32C_TABLE.append(c)
+    t = _CRC32C_TABLE
+    for b in bytes(data):
+        crc = t[(crc ^ b) & 0xFF] ^ (crc >> 8)
+    return crc
+
+
+def verify_block_checksums(raw, pos, overall):
+    """AppendOnlyStorageFormat_VerifyHeaderChecksum / _VerifyBlockChecksum (cdbappendonlystorageformat.c:1657-1720):
+    header checksum (bytes 12..15) covers bytes [0,12); block checksum (bytes 8..11) covers [16, overall)."""
+    stored_block = int.from_bytes(raw[pos + 8:pos + 12], "little")
+    stored_header = int.from_bytes(raw[pos + 12:pos + 16], "little")
+    if crc32c_raw(raw[pos:pos + 12]) != stored_header:
+        raise ValueError("block at %d: header checksum does not match" % pos)
+    if crc32c_raw(raw[pos + 16:pos + overall]) != stored_block:
+        raise ValueError("block at %d: block checksum does not match" % pos)
+
+
+def walk_blocks(raw, checksum, verify=False):
     """[(content offset, content length, row count, first row number)] of a column file"""
     out = []
     pos = 0
@@ -210,6 +239,8 @@ def walk_blocks(raw, checksum):
         if has_first:
             first = int.from_bytes(raw[pos + hlen:pos + hlen + 8], "little", signed=True)
             hlen += 8
+        if verify and checksum:
+            verify_block_checksums(raw, pos, hlen + (dlen + 7) // 8 * 8)
         out.append((pos + hlen, dlen, rows, first))
         pos += hlen + (dlen + 7) // 8 * 8
     return out

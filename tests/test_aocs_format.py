@@ -61,6 +61,27 @@ def test_walker_against_reference_header_accessors(case):
             assert L.ref_aocs_verify_block(hdr, hlen_guess + (dlen + 7) // 8 * 8) == 0
 
 
+def test_checksum_restatement_on_reference_written_files():
+    """every checksummed fixture (written by the reference's own block writer) verifies under the restated CRC-32C;
+    one flipped content bit / one flipped header bit does not; the known CRC-32C check value pins the polynomial"""
+    assert A.crc32c_raw(b"123456789") ^ 0xFFFFFFFF == 0xE3069283
+    seen = 0
+    for name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls in CASES:
+        if not checksum:
+            continue
+        assert len(A.walk_blocks(raw, checksum, verify=True)) == nblocks
+        seen += 1
+        bad = bytearray(raw)
+        bad[len(raw) // 2 if len(raw) > 64 else 30] ^= 0x10
+        with pytest.raises(ValueError, match="checksum"):
+            A.walk_blocks(bytes(bad), checksum, verify=True)
+        bad = bytearray(raw)
+        bad[5] ^= 0x01                                  # inside header bytes [0,12)
+        with pytest.raises(ValueError):
+            A.walk_blocks(bytes(bad), checksum, verify=True)
+    assert seen >= 10
+
+
 @pytest.mark.skipif(A.ref_lib() is None, reason="reference library only where /root/reference exists")
 def test_numeric_encoding_against_reference_macros():
     L = A.ref_lib()

@@ -52,6 +52,37 @@ def test_refuses_what_it_does_not_decode(ctx):
     rel.free()
 
 
+@pytest.mark.parametrize("name", ["int4_plain", "numeric_price", "rle_float8_many_blocks_nulls", "delta_date_sorted_nulls", "int4_tiny"])
+def test_checksum_failure_is_reported(ctx, name):
+    """a flipped bit anywhere in a checksummed block -> CBGPU_ERR_CORRUPT from the device-side CRC-32C check
+    (AppendOnlyStorageFormat_VerifyBlockChecksum / _VerifyHeaderChecksum, cdbappendonlystorageformat.c:1657-1720)"""
+    case = {c[0]: c for c in CASES}[name]
+    _, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = case
+    assert checksum
+    ctype, attlen, varkind, align = DECODE[typname]
+    rel = capi.DeviceRelation(ctx, len(values), [ctype], dscales=[dscale])
+    rng = np.random.default_rng(len(raw))
+    spots = {16, len(raw) - 1, len(raw) // 2, 8, 12} | set(int(x) for x in rng.integers(16, len(raw), 6))
+    for pos in sorted(spots):
+        if pos < 8:
+            continue
+        bad = bytearray(raw)
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        with pytest.raises(capi.CbgpuError) as e:
+            rel.load_aocs_column(0, bytes(bad), checksum, attlen, varkind, align)
+        # a flip inside a header's length bits may already stop the host-side block walk (invalid file)
+        assert e.value.code in (-6, -2), (pos, e.value)
+    # the untouched file still loads afterwards: the error state does not stick
+    assert rel.load_aocs_column(0, raw, checksum, attlen, varkind, align) == len(values)
+    got, gotnull = rel.read_column(0)
+    keep = nulls == 0
+    if typname == "float8":
+        assert np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64))
+    else:
+        assert np.array_equal(got[keep].astype(np.int64), values[keep])
+    rel.free()
+
+
 def test_query_over_decoded_files(ctx, oracle):
     """scan + aggregate over a relation whose columns came from reference-written column files"""
     by = {c[0]: c for c in CASES}

@@ -32,9 +32,11 @@ def main():
         got = rel.load_aocs_column(0, big, checksum, attlen, varkind, align)
         tr = ctx.trace_end()
         ms = sum(m for nme, m in tr if nme == "k_aocs_decode")
+        vms = sum(m for nme, m in tr if nme == "k_aocs_verify")
         assert got == n
-        print("%-30s %8.1f MB file  %10d rows  kernel %7.3f ms  %7.1f GB/s of file  %7.2f G rows/s  (%d blocks)" %
-              (name, len(big) / 1e6, n, ms, len(big) / ms / 1e6, n / ms / 1e6, nblocks * k))
+        print("%-30s %8.1f MB file  %10d rows  kernel %7.3f ms  %7.1f GB/s of file  %7.2f G rows/s  (%d blocks)  crc32c %s" %
+              (name, len(big) / 1e6, n, ms, len(big) / ms / 1e6, n / ms / 1e6, nblocks * k,
+               "%.3f ms %.1f GB/s" % (vms, len(big) / vms / 1e6) if vms else "off"))
         rel.free()
     ctx.close()
 
