@@ -155,6 +155,7 @@ def gpu():
             "cbgpu_gen_customer": (C.c_int, [vp, vp, u64]),
             "cbgpu_gen_supplier": (C.c_int, [vp, vp, u64]),
             "cbgpu_aocs_decode_column": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, vp, i32, i64, C.POINTER(i64)]),
+            "cbgpu_aocs_decode_column_ex": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, i32, vp, i32, i64, C.POINTER(i64)]),
             "cbgpu_gen_customer_range": (C.c_int, [vp, vp, u64, i64]),
             "cbgpu_gen_supplier_range": (C.c_int, [vp, vp, u64, i64]),
         }
@@ -381,13 +382,13 @@ class DeviceRelation:
         if sync:
             self.ctx.sync()
 
-    def load_aocs_column(self, col, file_bytes, checksum, attlen, varkind=0, typalign=4, row_offset=0):
-        """Decode one column's AOCS segment-file bytes on the device into this relation (cbgpu_aocs_decode_column);
-        returns the number of rows the file held."""
+    def load_aocs_column(self, col, file_bytes, checksum, attlen, varkind=0, typalign=4, row_offset=0, compresstype=0):
+        """Decode one column's AOCS segment-file bytes on the device into this relation (cbgpu_aocs_decode_column_ex);
+        compresstype 1 = zlib bulk compression.  Returns the number of rows the file held."""
         buf = np.frombuffer(file_bytes, dtype=np.uint8)
         n = C.c_int64()
-        self.ctx.check(self.ctx.L.cbgpu_aocs_decode_column(self.ctx.h, buf.ctypes.data, len(buf), 1 if checksum else 0, attlen, varkind,
-                                                           typalign, self.h, col, row_offset, C.byref(n)))
+        self.ctx.check(self.ctx.L.cbgpu_aocs_decode_column_ex(self.ctx.h, buf.ctypes.data, len(buf), 1 if checksum else 0, compresstype,
+                                                              attlen, varkind, typalign, self.h, col, row_offset, C.byref(n)))
         return int(n.value)
 
     def load_column_ptr(self, col, host_ptr):

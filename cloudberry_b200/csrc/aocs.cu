@@ -40,6 +40,7 @@
  * large-content blocks are refused with CBGPU_ERR_UNSUPPORTED, never guessed at.
  */
 #include "common.cuh"
+#include "inflate.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -47,9 +48,10 @@
 struct AocsDir
 {
 	long long	hoff;			/* storage block header offset in the file                            */
-	int32_t		overall;		/* header + firstRowNum + content rounded up                          */
-	int32_t		pad;
-	long long	off;			/* content offset in the file                                         */
+	int32_t		overall;		/* header + firstRowNum + stored content rounded up                   */
+	int32_t		clen;			/* compressed length of the stored content, 0 = stored as is          */
+	long long	zoff;			/* compressed content offset in the file (clen > 0)                   */
+	long long	off;			/* content offset: in the file, or in the inflate area behind it      */
 	long long	rowbase;		/* first output row of the block                                      */
 	int32_t		rows;
 	int32_t		dlen;
@@ -241,6 +243,181 @@ k_aocs_verify(const uint8_t *raw, const AocsDir *dir, int nblocks, int *status)
 				hc = tab[(hc ^ h[i]) & 0xffu] ^ (hc >> 8);
 			if (hc != stored_header || crc != stored_block)
 				atomicExch(status, CBGPU_ERR_CORRUPT);
+		}
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Bulk-compressed blocks (compresstype=zlib; rle_type compresslevel 2-4): AppendOnlyStorageRead_Content's
+ * gp_decompress step (cdbappendonlystorageread.c:1286-1310) on the device.  One warp per block: lane 0 runs the
+ * serial Huffman decoder of inflate.cuh into a 32-entry queue, then the warp applies the queue: output positions by a
+ * prefix sum over the entries' lengths; literals and matches whose source lies before the batch go in parallel (one
+ * entry per lane), matches that read this batch's own output follow in order, each copied by the whole warp.
+ * The result lands in the inflate area behind the file image (AocsDir.off), where k_aocs_decode reads it like a
+ * block that was stored uncompressed.  Length mismatch (gp_compress.c:73-79) or a bad stream / Adler-32
+ * (uncompress() -> Z_DATA_ERROR, pg_compression.c:342-365) raise CBGPU_ERR_CORRUPT.
+ * --------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ bool
+infl_apply_warp(uint8_t *out, uint32_t &outpos, uint32_t cap, const uint32_t *q, int n, int lane)
+{
+	const uint32_t e = lane < n ? q[lane] : 0u;
+	const bool	lit = (e & INFL_LIT) != 0;
+	const bool	match = lane < n && !lit;
+	const uint32_t len = lane < n ? (lit ? 1u : (e & 511u)) : 0u;
+	const uint32_t dist = (e >> 9) & 0xFFFFu;
+	uint32_t	incl = len;
+	bool		dep = false;
+
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+
+		if (lane >= d)
+			incl += v;
+	}
+	const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+	const uint32_t start = outpos + incl - len;
+
+	if (outpos + total > cap || __any_sync(0xffffffffu, match && dist > start))
+		return false;
+	if (lit)
+		out[start] = (uint8_t) e;
+	else if (match)
+	{
+		if (start - dist + len <= outpos)
+		{
+			const uint8_t *src = out + start - dist;
+
+			for (uint32_t i = 0; i < len; i++)
+				out[start + i] = src[i];
+		}
+		else
+			dep = true;
+	}
+	__syncwarp();
+	for (unsigned m = __ballot_sync(0xffffffffu, dep); m; m &= m - 1)
+	{
+		const int	k = __ffs(m) - 1;
+		const uint32_t s = __shfl_sync(0xffffffffu, start, k);
+		const uint32_t d = __shfl_sync(0xffffffffu, dist, k);
+		const uint32_t l = __shfl_sync(0xffffffffu, len, k);
+
+		for (uint32_t i = lane; i < l; i += 32)
+			out[s + i] = out[s - d + (d >= l ? i : i % d)];
+		__syncwarp();
+	}
+	outpos += total;
+	return true;
+}
+
+__device__ __forceinline__ uint32_t
+infl_adler32_warp(const uint8_t *d, uint32_t n, int lane)
+{
+	const uint32_t per = (n + 31u) / 32u;
+	const uint32_t lo = (uint32_t) lane * per < n ? (uint32_t) lane * per : n;
+	const uint32_t hi = lo + per < n ? lo + per : n;
+	uint64_t	a = 0,
+				b = 0;
+
+	for (uint32_t i = lo; i < hi; i++)
+	{
+		a += d[i];
+		b += a;
+	}
+	uint32_t	A = (uint32_t) (a % 65521u);
+	uint32_t	B = (uint32_t) ((b + a * (uint64_t) (n - hi)) % 65521u);
+
+	for (int o = 16; o; o >>= 1)
+	{
+		A += __shfl_xor_sync(0xffffffffu, A, o);
+		B += __shfl_xor_sync(0xffffffffu, B, o);
+	}
+	A = (1u + A) % 65521u;
+	B = (n % 65521u + B) % 65521u;
+	return (B << 16) | A;
+}
+
+__global__ void __launch_bounds__(AOCS_WARPS * 32)
+k_aocs_inflate(uint8_t *raw, const AocsDir *dir, int nblocks, int *status, int *anynull)
+{
+	__shared__ InflTables s_tab[AOCS_WARPS];
+	__shared__ uint32_t s_q[AOCS_WARPS][INFL_QN];
+	const int	lane = threadIdx.x & 31;
+	const int	w = threadIdx.x >> 5;
+	const int	nwarps = gridDim.x * AOCS_WARPS;
+
+	if (*status == CBGPU_ERR_CORRUPT)
+		return;
+	for (int b = blockIdx.x * AOCS_WARPS + w; b < nblocks; b += nwarps)
+	{
+		const AocsDir D = dir[b];
+
+		if (D.clen == 0)
+			continue;
+		const uint8_t *in = raw + D.zoff;
+		uint8_t    *out = raw + D.off;
+		const uint32_t cap = (uint32_t) D.dlen;
+		const uint32_t inlen = (uint32_t) D.clen;
+		uint32_t	outpos = 0;
+		InflState	st;
+		bool		ok = true;
+
+		infl_init(st, in, inlen, 2);
+		if (lane == 0)
+			ok = infl_zlib_header_ok(in, inlen);
+		ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+		while (ok)
+		{
+			int			n = 0,
+						rc = INFL_ERROR;
+
+			if (lane == 0)
+				rc = infl_step(st, s_tab[w], s_q[w], &n);
+			__syncwarp();
+			rc = __shfl_sync(0xffffffffu, rc, 0);
+			n = __shfl_sync(0xffffffffu, n, 0);
+			if (rc == INFL_ERROR || (n && !infl_apply_warp(out, outpos, cap, s_q[w], n, lane)))
+			{
+				ok = false;
+				break;
+			}
+			if (rc == INFL_STORED)
+			{
+				const uint32_t src = __shfl_sync(0xffffffffu, st.stored_src, 0);
+				const uint32_t len = __shfl_sync(0xffffffffu, st.stored_len, 0);
+
+				if (outpos + len > cap)
+				{
+					ok = false;
+					break;
+				}
+				for (uint32_t i = lane; i < len; i += 32)
+					out[outpos + i] = in[src + i];
+				outpos += len;
+				__syncwarp();
+			}
+			if (rc == INFL_DONE)
+				break;
+		}
+		if (ok)
+		{
+			const uint32_t c = __shfl_sync(0xffffffffu, infl_consumed(st), 0);
+
+			if (outpos != cap || c + 4u > inlen)
+				ok = false;
+			else
+			{
+				const uint32_t want = ((uint32_t) in[c] << 24) | ((uint32_t) in[c + 1] << 16) | ((uint32_t) in[c + 2] << 8) | (uint32_t) in[c + 3];
+
+				ok = infl_adler32_warp(out, cap, lane) == want;
+			}
+		}
+		if (lane == 0)
+		{
+			if (!ok)
+				atomicExch(status, CBGPU_ERR_CORRUPT);
+			else if (cap > 2 && (out[2] & 1u))	/* DSB_HAS_NULLBITMAP of the inflated datum stream block */
+				atomicOr(anynull, 1);
 		}
 	}
 }
@@ -666,17 +843,30 @@ extern "C" int
 cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t attlen, int32_t varkind,
 						 int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows_out)
 {
+	return cbgpu_aocs_decode_column_ex(ctx, file_bytes, nbytes, checksum, CBGPU_AOCS_COMPRESS_NONE, attlen, varkind, typalign, rel, col,
+									   row_offset, nrows_out);
+}
+
+extern "C" int
+cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t compress_kind,
+							int32_t attlen, int32_t varkind, int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset,
+							int64_t *nrows_out)
+{
 	const uint8_t *raw = (const uint8_t *) file_bytes;
 	AocsDir    *dir = NULL;
 	int64_t		ndir = 0,
 				capdir = 0,
 				pos = 0,
-				rows = 0;
+				rows = 0,
+				ztotal = 0,
+				ncompressed = 0;
 	bool		anynull = false;
+	int		   *d_flag = NULL;
 	AocsParams	P;
 	uint8_t    *d_raw = NULL;
 	AocsDir    *d_dir = NULL;
 	int			outw;
+	int			nblk;
 
 	*nrows_out = 0;
 	if (col < 0 || col >= rel->ncols)
@@ -702,6 +892,9 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 		memcpy(&w1, raw + pos + 4, 4);
 		kind = (int) ((w0 & 0x70000000u) >> 28);
 		has_first = (int) ((w0 & 0x08000000u) >> 27);
+		int			ext = 0;
+		int64_t		stored;
+
 		if (kind == 3)
 		{
 			/* AoHeaderKind_NonBulkDenseContent (cdbappendonlystorage_int.h:259-325): 30-bit row count */
@@ -711,21 +904,38 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 		}
 		else
 		{
+			/* SmallContent (:64-147) and BulkDenseContent (:350-466) share the length fields */
 			nrow = (int) ((w0 & 0x00FFFC00u) >> 10);
 			dlen = (int) (((w0 & 0x000003FFu) << 11) | ((w1 & 0xFFE00000u) >> 21));
 			clen = (int) (w1 & 0x001FFFFFu);
 		}
-		if ((w0 >> 31) != 0 || (kind != 1 /* AoHeaderKind_SmallContent */ && kind != 3) || clen != 0)
+		if ((w0 >> 31) != 0 || (kind != 1 /* AoHeaderKind_SmallContent */ && kind != 3 && kind != 4 /* BulkDenseContent */))
 		{
 			free(dir);
 			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED,
-						   "AOCS block at offset %s%lld is not an uncompressed SmallContent / NonBulkDenseContent block (bulk-compressed and large-content blocks are not decoded on the device)",
+						   "AOCS block at offset %s%lld is not a SmallContent / NonBulkDenseContent / BulkDenseContent block (large-content blocks are not decoded on the device)",
 						   "", pos);
 		}
-		hlen = 8 + (checksum ? 8 : 0) + (has_first ? 8 : 0);
-		if (pos + hlen + dlen > nbytes || dlen < 16)
+		if (kind == 4)
+		{
+			/* the extension header with the 30-bit row count follows the checksums (cdbappendonlystorageformat.c:1547-1640) */
+			ext = 8;
+			if (pos + 8 + (checksum ? 8 : 0) + 8 > nbytes)
+			{
+				free(dir);
+				return cb_fail(ctx, CBGPU_ERR_INVALID, "AOCS column file ends inside a block header%s (offset %lld)", "", pos);
+			}
+			memcpy(&w1, raw + pos + 8 + (checksum ? 8 : 0) + 4, 4);
+			nrow = (int) (w1 & 0x3FFFFFFFu);
+		}
+		hlen = 8 + (checksum ? 8 : 0) + ext + (has_first ? 8 : 0);
+		stored = clen ? clen : dlen;
+		if (pos + hlen + stored > nbytes || dlen < 16 || (clen && compress_kind != CBGPU_AOCS_COMPRESS_ZLIB))
 		{
 			free(dir);
+			if (clen && compress_kind != CBGPU_AOCS_COMPRESS_ZLIB && pos + hlen + stored <= nbytes)
+				return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED,
+							   "AOCS block at offset %s%lld is bulk-compressed, and not with zlib (zstd / quicklz blocks are not decoded on the device)", "", pos);
 			return cb_fail(ctx, CBGPU_ERR_INVALID, "AOCS block at offset %s%lld runs past the end of the file", "", pos);
 		}
 		if (ndir == capdir)
@@ -736,16 +946,28 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 				return CBGPU_ERR_NOMEM;
 		}
 		dir[ndir].hoff = pos;
-		dir[ndir].overall = (int32_t) (hlen + ((int64_t) dlen + 7) / 8 * 8);
-		dir[ndir].off = pos + hlen;
+		dir[ndir].overall = (int32_t) (hlen + (stored + 7) / 8 * 8);
+		dir[ndir].clen = clen;
+		dir[ndir].zoff = pos + hlen;
+		if (clen)
+		{
+			/* inflated behind the file image */
+			dir[ndir].off = (nbytes + 15) / 16 * 16 + ztotal;
+			ztotal += ((int64_t) dlen + 15) / 16 * 16;
+			ncompressed++;
+		}
+		else
+		{
+			dir[ndir].off = pos + hlen;
+			if (raw[pos + hlen + 2] & 1)	/* DSB_HAS_NULLBITMAP */
+				anynull = true;
+		}
 		dir[ndir].rowbase = row_offset + rows;
 		dir[ndir].rows = nrow;
 		dir[ndir].dlen = dlen;
 		ndir++;
-		if (raw[pos + hlen + 2] & 1)	/* DSB_HAS_NULLBITMAP */
-			anynull = true;
 		rows += nrow;
-		pos += hlen + ((int64_t) dlen + 7) / 8 * 8;
+		pos += hlen + (stored + 7) / 8 * 8;
 	}
 	if (row_offset < 0 || row_offset + rows > rel->capacity)
 	{
@@ -758,22 +980,51 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 		return CBGPU_OK;
 	}
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	CB_CUDA(ctx, cudaMallocAsync(&d_raw, (size_t) ((nbytes + 15) / 16 * 16 + ztotal + 16), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&d_dir, sizeof(AocsDir) * (size_t) ndir, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, (size_t) nbytes, cudaMemcpyHostToDevice, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(d_dir, dir, sizeof(AocsDir) * (size_t) ndir, cudaMemcpyHostToDevice, ctx->stream));
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, "aocs:h2d");
+	nblk = (int) ((ndir + AOCS_WARPS - 1) / AOCS_WARPS);
+	if (nblk > ctx->sm_count * 16)
+		nblk = ctx->sm_count * 16;
+	if (checksum)
+	{
+		/* AppendOnlyStorageRead verifies header and block checksums before handing a block on */
+		k_aocs_verify<<<nblk, AOCS_WARPS * 32, 0, ctx->stream>>>(d_raw, d_dir, (int) ndir, ctx->d_status);
+		CB_LAUNCHED(ctx, "k_aocs_verify");
+	}
+	if (ncompressed)
+	{
+		int			flag = 0;
+
+		CB_CUDA(ctx, cudaMallocAsync(&d_flag, sizeof(int), ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+		k_aocs_inflate<<<nblk, AOCS_WARPS * 32, 0, ctx->stream>>>(d_raw, d_dir, (int) ndir, ctx->d_status, d_flag);
+		CB_LAUNCHED(ctx, "k_aocs_inflate");
+		if (!anynull && !rel->nulls[col])
+		{
+			/* whether an inflated block carries a NULL bitmap is only known now */
+			CB_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			anynull = flag != 0;
+		}
+		CB_CUDA(ctx, cudaFreeAsync(d_flag, ctx->stream));
+	}
 	if (anynull && !rel->nulls[col])
 	{
 		int			rc = cbgpu_rel_add_nullmap(rel, col);
 
 		if (rc)
 		{
+			cudaStreamSynchronize(ctx->stream);
+			cudaFreeAsync(d_raw, ctx->stream);
+			cudaFreeAsync(d_dir, ctx->stream);
 			free(dir);
 			return rc;
 		}
 	}
-	CB_CUDA(ctx, cudaMallocAsync(&d_raw, (size_t) nbytes + 16, ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&d_dir, sizeof(AocsDir) * (size_t) ndir, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(d_raw, raw, (size_t) nbytes, cudaMemcpyHostToDevice, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(d_dir, dir, sizeof(AocsDir) * (size_t) ndir, cudaMemcpyHostToDevice, ctx->stream));
-	if (ctx->trace_on)
-		cb_trace_mark(ctx, "aocs:h2d");
 	memset(&P, 0, sizeof(P));
 	P.raw = d_raw;
 	P.dir = d_dir;
@@ -785,20 +1036,8 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 	P.out = rel->data[col];
 	P.outnull = rel->nulls[col];
 	P.status = ctx->d_status;
-	{
-		int			blocks = (int) ((ndir + AOCS_WARPS - 1) / AOCS_WARPS);
-
-		if (blocks > ctx->sm_count * 16)
-			blocks = ctx->sm_count * 16;
-		if (checksum)
-		{
-			/* AppendOnlyStorageRead verifies header and block checksums before handing a block on */
-			k_aocs_verify<<<blocks, AOCS_WARPS * 32, 0, ctx->stream>>>(d_raw, d_dir, (int) ndir, ctx->d_status);
-			CB_LAUNCHED(ctx, "k_aocs_verify");
-		}
-		k_aocs_decode<<<blocks, AOCS_WARPS * 32, 0, ctx->stream>>>(P);
-		CB_LAUNCHED(ctx, "k_aocs_decode");
-	}
+	k_aocs_decode<<<nblk, AOCS_WARPS * 32, 0, ctx->stream>>>(P);
+	CB_LAUNCHED(ctx, "k_aocs_decode");
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));	/* the caller's file buffer and `dir` are free again */
 	CB_CUDA(ctx, cudaFreeAsync(d_raw, ctx->stream));
 	CB_CUDA(ctx, cudaFreeAsync(d_dir, ctx->stream));

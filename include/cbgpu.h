@@ -360,15 +360,25 @@ int			cbgpu_motion_broadcast(cbgpu_motion *m, cbgpu_rel *send, int64_t nrows, cb
  * ------------------------------------------------------------------------------------------ */
 #define CBGPU_AOCS_VAR_NUMERIC 1	/* numeric varlena -> int64 scaled by the column's dscale             */
 #define CBGPU_AOCS_VAR_BPCHAR1 2	/* character(1) varlena -> its byte                                   */
+#define CBGPU_AOCS_COMPRESS_NONE 0	/* compresstype=none, or rle_type with compresslevel 1                */
+#define CBGPU_AOCS_COMPRESS_ZLIB 1	/* compresstype=zlib (any level), or rle_type with compresslevel 2-4   */
 /* file_bytes: one column's segment file (<relfilenode>.<n>) as it lies on disk, in host memory:
- * uncompressed SmallContent storage blocks holding Original datum stream blocks.  attlen = pg_type
- * typlen (1/2/4/8, or -1 with varkind), typalign in bytes.  Decodes into rows [row_offset, +nrows) of
- * column `col` (NULL bitmaps become the column's null map).  With checksum != 0 every block's header and
- * block CRC-32C are verified on the device first (CBGPU_ERR_CORRUPT), as the reference does on read
- * (AppendOnlyStorageFormat_VerifyHeaderChecksum / _VerifyBlockChecksum).  Other block kinds: CBGPU_ERR_UNSUPPORTED. */
+ * SmallContent / NonBulkDenseContent / BulkDenseContent storage blocks holding Original or Dense (RLE, delta)
+ * datum stream blocks.  attlen = pg_type typlen (1/2/4/8, or -1 with varkind), typalign in bytes.  Decodes into
+ * rows [row_offset, +nrows) of column `col` (NULL bitmaps become the column's null map).  With checksum != 0 every
+ * block's header and block CRC-32C are verified on the device first (CBGPU_ERR_CORRUPT), as the reference does on
+ * read (AppendOnlyStorageFormat_VerifyHeaderChecksum / _VerifyBlockChecksum).  LargeContent blocks:
+ * CBGPU_ERR_UNSUPPORTED.  Bulk-compressed blocks need the _ex entry point with the column's compresstype. */
 int			cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum,
 									 int32_t attlen, int32_t varkind, int32_t typalign, cbgpu_rel *rel, int32_t col,
 									 int64_t row_offset, int64_t *nrows);
+/* The same for a column stored with bulk compression (pg_attribute_encoding compresstype; gp_decompress,
+ * cdb/cdbappendonlystorageread.c:1286-1310): blocks whose header carries a compressed length are inflated on the
+ * device (zlib streams as catalog/pg_compression.c:272 writes them with compress2()); a bad stream, a wrong
+ * Adler-32 or a length other than the header's is CBGPU_ERR_CORRUPT.  zstd: CBGPU_ERR_UNSUPPORTED. */
+int			cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum,
+										int32_t compresstype, int32_t attlen, int32_t varkind, int32_t typalign,
+										cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows);
 
 /* ------------------------------------------------------------------------------------------
  * synthetic TPC-H shaped generator (harness; same counter-based formulas as

@@ -130,6 +130,9 @@ def ref_lib():
         L.ref_aocs_write_column_ex.restype = C.c_int64
         L.ref_aocs_write_column_ex.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                                                C.POINTER(C.c_int64)]
+        L.ref_aocs_write_column_z.restype = C.c_int64
+        L.ref_aocs_write_column_z.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                                              C.POINTER(C.c_int64)]
         L.ref_aocs_last_error.restype = C.c_char_p
         L.ref_numeric_inspect.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.c_void_p, C.c_int]
@@ -140,7 +143,9 @@ def ref_lib():
     return _REF
 
 
-def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768, dscale=0, rle=False):
+def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768, dscale=0, rle=False, zlevel=0):
+    # zlevel: zlib level of the storage layer's bulk compression (compresstype=zlib compresslevel=zlevel; with rle:
+    # rle_type compresslevel 2 / 3 / 4 = zlevel 1 / 5 / 9), 0 = none
     # rle: False / 0 plain, True / 1 rle_type, 2 rle_type with delta range encoding (what the reference picks for
     # int4 / int8 / date columns under rle_type)
     """Column file bytes as the reference's insert path writes them.  values: ints / floats (by-value types), scaled
@@ -174,7 +179,7 @@ def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768
     out = (C.c_ubyte * cap)()
     nb = C.c_int64()
     vb = (C.c_ubyte * max(len(varbuf), 1)).from_buffer_copy(varbuf or b"\0")
-    r = L.ref_aocs_write_column_ex(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize, int(rle),
+    r = L.ref_aocs_write_column_z(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize, int(rle), int(zlevel),
                                    vals.ctypes.data, C.addressof(vb), nl.ctypes.data if nl is not None else None, n,
                                    C.addressof(out), cap, C.byref(nb))
     if r < 0:
@@ -214,8 +219,10 @@ def verify_block_checksums(raw, pos, overall):
         raise ValueError("block at %d: block checksum does not match" % pos)
 
 
-def walk_blocks(raw, checksum, verify=False):
-    """[(content offset, content length, row count, first row number)] of a column file"""
+def walk_blocks_ex(raw, checksum, verify=False):
+    """every storage block of a column file: dict(hoff, hlen, off, dlen, clen, rows, first, kind); clen > 0 = the content
+    is stored bulk-compressed in clen bytes (AppendOnlyStorageFormat_GetSmallContentHeaderInfo /
+    _GetBulkDenseContentHeaderInfo, cdbappendonlystorageformat.c:1327-1400, 1480-1560)"""
     out = []
     pos = 0
     n = len(raw)
@@ -224,25 +231,56 @@ def walk_blocks(raw, checksum, verify=False):
         w1 = int.from_bytes(raw[pos + 4:pos + 8], "little")
         kind = (w0 & 0x70000000) >> 28
         has_first = (w0 & 0x08000000) >> 27
-        if kind == 1:           # SmallContent
+        hlen = 8 + (8 if checksum else 0)
+        clen = 0
+        if kind in (1, 4):      # SmallContent / BulkDenseContent: same length fields
             rows = (w0 & 0x00FFFC00) >> 10
             dlen = ((w0 & 0x3FF) << 11) | ((w1 & 0xFFE00000) >> 21)
-            if w1 & 0x001FFFFF:
-                raise ValueError("compressed block")
+            clen = w1 & 0x001FFFFF
+            if kind == 4:       # extension header behind the checksums: 30-bit row count
+                rows = int.from_bytes(raw[pos + hlen + 4:pos + hlen + 8], "little") & 0x3FFFFFFF
+                hlen += 8
         elif kind == 3:         # NonBulkDenseContent: 30-bit row count
             dlen = w0 & 0x001FFFFF
             rows = w1 & 0x3FFFFFFF
         else:
-            raise ValueError("block at %d: header kind %d is neither SmallContent nor NonBulkDenseContent" % (pos, kind))
-        hlen = 8 + (8 if checksum else 0)
+            raise ValueError("block at %d: header kind %d is not SmallContent / NonBulkDenseContent / BulkDenseContent" % (pos, kind))
         first = -1
         if has_first:
             first = int.from_bytes(raw[pos + hlen:pos + hlen + 8], "little", signed=True)
             hlen += 8
+        stored = clen if clen else dlen
         if verify and checksum:
-            verify_block_checksums(raw, pos, hlen + (dlen + 7) // 8 * 8)
-        out.append((pos + hlen, dlen, rows, first))
-        pos += hlen + (dlen + 7) // 8 * 8
+            verify_block_checksums(raw, pos, hlen + (stored + 7) // 8 * 8)
+        out.append(dict(hoff=pos, hlen=hlen, off=pos + hlen, dlen=dlen, clen=clen, rows=rows, first=first, kind=kind))
+        pos += hlen + (stored + 7) // 8 * 8
+    return out
+
+
+def walk_blocks(raw, checksum, verify=False):
+    """[(content offset, content length, row count, first row number)] of an uncompressed column file"""
+    out = []
+    for b in walk_blocks_ex(raw, checksum, verify):
+        if b["clen"]:
+            raise ValueError("compressed block")
+        out.append((b["off"], b["dlen"], b["rows"], b["first"]))
+    return out
+
+
+def block_contents(raw, checksum, verify=False):
+    """[(datum stream block bytes, row count)]: AppendOnlyStorageRead_Content (cdbappendonlystorageread.c:1136-1320):
+    the stored bytes, or for a bulk-compressed block what zlib's uncompress() makes of them (zlib_decompress,
+    catalog/pg_compression.c:321-370; gp_decompress checks the length, storage/file/gp_compress.c:52-90)"""
+    import zlib
+    out = []
+    for b in walk_blocks_ex(raw, checksum, verify):
+        if b["clen"]:
+            blk = zlib.decompress(bytes(raw[b["off"]:b["off"] + b["clen"]]))
+            if len(blk) != b["dlen"]:
+                raise ValueError("block at %d: inflated to %d bytes, header says %d" % (b["hoff"], len(blk), b["dlen"]))
+        else:
+            blk = raw[b["off"]:b["off"] + b["dlen"]]
+        out.append((blk, b["rows"]))
     return out
 
 
@@ -287,8 +325,7 @@ class _Datums:
 def decode_column(raw, typname, checksum, dscale=0):
     """(values, nulls): numeric -> scaled int64, bpchar -> first byte, fixed width -> the value"""
     vals, nulls = [], []
-    for off, dlen, rows, first in walk_blocks(raw, checksum):
-        blk = raw[off:off + dlen]
+    for blk, rows in block_contents(raw, checksum):
         version, flags = int.from_bytes(blk[0:2], "little", signed=True), int.from_bytes(blk[2:4], "little")
         if version == 0:
             # DatumStreamBlock_Orig

@@ -21,6 +21,7 @@
 
 #include <setjmp.h>
 #include <stdarg.h>
+#include <zlib.h>
 
 #include "catalog/pg_appendonly.h"
 #include "cdb/cdbappendonlystorage.h"
@@ -201,6 +202,9 @@ ref_numeric_inspect(const unsigned char *varlena4, int *sign, int *dscale, int *
 int64		ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle,
 									 const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
 									 unsigned char *out, int64 outcap, int64 *nblocks_out);
+int64		ref_aocs_write_column_z(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle,
+									int zlevel, const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
+									unsigned char *out, int64 outcap, int64 *nblocks_out);
 
 /*
  * Write one column.  `values`: by-value datums (attlen 1/2/4/8), or for attlen -1 offsets into
@@ -226,6 +230,23 @@ ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storag
 						 const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
 						 unsigned char *out, int64 outcap, int64 *nblocks_out)
 {
+	return ref_aocs_write_column_z(typid, attlen, byval, align, storage, checksum, blocksize, rle, 0, values, varbuf, nulls, n, out,
+								   outcap, nblocks_out);
+}
+
+/* zlevel > 0: bulk compression by the storage layer, restating AppendOnlyStorageWrite_CompressAppend
+ * (cdbappendonlystoragewrite.c:1015-1160; that file needs the backend's file layer and is not compiled here):
+ * the content goes through zlib's compress2() exactly as zlib_compress does (catalog/pg_compression.c:272-318, with
+ * Z_BUF_ERROR meaning "did not fit: store as is"), is kept compressed only when shorter than the source, and the
+ * REFERENCE's own header makers record the compressed length.  Dense blocks beyond 16383 rows take the
+ * BulkDenseContent header when bulk compression is on (datumstreamwrite_block_dense, datumstream.c:944-956).
+ * compresstype=zlib, compresslevel=L: rle 0, zlevel L.  rle_type compresslevel 2 / 3 / 4: rle 1|2, zlevel 1 / 5 / 9
+ * (init_datumstream_info, datumstream.c:412-436). */
+int64
+ref_aocs_write_column_z(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle, int zlevel,
+						const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
+						unsigned char *out, int64 outcap, int64 *nblocks_out)
+{
 	DatumStreamBlockWrite dsw;
 	DatumStreamTypeInfo ti;
 	RelFileNode node;
@@ -235,6 +256,7 @@ ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storag
 	int64		first_row = 1;
 	int64		nblocks = 0;
 	unsigned char *blockbuf = malloc((size_t) blocksize + 64);
+	unsigned char *contentbuf = malloc((size_t) blocksize + 64);
 
 	memset(&node, 0, sizeof(node));
 	memset(&dsw, 0, sizeof(dsw));
@@ -265,25 +287,51 @@ ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storag
 		int			rowCount = DatumStreamBlockWrite_Nth(&dsw); \
 		int64		contentLen; \
 		int32		rounded; \
+		int32		compressedLen = 0; \
 		if (rowCount > 0) \
 		{ \
+			const int	bulk = rowCount > AOSmallContentHeader_MaxRowCount && zlevel > 0; \
+			const int	hl = hdrlen + (bulk ? AoHeader_RegularSize : 0);	/* + the extension header */ \
 			memset(blockbuf, 0, (size_t) blocksize + 64); \
-			contentLen = DatumStreamBlockWrite_Block(&dsw, blockbuf + hdrlen, &node); \
-			rounded = AOStorage_RoundUp((int32) contentLen, version); \
+			contentLen = DatumStreamBlockWrite_Block(&dsw, contentbuf, &node); \
+			if (zlevel > 0) \
+			{ \
+				unsigned long used = (unsigned long) (blocksize - hl); \
+				int			zrc = compress2(blockbuf + hl, &used, contentbuf, (unsigned long) contentLen, zlevel); \
+				compressedLen = zrc == Z_OK ? (int32) used : (int32) contentLen; \
+				if (zrc != Z_OK && zrc != Z_BUF_ERROR) \
+				{ \
+					snprintf(ref_errbuf, sizeof(ref_errbuf), "compress2 failed: %d", zrc); \
+					free(blockbuf); free(contentbuf); \
+					return -1; \
+				} \
+			} \
+			if (zlevel <= 0 || compressedLen >= contentLen) \
+			{ \
+				memset(blockbuf + hl, 0, (size_t) blocksize + 64 - hl); \
+				memcpy(blockbuf + hl, contentbuf, (size_t) contentLen); \
+				compressedLen = 0; \
+			} \
+			rounded = AOStorage_RoundUp(compressedLen ? compressedLen : (int32) contentLen, version); \
+			memset(blockbuf + hl + (compressedLen ? compressedLen : (int32) contentLen), 0, \
+				   (size_t) (rounded - (compressedLen ? compressedLen : (int32) contentLen))); \
 			if (rowCount <= AOSmallContentHeader_MaxRowCount) \
 				AppendOnlyStorageFormat_MakeSmallContentHeader(blockbuf, checksum != 0, true, version, first_row, 1 /* AOCSBK_BLOCK */, \
-															   rowCount, (int32) contentLen, 0); \
+															   rowCount, (int32) contentLen, compressedLen); \
+			else if (bulk) \
+				AppendOnlyStorageFormat_MakeBulkDenseContentHeader(blockbuf, checksum != 0, true, version, first_row, 1, \
+																   rowCount, (int32) contentLen, compressedLen); \
 			else \
 				AppendOnlyStorageFormat_MakeNonBulkDenseContentHeader(blockbuf, checksum != 0, true, version, first_row, 1, \
 																	  rowCount, (int32) contentLen); \
-			if (pos + hdrlen + rounded > outcap) \
+			if (pos + hl + rounded > outcap) \
 			{ \
 				snprintf(ref_errbuf, sizeof(ref_errbuf), "output buffer too small"); \
-				free(blockbuf); \
+				free(blockbuf); free(contentbuf); \
 				return -1; \
 			} \
-			memcpy(out + pos, blockbuf, (size_t) hdrlen + (size_t) rounded); \
-			pos += hdrlen + rounded; \
+			memcpy(out + pos, blockbuf, (size_t) hl + (size_t) rounded); \
+			pos += hl + rounded; \
 			first_row += rowCount; \
 			nblocks++; \
 			DatumStreamBlockWrite_GetReady(&dsw); \
@@ -315,12 +363,22 @@ ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storag
 	FLUSH();
 	DatumStreamBlockWrite_Finish(&dsw);
 	free(blockbuf);
+	free(contentbuf);
 	if (nblocks_out)
 		*nblocks_out = nblocks;
 	return pos;
 }
 
-/* parse one storage block header with the reference's own accessor (for cross-checking a walker) */
+/* compressed length of the block ref_aocs_block_info looked at last (0 = stored as is) */
+static int32 ref_last_compressed_len;
+
+int
+ref_aocs_last_compressed_len(void)
+{
+	return ref_last_compressed_len;
+}
+
+/* parse one storage block header with the reference's own accessors (for cross-checking a walker) */
 int
 ref_aocs_block_info(const unsigned char *hdr, int checksum, int *header_len, int *row_count, int *data_len, int64 *first_row,
 					int *header_kind)
@@ -342,10 +400,24 @@ ref_aocs_block_info(const unsigned char *hdr, int checksum, int *header_len, int
 	e = AppendOnlyStorageFormat_GetHeaderInfo((uint8 *) hdr, checksum != 0, header_kind, &hlen);
 	if (e != AOHeaderCheckOk)
 		return -2;
-	e = AppendOnlyStorageFormat_GetSmallContentHeaderInfo((uint8 *) hdr, hlen, checksum != 0, 1 << 21, &overall, &offset, &uncompressed,
-														  &exec_kind, &has_first, version, &fr, &rc, (bool *) &compressed, &compressed);
+	{
+		bool		is_compressed = false;
+
+		if (*header_kind == AoHeaderKind_NonBulkDenseContent)
+			e = AppendOnlyStorageFormat_GetNonBulkDenseContentHeaderInfo((uint8 *) hdr, hlen, checksum != 0, 1 << 21, &overall, &offset,
+																		 &uncompressed, &exec_kind, &has_first, version, &fr, &rc);
+		else if (*header_kind == AoHeaderKind_BulkDenseContent)
+			e = AppendOnlyStorageFormat_GetBulkDenseContentHeaderInfo((uint8 *) hdr, hlen, checksum != 0, 1 << 21, &overall, &offset,
+																	  &uncompressed, &exec_kind, &has_first, version, &fr, &rc,
+																	  &is_compressed, &compressed);
+		else
+			e = AppendOnlyStorageFormat_GetSmallContentHeaderInfo((uint8 *) hdr, hlen, checksum != 0, 1 << 21, &overall, &offset,
+																  &uncompressed, &exec_kind, &has_first, version, &fr, &rc,
+																  &is_compressed, &compressed);
+	}
 	if (e != AOHeaderCheckOk)
 		return -3;
+	ref_last_compressed_len = compressed;
 	*header_len = offset;
 	*row_count = rc;
 	*data_len = uncompressed;

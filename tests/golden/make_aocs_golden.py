@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Write tests/golden/aocs_columns.npz: AOCS column files produced by the REFERENCE's own block writer
+"""Write tests/golden/aocs_columns.npz (and aocs_zlib_columns.npz, bulk-compressed columns): AOCS column files produced by the REFERENCE's own block writer
 (oracle/_ref/libaocs_ref.so = the reference's datumstreamblock.c + cdbappendonlystorageformat.c + pg_crc32c_sb8.c,
 driven by oracle/ref_aocs.c; run `make -C oracle` first) together with the values that went in.
 
@@ -21,8 +21,8 @@ def main():
     out = {}
     cases = []
 
-    def add(name, typname, values, nulls, checksum, blocksize, dscale=0, rle=False):
-        raw, nblocks = A.ref_write_column(typname, values, nulls, checksum, blocksize, dscale, rle=rle)
+    def add(name, typname, values, nulls, checksum, blocksize, dscale=0, rle=False, zlevel=0):
+        raw, nblocks = A.ref_write_column(typname, values, nulls, checksum, blocksize, dscale, rle=rle, zlevel=zlevel)
         out[name + "__raw"] = np.frombuffer(raw, dtype=np.uint8)
         if typname == "bpchar":
             out[name + "__values"] = np.array([ord(v[0]) if v else 32 for v in values], dtype=np.int64)
@@ -31,7 +31,10 @@ def main():
         else:
             out[name + "__values"] = np.asarray(values, dtype=np.int64)
         out[name + "__nulls"] = np.zeros(len(values), dtype=np.uint8) if nulls is None else np.asarray(nulls, dtype=np.uint8)
-        cases.append("%s|%s|%d|%d|%d|%d" % (name, typname, 1 if checksum else 0, blocksize, dscale, nblocks))
+        if zlevel:
+            cases.append("%s|%s|%d|%d|%d|%d|%d" % (name, typname, 1 if checksum else 0, blocksize, dscale, nblocks, zlevel))
+        else:
+            cases.append("%s|%s|%d|%d|%d|%d" % (name, typname, 1 if checksum else 0, blocksize, dscale, nblocks))
 
     n = 20011
     nul = (rng.random(n) < 0.07).astype(np.uint8)
@@ -79,6 +82,42 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes,", len(cases), "columns")
     for c in cases:
         print("  ", c)
+
+    # ---- bulk compression: compresstype=zlib compresslevel=L, and rle_type compresslevel 2 / 3 / 4 (= RLE + zlib 1 / 5 / 9)
+    out = {}
+    cases = []
+    rng = np.random.default_rng(20260923)
+    n = 20011
+    nul = (rng.random(n) < 0.07).astype(np.uint8)
+    add("zlib1_int4_sorted", "int4", np.cumsum(rng.integers(0, 4, n)) - 10**6, None, True, 32768, zlevel=1)
+    add("zlib5_numeric_price", "numeric", rng.integers(90000, 10500000, n), None, True, 32768, dscale=2, zlevel=5)
+    add("zlib9_bpchar1_flags_nulls", "bpchar", [("A", "N", "R", "F", "O")[i] for i in rng.integers(0, 5, n)], nul, True, 32768, zlevel=9)
+    # incompressible: compress2 makes it longer, the writer stores those blocks as they are (compressed length 0)
+    add("zlib1_int8_random_stored", "int8", rng.integers(-2**62, 2**62, 6000), None, True, 32768, zlevel=1)
+    add("zlib6_float8_nulls_8k_nocrc", "float8", np.round(rng.normal(0, 50, n)), nul, False, 8192, zlevel=6)
+    # large blocks: 16383 rows of int8 per block, matches reaching far back, several deflate blocks per stream
+    big = np.tile(rng.integers(-2**40, 2**40, 2500), 14)[:33000] + np.repeat(np.arange(33), 1000)
+    add("zlib6_int8_bigblocks", "int8", big, None, True, 2097152, zlevel=6)
+    add("zlib3_date_mixed", "date", np.where(rng.random(n) < 0.3, rng.integers(-3000, 9000, n), 7305), nul, True, 32768, zlevel=3)
+    add("zlib1_int4_tiny_stored", "int4", [7], None, True, 32768, zlevel=1)
+    add("zlib9_bool_allnull", "bool", [0] * 5000, [1] * 5000, True, 8192, zlevel=9)
+    # rle_type compresslevel 2: one 40000-row run -> a Dense block of more than 16383 rows -> BulkDenseContent header
+    add("rle2_numeric_long_run", "numeric", np.concatenate([np.full(40000, 12345), rng.integers(100, 10**7, 3000), np.full(20000, -5),
+                                                               np.repeat(rng.integers(0, 11, 500), rng.integers(1, 9, 500))]),
+        None, True, 32768, dscale=2, rle=True, zlevel=1)
+    add("rle3_date_delta_nulls", "date", np.cumsum(rng.integers(0, 3, 30000)) - 500, (rng.random(30000) < 0.03).astype(np.uint8), True, 32768,
+        rle=2, zlevel=5)
+    add("rle4_float8_runs_8k_nocrc", "float8", np.repeat(rng.normal(0, 1e3, 900), rng.integers(1, 60, 900)), None, False, 8192, rle=True, zlevel=9)
+    out["cases"] = np.array(cases)
+    path = os.path.join(ROOT, "tests", "golden", "aocs_zlib_columns.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(cases), "columns")
+    for c in cases:
+        print("  ", c)
+        name = c.split("|")[0]
+        blocks = A.walk_blocks_ex(bytes(out[name + "__raw"]), int(c.split("|")[2]))
+        print("      kinds", sorted(set(b["kind"] for b in blocks)), "compressed", sum(1 for b in blocks if b["clen"]), "of", len(blocks),
+              "file", len(out[name + "__raw"]), "bytes for", sum(b["dlen"] for b in blocks), "of content")
 
 
 if __name__ == "__main__":

@@ -27,6 +27,18 @@ def golden():
 CASES = list(golden())
 
 
+def golden_zlib():
+    """bulk-compressed columns (compresstype=zlib, rle_type compresslevel 2-4): the same tuple + the zlib level"""
+    d = np.load(os.path.join(HERE, "golden", "aocs_zlib_columns.npz"))
+    for c in d["cases"]:
+        name, typname, checksum, blocksize, dscale, nblocks, zlevel = str(c).split("|")
+        yield (name, typname, int(checksum), int(blocksize), int(dscale), int(nblocks), bytes(d[name + "__raw"]),
+               d[name + "__values"], d[name + "__nulls"], int(zlevel))
+
+
+ZCASES = list(golden_zlib())
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_restated_reader_reads_reference_written_columns(case):
     name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = case
@@ -59,6 +71,43 @@ def test_walker_against_reference_header_accessors(case):
         assert (hl.value, rc.value, dl.value, fr.value, kind.value) == (hlen_guess, rows, dlen, first, 1)
         if checksum:
             assert L.ref_aocs_verify_block(hdr, hlen_guess + (dlen + 7) // 8 * 8) == 0
+
+
+@pytest.mark.parametrize("case", ZCASES, ids=[c[0] for c in ZCASES])
+def test_restated_reader_reads_bulk_compressed_columns(case):
+    name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel = case
+    blocks = A.walk_blocks_ex(raw, checksum, verify=True)
+    assert len(blocks) == nblocks and sum(b["rows"] for b in blocks) == len(values)
+    assert blocks[0]["first"] == 1 and all(blocks[i + 1]["first"] == blocks[i]["first"] + blocks[i]["rows"] for i in range(nblocks - 1))
+    # the writer keeps a block compressed only when that is shorter (AppendOnlyStorageWrite_CompressAppend :1079-1096)
+    assert all(b["clen"] < b["dlen"] for b in blocks)
+    assert ("stored" in name) == all(b["clen"] == 0 for b in blocks)
+    # more than 16383 rows in a bulk-compressed Dense block -> BulkDenseContent header
+    assert all((b["kind"] == 4) == (b["rows"] > 16383) for b in blocks)
+    got, gotnull = A.decode_column(raw, typname, checksum, dscale)
+    assert np.array_equal(gotnull, nulls)
+    keep = nulls == 0
+    if typname == "float8":
+        assert np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64))
+    else:
+        assert np.array_equal(got[keep], values[keep])
+
+
+@pytest.mark.skipif(A.ref_lib() is None, reason="reference library only where /root/reference exists")
+def test_bulk_header_fields_against_reference_accessors():
+    L = A.ref_lib()
+    for name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel in ZCASES:
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        for b in A.walk_blocks_ex(raw, checksum):
+            hl, rc, dl, kind = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            fr = C.c_int64()
+            assert L.ref_aocs_block_info(C.addressof(buf) + b["hoff"], checksum, C.byref(hl), C.byref(rc), C.byref(dl), C.byref(fr),
+                                         C.byref(kind)) == 0, name
+            assert (hl.value, rc.value, dl.value, fr.value, kind.value) == (b["hlen"], b["rows"], b["dlen"], b["first"], b["kind"]), name
+            assert L.ref_aocs_last_compressed_len() == b["clen"]
+            if checksum:
+                stored = b["clen"] or b["dlen"]
+                assert L.ref_aocs_verify_block(C.addressof(buf) + b["hoff"], b["hlen"] + (stored + 7) // 8 * 8) == 0
 
 
 def test_checksum_restatement_on_reference_written_files():

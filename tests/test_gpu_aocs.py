@@ -5,7 +5,7 @@ import pytest
 
 from cloudberry_b200 import capi
 from cloudberry_b200 import plan as P
-from test_aocs_format import CASES
+from test_aocs_format import CASES, ZCASES
 
 pytestmark = pytest.mark.gpu
 
@@ -80,6 +80,61 @@ def test_checksum_failure_is_reported(ctx, name):
         assert np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64))
     else:
         assert np.array_equal(got[keep].astype(np.int64), values[keep])
+    rel.free()
+
+
+@pytest.mark.parametrize("case", ZCASES, ids=[c[0] for c in ZCASES])
+def test_device_inflates_bulk_compressed_columns(ctx, case):
+    """compresstype=zlib / rle_type compresslevel 2-4 column files, written through the reference's header makers and the
+    system zlib: inflated (k_aocs_inflate), then decoded like stored blocks"""
+    name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel = case
+    ctype, attlen, varkind, align = DECODE[typname]
+    rel = capi.DeviceRelation(ctx, len(values) + 5, [ctype], dscales=[dscale])
+    n = rel.load_aocs_column(0, raw, checksum, attlen, varkind, align, row_offset=5, compresstype=1)
+    assert n == len(values)
+    got, gotnull = rel.read_column(0, 5, 5 + n)
+    assert np.array_equal(gotnull.astype(np.uint8), nulls)
+    keep = nulls == 0
+    if typname == "float8":
+        assert np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64))
+    else:
+        assert np.array_equal(got[keep].astype(np.int64), values[keep])
+    # a column that turned out to hold no NULL keeps no null map, one with NULLs has one
+    assert bool(rel.ctx.L.cbgpu_rel_has_nulls(rel.h, 0)) == bool(nulls.any())
+    if "stored" not in name:
+        # without the column's compresstype the compressed blocks are refused, not misread
+        with pytest.raises(capi.CbgpuError) as e:
+            rel.load_aocs_column(0, raw, checksum, attlen, varkind, align)
+        assert e.value.code == -3
+    rel.free()
+
+
+@pytest.mark.parametrize("name", ["zlib5_numeric_price", "zlib6_float8_nulls_8k_nocrc", "zlib6_int8_bigblocks", "rle2_numeric_long_run",
+                                  "rle4_float8_runs_8k_nocrc"])
+def test_damaged_compressed_blocks_are_reported(ctx, name):
+    """flipped bits inside compressed content: with checksums the CRC catches them, without, the inflater does (bad
+    Huffman code, distance before the start, wrong length, Adler-32) -- as uncompress() / gp_decompress would"""
+    case = {c[0]: c for c in ZCASES}[name]
+    _, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel = case
+    ctype, attlen, varkind, align = DECODE[typname]
+    rel = capi.DeviceRelation(ctx, len(values), [ctype], dscales=[dscale])
+    rng = np.random.default_rng(len(raw) + 1)
+    hdr = 8 + (8 if checksum else 0) + 16
+    for pos in [hdr, hdr + 1, hdr + 2, len(raw) - 9] + [int(x) for x in rng.integers(hdr + 3, len(raw) - 8, 12)]:
+        bad = bytearray(raw)
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        try:
+            rel.load_aocs_column(0, bytes(bad), checksum, attlen, varkind, align, compresstype=1)
+        except capi.CbgpuError as e:
+            assert e.code in (-6, -2, -3), (pos, e)
+            continue
+        # not reported: only acceptable without checksums, when the flip hit padding or a later block's header in a way
+        # that still decodes to the same values (never silently different values)
+        assert not checksum, pos
+        got, gotnull = rel.read_column(0)
+        keep = nulls == 0
+        assert np.array_equal(gotnull.astype(np.uint8), nulls) and np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64)), pos
+    assert rel.load_aocs_column(0, raw, checksum, attlen, varkind, align, compresstype=1) == len(values)
     rel.free()
 
 

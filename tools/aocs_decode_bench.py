@@ -12,14 +12,17 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from cloudberry_b200 import capi  # noqa: E402
-from test_aocs_format import CASES  # noqa: E402
+from test_aocs_format import CASES, ZCASES  # noqa: E402
 from test_gpu_aocs import DECODE  # noqa: E402
+from oracle import aocs_format as A  # noqa: E402
 
 
 def main():
     ctx = capi.Context(0)
     target = 256 << 20
-    for name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls in CASES:
+    for case in CASES + ZCASES:
+        name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = case[:9]
+        ctype_z = 1 if len(case) > 9 else 0
         if len(values) < 1000:
             continue
         k = max(1, target // len(raw))
@@ -27,16 +30,19 @@ def main():
         n = len(values) * k
         ctype, attlen, varkind, align = DECODE[typname]
         rel = capi.DeviceRelation(ctx, n, [ctype], dscales=[dscale])
-        rel.load_aocs_column(0, big, checksum, attlen, varkind, align)      # warm-up
+        rel.load_aocs_column(0, big, checksum, attlen, varkind, align, compresstype=ctype_z)      # warm-up
         ctx.trace_begin()
-        got = rel.load_aocs_column(0, big, checksum, attlen, varkind, align)
+        got = rel.load_aocs_column(0, big, checksum, attlen, varkind, align, compresstype=ctype_z)
         tr = ctx.trace_end()
         ms = sum(m for nme, m in tr if nme == "k_aocs_decode")
         vms = sum(m for nme, m in tr if nme == "k_aocs_verify")
+        ims = sum(m for nme, m in tr if nme == "k_aocs_inflate")
         assert got == n
-        print("%-30s %8.1f MB file  %10d rows  kernel %7.3f ms  %7.1f GB/s of file  %7.2f G rows/s  (%d blocks)  crc32c %s" %
+        content = sum(b["dlen"] for b in A.walk_blocks_ex(raw, checksum) if b["clen"]) * k
+        print("%-30s %8.1f MB file  %10d rows  kernel %7.3f ms  %7.1f GB/s of file  %7.2f G rows/s  (%d blocks)  crc32c %s  inflate %s" %
               (name, len(big) / 1e6, n, ms, len(big) / ms / 1e6, n / ms / 1e6, nblocks * k,
-               "%.3f ms %.1f GB/s" % (vms, len(big) / vms / 1e6) if vms else "off"))
+               "%.3f ms %.1f GB/s" % (vms, len(big) / vms / 1e6) if vms else "off",
+               "%.3f ms %.1f GB/s out" % (ims, content / ims / 1e6) if ims else "-"))
         rel.free()
     ctx.close()
 
