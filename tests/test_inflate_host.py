@@ -23,13 +23,15 @@ def lib(tmp_path_factory):
     L = C.CDLL(so)
     L.infl_host_zlib.restype = C.c_longlong
     L.infl_host_zlib.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.infl_host_zlib_warp.restype = C.c_longlong
+    L.infl_host_zlib_warp.argtypes = L.infl_host_zlib.argtypes
     return L
 
 
-def inflate(L, z, cap):
+def inflate(L, z, cap, warp=False):
     out = (C.c_ubyte * max(cap, 1))()
     ad = C.c_uint32()
-    r = L.infl_host_zlib(z, len(z), out, cap, C.byref(ad))
+    r = (L.infl_host_zlib_warp if warp else L.infl_host_zlib)(z, len(z), out, cap, C.byref(ad))
     return r, bytes(out[:max(r, 0)]), ad.value
 
 
@@ -62,6 +64,14 @@ def test_against_system_zlib(lib):
         r, out, ad = inflate(lib, z, len(src))
         assert r == len(src) and out == src
         assert ad == zlib.adler32(src)
+
+
+def test_batch_schedule_of_the_warp_kernel(lib):
+    """the order in which k_aocs_inflate's warp applies a batch of 32 entries (independent entries in any order, then the
+    self-referencing ones in sequence, 32 bytes at a time) gives the serial result"""
+    for src, z in streams():
+        r, out, ad = inflate(lib, z, len(src), warp=True)
+        assert r == len(src) and out == src
 
 
 def test_sync_flushes_and_many_blocks(lib):
