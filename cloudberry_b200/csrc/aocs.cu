@@ -41,6 +41,7 @@
  */
 #include "common.cuh"
 #include "inflate.cuh"
+#include "zstd_dec.cuh"
 
 #include <stdlib.h>
 #include <string.h>
@@ -419,6 +420,292 @@ k_aocs_inflate(uint8_t *raw, const AocsDir *dir, int nblocks, int *status, int *
 			else if (cap > 2 && (out[2] & 1u))	/* DSB_HAS_NULLBITMAP of the inflated datum stream block */
 				atomicOr(anynull, 1);
 		}
+	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * compresstype=zstd blocks: the same step for Zstandard frames (zstd_dec.cuh; the reference's zstd_decompress,
+ * gpcontrib/zstd/zstd_compression.c:142-175).  One warp per storage block = one frame.  Lane 0 parses headers, builds
+ * the FSE / Huffman tables in shared memory and decodes sequences 32 at a time; the four Huffman literal streams decode
+ * on four lanes at once into the warp's scratch area; the warp then executes a batch of sequences: output and literal
+ * positions by two prefix sums, literal runs and matches that reach behind the batch in parallel, the rest in order,
+ * warp-wide.  Wrong sizes, malformed sections and (when the frame carries one) a wrong XXH64 checksum raise
+ * CBGPU_ERR_CORRUPT, as the ZSTD_isError() / length checks of the reference do.
+ * --------------------------------------------------------------------------------------------- */
+#define ZSTD_SCRATCH (Z_BLOCK_MAX + 64u)
+
+__device__ __forceinline__ void
+warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int lane)
+{
+	for (uint32_t i = lane; i < n; i += 32)
+		dst[i] = src[i];
+}
+
+__device__ __forceinline__ bool
+zstd_exec_warp(uint8_t *out, uint32_t &op, uint32_t cap, const uint8_t *lit, uint32_t &lp, uint32_t regen, const uint32_t *qll,
+			   const uint32_t *qml, const uint32_t *qoff, int n, int lane)
+{
+	const uint32_t ll = lane < n ? qll[lane] : 0u;
+	const uint32_t ml = lane < n ? qml[lane] : 0u;
+	const uint32_t off = lane < n ? qoff[lane] : 1u;
+	uint32_t	io = ll + ml,
+				il = ll;
+
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const uint32_t vo = __shfl_up_sync(0xffffffffu, io, d);
+		const uint32_t vl = __shfl_up_sync(0xffffffffu, il, d);
+
+		if (lane >= d)
+		{
+			io += vo;
+			il += vl;
+		}
+	}
+	const uint32_t total_out = __shfl_sync(0xffffffffu, io, 31);
+	const uint32_t total_lit = __shfl_sync(0xffffffffu, il, 31);
+	const uint32_t start = op + io - (ll + ml);
+	const uint32_t lstart = lp + il - ll;
+	const uint32_t mstart = start + ll;
+
+	if (total_lit > regen - lp || total_out > cap - op || __any_sync(0xffffffffu, lane < n && (off == 0 || off > mstart)))
+		return false;
+	/* literal runs: short ones one per lane, long ones by the whole warp */
+	if (ll <= 32)
+		for (uint32_t i = 0; i < ll; i++)
+			out[start + i] = lit[lstart + i];
+	for (unsigned m = __ballot_sync(0xffffffffu, ll > 32); m; m &= m - 1)
+	{
+		const int	k = __ffs(m) - 1;
+
+		warp_copy(out + __shfl_sync(0xffffffffu, start, k), lit + __shfl_sync(0xffffffffu, lstart, k), __shfl_sync(0xffffffffu, ll, k), lane);
+	}
+	/* matches whose source ends before the batch */
+	bool		dep = false;
+
+	if (lane < n && ml)
+	{
+		if (mstart - off + ml <= op && ml <= 64)
+		{
+			const uint8_t *src = out + mstart - off;
+
+			for (uint32_t i = 0; i < ml; i++)
+				out[mstart + i] = src[i];
+		}
+		else
+			dep = true;
+	}
+	__syncwarp();
+	for (unsigned m = __ballot_sync(0xffffffffu, dep); m; m &= m - 1)
+	{
+		const int	k = __ffs(m) - 1;
+		const uint32_t s = __shfl_sync(0xffffffffu, mstart, k);
+		const uint32_t d = __shfl_sync(0xffffffffu, off, k);
+		const uint32_t l = __shfl_sync(0xffffffffu, ml, k);
+
+		for (uint32_t i = lane; i < l; i += 32)
+			out[s + i] = out[s - d + (d >= l ? i : i % d)];
+		__syncwarp();
+	}
+	op += total_out;
+	lp += total_lit;
+	return true;
+}
+
+__global__ void __launch_bounds__(AOCS_WARPS * 32)
+k_aocs_unzstd(uint8_t *raw, const AocsDir *dir, int nblocks, int *status, int *anynull, uint8_t *scratch)
+{
+	__shared__ ZTab s_tab[AOCS_WARPS];
+	__shared__ uint32_t s_q[AOCS_WARPS][3][Z_SEQ_QN];
+	__shared__ ZLitStreams s_st[AOCS_WARPS];
+	const int	lane = threadIdx.x & 31;
+	const int	w = threadIdx.x >> 5;
+	const int	nwarps = gridDim.x * AOCS_WARPS;
+	uint8_t    *litbuf = scratch + (size_t) (blockIdx.x * AOCS_WARPS + w) * ZSTD_SCRATCH;
+	ZTab	   &T = s_tab[w];
+
+	if (*status == CBGPU_ERR_CORRUPT)
+		return;
+	for (int b = blockIdx.x * AOCS_WARPS + w; b < nblocks; b += nwarps)
+	{
+		const AocsDir D = dir[b];
+
+		if (D.clen == 0)
+			continue;
+		const uint8_t *z = raw + D.zoff;
+		uint8_t    *out = raw + D.off;
+		const uint32_t zl = (uint32_t) D.clen;
+		const uint32_t cap = (uint32_t) D.dlen;
+		uint32_t	op = 0,
+					pos = 0;
+		int			last = 0;
+		bool		ok = true;
+		ZFrame		F;
+		ZSeqState	S;
+
+		F.hdr = 0;
+		F.content_size = 0;
+		F.checksum = 0;
+		S.rep[0] = 1;
+		S.rep[1] = 4;
+		S.rep[2] = 8;
+		S.nseq = S.done = 0;
+		if (lane == 0)
+		{
+			T.have_ll = T.have_of = T.have_ml = T.have_huf = 0;
+			ok = z_frame_header(z, zl, F);
+		}
+		ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+		pos = __shfl_sync(0xffffffffu, F.hdr, 0);
+		while (ok && !last)
+		{
+			int			type = 0;
+			uint32_t	size = 0;
+
+			if (lane == 0)
+				ok = z_block_header(z, zl, pos, &last, &type, &size) && pos + 3 + (type == 1 ? 1u : size) <= zl;
+			ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+			last = __shfl_sync(0xffffffffu, last, 0);
+			type = __shfl_sync(0xffffffffu, type, 0);
+			size = __shfl_sync(0xffffffffu, size, 0);
+			if (!ok)
+				break;
+			pos += 3;
+			if (type == 0 || type == 1)
+			{
+				if (size > cap - op)
+				{
+					ok = false;
+					break;
+				}
+				if (type == 0)
+					warp_copy(out + op, z + pos, size, lane);
+				else
+				{
+					const uint8_t v = z[pos];
+
+					for (uint32_t i = lane; i < size; i += 32)
+						out[op + i] = v;
+				}
+				op += size;
+				pos += type == 0 ? size : 1u;
+				__syncwarp();
+				continue;
+			}
+			/* compressed block */
+			const uint8_t *blk = z + pos;
+			const uint8_t *lit = litbuf;
+			ZLit		L;
+			uint32_t	after = 0,
+						lp = 0;
+
+			L.type = 0;
+			L.regen = L.csize = L.hdr = 0;
+			L.streams = 1;
+			if (lane == 0)
+				ok = z_lit_header(blk, size, L) && L.regen <= Z_BLOCK_MAX && L.hdr + (L.type == 0 ? L.regen : L.type == 1 ? 1u : L.csize) <= size;
+			ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+			if (!ok)
+				break;
+			L.type = __shfl_sync(0xffffffffu, L.type, 0);
+			L.regen = __shfl_sync(0xffffffffu, L.regen, 0);
+			L.csize = __shfl_sync(0xffffffffu, L.csize, 0);
+			L.hdr = __shfl_sync(0xffffffffu, L.hdr, 0);
+			L.streams = __shfl_sync(0xffffffffu, L.streams, 0);
+			if (L.type == 0)
+			{
+				lit = blk + L.hdr;
+				after = L.hdr + L.regen;
+			}
+			else if (L.type == 1)
+			{
+				const uint8_t v = blk[L.hdr];
+
+				for (uint32_t i = lane; i < L.regen; i += 32)
+					litbuf[i] = v;
+				after = L.hdr + 1;
+			}
+			else
+			{
+				uint32_t	tree = 0;
+
+				if (lane == 0)
+				{
+					if (L.type == 2)
+					{
+						const int	used = z_huf_read_tree(blk + L.hdr, L.csize, T);
+
+						ok = used >= 0;
+						tree = ok ? (uint32_t) used : 0u;
+					}
+					else
+						ok = T.have_huf != 0;
+					ok = ok && z_lit_streams(L, blk + L.hdr + tree, L.csize - tree, s_st[w]);
+				}
+				__syncwarp();
+				ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+				tree = __shfl_sync(0xffffffffu, tree, 0);
+				if (!ok)
+					break;
+				/* the Huffman streams: one lane each */
+				bool		sok = true;
+
+				if (lane < L.streams)
+					sok = z_huf_stream(T, blk + L.hdr + tree + s_st[w].off[lane], s_st[w].len[lane], litbuf + s_st[w].outoff[lane],
+									   s_st[w].count[lane]);
+				ok = !__any_sync(0xffffffffu, !sok);
+				if (!ok)
+					break;
+				after = L.hdr + L.csize;
+			}
+			__syncwarp();
+			if (lane == 0)
+				ok = z_seq_begin(blk + after, size - after, T, S);
+			ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+			if (!ok)
+				break;
+			const uint32_t nseq = __shfl_sync(0xffffffffu, S.nseq, 0);
+
+			for (uint32_t done = 0; done < nseq && ok; done += Z_SEQ_QN)
+			{
+				const int	n = (int) (nseq - done < Z_SEQ_QN ? nseq - done : Z_SEQ_QN);
+
+				if (lane == 0)
+					for (int k = 0; k < n && ok; k++)
+						ok = z_seq_next(T, S, &s_q[w][0][k], &s_q[w][1][k], &s_q[w][2][k]);
+				__syncwarp();
+				ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+				if (ok)
+					ok = zstd_exec_warp(out, op, cap, lit, lp, L.regen, s_q[w][0], s_q[w][1], s_q[w][2], n, lane);
+				__syncwarp();
+			}
+			if (ok && nseq)
+				ok = __shfl_sync(0xffffffffu, S.bs.pos == 0 ? 1 : 0, 0) != 0;
+			if (ok && L.regen - lp > cap - op)
+				ok = false;
+			if (!ok)
+				break;
+			warp_copy(out + op, lit + lp, L.regen - lp, lane);
+			op += L.regen - lp;
+			pos += size;
+			__syncwarp();
+		}
+		if (ok && lane == 0)
+		{
+			if (op != cap || (F.content_size != ~0ull && F.content_size != op))
+				ok = false;
+			else if (F.checksum)
+				ok = pos + 4 <= zl &&
+					(uint32_t) z_xxh64(out, op) == ((uint32_t) z[pos] | ((uint32_t) z[pos + 1] << 8) | ((uint32_t) z[pos + 2] << 16) | ((uint32_t) z[pos + 3] << 24));
+		}
+		if (lane == 0)
+		{
+			if (!ok)
+				atomicExch(status, CBGPU_ERR_CORRUPT);
+			else if (cap > 2 && (out[2] & 1u))
+				atomicOr(anynull, 1);
+		}
+		__syncwarp();
 	}
 }
 
@@ -862,6 +1149,7 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 				ncompressed = 0;
 	bool		anynull = false;
 	int		   *d_flag = NULL;
+	uint8_t    *d_scratch = NULL;
 	AocsParams	P;
 	uint8_t    *d_raw = NULL;
 	AocsDir    *d_dir = NULL;
@@ -930,12 +1218,12 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 		}
 		hlen = 8 + (checksum ? 8 : 0) + ext + (has_first ? 8 : 0);
 		stored = clen ? clen : dlen;
-		if (pos + hlen + stored > nbytes || dlen < 16 || (clen && compress_kind != CBGPU_AOCS_COMPRESS_ZLIB))
+		if (pos + hlen + stored > nbytes || dlen < 16 || (clen && compress_kind != CBGPU_AOCS_COMPRESS_ZLIB && compress_kind != CBGPU_AOCS_COMPRESS_ZSTD))
 		{
 			free(dir);
-			if (clen && compress_kind != CBGPU_AOCS_COMPRESS_ZLIB && pos + hlen + stored <= nbytes)
+			if (clen && pos + hlen + stored <= nbytes && dlen >= 16)
 				return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED,
-							   "AOCS block at offset %s%lld is bulk-compressed, and not with zlib (zstd / quicklz blocks are not decoded on the device)", "", pos);
+							   "AOCS block at offset %s%lld is bulk-compressed: pass the column's compresstype (zlib or zstd; quicklz is not decoded on the device)", "", pos);
 			return cb_fail(ctx, CBGPU_ERR_INVALID, "AOCS block at offset %s%lld runs past the end of the file", "", pos);
 		}
 		if (ndir == capdir)
@@ -1001,8 +1289,21 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 
 		CB_CUDA(ctx, cudaMallocAsync(&d_flag, sizeof(int), ctx->stream));
 		CB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
-		k_aocs_inflate<<<nblk, AOCS_WARPS * 32, 0, ctx->stream>>>(d_raw, d_dir, (int) ndir, ctx->d_status, d_flag);
-		CB_LAUNCHED(ctx, "k_aocs_inflate");
+		if (compress_kind == CBGPU_AOCS_COMPRESS_ZSTD)
+		{
+			/* a literal scratch area per warp bounds the grid */
+			const int	zblk = nblk < ctx->sm_count * 4 ? nblk : ctx->sm_count * 4;
+
+			CB_CUDA(ctx, cudaMallocAsync(&d_scratch, (size_t) zblk * AOCS_WARPS * ZSTD_SCRATCH, ctx->stream));
+			k_aocs_unzstd<<<zblk, AOCS_WARPS * 32, 0, ctx->stream>>>(d_raw, d_dir, (int) ndir, ctx->d_status, d_flag, d_scratch);
+			CB_LAUNCHED(ctx, "k_aocs_unzstd");
+			CB_CUDA(ctx, cudaFreeAsync(d_scratch, ctx->stream));
+		}
+		else
+		{
+			k_aocs_inflate<<<nblk, AOCS_WARPS * 32, 0, ctx->stream>>>(d_raw, d_dir, (int) ndir, ctx->d_status, d_flag);
+			CB_LAUNCHED(ctx, "k_aocs_inflate");
+		}
 		if (!anynull && !rel->nulls[col])
 		{
 			/* whether an inflated block carries a NULL bitmap is only known now */

@@ -362,6 +362,7 @@ int			cbgpu_motion_broadcast(cbgpu_motion *m, cbgpu_rel *send, int64_t nrows, cb
 #define CBGPU_AOCS_VAR_BPCHAR1 2	/* character(1) varlena -> its byte                                   */
 #define CBGPU_AOCS_COMPRESS_NONE 0	/* compresstype=none, or rle_type with compresslevel 1                */
 #define CBGPU_AOCS_COMPRESS_ZLIB 1	/* compresstype=zlib (any level), or rle_type with compresslevel 2-4   */
+#define CBGPU_AOCS_COMPRESS_ZSTD 2	/* compresstype=zstd (any level)                                       */
 /* file_bytes: one column's segment file (<relfilenode>.<n>) as it lies on disk, in host memory:
  * SmallContent / NonBulkDenseContent / BulkDenseContent storage blocks holding Original or Dense (RLE, delta)
  * datum stream blocks.  attlen = pg_type typlen (1/2/4/8, or -1 with varkind), typalign in bytes.  Decodes into
@@ -374,8 +375,9 @@ int			cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t n
 									 int64_t row_offset, int64_t *nrows);
 /* The same for a column stored with bulk compression (pg_attribute_encoding compresstype; gp_decompress,
  * cdb/cdbappendonlystorageread.c:1286-1310): blocks whose header carries a compressed length are inflated on the
- * device (zlib streams as catalog/pg_compression.c:272 writes them with compress2()); a bad stream, a wrong
- * Adler-32 or a length other than the header's is CBGPU_ERR_CORRUPT.  zstd: CBGPU_ERR_UNSUPPORTED. */
+ * device (zlib streams as catalog/pg_compression.c:272 writes them with compress2(), Zstandard frames as
+ * gpcontrib/zstd/zstd_compression.c:104 writes them with ZSTD_compressCCtx()); a bad stream, a wrong Adler-32 /
+ * XXH64 or a length other than the header's is CBGPU_ERR_CORRUPT.  quicklz: CBGPU_ERR_UNSUPPORTED. */
 int			cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum,
 										int32_t compresstype, int32_t attlen, int32_t varkind, int32_t typalign,
 										cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows);

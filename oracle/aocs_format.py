@@ -133,6 +133,9 @@ def ref_lib():
         L.ref_aocs_write_column_z.restype = C.c_int64
         L.ref_aocs_write_column_z.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                                               C.POINTER(C.c_int64)]
+        L.ref_aocs_write_column_cb.restype = C.c_int64
+        L.ref_aocs_write_column_cb.argtypes = [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                                               C.POINTER(C.c_int64)]
         L.ref_aocs_last_error.restype = C.c_char_p
         L.ref_numeric_inspect.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.c_void_p, C.c_int]
@@ -143,7 +146,25 @@ def ref_lib():
     return _REF
 
 
-def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768, dscale=0, rle=False, zlevel=0):
+COMPRESS_CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_ubyte), C.c_int, C.POINTER(C.c_ubyte), C.c_int)
+
+
+def zstd_compressor(level):
+    """what the reference's zstd_compress does (gpcontrib/zstd/zstd_compression.c:104-140: ZSTD_compressCCtx at the
+    column's compresslevel; 'destination too small' reported as src_sz), with the libzstd bundled in pyarrow"""
+    import pyarrow as pa
+    codec = pa.Codec("zstd", compression_level=level)
+
+    def cb(src, srclen, dst, dstcap):
+        z = codec.compress(C.string_at(src, srclen), asbytes=True)
+        if len(z) > dstcap:
+            return srclen
+        C.memmove(dst, z, len(z))
+        return len(z)
+    return COMPRESS_CB(cb)
+
+
+def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768, dscale=0, rle=False, zlevel=0, compressor=None):
     # zlevel: zlib level of the storage layer's bulk compression (compresstype=zlib compresslevel=zlevel; with rle:
     # rle_type compresslevel 2 / 3 / 4 = zlevel 1 / 5 / 9), 0 = none
     # rle: False / 0 plain, True / 1 rle_type, 2 rle_type with delta range encoding (what the reference picks for
@@ -179,9 +200,14 @@ def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768
     out = (C.c_ubyte * cap)()
     nb = C.c_int64()
     vb = (C.c_ubyte * max(len(varbuf), 1)).from_buffer_copy(varbuf or b"\0")
-    r = L.ref_aocs_write_column_z(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize, int(rle), int(zlevel),
-                                   vals.ctypes.data, C.addressof(vb), nl.ctypes.data if nl is not None else None, n,
-                                   C.addressof(out), cap, C.byref(nb))
+    if compressor is not None:
+        r = L.ref_aocs_write_column_cb(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize, int(rle),
+                                       C.cast(compressor, C.c_void_p), vals.ctypes.data, C.addressof(vb),
+                                       nl.ctypes.data if nl is not None else None, n, C.addressof(out), cap, C.byref(nb))
+    else:
+        r = L.ref_aocs_write_column_z(typid, attlen, byval, ord(align), ord(storage), 1 if checksum else 0, blocksize, int(rle), int(zlevel),
+                                      vals.ctypes.data, C.addressof(vb), nl.ctypes.data if nl is not None else None, n,
+                                      C.addressof(out), cap, C.byref(nb))
     if r < 0:
         raise RuntimeError("reference writer: " + L.ref_aocs_last_error().decode())
     return bytes(out[:r]), int(nb.value)
@@ -267,15 +293,20 @@ def walk_blocks(raw, checksum, verify=False):
     return out
 
 
-def block_contents(raw, checksum, verify=False):
+def block_contents(raw, checksum, verify=False, compresstype="zlib"):
     """[(datum stream block bytes, row count)]: AppendOnlyStorageRead_Content (cdbappendonlystorageread.c:1136-1320):
     the stored bytes, or for a bulk-compressed block what zlib's uncompress() makes of them (zlib_decompress,
     catalog/pg_compression.c:321-370; gp_decompress checks the length, storage/file/gp_compress.c:52-90)"""
     import zlib
     out = []
     for b in walk_blocks_ex(raw, checksum, verify):
-        if b["clen"]:
+        if b["clen"] and compresstype == "zstd":
+            # zstd_decompress (gpcontrib/zstd/zstd_compression.c:142-175): ZSTD_decompressDCtx into dst_sz bytes
+            import pyarrow as pa
+            blk = pa.Codec("zstd").decompress(bytes(raw[b["off"]:b["off"] + b["clen"]]), decompressed_size=b["dlen"], asbytes=True)
+        elif b["clen"]:
             blk = zlib.decompress(bytes(raw[b["off"]:b["off"] + b["clen"]]))
+        if b["clen"]:
             if len(blk) != b["dlen"]:
                 raise ValueError("block at %d: inflated to %d bytes, header says %d" % (b["hoff"], len(blk), b["dlen"]))
         else:
@@ -322,10 +353,10 @@ class _Datums:
         return v
 
 
-def decode_column(raw, typname, checksum, dscale=0):
+def decode_column(raw, typname, checksum, dscale=0, compresstype="zlib"):
     """(values, nulls): numeric -> scaled int64, bpchar -> first byte, fixed width -> the value"""
     vals, nulls = [], []
-    for blk, rows in block_contents(raw, checksum):
+    for blk, rows in block_contents(raw, checksum, compresstype=compresstype):
         version, flags = int.from_bytes(blk[0:2], "little", signed=True), int.from_bytes(blk[2:4], "little")
         if version == 0:
             # DatumStreamBlock_Orig

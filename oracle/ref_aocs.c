@@ -242,10 +242,37 @@ ref_aocs_write_column_ex(int typid, int attlen, int byval, int align, int storag
  * BulkDenseContent header when bulk compression is on (datumstreamwrite_block_dense, datumstream.c:944-956).
  * compresstype=zlib, compresslevel=L: rle 0, zlevel L.  rle_type compresslevel 2 / 3 / 4: rle 1|2, zlevel 1 / 5 / 9
  * (init_datumstream_info, datumstream.c:412-436). */
+typedef int (*ref_compress_cb) (const unsigned char *src, int srclen, unsigned char *dst, int dstcap);
+
+static int64 ref_write_impl(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle, int zlevel,
+							ref_compress_cb cb, const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
+							unsigned char *out, int64 outcap, int64 *nblocks_out);
+
 int64
 ref_aocs_write_column_z(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle, int zlevel,
 						const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
 						unsigned char *out, int64 outcap, int64 *nblocks_out)
+{
+	return ref_write_impl(typid, attlen, byval, align, storage, checksum, blocksize, rle, zlevel, NULL, values, varbuf, nulls, n, out,
+						  outcap, nblocks_out);
+}
+
+/* Bulk compression through a caller-supplied compressor, for compression libraries this container cannot link (zstd:
+ * the reference's zstd_compress, gpcontrib/zstd/zstd_compression.c:104-140, calls ZSTD_compressCCtx and reports
+ * "did not fit" as dst_used = src_sz).  cb returns the compressed length, or srclen when dstcap was too small. */
+int64
+ref_aocs_write_column_cb(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle,
+						 ref_compress_cb cb, const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
+						 unsigned char *out, int64 outcap, int64 *nblocks_out)
+{
+	return ref_write_impl(typid, attlen, byval, align, storage, checksum, blocksize, rle, 1, cb, values, varbuf, nulls, n, out, outcap,
+						  nblocks_out);
+}
+
+static int64
+ref_write_impl(int typid, int attlen, int byval, int align, int storage, int checksum, int blocksize, int rle, int zlevel,
+			   ref_compress_cb cb, const int64 *values, const unsigned char *varbuf, const unsigned char *nulls, int64 n,
+			   unsigned char *out, int64 outcap, int64 *nblocks_out)
 {
 	DatumStreamBlockWrite dsw;
 	DatumStreamTypeInfo ti;
@@ -294,7 +321,9 @@ ref_aocs_write_column_z(int typid, int attlen, int byval, int align, int storage
 			const int	hl = hdrlen + (bulk ? AoHeader_RegularSize : 0);	/* + the extension header */ \
 			memset(blockbuf, 0, (size_t) blocksize + 64); \
 			contentLen = DatumStreamBlockWrite_Block(&dsw, contentbuf, &node); \
-			if (zlevel > 0) \
+			if (cb) \
+				compressedLen = cb(contentbuf, (int) contentLen, blockbuf + hl, blocksize - hl); \
+			else if (zlevel > 0) \
 			{ \
 				unsigned long used = (unsigned long) (blocksize - hl); \
 				int			zrc = compress2(blockbuf + hl, &used, contentbuf, (unsigned long) contentLen, zlevel); \

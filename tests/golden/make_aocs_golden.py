@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Write tests/golden/aocs_columns.npz (and aocs_zlib_columns.npz, bulk-compressed columns): AOCS column files produced by the REFERENCE's own block writer
+"""Write tests/golden/aocs_columns.npz (and aocs_zlib_columns.npz / aocs_zstd_columns.npz, bulk-compressed columns): AOCS column files produced by the REFERENCE's own block writer
 (oracle/_ref/libaocs_ref.so = the reference's datumstreamblock.c + cdbappendonlystorageformat.c + pg_crc32c_sb8.c,
 driven by oracle/ref_aocs.c; run `make -C oracle` first) together with the values that went in.
 
@@ -21,8 +21,10 @@ def main():
     out = {}
     cases = []
 
-    def add(name, typname, values, nulls, checksum, blocksize, dscale=0, rle=False, zlevel=0):
-        raw, nblocks = A.ref_write_column(typname, values, nulls, checksum, blocksize, dscale, rle=rle, zlevel=zlevel)
+    def add(name, typname, values, nulls, checksum, blocksize, dscale=0, rle=False, zlevel=0, zstd=0):
+        raw, nblocks = A.ref_write_column(typname, values, nulls, checksum, blocksize, dscale, rle=rle, zlevel=zlevel,
+                                          compressor=A.zstd_compressor(zstd) if zstd else None)
+        zlevel = zlevel or zstd
         out[name + "__raw"] = np.frombuffer(raw, dtype=np.uint8)
         if typname == "bpchar":
             out[name + "__values"] = np.array([ord(v[0]) if v else 32 for v in values], dtype=np.int64)
@@ -110,6 +112,35 @@ def main():
     add("rle4_float8_runs_8k_nocrc", "float8", np.repeat(rng.normal(0, 1e3, 900), rng.integers(1, 60, 900)), None, False, 8192, rle=True, zlevel=9)
     out["cases"] = np.array(cases)
     path = os.path.join(ROOT, "tests", "golden", "aocs_zlib_columns.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(cases), "columns")
+    for c in cases:
+        print("  ", c)
+        name = c.split("|")[0]
+        blocks = A.walk_blocks_ex(bytes(out[name + "__raw"]), int(c.split("|")[2]))
+        print("      kinds", sorted(set(b["kind"] for b in blocks)), "compressed", sum(1 for b in blocks if b["clen"]), "of", len(blocks),
+              "file", len(out[name + "__raw"]), "bytes for", sum(b["dlen"] for b in blocks), "of content")
+
+    # ---- compresstype=zstd compresslevel=L: the blocks go through a real libzstd (pyarrow's) the way zstd_compress does
+    out = {}
+    cases = []
+    rng = np.random.default_rng(20260924)
+    n = 20011
+    nul = (rng.random(n) < 0.07).astype(np.uint8)
+    add("zstd1_int4_sorted", "int4", np.cumsum(rng.integers(0, 4, n)) - 10**6, None, True, 32768, zstd=1)
+    add("zstd3_numeric_price", "numeric", rng.integers(90000, 10500000, n), None, True, 32768, dscale=2, zstd=3)
+    add("zstd9_bpchar1_flags_nulls", "bpchar", [("A", "N", "R", "F", "O")[i] for i in rng.integers(0, 5, n)], nul, True, 32768, zstd=9)
+    add("zstd1_int8_random_stored", "int8", rng.integers(-2**62, 2**62, 6000), None, True, 32768, zstd=1)
+    add("zstd5_float8_nulls_8k_nocrc", "float8", np.round(rng.normal(0, 50, n)), nul, False, 8192, zstd=5)
+    big = np.tile(rng.integers(-2**40, 2**40, 2500), 14)[:33000] + np.repeat(np.arange(33), 1000)
+    add("zstd3_int8_bigblocks", "int8", big, None, True, 2097152, zstd=3)                      # 131 KB content: two zstd blocks per frame
+    add("zstd19_date_mixed", "date", np.where(rng.random(n) < 0.3, rng.integers(-3000, 9000, n), 7305), nul, True, 32768, zstd=19)
+    add("zstd1_int4_tiny_stored", "int4", [7], None, True, 32768, zstd=1)
+    add("zstd3_bool_allnull", "bool", [0] * 5000, [1] * 5000, True, 8192, zstd=3)               # RLE-ish content
+    add("zstd3_int4_constant", "int4", [42] * 16000, None, True, 2097152, zstd=3)
+    add("zstd7_numeric_few_values", "numeric", rng.choice([0, 1, 5, 10, 100, 12345678], n), nul, True, 32768, dscale=2, zstd=7)
+    out["cases"] = np.array(cases)
+    path = os.path.join(ROOT, "tests", "golden", "aocs_zstd_columns.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(cases), "columns")
     for c in cases:

@@ -39,6 +39,18 @@ def golden_zlib():
 ZCASES = list(golden_zlib())
 
 
+def golden_zstd():
+    """compresstype=zstd columns: the same tuple, the last field is the zstd level"""
+    d = np.load(os.path.join(HERE, "golden", "aocs_zstd_columns.npz"))
+    for c in d["cases"]:
+        name, typname, checksum, blocksize, dscale, nblocks, zlevel = str(c).split("|")
+        yield (name, typname, int(checksum), int(blocksize), int(dscale), int(nblocks), bytes(d[name + "__raw"]),
+               d[name + "__values"], d[name + "__nulls"], int(zlevel))
+
+
+ZSTDCASES = list(golden_zstd())
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_restated_reader_reads_reference_written_columns(case):
     name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = case
@@ -93,10 +105,29 @@ def test_restated_reader_reads_bulk_compressed_columns(case):
         assert np.array_equal(got[keep], values[keep])
 
 
+@pytest.mark.parametrize("case", ZSTDCASES, ids=[c[0] for c in ZSTDCASES])
+def test_restated_reader_reads_zstd_columns(case):
+    pytest.importorskip("pyarrow")
+    name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel = case
+    blocks = A.walk_blocks_ex(raw, checksum, verify=True)
+    assert len(blocks) == nblocks and sum(b["rows"] for b in blocks) == len(values)
+    assert all(b["clen"] < b["dlen"] for b in blocks)
+    assert ("stored" in name) == all(b["clen"] == 0 for b in blocks)
+    # compressed contents are Zstandard frames
+    assert all(raw[b["off"]:b["off"] + 4] == b"\x28\xb5\x2f\xfd" for b in blocks if b["clen"])
+    got, gotnull = A.decode_column(raw, typname, checksum, dscale, compresstype="zstd")
+    assert np.array_equal(gotnull, nulls)
+    keep = nulls == 0
+    if typname == "float8":
+        assert np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64))
+    else:
+        assert np.array_equal(got[keep], values[keep])
+
+
 @pytest.mark.skipif(A.ref_lib() is None, reason="reference library only where /root/reference exists")
 def test_bulk_header_fields_against_reference_accessors():
     L = A.ref_lib()
-    for name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel in ZCASES:
+    for name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel in ZCASES + ZSTDCASES:
         buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
         for b in A.walk_blocks_ex(raw, checksum):
             hl, rc, dl, kind = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -5,7 +5,7 @@ import pytest
 
 from cloudberry_b200 import capi
 from cloudberry_b200 import plan as P
-from test_aocs_format import CASES, ZCASES
+from test_aocs_format import CASES, ZCASES, ZSTDCASES
 
 pytestmark = pytest.mark.gpu
 
@@ -83,14 +83,15 @@ def test_checksum_failure_is_reported(ctx, name):
     rel.free()
 
 
-@pytest.mark.parametrize("case", ZCASES, ids=[c[0] for c in ZCASES])
+@pytest.mark.parametrize("case", ZCASES + ZSTDCASES, ids=[c[0] for c in ZCASES + ZSTDCASES])
 def test_device_inflates_bulk_compressed_columns(ctx, case):
-    """compresstype=zlib / rle_type compresslevel 2-4 column files, written through the reference's header makers and the
-    system zlib: inflated (k_aocs_inflate), then decoded like stored blocks"""
+    """compresstype=zlib / rle_type compresslevel 2-4 / zstd column files, written through the reference's header makers
+    and a real zlib / libzstd: decompressed on the device (k_aocs_inflate / k_aocs_unzstd), then decoded like stored blocks"""
     name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel = case
     ctype, attlen, varkind, align = DECODE[typname]
+    kind = 2 if name.startswith("zstd") else 1
     rel = capi.DeviceRelation(ctx, len(values) + 5, [ctype], dscales=[dscale])
-    n = rel.load_aocs_column(0, raw, checksum, attlen, varkind, align, row_offset=5, compresstype=1)
+    n = rel.load_aocs_column(0, raw, checksum, attlen, varkind, align, row_offset=5, compresstype=kind)
     assert n == len(values)
     got, gotnull = rel.read_column(0, 5, 5 + n)
     assert np.array_equal(gotnull.astype(np.uint8), nulls)
@@ -106,17 +107,22 @@ def test_device_inflates_bulk_compressed_columns(ctx, case):
         with pytest.raises(capi.CbgpuError) as e:
             rel.load_aocs_column(0, raw, checksum, attlen, varkind, align)
         assert e.value.code == -3
+        # the wrong decompressor sees a stream that is not its own: reported, not followed
+        with pytest.raises(capi.CbgpuError) as e:
+            rel.load_aocs_column(0, raw, checksum, attlen, varkind, align, compresstype=3 - kind)
+        assert e.value.code == -6
     rel.free()
 
 
 @pytest.mark.parametrize("name", ["zlib5_numeric_price", "zlib6_float8_nulls_8k_nocrc", "zlib6_int8_bigblocks", "rle2_numeric_long_run",
-                                  "rle4_float8_runs_8k_nocrc"])
+                                  "rle4_float8_runs_8k_nocrc", "zstd3_numeric_price", "zstd3_int8_bigblocks"])
 def test_damaged_compressed_blocks_are_reported(ctx, name):
     """flipped bits inside compressed content: with checksums the CRC catches them, without, the inflater does (bad
     Huffman code, distance before the start, wrong length, Adler-32) -- as uncompress() / gp_decompress would"""
-    case = {c[0]: c for c in ZCASES}[name]
+    case = {c[0]: c for c in ZCASES + ZSTDCASES}[name]
     _, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel = case
     ctype, attlen, varkind, align = DECODE[typname]
+    kind = 2 if name.startswith("zstd") else 1
     rel = capi.DeviceRelation(ctx, len(values), [ctype], dscales=[dscale])
     rng = np.random.default_rng(len(raw) + 1)
     hdr = 8 + (8 if checksum else 0) + 16
@@ -124,7 +130,7 @@ def test_damaged_compressed_blocks_are_reported(ctx, name):
         bad = bytearray(raw)
         bad[pos] ^= 1 << int(rng.integers(0, 8))
         try:
-            rel.load_aocs_column(0, bytes(bad), checksum, attlen, varkind, align, compresstype=1)
+            rel.load_aocs_column(0, bytes(bad), checksum, attlen, varkind, align, compresstype=kind)
         except capi.CbgpuError as e:
             assert e.code in (-6, -2, -3), (pos, e)
             continue
@@ -134,7 +140,7 @@ def test_damaged_compressed_blocks_are_reported(ctx, name):
         got, gotnull = rel.read_column(0)
         keep = nulls == 0
         assert np.array_equal(gotnull.astype(np.uint8), nulls) and np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64)), pos
-    assert rel.load_aocs_column(0, raw, checksum, attlen, varkind, align, compresstype=1) == len(values)
+    assert rel.load_aocs_column(0, raw, checksum, attlen, varkind, align, compresstype=kind) == len(values)
     rel.free()
 
 

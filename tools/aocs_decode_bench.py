@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from cloudberry_b200 import capi  # noqa: E402
-from test_aocs_format import CASES, ZCASES  # noqa: E402
+from test_aocs_format import CASES, ZCASES, ZSTDCASES  # noqa: E402
 from test_gpu_aocs import DECODE  # noqa: E402
 from oracle import aocs_format as A  # noqa: E402
 
@@ -20,9 +20,9 @@ from oracle import aocs_format as A  # noqa: E402
 def main():
     ctx = capi.Context(0)
     target = 256 << 20
-    for case in CASES + ZCASES:
+    for case in CASES + ZCASES + ZSTDCASES:
         name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = case[:9]
-        ctype_z = 1 if len(case) > 9 else 0
+        ctype_z = 0 if len(case) <= 9 else 2 if name.startswith("zstd") else 1
         if len(values) < 1000:
             continue
         k = max(1, target // len(raw))
@@ -36,7 +36,7 @@ def main():
         tr = ctx.trace_end()
         ms = sum(m for nme, m in tr if nme == "k_aocs_decode")
         vms = sum(m for nme, m in tr if nme == "k_aocs_verify")
-        ims = sum(m for nme, m in tr if nme == "k_aocs_inflate")
+        ims = sum(m for nme, m in tr if nme in ("k_aocs_inflate", "k_aocs_unzstd"))
         assert got == n
         content = sum(b["dlen"] for b in A.walk_blocks_ex(raw, checksum) if b["clen"]) * k
         print("%-30s %8.1f MB file  %10d rows  kernel %7.3f ms  %7.1f GB/s of file  %7.2f G rows/s  (%d blocks)  crc32c %s  inflate %s" %
