@@ -9,10 +9,13 @@
  * RFC 1951: stored / fixed / dynamic Huffman blocks, LZ77 window of 32 KiB), and the parity tests inflate streams
  * produced by the system zlib the reference would link.
  *
- * Split in two so the serial part can be tested on the host (tests/test_inflate_host.py compiles this header with g++):
- *   infl_step()  one thread: decode block headers / Huffman symbols into a queue of up to INFL_QN
- *                literal / (length, distance) entries                                  [__host__ __device__]
- *   the caller   applies the queue to the output: serially on the host, a whole warp on the device (aocs.cu)
+ * The decoder is __host__ __device__ so it can be tested on the host (tests/test_inflate_host.py compiles this header
+ * with g++).  Two ways to drive it (aocs.cu picks by the number of compressed blocks in the file):
+ *   infl_run()   one thread decodes a whole stream, writing output as it goes: 32 streams per warp, the tables of
+ *                lane l interleaved in shared memory (element i of a table at [i * 32 + l]: template parameter S)
+ *   infl_step()  one thread decodes block headers / Huffman symbols into a queue of up to INFL_QN literal /
+ *                (length, distance) entries, which a whole warp then applies: one stream per warp, for files with
+ *                too few blocks to give every lane its own
  */
 #ifndef CB_INFLATE_CUH
 #define CB_INFLATE_CUH
@@ -48,6 +51,61 @@ struct InflTables
 	uint8_t		lens[320];		/* code lengths of the block being set up                               */
 };
 
+/* the tables as the decoder sees them: element i of a table lies at [i * S] */
+template <int S>
+struct InflView
+{
+	uint16_t   *lfast, *dfast, *lcount, *dcount, *lsym, *dsym;
+	uint8_t    *lens;			/* 320 code lengths of the block being set up, stride 1                  */
+	int			lbits, dbits;	/* first-level lookup bits                                               */
+};
+
+/* per-lane tables of the one-stream-per-thread mode: 9-bit / 7-bit lookups */
+#define INFL_T_LBITS 9
+#define INFL_T_DBITS 7
+#define INFL_T_ENTRIES ((1 << INFL_T_LBITS) + (1 << INFL_T_DBITS) + 16 + 16 + 288 + 32)	/* uint16_t per lane */
+
+INFL_HD InflView<1>
+infl_view(InflTables &T)
+{
+	InflView<1> V;
+
+	V.lfast = T.lfast;
+	V.dfast = T.dfast;
+	V.lcount = T.lcount;
+	V.dcount = T.dcount;
+	V.lsym = T.lsym;
+	V.dsym = T.dsym;
+	V.lens = T.lens;
+	V.lbits = INFL_FAST_L;
+	V.dbits = INFL_FAST_D;
+	return V;
+}
+
+/* lane's view of an interleaved area of INFL_T_ENTRIES * 32 uint16_t; lens = 320 bytes of the thread's own */
+INFL_HD InflView<32>
+infl_view_lane(uint16_t *area, int lane, uint8_t *lens)
+{
+	InflView<32> V;
+	uint16_t   *p = area + lane;
+
+	V.lfast = p;
+	p += (1 << INFL_T_LBITS) * 32;
+	V.dfast = p;
+	p += (1 << INFL_T_DBITS) * 32;
+	V.lcount = p;
+	p += 16 * 32;
+	V.dcount = p;
+	p += 16 * 32;
+	V.lsym = p;
+	p += 288 * 32;
+	V.dsym = p;
+	V.lens = lens;
+	V.lbits = INFL_T_LBITS;
+	V.dbits = INFL_T_DBITS;
+	return V;
+}
+
 struct InflState
 {
 	const uint8_t *in;
@@ -78,6 +136,24 @@ infl_init(InflState &s, const uint8_t *in, uint32_t inlen, uint32_t start)
 INFL_HD void
 infl_refill(InflState &s)
 {
+#ifdef __CUDA_ARCH__
+	/* s.in is 8-byte aligned on the device (block contents start on 8-byte file offsets): two aligned words give the
+	 * next 8 stream bytes; whole bytes that fit are accounted, the rest is OR-ed in again next time (same bits) */
+	if (s.inpos + 16u <= s.inlen)
+	{
+		const uint64_t *w = reinterpret_cast<const uint64_t *>(s.in) + (s.inpos >> 3);
+		const uint32_t sh = (s.inpos & 7u) * 8u;
+		uint64_t	v = w[0] >> sh;
+		const uint32_t take = (63u - s.nbits) >> 3;
+
+		if (sh)
+			v |= w[1] << (64u - sh);
+		s.bitbuf |= v << s.nbits;
+		s.inpos += take;
+		s.nbits += take * 8u;
+		return;
+	}
+#endif
 	while (s.nbits <= 56)
 	{
 		const uint64_t b = s.inpos < s.inlen ? s.in[s.inpos] : 0;
@@ -106,10 +182,11 @@ infl_consumed(const InflState &s)
 }
 
 /* one Huffman symbol; needs 15 valid bits in the buffer.  -1 = no such code */
+template <int S>
 INFL_HD int
 infl_sym(InflState &s, const uint16_t *fast, int fastbits, const uint16_t *count, const uint16_t *sym)
 {
-	const uint32_t e = fast[s.bitbuf & ((1u << fastbits) - 1)];
+	const uint32_t e = fast[(s.bitbuf & ((1u << fastbits) - 1)) * S];
 	uint32_t	code = 0,
 				first = 0,
 				index = 0;
@@ -124,7 +201,7 @@ infl_sym(InflState &s, const uint16_t *fast, int fastbits, const uint16_t *count
 	/* codes longer than the lookup: walk the canonical code one bit at a time */
 	for (int len = 1; len <= 15; len++)
 	{
-		const uint32_t c = count[len];
+		const uint32_t c = count[len * S];
 
 		code |= (uint32_t) (bb & 1);
 		bb >>= 1;
@@ -132,7 +209,7 @@ infl_sym(InflState &s, const uint16_t *fast, int fastbits, const uint16_t *count
 		{
 			s.bitbuf = bb;
 			s.nbits -= len;
-			return sym[index + (code - first)];
+			return sym[(index + (code - first)) * S];
 		}
 		index += c;
 		first += c;
@@ -143,6 +220,7 @@ infl_sym(InflState &s, const uint16_t *fast, int fastbits, const uint16_t *count
 }
 
 /* canonical Huffman tables from code lengths; false = over-subscribed set of lengths */
+template <int S>
 INFL_HD bool
 infl_build(const uint8_t *lens, int n, uint16_t *fast, int fastbits, uint16_t *count, uint16_t *sym)
 {
@@ -152,28 +230,28 @@ infl_build(const uint8_t *lens, int n, uint16_t *fast, int fastbits, uint16_t *c
 	uint32_t	code = 0;
 
 	for (int i = 0; i < 16; i++)
-		count[i] = 0;
+		count[i * S] = 0;
 	for (int i = 0; i < n; i++)
-		count[lens[i]]++;
+		count[lens[i] * S]++;
 	for (int len = 1; len <= 15; len++)
 	{
 		left <<= 1;
-		left -= count[len];
+		left -= count[len * S];
 		if (left < 0)
 			return false;
 	}
 	offs[1] = 0;
 	for (int len = 1; len < 15; len++)
-		offs[len + 1] = offs[len] + count[len];
+		offs[len + 1] = offs[len] + count[len * S];
 	for (int i = 0; i < n; i++)
 		if (lens[i])
-			sym[offs[lens[i]]++] = (uint16_t) i;
+			sym[(offs[lens[i]]++) * S] = (uint16_t) i;
 	for (int i = 0; i < (1 << fastbits); i++)
-		fast[i] = 0;
+		fast[i * S] = 0;
 	next[0] = 0;
 	for (int len = 1; len <= 15; len++)
 	{
-		code = (code + (len > 1 ? count[len - 1] : 0)) << 1;
+		code = (code + (len > 1 ? count[(len - 1) * S] : 0)) << 1;
 		next[len] = (uint16_t) code;
 	}
 	for (int i = 0; i < n; i++)
@@ -191,7 +269,7 @@ infl_build(const uint8_t *lens, int n, uint16_t *fast, int fastbits, uint16_t *c
 				c >>= 1;
 			}
 			for (uint32_t j = rev; j < (1u << fastbits); j += 1u << l)
-				fast[j] = (uint16_t) ((i << 4) | l);
+				fast[j * S] = (uint16_t) ((i << 4) | l);
 		}
 		else if (l)
 			next[l]++;
@@ -200,8 +278,9 @@ infl_build(const uint8_t *lens, int n, uint16_t *fast, int fastbits, uint16_t *c
 }
 
 /* block header at the current position: sets phase / stored_*; returns INFL_MORE / INFL_STORED / INFL_ERROR */
+template <int S>
 INFL_HD int
-infl_block_header(InflState &s, InflTables &T)
+infl_block_header(InflState &s, const InflView<S> &T)
 {
 	uint32_t	type;
 
@@ -235,10 +314,10 @@ infl_block_header(InflState &s, InflTables &T)
 	{
 		for (int i = 0; i < 288; i++)
 			T.lens[i] = (uint8_t) (i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
-		infl_build(T.lens, 288, T.lfast, INFL_FAST_L, T.lcount, T.lsym);
+		infl_build<S>(T.lens, 288, T.lfast, T.lbits, T.lcount, T.lsym);
 		for (int i = 0; i < 32; i++)
 			T.lens[i] = 5;
-		infl_build(T.lens, 32, T.dfast, INFL_FAST_D, T.dcount, T.dsym);
+		infl_build<S>(T.lens, 32, T.dfast, T.dbits, T.dcount, T.dsym);
 		s.phase = 1;
 		return INFL_MORE;
 	}
@@ -263,14 +342,14 @@ infl_block_header(InflState &s, InflTables &T)
 			cl[pos] = (uint8_t) infl_bits(s, 3);
 		}
 		/* the code-length code borrows the literal tables (at most 7-bit codes) */
-		if (!infl_build(cl, 19, T.lfast, 7, T.lcount, T.lsym))
+		if (!infl_build<S>(cl, 19, T.lfast, 7, T.lcount, T.lsym))
 			return INFL_ERROR;
 		while (i < hlit + hdist)
 		{
 			int			sy;
 
 			infl_refill(s);
-			sy = infl_sym(s, T.lfast, 7, T.lcount, T.lsym);
+			sy = infl_sym<S>(s, T.lfast, 7, T.lcount, T.lsym);
 			if (sy < 0)
 				return INFL_ERROR;
 			if (sy < 16)
@@ -299,10 +378,9 @@ infl_block_header(InflState &s, InflTables &T)
 		}
 		if (T.lens[256] == 0)
 			return INFL_ERROR;		/* no end-of-block code */
-		/* distance lengths first: building the literal tables overwrites nothing they need, but keep them apart */
-		if (!infl_build(T.lens + hlit, (int) hdist, T.dfast, INFL_FAST_D, T.dcount, T.dsym))
+		if (!infl_build<S>(T.lens + hlit, (int) hdist, T.dfast, T.dbits, T.dcount, T.dsym))
 			return INFL_ERROR;
-		if (!infl_build(T.lens, (int) hlit, T.lfast, INFL_FAST_L, T.lcount, T.lsym))
+		if (!infl_build<S>(T.lens, (int) hlit, T.lfast, T.lbits, T.lcount, T.lsym))
 			return INFL_ERROR;
 		s.phase = 1;
 		return INFL_MORE;
@@ -310,12 +388,51 @@ infl_block_header(InflState &s, InflTables &T)
 	return INFL_ERROR;
 }
 
+/* length and distance of the match whose length symbol is sy (257..285); false = bad code */
+template <int S>
+INFL_HD bool
+infl_lendist(InflState &s, const InflView<S> &T, int sy, uint32_t *lenp, uint32_t *distp)
+{
+	uint32_t	len,
+				dist;
+	int			ds;
+
+	sy -= 257;
+	if (sy >= 29)
+		return false;
+	if (sy < 8)
+		len = 3 + (uint32_t) sy;
+	else if (sy == 28)
+		len = 258;
+	else
+	{
+		const int	ext = (sy - 4) >> 2;
+
+		len = 3 + ((4u + ((uint32_t) sy & 3u)) << ext) + infl_bits(s, ext);
+	}
+	ds = infl_sym<S>(s, T.dfast, T.dbits, T.dcount, T.dsym);
+	if (ds < 0 || ds >= 30)
+		return false;
+	if (ds < 4)
+		dist = 1 + (uint32_t) ds;
+	else
+	{
+		const int	ext = (ds - 2) >> 1;
+
+		dist = 1 + ((2u + ((uint32_t) ds & 1u)) << ext) + infl_bits(s, ext);
+	}
+	*lenp = len;
+	*distp = dist;
+	return true;
+}
+
 /*
  * Decode until the queue holds INFL_QN entries, a block ends in a way the caller must act on, or the stream ends.
  * *n = entries queued.
  */
+template <int S>
 INFL_HD int
-infl_step(InflState &s, InflTables &T, uint32_t *q, int *n)
+infl_step(InflState &s, const InflView<S> &T, uint32_t *q, int *n)
 {
 	int			cnt = 0;
 
@@ -329,7 +446,7 @@ infl_step(InflState &s, InflTables &T, uint32_t *q, int *n)
 		}
 		if (s.phase == 0)
 		{
-			const int	rc = infl_block_header(s, T);
+			const int	rc = infl_block_header<S>(s, T);
 
 			if (rc != INFL_MORE)
 			{
@@ -342,7 +459,7 @@ infl_step(InflState &s, InflTables &T, uint32_t *q, int *n)
 			int			sy;
 
 			infl_refill(s);
-			sy = infl_sym(s, T.lfast, INFL_FAST_L, T.lcount, T.lsym);
+			sy = infl_sym<S>(s, T.lfast, T.lbits, T.lcount, T.lsym);
 			if (sy < 0)
 				return INFL_ERROR;
 			if (sy < 256)
@@ -356,32 +473,9 @@ infl_step(InflState &s, InflTables &T, uint32_t *q, int *n)
 			{
 				uint32_t	len,
 							dist;
-				int			ds;
 
-				sy -= 257;
-				if (sy >= 29)
+				if (!infl_lendist<S>(s, T, sy, &len, &dist))
 					return INFL_ERROR;
-				if (sy < 8)
-					len = 3 + (uint32_t) sy;
-				else if (sy == 28)
-					len = 258;
-				else
-				{
-					const int	ext = (sy - 4) >> 2;
-
-					len = 3 + ((4u + ((uint32_t) sy & 3u)) << ext) + infl_bits(s, ext);
-				}
-				ds = infl_sym(s, T.dfast, INFL_FAST_D, T.dcount, T.dsym);
-				if (ds < 0 || ds >= 30)
-					return INFL_ERROR;
-				if (ds < 4)
-					dist = 1 + (uint32_t) ds;
-				else
-				{
-					const int	ext = (ds - 2) >> 1;
-
-					dist = 1 + ((2u + ((uint32_t) ds & 1u)) << ext) + infl_bits(s, ext);
-				}
 				q[cnt++] = len | (dist << 9);
 			}
 		}
@@ -392,6 +486,75 @@ infl_step(InflState &s, InflTables &T, uint32_t *q, int *n)
 		}
 		if (infl_consumed(s) > s.inlen)
 			return INFL_ERROR;
+	}
+}
+
+/*
+ * A whole stream by one thread, output written as it is decoded.  true = the final block ended cleanly (the caller
+ * still checks the produced length and the Adler-32 trailer at infl_consumed()).
+ */
+template <int S>
+INFL_HD bool
+infl_run(InflState &s, const InflView<S> &T, uint8_t *out, uint32_t cap, uint32_t *produced)
+{
+	uint32_t	pos = 0;
+
+	*produced = 0;
+	for (;;)
+	{
+		if (s.phase == 2)
+		{
+			*produced = pos;
+			return true;
+		}
+		if (s.phase == 0)
+		{
+			const int	rc = infl_block_header<S>(s, T);
+
+			if (rc == INFL_ERROR)
+				return false;
+			if (rc == INFL_STORED)
+			{
+				if (s.stored_len > cap - pos)
+					return false;
+				for (uint32_t i = 0; i < s.stored_len; i++)
+					out[pos + i] = s.in[s.stored_src + i];
+				pos += s.stored_len;
+				continue;
+			}
+		}
+		for (;;)
+		{
+			int			sy;
+
+			infl_refill(s);
+			sy = infl_sym<S>(s, T.lfast, T.lbits, T.lcount, T.lsym);
+			if (sy < 0)
+				return false;
+			if (sy < 256)
+			{
+				if (pos >= cap)
+					return false;
+				out[pos++] = (uint8_t) sy;
+			}
+			else if (sy == 256)
+			{
+				s.phase = s.final ? 2 : 0;
+				break;
+			}
+			else
+			{
+				uint32_t	len,
+							dist;
+
+				if (!infl_lendist<S>(s, T, sy, &len, &dist) || dist > pos || len > cap - pos)
+					return false;
+				for (uint32_t i = 0; i < len; i++, pos++)
+					out[pos] = out[pos - dist];
+			}
+		}
+		if (infl_consumed(s) > s.inlen)
+			return false;
 	}
 }
 

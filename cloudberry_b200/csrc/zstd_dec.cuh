@@ -141,6 +141,20 @@ z_bits_peek_at(const ZBits &b, int64_t pos, int n)
 		shift = (int) -lo;
 		lo = 0;
 	}
+#ifdef __CUDA_ARCH__
+	{
+		/* two aligned words around the byte that holds bit `lo`: streams lie inside the file image on the device, which
+		 * has readable bytes on both sides (block headers before, the inflate area / 16 spare bytes behind) */
+		const uintptr_t a = (uintptr_t) (b.p + (lo >> 3));
+		const uint64_t *w = (const uint64_t *) (a & ~(uintptr_t) 7);
+		const uint32_t sh = (uint32_t) (a & 7) * 8u;
+		uint64_t	x = w[0] >> sh;
+
+		if (sh)
+			x |= w[1] << (64u - sh);
+		v = (x >> (lo & 7)) & ((1ull << (pos - lo)) - 1);
+	}
+#else
 	{
 		const int64_t byte = lo >> 3;
 		const int	nb = (int) (((pos + 7) >> 3) - byte);	/* bytes that hold bits [lo, pos): at most 5 */
@@ -150,6 +164,7 @@ z_bits_peek_at(const ZBits &b, int64_t pos, int n)
 		v >>= (lo & 7);
 		v &= (1ull << (pos - lo)) - 1;
 	}
+#endif
 	return (uint32_t) (v << shift);
 }
 

@@ -20,12 +20,17 @@ from oracle import aocs_format as A  # noqa: E402
 def main():
     ctx = capi.Context(0)
     target = 256 << 20
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     for case in CASES + ZCASES + ZSTDCASES:
+        if only and not case[0].startswith(tuple(only.split(","))):
+            continue
         name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = case[:9]
         ctype_z = 0 if len(case) <= 9 else 2 if name.startswith("zstd") else 1
         if len(values) < 1000:
             continue
         k = max(1, target // len(raw))
+        content = sum(b["dlen"] for b in A.walk_blocks_ex(raw, checksum))
+        k = max(1, min(k, (1 << 30) // max(len(values), 1), (3 << 30) // max(content, 1)))     # bound rows and inflated bytes
         big = raw * k
         n = len(values) * k
         ctype, attlen, varkind, align = DECODE[typname]
