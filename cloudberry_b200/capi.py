@@ -25,6 +25,10 @@ class CbgpuError(RuntimeError):
         self.code = code
 
 
+class CbgpuVisimapEntry(C.Structure):
+    _fields_ = [("first_row_num", C.c_int64), ("data", C.c_void_p), ("len", C.c_int32)]
+
+
 class CbNumericDatum(C.Structure):
     _fields_ = [("lo", C.c_int64), ("hi", C.c_int64), ("dscale", C.c_int32), ("text", C.c_char * 84)]
 
@@ -133,6 +137,8 @@ def gpu():
             "cbgpu_rel_load_column": (C.c_int, [vp, i32, vp, vp]),
             "cbgpu_rel_read_column": (C.c_int, [vp, i32, i64, i64, vp, vp]),
             "cbgpu_rel_set_visimap": (C.c_int, [vp, vp]),
+            "cbgpu_rel_read_visimap": (C.c_int, [vp, vp]),
+            "cbgpu_aocs_apply_visimap": (C.c_int, [vp, vp, i64, i32, vp, i32, vp, i64, C.POINTER(i64)]),
             "cbgpu_rel_set_dict_hash": (C.c_int, [vp, i32, vp, i32]),
             "cbgpu_rel_set_nrows": (C.c_int, [vp, i64]),
             "cbgpu_rel_col_devptr": (vp, [vp, i32]),
@@ -390,6 +396,33 @@ class DeviceRelation:
         self.ctx.check(self.ctx.L.cbgpu_aocs_decode_column_ex(self.ctx.h, buf.ctypes.data, len(buf), 1 if checksum else 0, compresstype,
                                                               attlen, varkind, typalign, self.h, col, row_offset, C.byref(n)))
         return int(n.value)
+
+    def apply_visimap(self, file_bytes, checksum, entries, row_offset=0):
+        """entries: [(first_row_no, payload bytes or None)] of the segment file's pg_aovisimap rows; file_bytes: any
+        column file of it (cbgpu_aocs_apply_visimap).  Returns the number of rows hidden."""
+        buf = np.frombuffer(file_bytes, dtype=np.uint8)
+        arr = (CbgpuVisimapEntry * max(len(entries), 1))()
+        keep = []
+        for i, (first, payload) in enumerate(entries):
+            arr[i].first_row_num = first
+            if payload is None:
+                arr[i].data = None
+                arr[i].len = 0
+            else:
+                b = C.create_string_buffer(bytes(payload), len(payload))
+                keep.append(b)
+                arr[i].data = C.cast(b, C.c_void_p)
+                arr[i].len = len(payload)
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.cbgpu_aocs_apply_visimap(self.ctx.h, buf.ctypes.data, len(buf), 1 if checksum else 0, arr, len(entries),
+                                                           self.h, row_offset, C.byref(n)))
+        return int(n.value)
+
+    def read_visimap(self):
+        """one bool per row (True = visible)"""
+        out = np.zeros((self.rows() + 7) // 8, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.cbgpu_rel_read_visimap(self.h, out.ctypes.data))
+        return np.unpackbits(out, bitorder="little")[:self.rows()].astype(bool)
 
     def load_column_ptr(self, col, host_ptr):
         self.ctx.check(self.ctx.L.cbgpu_rel_load_column(self.h, col, host_ptr, None))

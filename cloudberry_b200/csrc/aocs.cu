@@ -54,6 +54,7 @@ struct AocsDir
 	long long	zoff;			/* compressed content offset in the file (clen > 0)                   */
 	long long	off;			/* content offset: in the file, or in the inflate area behind it      */
 	long long	rowbase;		/* first output row of the block                                      */
+	long long	first;			/* the block's firstRowNum (AO row number of its first row), -1 if absent */
 	int32_t		rows;
 	int32_t		dlen;
 };
@@ -1200,20 +1201,22 @@ k_aocs_decode(AocsParams P)
 	}
 }
 
-extern "C" int
-cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t attlen, int32_t varkind,
-						 int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows_out)
+/* what the header walk over a column file found */
+struct AocsWalk
 {
-	return cbgpu_aocs_decode_column_ex(ctx, file_bytes, nbytes, checksum, CBGPU_AOCS_COMPRESS_NONE, attlen, varkind, typalign, rel, col,
-									   row_offset, nrows_out);
-}
+	AocsDir    *dir;
+	int64_t		ndir;
+	int64_t		rows;
+	int64_t		ztotal;			/* bytes of the inflate area behind the file image                    */
+	int64_t		ncompressed;
+	bool		anynull;		/* some uncompressed block has a NULL bitmap                          */
+};
 
-extern "C" int
-cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t compress_kind,
-							int32_t attlen, int32_t varkind, int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset,
-							int64_t *nrows_out)
+/* AppendOnlyStorageRead_GetBlockInfo for every block of the file.  compress_kind < 0: contents are not looked at
+ * (visibility map application needs the row numbers only). */
+static int
+aocs_walk(cbgpu_ctx *ctx, const uint8_t *raw, int64_t nbytes, int32_t checksum, int32_t compress_kind, int64_t row_offset, AocsWalk *W)
 {
-	const uint8_t *raw = (const uint8_t *) file_bytes;
 	AocsDir    *dir = NULL;
 	int64_t		ndir = 0,
 				capdir = 0,
@@ -1222,25 +1225,8 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 				ztotal = 0,
 				ncompressed = 0;
 	bool		anynull = false;
-	int		   *d_flag = NULL;
-	uint8_t    *d_scratch = NULL;
-	int		   *d_zlist = NULL;
-	AocsParams	P;
-	uint8_t    *d_raw = NULL;
-	AocsDir    *d_dir = NULL;
-	int			outw;
-	int			nblk;
 
-	*nrows_out = 0;
-	if (col < 0 || col >= rel->ncols)
-		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_aocs_decode_column: bad column%s %lld", "", col);
-	outw = cb_type_w(rel->types[col]);
-	if (attlen > 0 ? (attlen != outw || (attlen != 1 && attlen != 2 && attlen != 4 && attlen != 8))
-		: !((varkind == CBGPU_AOCS_VAR_NUMERIC && rel->types[col] == CB_NUMERIC) || (varkind == CBGPU_AOCS_VAR_BPCHAR1 && outw == 1)))
-		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "AOCS column of length %s%lld does not decode into this relation column", "", attlen);
-	if (typalign != 1 && typalign != 2 && typalign != 4 && typalign != 8)
-		return cb_fail(ctx, CBGPU_ERR_INVALID, "type alignment %s%lld", "", typalign);
-	/* AppendOnlyStorageRead_GetBlockInfo for every block of the file */
+	memset(W, 0, sizeof(*W));
 	while (pos < nbytes)
 	{
 		uint32_t	w0, w1;
@@ -1293,7 +1279,7 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 		}
 		hlen = 8 + (checksum ? 8 : 0) + ext + (has_first ? 8 : 0);
 		stored = clen ? clen : dlen;
-		if (pos + hlen + stored > nbytes || dlen < 16 || (clen && compress_kind != CBGPU_AOCS_COMPRESS_ZLIB && compress_kind != CBGPU_AOCS_COMPRESS_ZSTD))
+		if (pos + hlen + stored > nbytes || dlen < 16 || (clen && compress_kind >= 0 && compress_kind != CBGPU_AOCS_COMPRESS_ZLIB && compress_kind != CBGPU_AOCS_COMPRESS_ZSTD))
 		{
 			free(dir);
 			if (clen && pos + hlen + stored <= nbytes && dlen >= 16)
@@ -1322,15 +1308,78 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 		else
 		{
 			dir[ndir].off = pos + hlen;
-			if (raw[pos + hlen + 2] & 1)	/* DSB_HAS_NULLBITMAP */
+			if (compress_kind >= 0 && (raw[pos + hlen + 2] & 1))	/* DSB_HAS_NULLBITMAP */
 				anynull = true;
 		}
+		dir[ndir].first = -1;
+		if (has_first)
+			memcpy(&dir[ndir].first, raw + pos + hlen - 8, 8);
 		dir[ndir].rowbase = row_offset + rows;
 		dir[ndir].rows = nrow;
 		dir[ndir].dlen = dlen;
 		ndir++;
 		rows += nrow;
 		pos += hlen + (stored + 7) / 8 * 8;
+	}
+	W->dir = dir;
+	W->ndir = ndir;
+	W->rows = rows;
+	W->ztotal = ztotal;
+	W->ncompressed = ncompressed;
+	W->anynull = anynull;
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t attlen, int32_t varkind,
+						 int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows_out)
+{
+	return cbgpu_aocs_decode_column_ex(ctx, file_bytes, nbytes, checksum, CBGPU_AOCS_COMPRESS_NONE, attlen, varkind, typalign, rel, col,
+									   row_offset, nrows_out);
+}
+
+extern "C" int
+cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t compress_kind,
+							int32_t attlen, int32_t varkind, int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset,
+							int64_t *nrows_out)
+{
+	const uint8_t *raw = (const uint8_t *) file_bytes;
+	AocsDir    *dir = NULL;
+	AocsWalk	W;
+	int64_t		ndir = 0,
+				rows = 0,
+				ztotal = 0,
+				ncompressed = 0;
+	bool		anynull = false;
+	int		   *d_flag = NULL;
+	uint8_t    *d_scratch = NULL;
+	int		   *d_zlist = NULL;
+	AocsParams	P;
+	uint8_t    *d_raw = NULL;
+	AocsDir    *d_dir = NULL;
+	int			outw;
+	int			nblk;
+
+	*nrows_out = 0;
+	if (col < 0 || col >= rel->ncols)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_aocs_decode_column: bad column%s %lld", "", col);
+	outw = cb_type_w(rel->types[col]);
+	if (attlen > 0 ? (attlen != outw || (attlen != 1 && attlen != 2 && attlen != 4 && attlen != 8))
+		: !((varkind == CBGPU_AOCS_VAR_NUMERIC && rel->types[col] == CB_NUMERIC) || (varkind == CBGPU_AOCS_VAR_BPCHAR1 && outw == 1)))
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "AOCS column of length %s%lld does not decode into this relation column", "", attlen);
+	if (typalign != 1 && typalign != 2 && typalign != 4 && typalign != 8)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "type alignment %s%lld", "", typalign);
+	{
+		const int	rc = aocs_walk(ctx, raw, nbytes, checksum, compress_kind < 0 ? 0 : compress_kind, row_offset, &W);
+
+		if (rc)
+			return rc;
+		dir = W.dir;
+		ndir = W.ndir;
+		rows = W.rows;
+		ztotal = W.ztotal;
+		ncompressed = W.ncompressed;
+		anynull = W.anynull;
 	}
 	if (row_offset < 0 || row_offset + rows > rel->capacity)
 	{
@@ -1450,5 +1499,323 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 	CB_CUDA(ctx, cudaFreeAsync(d_dir, ctx->stream));
 	free(dir);
 	*nrows_out = rows;
+	return cbgpu_check_status(ctx);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Visibility map: pg_aovisimap entries -> the relation's one-bit-per-row visibility bitmap.
+ * AppendOnlyVisimap_IsVisible (access/appendonly/appendonly_visimap.c:198) looks a row up by its AO row number: the
+ * entry for (rownum / 32768) * 32768 (AppendOnlyVisimapEntry_GetFirstRowNum, appendonly_visimap_entry.c:427-437) holds a
+ * bitmap of HIDDEN rows, bit (rownum - first_row_no) (:451-493), stored through Bitmap_Compress
+ * (utils/misc/bitmap_compression.c:31-190: MSB-first bit stream (utils/misc/bitstream.c:52-70,160-178), 1 bit type, 3
+ * unused, 12 bits block count; per 32-bit block a 2-bit flag: 00 zero, 01 ones, 11 raw 32 bits, 10 repeat the last
+ * block 8-bit-count + 1 times).  A row's number is its block's firstRowNum + its position in the block.
+ *   k_visimap_expand  one thread per entry: the compressed stream -> 1024 words (a 32768-row range)
+ *   k_visimap_apply   one thread per byte of the relation's bitmap (8 rows): block by binary search over the row
+ *                     bases, entry by binary search over the sorted first row numbers, bit test, write 1 = visible
+ * --------------------------------------------------------------------------------------------- */
+#define VISIMAP_RANGE 32768
+#define VISIMAP_WORDS (VISIMAP_RANGE / 32)
+
+struct VisiEntryDev
+{
+	long long	first;			/* first_row_no                                                       */
+	long long	off;			/* payload offset in the uploaded buffer, -1 = NULL visimap (all visible) */
+	int32_t		len;
+	int32_t		pad;
+};
+
+__global__ void
+k_visimap_expand(const uint8_t *data, const VisiEntryDev *ent, int nent, uint32_t *words, int *status)
+{
+	const int	e = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (e >= nent)
+		return;
+	uint32_t   *out = words + (size_t) e * VISIMAP_WORDS;
+	const VisiEntryDev E = ent[e];
+	uint32_t	n = 0;
+
+	if (E.off >= 0)
+	{
+		const uint8_t *p = data + E.off;
+		const uint32_t nbits = ((uint32_t) E.len - 4u) * 8u;
+		uint32_t	pos = 0;
+		bool		bad = false;
+		/* n bits, most significant first; past the end: error (Bitstream_CheckForError) */
+		auto		get = [&](int k) -> uint32_t {
+			uint32_t	v = 0;
+
+			if (pos + (uint32_t) k > nbits)
+			{
+				bad = true;
+				return 0u;
+			}
+			for (int i = 0; i < k; i++, pos++)
+				v = (v << 1) | ((p[4 + (pos >> 3)] >> (7 - (pos & 7))) & 1u);
+			return v;
+		};
+
+		if (E.len < 6 || p[0] != 1 || p[1] || p[2] || p[3])
+			bad = true;			/* AppendOnlyVisimapData.version */
+		else
+		{
+			const uint32_t type = get(1);
+
+			get(3);
+			n = get(12);
+			if (n > VISIMAP_WORDS)
+				bad = true;
+			else if (type == 0)
+			{
+				if (2u + 4u * n > (uint32_t) E.len - 4u)
+					bad = true;
+				else
+					for (uint32_t i = 0; i < n; i++)
+						out[i] = aocs_le32(p + 4 + 2 + 4 * i);
+			}
+			else
+			{
+				uint32_t	last = 0,
+							repeat = 0;
+
+				for (uint32_t i = 0; i < n && !bad; i++)
+				{
+					if (repeat)
+						repeat--;
+					else
+					{
+						const uint32_t flag = get(2);
+
+						if (flag == 0)
+							last = 0;
+						else if (flag == 1)
+							last = 0xFFFFFFFFu;
+						else if (flag == 3)
+							last = get(32);
+						else if (i == 0)
+							bad = true;
+						else
+							repeat = get(8);
+					}
+					out[i] = last;
+				}
+				if (repeat)
+					bad = true;
+			}
+		}
+		if (bad)
+		{
+			atomicExch(status, CBGPU_ERR_CORRUPT);
+			n = 0;
+		}
+	}
+	for (uint32_t i = n; i < VISIMAP_WORDS; i++)
+		out[i] = 0;
+}
+
+__global__ void
+k_visimap_apply(const AocsDir *dir, int ndir, const VisiEntryDev *ent, int nent, const uint32_t *words, uint8_t *vis, long long row_lo,
+				long long row_hi, unsigned long long *nhidden)
+{
+	const long long byte0 = row_lo >> 3;
+	const long long B = byte0 + (long long) blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (B * 8 >= row_hi)
+		return;
+	uint32_t	bits = vis[B];
+	int			blk = -1;
+	int			hidden = 0;
+
+	for (int j = 0; j < 8; j++)
+	{
+		const long long g = B * 8 + j;	/* row of the relation */
+
+		if (g < row_lo || g >= row_hi)
+			continue;
+		if (blk < 0 || g >= dir[blk].rowbase + dir[blk].rows)
+		{
+			int			lo = 0,
+						hi = ndir - 1;
+
+			while (lo < hi)
+			{
+				const int	mid = (lo + hi + 1) >> 1;
+
+				if (dir[mid].rowbase <= g)
+					lo = mid;
+				else
+					hi = mid - 1;
+			}
+			blk = lo;
+		}
+		const long long rn = dir[blk].first + (g - dir[blk].rowbase);
+		const long long want = rn / VISIMAP_RANGE * VISIMAP_RANGE;
+		int			lo = 0,
+					hi = nent - 1;
+		bool		hide = false;
+
+		while (lo < hi)
+		{
+			const int	mid = (lo + hi) >> 1;
+
+			if (ent[mid].first < want)
+				lo = mid + 1;
+			else
+				hi = mid;
+		}
+		if (nent > 0 && ent[lo].first == want)
+		{
+			const uint32_t o = (uint32_t) (rn - want);
+
+			hide = (words[(size_t) lo * VISIMAP_WORDS + (o >> 5)] >> (o & 31)) & 1u;
+		}
+		if (hide)
+		{
+			bits &= ~(1u << j);
+			hidden++;
+		}
+		else
+			bits |= 1u << j;
+	}
+	vis[B] = (uint8_t) bits;
+	if (hidden)
+		atomicAdd(nhidden, (unsigned long long) hidden);
+}
+
+static int
+visi_entry_cmp(const void *a, const void *b)
+{
+	const long long x = ((const VisiEntryDev *) a)->first, y = ((const VisiEntryDev *) b)->first;
+
+	return x < y ? -1 : x > y;
+}
+
+extern "C" int
+cbgpu_aocs_apply_visimap(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, const cbgpu_visimap_entry *entries,
+						 int32_t nentries, cbgpu_rel *rel, int64_t row_offset, int64_t *nhidden_out)
+{
+	AocsWalk	W;
+	VisiEntryDev *ent = NULL;
+	uint8_t    *blob = NULL;
+	int64_t		blobsz = 0;
+	uint8_t    *d_blob = NULL;
+	VisiEntryDev *d_ent = NULL;
+	AocsDir    *d_dir = NULL;
+	uint32_t   *d_words = NULL;
+	unsigned long long *d_cnt = NULL;
+	unsigned long long cnt = 0;
+	int			rc;
+
+	if (nhidden_out)
+		*nhidden_out = 0;
+	if (nentries < 0 || (nentries > 0 && !entries))
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_aocs_apply_visimap: bad entry list%s (%lld)", "", nentries);
+	rc = aocs_walk(ctx, (const uint8_t *) file_bytes, nbytes, checksum, -1, row_offset, &W);
+	if (rc)
+		return rc;
+	if (row_offset < 0 || row_offset + W.rows > rel->capacity)
+	{
+		free(W.dir);
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "AOCS column file holds %s%lld rows: more than the relation has room for", "", W.rows);
+	}
+	for (int64_t i = 0; i < W.ndir; i++)
+		if (W.dir[i].first < 0)
+		{
+			free(W.dir);
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "AOCS block %s%lld carries no first row number: rows cannot be matched to visimap entries", "", i);
+		}
+	if (W.ndir == 0)
+	{
+		free(W.dir);
+		return CBGPU_OK;
+	}
+	ent = (VisiEntryDev *) malloc(sizeof(VisiEntryDev) * (size_t) (nentries ? nentries : 1));
+	for (int i = 0; i < nentries; i++)
+		blobsz += entries[i].data ? ((int64_t) entries[i].len + 7) / 8 * 8 : 0;
+	blob = (uint8_t *) calloc((size_t) blobsz + 8, 1);
+	if (!ent || !blob)
+	{
+		free(W.dir);
+		free(ent);
+		free(blob);
+		return CBGPU_ERR_NOMEM;
+	}
+	blobsz = 0;
+	for (int i = 0; i < nentries; i++)
+	{
+		if (entries[i].first_row_num < 0 || entries[i].first_row_num % VISIMAP_RANGE != 0 || (entries[i].data && entries[i].len < 6))
+		{
+			free(W.dir);
+			free(ent);
+			free(blob);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "visimap entry %s%lld: first row number is not a multiple of 32768, or the data is too short", "", i);
+		}
+		ent[i].first = entries[i].first_row_num;
+		ent[i].len = entries[i].data ? entries[i].len : 0;
+		ent[i].pad = 0;
+		ent[i].off = -1;
+		if (entries[i].data)
+		{
+			ent[i].off = blobsz;
+			memcpy(blob + blobsz, entries[i].data, (size_t) entries[i].len);
+			blobsz += ((int64_t) entries[i].len + 7) / 8 * 8;
+		}
+	}
+	qsort(ent, (size_t) nentries, sizeof(VisiEntryDev), visi_entry_cmp);
+	for (int i = 1; i < nentries; i++)
+		if (ent[i].first == ent[i - 1].first)
+		{
+			free(W.dir);
+			free(ent);
+			free(blob);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "two visimap entries for first row number %s%lld", "", ent[i].first);
+		}
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!rel->visimap)
+	{
+		const size_t bytes = (size_t) ((rel->capacity + 7) / 8);
+
+		CB_CUDA(ctx, cudaMallocAsync(&rel->visimap, ((bytes + 255) & ~(size_t) 255) + 256, ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(rel->visimap, 0xFF, ((bytes + 255) & ~(size_t) 255) + 256, ctx->stream));
+	}
+	CB_CUDA(ctx, cudaMallocAsync(&d_dir, sizeof(AocsDir) * (size_t) W.ndir, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(d_dir, W.dir, sizeof(AocsDir) * (size_t) W.ndir, cudaMemcpyHostToDevice, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&d_cnt, sizeof(unsigned long long), ctx->stream));
+	CB_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
+	if (nentries)
+	{
+		CB_CUDA(ctx, cudaMallocAsync(&d_ent, sizeof(VisiEntryDev) * (size_t) nentries, ctx->stream));
+		CB_CUDA(ctx, cudaMemcpyAsync(d_ent, ent, sizeof(VisiEntryDev) * (size_t) nentries, cudaMemcpyHostToDevice, ctx->stream));
+		CB_CUDA(ctx, cudaMallocAsync(&d_blob, (size_t) blobsz + 8, ctx->stream));
+		CB_CUDA(ctx, cudaMemcpyAsync(d_blob, blob, (size_t) blobsz + 8, cudaMemcpyHostToDevice, ctx->stream));
+		CB_CUDA(ctx, cudaMallocAsync(&d_words, sizeof(uint32_t) * VISIMAP_WORDS * (size_t) nentries, ctx->stream));
+		k_visimap_expand<<<(nentries + 127) / 128, 128, 0, ctx->stream>>>(d_blob, d_ent, nentries, d_words, ctx->d_status);
+		CB_LAUNCHED(ctx, "k_visimap_expand");
+	}
+	{
+		const long long lo = row_offset,
+					hi = row_offset + W.rows;
+		const long long nbytes_out = ((hi + 7) >> 3) - (lo >> 3);
+
+		k_visimap_apply<<<(unsigned) ((nbytes_out + 255) / 256), 256, 0, ctx->stream>>>(d_dir, (int) W.ndir, d_ent, nentries, d_words,
+																						 rel->visimap, lo, hi, d_cnt);
+		CB_LAUNCHED(ctx, "k_visimap_apply");
+	}
+	CB_CUDA(ctx, cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	CB_CUDA(ctx, cudaFreeAsync(d_dir, ctx->stream));
+	CB_CUDA(ctx, cudaFreeAsync(d_cnt, ctx->stream));
+	if (nentries)
+	{
+		CB_CUDA(ctx, cudaFreeAsync(d_ent, ctx->stream));
+		CB_CUDA(ctx, cudaFreeAsync(d_blob, ctx->stream));
+		CB_CUDA(ctx, cudaFreeAsync(d_words, ctx->stream));
+	}
+	free(W.dir);
+	free(ent);
+	free(blob);
+	if (nhidden_out)
+		*nhidden_out = (int64_t) cnt;
 	return cbgpu_check_status(ctx);
 }

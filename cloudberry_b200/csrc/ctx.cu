@@ -570,6 +570,22 @@ cbgpu_rel_set_visimap(cbgpu_rel *rel, const uint8_t *bits)
 }
 
 extern "C" int
+cbgpu_rel_read_visimap(cbgpu_rel *rel, uint8_t *bits)
+{
+	cbgpu_ctx  *ctx = rel->ctx;
+	const size_t bytes = (size_t) ((rel->nrows + 7) / 8);
+
+	if (!rel->visimap)
+	{
+		memset(bits, 0xFF, bytes);
+		return CBGPU_OK;
+	}
+	CB_CUDA(ctx, cudaMemcpyAsync(bits, rel->visimap, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return CBGPU_OK;
+}
+
+extern "C" int
 cbgpu_rel_set_dict_hash(cbgpu_rel *rel, int32_t col, const uint32_t *hashes, int32_t n)
 {
 	cbgpu_ctx  *ctx = rel->ctx;

@@ -111,6 +111,8 @@ int			cbgpu_rel_load_column(cbgpu_rel *rel, int32_t col, const void *host, const
 int			cbgpu_rel_read_column(cbgpu_rel *rel, int32_t col, int64_t lo, int64_t hi, void *host, uint8_t *nulls);
 /* visibility bitmap, one bit per row, 1 = visible (appendonly_visimap.c:198); NULL clears it */
 int			cbgpu_rel_set_visimap(cbgpu_rel *rel, const uint8_t *bits);
+/* the bitmap back ((nrows + 7) / 8 bytes; all ones when the relation has none) */
+int			cbgpu_rel_read_visimap(cbgpu_rel *rel, uint8_t *bits);
 /* per-code hashbpchar values of a dictionary column (so it can be a hash key) */
 int			cbgpu_rel_set_dict_hash(cbgpu_rel *rel, int32_t col, const uint32_t *hashes, int32_t n);
 /* shrink the logical row count (relations allocated at an upper bound, e.g. Motion receive) */
@@ -381,6 +383,25 @@ int			cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t n
 int			cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum,
 										int32_t compresstype, int32_t attlen, int32_t varkind, int32_t typalign,
 										cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows);
+
+/* One row of the table's pg_aovisimap_<oid> for the segment file being loaded (access/appendonly/appendonly_visimap_entry.c:
+ * AppendOnlyVisimapEntry_Copyout :196-262): first_row_no, and the detoasted `visimap` value after its varlena length
+ * word (int32 version + Bitmap_Compress output); data NULL = SQL NULL = every row of the range visible. */
+typedef struct cbgpu_visimap_entry
+{
+	int64_t		first_row_num;
+	const void *data;
+	int32_t		len;
+} cbgpu_visimap_entry;
+/* Visibility of the rows of one segment file (AppendOnlyVisimap_IsVisible, access/appendonly/appendonly_visimap.c:198):
+ * file_bytes = any one column's file of that segment file (only block headers are read: row numbers run
+ * firstRowNum, firstRowNum + 1, ... within a block); entries = the pg_aovisimap rows of that segno, any order.
+ * Writes rows [row_offset, +rows of the file) of the relation's visibility bitmap (1 = visible; rows outside keep
+ * their state, a relation without a bitmap starts all visible); *nhidden = rows hidden.  The entries are expanded
+ * and looked up on the device; a malformed entry is CBGPU_ERR_CORRUPT. */
+int			cbgpu_aocs_apply_visimap(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum,
+									 const cbgpu_visimap_entry *entries, int32_t nentries, cbgpu_rel *rel,
+									 int64_t row_offset, int64_t *nhidden);
 
 /* ------------------------------------------------------------------------------------------
  * synthetic TPC-H shaped generator (harness; same counter-based formulas as

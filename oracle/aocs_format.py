@@ -142,6 +142,8 @@ def ref_lib():
         L.ref_aocs_block_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_int64), C.POINTER(C.c_int)]
         L.ref_aocs_verify_block.argtypes = [C.c_void_p, C.c_int]
+        L.ref_visimap_entry_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.ref_visimap_entry_read.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int]
         _REF = L
     return _REF
 
@@ -454,3 +456,98 @@ def decode_column(raw, typname, checksum, dscale=0, compresstype="zlib"):
     if typname == "float8":
         return np.array(vals, dtype=np.int64).view(np.float64), np.array(nulls, dtype=np.uint8)
     return np.array(vals, dtype=np.int64), np.array(nulls, dtype=np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------
+# visibility map entries (pg_aovisimap_<oid>: segno, first_row_no, visimap)
+# ------------------------------------------------------------------------------------------------
+VISIMAP_RANGE = 32768           # APPENDONLY_VISIMAP_MAX_RANGE (access/appendonly_visimap.h:36): rows per entry
+
+
+def ref_visimap_entry(offsets, raw=False):
+    """payload of pg_aovisimap.visimap (after the varlena length word) hiding the given row offsets of one entry,
+    through the reference's Bitmap_Compress"""
+    L = ref_lib()
+    offs = np.ascontiguousarray(offsets, dtype=np.int32)
+    out = (C.c_ubyte * 4200)()
+    n = L.ref_visimap_entry_write(offs.ctypes.data, len(offs), 1 if raw else 0, out, 4200)
+    if n < 0:
+        raise RuntimeError("reference visimap writer failed")
+    return bytes(out[:n])
+
+
+def visimap_entry_blocks(payload):
+    """the 32-bit bitmap blocks of one entry (bit j of block i = row offset 32 i + j is HIDDEN): int32 version 1, then
+    BitmapDecompress_Init / _Decompress (utils/misc/bitmap_compression.c:31-52, 96-190) over an MSB-first bit stream
+    (utils/misc/bitstream.c:52-70, 160-178): 1 bit compression type, 3 unused, 12 bits block count; type 0 = raw
+    little-endian words from byte 2; type 1 = per block a 2-bit flag: 00 zero, 01 all ones, 11 raw 32 bits, 10 repeat
+    the last block (8-bit count + 1 times in total)"""
+    if len(payload) < 6 or int.from_bytes(payload[0:4], "little") != 1:
+        raise ValueError("visimap entry: version")
+    data = payload[4:]
+    pos = 0
+
+    def get(n):
+        nonlocal pos
+        v = 0
+        for _ in range(n):
+            if pos >> 3 >= len(data):
+                raise ValueError("visimap entry: bit stream ends early")
+            v = (v << 1) | ((data[pos >> 3] >> (7 - (pos & 7))) & 1)
+            pos += 1
+        return v
+    ctype = get(1)
+    get(3)
+    count = get(12)
+    if count > 1024:
+        raise ValueError("visimap entry: block count")
+    out = np.zeros(count, dtype=np.uint32)
+    if ctype == 0:
+        if 2 + 4 * count > len(data):
+            raise ValueError("visimap entry: short raw bitmap")
+        return np.frombuffer(data[2:2 + 4 * count], dtype="<u4").copy()
+    last = 0
+    repeat = 0
+    for i in range(count):
+        if repeat:
+            repeat -= 1
+        else:
+            flag = get(2)
+            if flag == 0:
+                last = 0
+            elif flag == 1:
+                last = 0xFFFFFFFF
+            elif flag == 3:
+                last = get(32)
+            else:
+                if i == 0:
+                    raise ValueError("visimap entry: repeat before any block")
+                repeat = get(8)
+        out[i] = last
+    if repeat:
+        raise ValueError("visimap entry: repeat runs past the last block")
+    return out
+
+
+def visimap_visible(raw, checksum, entries):
+    """one bool per row of a column file, in file order: AppendOnlyVisimap_IsVisible
+    (access/appendonly/appendonly_visimap.c:198 -> AppendOnlyVisimapEntry_IsVisible, appendonly_visimap_entry.c:451-493)
+    for row number = the block's firstRowNum + position in the block.  entries: {first_row_no: payload or None}; a row
+    whose range has no entry, or a NULL visimap, is visible."""
+    decoded = {}
+    out = []
+    for b in walk_blocks_ex(raw, checksum):
+        if b["first"] < 0:
+            raise ValueError("block without a first row number")
+        for i in range(b["rows"]):
+            rn = b["first"] + i
+            first = rn // VISIMAP_RANGE * VISIMAP_RANGE
+            if first not in entries or entries[first] is None:
+                out.append(True)
+                continue
+            if first not in decoded:
+                decoded[first] = visimap_entry_blocks(entries[first])
+            blocks = decoded[first]
+            off = rn - first
+            out.append(not (off // 32 < len(blocks) and (int(blocks[off // 32]) >> (off % 32)) & 1))
+    return np.array(out, dtype=bool)

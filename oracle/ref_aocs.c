@@ -27,6 +27,7 @@
 #include "cdb/cdbappendonlystorage.h"
 #include "cdb/cdbappendonlystorageformat.h"
 #include "utils/datumstreamblock.h"
+#include "utils/bitmap_compression.h"
 #include "utils/numeric.h"
 
 /* port.h routes the printf family to the reference's own src/port implementations, which are not linked here */
@@ -468,4 +469,70 @@ ref_aocs_verify_block(const unsigned char *hdr, int overall_len)
 	if (!AppendOnlyStorageFormat_VerifyBlockChecksum((uint8 *) hdr, overall_len, &stored, &computed))
 		return 2;
 	return 0;
+}
+
+
+/* ---- visibility map entries: the reference's own bitmap codec (utils/misc/bitmap_compression.c, bitstream.c) ---- */
+
+/*
+ * pg_aovisimap.visimap payload (after the varlena length word) for a set of hidden row offsets within one entry's
+ * 32768-row range, as AppendOnlyVisimapEntry_WriteData builds it (appendonly_visimap_entry.c:282-316): int32 version 1,
+ * then Bitmap_Compress(DEFAULT) over the bitmapset's words as 32-bit blocks.  The bitmapset machinery (nodes/bitmapset.c)
+ * is not compiled here; its word count is restated: grown in powers of two to cover the highest member
+ * (AppendOnlyVisimapEntry_HideTuple :556-566), one block when only the low 32 bits of a single word are used, else two
+ * blocks per 64-bit word (BitmapCompress_CalculateBlockCounts, bitmap_compression.c:415-460).
+ * Returns bytes written, -1 on error.
+ */
+int
+ref_visimap_entry_write(const int *offsets, int noffsets, int raw, unsigned char *out, int outcap)
+{
+	uint32		blocks[1024];
+	int			maxoff = -1;
+	int			nwords64 = 0;
+	int			blockCount;
+	int			n;
+
+	if (setjmp(ref_jmp))
+		return -1;
+	memset(blocks, 0, sizeof(blocks));
+	for (int i = 0; i < noffsets; i++)
+	{
+		if (offsets[i] < 0 || offsets[i] >= 32768)
+			return -1;
+		blocks[offsets[i] / 32] |= 1u << (offsets[i] % 32);
+		if (offsets[i] > maxoff)
+			maxoff = offsets[i];
+	}
+	if (maxoff >= 0)
+	{
+		nwords64 = 1;
+		while (nwords64 * 64 <= maxoff)
+			nwords64 *= 2;
+	}
+	blockCount = nwords64 == 0 ? 0 : (nwords64 == 1 && blocks[1] == 0) ? 1 : nwords64 * 2;
+	if (outcap < 4 + 2 + 4 * blockCount + 8)
+		return -1;
+	memset(out, 0, (size_t) outcap);
+	out[0] = 1;					/* version, little endian int32 */
+	/* raw != 0: BITMAP_COMPRESSION_TYPE_NO, which the decompressor also accepts (bitmap_compression.c:118-123) */
+	n = Bitmap_Compress(raw ? BITMAP_COMPRESSION_TYPE_NO : BITMAP_COMPRESSION_TYPE_DEFAULT, blocks, blockCount, out + 4, 2 + 4 * blockCount);
+	return n < 0 ? -1 : 4 + n;
+}
+
+/* the reference's decompressor over such a payload: 32-bit blocks into out, returns the block count or -1 */
+int
+ref_visimap_entry_read(const unsigned char *payload, int len, uint32 *out, int outcap)
+{
+	BitmapDecompressState st;
+
+	if (setjmp(ref_jmp))
+		return -1;
+	if (len < 4 + 2 || payload[0] != 1)
+		return -1;
+	if (!BitmapDecompress_Init(&st, (unsigned char *) payload + 4, len - 4) || BitmapDecompress_HasError(&st))
+		return -1;
+	if (BitmapDecompress_GetBlockCount(&st) > outcap)
+		return -1;
+	BitmapDecompress_Decompress(&st, out, outcap);
+	return BitmapDecompress_GetBlockCount(&st);
 }
