@@ -29,6 +29,19 @@ class CbgpuVisimapEntry(C.Structure):
     _fields_ = [("first_row_num", C.c_int64), ("data", C.c_void_p), ("len", C.c_int32)]
 
 
+class CbAocsColumnSpec(C.Structure):
+    _fields_ = [("relcol", C.c_int32), ("filenum", C.c_int32), ("attlen", C.c_int32), ("varkind", C.c_int32), ("typalign", C.c_int32),
+                ("compresstype", C.c_int32), ("eof", C.c_int64)]
+
+
+def aocs_segfile_path(basepath, segno, filenum):
+    """FormatAOSegmentFileName (access/appendonly/aomd.c:84-117) through cb_aocs_segfile_path; None = out of range"""
+    buf = C.create_string_buffer(4096)
+    if ex().cb_aocs_segfile_path(os.fsencode(basepath), segno, filenum, buf, 4096) != 0:
+        return None
+    return os.fsdecode(buf.value)
+
+
 class CbNumericDatum(C.Structure):
     _fields_ = [("lo", C.c_int64), ("hi", C.c_int64), ("dscale", C.c_int32), ("text", C.c_char * 84)]
 
@@ -207,6 +220,12 @@ def ex():
         L.cb_interconnect_nccl_create.restype = vp
         L.cb_interconnect_nccl_create.argtypes = [vp]
         L.cb_interconnect_destroy.argtypes = [vp]
+        L.cb_aocs_segfile_path.restype = C.c_int
+        L.cb_aocs_segfile_path.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+        L.cb_aocs_load_segfile.restype = C.c_int
+        L.cb_aocs_load_segfile.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(CbAocsColumnSpec), vp, C.c_int64,
+                                           C.POINTER(CbgpuVisimapEntry), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                           C.c_char_p, C.c_size_t]
         L.cb_cluster_create.restype = vp
         L.cb_cluster_create.argtypes = [vp, C.c_int32]
         L.cb_cluster_set_range_table.restype = C.c_int
@@ -417,6 +436,27 @@ class DeviceRelation:
         self.ctx.check(self.ctx.L.cbgpu_aocs_apply_visimap(self.ctx.h, buf.ctypes.data, len(buf), 1 if checksum else 0, arr, len(entries),
                                                            self.h, row_offset, C.byref(n)))
         return int(n.value)
+
+    def load_segfile(self, basepath, segno, checksum, cols, entries=(), row_offset=0):
+        """cols: [(relcol, filenum, attlen, varkind, typalign, compresstype, eof)]; entries: [(first_row_no, payload or None)].
+        Reads the segment file set from disk (cb_aocs_load_segfile); returns (rows, rows hidden)."""
+        specs = (CbAocsColumnSpec * len(cols))(*[CbAocsColumnSpec(*c) for c in cols])
+        arr = (CbgpuVisimapEntry * max(len(entries), 1))()
+        keep = []
+        for i, (first, payload) in enumerate(entries):
+            arr[i].first_row_num = first
+            if payload is not None:
+                b = C.create_string_buffer(bytes(payload), len(payload))
+                keep.append(b)
+                arr[i].data = C.cast(b, C.c_void_p)
+                arr[i].len = len(payload)
+        n, h = C.c_int64(), C.c_int64()
+        err = C.create_string_buffer(512)
+        rc = ex().cb_aocs_load_segfile(self.ctx.h, os.fsencode(basepath), segno, 1 if checksum else 0, len(cols), specs, self.h, row_offset,
+                                       arr, len(entries), C.byref(n), C.byref(h), err, 512)
+        if rc != 0:
+            raise CbgpuError(rc, err.value.decode() or self.ctx.error())
+        return int(n.value), int(h.value)
 
     def read_visimap(self):
         """one bool per row (True = visible)"""

@@ -193,6 +193,34 @@ void		cb_cluster_end(CbCluster *c);
 void		cb_cluster_destroy(CbCluster *c);
 const char *cb_cluster_error(CbCluster *c);
 
+/* ------------------------------------------------------------------------------------------
+ * AOCS segment files from disk (the storage side of aocs_beginscan / open_next_scan_seg, access/aocs/aocsam.c)
+ * ------------------------------------------------------------------------------------------ */
+/* <basepath>[.<(filenum - 1) * 128 + segno>]: FormatAOSegmentFileName (access/appendonly/aomd.c:84-117); basepath =
+ * relpathbackend() of the relation, filenum = pg_attribute_encoding.filenum of the column (1-based), segno 0..127.
+ * 0, or -1 when the arguments are out of range or `out` is too small. */
+int			cb_aocs_segfile_path(const char *basepath, int segno, int filenum, char *out, size_t outsz);
+
+typedef struct CbAocsColumnSpec
+{
+	int32_t		relcol;			/* column of the device relation to fill                               */
+	int32_t		filenum;		/* pg_attribute_encoding.filenum                                       */
+	int32_t		attlen;			/* pg_attribute.attlen: 1/2/4/8, or -1 with varkind                    */
+	int32_t		varkind;		/* CBGPU_AOCS_VAR_*                                                    */
+	int32_t		typalign;		/* bytes                                                               */
+	int32_t		compresstype;	/* CBGPU_AOCS_COMPRESS_*                                               */
+	int64_t		eof;			/* pg_aocsseg.vpinfo eof of the column for this segno; < 0 = whole file */
+} CbAocsColumnSpec;
+/* Reads every listed column's segment file of `segno` up to its EOF and decodes it on the device into rows
+ * [row_offset, +nrows) of `rel` (cbgpu_aocs_decode_column_ex: block CRC-32C when checksum != 0, zlib / zstd
+ * decompression, datum stream decode), checks that the columns agree on the row count, then applies the segment
+ * file's pg_aovisimap rows (cbgpu_aocs_apply_visimap; none and no earlier bitmap = nothing to do).  err (optional)
+ * receives a message naming the file. */
+int			cb_aocs_load_segfile(cbgpu_ctx *ctx, const char *basepath, int segno, int checksum, int ncols,
+								 const CbAocsColumnSpec *cols, cbgpu_rel *rel, int64_t row_offset,
+								 const cbgpu_visimap_entry *entries, int nentries, int64_t *nrows, int64_t *nhidden,
+								 char *err, size_t errsz);
+
 #ifdef __cplusplus
 }
 #endif

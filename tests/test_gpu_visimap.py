@@ -79,3 +79,56 @@ def test_query_sees_only_visible_rows(ctx, oracle):
     assert int(want.rows[0][1]) == int(visible.sum())
     ex.close()
     rel.free()
+
+
+def test_segment_files_from_disk(ctx, oracle, tmp_path):
+    """a two-column table's segment file 1 on disk under the reference's file names, bytes of an aborted append behind the
+    recorded EOF, its pg_aovisimap rows: cb_aocs_load_segfile reads, decodes, hides; a query over it == the oracle"""
+    from test_aocs_format import CASES, ZSTDCASES
+    from cloudberry_b200.relation import HostRelation
+    from cloudberry_b200.tpch import _child_var
+    from gpu_util import canon
+    by = {c[0]: c for c in CASES}
+    price, flags = by["numeric_price"], by["bpchar1_flags"]                      # the same 20011 rows, two columns
+    n = len(price[7])
+    base = str(tmp_path / "24576")
+    p1, p2 = capi.aocs_segfile_path(base, 1, 1), capi.aocs_segfile_path(base, 1, 2)
+    assert p1.endswith("24576.1") and p2.endswith("24576.129")
+    open(p1, "wb").write(flags[6] + b"\xde\xad\xbe\xef" * 100)                  # garbage past the EOF must not be read
+    open(p2, "wb").write(price[6])
+    hidden_rows = np.unique(np.random.default_rng(8).integers(1, n + 1, 700))     # row numbers 1..n (first_row_no 0 covers them)
+    from oracle import aocs_format as A
+    if A.ref_lib() is not None:
+        payload = A.ref_visimap_entry(hidden_rows)
+    else:
+        # no reference library on this box: the uncompressed entry type, assembled by hand (bitmap_compression.c:118-123)
+        words = np.zeros(1024, dtype="<u4")
+        np.bitwise_or.at(words, hidden_rows // 32, (1 << (hidden_rows % 32)).astype(np.uint32))
+        payload = (1).to_bytes(4, "little") + bytes([0x04, 0x00]) + words.tobytes()
+    rel = capi.DeviceRelation(ctx, n, [P.BPCHAR1, P.NUMERIC])
+    cols = [(0, 1, -1, 2, 4, 0, len(flags[6])), (1, 2, -1, 1, 4, 0, -1)]
+    rows, hidden = rel.load_segfile(base, 1, True, cols, [(0, payload)])
+    assert (rows, hidden) == (n, len(hidden_rows))
+    visible = np.ones(n, dtype=bool)
+    visible[hidden_rows - 1] = False
+    assert np.array_equal(rel.read_visimap(), visible)
+    host = HostRelation("t", ["f", "p"], [P.BPCHAR1, P.NUMERIC], [flags[7].astype(np.uint8), price[7]], nulls=[flags[8], None],
+                        visimap=np.packbits(visible, bitorder="little"))
+    sc = P.SeqScan(1, [("f", P.Var(1, 1, P.BPCHAR1)), ("p", P.Var(1, 2, P.NUMERIC, 2))])
+    v = _child_var(sc)
+    plan = P.Agg(sc, P.AGG_HASHED, P.AGGSPLIT_SIMPLE, [1], [("f", v("f")), ("s", P.Aggref(P.AGG_SUM, v("p"))), ("n", P.Aggref(P.AGG_COUNT_STAR))],
+                 num_groups=8)
+    ex = capi.Executor(ctx, [rel])
+    got = ex.run(plan)
+    want = oracle.execute(plan, [[host]])
+    assert canon(got.rows) == canon(want.rows)
+    ex.close()
+    # without the EOF the trailing garbage is read as a block header and refused; a missing file is named
+    with pytest.raises(capi.CbgpuError):
+        rel.load_segfile(base, 1, True, [(0, 1, -1, 2, 4, 0, -1)])
+    with pytest.raises(capi.CbgpuError) as e:
+        rel.load_segfile(base, 2, True, cols)
+    assert "24576.2" in str(e.value)
+    with pytest.raises(capi.CbgpuError):
+        rel.load_segfile(base, 1, True, [(0, 1, -1, 2, 4, 0, len(flags[6]) + 4000)])     # EOF beyond the file
+    rel.free()
