@@ -42,6 +42,47 @@ def aocs_segfile_path(basepath, segno, filenum):
     return os.fsdecode(buf.value)
 
 
+class DeviceDict:
+    """dictionary of a bpchar(n) / varchar / text column, built on the device from the column's files (cbgpu_dict)"""
+
+    def __init__(self, ctx, max_entries=4096, arena_bytes=1 << 20, bpchar=True):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(ctx.L.cbgpu_dict_create(ctx.h, max_entries, arena_bytes, 1 if bpchar else 0, C.byref(h)))
+        self.h = h
+
+    def collect(self, file_bytes, checksum, compresstype=0, typalign=4):
+        buf = np.frombuffer(file_bytes, dtype=np.uint8)
+        self.ctx.check(self.ctx.L.cbgpu_aocs_dict_collect(self.ctx.h, buf.ctypes.data, len(buf), 1 if checksum else 0, compresstype, typalign,
+                                                          self.h))
+
+    def finalize(self):
+        n = C.c_int32()
+        self.ctx.check(self.ctx.L.cbgpu_dict_finalize(self.h, C.byref(n)))
+        return int(n.value)
+
+    def entries(self):
+        out = []
+        n = self.finalize()
+        p = C.c_void_p()
+        ln = C.c_int32()
+        f = self.ctx.L.cbgpu_dict_entry
+        f.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+        for i in range(n):
+            self.ctx.check(f(self.h, i, C.byref(p), C.byref(ln)))
+            out.append(C.string_at(p.value, ln.value))
+        return out
+
+    def lookup(self, text):
+        b = text if isinstance(text, bytes) else text.encode()
+        return int(self.ctx.L.cbgpu_dict_lookup(self.h, b, len(b)))
+
+    def free(self):
+        if self.h:
+            self.ctx.L.cbgpu_dict_free(self.h)
+            self.h = None
+
+
 class CbNumericDatum(C.Structure):
     _fields_ = [("lo", C.c_int64), ("hi", C.c_int64), ("dscale", C.c_int32), ("text", C.c_char * 84)]
 
@@ -151,6 +192,13 @@ def gpu():
             "cbgpu_rel_read_column": (C.c_int, [vp, i32, i64, i64, vp, vp]),
             "cbgpu_rel_set_visimap": (C.c_int, [vp, vp]),
             "cbgpu_rel_read_visimap": (C.c_int, [vp, vp]),
+            "cbgpu_dict_create": (C.c_int, [vp, i32, i64, i32, C.POINTER(vp)]),
+            "cbgpu_dict_free": (None, [vp]),
+            "cbgpu_aocs_dict_collect": (C.c_int, [vp, vp, i64, i32, i32, i32, vp]),
+            "cbgpu_dict_finalize": (C.c_int, [vp, C.POINTER(i32)]),
+            "cbgpu_dict_entry": (C.c_int, [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i32)]),
+            "cbgpu_dict_lookup": (i32, [vp, C.c_char_p, i32]),
+            "cbgpu_aocs_decode_dict_column": (C.c_int, [vp, vp, i64, i32, i32, i32, vp, vp, i32, i64, C.POINTER(i64)]),
             "cbgpu_aocs_apply_visimap": (C.c_int, [vp, vp, i64, i32, vp, i32, vp, i64, C.POINTER(i64)]),
             "cbgpu_rel_set_dict_hash": (C.c_int, [vp, i32, vp, i32]),
             "cbgpu_rel_set_nrows": (C.c_int, [vp, i64]),
@@ -414,6 +462,14 @@ class DeviceRelation:
         n = C.c_int64()
         self.ctx.check(self.ctx.L.cbgpu_aocs_decode_column_ex(self.ctx.h, buf.ctypes.data, len(buf), 1 if checksum else 0, compresstype,
                                                               attlen, varkind, typalign, self.h, col, row_offset, C.byref(n)))
+        return int(n.value)
+
+    def load_aocs_dict_column(self, col, file_bytes, checksum, dictionary, compresstype=0, typalign=4, row_offset=0):
+        """rows of a string column as codes of `dictionary` (cbgpu_aocs_decode_dict_column)"""
+        buf = np.frombuffer(file_bytes, dtype=np.uint8)
+        n = C.c_int64()
+        self.ctx.check(self.ctx.L.cbgpu_aocs_decode_dict_column(self.ctx.h, buf.ctypes.data, len(buf), 1 if checksum else 0, compresstype,
+                                                                typalign, dictionary.h, self.h, col, row_offset, C.byref(n)))
         return int(n.value)
 
     def apply_visimap(self, file_bytes, checksum, entries, row_offset=0):

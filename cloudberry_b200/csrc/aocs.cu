@@ -59,6 +59,16 @@ struct AocsDir
 	int32_t		dlen;
 };
 
+/* one distinct string of a dictionary: tag = 64-bit hash of its bytes (never 0), bytes at arena[off, off + len) */
+struct DictSlot
+{
+	unsigned long long tag;
+	uint32_t	off;
+	uint32_t	len;
+	int32_t		code;			/* assigned by cbgpu_dict_finalize                                    */
+	int32_t		pad;
+};
+
 struct AocsParams
 {
 	const uint8_t *raw;
@@ -71,6 +81,16 @@ struct AocsParams
 	void	   *out;
 	uint8_t    *outnull;		/* NULL when no block of the file has a NULL bitmap                   */
 	int		   *status;
+	/* dictionary columns (CBGPU_AOCS_VAR_DICT): the string set of a cbgpu_dict */
+	struct DictSlot *dslots;
+	uint8_t    *darena;
+	unsigned long long *dcursor;	/* [0] arena bytes used, [1] entries                              */
+	uint32_t	dmask;
+	uint32_t	darena_cap;
+	int32_t		dmode;			/* 1 collect distinct strings, 2 look codes up                        */
+	int32_t		dtrim;			/* bpchar: trailing blanks do not count (bcTruelen, utils/adt/varchar.c) */
+	int32_t		doutw;			/* 1 (CB_DICT8) or 4 (CB_DICT32)                                      */
+	int32_t		dmax;			/* entries the table may hold                                         */
 };
 
 #define AOCS_WARPS 4
@@ -785,6 +805,88 @@ k_aocs_unzstd(uint8_t *raw, const AocsDir *dir, int nblocks, int *status, int *a
 }
 
 /* value of the datum at d (fixed width: the value; numeric: scaled integer; char(1): the byte) */
+/* ---------------------------------------------------------------------------------------------
+ * Dictionary columns: bpchar(n) / varchar / text values become codes into a per-column dictionary (data
+ * layout: CB_DICT8 / CB_DICT32 with a per-code hashbpchar).  Two passes over the column's files, both through the same
+ * block decode: COLLECT inserts every physical datum's bytes into an open-addressing set keyed by a 64-bit hash (claim
+ * by compare-and-swap on the tag; the winner copies the bytes into the arena; nobody waits on anybody, so lanes of one
+ * warp hitting the same string cannot stall each other); cbgpu_dict_finalize orders the distinct strings on the host and
+ * assigns codes; LOOKUP finds the tag again and now also compares the bytes, so two different strings with one 64-bit
+ * hash are reported (CBGPU_ERR_UNSUPPORTED) instead of sharing a code.
+ * --------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ unsigned long long
+dict_hash64(const uint8_t *p, int n)
+{
+	unsigned long long h = 0xcbf29ce484222325ull;	/* FNV-1a, then a finaliser */
+
+	for (int i = 0; i < n; i++)
+		h = (h ^ p[i]) * 0x100000001b3ull;
+	h ^= h >> 32;
+	h *= 0xd6e8feb86659fd93ull;
+	h ^= h >> 32;
+	return h ? h : 1ull;
+}
+
+__device__ __forceinline__ int64_t
+aocs_dict_value(const AocsParams &P, const uint8_t *body, int len)
+{
+	if (P.dtrim)
+		while (len > 0 && body[len - 1] == ' ')
+			len--;
+	const unsigned long long tag = dict_hash64(body, len);
+	uint32_t	i = (uint32_t) tag & P.dmask;
+
+	for (uint32_t probes = 0; probes <= P.dmask; probes++, i = (i + 1) & P.dmask)
+	{
+		DictSlot   *sl = P.dslots + i;
+		unsigned long long t = sl->tag;
+
+		if (t == 0 && P.dmode == 1)
+		{
+			t = atomicCAS(&sl->tag, 0ull, tag);
+			if (t == 0)
+			{
+				/* ours: room in the arena, then the bytes */
+				const unsigned long long off = atomicAdd(P.dcursor, (unsigned long long) ((len + 3) & ~3));
+
+				if (atomicAdd(P.dcursor + 1, 1ull) >= (unsigned long long) P.dmax || off + (unsigned long long) len > P.darena_cap)
+				{
+					atomicExch(P.status, CBGPU_ERR_NOMEM);
+					sl->len = 0;
+					sl->off = 0;
+					return 0;
+				}
+				for (int k = 0; k < len; k++)
+					P.darena[off + k] = body[k];
+				sl->off = (uint32_t) off;
+				sl->len = (uint32_t) len;
+				return 0;
+			}
+		}
+		if (t == tag)
+		{
+			if (P.dmode == 1)
+				return 0;
+			/* lookup: the dictionary is final, compare the bytes */
+			bool		same = sl->len == (uint32_t) len;
+
+			for (int k = 0; same && k < len; k++)
+				same = P.darena[sl->off + k] == body[k];
+			if (!same)
+			{
+				atomicExch(P.status, CBGPU_ERR_UNSUPPORTED);	/* two strings, one 64-bit hash */
+				return 0;
+			}
+			return sl->code;
+		}
+		if (t == 0)
+			break;
+	}
+	/* lookup of a string the collect pass never saw, or a full table */
+	atomicExch(P.status, P.dmode == 1 ? CBGPU_ERR_NOMEM : CBGPU_ERR_INVALID);
+	return 0;
+}
+
 __device__ __forceinline__ int64_t
 aocs_value(const AocsParams &P, const uint8_t *d)
 {
@@ -810,6 +912,13 @@ aocs_value(const AocsParams &P, const uint8_t *d)
 		if (size - hdr < 2 || !aocs_numeric(d + hdr, size - hdr, P.dscale, &v))
 			atomicExch(P.status, CBGPU_ERR_OVERFLOW);
 	}
+	else if (P.varkind == CBGPU_AOCS_VAR_DICT)
+	{
+		if (hdr == 4 && (b0 & 3u) != 0)
+			atomicExch(P.status, CBGPU_ERR_UNSUPPORTED);	/* compressed or external varlena: not stored in AOCS blocks */
+		else
+			v = aocs_dict_value(P, d + hdr, size - hdr);
+	}
 	else
 		v = size - hdr > 0 ? (int64_t) d[hdr] : (int64_t) ' ';
 	return v;
@@ -818,7 +927,9 @@ aocs_value(const AocsParams &P, const uint8_t *d)
 __device__ __forceinline__ void
 aocs_store(const AocsParams &P, int64_t orow, int64_t v, bool isnull)
 {
-	switch (P.attlen > 0 ? P.attlen : (P.varkind == CBGPU_AOCS_VAR_NUMERIC ? 8 : 1))
+	if (!P.out)
+		return;					/* collecting a dictionary: nothing is stored */
+	switch (P.attlen > 0 ? P.attlen : (P.varkind == CBGPU_AOCS_VAR_NUMERIC ? 8 : P.varkind == CBGPU_AOCS_VAR_DICT ? P.doutw : 1))
 	{
 		case 1: ((uint8_t *) P.out)[orow] = (uint8_t) v; break;
 		case 2: ((int16_t *) P.out)[orow] = (int16_t) v; break;
@@ -1170,30 +1281,9 @@ k_aocs_decode(AocsParams P)
 						}
 					}
 					else
-					{
-						const uint8_t *d = data + s_off[w][k];
-						const uint32_t b0 = d[0];
-						const int	hdr = (b0 & 1u) ? 1 : 4;
-						const int	size = (b0 & 1u) ? (int) (b0 >> 1) : (int) ((aocs_le32(d) >> 2) & 0x3FFFFFFFu);
-
-						if (P.varkind == CBGPU_AOCS_VAR_NUMERIC)
-						{
-							if (size - hdr < 2 || !aocs_numeric(d + hdr, size - hdr, P.dscale, &v))
-								atomicExch(P.status, CBGPU_ERR_OVERFLOW);
-						}
-						else
-							v = size - hdr > 0 ? (int64_t) d[hdr] : (int64_t) ' ';
-					}
+						v = aocs_value(P, data + s_off[w][k]);
 				}
-				switch (P.attlen > 0 ? P.attlen : (P.varkind == CBGPU_AOCS_VAR_NUMERIC ? 8 : 1))
-				{
-					case 1: ((uint8_t *) P.out)[orow] = (uint8_t) v; break;
-					case 2: ((int16_t *) P.out)[orow] = (int16_t) v; break;
-					case 4: ((int32_t *) P.out)[orow] = (int32_t) v; break;
-					default: ((int64_t *) P.out)[orow] = v; break;
-				}
-				if (P.outnull)
-					P.outnull[orow] = isnull ? 1 : 0;
+				aocs_store(P, orow, v, isnull);
 			}
 			phys += (uint32_t) cnt;
 			__syncwarp();
@@ -1338,10 +1428,44 @@ cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 									   row_offset, nrows_out);
 }
 
+/* a dictionary: the device string set, and after finalize its entries on the host in code order */
+struct cbgpu_dict
+{
+	cbgpu_ctx  *ctx;
+	DictSlot   *d_slots;
+	uint8_t    *d_arena;
+	unsigned long long *d_cursor;
+	uint32_t   *d_hashes;		/* per code, after finalize                                           */
+	uint32_t	nslots;
+	uint32_t	arena_cap;
+	int32_t		max_entries;
+	int32_t		bpchar;
+	int32_t		finalized;
+	int32_t		n;
+	char	   *texts;			/* host copy of the arena                                             */
+	uint32_t   *off, *len;		/* per code                                                           */
+	int32_t    *sorted;			/* codes in memcmp order == identity; kept for lookups: slot index per code */
+};
+
+static int	aocs_decode_impl(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t compress_kind, int32_t attlen,
+							 int32_t varkind, int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows_out,
+							 const cbgpu_dict *dict, int dmode);
+
 extern "C" int
 cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t compress_kind,
 							int32_t attlen, int32_t varkind, int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset,
 							int64_t *nrows_out)
+{
+	if (varkind == CBGPU_AOCS_VAR_DICT)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "dictionary columns are decoded by cbgpu_aocs_decode_dict_column%s (%lld)", "", varkind);
+	return aocs_decode_impl(ctx, file_bytes, nbytes, checksum, compress_kind, attlen, varkind, typalign, rel, col, row_offset, nrows_out,
+							NULL, 0);
+}
+
+static int
+aocs_decode_impl(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t compress_kind, int32_t attlen,
+				 int32_t varkind, int32_t typalign, cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows_out,
+				 const cbgpu_dict *dict, int dmode)
 {
 	const uint8_t *raw = (const uint8_t *) file_bytes;
 	AocsDir    *dir = NULL;
@@ -1361,12 +1485,18 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 	int			nblk;
 
 	*nrows_out = 0;
-	if (col < 0 || col >= rel->ncols)
-		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_aocs_decode_column: bad column%s %lld", "", col);
-	outw = cb_type_w(rel->types[col]);
-	if (attlen > 0 ? (attlen != outw || (attlen != 1 && attlen != 2 && attlen != 4 && attlen != 8))
-		: !((varkind == CBGPU_AOCS_VAR_NUMERIC && rel->types[col] == CB_NUMERIC) || (varkind == CBGPU_AOCS_VAR_BPCHAR1 && outw == 1)))
-		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "AOCS column of length %s%lld does not decode into this relation column", "", attlen);
+	if (dmode != 1)
+	{
+		if (col < 0 || col >= rel->ncols)
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_aocs_decode_column: bad column%s %lld", "", col);
+		outw = cb_type_w(rel->types[col]);
+		if (attlen > 0 ? (attlen != outw || (attlen != 1 && attlen != 2 && attlen != 4 && attlen != 8))
+			: !((varkind == CBGPU_AOCS_VAR_NUMERIC && rel->types[col] == CB_NUMERIC) || (varkind == CBGPU_AOCS_VAR_BPCHAR1 && outw == 1) ||
+				(varkind == CBGPU_AOCS_VAR_DICT && (rel->types[col] == CB_DICT8 || rel->types[col] == CB_DICT32))))
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "AOCS column of length %s%lld does not decode into this relation column", "", attlen);
+	}
+	else
+		outw = 0;
 	if (typalign != 1 && typalign != 2 && typalign != 4 && typalign != 8)
 		return cb_fail(ctx, CBGPU_ERR_INVALID, "type alignment %s%lld", "", typalign);
 	{
@@ -1381,7 +1511,7 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 		ncompressed = W.ncompressed;
 		anynull = W.anynull;
 	}
-	if (row_offset < 0 || row_offset + rows > rel->capacity)
+	if (dmode != 1 && (row_offset < 0 || row_offset + rows > rel->capacity))
 	{
 		free(dir);
 		return cb_fail(ctx, CBGPU_ERR_INVALID, "AOCS column file holds %s%lld rows: more than the relation has room for", "", rows);
@@ -1459,7 +1589,7 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 				CB_LAUNCHED(ctx, "k_aocs_inflate");
 			}
 		}
-		if (!anynull && !rel->nulls[col])
+		if (dmode != 1 && !anynull && !rel->nulls[col])
 		{
 			/* whether an inflated block carries a NULL bitmap is only known now */
 			CB_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1468,7 +1598,7 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 		}
 		CB_CUDA(ctx, cudaFreeAsync(d_flag, ctx->stream));
 	}
-	if (anynull && !rel->nulls[col])
+	if (dmode != 1 && anynull && !rel->nulls[col])
 	{
 		int			rc = cbgpu_rel_add_nullmap(rel, col);
 
@@ -1488,10 +1618,25 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 	P.attlen = attlen;
 	P.varkind = varkind;
 	P.typalign = typalign;
-	P.dscale = rel->dscales[col];
-	P.out = rel->data[col];
-	P.outnull = rel->nulls[col];
+	if (dmode != 1)
+	{
+		P.dscale = rel->dscales[col];
+		P.out = rel->data[col];
+		P.outnull = rel->nulls[col];
+	}
 	P.status = ctx->d_status;
+	if (dict)
+	{
+		P.dslots = dict->d_slots;
+		P.darena = dict->d_arena;
+		P.dcursor = dict->d_cursor;
+		P.dmask = dict->nslots - 1;
+		P.darena_cap = dict->arena_cap;
+		P.dmode = dmode;
+		P.dtrim = dict->bpchar;
+		P.doutw = outw;
+		P.dmax = dict->max_entries;
+	}
 	k_aocs_decode<<<nblk, AOCS_WARPS * 32, 0, ctx->stream>>>(P);
 	CB_LAUNCHED(ctx, "k_aocs_decode");
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));	/* the caller's file buffer and `dir` are free again */
@@ -1500,6 +1645,223 @@ cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbyt
 	free(dir);
 	*nrows_out = rows;
 	return cbgpu_check_status(ctx);
+}
+
+/* ---- dictionaries ---- */
+extern "C" int
+cbgpu_dict_create(cbgpu_ctx *ctx, int32_t max_entries, int64_t arena_bytes, int32_t bpchar, cbgpu_dict **out)
+{
+	cbgpu_dict *d;
+	uint32_t	nslots = 64;
+
+	*out = NULL;
+	if (max_entries < 1 || max_entries > (1 << 26) || arena_bytes < 16 || arena_bytes > 0xFFFFFFF0ll)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_dict_create: %s%lld entries", "", max_entries);
+	while (nslots < (uint32_t) max_entries * 2u)
+		nslots <<= 1;
+	d = (cbgpu_dict *) calloc(1, sizeof(*d));
+	if (!d)
+		return CBGPU_ERR_NOMEM;
+	d->ctx = ctx;
+	d->nslots = nslots;
+	d->arena_cap = (uint32_t) arena_bytes;
+	d->max_entries = max_entries;
+	d->bpchar = bpchar != 0;
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	CB_CUDA(ctx, cudaMallocAsync(&d->d_slots, sizeof(DictSlot) * (size_t) nslots, ctx->stream));
+	CB_CUDA(ctx, cudaMemsetAsync(d->d_slots, 0, sizeof(DictSlot) * (size_t) nslots, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&d->d_arena, (size_t) arena_bytes + 16, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&d->d_cursor, 2 * sizeof(unsigned long long), ctx->stream));
+	CB_CUDA(ctx, cudaMemsetAsync(d->d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
+	*out = d;
+	return CBGPU_OK;
+}
+
+extern "C" void
+cbgpu_dict_free(cbgpu_dict *d)
+{
+	if (!d)
+		return;
+	cudaSetDevice(d->ctx->device);
+	cudaFreeAsync(d->d_slots, d->ctx->stream);
+	cudaFreeAsync(d->d_arena, d->ctx->stream);
+	cudaFreeAsync(d->d_cursor, d->ctx->stream);
+	if (d->d_hashes)
+		cudaFreeAsync(d->d_hashes, d->ctx->stream);
+	free(d->texts);
+	free(d->off);
+	free(d->len);
+	free(d->sorted);
+	free(d);
+}
+
+extern "C" int
+cbgpu_aocs_dict_collect(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t compresstype, int32_t typalign,
+						cbgpu_dict *dict)
+{
+	int64_t		n = 0;
+
+	if (!dict || dict->finalized)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_aocs_dict_collect: the dictionary is %s (%lld)", dict ? "already finalized" : "missing", 0);
+	return aocs_decode_impl(ctx, file_bytes, nbytes, checksum, compresstype, -1, CBGPU_AOCS_VAR_DICT, typalign, NULL, 0, 0, &n, dict, 1);
+}
+
+extern "C" int
+cbgpu_aocs_decode_dict_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t compresstype,
+							  int32_t typalign, const cbgpu_dict *dict, cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows)
+{
+	int			rc;
+
+	*nrows = 0;
+	if (!dict || !dict->finalized)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_aocs_decode_dict_column: the dictionary is %s (%lld)", dict ? "not finalized" : "missing", 0);
+	if (col >= 0 && col < rel->ncols && rel->types[col] == CB_DICT8 && dict->n > 256)
+		return cb_fail(ctx, CBGPU_ERR_OVERFLOW, "%s%lld distinct values do not fit a CB_DICT8 column", "", dict->n);
+	rc = aocs_decode_impl(ctx, file_bytes, nbytes, checksum, compresstype, -1, CBGPU_AOCS_VAR_DICT, typalign, rel, col, row_offset, nrows, dict, 2);
+	if (rc)
+		return rc;
+	/* the column hashes as the reference's hashbpchar / hashtext would hash the strings: its own copy of the per-code
+	 * hashes, so the relation outlives the dictionary */
+	if (dict->n > 0)
+	{
+		if (rel->dict_hash[col] && rel->dict_n[col] > 0)
+			cudaFreeAsync(rel->dict_hash[col], ctx->stream);
+		CB_CUDA(ctx, cudaMallocAsync(&rel->dict_hash[col], (size_t) dict->n * sizeof(uint32_t), ctx->stream));
+		CB_CUDA(ctx, cudaMemcpyAsync(rel->dict_hash[col], dict->d_hashes, (size_t) dict->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+									 ctx->stream));
+		rel->dict_n[col] = dict->n;
+	}
+	return CBGPU_OK;
+}
+
+static const DictSlot *g_dict_sort_slots;
+static const char *g_dict_sort_texts;
+
+static int
+dict_slot_cmp(const void *a, const void *b)
+{
+	const DictSlot *x = g_dict_sort_slots + *(const int32_t *) a;
+	const DictSlot *y = g_dict_sort_slots + *(const int32_t *) b;
+	const uint32_t m = x->len < y->len ? x->len : y->len;
+	const int	c = memcmp(g_dict_sort_texts + x->off, g_dict_sort_texts + y->off, m);
+
+	if (c)
+		return c;
+	return x->len < y->len ? -1 : x->len > y->len;
+}
+
+extern "C" int
+cbgpu_dict_finalize(cbgpu_dict *d, int32_t *nentries)
+{
+	cbgpu_ctx  *ctx = d->ctx;
+	DictSlot   *slots;
+	unsigned long long cur[2];
+	uint32_t   *hashes;
+	int32_t		n = 0;
+	int			rc;
+
+	if (nentries)
+		*nentries = 0;
+	if (d->finalized)
+	{
+		if (nentries)
+			*nentries = d->n;
+		return CBGPU_OK;
+	}
+	rc = cbgpu_check_status(ctx);
+	if (rc)
+		return rc;
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	CB_CUDA(ctx, cudaMemcpyAsync(cur, d->d_cursor, sizeof(cur), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	slots = (DictSlot *) malloc(sizeof(DictSlot) * (size_t) d->nslots);
+	d->texts = (char *) malloc((size_t) cur[0] + 16);
+	d->sorted = (int32_t *) malloc(sizeof(int32_t) * (size_t) (cur[1] ? cur[1] : 1));
+	d->off = (uint32_t *) malloc(sizeof(uint32_t) * (size_t) (cur[1] ? cur[1] : 1));
+	d->len = (uint32_t *) malloc(sizeof(uint32_t) * (size_t) (cur[1] ? cur[1] : 1));
+	hashes = (uint32_t *) malloc(sizeof(uint32_t) * (size_t) (cur[1] ? cur[1] : 1));
+	if (!slots || !d->texts || !d->sorted || !d->off || !d->len || !hashes)
+	{
+		free(slots);
+		free(hashes);
+		return CBGPU_ERR_NOMEM;
+	}
+	CB_CUDA(ctx, cudaMemcpyAsync(slots, d->d_slots, sizeof(DictSlot) * (size_t) d->nslots, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(d->texts, d->d_arena, (size_t) cur[0], cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (uint32_t i = 0; i < d->nslots; i++)
+		if (slots[i].tag)
+			d->sorted[n++] = (int32_t) i;
+	if ((unsigned long long) n != cur[1])
+	{
+		free(slots);
+		free(hashes);
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "dictionary set holds %s%lld entries, its counter says otherwise", "", n);
+	}
+	g_dict_sort_slots = slots;
+	g_dict_sort_texts = d->texts;
+	qsort(d->sorted, (size_t) n, sizeof(int32_t), dict_slot_cmp);
+	for (int32_t c = 0; c < n; c++)
+	{
+		DictSlot   *sl = slots + d->sorted[c];
+
+		sl->code = c;
+		d->off[c] = sl->off;
+		d->len[c] = sl->len;
+		/* hashbpchar over the blank-trimmed bytes == hashtext over the same bytes: both hash_any (utils/adt/varchar.c:981-1010) */
+		hashes[c] = pg_hash_bytes_host((const unsigned char *) d->texts + sl->off, (int) sl->len);
+	}
+	CB_CUDA(ctx, cudaMemcpyAsync(d->d_slots, slots, sizeof(DictSlot) * (size_t) d->nslots, cudaMemcpyHostToDevice, ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&d->d_hashes, sizeof(uint32_t) * (size_t) (n ? n : 1), ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(d->d_hashes, hashes, sizeof(uint32_t) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	free(slots);
+	free(hashes);
+	d->n = n;
+	d->finalized = 1;
+	if (nentries)
+		*nentries = n;
+	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_dict_entry(const cbgpu_dict *d, int32_t code, const char **text, int32_t *len)
+{
+	if (!d || !d->finalized || code < 0 || code >= d->n)
+		return CBGPU_ERR_INVALID;
+	*text = d->texts + d->off[code];
+	*len = (int32_t) d->len[code];
+	return CBGPU_OK;
+}
+
+extern "C" int32_t
+cbgpu_dict_lookup(const cbgpu_dict *d, const char *text, int32_t len)
+{
+	int32_t		lo = 0,
+				hi;
+
+	if (!d || !d->finalized || len < 0)
+		return -1;
+	if (d->bpchar)
+		while (len > 0 && text[len - 1] == ' ')
+			len--;
+	hi = d->n - 1;
+	while (lo <= hi)
+	{
+		const int32_t mid = (lo + hi) / 2;
+		const uint32_t m = d->len[mid] < (uint32_t) len ? d->len[mid] : (uint32_t) len;
+		int			c = memcmp(d->texts + d->off[mid], text, m);
+
+		if (c == 0)
+			c = d->len[mid] < (uint32_t) len ? -1 : d->len[mid] > (uint32_t) len;
+		if (c == 0)
+			return mid;
+		if (c < 0)
+			lo = mid + 1;
+		else
+			hi = mid - 1;
+	}
+	return -1;
 }
 
 /* ---------------------------------------------------------------------------------------------

@@ -362,6 +362,7 @@ int			cbgpu_motion_broadcast(cbgpu_motion *m, cbgpu_rel *send, int64_t nrows, cb
  * ------------------------------------------------------------------------------------------ */
 #define CBGPU_AOCS_VAR_NUMERIC 1	/* numeric varlena -> int64 scaled by the column's dscale             */
 #define CBGPU_AOCS_VAR_BPCHAR1 2	/* character(1) varlena -> its byte                                   */
+#define CBGPU_AOCS_VAR_DICT 3		/* bpchar(n) / varchar / text -> dictionary code (cbgpu_dict, below)   */
 #define CBGPU_AOCS_COMPRESS_NONE 0	/* compresstype=none, or rle_type with compresslevel 1                */
 #define CBGPU_AOCS_COMPRESS_ZLIB 1	/* compresstype=zlib (any level), or rle_type with compresslevel 2-4   */
 #define CBGPU_AOCS_COMPRESS_ZSTD 2	/* compresstype=zstd (any level)                                       */
@@ -383,6 +384,29 @@ int			cbgpu_aocs_decode_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t n
 int			cbgpu_aocs_decode_column_ex(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum,
 										int32_t compresstype, int32_t attlen, int32_t varkind, int32_t typalign,
 										cbgpu_rel *rel, int32_t col, int64_t row_offset, int64_t *nrows);
+
+/* Dictionary of a bpchar(n) / varchar / text column (DESIGN.md data layout: CB_DICT8 / CB_DICT32 codes + per-code
+ * hashbpchar).  Built on the device from the column's own files in two passes:
+ *   cbgpu_aocs_dict_collect   every segment file of the column: its distinct strings join the set
+ *   cbgpu_dict_finalize       codes 0 .. n-1 in byte-wise (memcmp, shorter first on ties) order of the strings
+ *   cbgpu_aocs_decode_dict_column   every segment file again: rows become codes; the relation column gets the
+ *                             dictionary's per-code hashes (hashbpchar for bpchar: trailing blanks do not count,
+ *                             utils/adt/varchar.c:981; hashtext / hash_any of the bytes otherwise)
+ * One dictionary can serve several columns / relations (join keys must share one).  bpchar != 0: bpchar semantics,
+ * values are compared and kept without their trailing blanks (bpchareq, bcTruelen). */
+typedef struct cbgpu_dict cbgpu_dict;
+int			cbgpu_dict_create(cbgpu_ctx *ctx, int32_t max_entries, int64_t arena_bytes, int32_t bpchar, cbgpu_dict **out);
+void		cbgpu_dict_free(cbgpu_dict *d);
+int			cbgpu_aocs_dict_collect(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum, int32_t compresstype,
+									int32_t typalign, cbgpu_dict *dict);
+int			cbgpu_dict_finalize(cbgpu_dict *d, int32_t *nentries);
+/* entry `code` of a finalized dictionary: *text points at len bytes owned by the dictionary (no terminator) */
+int			cbgpu_dict_entry(const cbgpu_dict *d, int32_t code, const char **text, int32_t *len);
+/* code of a string (e.g. a Const of the plan), -1 when the column never holds it */
+int32_t		cbgpu_dict_lookup(const cbgpu_dict *d, const char *text, int32_t len);
+int			cbgpu_aocs_decode_dict_column(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t checksum,
+										  int32_t compresstype, int32_t typalign, const cbgpu_dict *dict, cbgpu_rel *rel,
+										  int32_t col, int64_t row_offset, int64_t *nrows);
 
 /* One row of the table's pg_aovisimap_<oid> for the segment file being loaded (access/appendonly/appendonly_visimap_entry.c:
  * AppendOnlyVisimapEntry_Copyout :196-262): first_row_no, and the detoasted `visimap` value after its varlena length

@@ -30,7 +30,10 @@ TYPEINFO = {
     "int4": (23, 4, 1, "i", "p"), "int8": (20, 8, 1, "d", "p"), "date": (1082, 4, 1, "i", "p"),
     "float8": (701, 8, 1, "d", "p"), "bool": (16, 1, 1, "c", "p"), "int2": (21, 2, 1, "s", "p"),
     "numeric": (1700, -1, 0, "i", "m"), "bpchar": (1042, -1, 0, "i", "x"),
+    # strings kept whole (dictionary columns): character(n) values arrive blank-padded to n, as bpcharin leaves them
+    "bpchars": (1042, -1, 0, "i", "x"), "varchar": (1043, -1, 0, "i", "x"), "text": (25, -1, 0, "i", "x"),
 }
+STRING_TYPES = ("bpchars", "varchar", "text")
 NBASE = 10000
 
 
@@ -107,7 +110,7 @@ def numeric_from_bytes(data, dscale_out):
 
 
 def bpchar_varlena(text):
-    b = text.encode()
+    b = text if isinstance(text, bytes) else text.encode()
     return int((4 + len(b)) << 2).to_bytes(4, "little") + b
 
 
@@ -198,7 +201,7 @@ def ref_write_column(typname, values, nulls=None, checksum=True, blocksize=32768
         vals = np.ascontiguousarray(values, dtype=np.int64)
         if attlen < 8:
             vals = vals & ((1 << (8 * attlen)) - 1)  # a by-value Datum holds the zero-extended low bytes
-    cap = n * 24 + (n // 100 + 4) * 64 + 4096
+    cap = n * 24 + (n // 100 + 4) * 64 + 4096 + 2 * len(varbuf)
     out = (C.c_ubyte * cap)()
     nb = C.c_int64()
     vb = (C.c_ubyte * max(len(varbuf), 1)).from_buffer_copy(varbuf or b"\0")
@@ -347,7 +350,10 @@ class _Datums:
         else:
             size = (int.from_bytes(blk[p:p + 4], "little") >> 2) & 0x3FFFFFFF
             body = blk[p + 4:p + size]
-        v = numeric_from_bytes(body, self.dscale) if self.typname == "numeric" else (body[0] if len(body) else 32)
+        if self.typname in STRING_TYPES:
+            v = bytes(body)
+        else:
+            v = numeric_from_bytes(body, self.dscale) if self.typname == "numeric" else (body[0] if len(body) else 32)
         p += size
         if p < self.end and blk[p] == 0:
             p = (p + self.alignto - 1) // self.alignto * self.alignto
@@ -455,6 +461,8 @@ def decode_column(raw, typname, checksum, dscale=0, compresstype="zlib"):
             raise ValueError("repeat counts overrun the block")
     if typname == "float8":
         return np.array(vals, dtype=np.int64).view(np.float64), np.array(nulls, dtype=np.uint8)
+    if typname in STRING_TYPES:
+        return [b"" if v == 0 else v for v in vals], np.array(nulls, dtype=np.uint8)
     return np.array(vals, dtype=np.int64), np.array(nulls, dtype=np.uint8)
 
 

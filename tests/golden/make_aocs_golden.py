@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Write tests/golden/aocs_columns.npz (and aocs_zlib_columns.npz / aocs_zstd_columns.npz, bulk-compressed columns): AOCS column files produced by the REFERENCE's own block writer
+"""Write tests/golden/aocs_columns.npz (and aocs_zlib_columns.npz / aocs_zstd_columns.npz, bulk-compressed columns;
+aocs_text_columns.npz, character(n) / varchar columns kept as strings): AOCS column files produced by the REFERENCE's own block writer
 (oracle/_ref/libaocs_ref.so = the reference's datumstreamblock.c + cdbappendonlystorageformat.c + pg_crc32c_sb8.c,
 driven by oracle/ref_aocs.c; run `make -C oracle` first) together with the values that went in.
 
@@ -26,7 +27,11 @@ def main():
                                           compressor=A.zstd_compressor(zstd) if zstd else None)
         zlevel = zlevel or zstd
         out[name + "__raw"] = np.frombuffer(raw, dtype=np.uint8)
-        if typname == "bpchar":
+        if typname in A.STRING_TYPES:
+            w = max([len(v) for v in values] + [1])
+            out[name + "__values"] = np.array([v if isinstance(v, bytes) else v.encode() for v in values], dtype="S%d" % w)
+            out[name + "__lens"] = np.array([len(v) for v in values], dtype=np.int32)      # 'S' arrays drop trailing NULs only
+        elif typname == "bpchar":
             out[name + "__values"] = np.array([ord(v[0]) if v else 32 for v in values], dtype=np.int64)
         elif typname == "float8":
             out[name + "__values"] = np.asarray(values, dtype=np.float64)
@@ -149,6 +154,35 @@ def main():
         blocks = A.walk_blocks_ex(bytes(out[name + "__raw"]), int(c.split("|")[2]))
         print("      kinds", sorted(set(b["kind"] for b in blocks)), "compressed", sum(1 for b in blocks if b["clen"]), "of", len(blocks),
               "file", len(out[name + "__raw"]), "bytes for", sum(b["dlen"] for b in blocks), "of content")
+
+    # ---- character(n) / varchar columns whose values are kept (dictionary columns on the device)
+    out = {}
+    cases = []
+    rng = np.random.default_rng(20260926)
+    n = 20011
+    nul = (rng.random(n) < 0.05).astype(np.uint8)
+    modes = ["REG AIR", "AIR", "RAIL", "SHIP", "TRUCK", "MAIL", "FOB"]
+    shipmode = [modes[i].ljust(10) for i in rng.integers(0, 7, n)]                           # character(10): blank padded
+    add("shipmode_bpchar10_nulls", "bpchars", shipmode, nul, True, 32768)
+    add("shipmode_rle", "bpchars", [modes[i].ljust(10) for i in np.repeat(rng.integers(0, 7, 700), rng.integers(1, 60, 700))], None, True,
+        32768, rle=True)
+    segs = ["AUTOMOBILE", "BUILDING", "FURNITURE", "MACHINERY", "HOUSEHOLD"]
+    add("mktsegment_zlib5", "bpchars", [segs[i].ljust(10) for i in rng.integers(0, 5, n)], None, True, 32768, zlevel=5)
+    nations = ["ALGERIA", "ARGENTINA", "BRAZIL", "CANADA", "EGYPT", "ETHIOPIA", "FRANCE", "GERMANY", "INDIA", "INDONESIA", "IRAN", "IRAQ",
+               "JAPAN", "JORDAN", "KENYA", "MOROCCO", "MOZAMBIQUE", "PERU", "CHINA", "ROMANIA", "SAUDI ARABIA", "VIETNAM", "RUSSIA",
+               "UNITED KINGDOM", "UNITED STATES"]
+    add("n_name_bpchar25", "bpchars", [s.ljust(25) for s in nations], None, True, 32768)
+    # varchar: lengths 0 .. 300 (1-byte and 4-byte varlena headers), trailing blanks that DO count, the empty string
+    words = ["", " ", "a", "a ", "ab", "carefully final deposits", "x" * 126, "y" * 127, "z" * 200, "w" * 300, "quick  ", "quick"]
+    add("varchar_mixed_nulls_8k", "varchar", [words[i] for i in rng.integers(0, len(words), 6000)], (rng.random(6000) < 0.1).astype(np.uint8),
+        False, 8192)
+    add("varchar_many_distinct_zstd", "varchar", ["Customer#%09d" % i for i in rng.integers(0, 3000, n)], None, True, 32768, zstd=3)
+    out["cases"] = np.array(cases)
+    path = os.path.join(ROOT, "tests", "golden", "aocs_text_columns.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(cases), "columns")
+    for c in cases:
+        print("  ", c)
 
 
 if __name__ == "__main__":

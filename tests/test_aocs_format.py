@@ -51,6 +51,21 @@ def golden_zstd():
 ZSTDCASES = list(golden_zstd())
 
 
+def golden_text():
+    """character(n) / varchar columns kept as strings: (name, typname, checksum, blocksize, nblocks, raw, values, nulls,
+    compression: "" / "zlib" / "zstd")"""
+    d = np.load(os.path.join(HERE, "golden", "aocs_text_columns.npz"))
+    for c in d["cases"]:
+        f = str(c).split("|")
+        name, typname, checksum, blocksize, nblocks = f[0], f[1], int(f[2]), int(f[3]), int(f[5])
+        vals = [bytes(v).ljust(int(n), b"\0") for v, n in zip(d[name + "__values"], d[name + "__lens"])]
+        yield (name, typname, checksum, blocksize, nblocks, bytes(d[name + "__raw"]), vals, d[name + "__nulls"],
+               "zstd" if "zstd" in name else "zlib" if "zlib" in name else "")
+
+
+TCASES = list(golden_text())
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_restated_reader_reads_reference_written_columns(case):
     name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = case
@@ -122,6 +137,17 @@ def test_restated_reader_reads_zstd_columns(case):
         assert np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64))
     else:
         assert np.array_equal(got[keep], values[keep])
+
+
+@pytest.mark.parametrize("case", TCASES, ids=[c[0] for c in TCASES])
+def test_restated_reader_reads_string_columns(case):
+    name, typname, checksum, blocksize, nblocks, raw, values, nulls, comp = case
+    if comp == "zstd":
+        pytest.importorskip("pyarrow")
+    assert len(A.walk_blocks_ex(raw, checksum, verify=True)) == nblocks
+    got, gotnull = A.decode_column(raw, typname, checksum, compresstype=comp or "zlib")
+    assert np.array_equal(gotnull, nulls)
+    assert [g for g, z in zip(got, nulls) if not z] == [v for v, z in zip(values, nulls) if not z]
 
 
 @pytest.mark.skipif(A.ref_lib() is None, reason="reference library only where /root/reference exists")
