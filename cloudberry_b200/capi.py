@@ -31,7 +31,21 @@ class CbgpuVisimapEntry(C.Structure):
 
 class CbAocsColumnSpec(C.Structure):
     _fields_ = [("relcol", C.c_int32), ("filenum", C.c_int32), ("attlen", C.c_int32), ("varkind", C.c_int32), ("typalign", C.c_int32),
-                ("compresstype", C.c_int32), ("eof", C.c_int64)]
+                ("compresstype", C.c_int32), ("eof", C.c_int64), ("dict", C.c_void_p)]
+
+
+def aocs_column_spec(c):
+    """(relcol, filenum, attlen, varkind, typalign, compresstype, eof[, DeviceDict]) -> CbAocsColumnSpec"""
+    return CbAocsColumnSpec(*c[:7], c[7].h if len(c) > 7 and c[7] is not None else None)
+
+
+def aocs_dict_collect_segfile(ctx, basepath, segno, checksum, col):
+    """first pass over a string column's segment file (cb_aocs_dict_collect_segfile)"""
+    spec = aocs_column_spec(col)
+    err = C.create_string_buffer(512)
+    rc = ex().cb_aocs_dict_collect_segfile(ctx.h, os.fsencode(basepath), segno, 1 if checksum else 0, C.byref(spec), err, 512)
+    if rc != 0:
+        raise CbgpuError(rc, err.value.decode() or ctx.error())
 
 
 def aocs_segfile_path(basepath, segno, filenum):
@@ -270,6 +284,8 @@ def ex():
         L.cb_interconnect_destroy.argtypes = [vp]
         L.cb_aocs_segfile_path.restype = C.c_int
         L.cb_aocs_segfile_path.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+        L.cb_aocs_dict_collect_segfile.restype = C.c_int
+        L.cb_aocs_dict_collect_segfile.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(CbAocsColumnSpec), C.c_char_p, C.c_size_t]
         L.cb_aocs_load_segfile.restype = C.c_int
         L.cb_aocs_load_segfile.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(CbAocsColumnSpec), vp, C.c_int64,
                                            C.POINTER(CbgpuVisimapEntry), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
@@ -494,9 +510,9 @@ class DeviceRelation:
         return int(n.value)
 
     def load_segfile(self, basepath, segno, checksum, cols, entries=(), row_offset=0):
-        """cols: [(relcol, filenum, attlen, varkind, typalign, compresstype, eof)]; entries: [(first_row_no, payload or None)].
-        Reads the segment file set from disk (cb_aocs_load_segfile); returns (rows, rows hidden)."""
-        specs = (CbAocsColumnSpec * len(cols))(*[CbAocsColumnSpec(*c) for c in cols])
+        """cols: [(relcol, filenum, attlen, varkind, typalign, compresstype, eof[, DeviceDict])]; entries: [(first_row_no,
+        payload or None)].  Reads the segment file set from disk (cb_aocs_load_segfile); returns (rows, rows hidden)."""
+        specs = (CbAocsColumnSpec * len(cols))(*[aocs_column_spec(c) for c in cols])
         arr = (CbgpuVisimapEntry * max(len(entries), 1))()
         keep = []
         for i, (first, payload) in enumerate(entries):

@@ -96,6 +96,30 @@ read_prefix(const char *path, int64_t eof, unsigned char **bufp, int64_t *lenp, 
 }
 
 int
+cb_aocs_dict_collect_segfile(cbgpu_ctx *ctx, const char *basepath, int segno, int checksum, const CbAocsColumnSpec *spec, char *err,
+							 size_t errsz)
+{
+	char		path[4096];
+	unsigned char *buf = NULL;
+	int64_t		len = 0;
+	int			rc;
+
+	if (err && errsz)
+		err[0] = 0;
+	if (!spec || spec->varkind != CBGPU_AOCS_VAR_DICT || !spec->dict ||
+		cb_aocs_segfile_path(basepath, segno, spec->filenum, path, sizeof(path)) != 0)
+		return load_fail(err, errsz, CBGPU_ERR_INVALID, "bad dictionary column specification for %s (%lld)", basepath ? basepath : "", (long long) segno);
+	rc = read_prefix(path, spec->eof, &buf, &len, err, errsz);
+	if (rc != CBGPU_OK)
+		return rc;
+	rc = cbgpu_aocs_dict_collect(ctx, buf, len, checksum, spec->compresstype, spec->typalign, spec->dict);
+	if (rc != CBGPU_OK && err && errsz)
+		snprintf(err, errsz, "%s: %s", path, cbgpu_last_error(ctx));
+	free(buf);
+	return rc;
+}
+
+int
 cb_aocs_load_segfile(cbgpu_ctx *ctx, const char *basepath, int segno, int checksum, int ncols, const CbAocsColumnSpec *cols,
 					 cbgpu_rel *rel, int64_t row_offset, const cbgpu_visimap_entry *entries, int nentries, int64_t *nrows_out,
 					 int64_t *nhidden_out, char *err, size_t errsz)
@@ -128,8 +152,12 @@ cb_aocs_load_segfile(cbgpu_ctx *ctx, const char *basepath, int segno, int checks
 		rc = read_prefix(path, cols[c].eof, &buf, &len, err, errsz);
 		if (rc != CBGPU_OK)
 			break;
-		rc = cbgpu_aocs_decode_column_ex(ctx, buf, len, checksum, cols[c].compresstype, cols[c].attlen, cols[c].varkind, cols[c].typalign,
-										 rel, cols[c].relcol, row_offset, &n);
+		if (cols[c].varkind == CBGPU_AOCS_VAR_DICT)
+			rc = cbgpu_aocs_decode_dict_column(ctx, buf, len, checksum, cols[c].compresstype, cols[c].typalign, cols[c].dict, rel,
+											   cols[c].relcol, row_offset, &n);
+		else
+			rc = cbgpu_aocs_decode_column_ex(ctx, buf, len, checksum, cols[c].compresstype, cols[c].attlen, cols[c].varkind,
+											 cols[c].typalign, rel, cols[c].relcol, row_offset, &n);
 		if (rc != CBGPU_OK)
 		{
 			if (err && errsz)

@@ -210,7 +210,11 @@ typedef struct CbAocsColumnSpec
 	int32_t		typalign;		/* bytes                                                               */
 	int32_t		compresstype;	/* CBGPU_AOCS_COMPRESS_*                                               */
 	int64_t		eof;			/* pg_aocsseg.vpinfo eof of the column for this segno; < 0 = whole file */
+	cbgpu_dict *dict;			/* varkind CBGPU_AOCS_VAR_DICT: the column's (finalized) dictionary    */
 } CbAocsColumnSpec;
+/* first pass for a string column: the distinct values of this segment file join spec->dict (cbgpu_aocs_dict_collect) */
+int			cb_aocs_dict_collect_segfile(cbgpu_ctx *ctx, const char *basepath, int segno, int checksum, const CbAocsColumnSpec *spec,
+										 char *err, size_t errsz);
 /* Reads every listed column's segment file of `segno` up to its EOF and decodes it on the device into rows
  * [row_offset, +nrows) of `rel` (cbgpu_aocs_decode_column_ex: block CRC-32C when checksum != 0, zlib / zstd
  * decompression, datum stream decode), checks that the columns agree on the row count, then applies the segment
