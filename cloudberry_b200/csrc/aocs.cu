@@ -444,80 +444,6 @@ k_aocs_inflate(uint8_t *raw, const AocsDir *dir, int nblocks, int *status, int *
 	}
 }
 
-/*
- * The same, one stream per THREAD: with thousands of compressed blocks in a file the serial decoder is the whole cost and
- * the warp-per-block kernel above spends an issue slot per decoded bit-field on one lane in 32 (measured: issue-bound at
- * ~25 GB/s of output, profiles/r01f_aocs_decode_compressed.txt).  Here every lane runs infl_run() on its own block, its
- * tables interleaved with the other lanes' in shared memory (62 KB per warp, 3 warps per SM); the Adler-32 of the 32
- * outputs is then taken by the whole warp, one block after the other.  Blocks are handed out 32 at a time from a counter.
- */
-#define INFL_LANES_SMEM (INFL_T_ENTRIES * 32 * (int) sizeof(uint16_t))
-
-__global__ void __launch_bounds__(32)
-k_aocs_inflate_lanes(uint8_t *raw, const AocsDir *dir, const int *zlist, int nz, int *status, int *anynull, int *counter)
-{
-	extern __shared__ uint16_t s_area[];
-	const int	lane = threadIdx.x;
-	uint8_t		lens[320];
-
-	if (*status == CBGPU_ERR_CORRUPT)
-		return;
-	for (;;)
-	{
-		int			base = 0;
-
-		if (lane == 0)
-			base = atomicAdd(counter, 32);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= nz)
-			break;
-		const bool	have = base + lane < nz;
-		const AocsDir D = dir[zlist[have ? base + lane : base]];
-		const uint8_t *in = raw + D.zoff;
-		uint8_t    *out = raw + D.off;
-		const uint32_t cap = (uint32_t) D.dlen;
-		const uint32_t inlen = (uint32_t) D.clen;
-		uint32_t	produced = 0,
-					want = 0;
-		bool		ok = true;
-
-		if (have)
-		{
-			InflState	st;
-
-			infl_init(st, in, inlen, 2);
-			ok = infl_zlib_header_ok(in, inlen) && infl_run<32>(st, infl_view_lane(s_area, lane, lens), out, cap, &produced);
-			if (ok)
-			{
-				const uint32_t c = infl_consumed(st);
-
-				ok = produced == cap && c + 4u <= inlen;
-				if (ok)
-					want = ((uint32_t) in[c] << 24) | ((uint32_t) in[c + 1] << 16) | ((uint32_t) in[c + 2] << 8) | (uint32_t) in[c + 3];
-			}
-		}
-		__syncwarp();
-		for (int k = 0; k < 32; k++)
-		{
-			if (!__shfl_sync(0xffffffffu, have && ok ? 1 : 0, k))
-				continue;
-			const uint8_t *o = (const uint8_t *) __shfl_sync(0xffffffffu, (unsigned long long) out, k);
-			const uint32_t a = infl_adler32_warp(o, __shfl_sync(0xffffffffu, cap, k), lane);
-
-			if (lane == k && a != want)
-				ok = false;
-		}
-		if (have)
-		{
-			if (!ok)
-				atomicExch(status, CBGPU_ERR_CORRUPT);
-			else if (cap > 2 && (out[2] & 1u))
-				atomicOr(anynull, 1);
-		}
-		__syncwarp();
-	}
-}
-
 /* ---------------------------------------------------------------------------------------------
  * compresstype=zstd blocks: the same step for Zstandard frames (zstd_dec.cuh; the reference's zstd_decompress,
  * gpcontrib/zstd/zstd_compression.c:142-175).  One warp per storage block = one frame.  Lane 0 parses headers, builds
@@ -1477,7 +1403,6 @@ aocs_decode_impl(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t
 	bool		anynull = false;
 	int		   *d_flag = NULL;
 	uint8_t    *d_scratch = NULL;
-	int		   *d_zlist = NULL;
 	AocsParams	P;
 	uint8_t    *d_raw = NULL;
 	AocsDir    *d_dir = NULL;
@@ -1541,8 +1466,8 @@ aocs_decode_impl(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t
 	{
 		int			flag = 0;
 
-		CB_CUDA(ctx, cudaMallocAsync(&d_flag, 2 * sizeof(int), ctx->stream));	/* NULL-bitmap flag, work counter */
-		CB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), ctx->stream));
+		CB_CUDA(ctx, cudaMallocAsync(&d_flag, sizeof(int), ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
 		if (compress_kind == CBGPU_AOCS_COMPRESS_ZSTD)
 		{
 			/* a literal scratch area per warp bounds the grid */
@@ -1555,39 +1480,8 @@ aocs_decode_impl(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes, int32_t
 		}
 		else
 		{
-			const char *mode = getenv("CBGPU_INFLATE");	/* "lanes" / "warp": force one of the two kernels */
-
-			if (mode ? strcmp(mode, "lanes") == 0 : ncompressed >= 2048)
-			{
-				/* enough blocks to give every lane its own stream */
-				int		   *zlist = (int *) malloc(sizeof(int) * (size_t) ncompressed);
-				int			nz = 0;
-				int			grid = (int) ((ncompressed + 31) / 32);
-
-				if (!zlist)
-				{
-					free(dir);
-					return CBGPU_ERR_NOMEM;
-				}
-				for (int64_t i = 0; i < ndir; i++)
-					if (dir[i].clen)
-						zlist[nz++] = (int) i;
-				if (grid > ctx->sm_count * 3)
-					grid = ctx->sm_count * 3;
-				CB_CUDA(ctx, cudaMallocAsync(&d_zlist, sizeof(int) * (size_t) nz, ctx->stream));
-				CB_CUDA(ctx, cudaMemcpyAsync(d_zlist, zlist, sizeof(int) * (size_t) nz, cudaMemcpyHostToDevice, ctx->stream));
-				CB_CUDA(ctx, cudaFuncSetAttribute(k_aocs_inflate_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, INFL_LANES_SMEM));
-				k_aocs_inflate_lanes<<<grid, 32, INFL_LANES_SMEM, ctx->stream>>>(d_raw, d_dir, d_zlist, nz, ctx->d_status, d_flag, d_flag + 1);
-				CB_LAUNCHED(ctx, "k_aocs_inflate_lanes");
-				CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));	/* zlist is read by the copy */
-				CB_CUDA(ctx, cudaFreeAsync(d_zlist, ctx->stream));
-				free(zlist);
-			}
-			else
-			{
-				k_aocs_inflate<<<nblk, AOCS_WARPS * 32, 0, ctx->stream>>>(d_raw, d_dir, (int) ndir, ctx->d_status, d_flag);
-				CB_LAUNCHED(ctx, "k_aocs_inflate");
-			}
+			k_aocs_inflate<<<nblk, AOCS_WARPS * 32, 0, ctx->stream>>>(d_raw, d_dir, (int) ndir, ctx->d_status, d_flag);
+			CB_LAUNCHED(ctx, "k_aocs_inflate");
 		}
 		if (dmode != 1 && !anynull && !rel->nulls[col])
 		{

@@ -9,13 +9,13 @@
  * RFC 1951: stored / fixed / dynamic Huffman blocks, LZ77 window of 32 KiB), and the parity tests inflate streams
  * produced by the system zlib the reference would link.
  *
- * The decoder is __host__ __device__ so it can be tested on the host (tests/test_inflate_host.py compiles this header
- * with g++).  Two ways to drive it (aocs.cu picks by the number of compressed blocks in the file):
- *   infl_run()   one thread decodes a whole stream, writing output as it goes: 32 streams per warp, the tables of
- *                lane l interleaved in shared memory (element i of a table at [i * 32 + l]: template parameter S)
- *   infl_step()  one thread decodes block headers / Huffman symbols into a queue of up to INFL_QN literal /
- *                (length, distance) entries, which a whole warp then applies: one stream per warp, for files with
- *                too few blocks to give every lane its own
+ * Split in two so the serial part can be tested on the host (tests/test_inflate_host.py compiles this header with g++):
+ *   infl_step()  one thread: decode block headers / Huffman symbols into a queue of up to INFL_QN
+ *                literal / (length, distance) entries                                  [__host__ __device__]
+ *   the caller   applies the queue to the output: serially on the host, a whole warp on the device (aocs.cu)
+ * (A one-stream-per-thread driver with per-lane tables interleaved in shared memory was measured and dropped: 3 warps
+ * per SM could not hide the decoder's latencies, 8-30 GB/s against 22-44 GB/s for one stream per warp,
+ * profiles/r01f_aocs_decode_inflate_lanes_experiment.txt.  The table stride S of the templates below is what is left.)
  */
 #ifndef CB_INFLATE_CUH
 #define CB_INFLATE_CUH
@@ -60,11 +60,6 @@ struct InflView
 	int			lbits, dbits;	/* first-level lookup bits                                               */
 };
 
-/* per-lane tables of the one-stream-per-thread mode: 9-bit / 7-bit lookups */
-#define INFL_T_LBITS 9
-#define INFL_T_DBITS 7
-#define INFL_T_ENTRIES ((1 << INFL_T_LBITS) + (1 << INFL_T_DBITS) + 16 + 16 + 288 + 32)	/* uint16_t per lane */
-
 INFL_HD InflView<1>
 infl_view(InflTables &T)
 {
@@ -79,30 +74,6 @@ infl_view(InflTables &T)
 	V.lens = T.lens;
 	V.lbits = INFL_FAST_L;
 	V.dbits = INFL_FAST_D;
-	return V;
-}
-
-/* lane's view of an interleaved area of INFL_T_ENTRIES * 32 uint16_t; lens = 320 bytes of the thread's own */
-INFL_HD InflView<32>
-infl_view_lane(uint16_t *area, int lane, uint8_t *lens)
-{
-	InflView<32> V;
-	uint16_t   *p = area + lane;
-
-	V.lfast = p;
-	p += (1 << INFL_T_LBITS) * 32;
-	V.dfast = p;
-	p += (1 << INFL_T_DBITS) * 32;
-	V.lcount = p;
-	p += 16 * 32;
-	V.dcount = p;
-	p += 16 * 32;
-	V.lsym = p;
-	p += 288 * 32;
-	V.dsym = p;
-	V.lens = lens;
-	V.lbits = INFL_T_LBITS;
-	V.dbits = INFL_T_DBITS;
 	return V;
 }
 
@@ -486,75 +457,6 @@ infl_step(InflState &s, const InflView<S> &T, uint32_t *q, int *n)
 		}
 		if (infl_consumed(s) > s.inlen)
 			return INFL_ERROR;
-	}
-}
-
-/*
- * A whole stream by one thread, output written as it is decoded.  true = the final block ended cleanly (the caller
- * still checks the produced length and the Adler-32 trailer at infl_consumed()).
- */
-template <int S>
-INFL_HD bool
-infl_run(InflState &s, const InflView<S> &T, uint8_t *out, uint32_t cap, uint32_t *produced)
-{
-	uint32_t	pos = 0;
-
-	*produced = 0;
-	for (;;)
-	{
-		if (s.phase == 2)
-		{
-			*produced = pos;
-			return true;
-		}
-		if (s.phase == 0)
-		{
-			const int	rc = infl_block_header<S>(s, T);
-
-			if (rc == INFL_ERROR)
-				return false;
-			if (rc == INFL_STORED)
-			{
-				if (s.stored_len > cap - pos)
-					return false;
-				for (uint32_t i = 0; i < s.stored_len; i++)
-					out[pos + i] = s.in[s.stored_src + i];
-				pos += s.stored_len;
-				continue;
-			}
-		}
-		for (;;)
-		{
-			int			sy;
-
-			infl_refill(s);
-			sy = infl_sym<S>(s, T.lfast, T.lbits, T.lcount, T.lsym);
-			if (sy < 0)
-				return false;
-			if (sy < 256)
-			{
-				if (pos >= cap)
-					return false;
-				out[pos++] = (uint8_t) sy;
-			}
-			else if (sy == 256)
-			{
-				s.phase = s.final ? 2 : 0;
-				break;
-			}
-			else
-			{
-				uint32_t	len,
-							dist;
-
-				if (!infl_lendist<S>(s, T, sy, &len, &dist) || dist > pos || len > cap - pos)
-					return false;
-				for (uint32_t i = 0; i < len; i++, pos++)
-					out[pos] = out[pos - dist];
-			}
-		}
-		if (infl_consumed(s) > s.inlen)
-			return false;
 	}
 }
 

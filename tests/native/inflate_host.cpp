@@ -97,34 +97,6 @@ infl_host_zlib_warp(const uint8_t *z, uint32_t zl, uint8_t *out, uint32_t cap, u
 	return pos;
 }
 
-/* the one-stream-per-thread mode of k_aocs_inflate_lanes: infl_run over the interleaved table layout, as lane `lane` */
-extern "C" long long
-infl_host_zlib_lane(const uint8_t *z, uint32_t zl, uint8_t *out, uint32_t cap, uint32_t *adler_stored, int lane)
-{
-	static thread_local uint16_t area[INFL_T_ENTRIES * 32];
-	uint8_t		lens[320];
-	InflState	s;
-	uint32_t	pos = 0;
-
-	if (!infl_zlib_header_ok(z, zl))
-		return -1;
-	for (int i = 0; i < INFL_T_ENTRIES * 32; i++)
-		if (i % 32 != lane)
-			area[i] = 0xA5A5;		/* the other lanes' entries must survive */
-	infl_init(s, z, zl, 2);
-	if (!infl_run<32>(s, infl_view_lane(area, lane, lens), out, cap, &pos))
-		return -2;
-	for (int i = 0; i < INFL_T_ENTRIES * 32; i++)
-		if (i % 32 != lane && area[i] != 0xA5A5)
-			return -9;
-	const uint32_t c = infl_consumed(s);
-
-	if (c + 4 > zl)
-		return -6;
-	*adler_stored = ((uint32_t) z[c] << 24) | ((uint32_t) z[c + 1] << 16) | ((uint32_t) z[c + 2] << 8) | z[c + 3];
-	return pos;
-}
-
 extern "C" long long
 infl_host_zlib(const uint8_t *z, uint32_t zl, uint8_t *out, uint32_t cap, uint32_t *adler_stored)
 {

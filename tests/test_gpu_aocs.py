@@ -114,66 +114,6 @@ def test_device_inflates_bulk_compressed_columns(ctx, case):
     rel.free()
 
 
-@pytest.fixture
-def lanes_mode():
-    """force the one-stream-per-thread inflate kernel (otherwise chosen from 2048 compressed blocks up)"""
-    import os
-    os.environ["CBGPU_INFLATE"] = "lanes"
-    yield
-    del os.environ["CBGPU_INFLATE"]
-
-
-@pytest.mark.parametrize("case", ZCASES, ids=[c[0] for c in ZCASES])
-def test_inflate_one_stream_per_thread(ctx, case, lanes_mode):
-    name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel = case
-    ctype, attlen, varkind, align = DECODE[typname]
-    rel = capi.DeviceRelation(ctx, len(values), [ctype], dscales=[dscale])
-    ctx.trace_begin()
-    n = rel.load_aocs_column(0, raw, checksum, attlen, varkind, align, compresstype=1)
-    launched = [k for k, _ in ctx.trace_end()]
-    assert n == len(values)
-    assert ("k_aocs_inflate_lanes" in launched) == ("stored" not in name) and "k_aocs_inflate" not in launched
-    got, gotnull = rel.read_column(0)
-    assert np.array_equal(gotnull.astype(np.uint8), nulls)
-    keep = nulls == 0
-    if typname == "float8":
-        assert np.array_equal(got[keep].view(np.int64), values[keep].view(np.int64))
-    else:
-        assert np.array_equal(got[keep].astype(np.int64), values[keep])
-    if not checksum and "stored" not in name:
-        # no CRC in front: the inflater itself has to notice damage (bad code, distance, length, Adler-32)
-        rng = np.random.default_rng(5)
-        caught = 0
-        for pos in rng.integers(8 + 16 + 2, len(raw) - 8, 10):
-            bad = bytearray(raw)
-            bad[int(pos)] ^= 1 << int(rng.integers(0, 8))
-            try:
-                rel.load_aocs_column(0, bytes(bad), checksum, attlen, varkind, align, compresstype=1)
-            except capi.CbgpuError as e:
-                assert e.code in (-6, -2, -3)
-                caught += 1
-        assert caught >= 7
-        assert rel.load_aocs_column(0, raw, checksum, attlen, varkind, align, compresstype=1) == len(values)
-    rel.free()
-
-
-def test_inflate_many_blocks_picks_the_thread_kernel(ctx):
-    """a file with thousands of compressed blocks: the per-thread kernel on its own, partial last warp, work counter"""
-    case = {c[0]: c for c in ZCASES}["zlib6_float8_nulls_8k_nocrc"]
-    name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls, zlevel = case
-    k = 2048 // nblocks + 3
-    rel = capi.DeviceRelation(ctx, len(values) * k, [P.FLOAT8])
-    ctx.trace_begin()
-    assert rel.load_aocs_column(0, raw * k, checksum, 8, 0, 8, compresstype=1) == len(values) * k
-    launched = [n for n, _ in ctx.trace_end()]
-    assert "k_aocs_inflate_lanes" in launched and "k_aocs_inflate" not in launched
-    got, gotnull = rel.read_column(0)
-    assert np.array_equal(gotnull.astype(np.uint8), np.tile(nulls, k))
-    keep = np.tile(nulls, k) == 0
-    assert np.array_equal(got[keep].view(np.int64), np.tile(values, k)[keep].view(np.int64))
-    rel.free()
-
-
 @pytest.mark.parametrize("name", ["zlib5_numeric_price", "zlib6_float8_nulls_8k_nocrc", "zlib6_int8_bigblocks", "rle2_numeric_long_run",
                                   "rle4_float8_runs_8k_nocrc", "zstd3_numeric_price", "zstd3_int8_bigblocks"])
 def test_damaged_compressed_blocks_are_reported(ctx, name):

@@ -25,18 +25,13 @@ def lib(tmp_path_factory):
     L.infl_host_zlib.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.infl_host_zlib_warp.restype = C.c_longlong
     L.infl_host_zlib_warp.argtypes = L.infl_host_zlib.argtypes
-    L.infl_host_zlib_lane.restype = C.c_longlong
-    L.infl_host_zlib_lane.argtypes = L.infl_host_zlib.argtypes + [C.c_int]
     return L
 
 
-def inflate(L, z, cap, warp=False, lane=None):
+def inflate(L, z, cap, warp=False):
     out = (C.c_ubyte * max(cap, 1))()
     ad = C.c_uint32()
-    if lane is not None:
-        r = L.infl_host_zlib_lane(z, len(z), out, cap, C.byref(ad), lane)
-    else:
-        r = (L.infl_host_zlib_warp if warp else L.infl_host_zlib)(z, len(z), out, cap, C.byref(ad))
+    r = (L.infl_host_zlib_warp if warp else L.infl_host_zlib)(z, len(z), out, cap, C.byref(ad))
     return r, bytes(out[:max(r, 0)]), ad.value
 
 
@@ -69,24 +64,6 @@ def test_against_system_zlib(lib):
         r, out, ad = inflate(lib, z, len(src))
         assert r == len(src) and out == src
         assert ad == zlib.adler32(src)
-
-
-def test_one_stream_per_thread_mode(lib):
-    """infl_run with the interleaved per-lane table layout (9-bit / 7-bit lookups): same output, and no lane's tables
-    touch another lane's entries"""
-    for i, (src, z) in enumerate(streams()):
-        r, out, ad = inflate(lib, z, len(src), lane=(0, 7, 31, 16)[i % 4])
-        assert r == len(src) and out == src and ad == zlib.adler32(src)
-    src = bytes(range(256)) * 40
-    z = zlib.compress(src, 6)
-    assert inflate(lib, z, len(src) - 1, lane=3)[0] < 0
-    assert inflate(lib, z[:len(z) // 2], len(src), lane=3)[0] < 0
-    rng = np.random.default_rng(13)
-    for t in range(200):
-        zb = bytearray(z)
-        zb[int(rng.integers(2, len(z) - 4))] ^= 1 << int(rng.integers(0, 8))
-        r, out, ad = inflate(lib, bytes(zb), len(src), lane=5)
-        assert r < 0 or r != len(src) or ad != zlib.adler32(out) or out == src
 
 
 def test_batch_schedule_of_the_warp_kernel(lib):

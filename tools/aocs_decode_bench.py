@@ -41,7 +41,7 @@ def main():
         tr = ctx.trace_end()
         ms = sum(m for nme, m in tr if nme == "k_aocs_decode")
         vms = sum(m for nme, m in tr if nme == "k_aocs_verify")
-        ims = sum(m for nme, m in tr if nme in ("k_aocs_inflate", "k_aocs_inflate_lanes", "k_aocs_unzstd"))
+        ims = sum(m for nme, m in tr if nme in ("k_aocs_inflate", "k_aocs_unzstd"))
         assert got == n
         content = sum(b["dlen"] for b in A.walk_blocks_ex(raw, checksum) if b["clen"]) * k
         print("%-30s %8.1f MB file  %10d rows  kernel %7.3f ms  %7.1f GB/s of file  %7.2f G rows/s  (%d blocks)  crc32c %s  inflate %s" %
