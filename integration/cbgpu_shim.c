@@ -20,10 +20,15 @@
  *                                  library errors become ereport(ERROR) only after the device state is released
  *   memory context reset callback  frees device state when the query context goes away on an error path
  *
- * Loading the range table (cbgpu_aocs_decode_column per projected column file) and shipping the NCCL
- * rendezvous token with the dispatched plan are sketched in INTEGRATION.md and left as calls to two
- * extern hooks here (cbgpu_shim_load_relation, cbgpu_shim_interconnect), so this file stays about the
- * operator boundary.
+ * Loading the range table is integration/cbgpu_shim_storage.c (cbgpu_shim_load_relation: only the columns a scan's
+ * target list and quals mention are read, so Var.varattno is remapped to the position among them); shipping the NCCL
+ * rendezvous token with the dispatched plan is sketched in INTEGRATION.md and left as an extern hook
+ * (cbgpu_shim_interconnect), so this file stays about the operator boundary.
+ *
+ * character(n > 1) / varchar / text columns live on the device as codes of a per-segment dictionary the loader builds
+ * (cbgpu_shim_dict).  Codes mean nothing outside the segment that made them, so such a column is accepted only where
+ * it never leaves its scan: in a SeqScan qual of the form column = 'literal' / column <> 'literal', the literal being
+ * translated to the segment's code once the relation is loaded.  Anything else on such a column declines the sub-tree.
  */
 #include "postgres.h"
 
@@ -39,6 +44,8 @@
 #include "nodes/nodeFuncs.h"
 #include "nodes/plannodes.h"
 #include "nodes/primnodes.h"
+#include "optimizer/optimizer.h"
+#include "access/sysattr.h"
 #include "utils/builtins.h"
 #include "utils/lsyscache.h"
 #include "utils/memutils.h"
@@ -52,6 +59,28 @@ void		_PG_init(void);
 
 /* provided by the loader / dispatcher glue */
 extern cbgpu_rel *cbgpu_shim_load_relation(cbgpu_ctx *ctx, Relation rel, List *projected_attnos);
+extern cbgpu_dict *cbgpu_shim_dict(Oid relid, AttrNumber attno);
+
+/* one SeqScan of the sub-tree: its range-table index and the columns it needs, ascending (= device column order) */
+typedef struct ShimScan
+{
+	Index		scanrelid;
+	List	   *attnos;
+} ShimScan;
+
+/* a string literal compared with a dictionary column in a scan qual: becomes a code after the relation is loaded */
+typedef struct ShimPendingConst
+{
+	CbExpr	   *x;
+	Index		scanrelid;
+	AttrNumber	attno;
+	Const	   *c;
+} ShimPendingConst;
+
+/* translation context (one sub-tree at a time, backend-local) */
+static ShimScan *cur_scan = NULL;		/* the SeqScan whose expressions are being translated, else NULL   */
+static bool cur_in_qual = false;
+static List *pending_consts = NIL;
 extern CbInterconnect *cbgpu_shim_interconnect(cbgpu_ctx *ctx, EState *estate);
 
 static ExecutorStart_hook_type prev_ExecutorStart = NULL;
@@ -137,6 +166,36 @@ translate_args(CbExpr *x, List *args)
 	return true;
 }
 
+static bool
+is_string_type(Oid typid, int32 typmod)
+{
+	return typid == VARCHAROID || typid == TEXTOID || (typid == BPCHAROID && typmod != (int32) VARHDRSZ + 1);
+}
+
+static Node *
+strip_relabel(Node *n)
+{
+	while (n && IsA(n, RelabelType))
+		n = (Node *) ((RelabelType *) n)->arg;
+	return n;
+}
+
+/* 1-based position of v in an integer list, 0 when absent */
+static int
+list_position_int(List *l, int v)
+{
+	ListCell   *lc;
+	int			pos = 0;
+
+	foreach(lc, l)
+	{
+		pos++;
+		if (lfirst_int(lc) == v)
+			return pos;
+	}
+	return 0;
+}
+
 static CbExpr *
 translate_expr(Expr *e)
 {
@@ -157,6 +216,22 @@ translate_expr(Expr *e)
 				x = new_expr(T_CbVar, t, ds);
 				x->varno = v->varno;	/* INNER_VAR / OUTER_VAR keep their values (65000 / 65001) */
 				x->varattno = v->varattno;
+				if (cur_scan && v->varno == cur_scan->scanrelid)
+				{
+					/* the device relation holds only the projected columns, in attribute order */
+					ListCell   *lc;
+					int			pos = 0;
+
+					x->varattno = 0;
+					foreach(lc, cur_scan->attnos)
+					{
+						pos++;
+						if (lfirst_int(lc) == v->varattno)
+							x->varattno = pos;
+					}
+					if (x->varattno == 0)
+						return NULL;
+				}
 				return x;
 			}
 		case T_Const:
@@ -224,6 +299,48 @@ translate_expr(Expr *e)
 
 				if (name == NULL || list_length(o->args) != 2)
 					return NULL;
+				{
+					/* dictionary column = / <> string literal, in the qual of the scan that owns the column */
+					Node	   *l = strip_relabel((Node *) linitial(o->args));
+					Node	   *r = strip_relabel((Node *) lsecond(o->args));
+
+					if (IsA(l, Const) && IsA(r, Var))
+					{
+						Node	   *tmp = l;
+
+						l = r;
+						r = tmp;
+					}
+					if (IsA(l, Var) && is_string_type(((Var *) l)->vartype, ((Var *) l)->vartypmod))
+					{
+						Var		   *v = (Var *) l;
+						ShimPendingConst *pc;
+						CbExpr	   *cx;
+
+						if (!cur_scan || !cur_in_qual || v->varno != cur_scan->scanrelid || !IsA(r, Const) || ((Const *) r)->constisnull ||
+							!is_string_type(((Const *) r)->consttype, -1) || (strcmp(name, "=") != 0 && strcmp(name, "<>") != 0))
+							return NULL;
+						x = new_expr(T_CbOpExpr, CB_BOOL, 0);
+						x->op = strcmp(name, "=") == 0 ? CB_OP_EQ : CB_OP_NE;
+						x->nargs = 2;
+						x->args = (CbExpr **) palloc0(sizeof(CbExpr *) * 2);
+						x->args[0] = new_expr(T_CbVar, CB_DICT32, 0);
+						x->args[0]->varno = v->varno;
+						x->args[0]->varattno = list_position_int(cur_scan->attnos, v->varattno);
+						cx = new_expr(T_CbConst, CB_DICT32, 0);
+						cx->constval = -1;		/* no row has this code: "the column never holds the value" */
+						x->args[1] = cx;
+						if (x->args[0]->varattno == 0)
+							return NULL;
+						pc = (ShimPendingConst *) palloc(sizeof(ShimPendingConst));
+						pc->x = cx;
+						pc->scanrelid = cur_scan->scanrelid;
+						pc->attno = v->varattno;
+						pc->c = (Const *) r;
+						pending_consts = lappend(pending_consts, pc);
+						return x;
+					}
+				}
 				if (strcmp(name, "+") == 0) op = CB_OP_ADD;
 				else if (strcmp(name, "-") == 0) op = CB_OP_SUB;
 				else if (strcmp(name, "*") == 0) op = CB_OP_MUL;
@@ -337,7 +454,14 @@ fill_plan(CbPlan *c, CbNodeTag tag, Plan *p)
 		c->targetlist[i].resname = te->resname;
 		i++;
 	}
-	return translate_exprs(p->qual, &c->nquals, &c->qual);
+	{
+		bool		ok;
+
+		cur_in_qual = true;
+		ok = translate_exprs(p->qual, &c->nquals, &c->qual);
+		cur_in_qual = false;
+		return ok;
+	}
 }
 
 static CbPlan *
@@ -350,11 +474,33 @@ translate_plan(Plan *p, EState *estate, List **rels)
 		case T_SeqScan:
 			{
 				CbSeqScan  *c = (CbSeqScan *) palloc0(sizeof(CbSeqScan));
+				ShimScan   *sc = (ShimScan *) palloc0(sizeof(ShimScan));
+				Bitmapset  *used = NULL;
+				int			k = -1;
+				bool		ok;
 
-				if (!fill_plan(&c->plan, T_CbSeqScan, p))
+				/* the columns this scan reads: what its target list and quals mention (as aoco_beginscan_extractcolumns
+				 * projects, access/aocs/aocsam_handler.c:612) */
+				sc->scanrelid = ((Scan *) p)->scanrelid;
+				pull_varattnos((Node *) p->targetlist, sc->scanrelid, &used);
+				pull_varattnos((Node *) p->qual, sc->scanrelid, &used);
+				while ((k = bms_next_member(used, k)) >= 0)
+				{
+					const int	attno = k + FirstLowInvalidHeapAttributeNumber;
+
+					if (attno <= 0)
+						return NULL;	/* system columns, whole-row references */
+					sc->attnos = lappend_int(sc->attnos, attno);
+				}
+				if (sc->attnos == NIL)
+					return NULL;
+				cur_scan = sc;
+				ok = fill_plan(&c->plan, T_CbSeqScan, p);
+				cur_scan = NULL;
+				if (!ok)
 					return NULL;
 				/* the range-table index of this scan in the GPU executor = its position in `rels` */
-				*rels = lappend_int(*rels, ((Scan *) p)->scanrelid);
+				*rels = lappend(*rels, sc);
 				c->scanrelid = list_length(*rels);
 				return &c->plan;
 			}
@@ -539,7 +685,7 @@ static bool
 shim_take_over(PlanState *ps, EState *estate)
 {
 	List	   *rels = NIL;
-	CbPlan	   *cplan = translate_plan(ps->plan, estate, &rels);
+	CbPlan	   *cplan = (pending_consts = NIL, translate_plan(ps->plan, estate, &rels));
 	cbgpu_rel **rt;
 	CbgpuShim  *shim;
 	ListCell   *lc;
@@ -553,13 +699,27 @@ shim_take_over(PlanState *ps, EState *estate)
 	rt = (cbgpu_rel **) palloc0(sizeof(cbgpu_rel *) * Max(list_length(rels), 1));
 	foreach(lc, rels)
 	{
-		Relation	r = ExecGetRangeTableRelation(estate, (Index) lfirst_int(lc));
+		ShimScan   *sc = (ShimScan *) lfirst(lc);
+		Relation	r = ExecGetRangeTableRelation(estate, sc->scanrelid);
 
-		rt[i] = cbgpu_shim_load_relation(shim_ctx, r, NIL);
+		rt[i] = cbgpu_shim_load_relation(shim_ctx, r, sc->attnos);
 		if (rt[i] == NULL)
 			return false;
 		i++;
 	}
+	/* string literals -> this segment's dictionary codes, now that the dictionaries exist */
+	foreach(lc, pending_consts)
+	{
+		ShimPendingConst *pc = (ShimPendingConst *) lfirst(lc);
+		cbgpu_dict *dict = cbgpu_shim_dict(exec_rt_fetch(pc->scanrelid, estate)->relid, pc->attno);
+		struct varlena *v = (struct varlena *) DatumGetPointer(pc->c->constvalue);
+
+		if (dict == NULL)
+			return false;
+		/* -1 (the value occurs nowhere in this segment's files) stays -1: = is false, <> true for every non-NULL row */
+		pc->x->constval = cbgpu_dict_lookup(dict, VARDATA_ANY(v), (int32) VARSIZE_ANY_EXHDR(v));
+	}
+	pending_consts = NIL;
 	shim = (CbgpuShim *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(CbgpuShim));
 	shim->cbestate = cb_CreateExecutorState(shim_ctx, rt, list_length(rels));
 	shim->cbestate->es_interconnect = cbgpu_shim_interconnect(shim_ctx, estate);

@@ -227,7 +227,7 @@ cbgpu_shim_load_relation(cbgpu_ctx *ctx, Relation rel, List *projected_attnos)
 		sd->relid = RelationGetRelid(rel);
 		sd->attno = attno[c];
 		sd->dict = spec[c].dict;
-		shim_dicts = lappend(shim_dicts, sd);
+		shim_dicts = lcons(sd, shim_dicts);	/* newest first: a reload of the relation supersedes the older dictionary */
 		MemoryContextSwitchTo(old);
 	}
 
