@@ -29,6 +29,76 @@ class CbgpuVisimapEntry(C.Structure):
     _fields_ = [("first_row_num", C.c_int64), ("data", C.c_void_p), ("len", C.c_int32)]
 
 
+class CbTupAttr(C.Structure):
+    _fields_ = [("type", C.c_int32), ("dscale", C.c_int32), ("bpchar_len", C.c_int32), ("ntexts", C.c_int32),
+                ("texts", C.POINTER(C.c_char_p)), ("text_lens", C.POINTER(C.c_int32))]
+
+
+def _tup_attrs(attrs):
+    """[(CbTypeId, dscale, bpchar_len[, texts])] -> (CbTupAttr array, keep-alive list); texts: the column's dictionary in
+    byte order (DeviceDict.entries())"""
+    arr = (CbTupAttr * max(len(attrs), 1))()
+    keep = []
+    for i, a in enumerate(attrs):
+        arr[i].type, arr[i].dscale, arr[i].bpchar_len = a[0], a[1], a[2]
+        texts = a[3] if len(a) > 3 and a[3] is not None else []
+        if texts:
+            bufs = [C.create_string_buffer(bytes(t), len(t)) for t in texts]
+            ptrs = (C.c_char_p * len(texts))(*[C.cast(b, C.c_char_p) for b in bufs])
+            lens = (C.c_int32 * len(texts))(*[len(t) for t in texts])
+            keep += [bufs, ptrs, lens]
+            arr[i].ntexts = len(texts)
+            arr[i].texts = ptrs
+            arr[i].text_lens = lens
+    return arr, keep
+
+
+def tupser_rows(attrs, rows, nulls=None, max_chunk=8160, end=True):
+    """rows (lists of ints as the executor holds them) -> the reference's tuple chunk stream (cb_tupser_row);
+    attrs: [(CbTypeId, dscale, bpchar_len, DeviceDict or None)]"""
+    L = ex()
+    n = len(attrs)
+    arr, keep = _tup_attrs(attrs)
+    out = bytearray()
+    buf = C.create_string_buffer(1 << 20)
+    for r, row in enumerate(rows):
+        vals = (C.c_int64 * max(n, 1))(*[int(v) for v in row])
+        isn = (C.c_uint8 * max(n, 1))(*([int(x) for x in nulls[r]] if nulls is not None else [0] * n))
+        k = L.cb_tupser_row(arr, n, vals, isn, max_chunk, buf, len(buf))
+        if k < 0:
+            raise CbgpuError(int(k), "cb_tupser_row failed")
+        out += buf.raw[:k]
+    if end:
+        k = L.cb_tupser_end_of_stream(buf, len(buf))
+        out += buf.raw[:k]
+    return bytes(out)
+
+
+def tupser_parse(attrs, data):
+    """a tuple chunk stream -> (rows, nulls, bytes consumed, ended) through cb_tupser_next"""
+    L = ex()
+    n = len(attrs)
+    arr, keep = _tup_attrs(attrs)
+    buf = C.create_string_buffer(bytes(data), len(data))
+    pos = 0
+    rows, nulls = [], []
+    vals = (C.c_int64 * max(n, 1))()
+    isn = (C.c_uint8 * max(n, 1))()
+    used = C.c_int64()
+    while True:
+        rc = L.cb_tupser_next(arr, n, C.byref(buf, pos), len(data) - pos, C.byref(used), vals, isn)
+        if rc == 1:
+            rows.append([int(vals[i]) for i in range(n)])
+            nulls.append([int(isn[i]) for i in range(n)])
+            pos += used.value
+            continue
+        if rc == 0:
+            return rows, nulls, pos + used.value, True
+        if rc == -1:
+            return rows, nulls, pos, False
+        raise CbgpuError(int(rc), "cb_tupser_next: malformed chunk stream at byte %d" % pos)
+
+
 class CbAocsColumnSpec(C.Structure):
     _fields_ = [("relcol", C.c_int32), ("filenum", C.c_int32), ("attlen", C.c_int32), ("varkind", C.c_int32), ("typalign", C.c_int32),
                 ("compresstype", C.c_int32), ("eof", C.c_int64), ("dict", C.c_void_p)]
@@ -290,6 +360,13 @@ def ex():
         L.cb_aocs_load_segfile.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(CbAocsColumnSpec), vp, C.c_int64,
                                            C.POINTER(CbgpuVisimapEntry), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                            C.c_char_p, C.c_size_t]
+        L.cb_tupser_row.restype = C.c_int64
+        L.cb_tupser_row.argtypes = [C.POINTER(CbTupAttr), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.c_int, vp, C.c_int64]
+        L.cb_tupser_end_of_stream.restype = C.c_int
+        L.cb_tupser_end_of_stream.argtypes = [vp, C.c_int64]
+        L.cb_tupser_next.restype = C.c_int64
+        L.cb_tupser_next.argtypes = [C.POINTER(CbTupAttr), C.c_int, vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_uint8)]
         L.cb_cluster_create.restype = vp
         L.cb_cluster_create.argtypes = [vp, C.c_int32]
         L.cb_cluster_set_range_table.restype = C.c_int

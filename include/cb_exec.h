@@ -225,6 +225,36 @@ int			cb_aocs_load_segfile(cbgpu_ctx *ctx, const char *basepath, int segno, int 
 								 const cbgpu_visimap_entry *entries, int nentries, int64_t *nrows, int64_t *nhidden,
 								 char *err, size_t errsz);
 
+/* ------------------------------------------------------------------------------------------
+ * Rows in the reference's Motion wire format (cdb/motion/tupser.c: SerializeTuple :349, CvtChunksToTup :515;
+ * include/cdb/tupchunk.h), for interconnect traffic between GPU segments and un-replaced CPU operators
+ * ------------------------------------------------------------------------------------------ */
+#define CB_TUPSER_MAX_ATTS 1600	/* MaxTupleAttributeNumber */
+#define CB_TUPSER_MAX_TEXT 8192	/* longest character(n) padding done here                              */
+typedef struct CbTupAttr
+{
+	int32_t		type;			/* CbTypeId of the column                                              */
+	int32_t		dscale;			/* CB_NUMERIC: scale of the int64 values                               */
+	int32_t		bpchar_len;		/* dictionary column declared character(n): n, else 0 (varchar / text) */
+	int32_t		ntexts;			/* dictionary columns: the texts of codes 0 .. ntexts-1, in byte order  */
+	const char *const *texts;	/* (what cbgpu_dict_entry returns for each code; character(n) texts     */
+	const int32_t *text_lens;	/* without their trailing blanks)                                      */
+} CbTupAttr;
+/* One row (values as the executor holds them: by-value datums, scaled numerics, dictionary codes) -> its tuple chunks:
+ * TC_WHOLE, or TC_PARTIAL_START / _MID / _END when [int32 length][MinimalTuple body] exceeds max_chunk
+ * (Gp_max_tuple_chunk_size) minus the 4-byte chunk header.  Returns the bytes written, < 0 on error (-2: out too small). */
+int64_t		cb_tupser_row(const CbTupAttr *attrs, int natts, const int64_t *values, const uint8_t *isnull, int max_chunk,
+						  unsigned char *out, int64_t outcap);
+/* the TC_END_OF_STREAM chunk a sender finishes with */
+int			cb_tupser_end_of_stream(unsigned char *out, int64_t outcap);
+#define CB_TUPSER_END 0			/* TC_END_OF_STREAM                                                    */
+#define CB_TUPSER_NEED_MORE (-1)	/* the buffer ends inside a tuple: call again with more bytes          */
+#define CB_TUPSER_BAD (-2)		/* chunk sequence or tuple layout the reference would reject           */
+/* The next row of a chunk stream: 1 and *consumed bytes used, or one of the codes above.  Strings are mapped to the
+ * attribute's dictionary codes (a string it does not hold: CB_TUPSER_BAD). */
+int64_t		cb_tupser_next(const CbTupAttr *attrs, int natts, const unsigned char *in, int64_t inlen, int64_t *consumed,
+						   int64_t *values, uint8_t *isnull);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,9 +55,17 @@ bool		Debug_datumstream_read_check_large_varlena_integrity = false;
 bool		Debug_datumstream_read_print_varlena_info = false;
 bool		FileEncryptionEnabled = false;
 
-static jmp_buf ref_jmp;
+jmp_buf		ref_jmp;			/* shared with ref_tupser.c */
 static char ref_errbuf[512];
 static int	ref_elevel;
+
+/* a backend function the compiled reference files link against but these drivers never reach */
+void
+ref_abort(const char *what)
+{
+	snprintf(ref_errbuf, sizeof(ref_errbuf), "oracle/_ref: %s is a stub", what);
+	longjmp(ref_jmp, 1);
+}
 
 void	   *palloc(Size size) { return malloc(size ? size : 1); }
 void	   *palloc0(Size size) { return calloc(1, size ? size : 1); }

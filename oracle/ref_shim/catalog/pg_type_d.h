@@ -26,4 +26,11 @@
 #define TIMESTAMPOID 1114
 #define TIMESTAMPTZOID 1184
 #define NUMERICOID 1700
+/* the EXPOSE_TO_CLIENT_CODE part of catalog/pg_type.h:280-300 that genbki copies here */
+#define TYPTYPE_BASE 'b'
+#define TYPTYPE_COMPOSITE 'c'
+#define TYPTYPE_DOMAIN 'd'
+#define TYPTYPE_ENUM 'e'
+#define TYPTYPE_PSEUDO 'p'
+#define TYPTYPE_RANGE 'r'
 #endif
