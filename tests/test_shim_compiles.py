@@ -16,10 +16,11 @@ REF = "/root/reference/src/include"
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference headers only in the build container")
-@pytest.mark.parametrize("source", ["cbgpu_shim.c", "cbgpu_shim_storage.c"])
+@pytest.mark.parametrize("source", ["cbgpu_shim.c", "cbgpu_shim_storage.c", "cbgpu_shim_motion.c"])
 def test_shim_type_checks_against_reference_headers(source):
     """cbgpu_shim.c: the operator boundary; cbgpu_shim_storage.c: catalogs (pg_aocsseg, pg_attribute_encoding, pg_aovisimap,
-    relation options) -> cb_aocs_load_segfile"""
+    relation options) -> cb_aocs_load_segfile; cbgpu_shim_motion.c: executor rows <-> the configured MotionIPCLayer's
+    tuple chunks (SendTupleChunkToAMS / RecvTupleChunkFromAny) through cb_tupser_*"""
     p = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused-function",
                         "-I" + os.path.join(ROOT, "oracle", "ref_shim"), "-I" + REF, "-I" + os.path.join(ROOT, "include"),
                         os.path.join(ROOT, "integration", source)], capture_output=True, text=True)
