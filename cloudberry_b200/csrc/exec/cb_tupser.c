@@ -472,7 +472,8 @@ cb_tupser_next(const CbTupAttr *attrs, int natts, const unsigned char *in, int64
 			if (!buf)
 				return CB_TUPSER_BAD;
 		}
-		memcpy(buf + got, in + pos + TC_HDR, (size_t) size);
+		if (size)
+			memcpy(buf + got, in + pos + TC_HDR, (size_t) size);
 		got += size;
 		pos += TC_HDR + size;
 		if (type == TC_WHOLE || type == TC_PARTIAL_END)
