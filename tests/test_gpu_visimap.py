@@ -84,7 +84,7 @@ def test_query_sees_only_visible_rows(ctx, oracle):
 def test_segment_files_from_disk(ctx, oracle, tmp_path):
     """a two-column table's segment file 1 on disk under the reference's file names, bytes of an aborted append behind the
     recorded EOF, its pg_aovisimap rows: cb_aocs_load_segfile reads, decodes, hides; a query over it == the oracle"""
-    from test_aocs_format import CASES, ZSTDCASES
+    from test_aocs_format import CASES
     from cloudberry_b200.relation import HostRelation
     from cloudberry_b200.tpch import _child_var
     from gpu_util import canon

@@ -5,8 +5,6 @@ and rows/s per column kind.  Profiling aid; the H2D copy of the file (pageable h
 import os
 import sys
 
-import numpy as np
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
