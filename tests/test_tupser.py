@@ -79,10 +79,12 @@ def test_bytes_equal_the_reference_senders(case):
 @pytest.mark.skipif(A.ref_lib() is None, reason="reference library only where /root/reference exists")
 def test_reference_receiver_reads_our_chunks_and_random_rows_agree():
     rng = np.random.default_rng(5)
-    kinds = ["int4", "int8", "date", "float8", "bool", "numeric"]
-    for t in range(60):
+    kinds = ["int4", "int8", "date", "float8", "bool", "numeric", "text", "bpchar"]
+    pool = ["", " ", "x", "ab ", "MAIL", "REG AIR", "q" * 125, "r" * 126, "s" * 127, "t" * 128, "u" * 1000, "trailing   "]
+    for t in range(80):
         natts = int(rng.integers(1, 40))
-        cols = [(kinds[int(k)], int(rng.integers(0, 7)) if kinds[int(k)] == "numeric" else 0, 0) for k in rng.integers(0, 6, natts)]
+        cols = [(kinds[int(k)], int(rng.integers(0, 7)) if kinds[int(k)] == "numeric" else 0,
+                 int(rng.choice([1, 10, 25])) if kinds[int(k)] == "bpchar" else 0) for k in rng.integers(0, 8, natts)]
         nrows = int(rng.integers(1, 30))
         rows = []
         for _ in range(nrows):
@@ -96,6 +98,10 @@ def test_reference_receiver_reads_our_chunks_and_random_rows_agree():
                     row.append(int(rng.integers(-2**31, 2**31)))
                 elif kind == "numeric":
                     row.append(int(rng.choice([0, 1, -1, 10**ds, -10**(ds + 3), int(rng.integers(-2**62, 2**62)), int(rng.integers(-10**9, 10**9))])))
+                elif kind == "text":
+                    row.append(pool[int(rng.integers(0, len(pool)))])
+                elif kind == "bpchar":
+                    row.append(pool[int(rng.integers(0, 6))][:_n].rstrip(" ") if _n > 1 else chr(int(rng.integers(65, 91))))
                 else:
                     row.append(int(rng.integers(-2**63, 2**63 - 1)))
             rows.append(row)
@@ -114,8 +120,9 @@ def test_reference_receiver_reads_our_chunks_and_random_rows_agree():
                     assert A.numeric_from_bytes(ref_rows[r][a][1:] if ref_rows[r][a][0] & 1 else ref_rows[r][a][4:], ds) == rows[r][a]
                 elif kind == "float8":
                     assert ref_rows[r][a] == xrows[r][a]
-                elif kind == "bool":
-                    assert ref_rows[r][a] == rows[r][a]
+                elif kind in ("text", "bpchar"):
+                    body = ref_rows[r][a][1:] if ref_rows[r][a][0] & 1 else ref_rows[r][a][4:]
+                    assert body == (rows[r][a].ljust(_n) if kind == "bpchar" else rows[r][a]).encode()
                 else:
                     assert ref_rows[r][a] == rows[r][a]
 
