@@ -40,12 +40,31 @@ def main():
         ms = sum(m for nme, m in tr if nme == "k_aocs_decode")
         vms = sum(m for nme, m in tr if nme == "k_aocs_verify")
         ims = sum(m for nme, m in tr if nme in ("k_aocs_inflate", "k_aocs_unzstd"))
+        cpu = ""
+        if ctype_z:
+            # the library the reference calls, one host core, on this column's own compressed blocks (uncompress / ZSTD_decompress)
+            import time
+            import zlib
+            blocks = [(raw[b["off"]:b["off"] + b["clen"]], b["dlen"]) for b in A.walk_blocks_ex(raw, checksum) if b["clen"]]
+            if blocks:
+                if ctype_z == 2:
+                    import pyarrow as pa
+                    codec = pa.Codec("zstd")
+                    dec = lambda z, n: codec.decompress(z, decompressed_size=n, asbytes=True)      # noqa: E731
+                else:
+                    dec = lambda z, n: zlib.decompress(z)                                            # noqa: E731
+                t0, done = time.perf_counter(), 0
+                while time.perf_counter() - t0 < 0.2:
+                    for z, n_out in blocks:
+                        dec(z, n_out)
+                        done += n_out
+                cpu = "  cpu core %.2f GB/s out" % (done / (time.perf_counter() - t0) / 1e9)
         assert got == n
         content = sum(b["dlen"] for b in A.walk_blocks_ex(raw, checksum) if b["clen"]) * k
         print("%-30s %8.1f MB file  %10d rows  kernel %7.3f ms  %7.1f GB/s of file  %7.2f G rows/s  (%d blocks)  crc32c %s  inflate %s" %
               (name, len(big) / 1e6, n, ms, len(big) / ms / 1e6, n / ms / 1e6, nblocks * k,
                "%.3f ms %.1f GB/s" % (vms, len(big) / vms / 1e6) if vms else "off",
-               "%.3f ms %.1f GB/s out" % (ims, content / ims / 1e6) if ims else "-"))
+               ("%.3f ms %.1f GB/s out" % (ims, content / ims / 1e6) if ims else "-") + cpu))
         rel.free()
     ctx.close()
 
