@@ -468,9 +468,14 @@ cb_tupser_next(const CbTupAttr *attrs, int natts, const unsigned char *in, int64
 		if (got + size > cap)
 		{
 			cap = (got + size) * 2 + 64;
-			buf = realloc(buf, (size_t) cap);
-			if (!buf)
+			unsigned char *grown = realloc(buf, (size_t) cap);
+
+			if (!grown)
+			{
+				free(buf);
 				return CB_TUPSER_BAD;
+			}
+			buf = grown;
 		}
 		if (size)
 			memcpy(buf + got, in + pos + TC_HDR, (size_t) size);

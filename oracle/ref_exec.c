@@ -383,11 +383,12 @@ num_out(Datum d, char *out, int cap)
 	snprintf(out, (size_t) cap, "%s", s);
 }
 
-/* op 0 = numeric_add, 1 = numeric_sub, 2 = numeric_mul: what ExecInterpExpr calls for l_extendedprice * (1 - l_discount) */
+/* op 0 = numeric_add, 1 = numeric_sub, 2 = numeric_mul: what ExecInterpExpr calls for l_extendedprice * (1 - l_discount);
+ * 3 = numeric_div, which is all numeric_avg does with (sumX, N) (numeric.c:6056-6088) */
 int
 ref_numeric_binop(int op, const char *a, const char *b, char *out, int cap)
 {
-	PGFunction	f = op == 0 ? numeric_add : op == 1 ? numeric_sub : numeric_mul;
+	PGFunction	f = op == 0 ? numeric_add : op == 1 ? numeric_sub : op == 2 ? numeric_mul : numeric_div;
 
 	if (setjmp(ref_jmp))
 		return -1;
