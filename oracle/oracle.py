@@ -184,3 +184,67 @@ def execute(plan_node, segments, nthreads=1):
     if not h:
         raise RuntimeError("oracle: " + L.ora_last_error().decode())
     return Result(h)
+
+
+# ------------------------------------------------------------------------------------------------
+# Q1 through the reference's own per-row functions (oracle/ref_q1.c in oracle/_ref/libexec_ref.so)
+# ------------------------------------------------------------------------------------------------
+_REFEXEC = None
+
+
+def ref_exec_lib():
+    """oracle/_ref/libexec_ref.so (the reference's hashfunc.c / varchar.c / cdbhash.c / numeric.c / datumstreamblock.c compiled
+    where they lie + oracle/ref_exec.c, ref_q1.c); None when not built."""
+    global _REFEXEC
+    if _REFEXEC is None:
+        so = os.path.join(HERE, "_ref", "libexec_ref.so")
+        if not os.path.exists(so):
+            return None
+        R = C.CDLL(so)
+        R.ref_exec_last_error.restype = C.c_char_p
+        R.ref_q1_load.restype = C.c_void_p
+        R.ref_q1_load.argtypes = [C.c_int64] + [C.c_void_p] * 7 + [C.c_int, C.c_int]
+        R.ref_q1_run.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int, C.POINTER(C.c_int64)]
+        R.ref_q1_file_bytes.restype = C.c_int64
+        R.ref_q1_file_bytes.argtypes = [C.c_void_p]
+        R.ref_q1_free.argtypes = [C.c_void_p]
+        _REFEXEC = R
+    return _REFEXEC
+
+
+class RefQ1:
+    """lineitem's Q1 columns as reference-written AOCS column files in memory; run() = the reference's scan cursor, numeric
+    expressions, grouping hash and sum / avg transition + final functions over them, row at a time (see ref_q1.c's header for
+    what is reference code and what is glue)."""
+
+    def __init__(self, lineitem, checksum=True, blocksize=32768):
+        import numpy as np
+        R = ref_exec_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libexec_ref.so is not built")
+        col = lambda n: np.ascontiguousarray(lineitem.columns[lineitem.attno(n) - 1])
+        dec = [col(n).astype(np.int64) for n in ("l_quantity", "l_extendedprice", "l_discount", "l_tax")]
+        sd = col("l_shipdate").astype(np.int32)
+        rf = col("l_returnflag").astype(np.uint8)
+        ls = col("l_linestatus").astype(np.uint8)
+        self.nrows = int(len(sd))
+        self.h = R.ref_q1_load(self.nrows, *[c.ctypes.data for c in dec], sd.ctypes.data, rf.ctypes.data, ls.ctypes.data,
+                               1 if checksum else 0, blocksize)
+        if not self.h:
+            raise RuntimeError("ref_q1_load: " + R.ref_exec_last_error().decode())
+        self.file_bytes = int(R.ref_q1_file_bytes(self.h))
+
+    def run(self, cutoff):
+        """-> (rows as lists of text in the regression output's column order, rows that passed the qual)"""
+        R = ref_exec_lib()
+        out = C.create_string_buffer(1 << 16)
+        passed = C.c_int64()
+        ng = R.ref_q1_run(self.h, cutoff, out, 1 << 16, C.byref(passed))
+        if ng < 0:
+            raise RuntimeError("ref_q1_run: " + R.ref_exec_last_error().decode())
+        return [ln.split("|") for ln in out.value.decode().splitlines()], int(passed.value)
+
+    def free(self):
+        if self.h:
+            ref_exec_lib().ref_q1_free(self.h)
+            self.h = None

@@ -11,6 +11,7 @@
  *     src/backend/cdb/cdbhash.c               makeCdbHash, cdbhashinit, cdbhash, cdbhashreduce, jump_consistent_hash
  *     src/backend/utils/adt/numeric.c         numeric_in/out, numeric_mul/add/sub, numeric_avg_accum, int8_avg_accum,
  *                                             int4_sum, numeric_sum / numeric_avg / numeric_poly_sum / numeric_poly_avg
+ *     (and, for oracle/ref_q1.c, the AOCS block reader / writer: datumstreamblock.c, cdbappendonlystorageformat.c, pg_crc32c_sb8.c)
  * The generated headers are stand-ins (oracle/ref_shim/) or are derived at build time from the reference's own
  * errcodes.txt and function definitions (oracle/gen_ref_headers.py -> oracle/_ref/gen/).  No reference source is copied:
  * this file stubs the backend services those sources call (palloc, ereport, the fmgr call helpers, interrupt flags)
@@ -58,6 +59,14 @@ static char ref_errbuf[512];
 static int	ref_elevel;
 
 void		ref_exec_abort(const char *what);
+jmp_buf    *ref_exec_jmp(void);
+
+/* the unwind target of ereport(ERROR) / ref_exec_abort, for the drivers in ref_q1.c */
+jmp_buf *
+ref_exec_jmp(void)
+{
+	return &ref_jmp;
+}
 
 void
 ref_exec_abort(const char *what)
@@ -66,11 +75,91 @@ ref_exec_abort(const char *what)
 	longjmp(ref_jmp, 1);
 }
 
-void	   *palloc(Size size) { return malloc(size ? size : 1); }
-void	   *palloc0(Size size) { return calloc(1, size ? size : 1); }
-void	   *repalloc(void *p, Size size) { return realloc(p, size ? size : 1); }
-void		pfree(void *p) { free(p); }
-char	   *pstrdup(const char *s) { return strdup(s); }
+/*
+ * palloc: malloc by default.  ref_q1.c switches on a bump arena that stands in for the executor's per-tuple memory context
+ * (ResetExprContext once per row, execScan.c:195): allocations made while CurrentMemoryContext is REF_AGG_CONTEXT - the
+ * aggregate transition states, which nodeAgg.c keeps in aggcontext - stay on malloc and survive the reset.
+ */
+#define REF_AGG_CONTEXT ((MemoryContext) (uintptr_t) 16)
+#define ARENA_CAP ((size_t) 1 << 22)
+static char *arena;
+static size_t arena_off;
+static int	arena_on;
+
+void		ref_arena_enable(int on);
+void		ref_arena_reset(void);
+
+void
+ref_arena_enable(int on)
+{
+	if (on && !arena)
+		arena = malloc(ARENA_CAP);
+	arena_on = on;
+	arena_off = 0;
+}
+
+void		ref_arena_reset(void) { arena_off = 0; }
+
+static inline bool
+in_arena(const void *p)
+{
+	return arena && (const char *) p >= arena && (const char *) p < arena + ARENA_CAP;
+}
+
+void *
+palloc(Size size)
+{
+	size_t		need = ((size ? size : 1) + 15) & ~(size_t) 15;
+
+	if (arena_on && CurrentMemoryContext != REF_AGG_CONTEXT && arena_off + need + 16 <= ARENA_CAP)
+	{
+		char	   *p = arena + arena_off;
+
+		*(size_t *) p = size;	/* repalloc needs the old size */
+		arena_off += need + 16;
+		return p + 16;
+	}
+	return malloc(size ? size : 1);
+}
+
+void *
+palloc0(Size size)
+{
+	void	   *p = palloc(size);
+
+	memset(p, 0, size ? size : 1);
+	return p;
+}
+
+void *
+repalloc(void *p, Size size)
+{
+	if (in_arena(p))
+	{
+		size_t		old = *(size_t *) ((char *) p - 16);
+		void	   *q = palloc(size);
+
+		memcpy(q, p, old < size ? old : size);
+		return q;
+	}
+	return realloc(p, size ? size : 1);
+}
+
+void
+pfree(void *p)
+{
+	if (!in_arena(p))
+		free(p);
+}
+
+char *
+pstrdup(const char *s)
+{
+	char	   *r = palloc(strlen(s) + 1);
+
+	strcpy(r, s);
+	return r;
+}
 
 bool
 errstart(int elevel, const char *domain)
@@ -129,6 +218,41 @@ pg_snprintf(char *str, size_t count, const char *fmt,...)
 	n = vsnprintf(str, count, fmt, ap);
 	va_end(ap);
 	return n;
+}
+
+int
+pg_sprintf(char *str, const char *fmt,...)
+{
+	va_list		ap;
+	int			n;
+
+	va_start(ap, fmt);
+	n = vsprintf(str, fmt, ap);
+	va_end(ap);
+	return n;
+}
+
+char *
+psprintf(const char *fmt,...)
+{
+	char	   *buf = palloc(1024);
+	va_list		ap;
+
+	va_start(ap, fmt);
+	vsnprintf(buf, 1024, fmt, ap);
+	va_end(ap);
+	return buf;
+}
+
+void		errdetail_internal(const char *fmt,...) { (void) fmt; }
+int			errprintstack(bool printstack) { (void) printstack; return 0; }
+
+/* src/port/qsort.c's name for it (port.h maps qsort to pg_qsort: undo that here or this calls itself) */
+#undef qsort
+void
+pg_qsort(void *base, size_t nel, size_t elsize, int (*cmp) (const void *, const void *))
+{
+	qsort(base, nel, elsize, cmp);
 }
 
 /* fmgr.c:793-860 call helpers: one fcinfo on the stack, NULL result is an error */
@@ -190,7 +314,7 @@ pg_detoast_datum(struct varlena *datum)
 	if (VARATT_IS_SHORT(datum))
 	{
 		Size		data_size = VARSIZE_SHORT(datum) - VARHDRSZ_SHORT;
-		struct varlena *res = malloc(data_size + VARHDRSZ);
+		struct varlena *res = palloc(data_size + VARHDRSZ);
 
 		SET_VARSIZE(res, data_size + VARHDRSZ);
 		memcpy(VARDATA(res), VARDATA_SHORT(datum), data_size);
@@ -207,7 +331,7 @@ AggCheckCallContext(FunctionCallInfo fcinfo, MemoryContext *aggcontext)
 {
 	(void) fcinfo;
 	if (aggcontext)
-		*aggcontext = NULL;
+		*aggcontext = REF_AGG_CONTEXT;
 	return AGG_CONTEXT_AGGREGATE;
 }
 

@@ -237,3 +237,32 @@ def test_scaled_integer_arithmetic_is_numeric_arithmetic(ref):
         assert ref.ref_numeric_binop(0, b"1", _dec(tax, 2).encode(), buf, 256) == 0
         assert ref.ref_numeric_binop(2, buf2.value, buf.value, buf2, 256) == 0
         assert buf2.value.decode() == _dec(ext * (100 - disc) * (100 + tax), 6)
+
+
+def test_q1_through_reference_functions_matches_expected_rows(oracle, ref, golden):
+    """oracle/ref_q1.c: the reference's block writer + reader, numeric_sub / _mul / _add, hashbpchar / bpchareq, numeric_avg_accum,
+    numeric_sum / numeric_avg over lineitem reproduce rpt_tpch's expected Q1 rows (rpt_tpch.source:334-340)"""
+    from cloudberry_b200 import tpch
+    rels, exp = golden
+    q = oracle.RefQ1(rels[0])
+    rows, passed = q.run(tpch.Q1_CUTOFF)
+    assert rows == exp["q1"]
+    assert passed == sum(int(r[-1]) for r in rows)
+    # a cutoff before every row: no groups (a grouped aggregate over no rows returns no rows)
+    assert q.run(-100000) == ([], 0)
+    q.free()
+
+
+@pytest.mark.parametrize("checksum,blocksize", [(True, 32768), (False, 8192), (True, 1 << 20)])
+def test_q1_reference_functions_agree_with_oracle_on_synthetic(oracle, ref, checksum, blocksize):
+    """the same at a size the reference has no fixture for: 300 000 synthetic lineitem rows, oracle (int64 arithmetic) ==
+    reference functions (varlena numeric arithmetic), text for text"""
+    from cloudberry_b200 import tpch
+    sz = tpch.sizes(1)
+    li = tpch._rel("lineitem", tpch.gen_lineitem(42, sz["lineitem"], sz["supplier"], sz["part"], lo=0, hi=300000))
+    want = tpch.format_q1(oracle.execute(tpch.q1_plan(1), [[li]], nthreads=1).rows)
+    q = oracle.RefQ1(li, checksum=checksum, blocksize=blocksize)
+    rows, passed = q.run(tpch.Q1_CUTOFF)
+    q.free()
+    assert rows == want
+    assert len(rows) == 4 and passed == sum(int(r[-1]) for r in rows)
