@@ -9,9 +9,12 @@ Contract (see the task statement): `python bench.py --gpus N --steps K --warmup 
              runs the query, and reads the result rows back
   roofline   algorithmic bytes (38 B/row: SURVEY.md 8d) / CUDA-event duration of the scan+agg kernel, against the
              measured HBM copy bandwidth in MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (row-at-a-time restatement of the reference path) on a bounded sample, rank 0, N=1
-`--impl reference` times that CPU restatement on all host cores (the reference server itself cannot be built
-here: no bison/flex) with the same metric / config keys.
+  cpu_baseline  Q1 on one host core over a bounded sample, rank 0, N=1: kind "reference" = the reference's own per-row code
+             (block reader, numeric arithmetic, hash / equality, transition and final functions compiled where they lie into
+             oracle/_ref/libexec_ref.so, driven by oracle/ref_q1.c), with the oracle's int64 restatement beside it under "port";
+             kind "port" alone where oracle/_ref did not travel
+`--impl reference` times the same reference code on all host cores, one process per core (the reference server itself cannot
+be built here: no bison/flex), with the same metric / config keys; CBGPU_BENCH_CPU=port forces the restatement.
 """
 import argparse
 import json
@@ -93,6 +96,12 @@ class ClockSampler:
         return out
 
 
+def workload_name(sf, world):
+    """config.workload: the same string on both arms"""
+    return "TPC-H SF%g Q1 on %d GPU-segment(s) (scan + hash-agg kernel%s)" % (
+        sf, world, ", two-stage agg over Redistribute Motion" if world > 1 else ", no Motion")
+
+
 def cpu_q1_sample(nthreads, rows_total, seed=42):
     """Run the oracle's Q1 on a bounded sample of the same synthetic lineitem; returns (rows/s, rows, seconds)."""
     from cloudberry_b200 import tpch
@@ -113,13 +122,100 @@ def cpu_q1_sample(nthreads, rows_total, seed=42):
     return per * nthreads / dt, per * nthreads, dt
 
 
+REF_Q1_NOTE = ("reference code per row: datumstreamblock.c block reader over reference-written AOCS column files (CRC-32C verified), "
+               "numeric.c numeric_sub/_mul/_add + numeric_avg_accum/numeric_sum/numeric_avg, varchar.c hashbpchar/bpchareq, hashfn.c, "
+               "compiled where they lie into oracle/_ref/libexec_ref.so; executor glue (ExecScan/ExecAgg/interpreter, not buildable "
+               "here: no bison/flex) restated minimally in oracle/ref_q1.c, so a lower bound on the reference's CPU time")
+
+
+def _ref_q1_worker(idx, per, seed, nsteps, barrier, conn):
+    """One CPU segment: its slice of the synthetic lineitem as reference-written column files, then nsteps timed Q1 runs."""
+    try:
+        from cloudberry_b200 import tpch
+        from oracle import oracle as O
+        sz = tpch.sizes(100)
+        li = tpch._rel("lineitem", tpch.gen_lineitem(seed, sz["lineitem"], sz["supplier"], sz["part"], lo=idx * per, hi=(idx + 1) * per))
+        q = O.RefQ1(li)
+        times = []
+        for _ in range(nsteps):
+            barrier.wait()
+            t0 = time.perf_counter()
+            rows, passed = q.run(tpch.Q1_CUTOFF)
+            times.append(time.perf_counter() - t0)
+            assert len(rows) >= 1 and passed > 0
+        q.free()
+        conn.send(times)
+    except BaseException as e:      # report instead of leaving the parent waiting on the barrier
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+        conn.send("error: %r" % (e,))
+    finally:
+        conn.close()
+
+
+def ref_q1_steps(nproc, per, nsteps, seed=42):
+    """Q1 through the reference's own per-row functions (oracle/ref_q1.c) on nproc CPU segments (one process each, as the
+    reference runs one backend per segment); returns the per-step wall times (max over segments), or None if unavailable."""
+    import multiprocessing as mp
+    from oracle import oracle as O
+    if O.ref_exec_lib() is None or os.environ.get("CBGPU_BENCH_CPU") == "port":
+        return None
+    # spawn, not fork: the main arm calls this from a process that holds a CUDA context and pinned buffers
+    ctx = mp.get_context("spawn")
+    barrier = ctx.Barrier(nproc)
+    pipes, procs = [], []
+    for i in range(nproc):
+        a, b = ctx.Pipe(duplex=False)
+        pr = ctx.Process(target=_ref_q1_worker, args=(i, per, seed, nsteps, barrier, b), daemon=True)
+        pr.start()
+        b.close()
+        pipes.append(a)
+        procs.append(pr)
+    results = []
+    for a in pipes:
+        try:
+            results.append(a.recv() if a.poll(600) else "error: timed out")
+        except (EOFError, OSError):
+            results.append("error: a worker process died")
+    for pr in procs:
+        pr.join(10)
+    if any(isinstance(r, str) for r in results):
+        sys.stderr.write("ref_q1: %s\n" % [r for r in results if isinstance(r, str)][0])
+        return None
+    return [max(r[k] for r in results) for k in range(nsteps)]
+
+
 def run_reference(args):
-    """CPU arm: the restated reference path (oracle) on all host cores, bounded sample per step."""
+    """CPU arm.  Where oracle/_ref/libexec_ref.so exists: TPC-H Q1 through the reference's own per-row code, one process per host
+    core (kind "reference"); else the restated reference path (oracle, kind "port").  Bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     nthreads = min(cores, 64)
+    from cloudberry_b200 import tpch as _tpch
+    per_ref = 1_000_000
+    steps = ref_q1_steps(nthreads, per_ref, args.warmup + args.steps)
+    if steps is not None:
+        timed = steps[args.warmup:]
+        dt = sum(timed)
+        value = per_ref * nthreads * args.steps / dt
+        sample = "Q1 over %d synthetic lineitem rows per step (%d CPU segments = processes x %d rows; %s)" % (
+            per_ref * nthreads, nthreads, per_ref, REF_Q1_NOTE)
+        line = {
+            "impl": "reference", "metric": "TPC-H SF100 Q1 rows/sec", "value": value, "unit": "rows/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "numeric", "data": "synthetic",
+            "config": {"workload": workload_name(args.sf, args.gpus),
+                       "rows_per_gpu": _tpch.sizes(100)["lineitem"],
+                       "note": "the reference's own per-row code for the path on the host cores; the reference server itself needs bison/flex and cannot be built here"},
+            "cpu_baseline": {"value": value, "unit": "rows/s", "cores": nthreads, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
     rows = min(64_000_000, 2_000_000 * nthreads)
     # generate once, time K steps after W warm-ups
     from cloudberry_b200 import tpch
@@ -142,7 +238,7 @@ def run_reference(args):
         "impl": "reference", "metric": "TPC-H SF100 Q1 rows/sec", "value": value, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "TPC-H SF100 Q1 on 1 GPU-segment (scan + hash-agg kernel, no Motion)", "rows_per_gpu": sz["lineitem"],
+        "config": {"workload": workload_name(args.sf, args.gpus), "rows_per_gpu": sz["lineitem"],
                    "note": "CPU restatement of the reference path (oracle/); the reference server needs bison/flex and cannot be built here"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -386,13 +482,25 @@ def main():
         rate, rows, secs = cpu_q1_sample(1, 24_000_000)
         cpu = {"value": rate, "unit": "rows/s", "cores": 1, "kind": "port",
                "sample": "Q1 over the first %d rows of the same synthetic lineitem, %.1f s, one thread (row-at-a-time oracle)" % (rows, secs)}
+        # the same through the reference's own per-row code, one core, where oracle/_ref travelled to this box
+        try:
+            ref_rows = 8_000_000
+            st = ref_q1_steps(1, ref_rows, 2)
+        except Exception as e:
+            sys.stderr.write("ref_q1 baseline skipped: %r\n" % (e,))
+            st = None
+        if st:
+            cpu = {"value": ref_rows / st[1], "unit": "rows/s", "cores": 1, "kind": "reference",
+                   "sample": "Q1 over the first %d rows of the same synthetic lineitem, %.1f s, one process; %s" % (ref_rows, st[1], REF_Q1_NOTE),
+                   "port": {"value": rate, "unit": "rows/s", "cores": 1,
+                            "sample": "the oracle's int64 restatement (oracle/oracle.c) over the first %d rows, %.1f s, one thread" % (rows, secs)}}
 
     if rank == 0:
         line = {
             "metric": "TPC-H SF100 Q1 rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "TPC-H SF%g Q1 on %d GPU-segment(s) (scan + hash-agg kernel%s)" % (args.sf, world, ", two-stage agg over Redistribute Motion" if world > 1 else ", no Motion"),
+            "config": {"workload": workload_name(args.sf, world),
                        "rows_per_gpu": nrows, "groups": ngroups, "l2": "inputs (%.1f GB per GPU) larger than L2" % (nrows * Q1_BYTES_PER_ROW / 1e9),
                        "timing": "CUDA events on the executor's stream, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
