@@ -266,3 +266,16 @@ def test_q1_reference_functions_agree_with_oracle_on_synthetic(oracle, ref, chec
     q.free()
     assert rows == want
     assert len(rows) == 4 and passed == sum(int(r[-1]) for r in rows)
+
+
+def test_product_hashbpchar_is_the_reference_function(ref):
+    """cbgpu_hashbpchar (libcbgpu.so, host side: the per-code hash table of dictionary columns and string constants) ==
+    the reference's hashbpchar on random strings, blank padding included"""
+    rng = random.Random(41)
+    for n in list(range(0, 40)) + [64, 200]:
+        s = bytes(rng.choice(b"ABCDEFGHIJKLMNOPQRSTUVWXYZ abcdefghij0123456789") for _ in range(n))
+        s += b" " * rng.randrange(0, 6)
+        assert capi.hashbpchar(s) == ref.ref_hash_datum(BPCHAR, 0, s, len(s)), s
+    for name in ("BUILDING", "AUTOMOBILE", "MACHINERY", "HOUSEHOLD", "FURNITURE", "ASIA", "AMERICA", "UNITED STATES"):
+        padded = name.ljust(25).encode()
+        assert capi.hashbpchar(name) == ref.ref_hash_datum(BPCHAR, 0, padded, len(padded))
