@@ -255,6 +255,8 @@ def main():
     ap.add_argument("--sf", type=float, default=100.0, help="scale factor of each GPU-segment's shard (default: the BASELINE config)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--joins-sf", type=float, default=None,
+                    help="N > 1 only: scale factor of the ONE database Q3 / Q5 run on (default: --sf; BASELINE configs[3] is 300 on 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-joins", action="store_true", help="skip the Q3 / Q5 join pipelines (extra keys q3, q5)")
     args = ap.parse_args()
@@ -424,6 +426,8 @@ def main():
     joins = {}
     if not args.no_joins:
         from cloudberry_b200 import harness
+        jsf = args.joins_sf if (args.joins_sf and world > 1) else args.sf
+        szj = tpch.sizes(int(jsf) if float(jsf).is_integer() else jsf)
         if world == 1:
             rt_all, _ = harness.device_tables(ctx, args.sf, lineitem=li)
             exj = capi.Executor(ctx, rt_all)
@@ -433,7 +437,7 @@ def main():
             ex = None
             li.free()           # the weak-scaling Q1 shard makes room for the distributed database
             li = None
-            rt_all, _ = harness.distributed_tables(ctx, motion, args.sf, rank, world)
+            rt_all, _ = harness.distributed_tables(ctx, motion, jsf, rank, world)
             exj = capi.Executor(ctx, rt_all, motion=motion)
             owned = rt_all
         plans = {"q3": tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), world, customer_replicated=False),
@@ -462,8 +466,8 @@ def main():
                 t2 = torch.tensor([float(sent)], device="cuda")
                 dist.all_reduce(t2, op=dist.ReduceOp.SUM)
                 sent = float(t2.item())
-            rows_in, nbytes = harness.query_rows_bytes(q, sz)
-            joins[q] = {"value": rows_in / (qms / 1e3), "unit": "rows/s", "ms_per_step": qms, "steps": jsteps, "rows_scanned": rows_in,
+            rows_in, nbytes = harness.query_rows_bytes(q, szj)
+            joins[q] = {"value": rows_in / (qms / 1e3), "unit": "rows/s", "sf": jsf, "ms_per_step": qms, "steps": jsteps, "rows_scanned": rows_in,
                         "scaling": "strong" if world > 1 else "n/a", "result_rows": nres,
                         "gpu_launches_per_step": (ctx.launches() - l0j) // jsteps,
                         "longest_kernel": kn, "longest_kernel_ms": km, "motion_bytes_per_step": int(sent),
