@@ -13,6 +13,8 @@ Contract (see the task statement): `python bench.py --gpus N --steps K --warmup 
              (block reader, numeric arithmetic, hash / equality, transition and final functions compiled where they lie into
              oracle/_ref/libexec_ref.so, driven by oracle/ref_q1.c), with the oracle's int64 restatement beside it under "port";
              kind "port" alone where oracle/_ref did not travel
+  q3, q5     whole-query lines of the metric's join queries (rows scanned / s, whole-query roofline fraction, Motion bytes), each
+             with its own cpu_baseline (the oracle on one core over an SF1 database) at N=1
 `--impl reference` times the same reference code on all host cores, one process per core (the reference server itself cannot
 be built here: no bison/flex), with the same metric / config keys; CBGPU_BENCH_CPU=port forces the restatement.
 """
@@ -185,6 +187,26 @@ def ref_q1_steps(nproc, per, nsteps, seed=42):
         sys.stderr.write("ref_q1: %s\n" % [r for r in results if isinstance(r, str)][0])
         return None
     return [max(r[k] for r in results) for k in range(nsteps)]
+
+
+def cpu_join_samples(sf=1):
+    """Q3 / Q5 through the oracle on one thread over an SF`sf` synthetic database -> {q: cpu_baseline object}."""
+    from cloudberry_b200 import harness, tpch
+    from oracle import oracle as O
+    rels = tpch.gen_tables(sf, O.hashbpchar)
+    sz = tpch.sizes(sf)
+    out = {}
+    for q, plan in (("q3", tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), 1)), ("q5", tpch.q5_plan(tpch.REGIONS.index("AMERICA"), 1))):
+        O.execute(plan, [rels], nthreads=1)         # warm-up (page faults of the hash tables)
+        t0 = time.perf_counter()
+        res = O.execute(plan, [rels], nthreads=1)
+        dt = time.perf_counter() - t0
+        rows_in, _ = harness.query_rows_bytes(q, sz)
+        assert len(res.rows) >= 1
+        out[q] = {"value": rows_in / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                  "sample": "%s over an SF%g synthetic database (%d base-table rows scanned), %.2f s, one thread (row-at-a-time oracle)" % (
+                      q.upper(), sf, rows_in, dt)}
+    return out
 
 
 def run_reference(args):
@@ -516,6 +538,13 @@ def main():
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if joins and world == 1 and not args.no_cpu:
+            # the join queries on one host core: the oracle (restated reference path) over an SF1 database of the same generator
+            try:
+                for q, b in cpu_join_samples().items():
+                    joins[q]["cpu_baseline"] = b
+            except Exception as e:
+                sys.stderr.write("join cpu baselines skipped: %r\n" % (e,))
         line.update(joins)
         print(json.dumps(line))
     if ex:
