@@ -502,7 +502,8 @@ ref_q1_run(void *h, int32 cutoff, char *out, int cap, int64 *rows_passed)
 					charge;
 
 		ref_arena_reset();		/* ResetExprContext(econtext) per tuple */
-		/* aocs_getnext: every projected column's cursor advances for every row */
+		/* aocs_getnext: every projected column's cursor advances for every row (for a row the pushed-down qual rejects the
+		 * reference skips the remaining columns' Get, aocsam.c:1359-1360; Q1's qual rejects under 2 % of the rows) */
 		for (int c = 0; c < NCOLS; c++)
 			if (!reader_next(&rd[c], &v[c], &isnull[c]))
 				ref_exec_abort("column file ended early");
