@@ -279,3 +279,20 @@ def test_product_hashbpchar_is_the_reference_function(ref):
     for name in ("BUILDING", "AUTOMOBILE", "MACHINERY", "HOUSEHOLD", "FURNITURE", "ASIA", "AMERICA", "UNITED STATES"):
         padded = name.ljust(25).encode()
         assert capi.hashbpchar(name) == ref.ref_hash_datum(BPCHAR, 0, padded, len(padded))
+
+
+def test_avg_at_full_scale_against_numeric_div(oracle, ref):
+    """SF100-sized states: N up to 10^9 rows per group and scaled sums up to 10^24 (beyond 64 bits: the device's 128-bit
+    accumulator) - numeric_avg is numeric_div(sumX, N) (numeric.c:6056-6088), so the reference's numeric_div on the texts is
+    the expected answer for both finalisers"""
+    rng = random.Random(2024)
+    buf = C.create_string_buffer(256)
+    for _ in range(1500):
+        ds = rng.choice([0, 2, 4, 6])
+        n = rng.choice([1, 7, 148_000_000, 600_037_902, 999_999_999, rng.randrange(1, 10 ** 9)])
+        total = rng.randrange(0, 10 ** rng.choice([3, 9, 15, 18, 19, 20, 22, 24])) * rng.choice([1, 1, 1, -1])
+        assert ref.ref_numeric_binop(3, _dec(total, ds).encode(), str(n).encode(), buf, 256) == 0, ref.ref_exec_last_error()
+        want_avg = buf.value.decode()
+        for got_sum, got_avg in _both_texts(oracle, total, ds, n):
+            assert got_sum == _dec(total, ds)
+            assert got_avg == want_avg, (total, ds, n)
