@@ -98,6 +98,21 @@ class ClockSampler:
         return out
 
 
+def host_cores():
+    """cores this process may actually use: the affinity mask, capped by the cgroup's CPU quota if there is one"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def workload_name(sf, world):
     """config.workload: the same string on both arms"""
     return "TPC-H SF%g Q1 on %d GPU-segment(s) (scan + hash-agg kernel%s)" % (
@@ -215,7 +230,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     nthreads = min(cores, 64)
     from cloudberry_b200 import tpch as _tpch
     per_ref = 1_000_000
