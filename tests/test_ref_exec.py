@@ -296,3 +296,19 @@ def test_avg_at_full_scale_against_numeric_div(oracle, ref):
         for got_sum, got_avg in _both_texts(oracle, total, ds, n):
             assert got_sum == _dec(total, ds)
             assert got_avg == want_avg, (total, ds, n)
+
+
+def test_avg_at_the_edges_of_the_128_bit_state(oracle, ref):
+    """sums at +-2^127, N up to 2^63 - 1, display scales 0-12, powers of NBASE as divisors (the weight / first-digit rule of
+    select_div_scale flips there)"""
+    rng = random.Random(5)
+    buf = C.create_string_buffer(512)
+    for _ in range(4000):
+        ds = rng.choice([0, 1, 2, 3, 4, 6, 9, 12])
+        v = rng.choice([2 ** 127 - 1, -2 ** 127, rng.randrange(-10 ** 38, 10 ** 38), rng.randrange(-10 ** 30, 10 ** 30),
+                        rng.randrange(-10 ** 12, 10 ** 12), rng.randrange(0, 10 ** 5)])
+        n = rng.choice([1, 3, 9, 9999, 10000, 10001, 2 ** 31, 2 ** 62, 2 ** 63 - 1, rng.randrange(1, 10 ** 15), 10 ** rng.randrange(0, 18)])
+        assert ref.ref_numeric_binop(3, _dec(v, ds).encode(), str(n).encode(), buf, 512) == 0, ref.ref_exec_last_error()
+        for got_sum, got_avg in _both_texts(oracle, v, ds, n):
+            assert got_sum == _dec(v, ds)
+            assert got_avg == buf.value.decode(), (v, ds, n)
