@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """AddressSanitizer + UBSan fuzzing of the host builds of the decoders that also run on the device: the serial zlib and
 Zstandard decoders (cloudberry_b200/csrc/inflate.cuh, zstd_dec.cuh through tests/native/*.cpp, exact-size heap buffers so
-any read past the input or write past the output is reported) and the tuple chunk parser (csrc/exec/cb_tupser.c).
+any read past the input or write past the output is reported), the tuple chunk parser (csrc/exec/cb_tupser.c) and the numeric
+finaliser (csrc/exec/cb_numeric.c: 128-bit states at their limits, every display scale, output buffers that are too small).
 Streams are bit-flipped, truncated and given too-small outputs.  CPU only:
 
     python tools/fuzz_decoders.py [rounds]
@@ -24,6 +25,8 @@ def build():
     subprocess.check_call(["g++", "-std=c++17"] + flags + ["-o", OUT + "/libi.so", os.path.join(ROOT, "tests", "native", "inflate_host.cpp")])
     subprocess.check_call(["gcc"] + flags + ["-I" + os.path.join(ROOT, "include"), "-o", OUT + "/libt.so",
                                              os.path.join(ROOT, "cloudberry_b200", "csrc", "exec", "cb_tupser.c")])
+    subprocess.check_call(["gcc"] + flags + ["-fno-sanitize-recover=undefined", "-I" + os.path.join(ROOT, "include"), "-o", OUT + "/libn.so",
+                                             os.path.join(ROOT, "cloudberry_b200", "csrc", "exec", "cb_numeric.c")])
 
 
 def main():
@@ -118,6 +121,27 @@ def main():
             pos += used.value
         libc.free(pin)
     print("tuple chunks: %d parses of damaged streams, no sanitizer report" % m)
+    # numeric finalisation: extreme (sum, N) states into exact-size output buffers
+    import random
+    N = C.CDLL(OUT + "/libn.so")
+    N.cb_numeric_sum_text.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]
+    N.cb_numeric_avg_text.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_int32]
+    pr = random.Random(1)
+    k = 0
+    for _ in range(rounds * 100):
+        ds = pr.choice([0, 1, 2, 4, 6, 9, 12, 31])
+        v = pr.choice([0, 1, -1, 2 ** 127 - 1, -2 ** 127, pr.randrange(-10 ** 38, 10 ** 38), pr.randrange(-10 ** 6, 10 ** 6)])
+        cnt = pr.choice([1, 2, 3, 7, 2 ** 31, 2 ** 62, 2 ** 63 - 1, pr.randrange(1, 10 ** 12)])
+        u = v & (2 ** 128 - 1)
+        lo, hi = u & (2 ** 64 - 1), u >> 64
+        lo, hi = (lo - 2 ** 64 if lo >= 2 ** 63 else lo), (hi - 2 ** 64 if hi >= 2 ** 63 else hi)
+        for cap in (200, 48, 8, 1):
+            pout = libc.malloc(cap)
+            N.cb_numeric_sum_text(lo, hi, ds, pout, cap)
+            N.cb_numeric_avg_text(lo, hi, ds, cnt, pout, cap)
+            libc.free(pout)
+            k += 2
+    print("numeric finaliser: %d calls at the limits of the state, no sanitizer report" % k)
 
 if __name__ == "__main__":
     main()
