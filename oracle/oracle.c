@@ -8,7 +8,9 @@
  *
  * Parity pin: reproduces the reference regression test rpt_tpch's expected Q1/Q3/Q5 rows
  * (src/test/regress/output/rpt_tpch.source:334-340, 465-477, 536-543) from the reference's CSVs
- * (tests/test_oracle_golden.py); hashing is pinned separately (oracle/pg_hash.h).
+ * (tests/test_oracle_golden.py); hashing (oracle/pg_hash.h), cdbhash routes and the numeric finalisation are pinned
+ * against the reference's own hashfunc.c / varchar.c / cdbhash.c / numeric.c as compiled into oracle/_ref/libexec_ref.so
+ * (tests/test_ref_exec.py), where Q1 as a whole is also cross-checked against the reference's per-row code (ref_q1.c).
  *
  * Shape: a Volcano pull executor, one Datum-boxed row per call, like the code it restates:
  *   scan      aocs_getnext (access/aocs/aocsam.c:1418,1138) + visimap test (:1240) + ExecScan qual
