@@ -109,3 +109,24 @@ def test_join_and_aggregate_semantics(oracle, jointype, nf, nd, dup, null_frac, 
         got = [r[:av] + r[av + 1:] for r in got]
         want = [r[:av] + r[av + 1:] for r in want]
     assert _canon(got) == _canon(want)
+
+
+def test_float8_sum_is_sequential_float8pl(oracle):
+    """sum(float8) = float8pl row after row (float.c:774), avg = sum / N (float8_avg, float.c:3148): the oracle's doubles
+    are the ones a sequential executor produces, bit for bit - the GPU's tree-ordered sums are held to 1e-12 sqrt(N) of these"""
+    n = 50021
+    fo = fact(n, seed=7).set_dict_hashes(oracle.hashbpchar)
+    sc = scan(1, fo, ["g", "x"])
+    plan = agg_over(sc, ["g", "x"], ["g"], [("sx", P.AGG_SUM, "x"), ("ax", P.AGG_AVG, "x"), ("n", P.AGG_COUNT_STAR, None)])
+    got = {r[0]: r for r in oracle.execute(plan, [[fo]]).rows}
+    acc, cnt = {}, {}
+    g, x = fo.columns[fo.names.index("g")], fo.columns[fo.names.index("x")]
+    for i in range(n):
+        k = int(g[i])
+        acc[k] = acc.get(k, 0.0) + float(x[i])
+        cnt[k] = cnt.get(k, 0) + 1
+    assert set(got) == set(acc)
+    for k in acc:
+        assert float(got[k][1]) == acc[k]
+        assert float(got[k][2]) == acc[k] / cnt[k]
+        assert got[k][3] == cnt[k]
