@@ -33,6 +33,7 @@
 #include "postgres.h"
 
 #include "access/tupdesc.h"
+#include "access/xact.h"
 #include "catalog/pg_type.h"
 #include "cdb/cdbutil.h"
 #include "cdb/cdbvars.h"
@@ -81,9 +82,13 @@ typedef struct ShimPendingConst
 static ShimScan *cur_scan = NULL;		/* the SeqScan whose expressions are being translated, else NULL   */
 static bool cur_in_qual = false;
 static List *pending_consts = NIL;
+/* integration/cbgpu_shim_interconnect.c: the session's NCCL communicator, its token shipped as a synced GUC */
 extern CbInterconnect *cbgpu_shim_interconnect(cbgpu_ctx *ctx, EState *estate);
+extern void cbgpu_shim_define_gucs(void);
+extern void cbgpu_shim_qd_prepare(bool previous_query_failed);
 
 static ExecutorStart_hook_type prev_ExecutorStart = NULL;
+static ExecutorEnd_hook_type prev_ExecutorEnd = NULL;
 static cbgpu_ctx *shim_ctx = NULL;		/* one device context per backend, created after fork, on first use */
 
 typedef struct CbgpuShim
@@ -770,9 +775,56 @@ shim_walk(PlanState *ps, EState *estate)
 	shim_walk(innerPlanState(ps), estate);
 }
 
+/* dispatcher-side bookkeeping for the interconnect token: how many counted queries are between ExecutorStart and ExecutorEnd */
+static int	qd_depth = 0;
+static bool qd_failed = false;
+
+static bool
+qd_counts(CmdType operation, int eflags)
+{
+	return Gp_role == GP_ROLE_DISPATCH && operation == CMD_SELECT && !(eflags & EXEC_FLAG_EXPLAIN_ONLY);
+}
+
+static void
+cbgpu_ExecutorEnd(QueryDesc *queryDesc)
+{
+	bool		counted = queryDesc->estate != NULL && qd_counts(queryDesc->operation, queryDesc->estate->es_top_eflags);
+
+	if (prev_ExecutorEnd)
+		prev_ExecutorEnd(queryDesc);
+	else
+		standard_ExecutorEnd(queryDesc);
+	if (counted && qd_depth > 0)
+		qd_depth--;
+}
+
+/* ereport(ERROR) unwinds past ExecutorEnd: the abort is where an interrupted query shows (access/xact.h XACT_EVENT_ABORT) */
+static void
+cbgpu_xact_callback(XactEvent event, void *arg)
+{
+	(void) arg;
+	if (event == XACT_EVENT_ABORT || event == XACT_EVENT_PARALLEL_ABORT)
+	{
+		if (qd_depth > 0)
+			qd_failed = true;
+		qd_depth = 0;
+	}
+}
+
 static void
 cbgpu_ExecutorStart(QueryDesc *queryDesc, int eflags)
 {
+	/* on the dispatcher, before standard_ExecutorStart dispatches the plan: every QE must know the interconnect token.
+	 * A query that died in error may have left a collective half done on some segment: the next one starts a new token */
+	if (qd_counts(queryDesc->operation, eflags))
+	{
+		if (qd_depth == 0)
+		{
+			cbgpu_shim_qd_prepare(qd_failed);
+			qd_failed = false;
+		}
+		qd_depth++;				/* nested queries (SPI in functions) keep the outer query's token */
+	}
 	if (prev_ExecutorStart)
 		prev_ExecutorStart(queryDesc, eflags);
 	else
@@ -786,4 +838,8 @@ _PG_init(void)
 {
 	prev_ExecutorStart = ExecutorStart_hook;	/* executor/execMain.c:124 */
 	ExecutorStart_hook = cbgpu_ExecutorStart;
+	prev_ExecutorEnd = ExecutorEnd_hook;
+	ExecutorEnd_hook = cbgpu_ExecutorEnd;
+	RegisterXactCallback(cbgpu_xact_callback, NULL);
+	cbgpu_shim_define_gucs();
 }
