@@ -11,8 +11,8 @@
  *   cbgpu_ExecutorStart            standard_ExecutorStart, then walks the PlanState tree; the root of every
  *                                  maximal sub-tree made only of SeqScan / Hash / HashJoin / Agg / Motion nodes
  *                                  whose expressions translate gets its ExecProcNode replaced
- *                                  (ExecSetExecProcNode-style: execProcnode.c:580; PlanState.ExecProcNode,
- *                                  nodes/execnodes.h:1065)
+ *                                  (ExecSetExecProcNode, execProcnode.c:580: the GPDB wrapper with its instrumentation,
+ *                                  probes and interrupt checks stays around it; nodes/execnodes.h:1065)
  *   translate_plan / translate_expr   Plan -> CbPlan, Expr -> CbExpr (include/cb_plan.h), List* -> arrays,
  *                                  operator / aggregate Oids -> CbOp / CbAggFn by catalog name
  *   cbgpu_ExecNode                 ExecProcNodeMtd: pulls a CbTupleTableSlot from cb_ExecProcNode and stores it as
@@ -758,21 +758,31 @@ shim_take_over(PlanState *ps, EState *estate)
 		e->next = shim_list;
 		shim_list = e;
 	}
-	shim->saved_ExecProcNode = ps->ExecProcNode;
-	ps->ExecProcNode = cbgpu_ExecNode;	/* what ExecSetExecProcNode does (execProcnode.c:580) */
-	ps->ExecProcNodeReal = cbgpu_ExecNode;
+	shim->saved_ExecProcNode = ps->ExecProcNodeReal;
+	/* ExecProcNodeReal = ours, ExecProcNode = ExecProcNodeFirst -> ExecProcNodeGPDB (execProcnode.c:580-681): the reference's
+	 * own wrapper keeps doing, around every call of ours, what it does for its own nodes - the QueryFinishPending early-out,
+	 * the squelch check, the execprocnode DTrace probes, query_info_collect_hook(METRICS_PLAN_NODE_EXECUTING) and
+	 * InstrStartNode / InstrStopNode, so EXPLAIN ANALYZE shows the replaced node's rows and time on the node it replaced */
+	ExecSetExecProcNode(ps, cbgpu_ExecNode);
 	return true;
 }
 
+/*
+ * ExecReScan has no hook: a replaced node that were rescanned would have its (unused) CPU state reset by the node's own
+ * ReScan function while the device state went on from where it was.  So a sub-tree is taken over only where the executor
+ * cannot rescan it: nothing in it depends on a parameter (Plan.allParam empty: no correlated SubPlan / NestLoop parameter
+ * will ever set chgParam on it, execAmi.c:77-120), and it does not sit on the inner side of a NestLoop or MergeJoin (rescanned
+ * per outer row / restored to a mark).  SubPlans and InitPlans (PlanState.subPlan / initPlan) are not walked at all.
+ */
 static void
-shim_walk(PlanState *ps, EState *estate)
+shim_walk(PlanState *ps, EState *estate, bool may_rescan)
 {
 	if (ps == NULL)
 		return;
-	if (shim_take_over(ps, estate))
+	if (!may_rescan && bms_is_empty(ps->plan->allParam) && shim_take_over(ps, estate))
 		return;					/* the whole sub-tree is the GPU's: do not descend */
-	shim_walk(outerPlanState(ps), estate);
-	shim_walk(innerPlanState(ps), estate);
+	shim_walk(outerPlanState(ps), estate, may_rescan);
+	shim_walk(innerPlanState(ps), estate, may_rescan || IsA(ps, NestLoopState) || IsA(ps, MergeJoinState));
 }
 
 /* dispatcher-side bookkeeping for the interconnect token: how many counted queries are between ExecutorStart and ExecutorEnd */
@@ -830,7 +840,7 @@ cbgpu_ExecutorStart(QueryDesc *queryDesc, int eflags)
 	else
 		standard_ExecutorStart(queryDesc, eflags);
 	if (!(eflags & EXEC_FLAG_EXPLAIN_ONLY))
-		shim_walk(queryDesc->planstate, queryDesc->estate);
+		shim_walk(queryDesc->planstate, queryDesc->estate, (eflags & (EXEC_FLAG_REWIND | EXEC_FLAG_BACKWARD | EXEC_FLAG_MARK)) != 0);
 }
 
 void
