@@ -67,3 +67,33 @@ def test_numeric_avg_against_python_decimal():
 def test_hashbpchar_host_matches_oracle(oracle):
     for t in ["", "A", "MACHINERY", "UNITED STATES", "MIDDLE EAST     ", "x" * 40, "1-URGENT", " "]:
         assert capi.hashbpchar(t) == oracle.hashbpchar(t)
+
+
+def test_no_device_means_a_loud_error_not_a_fallback():
+    """On a box without a usable GPU every way into the product ends in an error that says so: the context cannot be
+    created (CbgpuError with the CUDA runtime's message), and the operator entry points refuse a NULL context / executor
+    state instead of computing anything on the host.  (Skipped where a device is visible: there the -m gpu tests apply.)"""
+    import ctypes as C
+
+    import pytest
+    G = capi.gpu()
+    if G.cbgpu_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(capi.CbgpuError) as ei:
+        capi.Context(0)
+    assert ei.value.code != 0 and "cuda" in str(ei.value).lower()
+    E = capi.ex()
+    # no context -> no executor state; no executor state -> no plan state (execProcnode.c:190's contract: NULL in, NULL out)
+    es = E.cb_CreateExecutorState(None, None, 0)
+    if es:
+        from cloudberry_b200 import tpch
+        from cloudberry_b200 import plan as P
+        ps = E.cb_ExecInitNode(P.plan_ptr(tpch.q1_plan(1)), es, 0)
+        if ps:
+            # initialisation is lazy (streams are opened by the first pull): the first ExecProcNode must fail, with a message
+            slot = E.cb_ExecProcNode(ps)
+            assert (not slot) or slot.contents.tts_empty
+            E.cb_ExecEndNode(ps)
+        assert es.contents.es_errcode != 0
+        assert E.cb_estate_error(es)
+        E.cb_FreeExecutorState(es)
