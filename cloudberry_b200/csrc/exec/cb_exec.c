@@ -2666,7 +2666,7 @@ cb_cluster_init_plan(CbCluster *c, CbPlan *plan)
 		c->roots[s] = cb_ExecInitNode(plan, c->estates[s], 0);
 		if (!c->roots[s])
 		{
-			snprintf(c->err, sizeof(c->err), "segment %d: %s", s, c->estates[s]->es_errmsg);
+			snprintf(c->err, sizeof(c->err), "segment %d: %.480s", s, c->estates[s]->es_errmsg);
 			return c->estates[s]->es_errcode ? c->estates[s]->es_errcode : CBGPU_ERR_INVALID;
 		}
 	}
@@ -2840,7 +2840,7 @@ cb_cluster_next(CbCluster *c)
 		slot = cb_ExecProcNode(c->roots[c->cur]);
 		if (c->estates[c->cur]->es_errcode)
 		{
-			snprintf(c->err, sizeof(c->err), "segment %d: %s", c->cur, c->estates[c->cur]->es_errmsg);
+			snprintf(c->err, sizeof(c->err), "segment %d: %.480s", c->cur, c->estates[c->cur]->es_errmsg);
 			return NULL;
 		}
 		if (!CbTupIsNull(slot))
@@ -2861,7 +2861,7 @@ cb_cluster_error(CbCluster *c)
 {
 	for (int s = 0; s < c->nsegs; s++)
 		if (c->estates[s]->es_errcode && !c->err[0])
-			snprintf(c->err, sizeof(c->err), "segment %d: %s", s, c->estates[s]->es_errmsg);
+			snprintf(c->err, sizeof(c->err), "segment %d: %.480s", s, c->estates[s]->es_errmsg);
 	return c->err;
 }
 

@@ -1,0 +1,74 @@
+"""The host side of the product without a GPU (not gpu): libcbexec.so + the host code of libcbgpu.so run over a CUDA runtime
+that computes nothing (tests/native/fake_cudart.c, LD_PRELOADed into a subprocess: zeroed host memory as "device" memory,
+kernel launches are no-ops).  No result can come out of that - every query returns zero rows, which the test asserts - but
+everything the host does around the kernels is exercised: Plan -> stream translation, pipeline program emission, the
+specialised-kernel matcher, Motions inside a 3-segment cluster, launch bookkeeping, read-back, clean-up, and the refusals
+(HAVING, sorted aggregation, Sort without LIMIT, RIGHT join, numeric join keys, a scanrelid outside the range table) with the
+error code and message a caller sees.  Run twice: as built, and with libcbexec.so rebuilt under AddressSanitizer + UBSan."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = "/usr/local/cuda/include"
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime_api.h")), reason="needs the CUDA headers")
+
+UNSUPPORTED, INVALID = -3, -2
+
+
+@pytest.fixture(scope="module")
+def fake(tmp_path_factory):
+    d = tmp_path_factory.mktemp("fakecuda")
+    so = str(d / "libfakecudart.so")
+    subprocess.check_call(["gcc", "-O1", "-g", "-shared", "-fPIC", "-Wall", "-Werror", "-I" + CUDA_INC, "-o", so,
+                           os.path.join(ROOT, "tests", "native", "fake_cudart.c")])
+    return d, so
+
+
+def _run(env):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "host_logic_worker.py")], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, **env))
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("HOSTLOGIC ")]
+    assert p.returncode == 0 and lines, (p.stdout[-2000:], p.stderr[-4000:])
+    return json.loads(lines[0][len("HOSTLOGIC "):])
+
+
+def _check(out):
+    ran, refused = out["ran"], out["refused"]
+    for name in ("q1", "q3", "q5", "q1_generic", "q3_generic", "q5_generic", "q1_3seg", "q3_3seg", "q5_3seg",
+                 "ssb_q4_1", "ssb_q4_2", "ssb_q4_3", "q1_after_refusals"):
+        assert ran[name]["rows"] == 0, name            # nothing is computed on the host: no kernel, no rows
+    for name in ("q1", "q3", "q5", "q1_3seg", "q3_3seg", "q5_3seg"):
+        assert ran[name]["launches"] > 0
+    assert ran["q3_3seg"]["launches"] > ran["q3"]["launches"]      # three segment executors and their Motions
+    want = {"having": (UNSUPPORTED, "HAVING"), "sorted_agg": (UNSUPPORTED, "hashed / plain"),
+            "sort_without_limit": (UNSUPPORTED, "Sort without LIMIT"), "right_join": (UNSUPPORTED, "join type"),
+            "numeric_join_key": (UNSUPPORTED, "hash_numeric"), "bad_scanrelid": (INVALID, "scanrelid 9")}
+    for name, (code, frag) in want.items():
+        assert refused[name]["error"] is not None, name
+        assert refused[name]["code"] == code and frag in refused[name]["error"], refused[name]
+    for name in ("having", "sorted_agg", "numeric_join_key", "bad_scanrelid"):
+        assert refused[name]["launches"] == 0          # refused before anything reached the device
+
+
+def test_host_executor_over_a_runtime_that_computes_nothing(fake):
+    _, so = fake
+    _check(_run({"LD_PRELOAD": so}))
+
+
+def test_the_same_under_address_and_ub_sanitizers(fake):
+    d, so = fake
+    asan = subprocess.check_output(["gcc", "-print-file-name=libasan.so"], text=True).strip()
+    if not os.path.exists(asan):
+        pytest.skip("no libasan")
+    libdir = str(d)
+    src = os.path.join(ROOT, "cloudberry_b200", "csrc", "exec")
+    os.symlink(os.path.join(ROOT, "cloudberry_b200", "libcbgpu.so"), os.path.join(libdir, "libcbgpu.so"))
+    subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-shared", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                           "-o", os.path.join(libdir, "libcbexec.so")] +
+                          [os.path.join(src, f) for f in ("cb_exec.c", "cb_numeric.c", "cb_aocs_load.c", "cb_tupser.c")] +
+                          ["-L" + libdir, "-lcbgpu", "-Wl,-rpath," + libdir])
+    _check(_run({"LD_PRELOAD": asan + ":" + so, "ASAN_OPTIONS": "detect_leaks=0", "CB_TEST_LIBDIR": libdir}))
