@@ -102,6 +102,52 @@ def main():
             d.free()
     for d in dev:
         d.free()
+
+    # 5. the storage side's host half: the block header walk of cbgpu_aocs_decode_column over reference-written column files,
+    #    whole and damaged (bit flips, truncations), handed over in exact-size malloc'd buffers so that a sanitizer build sees any
+    #    read past the file.  The kernels being no-ops, only return codes matter: no crash, no report, errors stay errors.
+    if os.environ.get("CB_TEST_AOCS_FUZZ"):
+        import ctypes as C
+
+        import numpy as np
+        from test_aocs_format import CASES, ZCASES, ZSTDCASES
+        decode = {"int4": (P.INT4, 4, 0, 4), "int8": (P.INT8, 8, 0, 8), "date": (P.DATE, 4, 0, 4), "float8": (P.FLOAT8, 8, 0, 8),
+                  "bool": (P.BOOL, 1, 0, 1), "numeric": (P.NUMERIC, -1, 1, 4), "bpchar": (P.BPCHAR1, -1, 2, 4)}
+        libc = C.CDLL(None)
+        libc.malloc.restype = C.c_void_p
+        libc.malloc.argtypes = [C.c_size_t]
+        libc.free.argtypes = [C.c_void_p]
+        rng = np.random.default_rng(11)
+        calls = errors = 0
+        for case in CASES + ZCASES + ZSTDCASES:
+            name, typname, checksum, blocksize, dscale, nblocks, raw, values, nulls = case[:9]
+            kind = 0 if len(case) == 9 else (2 if name.startswith("zstd") else 1)
+            ctype, attlen, varkind, align = decode[typname]
+            rel = capi.DeviceRelation(ctx, len(values) + 8, [ctype], dscales=[dscale])
+            variants = [raw]
+            for _ in range(int(os.environ["CB_TEST_AOCS_FUZZ"])):
+                bad = bytearray(raw)
+                how = rng.integers(0, 3)
+                if how == 0:                                    # a flipped bit in the first bytes of some 4 KB stretch: headers live there
+                    pos = int(rng.integers(0, max(len(bad) // 4096, 1))) * 4096 + int(rng.integers(0, 32))
+                    bad[min(pos, len(bad) - 1)] ^= 1 << int(rng.integers(0, 8))
+                elif how == 1:                                  # anywhere
+                    bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+                else:                                           # cut short
+                    bad = bad[:int(rng.integers(0, len(bad)))]
+                variants.append(bytes(bad))
+            for v in variants:
+                pin = libc.malloc(max(len(v), 1))
+                C.memmove(pin, v, len(v))
+                n = C.c_int64()
+                rc = G.cbgpu_aocs_decode_column_ex(ctx.h, pin, len(v), 1 if checksum else 0, kind, attlen, varkind, align, rel.h, 0, 0, C.byref(n))
+                libc.free(pin)
+                calls += 1
+                errors += 1 if rc else 0
+                if v is raw:
+                    assert rc == 0 and n.value == len(values), (name, rc, ctx.error())
+            rel.free()
+        out["aocs_fuzz"] = {"calls": calls, "errors": errors}
     ctx.close()
     print("HOSTLOGIC " + json.dumps(out))
 

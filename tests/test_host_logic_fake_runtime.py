@@ -72,3 +72,31 @@ def test_the_same_under_address_and_ub_sanitizers(fake):
                           [os.path.join(src, f) for f in ("cb_exec.c", "cb_numeric.c", "cb_aocs_load.c", "cb_tupser.c")] +
                           ["-L" + libdir, "-lcbgpu", "-Wl,-rpath," + libdir])
     _check(_run({"LD_PRELOAD": asan + ":" + so, "ASAN_OPTIONS": "detect_leaks=0", "CB_TEST_LIBDIR": libdir}))
+
+
+def test_storage_side_host_walk_under_sanitizers(fake, tmp_path):
+    """BOTH libraries rebuilt with AddressSanitizer + UBSan on their host code (the .cu files' host half through nvcc
+    -Xcompiler): the plan shapes again, then cbgpu_aocs_decode_column's block header walk over every reference-written golden
+    column file (plain, RLE / delta, zlib, zstd) and 40 damaged copies of each from exact-size buffers"""
+    import shutil
+    _, so = fake
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    asan = subprocess.check_output(["gcc", "-print-file-name=libasan.so"], text=True).strip()
+    if not (os.path.exists(nvcc) and os.path.exists(asan)):
+        pytest.skip("needs nvcc and libasan")
+    tree = tmp_path / "tree"
+    shutil.copytree(os.path.join(ROOT, "cloudberry_b200", "csrc"), tree / "cloudberry_b200" / "csrc",
+                    ignore=shutil.ignore_patterns("*.o"))
+    shutil.copytree(os.path.join(ROOT, "include"), tree / "include")
+    san = "-Xcompiler -fsanitize=address -Xcompiler -fsanitize=undefined -Xcompiler -fno-omit-frame-pointer"
+    subprocess.check_call(["make", "-s", "-j8", "-C", str(tree / "cloudberry_b200" / "csrc"), "../libcbgpu.so",
+                           "ARCH=-gencode arch=compute_100a,code=sm_100a " + san])
+    libdir = str(tree / "cloudberry_b200")
+    src = os.path.join(ROOT, "cloudberry_b200", "csrc", "exec")
+    subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-shared", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                           "-o", os.path.join(libdir, "libcbexec.so")] +
+                          [os.path.join(src, f) for f in ("cb_exec.c", "cb_numeric.c", "cb_aocs_load.c", "cb_tupser.c")] +
+                          ["-L" + libdir, "-lcbgpu", "-Wl,-rpath," + libdir])
+    out = _run({"LD_PRELOAD": asan + ":" + so, "ASAN_OPTIONS": "detect_leaks=0", "CB_TEST_LIBDIR": libdir, "CB_TEST_AOCS_FUZZ": "40"})
+    _check(out)
+    assert out["aocs_fuzz"]["calls"] > 1000 and out["aocs_fuzz"]["errors"] > 100
