@@ -103,6 +103,43 @@ def main():
     for d in dev:
         d.free()
 
+    # 4b. the segment file loader's file handling (cb_aocs_load_segfile): reference naming, EOF bookkeeping, what is missing
+    import tempfile
+
+    import numpy as np
+    from test_aocs_format import CASES
+    byname = {c[0]: c for c in CASES}
+    a, b = byname["int4_plain"], byname["numeric_price"]
+    nrows = min(len(a[7]), len(b[7]))
+    seg = {"loads": {}, "errors": {}}
+    with tempfile.TemporaryDirectory() as td:
+        base = os.path.join(td, "16384")
+        segno = 2
+        for filenum, case in ((1, a), (2, b)):
+            with open(capi.aocs_segfile_path(base, segno, filenum), "wb") as f:
+                f.write(case[6] + b"\0" * 100)                 # bytes past the recorded EOF exist on disk and must be ignored
+        cols = [(0, 1, 4, 0, 4, 0, len(a[6])), (1, 2, -1, 1, 4, 0, len(b[6]))]
+        rel = capi.DeviceRelation(ctx, max(len(a[7]), len(b[7])) + 4, [P.INT4, P.NUMERIC], dscales=[0, b[4]])
+
+        def attempt(name, *args, **kw):
+            try:
+                seg["loads"][name] = list(rel.load_segfile(*args, **kw))
+            except capi.CbgpuError as e:
+                seg["errors"][name] = {"code": e.code, "msg": str(e)}
+        if len(a[7]) == len(b[7]):
+            attempt("as_recorded", base, segno, a[2], cols)
+        attempt("one_column", base, segno, a[2], cols[:1])
+        attempt("eof_beyond_file", base, segno, a[2], [(0, 1, 4, 0, 4, 0, len(a[6]) + 4096)])
+        attempt("eof_inside_a_block", base, segno, a[2], [(0, 1, 4, 0, 4, 0, len(a[6]) - 7)])
+        attempt("missing_column_file", base, segno, a[2], [(0, 5, 4, 0, 4, 0, 64)])
+        attempt("missing_segno", base, 9, a[2], cols[:1])
+        attempt("segno_out_of_range", base, 128, a[2], cols[:1])
+        attempt("eof_zero", base, segno, a[2], [(0, 1, 4, 0, 4, 0, 0)])
+        rel.free()
+    seg["rows"] = {"int4_plain": int(len(a[7])), "numeric_price": int(len(b[7]))}
+    out["segfile"] = seg
+    del nrows, np
+
     # 5. the storage side's host half: the block header walk of cbgpu_aocs_decode_column over reference-written column files,
     #    whole and damaged (bit flips, truncations), handed over in exact-size malloc'd buffers so that a sanitizer build sees any
     #    read past the file.  The kernels being no-ops, only return codes matter: no crash, no report, errors stay errors.

@@ -2,7 +2,7 @@
 that computes nothing (tests/native/fake_cudart.c, LD_PRELOADed into a subprocess: zeroed host memory as "device" memory,
 kernel launches are no-ops).  No result can come out of that - every query returns zero rows, which the test asserts - but
 everything the host does around the kernels is exercised: Plan -> stream translation, pipeline program emission, the
-specialised-kernel matcher, Motions inside a 3-segment cluster, launch bookkeeping, read-back, clean-up, and the refusals
+specialised-kernel matcher, Motions inside a 3-segment cluster, launch bookkeeping, read-back, clean-up, the segment file loader's file handling (naming, EOFs, missing files), and the refusals
 (HAVING, sorted aggregation, Sort without LIMIT, RIGHT join, numeric join keys, a scanrelid outside the range table) with the
 error code and message a caller sees.  Run twice: as built, and with libcbexec.so rebuilt under AddressSanitizer + UBSan."""
 import json
@@ -52,6 +52,15 @@ def _check(out):
         assert refused[name]["code"] == code and frag in refused[name]["error"], refused[name]
     for name in ("having", "sorted_agg", "numeric_join_key", "bad_scanrelid"):
         assert refused[name]["launches"] == 0          # refused before anything reached the device
+    # the segment file loader: reference file naming, bytes past the recorded EOF ignored, and what cannot be read says why
+    seg = out["segfile"]
+    rows = seg["rows"]["int4_plain"]
+    assert seg["loads"]["one_column"] == [rows, 0] and seg["loads"]["eof_zero"] == [0, 0]
+    if "as_recorded" in seg["loads"]:
+        assert seg["loads"]["as_recorded"] == [rows, 0]
+    for name, frag in (("eof_beyond_file", "shorter than its recorded EOF"), ("eof_inside_a_block", "runs past the end of the file"),
+                       ("missing_column_file", "16384.514"), ("missing_segno", "16384.9"), ("segno_out_of_range", "bad segment file name")):
+        assert seg["errors"][name]["code"] == INVALID and frag in seg["errors"][name]["msg"], seg["errors"][name]
 
 
 def test_host_executor_over_a_runtime_that_computes_nothing(fake):
