@@ -2022,10 +2022,12 @@ cbgpu_aocs_apply_visimap(cbgpu_ctx *ctx, const void *file_bytes, int64_t nbytes,
 	for (int i = 1; i < nentries; i++)
 		if (ent[i].first == ent[i - 1].first)
 		{
+			const long long twice = ent[i].first;
+
 			free(W.dir);
 			free(ent);
 			free(blob);
-			return cb_fail(ctx, CBGPU_ERR_INVALID, "two visimap entries for first row number %s%lld", "", ent[i].first);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "two visimap entries for first row number %s%lld", "", twice);
 		}
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
 	if (!rel->visimap)

@@ -140,7 +140,10 @@ cb_fail(cbgpu_ctx *ctx, int code, const char *fmt, const char *a = "", long long
 		{ \
 			if (ctx) \
 				snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-			return CBGPU_ERR_CUDA; \
+			(void) cudaGetLastError();	/* not sticky: do not let the next launch check trip over it */ \
+			/* the device is full: a limit of this path (inputs must fit HBM), reported as such so that a caller can leave the \
+			 * sub-tree to the CPU executor (cb_exec.c, cb_cluster_init_plan) instead of treating it as a broken device */ \
+			return e__ == cudaErrorMemoryAllocation ? CBGPU_ERR_NOMEM : CBGPU_ERR_CUDA; \
 		} \
 	} while (0)
 

@@ -90,6 +90,31 @@ def main():
     out["ran"]["q1_after_refusals"] = {"rows": len(ex.run(tpch.q1_plan(1)).rows)}
     ex.close()
 
+    # 3b. device out-of-memory at every allocation of a join query in turn: an error (never a crash), and the next run is clean
+    import ctypes as C
+    fake = C.CDLL(None)
+    fake.fake_cudart_fail_alloc_in.argtypes = [C.c_long]
+    ex = capi.Executor(ctx, dev)
+    oom = {"failed": 0, "passed": 0, "codes": []}
+    clean_in_a_row = 0
+    for n in range(1, 400):
+        fake.fake_cudart_fail_alloc_in(n)
+        try:
+            ex.run(tpch.q5_plan(reg, 1))
+            oom["passed"] += 1
+            clean_in_a_row += 1
+        except capi.CbgpuError as e:
+            oom["failed"] += 1
+            clean_in_a_row = 0
+            if e.code not in oom["codes"]:
+                oom["codes"].append(e.code)
+        fake.fake_cudart_fail_alloc_in(0)
+        assert len(ex.run(tpch.q5_plan(reg, 1)).rows) == 0      # the executor state survives the failure
+        if clean_in_a_row >= 3:                                  # n is past the query's last allocation
+            break
+    ex.close()
+    out["oom"] = oom
+
     # 4. SSB Q4.x: wide group-by plans
     srels = ssb.gen_tables(0.01, capi.hashbpchar)
     if srels is not None:
@@ -135,6 +160,16 @@ def main():
         attempt("missing_segno", base, 9, a[2], cols[:1])
         attempt("segno_out_of_range", base, 128, a[2], cols[:1])
         attempt("eof_zero", base, segno, a[2], [(0, 1, 4, 0, 4, 0, 0)])
+        # visibility map entries are checked on the host before they go to the device: the same range twice, a first row
+        # number that is not a multiple of 32 768
+        empty_entry = b"\x01\0\0\0" + b"\0\0"              # version 1, no compression, zero blocks
+        for name, entries in (("visimap_same_range_twice", [(0, empty_entry), (0, empty_entry)]),
+                              ("visimap_misaligned_first_row", [(5, empty_entry)]),
+                              ("visimap_ok", [(0, empty_entry), (32768, None)])):
+            try:
+                seg["loads"][name] = rel.apply_visimap(a[6], a[2], entries)
+            except capi.CbgpuError as e:
+                seg["errors"][name] = {"code": e.code, "msg": str(e)}
         rel.free()
     seg["rows"] = {"int4_plain": int(len(a[7])), "numeric_price": int(len(b[7]))}
     out["segfile"] = seg

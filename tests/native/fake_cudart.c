@@ -44,6 +44,23 @@ cudaGetDeviceProperties_v2(struct cudaDeviceProp *p, int d)
 
 cudaError_t cudaMemGetInfo(size_t *fr, size_t *tot) { *fr = (size_t) 170 << 30; *tot = (size_t) 180 << 30; return cudaSuccess; }
 
+/* fault injection: the n-th device allocation from now fails (0 = off) - the host's out-of-memory paths */
+static long	fail_alloc_in;
+
+void		fake_cudart_fail_alloc_in(long n) { fail_alloc_in = n; }
+
+static cudaError_t
+zalloc_dev(void **p, size_t n)
+{
+	if (fail_alloc_in > 0 && --fail_alloc_in == 0)
+	{
+		*p = NULL;
+		return cudaErrorMemoryAllocation;
+	}
+	*p = calloc(1, n ? n : 1);
+	return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+
 static cudaError_t
 zalloc(void **p, size_t n)
 {
@@ -51,8 +68,8 @@ zalloc(void **p, size_t n)
 	return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 
-cudaError_t cudaMalloc(void **p, size_t n) { return zalloc(p, n); }
-cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t s) { (void) s; return zalloc(p, n); }
+cudaError_t cudaMalloc(void **p, size_t n) { return zalloc_dev(p, n); }
+cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t s) { (void) s; return zalloc_dev(p, n); }
 cudaError_t cudaMallocHost(void **p, size_t n) { return zalloc(p, n); }
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int f) { (void) f; return zalloc(p, n); }
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }

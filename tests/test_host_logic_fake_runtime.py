@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUDA_INC = "/usr/local/cuda/include"
 pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime_api.h")), reason="needs the CUDA headers")
 
-UNSUPPORTED, INVALID = -3, -2
+UNSUPPORTED, INVALID, NOMEM = -3, -2, -5
 
 
 @pytest.fixture(scope="module")
@@ -59,8 +59,13 @@ def _check(out):
     if "as_recorded" in seg["loads"]:
         assert seg["loads"]["as_recorded"] == [rows, 0]
     for name, frag in (("eof_beyond_file", "shorter than its recorded EOF"), ("eof_inside_a_block", "runs past the end of the file"),
-                       ("missing_column_file", "16384.514"), ("missing_segno", "16384.9"), ("segno_out_of_range", "bad segment file name")):
+                       ("missing_column_file", "16384.514"), ("missing_segno", "16384.9"), ("segno_out_of_range", "bad segment file name"),
+                       ("visimap_same_range_twice", "two visimap entries"), ("visimap_misaligned_first_row", "multiple of 32768")):
         assert seg["errors"][name]["code"] == INVALID and frag in seg["errors"][name]["msg"], seg["errors"][name]
+    assert "visimap_ok" in seg["loads"]
+    # a full device: every allocation of Q5 failing in turn is CBGPU_ERR_NOMEM (the limit "inputs must fit HBM", which a caller may
+    # answer by leaving the sub-tree to the CPU executor), never a crash, and the executor runs the query again afterwards
+    assert out["oom"]["failed"] > 10 and out["oom"]["codes"] == [NOMEM] and out["oom"]["passed"] >= 3
 
 
 def test_host_executor_over_a_runtime_that_computes_nothing(fake):
