@@ -114,3 +114,35 @@ def test_storage_side_host_walk_under_sanitizers(fake, tmp_path):
     out = _run({"LD_PRELOAD": asan + ":" + so, "ASAN_OPTIONS": "detect_leaks=0", "CB_TEST_LIBDIR": libdir, "CB_TEST_AOCS_FUZZ": "40"})
     _check(out)
     assert out["aocs_fuzz"]["calls"] > 1000 and out["aocs_fuzz"]["errors"] > 100
+
+
+def test_bench_main_arm_control_flow(fake):
+    """bench.py's GPU arm from argument parsing to the JSON line, over the no-op runtime at a small scale factor: the numbers
+    mean nothing (no kernel runs), the contract's keys and their bookkeeping do - steps, warm-up, launches counted, the e2e
+    leg's byte counts, the q3 / q5 lines.  (The CPU legs have their own test, tests/test_bench_cpu.py.)"""
+    _, so = fake
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--sf", "0.05", "--steps", "2", "--warmup", "3", "--no-cpu"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, LD_PRELOAD=so), cwd=ROOT)
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert p.returncode == 0 and len(lines) == 1, (p.stdout[-2000:], p.stderr[-3000:])
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "clocks", "gpu_launches", "e2e", "q3", "q5"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["unit"] == "rows/s"
+    assert line["gpu_launches"] > 0 and "impl" not in line and "cpu_baseline" not in line
+    rows = line["config"]["rows_per_gpu"]
+    assert line["roofline"]["algorithmic_bytes_per_launch"] == 38 * rows and line["roofline"]["bound"] == "hbm"
+    assert line["e2e"]["h2d_bytes_per_step"] == 38 * rows and line["e2e"]["unit"] == "rows/s"
+    for q in ("q3", "q5"):
+        assert line[q]["gpu_launches_per_step"] > 0 and line[q]["roofline"]["algorithmic_bytes"] > 0
+
+
+def test_smoke_cannot_pass_without_real_kernels(fake):
+    """__graft_entry__.smoke() compares the device's rows with the oracle's and the reference's expected rows: over a runtime
+    whose kernels do nothing it must fail - it is a check of results, not of plumbing"""
+    _, so = fake
+    p = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, LD_PRELOAD=so), cwd=ROOT)
+    assert p.returncode != 0 and "AssertionError" in p.stderr, (p.stdout[-500:], p.stderr[-1500:])
+    assert "smoke ok" not in p.stdout
