@@ -115,6 +115,31 @@ def main():
     ex.close()
     out["oom"] = oom
 
+    # 3c. the device reports an error in its status word (or hands back a word that makes no sense) at each 4-byte read-back of a
+    #     join query in turn: the caller gets an error or an answer, never a crash, and the next run is clean
+    fake.fake_cudart_poison_int_d2h.argtypes = [C.c_long, C.c_int]
+    ex = capi.Executor(ctx, dev)
+    dev_err = {"raised": 0, "returned": 0, "codes": []}
+    for value in (-4, -6, -5, 0x7fffffff):
+        quiet = 0
+        for n in range(1, 60):
+            fake.fake_cudart_poison_int_d2h(n, value)
+            try:
+                ex.run(tpch.q3_plan(seg, 1))
+                dev_err["returned"] += 1
+                quiet += 1
+            except capi.CbgpuError as e:
+                dev_err["raised"] += 1
+                quiet = 0
+                if e.code not in dev_err["codes"]:
+                    dev_err["codes"].append(e.code)
+            fake.fake_cudart_poison_int_d2h(0, 0)
+            assert len(ex.run(tpch.q3_plan(seg, 1)).rows) == 0
+            if quiet >= 4:
+                break
+    ex.close()
+    out["device_errors"] = dev_err
+
     # 4. SSB Q4.x: wide group-by plans
     srels = ssb.gen_tables(0.01, capi.hashbpchar)
     if srels is not None:

@@ -76,12 +76,20 @@ cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaFreeAsync(void *p, cudaStream_t s) { (void) s; free(p); return cudaSuccess; }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 
+/* fault injection: the n-th 4-byte device-to-host copy from now delivers `value` instead of what the "device" holds - a status
+ * word reporting an error, or a count that makes no sense (0 = off) */
+static long	poison_in;
+static int	poison_value;
+
+void		fake_cudart_poison_int_d2h(long n, int value) { poison_in = n; poison_value = value; }
+
 cudaError_t
 cudaMemcpyAsync(void *dst, const void *src, size_t n, enum cudaMemcpyKind k, cudaStream_t s)
 {
-	(void) k;
 	(void) s;
 	memmove(dst, src, n);
+	if (k == cudaMemcpyDeviceToHost && n == sizeof(int) && poison_in > 0 && --poison_in == 0)
+		memcpy(dst, &poison_value, sizeof(int));
 	return cudaSuccess;
 }
 

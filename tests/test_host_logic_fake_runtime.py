@@ -66,6 +66,10 @@ def _check(out):
     # a full device: every allocation of Q5 failing in turn is CBGPU_ERR_NOMEM (the limit "inputs must fit HBM", which a caller may
     # answer by leaving the sub-tree to the CPU executor), never a crash, and the executor runs the query again afterwards
     assert out["oom"]["failed"] > 10 and out["oom"]["codes"] == [NOMEM] and out["oom"]["passed"] >= 3
+    # an error the device reports in its status word (overflow, corrupt block, table full) reaches the caller with its code; a
+    # word that makes no sense is an error too; the executor runs the query again afterwards
+    de = out["device_errors"]
+    assert de["raised"] >= 4 and {-4, -6, -5} <= set(de["codes"])
 
 
 def test_host_executor_over_a_runtime_that_computes_nothing(fake):
