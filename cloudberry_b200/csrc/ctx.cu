@@ -109,6 +109,12 @@ cb_check_status(cbgpu_ctx *ctx, const char *what)
 				 code == CBGPU_ERR_OVERFLOW ? "value out of range (integer/numeric overflow)" :
 				 code == CBGPU_ERR_NOMEM ? "device table or output buffer full" :
 				 code == CBGPU_ERR_CORRUPT ? "stored block fails its checksum" : "device-side error");
+		if (code > 0 || code < CBGPU_ERR_CORRUPT)
+		{
+			/* kernels only ever store one of the library's codes: anything else means the word itself was damaged */
+			snprintf(ctx->err, sizeof(ctx->err), "%s: device status word holds %d, not an error code of this library", what, code);
+			return CBGPU_ERR_CUDA;
+		}
 		return code;
 	}
 	return CBGPU_OK;

@@ -69,7 +69,7 @@ def _check(out):
     # an error the device reports in its status word (overflow, corrupt block, table full) reaches the caller with its code; a
     # word that makes no sense is an error too; the executor runs the query again afterwards
     de = out["device_errors"]
-    assert de["raised"] >= 4 and {-4, -6, -5} <= set(de["codes"])
+    assert de["raised"] >= 4 and {-4, -6, -5} <= set(de["codes"]) and all(-6 <= c < 0 for c in de["codes"])
 
 
 def test_host_executor_over_a_runtime_that_computes_nothing(fake):
