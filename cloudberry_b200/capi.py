@@ -180,7 +180,7 @@ class CbTupleTableSlot(C.Structure):
 
 class CbInstrumentation(C.Structure):
     _fields_ = [("ntuples", C.c_double), ("nloops", C.c_double), ("kernels", C.c_int64), ("device_ms", C.c_double),
-                ("rows_in", C.c_int64)]
+                ("rows_in", C.c_int64), ("motion_repartitions", C.c_int64)]
 
 
 class CbPlanState(C.Structure):
@@ -297,7 +297,11 @@ def gpu():
             "cbgpu_read_u32": (C.c_int, [vp, vp, i64, vp]),
             "cbgpu_motion_unique_id": (C.c_int, [vp]),
             "cbgpu_motion_create": (C.c_int, [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]),
+            "cbgpu_motion_create_boot": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.POINTER(vp)]),
             "cbgpu_motion_destroy": (None, [vp]),
+            "cbgpu_motion_abort": (None, [vp]),
+            "cbgpu_motion_host_syncs": (i64, [vp]),
+            "cbgpu_motion_collectives": (i64, [vp]),
             "cbgpu_motion_bytes_sent": (i64, [vp]),
             "cbgpu_motion_direct_bytes": (i64, [vp]),
             "cbgpu_motion_direct_available": (C.c_int, [vp]),
@@ -461,8 +465,16 @@ class Context:
             self.h = None
 
 
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
 class Motion:
-    """NCCL interconnect endpoint of one GPU-segment (one process per GPU)."""
+    """Interconnect endpoint of one GPU-segment (one process per GPU): peer-memory windows with device-side
+    signalling, plus NCCL for what the windows cannot take.
+
+    unique_id: the NCCL rendezvous token (rank 0 makes it, everyone gets it).  unique_id=None with
+    allgather=f: windows only, bootstrapped through f(my_bytes) -> [bytes of rank 0, 1, ...] (e.g. over a
+    torch.distributed gloo group): no NCCL communicator, so two ranks may share one GPU."""
 
     @staticmethod
     def unique_id():
@@ -472,13 +484,26 @@ class Motion:
             raise CbgpuError(rc, "ncclGetUniqueId failed")
         return buf.raw
 
-    def __init__(self, ctx, rank, nranks, unique_id):
+    def __init__(self, ctx, rank, nranks, unique_id=None, allgather=None):
         self.ctx = ctx
         self.rank = rank
         self.nranks = nranks
         h = C.c_void_p()
-        buf = C.create_string_buffer(unique_id, 128)
-        ctx.check(ctx.L.cbgpu_motion_create(ctx.h, rank, nranks, buf, C.byref(h)))
+        if unique_id is not None:
+            buf = C.create_string_buffer(unique_id, 128)
+            ctx.check(ctx.L.cbgpu_motion_create(ctx.h, rank, nranks, buf, C.byref(h)))
+        else:
+            def _cb(_arg, mine, allp, nbytes):
+                try:
+                    parts = allgather(C.string_at(mine, nbytes))
+                    if len(parts) != nranks or any(len(x) != nbytes for x in parts):
+                        return 1
+                    C.memmove(allp, b"".join(parts), nbytes * nranks)
+                    return 0
+                except Exception:       # noqa: BLE001 - reported to the C side as a failed all-gather
+                    return 1
+            self._cb = ALLGATHER_FN(_cb)        # must outlive the interconnect (tear-down calls it too)
+            ctx.check(ctx.L.cbgpu_motion_create_boot(ctx.h, rank, nranks, C.cast(self._cb, C.c_void_p), None, C.byref(h)))
         self.h = h
 
     def bytes_sent(self):
@@ -490,9 +515,21 @@ class Motion:
         """True when Redistribute runs fused over peer memory (CUDA IPC windows), False: staged over NCCL"""
         return bool(self.ctx.L.cbgpu_motion_direct_available(self.h))
 
+    def host_syncs(self):
+        return int(self.ctx.L.cbgpu_motion_host_syncs(self.h))
+
+    def collectives(self):
+        return int(self.ctx.L.cbgpu_motion_collectives(self.h))
+
     def close(self):
         if self.h:
             self.ctx.L.cbgpu_motion_destroy(self.h)
+            self.h = None
+
+    def abort(self):
+        """tear down without any collective step (after a failed query)"""
+        if self.h:
+            self.ctx.L.cbgpu_motion_abort(self.h)
             self.h = None
 
 
@@ -673,7 +710,8 @@ def _collect_instrument(ps, out):
     n = ps.contents
     ins = n.instrument
     out[n.plan.contents.plan_node_id] = {"node": n.type, "ntuples": ins.ntuples, "kernels": ins.kernels,
-                                         "device_ms": ins.device_ms, "rows_in": ins.rows_in}
+                                         "device_ms": ins.device_ms, "rows_in": ins.rows_in,
+                                         "motion_repartitions": ins.motion_repartitions}
     _collect_instrument(n.lefttree, out)
     _collect_instrument(n.righttree, out)
 

@@ -108,8 +108,9 @@ cb_check_status(cbgpu_ctx *ctx, const char *what)
 		snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what,
 				 code == CBGPU_ERR_OVERFLOW ? "value out of range (integer/numeric overflow)" :
 				 code == CBGPU_ERR_NOMEM ? "device table or output buffer full" :
-				 code == CBGPU_ERR_CORRUPT ? "stored block fails its checksum" : "device-side error");
-		if (code > 0 || code < CBGPU_ERR_CORRUPT)
+				 code == CBGPU_ERR_CORRUPT ? "stored block fails its checksum" :
+				 code == CBGPU_ERR_PEER ? "a peer segment did not signal within the interconnect's time limit" : "device-side error");
+		if (code > 0 || code < CBGPU_ERR_INTERRUPTED)
 		{
 			/* kernels only ever store one of the library's codes: anything else means the word itself was damaged */
 			snprintf(ctx->err, sizeof(ctx->err), "%s: device status word holds %d, not an error code of this library", what, code);

@@ -205,6 +205,8 @@ typedef struct NodePriv
 	/* Motion (local interconnect): received rows deposited by the cluster */
 	cbgpu_rel  *recv;
 	int			recv_ready;
+	int			xstage;			/* 0: no exchange of this Motion yet; 1: its direct attempt is over (peers now
+								 * expect the staged one); 2: delivered                               */
 	PExpr		send_pe[MAX_OUT];
 	int			send_nout;
 } NodePriv;
@@ -1535,10 +1537,41 @@ open_agg(CbPlanState *ps, CbStream **out)
 }
 
 /* ---- Motion ---- */
+/* one run of the sender slice's pipeline into a staged PARTITION sink: `out` holds destination d's rows from
+ * row base[d] on, cap[d] of them fit.  counts[] = rows ROUTED to each destination, whether they fitted or not. */
 static int
-motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *seg_capacity)
+partition_pass(CbPlanState *ps, CbStream *s, cbgpu_rel *out, void *counter, void *flagword, const int64_t *base, const int64_t *cap,
+			   int nsegs, int64_t *counts)
 {
-	/* execMotionSender (nodeMotion.c:203): run the child, route every row */
+	CbEState   *es = ps->state;
+	CbPipeline *pl = &s->pipe;
+	int64_t		before = cbgpu_kernel_launches(es->es_ctx);
+	int64_t		zeros[65];
+
+	memset(zeros, 0, sizeof(zeros));
+	GPU(es, cbgpu_dev_write(es->es_ctx, counter, sizeof(int64_t) * (size_t) nsegs, zeros));
+	GPU(es, cbgpu_dev_write(es->es_ctx, flagword, sizeof(int64_t), zeros));
+	pl->sink.out = out;
+	pl->sink.seg_base = base;
+	pl->sink.seg_cap = cap;
+	pl->sink.part_flags = (int32_t *) flagword;
+	GPU(es, cbgpu_pipeline_run(es->es_ctx, pl));
+	GPU(es, cbgpu_dev_read(es->es_ctx, counter, sizeof(int64_t) * (size_t) nsegs, counts));	/* the status word rides along */
+	GPU(es, cbgpu_check_status(es->es_ctx));
+	ps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
+	ps->instrument.rows_in += s->rows_in;
+	if (cbgpu_last_kernel_ms(es->es_ctx) > 0)
+		ps->instrument.device_ms += cbgpu_last_kernel_ms(es->es_ctx);
+	return CBGPU_OK;
+}
+
+/* execMotionSender (nodeMotion.c:203): run the child, route every row.  Leaves either the delivered rows in
+ * np(ps)->recv (direct Motion: recv_ready set) or this segment's rows grouped by destination in *send
+ * (destination d: offsets[d], counts[d]).  np(ps)->xstage tells open_motion how far the exchange got, for
+ * the peers' sake, when this fails. */
+static int
+motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *offsets)
+{
 	CbEState   *es = ps->state;
 	CbMotion   *m = (CbMotion *) ps->plan;
 	NodePriv   *p = np(ps);
@@ -1550,7 +1583,7 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 	{
 		TRY(stream_materialize(es, ps, s, &p->owned, send, p->send_pe, &p->send_nout));
 		counts[0] = cbgpu_rel_nrows(*send);
-		*seg_capacity = counts[0];
+		offsets[0] = 0;
 		return CBGPU_OK;
 	}
 	/* hash motion: PARTITION sink = evalHashKey (nodeMotion.c:1088) + per-destination buffers */
@@ -1566,9 +1599,7 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 		VarCtx		vc;
 		void	   *counter;
 		cbgpu_rel  *rel;
-		int			direct = 0;
-		void *const *part_cols = NULL;
-		unsigned long long *const *part_counts = NULL;
+		uint64_t	nullmask = 0;
 
 		if (m->nhashExprs < 1 || m->nhashExprs > CBP_MAX_KEYS)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "hash Motion with %d keys is beyond the GPU path's limit", m->nhashExprs);
@@ -1635,129 +1666,209 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *se
 		}
 		p->send_nout = s->nout;
 		TRY(emit_op(es, s, CBP_END, 0, 0));
-		/* every destination could receive every row: reserve nrows per destination only when small,
-		 * otherwise a skew allowance over the even share (overflow is detected, never silent) */
-		*seg_capacity = pl->nrows;
-		if (pl->nrows > (1 << 20))
-		{
-			*seg_capacity = pl->nrows / nsegs + pl->nrows / (4 * nsegs) + 65536;
-			if (*seg_capacity > pl->nrows)
-				*seg_capacity = pl->nrows;
-		}
-		/* direct Motion (interconnects with peer memory): the PARTITION sink stores every row straight
-		 * into its destination segment's receive buffer - no send buffer, no separate exchange */
-		{
-			CbInterconnect *ic = es->es_cluster ? NULL : es->es_interconnect;
-			int			anynull = 0;
-
-			for (int c = 0; c < ncols; c++)
-				anynull |= nullable[c];
-			if (ic && ic->direct_begin)
-			{
-				int64_t		cap = 0;
-
-				/* every segment calls begin (it is collective); one whose data rules the direct path out
-				 * here - a nullable column exists on this segment only - announces -1 rows and all of
-				 * them take the staged path together */
-				if (ic->direct_begin(ic, es, m->motionID, ncols, types, dscales, anynull ? -1 : pl->nrows, &cap, &part_cols, &part_counts) == CBGPU_OK)
-				{
-					direct = 1;
-					*seg_capacity = cap;
-				}
-			}
-		}
-		GPU(es, cbgpu_rel_create(es->es_ctx, direct ? 0 : *seg_capacity * nsegs, ncols, types, dscales, &rel));
-		p->owned.rels[p->owned.nrels++] = rel;
-		for (int c = 0; c < ncols; c++)
-			if (nullable[c])
-				GPU(es, cbgpu_rel_add_nullmap(rel, c));
-		{
-			int			c = m->nhashExprs;
-
-			for (int i = 0; i < s->nout; i++)
-			{
-				PExpr	   *x = &s->pe[s->out[i]];
-
-				if (x->kind == PE_STATE)
-				{
-					c += 3;
-					continue;
-				}
-				if (x->kind == PE_COL && (x->type == CB_DICT8 || x->type == CB_DICT32) && pl->cols[x->col].dict_hash)
-					GPU(es, cbgpu_rel_share_dict_hash(rel, c, s->col_rel[x->col], s->col_idx[x->col]));
-				c++;
-			}
-		}
-		GPU(es, cbgpu_dev_alloc(es->es_ctx, sizeof(int64_t) * (size_t) nsegs, &counter));
+		GPU(es, cbgpu_dev_alloc(es->es_ctx, sizeof(int64_t) * (size_t) (nsegs + 1), &counter));
 		p->owned.devs[p->owned.ndevs++] = counter;
 		pl->sink.kind = CBP_SINK_PARTITION;
 		pl->sink.nout = ncols;
-		pl->sink.out = rel;
 		pl->sink.out_count = (int64_t *) counter;
 		pl->sink.nhash = m->nhashExprs;
 		pl->sink.nsegs = m->numHashSegments > 0 ? m->numHashSegments : nsegs;
-		pl->sink.seg_capacity = *seg_capacity;
-		pl->sink.part_cols = direct ? part_cols : NULL;
-		pl->sink.part_counts = direct ? part_counts : NULL;
 		pl->force_generic = es->es_force_generic;
 		if (pl->sink.nsegs != nsegs)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "Motion to %d hash segments on a %d-segment cluster", pl->sink.nsegs, nsegs);
+		for (int c = 0; c < ncols; c++)
+			if (nullable[c])
+				nullmask |= 1ull << c;
+
+		/* direct Motion (interconnects with peer memory): the PARTITION sink stores every row straight into
+		 * its destination segment's receive window - no send buffer, no separate exchange, no collective */
 		{
-			int64_t		before = cbgpu_kernel_launches(es->es_ctx);
+			CbInterconnect *ic = es->es_cluster ? NULL : es->es_interconnect;
+			cbgpu_direct_dest dest;
 
-			GPU(es, cbgpu_pipeline_run(es->es_ctx, pl));
-			if (!direct)			/* direct: the counts come back with direct_end's own round trip */
-				GPU(es, cbgpu_dev_read(es->es_ctx, counter, sizeof(int64_t) * (size_t) nsegs, counts));
-			for (int d = 0; d < nsegs && !direct; d++)
-				if (counts[d] > *seg_capacity)
-					return es_fail(es, CBGPU_ERR_NOMEM, "Motion send buffer for segment %d overflowed (%lld rows, capacity %lld): data skew beyond the reserved allowance",
-								   d, (long long) counts[d], (long long) *seg_capacity);
-			if (!direct)
-				GPU(es, cbgpu_check_status(es->es_ctx));
-			ps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
-			ps->instrument.rows_in += s->rows_in;
-			if (cbgpu_last_kernel_ms(es->es_ctx) > 0)
-				ps->instrument.device_ms += cbgpu_last_kernel_ms(es->es_ctx);
-		}
-		for (int d = 0; d < nsegs && !direct; d++)
-			if (counts[d] > *seg_capacity)
-				return es_fail(es, CBGPU_ERR_NOMEM, "Motion send buffer for segment %d overflowed (%lld rows, capacity %lld): data skew beyond the reserved allowance",
-							   d, (long long) counts[d], (long long) *seg_capacity);
-		pl->nops = saved_nops;
-		*send = rel;
-		if (direct)
-		{
-			/* RecvTupleFrom for the whole stream: wait for every sender, take delivery */
-			CbInterconnect *ic = es->es_interconnect;
-			cbgpu_rel  *recv = NULL;
-			int			c = m->nhashExprs;
-
-			if (ic->direct_end(ic, es, m->motionID, (const int64_t *) counter, counts, &recv) != CBGPU_OK)
-				return es->es_errcode ? es->es_errcode : es_fail(es, CBGPU_ERR_CUDA, "%s", cbgpu_last_error(es->es_ctx));
-			GPU(es, cbgpu_check_status(es->es_ctx));	/* fetched with the completion: no extra round trip */
-			p->owned.rels[p->owned.nrels++] = recv;
-			for (int k = 0; k < m->nhashExprs; k++)
+			if (ic && ic->direct_begin && ic->direct_begin(ic, es, m->motionID, ncols, types, dscales, &dest) == CBGPU_OK)
 			{
-				PExpr	   *kx = &s->pe[hashpe[k]];
+				cbgpu_rel  *recv = NULL;
+				int32_t		outcome = CBGPU_DX_DELIVERED;
+				int			rc,
+							rc2;
+				int64_t		before = cbgpu_kernel_launches(es->es_ctx);
 
-				if (kx->kind == PE_COL && (kx->type == CB_DICT8 || kx->type == CB_DICT32) && pl->cols[kx->col].dict_hash)
-					GPU(es, cbgpu_rel_share_dict_hash(recv, k, s->col_rel[kx->col], s->col_idx[kx->col]));
-			}
-			for (int i = 0; i < s->nout; i++)
-			{
-				PExpr	   *x = &s->pe[s->out[i]];
-
-				if (x->kind == PE_STATE)
+				/* from here to direct_end nothing may return early: the peers wait for this segment's signal */
+				rc = cbgpu_rel_create(es->es_ctx, 0, ncols, types, dscales, &rel);
+				if (rc == CBGPU_OK)
 				{
-					c += 3;
-					continue;
+					p->owned.rels[p->owned.nrels++] = rel;
+					pl->sink.out = rel;
+					pl->sink.seg_capacity = dest.capacity;
+					pl->sink.part_cols = dest.cols;
+					pl->sink.part_counts = dest.counts;
+					pl->sink.part_nulls = dest.nulls;
+					pl->sink.part_nullmask = nullmask;
+					pl->sink.part_flags = dest.flags;
+					rc = cbgpu_pipeline_run(es->es_ctx, pl);
 				}
-				if (x->kind == PE_COL && (x->type == CB_DICT8 || x->type == CB_DICT32) && pl->cols[x->col].dict_hash)
-					GPU(es, cbgpu_rel_share_dict_hash(recv, c, s->col_rel[x->col], s->col_idx[x->col]));
-				c++;
+				if (rc)
+					es_fail(es, rc, "%s", cbgpu_last_error(es->es_ctx));
+				rc2 = ic->direct_end(ic, es, m->motionID, rc ? CBGPU_DX_ERROR : 0, nullmask, (const int64_t *) counter, counts, &recv, &outcome);
+				p->xstage = 1;
+				if (recv)
+					p->owned.rels[p->owned.nrels++] = recv;
+				if (rc)
+					return rc;
+				/* an error this segment's own kernels raised (fetched with the completion: no extra round trip) is
+				 * the one to report here; the peers see CBGPU_ERR_PEER */
+				{
+					char		peermsg[512];
+					int			st;
+
+					snprintf(peermsg, sizeof(peermsg), "%s", rc2 ? cbgpu_last_error(es->es_ctx) : "");
+					st = cbgpu_check_status(es->es_ctx);
+					if (st)
+					{
+						es->es_errcode = 0;
+						return es_fail(es, st, "%s", cbgpu_last_error(es->es_ctx));
+					}
+					if (rc2)
+						return es->es_errcode ? es->es_errcode : es_fail(es, rc2, "%s", peermsg);
+				}
+				ps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
+				ps->instrument.rows_in += s->rows_in;
+				if (cbgpu_last_kernel_ms(es->es_ctx) > 0)
+					ps->instrument.device_ms += cbgpu_last_kernel_ms(es->es_ctx);
+				if (outcome == CBGPU_DX_DELIVERED)
+				{
+					/* RecvTupleFrom for the whole stream, done */
+					int			c = m->nhashExprs;
+
+					for (int k = 0; k < m->nhashExprs; k++)
+					{
+						PExpr	   *kx = &s->pe[hashpe[k]];
+
+						if (kx->kind == PE_COL && (kx->type == CB_DICT8 || kx->type == CB_DICT32) && pl->cols[kx->col].dict_hash)
+							GPU(es, cbgpu_rel_share_dict_hash(recv, k, s->col_rel[kx->col], s->col_idx[kx->col]));
+					}
+					for (int i = 0; i < s->nout; i++)
+					{
+						PExpr	   *x = &s->pe[s->out[i]];
+
+						if (x->kind == PE_STATE)
+						{
+							c += 3;
+							continue;
+						}
+						if (x->kind == PE_COL && (x->type == CB_DICT8 || x->type == CB_DICT32) && pl->cols[x->col].dict_hash)
+							GPU(es, cbgpu_rel_share_dict_hash(recv, c, s->col_rel[x->col], s->col_idx[x->col]));
+						c++;
+					}
+					pl->nops = saved_nops;
+					memset(&pl->sink, 0, sizeof(pl->sink));
+					p->recv = recv;
+					p->recv_ready = 1;
+					p->xstage = 2;
+					*send = rel;
+					return CBGPU_OK;
+				}
+				/* CBGPU_DX_RETRY: a destination's window was full somewhere (skew, or a Motion larger than the
+				 * windows): every segment redoes it staged, with exactly sized buffers */
+				pl->sink.part_cols = NULL;
+				pl->sink.part_counts = NULL;
+				pl->sink.part_nulls = NULL;
+				pl->sink.part_nullmask = 0;
 			}
-			p->recv = recv;
-			p->recv_ready = 1;
+		}
+
+		/* staged Motion: partition into a local send buffer, then the interconnect's exchange.  First an
+		 * optimistic layout (every destination could receive every row: reserve nrows per destination only
+		 * when small, otherwise the even share plus a skew allowance); if a destination turns out fuller -
+		 * the reference never fails on skew, it sends tuple by tuple (cdbmotion.c:425) - the counts of that
+		 * pass size a second, exact one */
+		{
+			int64_t		base[64],
+						cap[64];
+			int64_t		each = pl->nrows;
+			int64_t		total = 0;
+			int			over = 0;
+			void	   *flagword = (char *) counter + sizeof(int64_t) * (size_t) nsegs;
+
+			if (pl->nrows > (1 << 20))
+			{
+				each = pl->nrows / nsegs + pl->nrows / (4 * nsegs) + 65536;
+				if (each > pl->nrows)
+					each = pl->nrows;
+			}
+			for (int d = 0; d < nsegs; d++)
+			{
+				base[d] = (int64_t) d * each;
+				cap[d] = each;
+			}
+			GPU(es, cbgpu_rel_create(es->es_ctx, each * nsegs, ncols, types, dscales, &rel));
+			p->owned.rels[p->owned.nrels++] = rel;
+			for (int c = 0; c < ncols; c++)
+				if (nullable[c])
+					GPU(es, cbgpu_rel_add_nullmap(rel, c));
+			TRY(partition_pass(ps, s, rel, counter, flagword, base, cap, nsegs, counts));
+			for (int d = 0; d < nsegs; d++)
+			{
+				over |= counts[d] > cap[d];
+				total += counts[d];
+			}
+			if (over)
+			{
+				int64_t		again[64];
+
+				for (int d = 0; d < nsegs; d++)
+				{
+					base[d] = d == 0 ? 0 : base[d - 1] + counts[d - 1];
+					cap[d] = counts[d];
+				}
+				/* the first buffer goes back before the exact one is taken */
+				for (int i = 0; i < p->owned.nrels; i++)
+					if (p->owned.rels[i] == rel)
+						p->owned.rels[i] = p->owned.rels[--p->owned.nrels];
+				cbgpu_rel_free(rel);
+				GPU(es, cbgpu_rel_create(es->es_ctx, total, ncols, types, dscales, &rel));
+				p->owned.rels[p->owned.nrels++] = rel;
+				for (int c = 0; c < ncols; c++)
+					if (nullable[c])
+						GPU(es, cbgpu_rel_add_nullmap(rel, c));
+				TRY(partition_pass(ps, s, rel, counter, flagword, base, cap, nsegs, again));
+				for (int d = 0; d < nsegs; d++)
+					if (again[d] != counts[d])
+						return es_fail(es, CBGPU_ERR_INVALID, "Motion %d: the sender slice routed %lld rows to segment %d on its second pass, %lld on its first",
+									   m->motionID, (long long) again[d], d, (long long) counts[d]);
+				ps->instrument.motion_repartitions += 1;
+			}
+			for (int d = 0; d < nsegs; d++)
+				offsets[d] = base[d];
+			{
+				int			c = m->nhashExprs;
+
+				for (int i = 0; i < s->nout; i++)
+				{
+					PExpr	   *x = &s->pe[s->out[i]];
+
+					if (x->kind == PE_STATE)
+					{
+						c += 3;
+						continue;
+					}
+					if (x->kind == PE_COL && (x->type == CB_DICT8 || x->type == CB_DICT32) && pl->cols[x->col].dict_hash)
+						GPU(es, cbgpu_rel_share_dict_hash(rel, c, s->col_rel[x->col], s->col_idx[x->col]));
+					c++;
+				}
+				for (int k = 0; k < m->nhashExprs; k++)
+				{
+					PExpr	   *kx = &s->pe[hashpe[k]];
+
+					if (kx->kind == PE_COL && (kx->type == CB_DICT8 || kx->type == CB_DICT32) && pl->cols[kx->col].dict_hash)
+						GPU(es, cbgpu_rel_share_dict_hash(rel, k, s->col_rel[kx->col], s->col_idx[kx->col]));
+				}
+			}
+			pl->nops = saved_nops;
+			pl->sink.seg_base = NULL;	/* they pointed into this frame */
+			pl->sink.seg_cap = NULL;
+			*send = rel;
 		}
 	}
 	return CBGPU_OK;
@@ -1826,22 +1937,33 @@ open_motion(CbPlanState *ps, CbStream **out)
 	if (!es->es_interconnect)
 		return es_fail(es, CBGPU_ERR_INVALID, "Motion node without an interconnect (SetupInterconnect not done)");
 	{
-		cbgpu_rel  *send,
+		cbgpu_rel  *send = NULL,
 				   *recv = NULL;
-		int64_t		counts[64];
-		int64_t		segcap;
+		int64_t		counts[64],
+					offsets[64];
 		CbInterconnect *ic = es->es_interconnect;
 		int			rc;
 
 		if (es->es_numsegments > 64)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "more than 64 segments");
-		TRY(motion_send_side(ps, &send, counts, &segcap));
+		memset(counts, 0, sizeof(counts));
+		memset(offsets, 0, sizeof(offsets));
+		rc = motion_send_side(ps, &send, counts, offsets);
+		if (rc)
+		{
+			/* this segment will not take part in the exchange the others are about to enter (or have entered):
+			 * say so instead of leaving them waiting (they then fail with CBGPU_ERR_PEER) */
+			if (p->xstage < 2 && ic->abandon)
+				ic->abandon(ic, es, m->motionID, p->xstage == 1);
+			p->xstage = 2;
+			return rc;
+		}
 		if (p->recv_ready)		/* direct Motion: the sender slice's kernel already delivered */
 			return motion_recv_stream(ps, p->recv, out);
 		switch (m->motionType)
 		{
 			case CB_MOTIONTYPE_HASH:
-				rc = ic->redistribute(ic, es, m->motionID, send, counts, segcap, &recv);
+				rc = ic->redistribute(ic, es, m->motionID, send, counts, offsets, &recv);
 				break;
 			case CB_MOTIONTYPE_GATHER:
 			case CB_MOTIONTYPE_GATHER_SINGLE:
@@ -1852,8 +1974,11 @@ open_motion(CbPlanState *ps, CbStream **out)
 				rc = ic->broadcast(ic, es, m->motionID, send, counts[0], &recv);
 				break;
 			default:
+				if (ic->abandon)
+					ic->abandon(ic, es, m->motionID, 0);
 				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "motion type %d", m->motionType);
 		}
+		p->xstage = 2;
 		if (rc)
 			return es->es_errcode ? es->es_errcode : es_fail(es, rc, "%s", cbgpu_last_error(es->es_ctx));
 		p->recv = recv;
@@ -2429,6 +2554,7 @@ node_reset(CbPlanState *node)
 	p->inner_rel = NULL;
 	p->recv = NULL;
 	p->recv_ready = 0;
+	p->xstage = 0;
 }
 
 void
@@ -2520,10 +2646,10 @@ cb_slot_text(const CbTupleTableSlot *slot, int attno, char *buf, int buflen)
  * ------------------------------------------------------------------------------------------ */
 static int
 ic_nccl_redistribute(CbInterconnect *ic, CbEState *es, int32_t motion_id, cbgpu_rel *send, const int64_t *counts,
-					 int64_t seg_capacity, cbgpu_rel **recv)
+					 const int64_t *offsets, cbgpu_rel **recv)
 {
 	(void) motion_id;
-	GPU(es, cbgpu_motion_redistribute((cbgpu_motion *) ic->priv, send, counts, seg_capacity, recv));
+	GPU(es, cbgpu_motion_redistribute((cbgpu_motion *) ic->priv, send, counts, offsets, recv));
 	return CBGPU_OK;
 }
 
@@ -2545,22 +2671,34 @@ ic_nccl_broadcast(CbInterconnect *ic, CbEState *es, int32_t motion_id, cbgpu_rel
 
 static int
 ic_nccl_direct_begin(CbInterconnect *ic, CbEState *es, int32_t motion_id, int32_t ncols, const int32_t *types, const int32_t *dscales,
-					 int64_t input_rows, int64_t *capacity, void *const **dest_cols, unsigned long long *const **dest_counts)
+					 cbgpu_direct_dest *dest)
 {
 	(void) motion_id;
 	(void) es;
-	/* not an error for the query: CBGPU_ERR_UNSUPPORTED / CBGPU_ERR_NOMEM here (the same on every
-	 * segment) sends this Motion down the staged path */
-	return cbgpu_motion_direct_begin((cbgpu_motion *) ic->priv, ncols, types, dscales, input_rows, capacity, dest_cols, dest_counts);
+	/* not an error for the query: CBGPU_ERR_UNSUPPORTED here (the same on every segment) sends this Motion
+	 * down the staged path */
+	return cbgpu_motion_direct_begin((cbgpu_motion *) ic->priv, ncols, types, dscales, dest);
 }
 
 static int
-ic_nccl_direct_end(CbInterconnect *ic, CbEState *es, int32_t motion_id, const int64_t *dev_sent_counts, int64_t *sent_counts,
-				   cbgpu_rel **recv)
+ic_nccl_direct_end(CbInterconnect *ic, CbEState *es, int32_t motion_id, int32_t local_flags, uint64_t local_nullmask,
+				   const int64_t *dev_sent_counts, int64_t *sent_counts, cbgpu_rel **recv, int32_t *outcome)
+{
+	int			rc;
+
+	(void) motion_id;
+	rc = cbgpu_motion_direct_end((cbgpu_motion *) ic->priv, local_flags, local_nullmask, dev_sent_counts, sent_counts, recv, outcome);
+	if (rc != CBGPU_OK && es->es_errcode == 0)
+		es_fail(es, rc, "%s", cbgpu_last_error(es->es_ctx));
+	return rc;
+}
+
+static void
+ic_nccl_abandon(CbInterconnect *ic, CbEState *es, int32_t motion_id, int32_t after_direct)
 {
 	(void) motion_id;
-	GPU(es, cbgpu_motion_direct_end((cbgpu_motion *) ic->priv, dev_sent_counts, sent_counts, recv));
-	return CBGPU_OK;
+	(void) es;
+	cbgpu_motion_abandon((cbgpu_motion *) ic->priv, after_direct);
 }
 
 CbInterconnect *
@@ -2573,12 +2711,13 @@ cb_interconnect_nccl_create(cbgpu_motion *motion)
 		ic->direct_begin = ic_nccl_direct_begin;
 		ic->direct_end = ic_nccl_direct_end;
 	}
-	ic->name = "nccl";
+	ic->name = cbgpu_motion_direct_available(motion) ? "peer-memory windows + nccl" : "nccl";
 	ic->nsegs = cbgpu_motion_nranks(motion);
 	ic->segindex = cbgpu_motion_rank(motion);
 	ic->redistribute = ic_nccl_redistribute;
 	ic->gather = ic_nccl_gather;
 	ic->broadcast = ic_nccl_broadcast;
+	ic->abandon = ic_nccl_abandon;
 	ic->priv = motion;
 	return ic;
 }
@@ -2698,7 +2837,7 @@ cluster_run_motion(CbPlanState *me)
 	CbPlanState **mps = calloc((size_t) nsegs, sizeof(CbPlanState *));
 	cbgpu_rel **send = calloc((size_t) nsegs, sizeof(cbgpu_rel *));
 	int64_t    *counts = calloc((size_t) nsegs * (size_t) nsegs, sizeof(int64_t));
-	int64_t    *segcap = calloc((size_t) nsegs, sizeof(int64_t));
+	int64_t    *soff = calloc((size_t) nsegs * (size_t) nsegs, sizeof(int64_t));
 	int			rc = CBGPU_OK;
 
 	/* sender side on every segment (a sender slice under a Gather receiver's own singleton slice
@@ -2713,7 +2852,7 @@ cluster_run_motion(CbPlanState *me)
 		}
 		if (slice_is_singleton(m->plan.lefttree) && s != 0)
 			continue;
-		rc = motion_send_side(mps[s], &send[s], counts + (size_t) s * nsegs, &segcap[s]);
+		rc = motion_send_side(mps[s], &send[s], counts + (size_t) s * nsegs, soff + (size_t) s * nsegs);
 		if (rc && me->state->es_errcode == 0)
 			es_fail(me->state, rc, "segment %d: %s", s, mps[s]->state->es_errmsg);
 	}
@@ -2782,7 +2921,7 @@ cluster_run_motion(CbPlanState *me)
 			{
 				case CB_MOTIONTYPE_HASH:
 					n = counts[(size_t) s * nsegs + d];
-					lo = (int64_t) d * segcap[s];
+					lo = soff[(size_t) s * nsegs + d];
 					break;
 				case CB_MOTIONTYPE_GATHER:
 					n = d == 0 ? counts[(size_t) s * nsegs] : 0;
@@ -2824,7 +2963,7 @@ cluster_run_motion(CbPlanState *me)
 	free(mps);
 	free(send);
 	free(counts);
-	free(segcap);
+	free(soff);
 	return rc;
 }
 

@@ -19,13 +19,53 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* control block at the start of every window: the device-side signalling of the direct exchanges.
+ * Slot [s] of each array is written by rank s only (remote stores over NVLink / peer memory). */
+struct DxCtl
+{
+	unsigned long long counter;	/* rows reserved in this window by the senders of the exchange in flight   */
+	unsigned long long pad[31];
+	unsigned long long done[64];	/* done[s] = epoch << 16 | flags: rank s's rows of that exchange are stored */
+	unsigned long long nmask[64];	/* columns for which rank s stored NULL bytes                              */
+	unsigned long long ready[64];	/* written INTO rank s's window by ... see k_dx_release: ready[r] in MY
+									 * window = last exchange rank r has finished taking delivery of         */
+};
+
+struct DxPeers
+{
+	DxCtl	   *ctl[64];
+};
+
+/* what k_dx_complete leaves in pinned host memory for the one round trip of an exchange */
+struct DxResult
+{
+	unsigned long long got;		/* my window's row counter                                                  */
+	unsigned long long flags;	/* union of every sender's flags (CBGPU_DX_*), DX_TIMEOUT if one never came */
+	unsigned long long nmask;
+	long long	cnt[64];		/* Gather: rows in every sender's slot                                      */
+	long long	sent[64];		/* the sink's own per-destination counts                                    */
+};
+
+#define DX_TIMEOUT 0x8000u
+#define DX_CTL_BYTES 4096
+#define DX_TAB_COLS (64 * CBP_MAX_OUT)
+#define DX_TAB_WORDS (2 * DX_TAB_COLS + 64)
+#define DX_TAB_SLOTS 4
+#define DX_ALIGN 256
+/* the tail of every window: two alternating Gather / Broadcast buffers; each holds [64 row counts] + one
+ * payload slot per sender */
+#define GX_BYTES ((size_t) 32 << 20)
+#define GX_HDR 1024
+
 struct cbgpu_motion
 {
 	cbgpu_ctx  *ctx;
-	ncclComm_t	comm;
+	ncclComm_t	comm;			/* NULL: windows only (cbgpu_motion_create_boot)                      */
+	cbgpu_allgather_fn boot;	/* set-up / tear-down all-gather                                      */
+	void	   *boot_arg;
 	int			rank;
 	int			nranks;
-	long long  *d_counts;		/* [nranks * nranks] scratch for the count exchange                   */
+	long long  *d_counts;		/* [(nranks + 2)^2] scratch for the count exchange                    */
 	int64_t		bytes_sent;		/* payload bytes this rank handed to NCCL (diagnostics / bench)       */
 	int64_t		exchanges;
 	/* peer-memory window: one cudaMalloc'ed arena per rank, mapped into every other rank's process
@@ -35,25 +75,27 @@ struct cbgpu_motion
 	size_t		win_bytes;		/* the smallest window of all ranks                                   */
 	char	   *peer_win[64];	/* peer_win[rank] == win                                              */
 	bool		direct_ok;
-	void	  **d_tab;			/* device table handed to the sink: [64 * CBP_MAX_OUT] column bases, [64] counters */
-	void	  **h_tab;			/* pinned host copy                                                   */
+	void	  **d_tab;			/* DX_TAB_SLOTS device tables handed to the sink: [DX_TAB_COLS] column bases,
+								 * [DX_TAB_COLS] NULL byte bases, [64] counters                       */
+	void	  **h_tab;			/* pinned host copies                                                 */
+	int			tab_slot;
+	int32_t    *d_flags;		/* the sink ORs CBGPU_DX_OVERFLOW in here                             */
+	DxResult   *h_res;			/* pinned; k_dx_complete writes it                                    */
+	DxPeers		peers;
+	unsigned long long epoch;	/* direct exchanges so far (every rank runs the same sequence)        */
+	unsigned long long timeout_ns;
 	/* the direct exchange in flight */
 	int32_t		dx_ncols;
 	int32_t		dx_types[CBP_MAX_OUT];
 	int32_t		dx_dscales[CBP_MAX_OUT];
 	int64_t		dx_cap;
 	size_t		dx_off[CBP_MAX_OUT];
+	size_t		dx_noff[CBP_MAX_OUT];
 	int64_t		direct_bytes;	/* payload bytes stored into peers' windows (diagnostics / bench)      */
 	int64_t		direct_exchanges;
-	int64_t		gather_seq;		/* direct Gathers so far: picks the buffer                            */
+	int64_t		host_syncs;
+	int64_t		collectives;
 };
-
-#define DX_TAB_COLS (64 * CBP_MAX_OUT)
-#define DX_ALIGN 256
-/* the tail of every window: two alternating Gather buffers; each holds [64 row counts] + one payload
- * slot per sender */
-#define GX_BYTES ((size_t) 32 << 20)
-#define GX_HDR 1024
 
 #define CB_NCCL(ctx, call) \
 	do { \
@@ -63,6 +105,12 @@ struct cbgpu_motion
 			snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
 			return CBGPU_ERR_CUDA; \
 		} \
+	} while (0)
+
+#define NEED_NCCL(m, what) \
+	do { \
+		if (!(m)->comm) \
+			return cb_fail((m)->ctx, CBGPU_ERR_UNSUPPORTED, "%s needs the NCCL transport, this interconnect has peer-memory windows only", what, 0); \
 	} while (0)
 
 extern "C" int
@@ -81,23 +129,81 @@ cbgpu_motion_unique_id(void *out128)
 static int	motion_window_setup(cbgpu_motion *m);
 static void motion_window_teardown(cbgpu_motion *m);
 
-extern "C" int
-cbgpu_motion_create(cbgpu_ctx *ctx, int rank, int nranks, const void *unique_id128, cbgpu_motion **out)
+/* the set-up all-gather over the communicator itself */
+static int
+nccl_boot_allgather(void *arg, const void *mine, void *all, size_t bytes)
+{
+	cbgpu_motion *m = (cbgpu_motion *) arg;
+	cbgpu_ctx  *ctx = m->ctx;
+	char	   *d = NULL;
+	const size_t n = (size_t) m->nranks;
+
+	CB_CUDA(ctx, cudaMalloc(&d, bytes * (n + 1)));
+	CB_CUDA(ctx, cudaMemcpyAsync(d + bytes * n, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CB_NCCL(ctx, ncclAllGather(d + bytes * n, d, bytes, ncclInt8, m->comm, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(all, d, bytes * n, cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	cudaFree(d);
+	return 0;
+}
+
+static int
+motion_create_common(cbgpu_ctx *ctx, int rank, int nranks, const void *unique_id128, cbgpu_allgather_fn boot, void *arg,
+					 cbgpu_motion **out)
 {
 	cbgpu_motion *m = (cbgpu_motion *) calloc(1, sizeof(cbgpu_motion));
-	ncclUniqueId id;
+	const char *env = getenv("CBGPU_MOTION_TIMEOUT_MS");
+	int			rc;
 
+	*out = NULL;
 	if (!m)
 		return CBGPU_ERR_NOMEM;
-	memcpy(&id, unique_id128, 128);
+	if (nranks < 1 || rank < 0 || rank >= nranks)
+	{
+		free(m);
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "interconnect rank %s%lld out of range", "", rank);
+	}
 	m->ctx = ctx;
 	m->rank = rank;
 	m->nranks = nranks;
+	m->timeout_ns = (unsigned long long) (env && atoll(env) > 0 ? atoll(env) : 30000) * 1000000ull;
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
-	CB_NCCL(ctx, ncclCommInitRank(&m->comm, nranks, id, rank));
+	if (unique_id128)
+	{
+		ncclUniqueId id;
+
+		memcpy(&id, unique_id128, 128);
+		CB_NCCL(ctx, ncclCommInitRank(&m->comm, nranks, id, rank));
+		m->boot = nccl_boot_allgather;
+		m->boot_arg = m;
+	}
+	else
+	{
+		m->boot = boot;
+		m->boot_arg = arg;
+	}
 	CB_CUDA(ctx, cudaMalloc(&m->d_counts, sizeof(long long) * (size_t) (nranks + 2) * (size_t) (nranks + 2)));
 	*out = m;
-	return motion_window_setup(m);
+	rc = motion_window_setup(m);
+	if (rc == CBGPU_OK && !m->comm && !m->direct_ok)
+		rc = cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "no peer-memory windows between the segments%s (CUDA IPC / P2P unavailable) and no NCCL transport", "", 0);
+	return rc;
+}
+
+extern "C" int
+cbgpu_motion_create(cbgpu_ctx *ctx, int rank, int nranks, const void *unique_id128, cbgpu_motion **out)
+{
+	if (!unique_id128)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_motion_create without a rendezvous token%s", "", 0);
+	return motion_create_common(ctx, rank, nranks, unique_id128, NULL, NULL, out);
+}
+
+extern "C" int
+cbgpu_motion_create_boot(cbgpu_ctx *ctx, int rank, int nranks, cbgpu_allgather_fn allgather, void *arg, cbgpu_motion **out)
+{
+	if (!allgather)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_motion_create_boot without an all-gather callback%s", "", 0);
+	return motion_create_common(ctx, rank, nranks, NULL, allgather, arg, out);
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -111,8 +217,8 @@ struct WinHello
 	char		pad[128 - sizeof(cudaIpcMemHandle_t) - sizeof(unsigned long long) - sizeof(int)];
 };
 
-/* allocate this rank's window, swap IPC handles through the communicator, map every peer's.
- * Any rank failing at any step turns the direct path off on ALL ranks (the decision is all-reduced):
+/* allocate this rank's window, swap IPC handles through the set-up all-gather, map every peer's.
+ * Any rank failing at any step turns the direct path off on ALL ranks (the decision is gathered too):
  * Redistribute then takes the staged NCCL path - both are device paths. */
 static int
 motion_window_setup(cbgpu_motion *m)
@@ -120,18 +226,17 @@ motion_window_setup(cbgpu_motion *m)
 	cbgpu_ctx  *ctx = m->ctx;
 	const int	n = m->nranks;
 	WinHello   *h_all = (WinHello *) calloc((size_t) n, sizeof(WinHello));
-	WinHello   *d_all = NULL;
+	int		   *ok_all = (int *) calloc((size_t) n, sizeof(int));
 	WinHello	mine;
 	size_t		want = (size_t) 16384 << 20;	/* of 180 GB: room for a Motion of ~500 M narrow rows per receiver */
 	const char *env = getenv("CBGPU_MOTION_WINDOW_MB");
 	int			ok = 1;
-	int		   *d_ok = NULL;
-	int			h_ok = 0;
+	int			all_ok = 1;
 
 	m->direct_ok = false;
-	if (!h_all)
+	if (!h_all || !ok_all)
 		return CBGPU_ERR_NOMEM;
-	if (n > 64 || (getenv("CBGPU_MOTION") && strcmp(getenv("CBGPU_MOTION"), "nccl") == 0))
+	if (n > 64 || (m->comm && getenv("CBGPU_MOTION") && strcmp(getenv("CBGPU_MOTION"), "nccl") == 0))
 		ok = 0;
 	if (env && atoll(env) > 0)
 		want = (size_t) atoll(env) << 20;
@@ -148,14 +253,22 @@ motion_window_setup(cbgpu_motion *m)
 			cudaGetLastError();
 			ok = 0;
 		}
+		else
+		{
+			/* control block, and the NULL byte areas of every exchange start out zero (dx_release keeps them so) */
+			CB_CUDA(ctx, cudaMemsetAsync(m->win, 0, want, ctx->stream));
+			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		}
 	}
 	mine.bytes = want;
 	mine.ok = ok;
-	CB_CUDA(ctx, cudaMalloc(&d_all, sizeof(WinHello) * (size_t) (n + 1)));
-	CB_CUDA(ctx, cudaMemcpyAsync(d_all + n, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
-	CB_NCCL(ctx, ncclAllGather(d_all + n, d_all, sizeof(WinHello), ncclInt8, m->comm, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(h_all, d_all, sizeof(WinHello) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
-	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (m->boot(m->boot_arg, &mine, h_all, sizeof(WinHello)) != 0)
+	{
+		free(h_all);
+		free(ok_all);
+		return m->comm ? CBGPU_ERR_CUDA : cb_fail(ctx, CBGPU_ERR_PEER, "interconnect set-up: the caller's all-gather failed%s", "", 0);
+	}
+	m->collectives++;
 	m->win_bytes = want;
 	for (int p = 0; p < n; p++)
 	{
@@ -178,19 +291,25 @@ motion_window_setup(cbgpu_motion *m)
 			ok = 0;
 		}
 	}
-	/* everyone or no one */
-	CB_CUDA(ctx, cudaMalloc(&d_ok, sizeof(int)));
-	CB_CUDA(ctx, cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-	CB_NCCL(ctx, ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, m->comm, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(&h_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	cudaFree(d_ok);
-	cudaFree(d_all);
+	/* everyone or no one; this second all-gather is also the barrier "every window is zeroed and mapped" */
+	if (m->boot(m->boot_arg, &ok, ok_all, sizeof(int)) != 0)
+		all_ok = 0;
+	m->collectives++;
+	for (int p = 0; p < n; p++)
+		if (!ok_all[p])
+			all_ok = 0;
 	free(h_all);
-	if (h_ok)
+	free(ok_all);
+	if (all_ok)
 	{
-		CB_CUDA(ctx, cudaMalloc(&m->d_tab, sizeof(void *) * (DX_TAB_COLS + 64)));
-		CB_CUDA(ctx, cudaMallocHost(&m->h_tab, sizeof(void *) * (DX_TAB_COLS + 64)));
+		CB_CUDA(ctx, cudaMalloc(&m->d_tab, sizeof(void *) * DX_TAB_WORDS * DX_TAB_SLOTS));
+		CB_CUDA(ctx, cudaMallocHost(&m->h_tab, sizeof(void *) * DX_TAB_WORDS * DX_TAB_SLOTS));
+		CB_CUDA(ctx, cudaMalloc(&m->d_flags, sizeof(int32_t)));
+		CB_CUDA(ctx, cudaMemsetAsync(m->d_flags, 0, sizeof(int32_t), ctx->stream));
+		CB_CUDA(ctx, cudaMallocHost(&m->h_res, sizeof(DxResult)));
+		memset(m->h_res, 0, sizeof(DxResult));
+		for (int p = 0; p < n; p++)
+			m->peers.ctl[p] = (DxCtl *) m->peer_win[p];
 		m->direct_ok = m->win_bytes >= 4 * GX_BYTES;
 	}
 	if (!m->direct_ok)
@@ -214,7 +333,13 @@ motion_window_teardown(cbgpu_motion *m)
 		cudaFree(m->d_tab);
 	if (m->h_tab)
 		cudaFreeHost(m->h_tab);
+	if (m->d_flags)
+		cudaFree(m->d_flags);
+	if (m->h_res)
+		cudaFreeHost(m->h_res);
 	m->d_tab = m->h_tab = NULL;
+	m->d_flags = NULL;
+	m->h_res = NULL;
 	m->direct_ok = false;
 }
 
@@ -225,21 +350,43 @@ cbgpu_motion_destroy(cbgpu_motion *m)
 		return;
 	cudaSetDevice(m->ctx->device);
 	cudaStreamSynchronize(m->ctx->stream);
+	if (m->direct_ok)
 	{
-		/* nobody unmaps a window a peer may still be storing into */
-		int		   *d = NULL;
+		/* nobody unmaps a window a peer may still be storing into, nobody frees one a peer has mapped:
+		 * (everyone has drained its stream) -> unmap the peers -> (everyone has unmapped) -> free */
+		int			one = 1;
+		int		   *all = (int *) calloc((size_t) m->nranks, sizeof(int));
 
-		if (m->direct_ok && cudaMalloc(&d, sizeof(int)) == cudaSuccess)
-		{
-			cudaMemsetAsync(d, 0, sizeof(int), m->ctx->stream);
-			ncclAllReduce(d, d, 1, ncclInt32, ncclMin, m->comm, m->ctx->stream);
-			cudaStreamSynchronize(m->ctx->stream);
-			cudaFree(d);
-		}
-		motion_window_teardown(m);
+		if (all)
+			m->boot(m->boot_arg, &one, all, sizeof(int));
+		for (int p = 0; p < m->nranks && p < 64; p++)
+			if (p != m->rank && m->peer_win[p])
+			{
+				cudaIpcCloseMemHandle(m->peer_win[p]);
+				m->peer_win[p] = NULL;
+			}
+		if (all)
+			m->boot(m->boot_arg, &one, all, sizeof(int));
+		free(all);
 	}
-	ncclCommDestroy(m->comm);
+	motion_window_teardown(m);
+	if (m->comm)
+		ncclCommDestroy(m->comm);
 	cudaFree(m->d_counts);
+	free(m);
+}
+
+extern "C" void
+cbgpu_motion_abort(cbgpu_motion *m)
+{
+	if (!m)
+		return;
+	cudaSetDevice(m->ctx->device);
+	if (m->comm)
+		ncclCommAbort(m->comm);		/* outstanding collectives return; nothing is waited for */
+	motion_window_teardown(m);
+	cudaFree(m->d_counts);
+	cudaGetLastError();
 	free(m);
 }
 
@@ -261,40 +408,63 @@ cbgpu_motion_bytes_sent(const cbgpu_motion *m)
 	return m->bytes_sent;
 }
 
+extern "C" int64_t
+cbgpu_motion_host_syncs(const cbgpu_motion *m)
+{
+	return m->host_syncs;
+}
+
+extern "C" int64_t
+cbgpu_motion_collectives(const cbgpu_motion *m)
+{
+	return m->collectives;
+}
+
 /* every rank learns every rank's per-destination row counts: matrix[s * nranks + d].  The same
  * all-gather carries which columns of `send` have a NULL map on each rank: a map may exist on one
  * segment only (it follows the data), but sender and receiver must post the same transfers, so every
- * rank gives `send` (zeroed) maps for the union before the rows move. */
+ * rank gives `send` (zeroed) maps for the union before the rows move.  It also carries "this rank
+ * failed before the exchange" (mine[0] < 0): then nobody posts a transfer and all return CBGPU_ERR_PEER
+ * - a failed segment must not leave the others waiting inside a collective. */
 static int
 exchange_counts(cbgpu_motion *m, cbgpu_rel *send, const int64_t *mine, int64_t *matrix)
 {
 	cbgpu_ctx  *ctx = m->ctx;
 	const int	n = m->nranks;
 	long long  *d_all = m->d_counts;
-	long long  *d_mine = m->d_counts + (size_t) (n + 1) * n;
-	long long	h_mine[65], h_all[65 * 64];
+	long long  *d_mine = m->d_counts + (size_t) (n + 2) * n;
+	long long	h_mine[66], h_all[66 * 64];
 	unsigned long long mask = 0,
 				all = 0;
+	const bool	failed = mine[0] < 0;
+	int			peer_failed = -1;
 
-	for (int c = 0; c < send->ncols && c < 64; c++)
+	for (int c = 0; send && c < send->ncols && c < 64; c++)
 		if (send->nulls[c])
 			mask |= 1ull << c;
 	for (int d = 0; d < n; d++)
-		h_mine[d] = mine[d];
+		h_mine[d] = failed ? 0 : mine[d];
 	h_mine[n] = (long long) mask;
-	CB_CUDA(ctx, cudaMemcpyAsync(d_mine, h_mine, sizeof(long long) * (size_t) (n + 1), cudaMemcpyHostToDevice, ctx->stream));
-	CB_NCCL(ctx, ncclAllGather(d_mine, d_all, (size_t) (n + 1), ncclInt64, m->comm, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(h_all, d_all, sizeof(long long) * (size_t) (n + 1) * n, cudaMemcpyDeviceToHost, ctx->stream));
+	h_mine[n + 1] = failed ? 1 : 0;
+	CB_CUDA(ctx, cudaMemcpyAsync(d_mine, h_mine, sizeof(long long) * (size_t) (n + 2), cudaMemcpyHostToDevice, ctx->stream));
+	CB_NCCL(ctx, ncclAllGather(d_mine, d_all, (size_t) (n + 2), ncclInt64, m->comm, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(h_all, d_all, sizeof(long long) * (size_t) (n + 2) * n, cudaMemcpyDeviceToHost, ctx->stream));
 	if (ctx->trace_on)
 		cb_trace_mark(ctx, "nccl:counts");
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	m->host_syncs++;
+	m->collectives++;
 	for (int s = 0; s < n; s++)
 	{
 		for (int d = 0; d < n; d++)
-			matrix[(size_t) s * n + d] = h_all[(size_t) s * (n + 1) + d];
-		all |= (unsigned long long) h_all[(size_t) s * (n + 1) + n];
+			matrix[(size_t) s * n + d] = h_all[(size_t) s * (n + 2) + d];
+		all |= (unsigned long long) h_all[(size_t) s * (n + 2) + n];
+		if (h_all[(size_t) s * (n + 2) + n + 1])
+			peer_failed = s;
 	}
-	for (int c = 0; c < send->ncols && c < 64; c++)
+	if (peer_failed >= 0)
+		return cb_fail(ctx, CBGPU_ERR_PEER, "Motion abandoned: segment %s%lld failed before the exchange", "", peer_failed);
+	for (int c = 0; send && c < send->ncols && c < 64; c++)
 		if (((all >> c) & 1) && !send->nulls[c])
 		{
 			int			rc = cbgpu_rel_add_nullmap(send, c);
@@ -386,22 +556,27 @@ exchange_rows(cbgpu_motion *m, cbgpu_rel *send, cbgpu_rel *recv, const int64_t *
 }
 
 extern "C" int
-cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *counts, int64_t seg_capacity, cbgpu_rel **recv)
+cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *counts, const int64_t *offsets, cbgpu_rel **recv)
 {
 	int			n = m->nranks;
-	int64_t    *matrix = (int64_t *) calloc((size_t) n * n, sizeof(int64_t));
+	int64_t    *matrix;
 	int64_t		send_off[64], send_cnt[64], recv_off[64], recv_cnt[64];
 	int64_t		total = 0;
 	int			rc;
 
+	*recv = NULL;
+	NEED_NCCL(m, "a staged Redistribute Motion");
 	if (n > 64)
 		return cb_fail(m->ctx, CBGPU_ERR_UNSUPPORTED, "more than 64 segments%s", "", 0);
+	matrix = (int64_t *) calloc((size_t) n * n, sizeof(int64_t));
+	if (!matrix)
+		return CBGPU_ERR_NOMEM;
 	rc = exchange_counts(m, send, counts, matrix);
 	if (rc == CBGPU_OK)
 	{
 		for (int s = 0; s < n; s++)
 		{
-			send_off[s] = (int64_t) s * seg_capacity;
+			send_off[s] = offsets[s];
 			send_cnt[s] = counts[s];
 			recv_off[s] = total;
 			recv_cnt[s] = matrix[(size_t) s * n + m->rank];
@@ -415,22 +590,156 @@ cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *count
 	return rc;
 }
 
-
 /* ---------------------------------------------------------------------------------------------
- * direct Redistribute: partition + exchange as ONE kernel over peer memory.
+ * direct exchanges over the peer-memory windows, framed by device-side signals.
  *
- *   begin   (collective) every rank announces how many rows enter its sender slice; all derive the
- *           same per-receiver capacity and the same layout of the exchange inside every window
- *           ([row counter][column 0][column 1]...); each rank zeroes ITS counter BEFORE the
- *           announcement all-gather, so no peer can store before the counter is clean; the caller
- *           gets device tables of every destination's column bases and counter
- *   kernel  the sender slice's pipeline runs with its PARTITION sink in direct mode: destination =
- *           cdbhashreduce(keys); a CTA reserves a slice of the DESTINATION's buffer with one
- *           system-scope atomic per destination and run, and stores the rows there over NVLink
- *   end     (collective) one 4-byte all-reduce = "every sender's kernel has finished"; the receiver
- *           reads its counter and moves the rows out of the window into a relation of its own, so
- *           the window is free again when the next Motion's announcement completes
+ * Every rank runs the same sequence of exchanges (the plan is the same on every segment), numbered by
+ * `epoch`.  Exchange e on rank r:
+ *
+ *   wait-ready   k_dx_wait_ready: spin (ld.acquire.sys on r's OWN window) until ready[p] >= e - 1 for every
+ *                p: every receiver has taken delivery of exchange e - 1 and cleared its row counter
+ *   store        the sender slice's pipeline kernel (PARTITION sink, direct mode): destination =
+ *                cdbhashreduce(keys); a CTA reserves a slice of the DESTINATION's buffer with one
+ *                system-scope atomic per destination and run, and stores the rows there over NVLink
+ *   complete     k_dx_complete: fence, then done[r] = e << 16 | flags into EVERY window (st.release.sys);
+ *                then spin until done[s] of exchange e has arrived from every sender s; the row counter,
+ *                the union of the flags and the NULL-column masks land in pinned host memory
+ *   (host)       ONE stream synchronisation: the receiver learns its row count and sizes the relation
+ *   take         copy the rows out of the window, re-zero the NULL byte areas that were used
+ *   release      k_dx_release: counter = 0, then ready[r] = e into every window
+ *
+ * No collective call, no host round trip except the one the executor needs anyway (a relation's row
+ * count lives on the host).  A rank that fails locally still runs `complete` with CBGPU_DX_ERROR so nobody
+ * waits for it; a rank that disappears is noticed by the spin loops' time limit (CBGPU_MOTION_TIMEOUT_MS,
+ * default 30 s) -> CBGPU_ERR_PEER.  Overflow of a destination (skew beyond what the window holds) is
+ * flagged by the sink, seen by every rank in `complete`, and answered by redoing the Motion staged with
+ * exactly sized buffers: never by failing the query (the reference sends tuple by tuple and cannot
+ * overflow, cdbmotion.c:425).
  * --------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ unsigned long long
+dx_ld_acquire(const unsigned long long *p)
+{
+	unsigned long long v;
+
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void
+dx_st_relaxed(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long
+dx_now_ns(void)
+{
+	unsigned long long t;
+
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+
+/* spin until *p >= need (compared on the epoch part when shift > 0); false on time-out */
+__device__ __forceinline__ bool
+dx_spin(const unsigned long long *p, unsigned long long need, int shift, unsigned long long timeout_ns, unsigned long long *seen)
+{
+	const unsigned long long t0 = dx_now_ns();
+	unsigned	spins = 0;
+
+	for (;;)
+	{
+		const unsigned long long v = dx_ld_acquire(p);
+
+		if ((v >> shift) >= need)
+		{
+			*seen = v;
+			return true;
+		}
+		if (++spins > 64)
+		{
+			__nanosleep(spins > 4096 ? 2000 : 100);
+			if ((spins & 255) == 0 && dx_now_ns() - t0 > timeout_ns)
+			{
+				*seen = v;
+				return false;
+			}
+		}
+	}
+}
+
+__global__ void
+k_dx_wait_ready(const DxCtl *me, int n, unsigned long long need, unsigned long long timeout_ns, int *status)
+{
+	unsigned long long v;
+
+	if ((int) threadIdx.x < n && !dx_spin(&me->ready[threadIdx.x], need, 0, timeout_ns, &v))
+		atomicExch(status, CBGPU_ERR_PEER);
+}
+
+__global__ void
+k_dx_complete(DxPeers peers, int me, int n, unsigned long long epoch, unsigned flags_host, const int32_t *dflags,
+			  const int *status, unsigned long long nmask, const long long *ghdr, const int64_t *dev_sent, DxResult *res,
+			  unsigned long long timeout_ns)
+{
+	__shared__ unsigned s_flags;
+	__shared__ unsigned long long s_nmask;
+	const int	p = threadIdx.x;
+
+	if (p == 0)
+	{
+		s_flags = 0;
+		s_nmask = 0;
+	}
+	__syncthreads();
+	if (p < n)
+	{
+		/* an error one of my kernels raised (overflow, ...) fails the exchange for everybody: my rows are not to be used */
+		const unsigned f = flags_host | (dflags ? (unsigned) *dflags : 0u) | (*status != 0 ? (unsigned) CBGPU_DX_ERROR : 0u);
+		unsigned long long v = 0;
+
+		/* my rows (stored by the kernels before me on this stream) before my signal, everywhere */
+		__threadfence_system();
+		dx_st_relaxed(&peers.ctl[p]->nmask[me], nmask);
+		__threadfence_system();
+		dx_st_relaxed(&peers.ctl[p]->done[me], (epoch << 16) | (f & 0xffffu));
+		/* sender p's signal for this exchange */
+		if (!dx_spin(&peers.ctl[me]->done[p], epoch, 16, timeout_ns, &v))
+			atomicOr(&s_flags, DX_TIMEOUT);
+		else
+		{
+			atomicOr(&s_flags, (unsigned) (v & 0xffffu));
+			atomicOr(&s_nmask, dx_ld_acquire(&peers.ctl[me]->nmask[p]));
+		}
+	}
+	__syncthreads();
+	if (p < 64)
+	{
+		res->cnt[p] = (ghdr && p < n) ? ((const volatile long long *) ghdr)[p] : 0;
+		res->sent[p] = (dev_sent && p < n) ? dev_sent[p] : 0;
+	}
+	if (p == 0)
+	{
+		res->got = dx_ld_acquire(&peers.ctl[me]->counter);
+		res->flags = s_flags;
+		res->nmask = s_nmask;
+	}
+	__threadfence_system();
+}
+
+__global__ void
+k_dx_release(DxPeers peers, int me, int n, unsigned long long epoch)
+{
+	if (threadIdx.x == 0)
+		peers.ctl[me]->counter = 0;
+	__syncthreads();
+	if ((int) threadIdx.x < n)
+	{
+		__threadfence_system();
+		dx_st_relaxed(&peers.ctl[threadIdx.x]->ready[me], epoch);
+	}
+}
+
 struct CopyCols
 {
 	void	   *dst[CBP_MAX_OUT];
@@ -462,44 +771,81 @@ cbgpu_motion_direct_bytes(const cbgpu_motion *m)
 	return m->direct_bytes;
 }
 
+/* start exchange number ++epoch: the device waits until every peer has released the previous one */
+static int
+dx_open(cbgpu_motion *m)
+{
+	cbgpu_ctx  *ctx = m->ctx;
+
+	m->epoch++;
+	k_dx_wait_ready<<<1, 64, 0, ctx->stream>>>((const DxCtl *) m->win, m->nranks, m->epoch - 1, m->timeout_ns, ctx->d_status);
+	CB_LAUNCHED(ctx, "k_dx_wait_ready");
+	return CBGPU_OK;
+}
+
+/* signal + wait + the exchange's one host round trip */
+static int
+dx_complete(cbgpu_motion *m, unsigned flags, unsigned long long nmask, const int32_t *dflags, const long long *ghdr,
+			const int64_t *dev_sent, const char *mark)
+{
+	cbgpu_ctx  *ctx = m->ctx;
+
+	k_dx_complete<<<1, 64, 0, ctx->stream>>>(m->peers, m->rank, m->nranks, m->epoch, flags, dflags, ctx->d_status, nmask, ghdr, dev_sent,
+											 m->h_res, m->timeout_ns);
+	CB_LAUNCHED(ctx, "k_dx_complete");
+	CB_CUDA(ctx, CB_STATUS_RIDE(ctx));
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, mark);
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	CB_STATUS_FETCHED(ctx);
+	m->host_syncs++;
+	return CBGPU_OK;
+}
+
+static int
+dx_release(cbgpu_motion *m)
+{
+	cbgpu_ctx  *ctx = m->ctx;
+
+	k_dx_release<<<1, 64, 0, ctx->stream>>>(m->peers, m->rank, m->nranks, m->epoch);
+	CB_LAUNCHED(ctx, "k_dx_release");
+	return CBGPU_OK;
+}
+
+static int
+dx_peer_failure(cbgpu_motion *m, unsigned long long flags, const char *what)
+{
+	if (flags & DX_TIMEOUT)
+		return cb_fail(m->ctx, CBGPU_ERR_PEER, "%s: a segment did not signal within the interconnect's time limit", what, 0);
+	return cb_fail(m->ctx, CBGPU_ERR_PEER, "%s abandoned: another segment failed", what, 0);
+}
+
 extern "C" int
-cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, const int32_t *dscales, int64_t input_rows,
-						  int64_t *capacity, void *const **dest_cols, unsigned long long *const **dest_counts)
+cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, const int32_t *dscales, cbgpu_direct_dest *dest)
 {
 	cbgpu_ctx  *ctx = m->ctx;
 	const int	n = m->nranks;
-	long long  *d_mine = m->d_counts + (size_t) n * n;
-	long long	h_rows[64];
-	int64_t		cap = 0,
-				total = 0;
-	size_t		off = DX_ALIGN;
+	size_t		off = DX_CTL_BYTES;
+	size_t		roww = 0;
+	size_t		avail;
+	int64_t		cap;
+	void	  **h, **d;
 
+	memset(dest, 0, sizeof(*dest));
 	if (!m->direct_ok)
 		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "direct Redistribute is not available%s (no peer-memory window)", "", 0);
 	if (ncols < 1 || ncols > CBP_MAX_OUT)
 		return cb_fail(ctx, CBGPU_ERR_INVALID, "direct Redistribute of %s%lld columns", "", ncols);
-	/* my counter is clean before anyone can learn that the exchange has started */
-	CB_CUDA(ctx, cudaMemsetAsync(m->win, 0, DX_ALIGN, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(d_mine, &input_rows, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-	CB_NCCL(ctx, ncclAllGather(d_mine, m->d_counts, 1, ncclInt64, m->comm, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(h_rows, m->d_counts, sizeof(long long) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
-	if (ctx->trace_on)
-		cb_trace_mark(ctx, "p2p:announce");
-	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	/* a rank that cannot take part (input_rows < 0: e.g. a nullable column there) vetoes for everyone */
-	for (int s = 0; s < n; s++)
-		if (h_rows[s] < 0)
-			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "direct Redistribute vetoed by segment %s%lld", "", s);
-	/* the same arithmetic on every rank: even share + 25 % skew allowance + slack per sender */
-	for (int s = 0; s < n; s++)
-	{
-		total += h_rows[s];
-		cap += h_rows[s] / n + h_rows[s] / (4 * n) + 65536;
-	}
-	if (cap > total)
-		cap = total;
-	if (cap < 1)
-		cap = 1;
+	if (m->dx_ncols)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_motion_direct_begin inside an open exchange%s", "", 0);
+	/* the same arithmetic on every rank: the whole window (less the control block and the Gather buffers)
+	 * divided by the row width, one NULL byte per column and row included */
+	for (int c = 0; c < ncols; c++)
+		roww += (size_t) cb_type_w(types[c]) + 1;
+	avail = m->win_bytes - DX_CTL_BYTES - 2 * GX_BYTES - (size_t) (2 * ncols) * DX_ALIGN;
+	cap = (int64_t) (avail / roww) & ~(int64_t) 255;
+	if (cap < 4096)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "direct Redistribute: a row of %s%lld bytes does not fit the window (raise CBGPU_MOTION_WINDOW_MB)", "", (long long) roww);
 	for (int c = 0; c < ncols; c++)
 	{
 		m->dx_types[c] = types[c];
@@ -507,219 +853,305 @@ cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, 
 		m->dx_off[c] = off;
 		off += (((size_t) cap * (size_t) cb_type_w(types[c])) + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
 	}
-	if (off + 2 * GX_BYTES > m->win_bytes)
-		return cb_fail(ctx, CBGPU_ERR_NOMEM, "direct Redistribute needs %s%lld bytes of window (raise CBGPU_MOTION_WINDOW_MB)", "", (long long) off);
+	for (int c = 0; c < ncols; c++)
+	{
+		m->dx_noff[c] = off;
+		off += ((size_t) cap + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
+	}
 	m->dx_ncols = ncols;
 	m->dx_cap = cap;
-	for (int d = 0; d < n; d++)
+	m->tab_slot = (m->tab_slot + 1) % DX_TAB_SLOTS;
+	h = m->h_tab + (size_t) m->tab_slot * DX_TAB_WORDS;
+	d = m->d_tab + (size_t) m->tab_slot * DX_TAB_WORDS;
+	for (int p = 0; p < n; p++)
 	{
 		for (int c = 0; c < ncols; c++)
-			m->h_tab[(size_t) d * ncols + c] = m->peer_win[d] + m->dx_off[c];
-		m->h_tab[DX_TAB_COLS + d] = m->peer_win[d];
+		{
+			h[(size_t) p * ncols + c] = m->peer_win[p] + m->dx_off[c];
+			h[DX_TAB_COLS + (size_t) p * ncols + c] = m->peer_win[p] + m->dx_noff[c];
+		}
+		h[2 * DX_TAB_COLS + p] = m->peer_win[p];	/* DxCtl.counter */
 	}
-	CB_CUDA(ctx, cudaMemcpyAsync(m->d_tab, m->h_tab, sizeof(void *) * (DX_TAB_COLS + 64), cudaMemcpyHostToDevice, ctx->stream));
-	*capacity = cap;
-	*dest_cols = (void *const *) m->d_tab;
-	*dest_counts = (unsigned long long *const *) (m->d_tab + DX_TAB_COLS);
+	CB_CUDA(ctx, cudaMemcpyAsync(d, h, sizeof(void *) * DX_TAB_WORDS, cudaMemcpyHostToDevice, ctx->stream));
+	CB_CUDA(ctx, cudaMemsetAsync(m->d_flags, 0, sizeof(int32_t), ctx->stream));
+	dx_open(m);
+	if (ctx->trace_on)
+		cb_trace_mark(ctx, "p2p:open");
+	dest->capacity = cap;
+	dest->cols = (void *const *) d;
+	dest->nulls = (uint8_t *const *) (d + DX_TAB_COLS);
+	dest->counts = (unsigned long long *const *) (d + 2 * DX_TAB_COLS);
+	dest->flags = m->d_flags;
 	return CBGPU_OK;
 }
 
 extern "C" int
-cbgpu_motion_direct_end(cbgpu_motion *m, const int64_t *dev_sent_counts, int64_t *sent_counts, cbgpu_rel **recv)
+cbgpu_motion_direct_end(cbgpu_motion *m, int32_t local_flags, uint64_t local_nullmask, const int64_t *dev_sent_counts,
+						int64_t *sent_counts, cbgpu_rel **recv, int32_t *outcome)
 {
-	int64_t		rows_sent_elsewhere = 0;
-
 	cbgpu_ctx  *ctx = m->ctx;
-	int		   *d_flag = (int *) (m->d_counts + (size_t) m->nranks * m->nranks);
-	unsigned long long got = 0;
+	DxResult	res;
+	int64_t		got,
+				used;
+	int64_t		rows_sent_elsewhere = 0;
+	const int	ncols = m->dx_ncols;
 	int			rc;
 
 	*recv = NULL;
-	if (!m->direct_ok || m->dx_ncols < 1)
+	*outcome = CBGPU_DX_DELIVERED;
+	if (!m->direct_ok || ncols < 1)
 		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_motion_direct_end without a begin%s", "", 0);
-	/* stream order puts this after my kernel; its completion anywhere means every kernel is done */
-	CB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
-	CB_NCCL(ctx, ncclAllReduce(d_flag, d_flag, 1, ncclInt32, ncclMax, m->comm, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(&got, m->win, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream));
-	/* the sender slice's own per-destination counts (a statistic) and the status word ride in the same round trip */
-	if (dev_sent_counts && sent_counts)
-		CB_CUDA(ctx, cudaMemcpyAsync(sent_counts, dev_sent_counts, sizeof(int64_t) * (size_t) m->nranks, cudaMemcpyDeviceToHost, ctx->stream));
-	CB_CUDA(ctx, CB_STATUS_RIDE(ctx));
-	if (ctx->trace_on)
-		cb_trace_mark(ctx, "p2p:complete");
-	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	CB_STATUS_FETCHED(ctx);
-	for (int d = 0; d < m->nranks && dev_sent_counts && sent_counts; d++)
-		if (d != m->rank)
-			rows_sent_elsewhere += sent_counts[d];
-	if ((int64_t) got > m->dx_cap)
-		return cb_fail(ctx, CBGPU_ERR_NOMEM, "Motion receive buffer overflowed (%s%lld rows): data skew beyond the reserved allowance", "", (long long) got);
-	rc = cbgpu_rel_create(ctx, (int64_t) got, m->dx_ncols, m->dx_types, m->dx_dscales, recv);
+	m->dx_ncols = 0;
+	rc = dx_complete(m, (unsigned) local_flags, local_nullmask, m->d_flags, NULL, dev_sent_counts, "p2p:complete");
 	if (rc)
 		return rc;
-	if (got > 0 && got <= 65536)
+	res = *m->h_res;
+	got = (int64_t) res.got;
+	used = got < m->dx_cap ? got : m->dx_cap;
+	for (int d = 0; d < m->nranks; d++)
 	{
-		/* a few rows (partial aggregate states, top-N candidates): one launch for all columns */
-		CopyCols	cc;
-
-		for (int c = 0; c < m->dx_ncols; c++)
-		{
-			cc.dst[c] = (*recv)->data[c];
-			cc.src[c] = m->win + m->dx_off[c];
-			cc.bytes[c] = (size_t) got * (size_t) cb_type_w(m->dx_types[c]);
-		}
-		k_copy_cols<<<m->dx_ncols, 256, 0, ctx->stream>>>(cc);
-		CB_LAUNCHED(ctx, "k_copy_cols");
+		if (sent_counts)
+			sent_counts[d] = res.sent[d];
+		if (d != m->rank)
+			rows_sent_elsewhere += res.sent[d];
 	}
-	else
-		for (int c = 0; c < m->dx_ncols && got > 0; c++)
-			CB_CUDA(ctx, cudaMemcpyAsync((*recv)->data[c], m->win + m->dx_off[c], (size_t) got * (size_t) cb_type_w(m->dx_types[c]),
-										 cudaMemcpyDeviceToDevice, ctx->stream));
-	if (ctx->trace_on)
-		cb_trace_mark(ctx, "p2p:copy-out");
+	/* NULL bytes a sender stored must be gone before the next exchange (senders without NULLs store none) */
+	if (!(res.flags & (DX_TIMEOUT | CBGPU_DX_ERROR | CBGPU_DX_OVERFLOW | CBGPU_DX_VETO)))
+	{
+		rc = cbgpu_rel_create(ctx, got, ncols, m->dx_types, m->dx_dscales, recv);
+		if (rc)
+			return rc;
+		for (int c = 0; c < ncols; c++)
+			if ((res.nmask >> c) & 1)
+			{
+				rc = cbgpu_rel_add_nullmap(*recv, c);
+				if (rc)
+					return rc;
+				if (got > 0)
+					CB_CUDA(ctx, cudaMemcpyAsync((*recv)->nulls[c], m->win + m->dx_noff[c], (size_t) got, cudaMemcpyDeviceToDevice, ctx->stream));
+			}
+		if (got > 0 && got <= 65536)
+		{
+			/* a few rows (partial aggregate states, top-N candidates): one launch for all columns */
+			CopyCols	cc;
+
+			for (int c = 0; c < ncols; c++)
+			{
+				cc.dst[c] = (*recv)->data[c];
+				cc.src[c] = m->win + m->dx_off[c];
+				cc.bytes[c] = (size_t) got * (size_t) cb_type_w(m->dx_types[c]);
+			}
+			k_copy_cols<<<ncols, 256, 0, ctx->stream>>>(cc);
+			CB_LAUNCHED(ctx, "k_copy_cols");
+		}
+		else
+			for (int c = 0; c < ncols && got > 0; c++)
+				CB_CUDA(ctx, cudaMemcpyAsync((*recv)->data[c], m->win + m->dx_off[c], (size_t) got * (size_t) cb_type_w(m->dx_types[c]),
+											 cudaMemcpyDeviceToDevice, ctx->stream));
+		if (ctx->trace_on)
+			cb_trace_mark(ctx, "p2p:copy-out");
+	}
+	for (int c = 0; c < ncols && used > 0; c++)
+		if ((res.nmask >> c) & 1)
+			CB_CUDA(ctx, cudaMemsetAsync(m->win + m->dx_noff[c], 0, (size_t) used, ctx->stream));
+	dx_release(m);
+	if (res.flags & (DX_TIMEOUT | CBGPU_DX_ERROR))
+		return dx_peer_failure(m, res.flags, "direct Redistribute");
+	if (res.flags & (CBGPU_DX_OVERFLOW | CBGPU_DX_VETO))
+	{
+		*outcome = CBGPU_DX_RETRY;
+		return CBGPU_OK;
+	}
 	{
 		int64_t		roww = 0;
 
-		for (int c = 0; c < m->dx_ncols; c++)
+		for (int c = 0; c < ncols; c++)
 			roww += cb_type_w(m->dx_types[c]);
 		m->direct_bytes += rows_sent_elsewhere * roww;
 	}
 	m->direct_exchanges++;
-	m->dx_ncols = 0;
 	return CBGPU_OK;
 }
 
-/* direct Gather (a handful of rows per sender: final aggregates, top-N candidates): every sender
- * stores its row count and its rows into ITS slot of the root's Gather buffer, one 4-byte all-reduce
- * says "all stored" (and carries "somebody's rows did not fit": then everyone takes the NCCL path),
- * the root assembles.  Two buffers alternate, so the all-reduce of Gather k + 1 is also the proof that
- * the root has emptied the buffer Gather k + 2 will overwrite. */
+extern "C" int
+cbgpu_motion_abandon(cbgpu_motion *m, int staged)
+{
+	if (m->dx_ncols)
+	{
+		/* inside an open direct exchange: close it with the error flag */
+		cbgpu_rel  *recv = NULL;
+		int32_t		outcome;
+
+		cbgpu_motion_direct_end(m, CBGPU_DX_ERROR, 0, NULL, NULL, &recv, &outcome);
+		if (recv)
+			cbgpu_rel_free(recv);
+		return CBGPU_OK;
+	}
+	if (!staged && m->direct_ok)
+	{
+		dx_open(m);
+		dx_complete(m, CBGPU_DX_ERROR, 0, NULL, NULL, NULL, "p2p:abandon");
+		dx_release(m);
+		return CBGPU_OK;
+	}
+	if (m->comm)
+	{
+		int64_t		mine[64];
+		int64_t    *matrix = (int64_t *) calloc((size_t) m->nranks * m->nranks, sizeof(int64_t));
+
+		memset(mine, 0, sizeof(mine));
+		mine[0] = -1;
+		if (matrix)
+			exchange_counts(m, NULL, mine, matrix);
+		free(matrix);
+	}
+	return CBGPU_OK;
+}
+
+/* direct Gather / Broadcast (a handful of rows per sender: final aggregates, top-N candidates): every
+ * sender stores its row count and its rows into ITS slot of the Gather buffer of the root (Broadcast: of
+ * every rank), `complete` says "all stored" and carries "somebody's rows did not fit" (CBGPU_DX_NOFIT:
+ * then nothing is consumed and everyone takes the NCCL path), the receiver assembles.  Two buffers
+ * alternate by epoch parity; `release` of exchange e is the proof that a buffer of exchange e - 1 is empty. */
 struct GatherPut
 {
-	long long  *hdr;			/* root's count slot for this sender                                  */
+	long long  *hdr[64];		/* the receivers' count slot for this sender                          */
+	char	   *base[64];		/* ... and payload slot                                               */
+	int			ndest;
 	long long	nrows;
-	CopyCols	cc;
+	const void *src[CBP_MAX_OUT];
+	size_t		off[CBP_MAX_OUT];
+	size_t		bytes[CBP_MAX_OUT];
 	int			ncols;
 };
 
 __global__ void
 k_gather_put(GatherPut g)
 {
+	const int	d = blockIdx.y;
+
 	if (blockIdx.x == 0 && threadIdx.x == 0)
-		*g.hdr = g.nrows;
+		*g.hdr[d] = g.nrows;
 	if ((int) blockIdx.x < g.ncols)
 	{
-		const size_t n = g.cc.bytes[blockIdx.x];
-		unsigned char *d = (unsigned char *) g.cc.dst[blockIdx.x];
-		const unsigned char *s = (const unsigned char *) g.cc.src[blockIdx.x];
+		const size_t n = g.bytes[blockIdx.x];
+		unsigned char *dst = (unsigned char *) g.base[d] + g.off[blockIdx.x];
+		const unsigned char *s = (const unsigned char *) g.src[blockIdx.x];
 
 		for (size_t i = threadIdx.x; i < n; i += blockDim.x)
-			d[i] = s[i];
+			dst[i] = s[i];
 	}
 }
 
-/* returns 1 when done directly, 0 when the caller must take the staged path, < 0 on error */
+/* root >= 0: Gather to that rank; root < 0: Broadcast.  Returns 1 when done directly, 0 when the caller must
+ * take the staged path (decided identically on every rank), < 0 on error */
 static int
 gather_direct(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv)
 {
 	cbgpu_ctx  *ctx = m->ctx;
 	const int	n = m->nranks;
 	const size_t slot = ((GX_BYTES - GX_HDR) / (size_t) n) / DX_ALIGN * DX_ALIGN;
-	const size_t buf = m->win_bytes - 2 * GX_BYTES + (size_t) (m->gather_seq & 1) * GX_BYTES;
-	int		   *d_flag = (int *) (m->d_counts + (size_t) n * n);
-	size_t		off[CBP_MAX_OUT];
+	size_t		buf;
 	size_t		need = 0;
 	int			fits = 1;
-	int			h_flag = 0;
-	long long	h_cnt[64];
+	const bool	receiver = root < 0 || m->rank == root;
+	GatherPut	g;
+	DxResult	res;
 
 	if (!m->direct_ok || n > 64 || send->ncols > CBP_MAX_OUT)
 		return 0;
+	memset(&g, 0, sizeof(g));
 	for (int c = 0; c < send->ncols; c++)
 	{
 		if (send->nulls[c])
-			fits = 0;			/* a null map may exist on one rank only: the decision rides on the all-reduce */
-		off[c] = need;
+			fits = 0;			/* a null map may exist on one rank only: the decision rides on the signal */
+		g.off[c] = need;
 		need += ((size_t) nrows * (size_t) cb_type_w(send->types[c]) + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
 	}
 	if (need > slot)
 		fits = 0;
-	m->gather_seq++;
+	dx_open(m);
+	buf = m->win_bytes - 2 * GX_BYTES + (size_t) (m->epoch & 1) * GX_BYTES;
 	if (fits)
 	{
-		GatherPut	g;
-		char	   *base = m->peer_win[root] + buf;
-
-		memset(&g, 0, sizeof(g));
-		g.hdr = (long long *) base + m->rank;
+		for (int p = 0; p < n; p++)
+			if (root < 0 || p == root)
+			{
+				g.hdr[g.ndest] = (long long *) (m->peer_win[p] + buf) + m->rank;
+				g.base[g.ndest] = m->peer_win[p] + buf + GX_HDR + (size_t) m->rank * slot;
+				g.ndest++;
+			}
 		g.nrows = nrows;
 		g.ncols = send->ncols;
 		for (int c = 0; c < send->ncols; c++)
 		{
-			g.cc.dst[c] = base + GX_HDR + (size_t) m->rank * slot + off[c];
-			g.cc.src[c] = send->data[c];
-			g.cc.bytes[c] = (size_t) nrows * (size_t) cb_type_w(send->types[c]);
+			g.src[c] = send->data[c];
+			g.bytes[c] = (size_t) nrows * (size_t) cb_type_w(send->types[c]);
 		}
-		k_gather_put<<<send->ncols > 0 ? send->ncols : 1, 256, 0, ctx->stream>>>(g);
+		k_gather_put<<<dim3(send->ncols > 0 ? send->ncols : 1, g.ndest), 256, 0, ctx->stream>>>(g);
 		CB_LAUNCHED(ctx, "k_gather_put");
 	}
-	h_flag = fits ? 0 : 1;
-	CB_CUDA(ctx, cudaMemcpyAsync(d_flag, &h_flag, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-	CB_NCCL(ctx, ncclAllReduce(d_flag, d_flag, 1, ncclInt32, ncclMax, m->comm, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-	if (m->rank == root)
-		CB_CUDA(ctx, cudaMemcpyAsync(h_cnt, m->win + buf, sizeof(long long) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
-	if (ctx->trace_on)
-		cb_trace_mark(ctx, "p2p:gather");
-	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	if (h_flag)
+	if (dx_complete(m, fits ? 0u : CBGPU_DX_NOFIT, 0, NULL, receiver ? (const long long *) (m->win + buf) : NULL, NULL, "p2p:gather") != CBGPU_OK)
+		return -CBGPU_ERR_CUDA;
+	res = *m->h_res;
+	if (res.flags & (DX_TIMEOUT | CBGPU_DX_ERROR))
+	{
+		dx_release(m);
+		return -dx_peer_failure(m, res.flags, root < 0 ? "Broadcast Motion" : "Gather Motion");
+	}
+	if (res.flags & CBGPU_DX_NOFIT)
+	{
+		dx_release(m);
 		return 0;				/* somebody's rows were too many for a slot: nothing was consumed, go staged */
+	}
 	{
 		int64_t		total = 0;
 		int			rc;
 
-		if (m->rank == root)
+		if (receiver)
 			for (int s = 0; s < n; s++)
-				total += h_cnt[s];
+				total += res.cnt[s];
 		rc = make_recv(m, send, total, recv);
 		if (rc)
+		{
+			dx_release(m);
 			return -rc;
-		if (m->rank == root && total > 0)
+		}
+		if (receiver && total > 0)
 		{
 			int64_t		at = 0;
 
 			for (int s = 0; s < n; s++)
 			{
 				CopyCols	cc;
+				size_t		o = 0;
 
-				if (h_cnt[s] == 0)
+				if (res.cnt[s] == 0)
 					continue;
 				for (int c = 0; c < send->ncols; c++)
 				{
 					const size_t w = (size_t) cb_type_w(send->types[c]);
-					/* every sender laid its columns out with ITS row count */
-					size_t		o = 0;
 
-					for (int cc2 = 0; cc2 < c; cc2++)
-						o += ((size_t) h_cnt[s] * (size_t) cb_type_w(send->types[cc2]) + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
+					/* every sender laid its columns out with ITS row count */
 					cc.dst[c] = (char *) (*recv)->data[c] + (size_t) at * w;
 					cc.src[c] = m->win + buf + GX_HDR + (size_t) s * slot + o;
-					cc.bytes[c] = (size_t) h_cnt[s] * w;
+					cc.bytes[c] = (size_t) res.cnt[s] * w;
+					o += ((size_t) res.cnt[s] * w + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
 				}
 				k_copy_cols<<<send->ncols, 256, 0, ctx->stream>>>(cc);
 				CB_LAUNCHED(ctx, "k_copy_cols");
-				at += h_cnt[s];
+				at += res.cnt[s];
 			}
 		}
-		if (m->rank != root)
 		{
 			int64_t		roww = 0;
 
 			for (int c = 0; c < send->ncols; c++)
 				roww += cb_type_w(send->types[c]);
-			m->direct_bytes += nrows * roww;
+			m->direct_bytes += nrows * roww * (root < 0 ? n - 1 : (m->rank != root ? 1 : 0));
 		}
 	}
+	dx_release(m);
 	m->direct_exchanges++;
 	return 1;
 }
@@ -728,19 +1160,21 @@ extern "C" int
 cbgpu_motion_gather(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv)
 {
 	int			n = m->nranks;
-	int64_t    *matrix = (int64_t *) calloc((size_t) n * n, sizeof(int64_t));
-	int64_t		mine[64], send_off[64], send_cnt[64], recv_off[64], recv_cnt[64];
+	int64_t    *matrix;
+	int64_t		mine[64] = {0}, send_off[64], send_cnt[64], recv_off[64], recv_cnt[64];
 	int64_t		total = 0;
 	int			rc;
 
-	if (n > 64)
-		return cb_fail(m->ctx, CBGPU_ERR_UNSUPPORTED, "more than 64 segments%s", "", 0);
+	*recv = NULL;
+	if (n > 64 || root < 0 || root >= n)
+		return cb_fail(m->ctx, CBGPU_ERR_UNSUPPORTED, "Gather Motion to segment %s%lld", "", root);
 	rc = gather_direct(m, root, send, nrows, recv);
 	if (rc != 0)
-	{
-		free(matrix);
 		return rc > 0 ? CBGPU_OK : -rc;
-	}
+	NEED_NCCL(m, "a Gather Motion too large for the window's Gather slots");
+	matrix = (int64_t *) calloc((size_t) n * n, sizeof(int64_t));
+	if (!matrix)
+		return CBGPU_ERR_NOMEM;
 	for (int d = 0; d < n; d++)
 		mine[d] = d == root ? nrows : 0;
 	rc = exchange_counts(m, send, mine, matrix);
@@ -766,13 +1200,21 @@ extern "C" int
 cbgpu_motion_broadcast(cbgpu_motion *m, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv)
 {
 	int			n = m->nranks;
-	int64_t    *matrix = (int64_t *) calloc((size_t) n * n, sizeof(int64_t));
-	int64_t		mine[64], send_off[64], send_cnt[64], recv_off[64], recv_cnt[64];
+	int64_t    *matrix;
+	int64_t		mine[64] = {0}, send_off[64], send_cnt[64], recv_off[64], recv_cnt[64];
 	int64_t		total = 0;
 	int			rc;
 
+	*recv = NULL;
 	if (n > 64)
 		return cb_fail(m->ctx, CBGPU_ERR_UNSUPPORTED, "more than 64 segments%s", "", 0);
+	rc = gather_direct(m, -1, send, nrows, recv);
+	if (rc != 0)
+		return rc > 0 ? CBGPU_OK : -rc;
+	NEED_NCCL(m, "a Broadcast Motion too large for the window's Gather slots");
+	matrix = (int64_t *) calloc((size_t) n * n, sizeof(int64_t));
+	if (!matrix)
+		return CBGPU_ERR_NOMEM;
 	for (int d = 0; d < n; d++)
 		mine[d] = nrows;
 	rc = exchange_counts(m, send, mine, matrix);

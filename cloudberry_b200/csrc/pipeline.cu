@@ -176,18 +176,25 @@ cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
 			ds->out_capacity = s->out->capacity;
 			if (s->kind == CBP_SINK_PARTITION)
 			{
-				if (s->nsegs < 1 || s->nhash < 1 || s->nhash > CBP_MAX_KEYS || s->nhash > s->nout ||
-					(!s->part_cols && s->seg_capacity * s->nsegs > s->out->capacity) || (s->part_cols && !s->part_counts))
+				if (s->nsegs < 1 || s->nsegs > 64 || s->nhash < 1 || s->nhash > CBP_MAX_KEYS || s->nhash > s->nout ||
+					(!s->part_cols && !s->seg_base && s->seg_capacity * s->nsegs > s->out->capacity) || (s->part_cols && !s->part_counts) ||
+					(s->part_cols && s->part_nullmask && !s->part_nulls) || (!s->seg_base != !s->seg_cap))
 					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: bad partition description%s", "", 0);
 				ds->part_cols = s->part_cols;
 				ds->part_counts = s->part_counts;
-				if (s->part_cols)
-					for (int c = 0; c < s->nout; c++)
-						if (s->out->nulls[c])
-							return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "direct Motion of a nullable column%s", "", 0);
+				ds->part_nulls = s->part_nulls;
+				ds->part_nullmask = s->part_cols ? s->part_nullmask : 0;
+				ds->part_flags = s->part_flags;
 				ds->nhash = s->nhash;
 				ds->nsegs = s->nsegs;
 				ds->seg_capacity = s->seg_capacity;
+				for (int g = 0; g < s->nsegs; g++)
+				{
+					ds->seg_base[g] = s->seg_base ? s->seg_base[g] : (int64_t) g * s->seg_capacity;
+					ds->seg_cap[g] = s->part_cols ? s->seg_capacity : s->seg_cap ? s->seg_cap[g] : s->seg_capacity;
+					if (!s->part_cols && (ds->seg_base[g] < 0 || ds->seg_cap[g] < 0 || ds->seg_base[g] + ds->seg_cap[g] > s->out->capacity))
+						return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline sink: destination %s%lld's range lies outside the send buffer", "", g);
+				}
 				for (int k = 0; k < s->nhash; k++)
 				{
 					ds->hashtype[k] = s->hashtype[k];
@@ -844,22 +851,30 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 						pos = atomicAdd_system(S.part_counts[seg], (unsigned long long) __popc(peers));
 				}
 				pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1));
-				int64_t		cap = S.kind == CBP_SINK_PARTITION ? S.seg_capacity : S.out_capacity;
+				int64_t		cap = S.kind == CBP_SINK_PARTITION ? S.seg_cap[seg] : S.out_capacity;
 
 				if ((int64_t) pos >= cap)
-					atomicExch(P.status, CBGPU_ERR_NOMEM);
+				{
+					/* a full Motion destination is not an error: the host redoes the pass with exact sizes */
+					if (S.kind == CBP_SINK_PARTITION && S.part_flags)
+						atomicOr(S.part_flags, CBGPU_DX_OVERFLOW);
+					else
+						atomicExch(P.status, CBGPU_ERR_NOMEM);
+				}
 				else if (direct)
 				{
 					for (int c = 0; c < S.nout; c++)
 					{
 						sink_store(S.part_cols[seg * S.nout + c], S.outtype[c], pos, st[c]);
-						if ((snull >> c) & 1)
+						if ((S.part_nullmask >> c) & 1)
+							S.part_nulls[seg * S.nout + c][pos] = (snull >> c) & 1;
+						else if ((snull >> c) & 1)
 							atomicExch(P.status, CBGPU_ERR_INVALID);
 					}
 				}
 				else
 				{
-					uint64_t	dst = (uint64_t) seg * (uint64_t) S.seg_capacity + pos;
+					uint64_t	dst = (uint64_t) (S.kind == CBP_SINK_PARTITION ? S.seg_base[seg] : 0) + pos;
 
 					for (int c = 0; c < S.nout; c++)
 					{

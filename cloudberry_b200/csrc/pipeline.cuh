@@ -43,6 +43,11 @@ struct DSink
 	int64_t		seg_capacity;
 	void *const *part_cols;		/* direct Motion: destination d's column c at part_cols[d * nout + c]  */
 	unsigned long long *const *part_counts;	/* ... and its row counter (peer memory)               */
+	uint8_t *const *part_nulls;	/* ... and its NULL bytes                                             */
+	unsigned long long part_nullmask;
+	int32_t    *part_flags;		/* a full destination ORs CBGPU_DX_OVERFLOW in here (NULL: status word) */
+	int64_t		seg_base[64];	/* staged: first row of destination d's range in the output columns    */
+	int64_t		seg_cap[64];	/* ... and how many rows fit                                           */
 };
 
 struct PipeDev

@@ -125,6 +125,9 @@ struct PcParams
 	int64_t		seg_capacity;
 	void *const *part_cols;		/* direct Motion: destination d's column c at part_cols[d * nout + c]  */
 	unsigned long long *const *part_counts;
+	int32_t    *part_flags;		/* a full destination ORs CBGPU_DX_OVERFLOW in here (NULL: status word) */
+	int64_t		seg_base[64];
+	int64_t		seg_cap[64];
 	int		   *status;
 };
 
@@ -454,8 +457,14 @@ pc_stage_sink(const PcParams &P, PcQ Q, unsigned base, unsigned n, unsigned long
 			if (P.part_cols)
 				b = atomicAdd_system(P.part_counts[threadIdx.x], (unsigned long long) part->count[threadIdx.x]);
 			part->base[threadIdx.x] = b;
-			if ((int64_t) (b + part->count[threadIdx.x]) > P.seg_capacity)
-				atomicExch(P.status, CBGPU_ERR_NOMEM);
+			if ((int64_t) (b + part->count[threadIdx.x]) > P.seg_cap[threadIdx.x])
+			{
+				/* a full Motion destination is not an error: the host redoes the pass with exact sizes */
+				if (P.part_flags)
+					atomicOr(P.part_flags, CBGPU_DX_OVERFLOW);
+				else
+					atomicExch(P.status, CBGPU_ERR_NOMEM);
+			}
 		}
 		__syncthreads();
 		for (unsigned i = threadIdx.x; i < n; i += PC_THREADS)
@@ -463,9 +472,9 @@ pc_stage_sink(const PcParams &P, PcQ Q, unsigned base, unsigned n, unsigned long
 			const int	seg = part->seg[i];
 			const unsigned long long pos = part->base[seg] + part->rank[i];
 
-			if ((int64_t) pos < P.seg_capacity)
+			if ((int64_t) pos < P.seg_cap[seg])
 			{
-				const uint64_t dst = P.part_cols ? pos : (uint64_t) seg * (uint64_t) P.seg_capacity + pos;
+				const uint64_t dst = P.part_cols ? pos : (uint64_t) P.seg_base[seg] + pos;
 
 				for (int c = 0; c < P.nout; c++)
 					sink_store(P.part_cols ? P.part_cols[seg * P.nout + c] : P.outcol[c], P.outtype[c], dst, pc_load(P.out[c], Q, base + i));
@@ -1076,6 +1085,12 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 			P.seg_capacity = d->sink.seg_capacity;
 			P.part_cols = d->sink.part_cols;
 			P.part_counts = d->sink.part_counts;
+			P.part_flags = d->sink.part_flags;
+			for (int g = 0; g < P.nsegs && g < 64; g++)
+			{
+				P.seg_base[g] = d->sink.seg_base[g];
+				P.seg_cap[g] = d->sink.seg_cap[g];
+			}
 			for (int k = 0; k < P.nhash; k++)
 			{
 				P.hashtype[k] = d->sink.hashtype[k];

@@ -70,6 +70,8 @@ typedef struct CbInstrumentation
 	int64_t		kernels;		/* device kernels launched on behalf of this node                    */
 	double		device_ms;		/* CUDA-event time of this node's pipelines                          */
 	int64_t		rows_in;		/* rows of the driving relation(s) this node's pipelines scanned     */
+	int64_t		motion_repartitions;	/* Motion sender: passes redone with exact sizes after a destination
+								 * outgrew its share (data skew)                                     */
 } CbInstrumentation;
 
 typedef struct CbPlanState
@@ -143,10 +145,10 @@ typedef struct CbInterconnect
 	const char *name;
 	int32_t		nsegs;
 	int32_t		segindex;
-	/* Redistribute: `send` holds this segment's rows grouped by destination (destination d's rows
-	 * start at d * seg_capacity, counts[d] of them).  Returns the rows addressed to this segment. */
+	/* Redistribute (staged): `send` holds this segment's rows grouped by destination (destination d's rows
+	 * start at row offsets[d], counts[d] of them).  Returns the rows addressed to this segment. */
 	int			(*redistribute) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id,
-								 cbgpu_rel *send, const int64_t *counts, int64_t seg_capacity, cbgpu_rel **recv);
+								 cbgpu_rel *send, const int64_t *counts, const int64_t *offsets, cbgpu_rel **recv);
 	/* Gather: every segment's rows to segment `root`; other segments get an empty relation */
 	int			(*gather) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id, int32_t root,
 						   cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
@@ -156,15 +158,21 @@ typedef struct CbInterconnect
 	void		(*teardown) (struct CbInterconnect *ic);
 	void	   *priv;
 	/* optional (NULL when the interconnect has no peer memory): Redistribute fused into the sender
-	 * slice's kernel.  begin is collective and returns the PARTITION sink's destination tables
-	 * (CbpSink.part_cols / part_counts) and the per-receiver capacity; a non-zero return means "use
-	 * redistribute() for this Motion" and must be the same on every segment.  end is collective and
-	 * returns the rows delivered to this segment. */
+	 * slice's kernel (cbgpu_motion_direct_begin / _end, include/cbgpu.h).  begin is local and returns the
+	 * PARTITION sink's destination tables; a non-zero return means "use redistribute() for this Motion" and
+	 * is the same on every segment.  end signals, waits for every sender, takes delivery; *outcome ==
+	 * CBGPU_DX_RETRY: nothing was delivered (a destination overflowed somewhere), every segment redoes the
+	 * Motion through redistribute(). */
 	int			(*direct_begin) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id, int32_t ncols,
-								 const int32_t *types, const int32_t *dscales, int64_t input_rows, int64_t *capacity,
-								 void *const **dest_cols, unsigned long long *const **dest_counts);
-	int			(*direct_end) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id,
-							   const int64_t *dev_sent_counts, int64_t *sent_counts, cbgpu_rel **recv);
+								 const int32_t *types, const int32_t *dscales, cbgpu_direct_dest *dest);
+	int			(*direct_end) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id, int32_t local_flags,
+							   uint64_t local_nullmask, const int64_t *dev_sent_counts, int64_t *sent_counts, cbgpu_rel **recv,
+							   int32_t *outcome);
+	/* this segment failed before (after_direct = 0) or after (1: the direct attempt ended in CBGPU_DX_RETRY)
+	 * the Motion's first exchange and will not take part: tell the peers, which then fail with
+	 * CBGPU_ERR_PEER instead of waiting (the reference's senders notice a dead peer through the
+	 * interconnect's own error path, ic_udpifc.c; TeardownInterconnect hasErrors, ml_ipc.h:106).  Optional. */
+	void		(*abandon) (struct CbInterconnect *ic, struct CbEState *estate, int32_t motion_id, int32_t after_direct);
 } CbInterconnect;
 
 /* interconnect over NCCL (cbgpu_motion_*): one process per GPU-segment.  SetupInterconnect

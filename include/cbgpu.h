@@ -52,6 +52,9 @@ extern "C" {
 #define CBGPU_ERR_OVERFLOW (-4)		/* integer / numeric value out of range during execution           */
 #define CBGPU_ERR_NOMEM (-5)
 #define CBGPU_ERR_CORRUPT (-6)		/* stored data fails its checksum (AOCS block CRC-32C)              */
+#define CBGPU_ERR_PEER (-7)			/* another segment failed, or did not signal within the interconnect's
+									 * time limit (CBGPU_MOTION_TIMEOUT_MS)                             */
+#define CBGPU_ERR_INTERRUPTED (-8)	/* the caller's interrupt callback asked for the query to stop      */
 
 typedef struct cbgpu_ctx cbgpu_ctx;
 typedef struct cbgpu_rel cbgpu_rel;
@@ -230,6 +233,16 @@ typedef struct CbpSink
 	 * part_counts[d]; seg_capacity = rows every destination can take */
 	void *const *part_cols;
 	unsigned long long *const *part_counts;
+	uint8_t *const *part_nulls;	/* direct mode: NULL byte bases, [d * nout + c]                       */
+	uint64_t	part_nullmask;	/* direct mode: bit c = store column c's NULL bytes                   */
+	/* where a full destination is reported (CBGPU_DX_OVERFLOW is ORed in; the rows beyond the capacity are
+	 * dropped, the per-destination counters still count them, the caller redoes the pass with exact sizes).
+	 * NULL: a full destination raises CBGPU_ERR_NOMEM in the status word instead. */
+	int32_t    *part_flags;
+	/* staged mode, exact layout: destination d's rows start at row seg_base[d] of `out` and seg_cap[d] of
+	 * them fit (host arrays of nsegs entries); NULL: d * seg_capacity, seg_capacity */
+	const int64_t *seg_base;
+	const int64_t *seg_cap;
 } CbpSink;
 
 typedef struct CbPipeline
@@ -319,36 +332,91 @@ int			cbgpu_topn(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const i
 					   int64_t *nout);
 
 /* ------------------------------------------------------------------------------------------
- * interconnect over NCCL: one process per GPU-segment (backend/cdb/motion/cdbmotion.c:425,549 and
- * the MotionIPCLayer implementations under contrib/interconnect are what this replaces)
+ * interconnect between GPU-segments, one process per GPU (backend/cdb/motion/cdbmotion.c:425,549 and
+ * the MotionIPCLayer implementations under contrib/interconnect are what this replaces).
+ *
+ * Two transports share one object:
+ *   peer-memory windows   every rank owns a receive window in its HBM, mapped into every other rank's
+ *                         process (CUDA IPC) at create time.  A Motion is the sender slice's own kernel
+ *                         storing rows into the destination's window over NVLink, framed by DEVICE-side
+ *                         signals in the windows' control blocks (st.release.sys / ld.acquire.sys epoch
+ *                         words): no collective call and one host round trip (the receiver learning its
+ *                         row count) per Motion.
+ *   NCCL                  staged partition + count all-gather + grouped ncclSend / ncclRecv: the fallback
+ *                         for what the windows cannot take (a Motion larger than the window, Broadcast),
+ *                         and the only transport where P2P / IPC is unavailable.
  * ------------------------------------------------------------------------------------------ */
 /* 128-byte rendezvous token created on one rank and handed to all (the harness broadcasts it) */
 int			cbgpu_motion_unique_id(void *out128);
 int			cbgpu_motion_create(cbgpu_ctx *ctx, int rank, int nranks, const void *unique_id128, cbgpu_motion **out);
+/* Interconnect over the peer-memory windows alone, bootstrapped through an all-gather the CALLER
+ * provides (the backend's dispatcher connection, a torch.distributed store ...): every rank passes
+ * `bytes` of `mine` and gets nranks * bytes back in rank order; blocking; returns 0 on success.  No
+ * NCCL communicator is created (two ranks may share one device: the single-GPU multi-process tests run
+ * so), hence no staged fallback: a Motion the windows cannot take is an error. */
+typedef int (*cbgpu_allgather_fn) (void *arg, const void *mine, void *all, size_t bytes);
+int			cbgpu_motion_create_boot(cbgpu_ctx *ctx, int rank, int nranks, cbgpu_allgather_fn allgather, void *arg,
+									 cbgpu_motion **out);
 void		cbgpu_motion_destroy(cbgpu_motion *m);
+/* tear down WITHOUT any collective step (after a failed query the peers may be gone or out of step:
+ * cdbmotion's TeardownInterconnect with hasErrors, include/cdb/ml_ipc.h:106): aborts the NCCL
+ * communicator, unmaps the windows */
+void		cbgpu_motion_abort(cbgpu_motion *m);
 int			cbgpu_motion_rank(const cbgpu_motion *m);
 int			cbgpu_motion_nranks(const cbgpu_motion *m);
 int64_t		cbgpu_motion_bytes_sent(const cbgpu_motion *m);
-/* Redistribute: `send` holds this rank's rows grouped by destination (destination d at row
- * d * seg_capacity, counts[d] rows); returns the rows addressed to this rank, sender by sender */
-int			cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *counts, int64_t seg_capacity,
+/* Redistribute (staged): `send` holds this rank's rows grouped by destination (destination d's rows start
+ * at row offsets[d], counts[d] of them); returns the rows addressed to this rank, sender by sender.
+ * Receive sizes are exchanged exactly, so no skew can overflow a receiver.  counts[0] < 0 announces "this
+ * rank failed before the exchange": every rank then returns CBGPU_ERR_PEER instead of waiting for it. */
+int			cbgpu_motion_redistribute(cbgpu_motion *m, cbgpu_rel *send, const int64_t *counts, const int64_t *offsets,
 									  cbgpu_rel **recv);
-/* Direct Redistribute: partition + exchange fused into the sender slice's own kernel, over peer memory
- * (every rank's receive window is mapped into every other rank through CUDA IPC at create time; rows
- * are stored straight into the destination's HBM over NVLink).  begin and end are collective.
- *   begin: announce this rank's sender input rows (-1 = this rank cannot go direct, e.g. a nullable
- *          column: then begin fails on EVERY rank and all take cbgpu_motion_redistribute); returns the per-receiver row capacity and two device
- *          tables for the PARTITION sink: dest_cols[d * ncols + c] = base of column c in segment d's
- *          window, dest_counts[d] = segment d's row counter (CbpSink.part_cols / part_counts)
- *   end:   after the pipeline ran: wait for every sender, return the rows addressed to this rank; the sink's own
- *          per-destination counters (dev_sent_counts, device) are copied to sent_counts in the same round trip.
- * cbgpu_motion_direct_available() == 0 (no P2P / IPC, or CBGPU_MOTION=nccl): use cbgpu_motion_redistribute. */
+/* this rank failed before its part of the next exchange: tell the peers so that they return CBGPU_ERR_PEER
+ * instead of waiting for it.  staged = 0: the peers are entering a direct exchange (or a staged one where
+ * there are no windows); staged = 1: they are entering the staged exchange that follows a CBGPU_DX_RETRY. */
+int			cbgpu_motion_abandon(cbgpu_motion *m, int staged);
+/* Direct Redistribute: partition + exchange fused into the sender slice's own kernel, over the windows.
+ *   begin  (local, no synchronisation) lays the exchange out inside every window - the same arithmetic on
+ *          every rank, from the column types and the common window size alone - and queues the device-side
+ *          wait for "every receiver has emptied its window of the previous exchange".  Returns what the
+ *          PARTITION sink needs: per destination d the column bases cols[d * ncols + c], the NULL byte
+ *          bases nulls[d * ncols + c], the row counter counts[d] (peer memory, system-scope atomics), the
+ *          capacity in rows of every destination, and a device flag word the sink ORs CBGPU_DX_OVERFLOW
+ *          into when a destination is full (rows beyond the capacity are dropped, the exchange is redone
+ *          staged: the reference never fails on skew, cdbmotion.c:425).
+ *          CBGPU_ERR_UNSUPPORTED = no windows, or a row too wide for them: use cbgpu_motion_redistribute
+ *          (the answer depends on nothing rank-specific, so all ranks agree).
+ *   end    after the pipeline ran (or failed: pass CBGPU_DX_ERROR, the peers must not wait for this rank
+ *          for ever): signal "my rows are stored" into every window, wait for every sender's signal, take
+ *          delivery.  local_nullmask: bit c = this rank stored NULL bytes for column c.  *outcome:
+ *          CBGPU_DX_DELIVERED, or CBGPU_DX_RETRY (some destination overflowed or some rank vetoed;
+ *          nothing was delivered anywhere, every rank redoes the Motion through cbgpu_motion_redistribute).
+ *          A rank that passed CBGPU_DX_ERROR makes every rank return CBGPU_ERR_PEER.
+ *          The sink's own per-destination counters (dev_sent_counts, device) come back in the same round trip. */
+#define CBGPU_DX_OVERFLOW 1
+#define CBGPU_DX_VETO 2
+#define CBGPU_DX_ERROR 4
+#define CBGPU_DX_NOFIT 8
+#define CBGPU_DX_DELIVERED 0
+#define CBGPU_DX_RETRY 1
+typedef struct cbgpu_direct_dest
+{
+	int64_t		capacity;
+	void *const *cols;
+	uint8_t *const *nulls;
+	unsigned long long *const *counts;
+	int32_t    *flags;
+} cbgpu_direct_dest;
 int			cbgpu_motion_direct_available(const cbgpu_motion *m);
 int			cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, const int32_t *dscales,
-									  int64_t input_rows, int64_t *capacity, void *const **dest_cols,
-									  unsigned long long *const **dest_counts);
-int			cbgpu_motion_direct_end(cbgpu_motion *m, const int64_t *dev_sent_counts, int64_t *sent_counts, cbgpu_rel **recv);
+									  cbgpu_direct_dest *dest);
+int			cbgpu_motion_direct_end(cbgpu_motion *m, int32_t local_flags, uint64_t local_nullmask,
+									const int64_t *dev_sent_counts, int64_t *sent_counts, cbgpu_rel **recv, int32_t *outcome);
 int64_t		cbgpu_motion_direct_bytes(const cbgpu_motion *m);
+/* host round trips (stream synchronisations) and NCCL collectives spent inside Motions so far: what the
+ * device-side signalling is there to keep small (bench.py reports them per step) */
+int64_t		cbgpu_motion_host_syncs(const cbgpu_motion *m);
+int64_t		cbgpu_motion_collectives(const cbgpu_motion *m);
 /* Gather: the first nrows rows of every rank's `send` to rank `root` (others receive 0 rows) */
 int			cbgpu_motion_gather(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
 /* Broadcast: every rank receives every rank's first nrows rows */

@@ -22,8 +22,15 @@ def main():
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # CB_BOOT=gloo: the interconnect is the peer-memory windows alone, bootstrapped through a gloo all-gather (no NCCL
+    # communicator), and all ranks may share ONE device: the single-GPU box runs the inter-process transport this way
+    boot_gloo = os.environ.get("CB_BOOT") == "gloo"
+    if boot_gloo:
+        local = local % capi.gpu().cbgpu_device_count()
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rels, exp = tpch.load_golden(capi.hashbpchar)
     replicated = os.environ.get("CB_REPLICATED", "1") == "1"
     dist_keys = dict(tpch.DIST_KEY)
@@ -33,9 +40,16 @@ def main():
     mine = shard(O, rels, world, dist_keys)[rank]
     ctx = capi.Context(local)
     dev = to_device(ctx, mine)
-    ids = [capi.Motion.unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    motion = capi.Motion(ctx, rank, world, ids[0])
+    if boot_gloo:
+        def allgather(mine):
+            box = [None] * world
+            dist.all_gather_object(box, mine)
+            return box
+        motion = capi.Motion(ctx, rank, world, allgather=allgather)
+    else:
+        ids = [capi.Motion.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        motion = capi.Motion(ctx, rank, world, ids[0])
     ex = capi.Executor(ctx, dev, motion=motion)
     seg = exp["dict"]["c_mktsegment_dict"].index("MACHINERY")
     reg = exp["dict"]["r_name_dict"].index("AMERICA")
@@ -55,8 +69,8 @@ def main():
         print("MULTIRANK FAIL: distribute_by_hash gave %d rows, the oracle's shard has %d" % (len(got), len(want)))
     mine_li.free()
     sl.free()
-    # a null map that exists on ONE segment only: the direct-or-staged decision of every Motion must still be taken
-    # by all segments together (Redistribute: veto in the announcement; Gather: flag in the all-reduce)
+    # a null map that exists on ONE segment only: the direct Redistribute carries NULL bytes from the senders that have
+    # them (the mask rides on the completion signal); the Gather's direct-or-staged decision rides on its signal too
     from cloudberry_b200 import plan as P
     from cloudberry_b200.relation import HostRelation
     kk = np.arange(100, dtype=np.int64) + 1000 * rank
@@ -79,6 +93,54 @@ def main():
             print("MULTIRANK FAIL: asymmetric null map through Redistribute + Gather: %d rows" % len(rt.rows))
     ext.close()
     dt.free()
+    # skew: nine rows of ten go to ONE destination (the reference sends tuple by tuple and cannot overflow,
+    # cdbmotion.c:425): the Motion must deliver every row, direct (the window takes it) or by the exact-size staged redo
+    nsk = int(os.environ.get("CB_SKEW_ROWS", "300000"))
+    ks = np.where(np.arange(nsk) % 10 == 0, np.arange(nsk) + rank * nsk, 7).astype(np.int32)
+    tsk = HostRelation("sk", ["k", "v"], [P.INT4, P.INT8], [ks, np.arange(nsk, dtype=np.int64) + rank * nsk])
+    dsk = capi.DeviceRelation.from_host(ctx, tsk)
+    exs = capi.Executor(ctx, [dsk], motion=motion)
+    scs = P.SeqScan(1, [("k", P.Var(1, 1, P.INT4)), ("v", P.Var(1, 2, P.INT8))])
+    mhs = P.Motion(scs, P.MOTIONTYPE_HASH, [P.out_var(scs, 1)], world)
+    aggs = P.Agg(mhs, P.AGG_PLAIN, P.AGGSPLIT_SIMPLE, [], [("n", P.Aggref(P.AGG_COUNT_STAR)), ("s", P.Aggref(P.AGG_SUM, P.out_var(mhs, 2)))])
+    rsk = exs.run(P.Motion(aggs, P.MOTIONTYPE_GATHER))
+    if rank == 0:
+        tot_n = sum(int(r[0]) for r in rsk.rows)
+        tot_s = sum(int(r[1]) for r in rsk.rows if r[1] is not None)
+        big = max(int(r[0]) for r in rsk.rows)
+        if tot_n != nsk * world or tot_s != sum(range(nsk * world)) or big < 0.9 * nsk * world:
+            ok = False
+            print("MULTIRANK FAIL: skewed Motion delivered %d rows (sum %d), largest segment %d" % (tot_n, tot_s, big))
+        else:
+            print("skewed Motion ok: %d rows, %d on one segment, repartitions %s" % (
+                tot_n, big, [v.get("motion_repartitions") for v in rsk.instrument.values() if v.get("motion_repartitions")]))
+    exs.close()
+    dsk.free()
+    # a segment that fails in the middle of a query: the others must get CBGPU_ERR_PEER, not wait for ever, and the
+    # interconnect must be usable for the next query
+    bad = HostRelation("bad", ["k", "v"], [P.INT4, P.INT8], [np.arange(64, dtype=np.int32), np.full(64, (1 << 62) if rank == world - 1 else 1, dtype=np.int64)])
+    dbad = capi.DeviceRelation.from_host(ctx, bad)
+    exb = capi.Executor(ctx, [dbad], motion=motion)
+    scb = P.SeqScan(1, [("k", P.Var(1, 1, P.INT4)), ("v", P.Var(1, 2, P.INT8))])
+    # v * 4 overflows int8 on the last segment only: its sender slice fails (CBGPU_ERR_OVERFLOW)
+    mul = P.SeqScan(1, [("k", P.Var(1, 1, P.INT4)), ("v4", P.OpExpr(P.OP_MUL, P.Var(1, 2, P.INT8), P.Const(P.INT8, 4)))])
+    mb = P.Motion(mul, P.MOTIONTYPE_HASH, [P.out_var(mul, 1)], world)
+    code = None
+    try:
+        exb.run(P.Motion(mb, P.MOTIONTYPE_GATHER))
+    except capi.CbgpuError as e:
+        code = e.code
+    want_code = -4 if rank == world - 1 else -7       # CBGPU_ERR_OVERFLOW / CBGPU_ERR_PEER
+    if code != want_code:
+        ok = False
+        print("MULTIRANK FAIL: rank %d: failing segment gave code %r, expected %r" % (rank, code, want_code))
+    # ... and the next query works
+    rb = exb.run(P.Motion(P.Motion(scb, P.MOTIONTYPE_HASH, [P.out_var(scb, 1)], world), P.MOTIONTYPE_GATHER))
+    if rank == 0 and len(rb.rows) != 64 * world:
+        ok = False
+        print("MULTIRANK FAIL: query after a failed one returned %d rows" % len(rb.rows))
+    exb.close()
+    dbad.free()
     r1 = ex.run(tpch.q1_plan(world))
     r3 = ex.run(tpch.q3_plan(seg, world, customer_replicated=replicated))
     r5 = ex.run(tpch.q5_plan(reg, world, replicated=replicated))
@@ -86,14 +148,15 @@ def main():
         ok = ok and tpch.format_q1(r1.rows) == exp["q1"]
         ok = ok and tpch.format_q3(r3.rows) == exp["q3"]
         ok = ok and tpch.format_q5(r5.rows, exp["dict"]["n_name_dict"]) == exp["q5"]
-        print("MULTIRANK", "PASS" if ok else "FAIL", "world", world, "replicated", replicated, "direct" if motion.direct() else "staged", "motion bytes sent by rank 0", motion.bytes_sent())
+        print("MULTIRANK", "PASS" if ok else "FAIL", "world", world, "replicated", replicated, "direct" if motion.direct() else "staged",
+              "motion bytes sent by rank 0", motion.bytes_sent(), "host syncs", motion.host_syncs(), "collectives", motion.collectives())
         if not ok:
             print(tpch.format_q1(r1.rows), tpch.format_q3(r3.rows), tpch.format_q5(r5.rows, exp["dict"]["n_name_dict"]))
     else:
         ok = ok and len(r1.rows) == 0 and len(r3.rows) == 0 and len(r5.rows) == 0     # only the gather receiver emits
         if not ok:
             print("MULTIRANK FAIL: non-root rank emitted rows")
-    flag = torch.tensor([0 if ok else 1], device="cuda")
+    flag = torch.tensor([0 if ok else 1], device="cpu" if boot_gloo else "cuda")
     dist.all_reduce(flag)
     ex.close()
     motion.close()
