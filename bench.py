@@ -283,6 +283,31 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _rows_as_text(kind, rows):
+    from cloudberry_b200 import ssb, tpch
+    if kind == "q1":
+        return tpch.format_q1(rows)
+    if kind == "q3":
+        return tpch.format_q3(rows)
+    if kind == "q5":
+        return tpch.format_q5(rows, tpch.NATIONS)
+    return ssb.canon(rows)
+
+
+def traffic_of(kernel_name):
+    """dram bytes per launch of the dominant kernel from the round's ncu --set full capture (tools/gpu_round.sh writes
+    profiles/q1_kernel_traffic.json with the sha256 of the kernel source it measured): null when the source has changed since."""
+    import hashlib
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "q1_kernel_traffic.json")))
+        sha = hashlib.sha256(open(os.path.join(ROOT, "cloudberry_b200", "csrc", "scan_agg.cu"), "rb").read()).hexdigest()
+        if d.get("source_sha256") == sha and d.get("kernel", "").split("(")[0] == kernel_name.split("(")[0]:
+            return d.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -293,9 +318,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--joins-sf", type=float, default=None,
-                    help="N > 1 only: scale factor of the ONE database Q3 / Q5 run on (default: --sf; BASELINE configs[3] is 300 on 8 GPUs)")
+                    help="scale factor of the ONE database Q5 runs on at N > 1 (default: 300 on 8 GPUs = BASELINE configs[3], else --sf); "
+                         "Q3 always runs on SF --sf (configs[2])")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-joins", action="store_true", help="skip the Q3 / Q5 join pipelines (extra keys q3, q5)")
+    ap.add_argument("--no-ssb", action="store_true", help="skip SSB Q4.1 - Q4.3 (extra key ssb)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -314,8 +341,19 @@ def main():
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
+    from cloudberry_b200 import bench_golden as BG
     from cloudberry_b200 import capi, tpch
     import numpy as np
+
+    gold = BG.load() or {}
+    checks = []                 # every result_check of this run; any MISMATCH fails the run (rc 1) after the line is printed
+
+    def result_check(kind, rows, want_rows, missing):
+        if want_rows is None:
+            return "unchecked: %s" % missing
+        c = BG.check(kind, _rows_as_text(kind if kind in ("q1", "q3", "q5") else "ssb", rows), want_rows)
+        checks.append(c)
+        return c
 
     ctx = capi.Context(local_rank)
     G = ctx.L
@@ -344,8 +382,29 @@ def main():
             dist.barrier()
         ctx.sync()
 
-    def combine(rows_states):
-        return rows_states
+    def bcast_rows(rows):
+        """the Gather receiver's rows, on every rank (so that all ranks agree on the run's verdict)"""
+        if not dist:
+            return rows
+        box = [rows if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def maxr(vals):
+        if not dist:
+            return [float(v) for v in vals]
+        import torch
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sumr(vals):
+        if not dist:
+            return [float(v) for v in vals]
+        import torch
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
 
     # ---- device-resident: warm-up, then K timed steps ----
     sampler = ClockSampler(local_rank)
@@ -353,7 +412,7 @@ def main():
     for _ in range(args.warmup):
         res = ex.run(plan1)
     # keep the same load up (untimed) until the clock sampler is actually sampling; with several ranks the number of
-    # extra steps must be the same everywhere (every step holds collectives), so it is fixed there
+    # extra steps must be the same everywhere (every step holds Motions), so it is fixed there
     if dist:
         for _ in range(80):
             res = ex.run(plan1)
@@ -364,6 +423,7 @@ def main():
     kernel_ms = []
     barrier()
     l0 = ctx.launches()
+    hs0 = (motion.host_syncs(), motion.collectives()) if motion else (0, 0)
     ctx.timer_start()
     knames = []
     for _ in range(args.steps):
@@ -374,26 +434,21 @@ def main():
         knames.append(kn)
     ms = ctx.timer_stop_ms()
     l1 = ctx.launches()
+    hs1 = (motion.host_syncs(), motion.collectives()) if motion else (0, 0)
     barrier()
     clocks = sampler.stop()
     kname = knames[-1]
-    ngroups = len(res.rows)
-    if dist:
-        import torch
-        t = torch.tensor([ms, float(ngroups)], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0].item())
-        ngroups = int(t[1].item())
+    q1_rows = bcast_rows(res.rows)
+    ngroups = len(q1_rows)
+    ms = maxr([ms])[0]
     total_rows = nrows * world
     value = total_rows * args.steps / (ms / 1e3)
     peak, peak_src = measured_peak()
     kms = sorted(kernel_ms)[len(kernel_ms) // 2]
     achieved = nrows * Q1_BYTES_PER_ROW / (kms / 1e3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "q1_kernel_traffic.json"))).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    gq1 = gold.get(BG.key("q1", args.sf))
+    q1_check = result_check("q1", q1_rows, BG.q1_rows(gq1, world) if gq1 and len(gq1["shards"]) >= world and gq1["rows_per_shard"] == nrows else None,
+                            "no golden rows for SF%g x %d shards" % (args.sf, world))
 
     # ---- end to end: host (pinned) buffers -> H2D -> query -> rows back ----
     e2e = None
@@ -418,10 +473,7 @@ def main():
             host[c] = p
             ctx.check(G.cbgpu_rel_read_column(li_e.h, c, 0, e2e_rows, p, None))
         if dist:
-            import torch
-            t = torch.tensor([1.0 if ok else 0.0], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)      # every step holds collectives: all ranks run it, or none
-            ok = bool(t.item() > 0.5)
+            ok = maxr([0.0 if ok else 1.0])[0] < 0.5          # every step holds Motions: all ranks run it, or none
         if ok:
             h2d = sum(e2e_rows * capi.P.TYPE_WIDTH[li_types[c]] for c in cols)
             d2h = 0
@@ -441,15 +493,13 @@ def main():
             wall = time.perf_counter() - t0
             barrier()
             d2h = sum(8 * len(row) for row in r.rows)
-            e_ms = max(e_ms, wall * 1e3)
-            if dist:
-                import torch
-                t = torch.tensor([e_ms], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                e_ms = float(t.item())
+            e_ms = maxr([max(e_ms, wall * 1e3)])[0]
             e2e = {"value": e2e_rows * world * args.e2e_steps / (e_ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": h2d * world,
                    "d2h_bytes_per_step": d2h * world, "steps": args.e2e_steps, "ms_per_step": e_ms / args.e2e_steps,
-                   "rows_per_gpu": e2e_rows}
+                   "rows_per_gpu": e2e_rows, "bytes_per_row_shipped": h2d / e2e_rows,
+                   "note": "decoded projected columns from pinned host memory, one cudaMemcpyAsync per column, then the query; PCIe-bound"}
+            if e2e_rows == nrows:
+                e2e["result_check"] = result_check("q1", bcast_rows(r.rows), BG.q1_rows(gq1, world) if gq1 and len(gq1["shards"]) >= world else None, "no golden rows")
         for p in host.values():
             G.cbgpu_host_free(p)
         if ex_e is not ex:
@@ -457,65 +507,122 @@ def main():
             li_e.free()
 
     # ---- the join queries of the metric (Q3, Q5).  N = 1: on the same resident tables.  N > 1: the BASELINE
-    # configs "TPC-H SF100 Q3 / Q5 on N GPU-segments": ONE SF-sized database distributed over the segments as the
-    # reference's DDL would (lineitem / orders by orderkey, customer by c_custkey, supplier by s_suppkey, nation
-    # and region replicated), plans with Redistribute Motions over NCCL; strong scaling ----
+    # configs "TPC-H SF100 Q3 on N GPU-segments" and "TPC-H SF300 Q5 on 8 GPU-segments": ONE database distributed over the
+    # segments as the reference's DDL would (lineitem / orders by orderkey, customer by c_custkey, supplier by s_suppkey, nation
+    # and region replicated), plans with Redistribute Motions; strong scaling ----
     joins = {}
+
+    def timed_query(exq, plan, steps):
+        for _ in range(args.warmup):
+            r = exq.run(plan)
+        barrier()
+        l0j = ctx.launches()
+        sent0 = motion.bytes_sent() if motion else 0
+        h0 = (motion.host_syncs(), motion.collectives()) if motion else (0, 0)
+        ctx.timer_start()
+        for _ in range(steps):
+            ctx.kernel_log_reset()
+            r = exq.run(plan)
+        qms = ctx.timer_stop_ms() / steps
+        kn, km = ctx.longest_kernel()
+        sent = (motion.bytes_sent() - sent0) / steps if motion else 0
+        h1 = (motion.host_syncs(), motion.collectives()) if motion else (0, 0)
+        launches = (ctx.launches() - l0j) // steps
+        barrier()
+        qms = maxr([qms])[0]
+        sent = sumr([sent])[0]
+        return {"rows": bcast_rows(r.rows), "ms": qms, "kernel": kn, "kernel_ms": km, "sent": int(sent), "launches": launches,
+                "host_syncs": (h1[0] - h0[0]) / steps, "collectives": (h1[1] - h0[1]) / steps}
+
+    def motion_desc():
+        if not motion:
+            return "none"
+        return ("partition fused with the exchange over peer memory (CUDA IPC windows, NVLink stores, device-side epoch signals)"
+                if motion.direct() else "staged partition + NCCL send/recv")
+
     if not args.no_joins:
         from cloudberry_b200 import harness
-        jsf = args.joins_sf if (args.joins_sf and world > 1) else args.sf
-        szj = tpch.sizes(int(jsf) if float(jsf).is_integer() else jsf)
-        if world == 1:
-            rt_all, _ = harness.device_tables(ctx, args.sf, lineitem=li)
-            exj = capi.Executor(ctx, rt_all)
-            owned = rt_all[1:]
-        else:
+        q5_sf = args.joins_sf if (args.joins_sf and world > 1) else (300.0 if (world == 8 and args.sf == 100.0) else args.sf)
+        jsteps = max(3, min(args.steps, 10))
+        runs = [("q3", args.sf)] + [("q5", q5_sf)]
+        if world > 1:
             ex.close()
             ex = None
             li.free()           # the weak-scaling Q1 shard makes room for the distributed database
             li = None
-            rt_all, _ = harness.distributed_tables(ctx, motion, jsf, rank, world)
-            exj = capi.Executor(ctx, rt_all, motion=motion)
-            owned = rt_all
-        plans = {"q3": tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), world, customer_replicated=False),
-                 "q5": tpch.q5_plan(tpch.REGIONS.index("AMERICA"), world, replicated=False)}
-        jsteps = max(3, min(args.steps, 10))
-        for q, plan in plans.items():
-            for _ in range(args.warmup):
-                r = exj.run(plan)
-            barrier()
-            l0j = ctx.launches()
-            sent0 = motion.bytes_sent() if motion else 0
-            ctx.timer_start()
-            for _ in range(jsteps):
-                ctx.kernel_log_reset()
-                r = exj.run(plan)
-            qms = ctx.timer_stop_ms() / jsteps
-            kn, km = ctx.longest_kernel()
-            nres = len(r.rows)
-            sent = (motion.bytes_sent() - sent0) / jsteps if motion else 0
-            barrier()
-            if dist:
-                import torch
-                t = torch.tensor([qms, float(nres), float(sent)], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                qms, nres = float(t[0].item()), int(t[1].item())
-                t2 = torch.tensor([float(sent)], device="cuda")
-                dist.all_reduce(t2, op=dist.ReduceOp.SUM)
-                sent = float(t2.item())
+        cur_sf, rt_all, owned, exj = None, None, [], None
+        for q, jsf in runs:
+            if jsf != cur_sf:
+                if exj:
+                    exj.close()
+                for r_ in owned:
+                    r_.free()
+                if world == 1:
+                    rt_all, _ = harness.device_tables(ctx, jsf, lineitem=li if jsf == args.sf else None)
+                    owned = rt_all[1:] if jsf == args.sf else rt_all
+                    exj = capi.Executor(ctx, rt_all)
+                else:
+                    rt_all, _ = harness.distributed_tables(ctx, motion, jsf, rank, world)
+                    owned = rt_all
+                    exj = capi.Executor(ctx, rt_all, motion=motion)
+                cur_sf = jsf
+            szj = tpch.sizes(int(jsf) if float(jsf).is_integer() else jsf)
+            plan = (tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), world, customer_replicated=False) if q == "q3"
+                    else tpch.q5_plan(tpch.REGIONS.index("AMERICA"), world, replicated=False))
+            t = timed_query(exj, plan, jsteps)
             rows_in, nbytes = harness.query_rows_bytes(q, szj)
-            joins[q] = {"value": rows_in / (qms / 1e3), "unit": "rows/s", "sf": jsf, "ms_per_step": qms, "steps": jsteps, "rows_scanned": rows_in,
-                        "scaling": "strong" if world > 1 else "n/a", "result_rows": nres,
-                        "gpu_launches_per_step": (ctx.launches() - l0j) // jsteps,
-                        "longest_kernel": kn, "longest_kernel_ms": km, "motion_bytes_per_step": int(sent),
-                        "motion": ("fused partition + exchange over peer memory (CUDA IPC windows, NVLink stores)" if motion and motion.direct()
-                                   else "staged partition + NCCL send/recv") if motion else "none",
-                        "roofline": {"bound": "hbm", "achieved": nbytes / (qms / 1e3) / 1e9, "peak": peak * world, "unit": "GB/s",
-                                     "frac": nbytes / (qms / 1e3) / 1e9 / (peak * world), "algorithmic_bytes": nbytes,
+            g = gold.get(BG.key(q, jsf))
+            joins[q] = {"value": rows_in / (t["ms"] / 1e3), "unit": "rows/s", "sf": jsf, "ms_per_step": t["ms"], "steps": jsteps, "rows_scanned": rows_in,
+                        "scaling": "strong" if world > 1 else "n/a", "result_rows": len(t["rows"]),
+                        "result_check": result_check(q, t["rows"], (BG.q3_rows(g) if q == "q3" else BG.q5_rows(g)) if g else None,
+                                                     "no golden rows for SF%g" % jsf),
+                        "gpu_launches_per_step": t["launches"],
+                        "longest_kernel": t["kernel"], "longest_kernel_ms": t["kernel_ms"], "motion_bytes_per_step": t["sent"],
+                        "motion": motion_desc(), "motion_host_syncs_per_step": t["host_syncs"], "motion_collectives_per_step": t["collectives"],
+                        "roofline": {"bound": "hbm", "achieved": nbytes / (t["ms"] / 1e3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                                     "frac": nbytes / (t["ms"] / 1e3) / 1e9 / (peak * world), "algorithmic_bytes": nbytes,
                                      "note": "whole query (all pipelines, builds, Motions, top-N, host glue) against the projected base columns"}}
-        exj.close()
+        if exj:
+            exj.close()
         for r_ in owned:
             r_.free()
+
+    # ---- SSB Q4.1 - Q4.3 (BASELINE configs[4]: wide hash-agg, HBM-bound group-by): ONE SF100 database, lineorder spread over
+    # the segments by row range, the four dimensions replicated; star join + two-stage aggregation over Motions at N > 1 ----
+    ssbres = None
+    if not args.no_ssb:
+        from cloudberry_b200 import ssb
+        if world > 1 and ex:
+            ex.close()
+            ex = None
+        if li and world > 1:
+            li.free()
+            li = None
+        dev, ssz = ssb.device_tables(ctx, args.sf, capi.hashbpchar, rank, world)
+        exs = capi.Executor(ctx, dev, motion=motion)
+        rows_in, nbytes = ssb.query_rows_bytes(ssz)
+        gs = gold.get(BG.key("ssb", args.sf))
+        ssteps = max(3, min(args.steps, 10))
+        per, tot_ms = {}, 0.0
+        for q in ("q4.1", "q4.2", "q4.3"):
+            t = timed_query(exs, ssb.PLANS[q](world), ssteps)
+            tot_ms += t["ms"]
+            per[q] = {"ms_per_step": t["ms"], "groups": len(t["rows"]), "longest_kernel": t["kernel"], "longest_kernel_ms": t["kernel_ms"],
+                      "gpu_launches_per_step": t["launches"], "motion_bytes_per_step": t["sent"],
+                      "result_check": result_check(q, t["rows"], BG.ssb_rows(gs, q) if gs else None, "no golden rows for SF%g" % args.sf),
+                      "roofline_frac": nbytes / (t["ms"] / 1e3) / 1e9 / (peak * world)}
+        ssbres = {"value": 3 * rows_in / (tot_ms / 1e3), "unit": "rows/s", "sf": args.sf, "ms_per_step": tot_ms, "steps": ssteps,
+                  "rows_scanned": 3 * rows_in, "scaling": "strong" if world > 1 else "n/a", "queries": per,
+                  "result_check": "ok" if all(v["result_check"] == "ok" for v in per.values()) else
+                  next(v["result_check"] for v in per.values() if v["result_check"] != "ok"),
+                  "motion": motion_desc(),
+                  "roofline": {"bound": "hbm", "achieved": 3 * nbytes / (tot_ms / 1e3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                               "frac": 3 * nbytes / (tot_ms / 1e3) / 1e9 / (peak * world), "algorithmic_bytes": 3 * nbytes,
+                               "note": "Q4.1 + Q4.2 + Q4.3 back to back, each a whole query (dimension builds, star-join pipeline, aggregation, Motions) "
+                                       "against the projected base columns (SURVEY.md 8d: 19.3 GB per query)"}}
+        exs.close()
+        for d in dev:
+            d.free()
 
     # ---- CPU baseline (rank 0, N = 1): the oracle, scalar, on a bounded sample ----
     cpu = None
@@ -531,11 +638,12 @@ def main():
             sys.stderr.write("ref_q1 baseline skipped: %r\n" % (e,))
             st = None
         if st:
-            cpu = {"value": ref_rows / st[1], "unit": "rows/s", "cores": 1, "kind": "reference",
+            cpu = {"value": ref_rows / st[1], "unit": "rows/s", "cores": 1, "kind": "reference", "rows_timed": ref_rows,
                    "sample": "Q1 over the first %d rows of the same synthetic lineitem, %.1f s, one process; %s" % (ref_rows, st[1], REF_Q1_NOTE),
                    "port": {"value": rate, "unit": "rows/s", "cores": 1,
                             "sample": "the oracle's int64 restatement (oracle/oracle.c) over the first %d rows, %.1f s, one thread" % (rows, secs)}}
 
+    bad = [c for c in checks if c != "ok"]
     if rank == 0:
         line = {
             "metric": "TPC-H SF100 Q1 rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
@@ -544,11 +652,15 @@ def main():
             "config": {"workload": workload_name(args.sf, world),
                        "rows_per_gpu": nrows, "groups": ngroups, "l2": "inputs (%.1f GB per GPU) larger than L2" % (nrows * Q1_BYTES_PER_ROW / 1e9),
                        "timing": "CUDA events on the executor's stream, max over ranks"},
+            "result_check": q1_check, "result_check_source": BG.SOURCE,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": kname, "kernel_ms": kms, "peak_source": peak_src,
+                         "traffic": traffic_of(kname), "kernel": kname, "kernel_ms": kms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": nrows * Q1_BYTES_PER_ROW},
             "clocks": clocks, "gpu_launches": l1 - l0,
         }
+        if motion:
+            line["motion"] = {"transport": motion_desc(), "host_syncs_per_step": (hs1[0] - hs0[0]) / args.steps,
+                              "collectives_per_step": (hs1[1] - hs0[1]) / args.steps}
         if e2e:
             line["e2e"] = e2e
         if cpu:
@@ -561,7 +673,11 @@ def main():
             except Exception as e:
                 sys.stderr.write("join cpu baselines skipped: %r\n" % (e,))
         line.update(joins)
+        if ssbres:
+            line["ssb"] = ssbres
         print(json.dumps(line))
+        if bad:
+            sys.stderr.write("result_check FAILED: %s\n" % bad[0])
     if ex:
         ex.close()
     if li:
@@ -571,6 +687,8 @@ def main():
     ctx.close()
     if dist:
         dist.destroy_process_group()
+    if bad:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -313,6 +313,7 @@ def gpu():
             "cbgpu_aocs_decode_column_ex": (C.c_int, [vp, vp, i64, i32, i32, i32, i32, i32, vp, i32, i64, C.POINTER(i64)]),
             "cbgpu_gen_customer_range": (C.c_int, [vp, vp, u64, i64]),
             "cbgpu_gen_supplier_range": (C.c_int, [vp, vp, u64, i64]),
+            "cbgpu_gen_ssb_lineorder": (C.c_int, [vp, vp, u64, i64, i64, i64, i64]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)

@@ -225,3 +225,95 @@ cbgpu_gen_supplier_range(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed, int64_t 
 	CB_LAUNCHED(ctx, "k_gen_keyed");
 	return CBGPU_OK;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Star Schema Benchmark fact table (BASELINE.json configs[4]): the formulas of cloudberry_b200/ssb.py
+ * gen_tables, rows [row_lo, row_lo + n) of lineorder.  Dimensions are small and come from the host.
+ * --------------------------------------------------------------------------------------------- */
+struct GenLineorder
+{
+	int32_t    *custkey, *partkey, *suppkey, *orderdate;
+	int64_t    *revenue, *supplycost;
+	int64_t		n;
+	int64_t		row_lo;
+	uint64_t	seed;
+	uint64_t	n_cust, n_part, n_supp;
+};
+
+/* d_datekey (yyyymmdd) of day `idx` counted from 1992-01-01; 1992 and 1996 are the leap years in range */
+__host__ __device__ __forceinline__ int32_t
+gen_ssb_datekey(int idx)
+{
+	const int	mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+	int			y = 1992;
+
+	for (;;)
+	{
+		const int	ylen = (y % 4 == 0) ? 366 : 365;
+
+		if (idx < ylen)
+			break;
+		idx -= ylen;
+		y++;
+	}
+	for (int m = 0; m < 12; m++)
+	{
+		const int	n = mdays[m] + ((m == 1 && y % 4 == 0) ? 1 : 0);
+
+		if (idx < n)
+			return y * 10000 + (m + 1) * 100 + idx + 1;
+		idx -= n;
+	}
+	return y * 10000 + 1231;
+}
+
+__global__ void
+k_gen_lineorder(GenLineorder g)
+{
+	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t		stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; i < g.n; i += stride)
+	{
+		const uint64_t j = (uint64_t) (g.row_lo + i);
+
+		g.custkey[i] = (int32_t) (1 + gen_u(g.seed, 51, j) % g.n_cust);
+		g.partkey[i] = (int32_t) (1 + gen_u(g.seed, 52, j) % g.n_part);
+		g.suppkey[i] = (int32_t) (1 + gen_u(g.seed, 53, j) % g.n_supp);
+		g.orderdate[i] = gen_ssb_datekey((int) (gen_u(g.seed, 54, j) % 2556));
+		g.revenue[i] = (int64_t) (100 + gen_u(g.seed, 55, j) % 10000000);
+		g.supplycost[i] = (int64_t) (50 + gen_u(g.seed, 56, j) % 120000);
+	}
+}
+
+extern "C" int
+cbgpu_gen_ssb_lineorder(cbgpu_ctx *ctx, cbgpu_rel *rel, uint64_t seed, int64_t row_lo, int64_t n_cust, int64_t n_part, int64_t n_supp)
+{
+	const int	types[6] = {CB_INT4, CB_INT4, CB_INT4, CB_INT4, CB_INT8, CB_INT8};
+	int			rc = gen_check(ctx, rel, types, 6, "lineorder");
+	GenLineorder g;
+
+	if (rc)
+		return rc;
+	if (n_cust < 1 || n_part < 1 || n_supp < 1)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "generator: lineorder needs the dimension sizes%s", "", 0);
+	g.custkey = (int32_t *) rel->data[0];
+	g.partkey = (int32_t *) rel->data[1];
+	g.suppkey = (int32_t *) rel->data[2];
+	g.orderdate = (int32_t *) rel->data[3];
+	g.revenue = (int64_t *) rel->data[4];
+	g.supplycost = (int64_t *) rel->data[5];
+	g.n = rel->nrows;
+	g.row_lo = row_lo;
+	g.seed = seed;
+	g.n_cust = (uint64_t) n_cust;
+	g.n_part = (uint64_t) n_part;
+	g.n_supp = (uint64_t) n_supp;
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (rel->nrows > 0)
+	{
+		k_gen_lineorder<<<gen_blocks(ctx, rel->nrows), 256, 0, ctx->stream>>>(g);
+		CB_LAUNCHED(ctx, "k_gen_lineorder");
+	}
+	return CBGPU_OK;
+}

@@ -716,7 +716,8 @@ k_dx_complete(DxPeers peers, int me, int n, unsigned long long epoch, unsigned f
 	if (p < 64)
 	{
 		res->cnt[p] = (ghdr && p < n) ? ((const volatile long long *) ghdr)[p] : 0;
-		res->sent[p] = (dev_sent && p < n) ? dev_sent[p] : 0;
+		/* Redistribute: the sink's per-destination counts; Gather: every sender's NULL-column mask */
+		res->sent[p] = (dev_sent && p < n) ? dev_sent[p] : (ghdr && p < n) ? ((const volatile long long *) ghdr)[64 + p] : 0;
 	}
 	if (p == 0)
 	{
@@ -1015,14 +1016,15 @@ cbgpu_motion_abandon(cbgpu_motion *m, int staged)
  * alternate by epoch parity; `release` of exchange e is the proof that a buffer of exchange e - 1 is empty. */
 struct GatherPut
 {
-	long long  *hdr[64];		/* the receivers' count slot for this sender                          */
+	long long  *hdr[64];		/* the receivers' count slot for this sender (its NULL-column mask 64 slots on) */
 	char	   *base[64];		/* ... and payload slot                                               */
 	int			ndest;
 	long long	nrows;
-	const void *src[CBP_MAX_OUT];
-	size_t		off[CBP_MAX_OUT];
-	size_t		bytes[CBP_MAX_OUT];
-	int			ncols;
+	long long	nullmask;
+	const void *src[2 * CBP_MAX_OUT];	/* the columns, then the NULL maps of the columns that have one     */
+	size_t		off[2 * CBP_MAX_OUT];
+	size_t		bytes[2 * CBP_MAX_OUT];
+	int			nparts;
 };
 
 __global__ void
@@ -1031,8 +1033,11 @@ k_gather_put(GatherPut g)
 	const int	d = blockIdx.y;
 
 	if (blockIdx.x == 0 && threadIdx.x == 0)
-		*g.hdr[d] = g.nrows;
-	if ((int) blockIdx.x < g.ncols)
+	{
+		g.hdr[d][0] = g.nrows;
+		g.hdr[d][64] = g.nullmask;
+	}
+	if ((int) blockIdx.x < g.nparts)
 	{
 		const size_t n = g.bytes[blockIdx.x];
 		unsigned char *dst = (unsigned char *) g.base[d] + g.off[blockIdx.x];
@@ -1043,8 +1048,16 @@ k_gather_put(GatherPut g)
 	}
 }
 
+static size_t
+gx_pad(size_t bytes)
+{
+	return (bytes + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
+}
+
 /* root >= 0: Gather to that rank; root < 0: Broadcast.  Returns 1 when done directly, 0 when the caller must
- * take the staged path (decided identically on every rank), < 0 on error */
+ * take the staged path (decided identically on every rank), < 0 on error.  A sender lays its slot out as
+ * [column 0][column 1]...[NULL bytes of its nullable columns, in column order], every part padded to
+ * DX_ALIGN; row count and NULL-column mask go into the buffer's header. */
 static int
 gather_direct(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv)
 {
@@ -1063,11 +1076,22 @@ gather_direct(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_r
 	memset(&g, 0, sizeof(g));
 	for (int c = 0; c < send->ncols; c++)
 	{
-		if (send->nulls[c])
-			fits = 0;			/* a null map may exist on one rank only: the decision rides on the signal */
-		g.off[c] = need;
-		need += ((size_t) nrows * (size_t) cb_type_w(send->types[c]) + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
+		g.src[g.nparts] = send->data[c];
+		g.bytes[g.nparts] = (size_t) nrows * (size_t) cb_type_w(send->types[c]);
+		g.off[g.nparts] = need;
+		need += gx_pad(g.bytes[g.nparts]);
+		g.nparts++;
 	}
+	for (int c = 0; c < send->ncols; c++)
+		if (send->nulls[c])
+		{
+			g.nullmask |= 1ll << c;
+			g.src[g.nparts] = send->nulls[c];
+			g.bytes[g.nparts] = (size_t) nrows;
+			g.off[g.nparts] = need;
+			need += gx_pad(g.bytes[g.nparts]);
+			g.nparts++;
+		}
 	if (need > slot)
 		fits = 0;
 	dx_open(m);
@@ -1082,13 +1106,7 @@ gather_direct(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_r
 				g.ndest++;
 			}
 		g.nrows = nrows;
-		g.ncols = send->ncols;
-		for (int c = 0; c < send->ncols; c++)
-		{
-			g.src[c] = send->data[c];
-			g.bytes[c] = (size_t) nrows * (size_t) cb_type_w(send->types[c]);
-		}
-		k_gather_put<<<dim3(send->ncols > 0 ? send->ncols : 1, g.ndest), 256, 0, ctx->stream>>>(g);
+		k_gather_put<<<dim3(g.nparts > 0 ? g.nparts : 1, g.ndest), 256, 0, ctx->stream>>>(g);
 		CB_LAUNCHED(ctx, "k_gather_put");
 	}
 	if (dx_complete(m, fits ? 0u : CBGPU_DX_NOFIT, 0, NULL, receiver ? (const long long *) (m->win + buf) : NULL, NULL, "p2p:gather") != CBGPU_OK)
@@ -1106,12 +1124,24 @@ gather_direct(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_r
 	}
 	{
 		int64_t		total = 0;
+		unsigned long long anynull = 0;
 		int			rc;
 
 		if (receiver)
 			for (int s = 0; s < n; s++)
+			{
 				total += res.cnt[s];
-		rc = make_recv(m, send, total, recv);
+				if (res.cnt[s] > 0)
+					anynull |= (unsigned long long) res.sent[s];
+			}
+		rc = cbgpu_rel_create(ctx, total, send->ncols, send->types, send->dscales, recv);
+		for (int c = 0; c < send->ncols && rc == CBGPU_OK; c++)
+		{
+			if ((anynull >> c) & 1)
+				rc = cbgpu_rel_add_nullmap(*recv, c);	/* zero-filled: senders without a map for it sent no NULLs */
+			if (send->dict_hash[c])
+				cbgpu_rel_share_dict_hash(*recv, c, send, c);
+		}
 		if (rc)
 		{
 			dx_release(m);
@@ -1125,21 +1155,38 @@ gather_direct(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_r
 			{
 				CopyCols	cc;
 				size_t		o = 0;
+				int			parts = 0;
 
 				if (res.cnt[s] == 0)
 					continue;
+				/* every sender laid its slot out with ITS row count and ITS NULL maps */
 				for (int c = 0; c < send->ncols; c++)
 				{
 					const size_t w = (size_t) cb_type_w(send->types[c]);
 
-					/* every sender laid its columns out with ITS row count */
-					cc.dst[c] = (char *) (*recv)->data[c] + (size_t) at * w;
-					cc.src[c] = m->win + buf + GX_HDR + (size_t) s * slot + o;
-					cc.bytes[c] = (size_t) res.cnt[s] * w;
-					o += ((size_t) res.cnt[s] * w + DX_ALIGN - 1) / DX_ALIGN * DX_ALIGN;
+					cc.dst[parts] = (char *) (*recv)->data[c] + (size_t) at * w;
+					cc.src[parts] = m->win + buf + GX_HDR + (size_t) s * slot + o;
+					cc.bytes[parts] = (size_t) res.cnt[s] * w;
+					o += gx_pad(cc.bytes[parts]);
+					parts++;
 				}
-				k_copy_cols<<<send->ncols, 256, 0, ctx->stream>>>(cc);
+				k_copy_cols<<<parts, 256, 0, ctx->stream>>>(cc);
 				CB_LAUNCHED(ctx, "k_copy_cols");
+				parts = 0;
+				for (int c = 0; c < send->ncols; c++)
+					if (((unsigned long long) res.sent[s] >> c) & 1)
+					{
+						cc.dst[parts] = (char *) (*recv)->nulls[c] + (size_t) at;
+						cc.src[parts] = m->win + buf + GX_HDR + (size_t) s * slot + o;
+						cc.bytes[parts] = (size_t) res.cnt[s];
+						o += gx_pad(cc.bytes[parts]);
+						parts++;
+					}
+				if (parts)
+				{
+					k_copy_cols<<<parts, 256, 0, ctx->stream>>>(cc);
+					CB_LAUNCHED(ctx, "k_copy_cols");
+				}
 				at += res.cnt[s];
 			}
 		}

@@ -63,8 +63,12 @@ def _rel(name, cols, dict_texts=None):
     return HostRelation(name, names, types, [cols[n] for n in names], dscales=[0] * len(names), dict_texts=dt)
 
 
-def gen_tables(sf, hashfn, seed=7):
+def gen_tables(sf, hashfn, seed=7, fact=True):
+    """fact=False: the four dimensions only, lineorder as an empty relation (bench.py generates the fact table on the
+    device, csrc/gen.cu cbgpu_gen_ssb_lineorder: the same formulas)"""
     sz = sizes(sf)
+    if not fact:
+        sz = dict(sz, lineorder=0)
     dk, dy = _dates()
     i = np.arange(sz["customer"], dtype=np.int64)
     c_city = (_u(seed, 21, i) % np.uint64(250)).astype(np.int32)
@@ -145,10 +149,22 @@ def _star(dims, group, nsegs=1, num_groups=1000):
     profit = P.OpExpr(P.OP_SUB, v("lo_revenue"), v("lo_supplycost"))
     targets = [(g, v(g)) for g in group] + [("profit", P.Aggref(P.AGG_SUM, profit))]
     # grpColIdx: the group keys' positions in the child's target list (plannodes.h:1342 Agg.grpColIdx)
-    return P.Agg(cur, P.AGG_HASHED, P.AGGSPLIT_SIMPLE, [carried.index(g) + 1 for g in group], targets, num_groups=num_groups)
+    grp = [carried.index(g) + 1 for g in group]
+    if nsegs == 1:
+        return P.Agg(cur, P.AGG_HASHED, P.AGGSPLIT_SIMPLE, grp, targets, num_groups=num_groups)
+    # lineorder distributed, dimensions replicated: Gather Motion <- Finalize HashAggregate <- Redistribute Motion (group
+    # keys) <- Partial HashAggregate <- the star join (the two-stage shape of expected/aggregates.out:3313-3328)
+    partial = P.Agg(cur, P.AGG_HASHED, P.AGGSPLIT_INITIAL_SERIAL, grp, targets, num_groups=num_groups, streaming=True)
+    nk = len(group)
+    redist = P.Motion(partial, P.MOTIONTYPE_HASH, [P.out_var(partial, k + 1) for k in range(nk)], nsegs)
+    t, ds = P.out_type(redist, nk + 1)
+    final = P.Agg(redist, P.AGG_HASHED, P.AGGSPLIT_FINAL_DESERIAL, list(range(1, nk + 1)),
+                  [(g, P.out_var(redist, k + 1)) for k, g in enumerate(group)] +
+                  [("profit", P.Aggref(P.AGG_SUM, P.OuterVar(nk + 1, t, ds), restype=P.NUMERIC, dscale=0))], num_groups=num_groups)
+    return P.Motion(final, P.MOTIONTYPE_GATHER)
 
 
-def q4_1_plan():
+def q4_1_plan(nsegs=1):
     """select d_year, c_nation, sum(lo_revenue - lo_supplycost) ... where c_region = 'AMERICA' and
     s_region = 'AMERICA' and (p_mfgr = 'MFGR#1' or p_mfgr = 'MFGR#2') group by d_year, c_nation"""
     am = REGIONS.index("AMERICA")
@@ -157,10 +173,10 @@ def q4_1_plan():
         ("customer", "c_custkey", "lo_custkey", ["c_nation"], [_eq("customer", "c_region", am)]),
         ("part", "p_partkey", "lo_partkey", [], [_in("part", "p_mfgr", [0, 1])]),
         ("date", "d_datekey", "lo_orderdate", ["d_year"], []),
-    ], ["d_year", "c_nation"], num_groups=200)
+    ], ["d_year", "c_nation"], nsegs=nsegs, num_groups=200)
 
 
-def q4_2_plan():
+def q4_2_plan(nsegs=1):
     """... where c_region = 'AMERICA' and s_region = 'AMERICA' and (d_year = 1997 or d_year = 1998) and
     (p_mfgr = 'MFGR#1' or p_mfgr = 'MFGR#2') group by d_year, s_nation, p_category"""
     am = REGIONS.index("AMERICA")
@@ -169,10 +185,10 @@ def q4_2_plan():
         ("customer", "c_custkey", "lo_custkey", [], [_eq("customer", "c_region", am)]),
         ("part", "p_partkey", "lo_partkey", ["p_category"], [_in("part", "p_mfgr", [0, 1])]),
         ("date", "d_datekey", "lo_orderdate", ["d_year"], [_in("date", "d_year", [1997, 1998])]),
-    ], ["d_year", "s_nation", "p_category"], num_groups=500)
+    ], ["d_year", "s_nation", "p_category"], nsegs=nsegs, num_groups=500)
 
 
-def q4_3_plan():
+def q4_3_plan(nsegs=1):
     """... where s_nation = 'UNITED STATES' and (d_year = 1997 or d_year = 1998) and p_category = 'MFGR#14'
     group by d_year, s_city, p_brand1"""
     return _star([
@@ -180,7 +196,7 @@ def q4_3_plan():
         ("part", "p_partkey", "lo_partkey", ["p_brand1"], [_eq("part", "p_category", CATEGORIES.index("MFGR#14"))]),
         ("date", "d_datekey", "lo_orderdate", ["d_year"], [_in("date", "d_year", [1997, 1998])]),
         ("customer", "c_custkey", "lo_custkey", [], []),
-    ], ["d_year", "s_city", "p_brand1"], num_groups=2000)
+    ], ["d_year", "s_city", "p_brand1"], nsegs=nsegs, num_groups=2000)
 
 
 PLANS = {"q4.1": q4_1_plan, "q4.2": q4_2_plan, "q4.3": q4_3_plan}
@@ -219,3 +235,28 @@ def numpy_answer(q, rels):
 
 def canon(rows):
     return sorted([[int(x) if not isinstance(x, str) else x for x in r[:-1]] + [str(r[-1])] for r in rows])
+
+
+# projected bytes per row of every table Q4.x scans: lineorder custkey 4 + suppkey 4 + partkey 4 + orderdate 4
+# + revenue 8 + supplycost 8; the dimensions' key + attribute columns
+QUERY_BYTES = {"lineorder": 32, "customer": 10, "supplier": 10, "part": 10, "date": 8}
+
+
+def query_rows_bytes(sz):
+    return sum(sz[t] for t in QUERY_BYTES), sum(sz[t] * w for t, w in QUERY_BYTES.items())
+
+
+def device_tables(ctx, sf, hashfn, rank=0, world=1, seed=7):
+    """The SSB database on this GPU-segment: the dimensions whole (DISTRIBUTED REPLICATED), rows [rank * n / world,
+    (rank + 1) * n / world) of lineorder (any distribution is valid for a star join against replicated dimensions),
+    generated on the device."""
+    from . import capi
+    sz = sizes(sf)
+    host = gen_tables(sf, hashfn, seed=seed, fact=False)
+    n = sz["lineorder"]
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    fact = capi.DeviceRelation(ctx, hi - lo, [t for _, t in SCHEMA["lineorder"]], dscales=[0] * 6, name="lineorder")
+    ctx.check(ctx.L.cbgpu_gen_ssb_lineorder(ctx.h, fact.h, seed, lo, sz["customer"], sz["part"], sz["supplier"]))
+    dev = [fact] + [capi.DeviceRelation.from_host(ctx, r) for r in host[1:]]
+    ctx.sync()
+    return dev, sz

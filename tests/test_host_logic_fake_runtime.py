@@ -131,8 +131,11 @@ def test_bench_main_arm_control_flow(fake):
     assert p.returncode == 0 and len(lines) == 1, (p.stdout[-2000:], p.stderr[-3000:])
     line = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-                "dtype", "data", "config", "roofline", "clocks", "gpu_launches", "e2e", "q3", "q5"):
+                "dtype", "data", "config", "roofline", "clocks", "gpu_launches", "e2e", "q3", "q5", "ssb", "result_check"):
         assert key in line, key
+    # no golden rows exist for SF0.05: the line says so instead of claiming a check
+    assert line["result_check"].startswith("unchecked") and line["q3"]["result_check"].startswith("unchecked")
+    assert set(line["ssb"]["queries"]) == {"q4.1", "q4.2", "q4.3"}
     assert line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 3 and line["unit"] == "rows/s"
     assert line["gpu_launches"] > 0 and "impl" not in line and "cpu_baseline" not in line
     rows = line["config"]["rows_per_gpu"]
@@ -140,6 +143,26 @@ def test_bench_main_arm_control_flow(fake):
     assert line["e2e"]["h2d_bytes_per_step"] == 38 * rows and line["e2e"]["unit"] == "rows/s"
     for q in ("q3", "q5"):
         assert line[q]["gpu_launches_per_step"] > 0 and line[q]["roofline"]["algorithmic_bytes"] > 0
+
+
+def test_bench_result_check_bites(fake, tmp_path):
+    """with golden rows for the configuration at hand, a run whose kernels compute nothing must FAIL: bench.py prints its line with
+    result_check = MISMATCH and exits 1"""
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_bench_golden as G
+    _, so = fake
+    with mp.Pool(2) as pool:
+        gold = {"q1_sf0.05": G.run_q1(pool, 0.05, 1), "q3_sf0.05": G.run_q3(pool, 0.05), "q5_sf0.05": G.run_q5(pool, 0.05)}
+    path = tmp_path / "gold.json"
+    path.write_text(json.dumps(gold))
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--sf", "0.05", "--steps", "2", "--warmup", "3", "--no-cpu", "--no-e2e", "--no-ssb"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, LD_PRELOAD=so, CBGPU_BENCH_GOLDEN=str(path)), cwd=ROOT)
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert p.returncode == 1 and len(lines) == 1, (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
+    line = json.loads(lines[0])
+    assert line["result_check"].startswith("MISMATCH") and line["q5"]["result_check"].startswith("MISMATCH")
+    assert "result_check FAILED" in p.stderr
 
 
 def test_smoke_cannot_pass_without_real_kernels(fake):
