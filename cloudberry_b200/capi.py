@@ -198,7 +198,8 @@ class CbEState(C.Structure):
     _fields_ = [("es_ctx", C.c_void_p), ("es_nrels", C.c_int32), ("es_range_table", C.POINTER(C.c_void_p)),
                 ("es_segindex", C.c_int32), ("es_numsegments", C.c_int32), ("es_interconnect", C.c_void_p),
                 ("es_errcode", C.c_int32), ("es_errmsg", C.c_char * 512), ("es_error_hook", C.c_void_p),
-                ("es_force_generic", C.c_int32), ("es_processed", C.c_int64), ("es_cluster", C.c_void_p)]
+                ("es_force_generic", C.c_int32), ("es_processed", C.c_int64), ("es_cluster", C.c_void_p),
+                ("es_interrupt_pending", C.c_void_p), ("es_interrupt_arg", C.c_void_p), ("es_operator_mem_kb", C.c_int64)]
 
 
 def header_symbols(header):
@@ -238,7 +239,7 @@ def _preload_bundled_nccl():
 def gpu():
     global _GPU
     if _GPU is None:
-        so = os.path.join(HERE, "libcbgpu.so")
+        so = os.path.join(os.environ.get("CBGPU_LIBDIR") or HERE, "libcbgpu.so")     # CBGPU_LIBDIR: an experimental build (tools/)
         if not os.path.exists(so):
             raise CbgpuError(-1, "libcbgpu.so is not built (run __graft_entry__.build()); there is no CPU fallback")
         _preload_bundled_nccl()
@@ -327,7 +328,7 @@ def ex():
     global _EXEC
     if _EXEC is None:
         gpu()
-        so = os.path.join(HERE, "libcbexec.so")
+        so = os.path.join(os.environ.get("CBGPU_LIBDIR") or HERE, "libcbexec.so")
         if not os.path.exists(so):
             raise CbgpuError(-1, "libcbexec.so is not built (run __graft_entry__.build())")
         L = C.CDLL(so)

@@ -14,6 +14,9 @@
 
 #include "../../include/cbgpu.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 #define CB_MAX_COLS_REL 64
 
 struct cbgpu_ctx
@@ -46,7 +49,42 @@ struct cbgpu_ctx
 	int64_t		status_seen_at;	/* ctx->launches when h_status was last fetched (-1: never): every
 								 * synchronising read-back fetches the status word too, so the check
 								 * after it costs no second round trip                                 */
+	/* environment knobs, read ONCE when the context is created - not per launch */
+	bool		opt_debug, opt_no_early_filter, opt_no_keyslot, opt_no_fuse0, opt_no_spec0, opt_no_smem_ht, opt_l2_direct;
+	int			opt_bloom_div;
+	int			opt_htb_u;		/* rows a hash-build thread keeps in flight (CBGPU_HTB_U: 1, 2, 4)          */
+	/* host-side scratch of the launch path (decompiled programs, kernel parameter blocks: too large for the
+	 * stack), owned by the context so that two contexts on two threads never share any: slot -> malloc'ed block */
+#define CB_SCRATCH_SLOTS 8
+	void	   *scratch[CB_SCRATCH_SLOTS];
+	size_t		scratch_bytes[CB_SCRATCH_SLOTS];
+	/* scan-level runtime filter decisions, remembered per (build relation, rows, key column): the sample that
+	 * decides "worth building" costs a host round trip, the answer does not change while the table does not */
+#define CB_EARLY_CACHE 16
+	struct
+	{
+		const void *keydata;
+		int64_t		nrows;
+		const void *red0;
+		int			worth;
+	}			early_cache[CB_EARLY_CACHE];
+	int			early_cache_n;
 };
+
+/* zero-filled scratch block `slot` of at least `bytes` (grown on demand, freed with the context) */
+static inline void *
+cb_scratch(cbgpu_ctx *ctx, int slot, size_t bytes)
+{
+	if (ctx->scratch_bytes[slot] < bytes)
+	{
+		free(ctx->scratch[slot]);
+		ctx->scratch[slot] = malloc(bytes);
+		ctx->scratch_bytes[slot] = ctx->scratch[slot] ? bytes : 0;
+	}
+	if (ctx->scratch[slot])
+		memset(ctx->scratch[slot], 0, bytes);
+	return ctx->scratch[slot];
+}
 
 struct cbgpu_rel
 {
@@ -92,6 +130,11 @@ struct cbgpu_aggtable
 	int32_t		anynull;
 };
 
+#ifdef __CUDACC__
+#define CB_HD_DECL __host__ __device__ __forceinline__
+#else
+#define CB_HD_DECL static inline
+#endif
 /* join hash table, device view: slot = hash32 << 32 | rowid32, EMPTY = ~0 */
 #define HT_EMPTY 0xFFFFFFFFFFFFFFFFull
 struct HtDev
@@ -109,7 +152,20 @@ struct HtDev
 	const uint8_t *keynulls[CBP_MAX_KEYS];
 	const uint32_t *keydict[CBP_MAX_KEYS];
 	int32_t		keytype[CBP_MAX_KEYS];
+	/* key-in-slot tables: one integer key whose every build value fits 32 bits is stored IN the slot's upper
+	 * word instead of the hash value (slot = key32 << 32 | rowid32), so a probe settles a match on the slot
+	 * alone - no second random access to the build side's key column.  1: the int32 domain (int4 / date /
+	 * dictionary codes, and int8 keys between INT32_MIN and INT32_MAX are not used: see 2), 2: the uint32 domain
+	 * (int8 keys in [0, 2^32): TPC-H order keys up to SF 1000).  0: hash in the slot, key verified by row id. */
+	int32_t		keyslot;
 };
+
+/* is an outer key value inside a key-in-slot table's domain?  Outside it nothing can match. */
+CB_HD_DECL bool
+ht_key_in_domain(int32_t keyslot, int64_t key)
+{
+	return keyslot == 1 ? key == (int64_t) (int32_t) key : (uint64_t) key <= 0xFFFFFFFFull;
+}
 
 struct cbgpu_hashtable
 {
@@ -376,6 +432,53 @@ pg_hash_datum(int type, int64_t v, const uint32_t *dict)
 	}
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * hash of a join key for the device's OWN structures: join hash tables, their Bloom filters, the scan-level
+ * runtime filters.  Which slot a key lands in is not observable from outside (the reference's bucket number,
+ * nodeHash.c:2233, is not either), so these do not pay for the reference's lookup3 mix (hash_bytes_uint32,
+ * common/hashfn.c:627: ~22 dependent integer operations, a quarter of the join pipeline's instructions when
+ * measured): a two-multiply finaliser instead.  Everything observable keeps the reference's functions bit
+ * for bit - Motion placement (cdbhash, pg_hash_datum above) and the group hash (TupleHashTableHash).
+ * int8 keys fold their halves the way hashint8 does, so an int4 key and an int8 key of equal value still meet
+ * (cross-type joins).
+ * --------------------------------------------------------------------------------------------- */
+CB_HD uint32_t
+jh_mix32(uint32_t x)
+{
+	x ^= x >> 16;
+	x *= 0x7feb352du;
+	x ^= x >> 15;
+	x *= 0x846ca68bu;
+	x ^= x >> 16;
+	return x;
+}
+
+CB_HD uint32_t
+jh_int8(int64_t val)
+{
+	uint32_t	lohalf = (uint32_t) val;
+	const uint32_t hihalf = (uint32_t) ((uint64_t) val >> 32);
+
+	lohalf ^= (val >= 0) ? hihalf : ~hihalf;
+	return jh_mix32(lohalf);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t
+jh_hash_datum(int type, int64_t v, const uint32_t *dict)
+{
+	switch (type)
+	{
+		case CB_INT4: case CB_DATE:
+			return jh_mix32((uint32_t) (int32_t) v);
+		case CB_INT8:
+			return jh_int8(v);
+		default:
+			return pg_hash_datum(type, v, dict);	/* dictionary codes: the per-code table; bpchar(1), bool */
+	}
+}
+#endif
+
 /* Bloom word index and bit pattern of a 32-bit key hash: two multiplicative remixes, the word from
  * the top bits of one, the two bit positions from the top bits of the other */
 CB_HD uint32_t
@@ -454,6 +557,56 @@ ldg_stream_u64(const unsigned long long *a, uint64_t pol)
 	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
 	return v;
 }
+#endif
+
+#ifdef __CUDACC__
+/* ---- TMA bulk-copy pipeline primitives (sm_90+ PTX; SASS: UBLKCP / SYNCS) ---- */
+__device__ __forceinline__ uint32_t
+smem_u32(const void *p)
+{
+	return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void
+mbar_init(uint64_t *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void
+mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_wait(uint64_t *bar, unsigned parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+/* one contiguous global -> shared bulk copy, completion counted in bytes on `bar` */
+__device__ __forceinline__ void
+tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 #endif
 
 /* widen a column element to 64 bits (float8: raw bits) */

@@ -8,6 +8,8 @@
  */
 #include "common.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <stdlib.h>
 
 extern "C" int
@@ -51,6 +53,15 @@ cbgpu_ctx_create(int device, cbgpu_ctx **out)
 	CB_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
 	CB_CUDA(ctx, cudaMallocHost(&ctx->h_status, sizeof(int)));
 	*ctx->h_status = 0;
+	ctx->opt_debug = getenv("CBGPU_DEBUG") != NULL;
+	ctx->opt_no_early_filter = getenv("CBGPU_NO_EARLY_FILTER") != NULL;
+	ctx->opt_no_keyslot = getenv("CBGPU_NO_KEYSLOT") != NULL;
+	ctx->opt_no_fuse0 = getenv("CBGPU_NO_FUSE0") != NULL;
+	ctx->opt_no_spec0 = getenv("CBGPU_SPEC0") == NULL;	/* measured: loading probe 0's keys with the qual columns loses (Q3 3.49 vs 3.18 ms) */
+	ctx->opt_no_smem_ht = getenv("CBGPU_NO_SMEM_HT") != NULL;
+	ctx->opt_l2_direct = getenv("CBGPU_L2_DIRECT") != NULL;
+	ctx->opt_htb_u = getenv("CBGPU_HTB_U") && atoi(getenv("CBGPU_HTB_U")) > 0 ? atoi(getenv("CBGPU_HTB_U")) : 1;
+	ctx->opt_bloom_div = getenv("CBGPU_BLOOM_DIV") && atoi(getenv("CBGPU_BLOOM_DIV")) > 0 ? atoi(getenv("CBGPU_BLOOM_DIV")) : 2;
 	/* L2 is 126 MB on B200: flush buffer comfortably larger */
 	ctx->flush_bytes = (size_t) 512 << 20;
 	ctx->flush_buf = NULL;
@@ -68,6 +79,8 @@ cbgpu_ctx_destroy(cbgpu_ctx *ctx)
 		cudaFree(ctx->flush_buf);
 	cudaFree(ctx->d_status);
 	cudaFreeHost(ctx->h_status);
+	for (int i = 0; i < CB_SCRATCH_SLOTS; i++)
+		free(ctx->scratch[i]);
 	cudaEventDestroy(ctx->ev_t0);
 	cudaEventDestroy(ctx->ev_t1);
 	cudaEventDestroy(ctx->ev_k0);
@@ -80,6 +93,18 @@ extern "C" const char *
 cbgpu_last_error(cbgpu_ctx *ctx)
 {
 	return ctx ? ctx->err : "no context";
+}
+
+extern "C" void
+cbgpu_range_push(const char *name)
+{
+	nvtxRangePushA(name);
+}
+
+extern "C" void
+cbgpu_range_pop(void)
+{
+	nvtxRangePop();
 }
 
 extern "C" int

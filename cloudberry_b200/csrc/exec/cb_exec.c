@@ -735,6 +735,8 @@ stream_is_plain(const CbStream *s, cbgpu_rel **rel)
  * node_open: build (and, at pipeline breakers, run) a node's output stream
  * ------------------------------------------------------------------------------------------ */
 static int	node_open(CbPlanState *ps, CbStream **out);
+static int	node_open_inner(CbPlanState *ps, CbStream **out);
+static const char *node_name(CbNodeTag t);
 static int	cluster_run_motion(CbPlanState *ps);
 static int	open_limitsort(CbPlanState *ps, CbStream **out);
 
@@ -966,11 +968,19 @@ open_hashjoin(CbPlanState *ps, CbStream **out)
 			pr->keytype[k] = kx->type == CB_NUMERIC ? CB_INT8 : kx->type;
 			if (kx->type == CB_NUMERIC)
 				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "numeric join keys (hash_numeric) are not on the GPU path");
+			if (kx->type == CB_FLOAT8)
+				/* float8eq makes -0 = +0 and every NaN equal (hashfloat8 maps them to one hash value, hashfunc.c:194); the
+				 * tables compare key bits */
+				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "float8 join keys are not on the GPU path");
 			if (kx->type == CB_DICT8 || kx->type == CB_DICT32)
 			{
 				if (kx->kind != PE_COL || !s->pipe.cols[kx->col].dict_hash)
 					return es_fail(es, CBGPU_ERR_INVALID, "dictionary join key without per-code hashes");
 				pr->key_dict_hash[k] = s->pipe.cols[kx->col].dict_hash;
+				/* codes are compared, so both sides must be coded by ONE dictionary (cbgpu.h: a dictionary can be shared
+				 * between columns that are joined); two private dictionaries would silently lose matches */
+				if (cbgpu_ht_key_dict_hash(hp->ht, k) != pr->key_dict_hash[k])
+					return es_fail(es, CBGPU_ERR_UNSUPPORTED, "join of dictionary columns coded by two different dictionaries (share one dictionary between the columns)");
 			}
 		}
 		s->pipe.nprobes = j + 1;
@@ -2000,6 +2010,48 @@ node_open(CbPlanState *ps, CbStream **out)
 		*out = p->stream;
 		return CBGPU_OK;
 	}
+	/* CHECK_FOR_INTERRUPTS, once per node = before every pipeline of the query */
+	if (ps->state->es_interrupt_pending && ps->state->es_interrupt_pending(ps->state))
+	{
+		CbInterconnect *ic = ps->state->es_cluster ? NULL : ps->state->es_interconnect;
+
+		/* a Motion this segment will not enter: the peers must not wait for it */
+		if (ps->type == T_CbMotion && ic && ic->abandon && ps->state->es_numsegments > 1 && p->xstage < 2)
+		{
+			ic->abandon(ic, ps->state, ((CbMotion *) ps->plan)->motionID, p->xstage == 1);
+			p->xstage = 2;
+		}
+		return es_fail(ps->state, CBGPU_ERR_INTERRUPTED, "canceling statement due to user request");
+	}
+	cbgpu_range_push(node_name(ps->type));
+	{
+		int			rc = node_open_inner(ps, out);
+
+		cbgpu_range_pop();
+		return rc;
+	}
+}
+
+static const char *
+node_name(CbNodeTag t)
+{
+	switch (t)
+	{
+		case T_CbSeqScan: return "SeqScan";
+		case T_CbHash: return "Hash";
+		case T_CbHashJoin: return "HashJoin";
+		case T_CbAgg: return "Agg";
+		case T_CbMotion: return "Motion";
+		case T_CbLimitSort: return "Limit/Sort";
+		default: return "node";
+	}
+}
+
+static int
+node_open_inner(CbPlanState *ps, CbStream **out)
+{
+	NodePriv   *p = np(ps);
+
 	switch (ps->type)
 	{
 		case T_CbSeqScan:

@@ -509,8 +509,11 @@ cb_tupser_next(const CbTupAttr *attrs, int natts, const unsigned char *in, int64
 		n = (body[0] | (body[1] << 8)) & 0x07FF;	/* HEAP_NATTS_MASK */
 		hasnull = body[2] & HEAP_HASNULL;
 		hoff = body[4];
-		if (n != natts || hoff < HTUP_BITS_OFF || hoff - HTUP_BODY_OFF > bodylen)
+		if (n != natts || hoff < HTUP_BITS_OFF || hoff - HTUP_BODY_OFF > bodylen ||
+			(hasnull && hoff < HTUP_BITS_OFF + (natts + 7) / 8))
 		{
+			/* with HEAP_HASNULL the header must cover the whole NULL bitmap: a short tuple claiming many attributes would
+			 * otherwise be read beyond its body (heap_form_minimal_tuple: t_hoff = MAXALIGN(offsetof(t_bits) + BITMAPLEN)) */
 			free(buf);
 			return CB_TUPSER_BAD;
 		}

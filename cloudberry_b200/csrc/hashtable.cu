@@ -21,11 +21,11 @@ struct BuildParams
 {
 	HtDev		ht;
 	int64_t		nrows;
-	int		   *flags;			/* [0] duplicate key seen, [1] rows inserted                          */
+	int		   *flags;			/* [0] duplicate key seen, [1] rows inserted, [2] a key outside the key-in-slot domain */
 };
 
 __device__ __forceinline__ bool
-ht_row_hash(const HtDev &ht, uint32_t row, uint32_t *hash)
+ht_row_hash(const HtDev &ht, uint32_t row, uint32_t *hash, int64_t *key0)
 {
 	uint32_t	h = 0;
 
@@ -35,7 +35,9 @@ ht_row_hash(const HtDev &ht, uint32_t row, uint32_t *hash)
 			return false;
 		int64_t		v = cb_load_widen(ht.keydata[k], ht.keytype[k], row);
 
-		h = pg_hash_combine(h, pg_hash_datum(ht.keytype[k], v, ht.keydict[k]), false);
+		if (k == 0)
+			*key0 = v;
+		h = pg_hash_combine(h, jh_hash_datum(ht.keytype[k], v, ht.keydict[k]), false);
 	}
 	*hash = h;
 	return true;
@@ -60,52 +62,83 @@ k_ht_clear(unsigned long long *slots, size_t n)
 		slots[i] = HT_EMPTY;
 }
 
+/* U rows of a thread in flight: their key loads, then their filter words, then their first slots are issued back to back
+ * (a row's chain key -> filter word -> slot -> compare-and-swap is four dependent memory operations, the table rarely fits L2) */
+template <int HTB_U>
 __global__ void __launch_bounds__(256)
 k_ht_build(BuildParams p)
 {
-	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	int64_t		stride = (int64_t) gridDim.x * blockDim.x;
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
 	int			inserted = 0;
 	bool		dup = false;
+	bool		outside = false;
 
-	for (; i < p.nrows; i += stride)
+	for (int64_t i0 = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i0 < p.nrows; i0 += stride * HTB_U)
 	{
-		uint32_t	row = (uint32_t) i;
-		uint32_t	h;
+		uint32_t	h[HTB_U], pos[HTB_U], w[HTB_U], bits[HTB_U], word[HTB_U];
+		unsigned long long cur[HTB_U], e[HTB_U];
+		bool		v[HTB_U];
 
-		if (!ht_row_hash(p.ht, row, &h))
-			continue;
-		unsigned long long e = ((unsigned long long) h << 32) | row;
-		uint32_t	pos = h & p.ht.mask;
+#pragma unroll
+		for (int u = 0; u < HTB_U; u++)
+		{
+			const int64_t i = i0 + (int64_t) u * stride;
+			int64_t		key0 = 0;
 
+			h[u] = 0;
+			v[u] = i < p.nrows && ht_row_hash(p.ht, (uint32_t) i, &h[u], &key0);
+			if (v[u] && p.ht.keyslot && !ht_key_in_domain(p.ht.keyslot, key0))
+			{
+				outside = true;		/* the host builds the table again with hash values in the slots */
+				v[u] = false;
+			}
+			e[u] = ((unsigned long long) (p.ht.keyslot ? (uint32_t) key0 : h[u]) << 32) | (uint32_t) i;
+			pos[u] = h[u] & p.ht.mask;
+			bits[u] = ht_bloom_bits(h[u], &w[u], p.ht.bloom_mask);
+		}
 		if (p.ht.bloom)
 		{
-			uint32_t	w;
-			uint32_t	bits = ht_bloom_bits(h, &w, p.ht.bloom_mask);
-
-			if ((p.ht.bloom[w] & bits) != bits)
-				atomicOr(p.ht.bloom + w, bits);
+#pragma unroll
+			for (int u = 0; u < HTB_U; u++)
+				word[u] = v[u] ? p.ht.bloom[w[u]] : 0xFFFFFFFFu;
+#pragma unroll
+			for (int u = 0; u < HTB_U; u++)
+				if ((word[u] & bits[u]) != bits[u])
+					atomicOr(p.ht.bloom + w[u], bits[u]);
 		}
-
-		for (;;)
+#pragma unroll
+		for (int u = 0; u < HTB_U; u++)
+			cur[u] = v[u] ? p.ht.slots[pos[u]] : 0;
+#pragma unroll
+		for (int u = 0; u < HTB_U; u++)
 		{
-			unsigned long long cur = p.ht.slots[pos];
-
-			if (cur == HT_EMPTY)
+			if (!v[u])
+				continue;
+			for (;;)
 			{
-				cur = atomicCAS(p.ht.slots + pos, HT_EMPTY, e);
-				if (cur == HT_EMPTY)
-					break;
+				unsigned long long c = cur[u];
+
+				if (c == HT_EMPTY)
+				{
+					c = atomicCAS(p.ht.slots + pos[u], HT_EMPTY, e[u]);
+					if (c == HT_EMPTY)
+						break;
+				}
+				/* occupied: the same key -> a duplicate on the build side (key-in-slot tables see it in the slot; the others
+				 * compare hash values first, then the keys by row id) */
+				if (!dup && (uint32_t) (c >> 32) == (uint32_t) (e[u] >> 32) &&
+					(p.ht.keyslot || ht_keys_equal_rows(p.ht, (uint32_t) c, (uint32_t) e[u])))
+					dup = true;
+				pos[u] = (pos[u] + 1) & p.ht.mask;
+				cur[u] = p.ht.slots[pos[u]];
 			}
-			/* occupied: same hash value -> maybe the same key (a duplicate on the build side) */
-			if ((uint32_t) (cur >> 32) == h && !dup && ht_keys_equal_rows(p.ht, (uint32_t) cur, row))
-				dup = true;
-			pos = (pos + 1) & p.ht.mask;
+			inserted++;
 		}
-		inserted++;
 	}
 	if (dup)
 		atomicExch(p.flags, 1);
+	if (outside)
+		atomicExch(p.flags + 2, 1);
 	/* one atomic per warp for the inserted count */
 	for (int o = 16; o; o >>= 1)
 		inserted += __shfl_xor_sync(0xffffffffu, inserted, o);
@@ -119,7 +152,7 @@ cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t
 	cbgpu_hashtable *ht;
 	int64_t		nslots = 64;
 	BuildParams p;
-	int			h_flags[2];
+	int			h_flags[3];
 
 	if (nkeys < 1 || nkeys > CBP_MAX_KEYS)
 		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "hash join with %s%lld key columns is beyond the GPU path's limit (4)", "", nkeys);
@@ -161,12 +194,24 @@ cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t
 	}
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
 	CB_CUDA(ctx, cudaMallocAsync(&ht->d.slots, (size_t) nslots * sizeof(unsigned long long), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&ht->d_flags, 2 * sizeof(int), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&ht->d_flags, 3 * sizeof(int), ctx->stream));
+	/* one integer key: try the key-in-slot layout (int8 keys: as long as every build value lies in [0, 2^32)) */
+	if (nkeys == 1 && !ctx->opt_no_keyslot)
+		switch (ht->d.keytype[0])
+		{
+			case CB_INT8:
+				ht->d.keyslot = 2;
+				break;
+			case CB_INT4: case CB_DATE: case CB_DICT8: case CB_DICT32: case CB_BPCHAR1: case CB_BOOL:
+				ht->d.keyslot = 1;
+				break;
+			default:
+				break;
+		}
 	{
 		/* ~16 filter bits per build row, at least one cache line */
 		int64_t		words = 32;
-		const char *env = getenv("CBGPU_BLOOM_DIV");	/* rows per 32-bit filter word (tuning aid), default 2 */
-		int			div = env && atoi(env) > 0 ? atoi(env) : 2;
+		const int	div = ctx->opt_bloom_div;	/* rows per 32-bit filter word (CBGPU_BLOOM_DIV, tuning aid), default 2 */
 
 		while (words < inner->nrows / div)
 			words <<= 1;
@@ -174,26 +219,45 @@ cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t
 		CB_CUDA(ctx, cudaMemsetAsync(ht->d.bloom, 0, (size_t) words * sizeof(uint32_t), ctx->stream));
 		ht->d.bloom_mask = (uint32_t) (words - 1);
 	}
-	CB_CUDA(ctx, cudaMemsetAsync(ht->d_flags, 0, 2 * sizeof(int), ctx->stream));
-	int			blocks = (int) ((nslots + 255) / 256);
-
-	if (blocks > ctx->sm_count * 8)
-		blocks = ctx->sm_count * 8;
-	k_ht_clear<<<blocks, 256, 0, ctx->stream>>>(ht->d.slots, (size_t) nslots);
-	CB_LAUNCHED(ctx, "k_ht_clear");
-	p.ht = ht->d;
-	p.nrows = inner->nrows;
-	p.flags = ht->d_flags;
-	if (inner->nrows > 0)
+	for (;;)
 	{
-		blocks = (int) ((inner->nrows + 255) / 256);
+		int			blocks = (int) ((nslots + 255) / 256);
+
+		CB_CUDA(ctx, cudaMemsetAsync(ht->d_flags, 0, 3 * sizeof(int), ctx->stream));
 		if (blocks > ctx->sm_count * 8)
 			blocks = ctx->sm_count * 8;
-		k_ht_build<<<blocks, 256, 0, ctx->stream>>>(p);
-		CB_LAUNCHED(ctx, "k_ht_build");
+		k_ht_clear<<<blocks, 256, 0, ctx->stream>>>(ht->d.slots, (size_t) nslots);
+		CB_LAUNCHED(ctx, "k_ht_clear");
+		p.ht = ht->d;
+		p.nrows = inner->nrows;
+		p.flags = ht->d_flags;
+		if (inner->nrows > 0)
+		{
+			const int	u = ctx->opt_htb_u;
+
+			blocks = (int) ((inner->nrows + 256 * u - 1) / (256 * u));
+			if (blocks > ctx->sm_count * 8)
+				blocks = ctx->sm_count * 8;
+			if (u == 4)
+				k_ht_build<4><<<blocks, 256, 0, ctx->stream>>>(p);
+			else if (u == 2)
+				k_ht_build<2><<<blocks, 256, 0, ctx->stream>>>(p);
+			else
+				k_ht_build<1><<<blocks, 256, 0, ctx->stream>>>(p);
+			CB_LAUNCHED(ctx, "k_ht_build");
+		}
+		CB_CUDA(ctx, cudaMemcpyAsync(h_flags, ht->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream));
+		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if (h_flags[2] && ht->d.keyslot)
+		{
+			/* an int8 key beyond 32 bits: the general layout (hash value in the slot, key verified by row id) */
+			ht->d.keyslot = 0;
+			if (ht->d.bloom)
+				CB_CUDA(ctx, cudaMemsetAsync(ht->d.bloom, 0, ((size_t) ht->d.bloom_mask + 1) * sizeof(uint32_t), ctx->stream));
+			continue;
+		}
+		break;
 	}
-	CB_CUDA(ctx, cudaMemcpyAsync(h_flags, ht->d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, ctx->stream));
-	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	ht->has_dups = h_flags[0];
 	ht->ninserted = h_flags[1];
 	*out = ht;
@@ -223,6 +287,12 @@ extern "C" int
 cbgpu_ht_has_duplicates(const cbgpu_hashtable *ht)
 {
 	return ht->has_dups;
+}
+
+extern "C" const uint32_t *
+cbgpu_ht_key_dict_hash(const cbgpu_hashtable *ht, int32_t k)
+{
+	return (k >= 0 && k < ht->d.nkeys) ? ht->d.keydict[k] : NULL;
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -265,7 +335,7 @@ k_ht_probe_pairs(ProbeParams p)
 			if (p.onulls[k] && p.onulls[k][row])
 				isnull = true;
 			key[k] = cb_load_widen(p.okey[k], p.otype[k], row);
-			h = pg_hash_combine(h, pg_hash_datum(p.otype[k], key[k], p.odict[k]), false);
+			h = pg_hash_combine(h, jh_hash_datum(p.otype[k], key[k], p.odict[k]), false);
 		}
 		if (!isnull && p.ht.bloom)
 		{
@@ -275,6 +345,8 @@ k_ht_probe_pairs(ProbeParams p)
 			if ((__ldg(p.ht.bloom + w) & bits) != bits)
 				isnull = true;		/* certainly absent */
 		}
+		if (!isnull && p.ht.keyslot && !ht_key_in_domain(p.ht.keyslot, key[0]))
+			isnull = true;			/* outside the build side's key domain: no partner */
 		if (!isnull)
 		{
 			uint32_t	pos = h & p.ht.mask;
@@ -285,12 +357,12 @@ k_ht_probe_pairs(ProbeParams p)
 
 				if (e == HT_EMPTY)
 					break;
-				if ((uint32_t) (e >> 32) == h)
+				if ((uint32_t) (e >> 32) == (p.ht.keyslot ? (uint32_t) key[0] : h))
 				{
 					uint32_t	irow = (uint32_t) e;
 					bool		eq = true;
 
-					for (int k = 0; k < p.ht.nkeys; k++)
+					for (int k = 0; k < p.ht.nkeys && !p.ht.keyslot; k++)
 						if (cb_load_widen(p.ht.keydata[k], p.ht.keytype[k], irow) != key[k])
 							eq = false;
 					if (eq)

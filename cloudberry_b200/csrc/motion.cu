@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "../../include/cb_chan.h"
+
 /* control block at the start of every window: the device-side signalling of the direct exchanges.
  * Slot [s] of each array is written by rank s only (remote stores over NVLink / peer memory). */
 struct DxCtl
@@ -48,6 +50,10 @@ struct DxResult
 
 #define DX_TIMEOUT 0x8000u
 #define DX_CTL_BYTES 4096
+/* after the control block: the arena of the host packet channels (include/cb_chan.h; cbgpu_motion_chan_mem), then the
+ * direct exchanges' data area */
+#define CH_REGION_BYTES ((size_t) 8 << 20)
+#define DX_DATA0 (DX_CTL_BYTES + CH_REGION_BYTES)
 #define DX_TAB_COLS (64 * CBP_MAX_OUT)
 #define DX_TAB_WORDS (2 * DX_TAB_COLS + 64)
 #define DX_TAB_SLOTS 4
@@ -95,6 +101,7 @@ struct cbgpu_motion
 	int64_t		direct_exchanges;
 	int64_t		host_syncs;
 	int64_t		collectives;
+	cudaStream_t chan_stream;	/* the packet channels' copies: never queued behind the executor's kernels */
 };
 
 #define CB_NCCL(ctx, call) \
@@ -337,6 +344,9 @@ motion_window_teardown(cbgpu_motion *m)
 		cudaFree(m->d_flags);
 	if (m->h_res)
 		cudaFreeHost(m->h_res);
+	if (m->chan_stream)
+		cudaStreamDestroy(m->chan_stream);
+	m->chan_stream = NULL;
 	m->d_tab = m->h_tab = NULL;
 	m->d_flags = NULL;
 	m->h_res = NULL;
@@ -826,7 +836,7 @@ cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, 
 {
 	cbgpu_ctx  *ctx = m->ctx;
 	const int	n = m->nranks;
-	size_t		off = DX_CTL_BYTES;
+	size_t		off = DX_DATA0;
 	size_t		roww = 0;
 	size_t		avail;
 	int64_t		cap;
@@ -843,7 +853,7 @@ cbgpu_motion_direct_begin(cbgpu_motion *m, int32_t ncols, const int32_t *types, 
 	 * divided by the row width, one NULL byte per column and row included */
 	for (int c = 0; c < ncols; c++)
 		roww += (size_t) cb_type_w(types[c]) + 1;
-	avail = m->win_bytes - DX_CTL_BYTES - 2 * GX_BYTES - (size_t) (2 * ncols) * DX_ALIGN;
+	avail = m->win_bytes - DX_DATA0 - 2 * GX_BYTES - (size_t) (2 * ncols) * DX_ALIGN;
 	cap = (int64_t) (avail / roww) & ~(int64_t) 255;
 	if (cap < 4096)
 		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "direct Redistribute: a row of %s%lld bytes does not fit the window (raise CBGPU_MOTION_WINDOW_MB)", "", (long long) roww);
@@ -1281,4 +1291,47 @@ cbgpu_motion_broadcast(cbgpu_motion *m, cbgpu_rel *send, int64_t nrows, cbgpu_re
 		rc = exchange_rows(m, send, *recv, send_off, send_cnt, recv_off, recv_cnt);
 	free(matrix);
 	return rc;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * host packet channels over the windows (include/cb_chan.h): the arena is CH_REGION_BYTES of every window, a put is a
+ * host -> PEER-device copy (the copy engine stores over NVLink into the peer's HBM; copies on one stream land in
+ * order, so a packet is complete before the counter that publishes it), a get a device -> host copy of this rank's
+ * own window.  What integration/cbgpu_ic_layer.c moves tuple chunks with between QE processes.
+ * --------------------------------------------------------------------------------------------- */
+static int
+win_chan_put(void *arg, int peer, size_t off, const void *src, size_t len)
+{
+	cbgpu_motion *m = (cbgpu_motion *) arg;
+
+	if (peer < 0 || peer >= m->nranks || off + len > CH_REGION_BYTES)
+		return -1;
+	/* pageable source: the call returns once the bytes are staged, the caller may reuse its buffer */
+	return cudaMemcpyAsync(m->peer_win[peer] + DX_CTL_BYTES + off, src, len, cudaMemcpyDefault, m->chan_stream) == cudaSuccess ? 0 : -1;
+}
+
+static int
+win_chan_get(void *arg, size_t off, void *dst, size_t len)
+{
+	cbgpu_motion *m = (cbgpu_motion *) arg;
+
+	if (off + len > CH_REGION_BYTES)
+		return -1;
+	if (cudaMemcpyAsync(dst, m->win + DX_CTL_BYTES + off, len, cudaMemcpyDefault, m->chan_stream) != cudaSuccess)
+		return -1;
+	return cudaStreamSynchronize(m->chan_stream) == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int
+cbgpu_motion_chan_mem(cbgpu_motion *m, CbChanMem *mem, size_t *arena_bytes)
+{
+	if (!m->direct_ok)
+		return cb_fail(m->ctx, CBGPU_ERR_UNSUPPORTED, "packet channels need the peer-memory windows%s", "", 0);
+	if (!m->chan_stream)
+		CB_CUDA(m->ctx, cudaStreamCreateWithFlags(&m->chan_stream, cudaStreamNonBlocking));
+	mem->arg = m;
+	mem->put = win_chan_put;
+	mem->get = win_chan_get;
+	*arena_bytes = CH_REGION_BYTES;
+	return CBGPU_OK;
 }

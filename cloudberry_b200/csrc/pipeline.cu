@@ -208,7 +208,7 @@ cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
 	/* peephole: the three shapes nearly every plan on this path contains run as single fused ops
 	 * (no stack traffic): `col CMP const` quals, probes keyed by plain columns, a * (k - b) */
 	{
-		static CbpOp x[CBP_MAX_OPS];
+		CbpOp	   *x = (CbpOp *) cb_scratch(ctx, 0, sizeof(CbpOp) * CBP_MAX_OPS);
 		int			n = 0;
 		int			i = 0;
 
@@ -552,7 +552,7 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 					}
 				}
 				for (int k = 0; k < pr.nkeys; k++)
-					h = pg_hash_combine(h, pg_hash_datum(pr.keytype[k], key[k], pr.keydict[k]), false);
+					h = pg_hash_combine(h, jh_hash_datum(pr.keytype[k], key[k], pr.keydict[k]), false);
 				bool		maybe = alive && !knull;
 
 				if (maybe && pr.ht.bloom)
@@ -563,6 +563,8 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 
 					maybe = (__ldg(pr.ht.bloom + w) & bits) == bits;
 				}
+				if (maybe && pr.ht.keyslot && !ht_key_in_domain(pr.ht.keyslot, key[0]))
+					maybe = false;		/* outside the build side's key domain: no partner */
 				if (maybe)
 				{
 					uint32_t	pos = h & pr.ht.mask;
@@ -573,12 +575,12 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 
 						if (e == HT_EMPTY)
 							break;
-						if ((uint32_t) (e >> 32) == h)
+						if ((uint32_t) (e >> 32) == (pr.ht.keyslot ? (uint32_t) key[0] : h))
 						{
 							bool		eq = true;
 
 							irow = (uint32_t) e;
-							for (int k = 0; k < pr.nkeys; k++)
+							for (int k = 0; k < pr.nkeys && !pr.ht.keyslot; k++)
 								if (cb_load_widen(pr.ht.keydata[k], pr.ht.keytype[k], irow) != key[k])
 									eq = false;
 							if (eq)
@@ -805,6 +807,17 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 
 					if (isn)
 						st[k] = 0;
+					else if (S.keytype[k] == CB_FLOAT8)
+					{
+						/* float8eq groups -0 with +0 and all NaNs together (hashfloat8 gives them one hash value,
+						 * hashfunc.c:194-216); the table compares key bits, so the key is made canonical first */
+						const double dv = __longlong_as_double(st[k]);
+
+						if (dv == 0.0)
+							st[k] = 0;
+						else if (dv != dv)
+							st[k] = 0x7FF8000000000000ll;
+					}
 					h = pg_hash_combine(h, isn ? 0u : pg_hash_datum(S.keytype[k], st[k], S.keydict[k]), isn);
 				}
 				h = pg_murmurhash32(h);
@@ -893,7 +906,10 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 extern "C" int
 cbgpu_pipeline_run(cbgpu_ctx *ctx, const CbPipeline *p)
 {
-	static PipeDev d;			/* large: keep it off the stack (single-threaded callers, as a backend is) */
+	PipeDev    *dp = (PipeDev *) cb_scratch(ctx, 1, sizeof(PipeDev));	/* large: off the stack, per context (re-entrant) */
+	if (!dp)
+		return CBGPU_ERR_NOMEM;
+	PipeDev    &d = *dp;
 	int			rc = cb_pipeline_to_dev(ctx, p, &d);
 	bool		handled = false;
 

@@ -72,6 +72,13 @@ struct PcProbe
 	int32_t		kind;			/* 0: one int32 key, hashint4; 1: one int64 key, hashint8; 2: general */
 	PcCol		key[2];
 	int32_t		keytype[2];		/* hash function by the OUTER key's type (cross-type int4/int8 joins) */
+	/* how the table is reached.  0: Bloom filter stage B_j, then the table in HBM (stage H_j) - for build sides whose
+	 * tables miss L2.  1: ONE stage straight into the table - small build sides (L2-resident tables need no filter in
+	 * front of them).  2: the same, with the table's slots staged into the CTA's shared memory by a TMA bulk copy
+	 * (cp.async.bulk + mbarrier) when the kernel starts - dimension tables of a few thousand rows (nation, region, date):
+	 * such a probe never leaves the SM.  (nodeHash.c builds ONE table kind; SURVEY.md 8 row a6 asks for this split.) */
+	int32_t		mode;
+	int32_t		smem_off;		/* mode 2: first slot inside the dynamic shared memory, in slots       */
 };
 
 #define PC_MAXEARLY 2
@@ -100,6 +107,13 @@ struct PcParams
 	uint32_t   *qmem;			/* global queues: [CTA][q_cta_words]                                  */
 	int64_t		q_cta_words;
 	int32_t		q_off[PC_NQ];	/* queue k >= 1: word offset inside the CTA's slice                   */
+	int32_t		q_cap[PC_NQ];	/* ... and its capacity in entries                                    */
+	/* stage F also runs probe 0's key hash and Bloom test (its key is a column of the driving relation, read
+	 * 16 bytes at a time like the qual columns) and feeds queue 1 directly: the rows the quals pass never
+	 * go through queue 0 and a separate gather of their keys */
+	int32_t		fuse0;
+	int32_t		spec0;			/* ... and its keys are loaded together with the qual columns after a dense tile */
+	uint32_t	smem_table_bytes;	/* shared-memory tables of the mode 2 probes, all together             */
 	/* sink */
 	int32_t		sink_kind;		/* CBP_SINK_AGG or CBP_SINK_MATERIALIZE                               */
 	AggDev		agg;
@@ -182,13 +196,13 @@ __device__ __forceinline__ uint32_t
 pc_key_hash(const PcProbe &pr, int64_t k0, int64_t k1)
 {
 	if (KIND == 0)
-		return pg_hash_combine(0u, pg_hash_uint32((uint32_t) (int32_t) k0), false);
+		return pg_hash_combine(0u, jh_mix32((uint32_t) (int32_t) k0), false);
 	if (KIND == 1)
-		return pg_hash_combine(0u, pg_hashint8(k0), false);
-	uint32_t	h = pg_hash_combine(0u, pg_hash_datum(pr.keytype[0], k0, pr.key[0].dict), false);
+		return pg_hash_combine(0u, jh_int8(k0), false);
+	uint32_t	h = pg_hash_combine(0u, jh_hash_datum(pr.keytype[0], k0, pr.key[0].dict), false);
 
 	if (pr.nkeys > 1)
-		h = pg_hash_combine(h, pg_hash_datum(pr.keytype[1], k1, pr.key[1].dict), false);
+		h = pg_hash_combine(h, jh_hash_datum(pr.keytype[1], k1, pr.key[1].dict), false);
 	return h;
 }
 
@@ -210,7 +224,7 @@ pc_load_key0(const PcProbe &pr, uint32_t row, uint64_t pol_stream)
  * Bloom filter.  in: entries [base, base + n) of Q (j + 1 row ids); out: the same row ids + hash. */
 template <int KIND>
 __device__ __noinline__ void
-pc_stage_bloom(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t *out, unsigned *ocnt)
+pc_stage_bloom(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t *out, unsigned ocap, unsigned *ocnt)
 {
 	/* an anti join keeps the rows WITHOUT a match: the filter cannot drop anything */
 	const bool	use_bloom = pr.ht.bloom != NULL && pr.jointype != CB_JOIN_ANTI;
@@ -271,8 +285,8 @@ pc_stage_bloom(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint3
 			const uint32_t pos = wb + __popc(bal[u] & ((1u << lane) - 1));
 
 			for (int s = 0; s <= j; s++)
-				out[(size_t) s * PC_QCAP + pos] = pc_row(Q, s, e[u]);
-			out[(size_t) (j + 1) * PC_QCAP + pos] = h[u];
+				out[(size_t) s * ocap + pos] = pc_row(Q, s, e[u]);
+			out[(size_t) (j + 1) * ocap + pos] = h[u];
 		}
 		wb += __popc(bal[u]);
 	}
@@ -283,7 +297,7 @@ pc_stage_bloom(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint3
  * in: j + 1 row ids + hash; out: j + 2 row ids. */
 template <int KIND>
 __device__ __noinline__ void
-pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t *out, unsigned *ocnt)
+pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t *out, unsigned ocap, unsigned *ocnt)
 {
 	const uint64_t pol_stream = l2_policy_evict_first();
 	const int	lane = threadIdx.x & 31;
@@ -320,23 +334,42 @@ pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t
 			unsigned long long x = slot[u];
 			uint32_t	p = pos[u];
 
-			while (x != HT_EMPTY)
+			if (pr.ht.keyslot)
 			{
-				if ((uint32_t) (x >> 32) == h[u])
-				{
-					const uint32_t r = (uint32_t) x;
+				/* key-in-slot table: the slot settles it, no access to the build side's key column */
+				const uint32_t tag = (uint32_t) k0;
 
-					if (cb_load_widen(pr.ht.keydata[0], pr.ht.keytype[0], r) == k0 &&
-						(KIND != 2 || pr.nkeys < 2 || cb_load_widen(pr.ht.keydata[1], pr.ht.keytype[1], r) == k1))
+				if (ht_key_in_domain(pr.ht.keyslot, k0))
+					while (x != HT_EMPTY)
 					{
-						found = true;
-						irow[u] = r;
-						break;
+						if ((uint32_t) (x >> 32) == tag)
+						{
+							found = true;
+							irow[u] = (uint32_t) x;
+							break;
+						}
+						p = (p + 1) & pr.ht.mask;
+						x = __ldg(pr.ht.slots + p);
 					}
-				}
-				p = (p + 1) & pr.ht.mask;
-				x = __ldg(pr.ht.slots + p);
 			}
+			else
+				while (x != HT_EMPTY)
+				{
+					if ((uint32_t) (x >> 32) == h[u])
+					{
+						const uint32_t r = (uint32_t) x;
+
+						if (cb_load_widen(pr.ht.keydata[0], pr.ht.keytype[0], r) == k0 &&
+							(KIND != 2 || pr.nkeys < 2 || cb_load_widen(pr.ht.keydata[1], pr.ht.keytype[1], r) == k1))
+						{
+							found = true;
+							irow[u] = r;
+							break;
+						}
+					}
+					p = (p + 1) & pr.ht.mask;
+					x = __ldg(pr.ht.slots + p);
+				}
 		}
 		/* full-mask ballot: the warp reconverges here */
 		bal[u] = __ballot_sync(0xffffffffu, v[u] && (pr.jointype == CB_JOIN_ANTI ? !found : found));
@@ -355,8 +388,111 @@ pc_stage_ht(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t
 			const uint32_t opos = wb + __popc(bal[u] & ((1u << lane) - 1));
 
 			for (int s = 0; s <= j; s++)
-				out[(size_t) s * PC_QCAP + opos] = pc_row(Q, s, e[u]);
-			out[(size_t) (j + 1) * PC_QCAP + opos] = irow[u];
+				out[(size_t) s * ocap + opos] = pc_row(Q, s, e[u]);
+			out[(size_t) (j + 1) * ocap + opos] = irow[u];
+		}
+		wb += __popc(bal[u]);
+	}
+}
+
+/* stage D_j (PcProbe.mode 1 / 2): key hash and table probe in one stage, for tables that stay in L2 (`slots` = the
+ * table in global memory) or were staged into shared memory (`slots` = the CTA's copy).
+ * in: j + 1 row ids; out: j + 2 row ids, into queue 2j + 2 (queue 2j + 1 stays empty). */
+template <int KIND>
+__device__ __noinline__ void
+pc_stage_direct(const PcProbe &pr, int j, PcQ Q, unsigned base, unsigned n, uint32_t *out, unsigned ocap, unsigned *ocnt, const unsigned long long *slots)
+{
+	const uint64_t pol_stream = l2_policy_evict_first();
+	const int	lane = threadIdx.x & 31;
+	uint32_t	e[PC_U], h[PC_U], pos[PC_U], irow[PC_U], bal[PC_U];
+	int64_t		k0[PC_U], k1[PC_U];
+	unsigned long long slot[PC_U];
+	bool		v[PC_U];
+
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		const unsigned i = u * PC_THREADS + threadIdx.x;
+
+		v[u] = i < n;
+		e[u] = base + (v[u] ? i : 0u);
+		k0[u] = pc_load_key0<KIND>(pr, pc_row(Q, pr.key[0].src, e[u]), pol_stream);
+		k1[u] = (KIND == 2 && pr.nkeys > 1) ? pc_load(pr.key[1], Q, e[u]) : 0;
+	}
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		h[u] = pc_key_hash<KIND>(pr, k0[u], k1[u]);
+		pos[u] = h[u] & pr.ht.mask;
+	}
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+		slot[u] = v[u] ? slots[pos[u]] : HT_EMPTY;
+	unsigned	tot = 0,
+				wb = 0;
+
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		bool		found = false;
+		unsigned long long x = slot[u];
+		uint32_t	p = pos[u];
+
+		irow[u] = 0;
+		if (pr.ht.keyslot)
+		{
+			const uint32_t tag = (uint32_t) k0[u];
+
+			if (ht_key_in_domain(pr.ht.keyslot, k0[u]))
+				while (x != HT_EMPTY)
+				{
+					if ((uint32_t) (x >> 32) == tag)
+					{
+						found = true;
+						irow[u] = (uint32_t) x;
+						break;
+					}
+					p = (p + 1) & pr.ht.mask;
+					x = slots[p];
+				}
+		}
+		else
+			while (x != HT_EMPTY)
+			{
+				if ((uint32_t) (x >> 32) == h[u])
+				{
+					const uint32_t r = (uint32_t) x;
+
+					if (cb_load_widen(pr.ht.keydata[0], pr.ht.keytype[0], r) == k0[u] &&
+						(KIND != 2 || pr.nkeys < 2 || cb_load_widen(pr.ht.keydata[1], pr.ht.keytype[1], r) == k1[u]))
+					{
+						found = true;
+						irow[u] = r;
+						break;
+					}
+				}
+				p = (p + 1) & pr.ht.mask;
+				x = slots[p];
+			}
+		/* full-mask ballot: the warp reconverges here */
+		bal[u] = __ballot_sync(0xffffffffu, v[u] && (pr.jointype == CB_JOIN_ANTI ? !found : found));
+		tot += __popc(bal[u]);
+	}
+	if (tot == 0)
+		return;
+	if (lane == 0)
+		wb = atomicAdd(ocnt, tot);
+	wb = __shfl_sync(0xffffffffu, wb, 0);
+#pragma unroll
+	for (int u = 0; u < PC_U; u++)
+	{
+		if ((bal[u] >> lane) & 1)
+		{
+			const uint32_t opos = wb + __popc(bal[u] & ((1u << lane) - 1));
+
+			for (int s = 0; s <= j; s++)
+				out[(size_t) s * ocap + opos] = pc_row(Q, s, e[u]);
+			out[(size_t) (j + 1) * ocap + opos] = irow[u];
 		}
 		wb += __popc(bal[u]);
 	}
@@ -528,6 +664,180 @@ pc_range8(int4 a, int4 b, int32_t lo, uint32_t span)
 		((unsigned) ((unsigned) (b.z - lo) <= span) << 6) | ((unsigned) ((unsigned) (b.w - lo) <= span) << 7);
 }
 
+/* the key values of a thread's 8 consecutive driving rows: int8 keys fill four 16-byte words, int4 keys two */
+struct PcKeys8
+{
+	int4		q[4];
+};
+
+/* WIDE: 8-byte keys.  Unconditional 16-byte loads (a warp reads 2 KB / 1 KB contiguous): for warps whose rows are mostly alive */
+template <bool WIDE>
+__device__ __forceinline__ PcKeys8
+pc_keys8_vec(const void *col, int64_t row0, uint64_t pol)
+{
+	PcKeys8		k;
+
+	if (WIDE)
+	{
+		const int4 *p = (const int4 *) ((const long long *) col + row0);
+
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+			k.q[i] = ldg_stream_v4(p + i, pol);
+	}
+	else
+	{
+		const int4 *p = (const int4 *) ((const int32_t *) col + row0);
+
+		k.q[0] = ldg_stream_v4(p, pol);
+		k.q[1] = ldg_stream_v4(p + 1, pol);
+		k.q[2] = k.q[3] = make_int4(0, 0, 0, 0);
+	}
+	return k;
+}
+
+/* one load per alive row: for warps with few survivors, and for a relation's last, partial tile */
+template <bool WIDE>
+__device__ __forceinline__ PcKeys8
+pc_keys8_pred(const void *col, int64_t row0, unsigned am, uint64_t pol)
+{
+	PcKeys8		k;
+	int			v[8];
+
+	if (WIDE)
+	{
+		long long	t[8];
+
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+			t[u] = ((am >> u) & 1) ? ldg_stream_s64((const long long *) col + row0 + u, pol) : 0;
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+			k.q[i] = make_int4((int) (unsigned) t[2 * i], (int) (unsigned) ((unsigned long long) t[2 * i] >> 32), (int) (unsigned) t[2 * i + 1],
+							   (int) (unsigned) ((unsigned long long) t[2 * i + 1] >> 32));
+	}
+	else
+	{
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+			v[u] = ((am >> u) & 1) ? ldg_stream_s32((const int32_t *) col + row0 + u, pol) : 0;
+		k.q[0] = make_int4(v[0], v[1], v[2], v[3]);
+		k.q[1] = make_int4(v[4], v[5], v[6], v[7]);
+		k.q[2] = k.q[3] = make_int4(0, 0, 0, 0);
+	}
+	return k;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ int64_t
+pc_keys8_get(const PcKeys8 &k, int u)
+{
+	if (WIDE)
+	{
+		const int4	t = k.q[u >> 1];
+		const unsigned lo = (u & 1) ? (unsigned) t.z : (unsigned) t.x;
+		const unsigned hi = (u & 1) ? (unsigned) t.w : (unsigned) t.y;
+
+		return (int64_t) (((unsigned long long) hi << 32) | lo);
+	}
+	const int4	t = k.q[u >> 2];
+
+	return (int64_t) ((u & 3) == 0 ? t.x : (u & 3) == 1 ? t.y : (u & 3) == 2 ? t.z : t.w);
+}
+
+/* is this warp's tile dense enough for unconditional 16-byte key loads?  (warp-uniform: the lanes must not split over
+ * the two load paths, a warp would run both) */
+__device__ __forceinline__ bool
+pc_warp_dense(bool full, unsigned am, unsigned at_least = 64u)
+{
+	return __all_sync(0xffffffffu, full) && __reduce_add_sync(0xffffffffu, (unsigned) __popc(am)) >= at_least;
+}
+
+/* stage F's tail when probe 0 is fused into it (P.fuse0): hash of the 8 keys, Bloom words of the alive ones in flight
+ * together, survivors to queue 1 as (row id, hash) in row order - one warp scan, one shared-memory atomic.
+ * WIDE: int8 key, else int4 / date. */
+template <bool WIDE>
+__device__ __forceinline__ void
+pc_stage_f_probe0(const PcProbe &pr, int64_t row0, const PcKeys8 &keys, unsigned am, uint32_t *out, unsigned cap, unsigned *ocnt)
+{
+	const bool	use_bloom = pr.ht.bloom != NULL && pr.jointype != CB_JOIN_ANTI;
+	const uint64_t pol_keep = l2_policy_evict_last();
+	const int	lane = threadIdx.x & 31;
+	uint32_t	h[8];
+
+#pragma unroll
+	for (int u = 0; u < 8; u++)
+		h[u] = WIDE ? jh_int8(pc_keys8_get<true>(keys, u)) : jh_mix32((uint32_t) (int32_t) pc_keys8_get<false>(keys, u));
+	if (use_bloom)
+	{
+		uint32_t	bits[8], word[8];
+
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+		{
+			uint32_t	w;
+
+			bits[u] = ht_bloom_bits(h[u], &w, pr.ht.bloom_mask);
+			word[u] = ((am >> u) & 1) ? ldg_hint_u32(pr.ht.bloom + w, pol_keep) : 0u;
+		}
+#pragma unroll
+		for (int u = 0; u < 8; u++)
+			if ((word[u] & bits[u]) != bits[u])
+				am &= ~(1u << u);
+	}
+	const unsigned c = __popc(am);
+	unsigned	x = c;
+
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const unsigned y = __shfl_up_sync(0xffffffffu, x, d);
+
+		if (lane >= d)
+			x += y;
+	}
+	const unsigned total = __shfl_sync(0xffffffffu, x, 31);
+	unsigned	wb = 0;
+
+	if (lane == 31 && total)
+		wb = atomicAdd(ocnt, total);
+	wb = __shfl_sync(0xffffffffu, wb, 31);
+	unsigned	pos = wb + x - c;
+
+#pragma unroll
+	for (int u = 0; u < 8; u++)
+		if ((am >> u) & 1)
+		{
+			out[pos] = (uint32_t) (row0 + u);
+			out[(size_t) cap + pos] = h[u];
+			pos++;
+		}
+}
+
+/* a scan-level runtime filter over the thread's 8 rows: returns the alive mask with the rows that miss it cleared */
+template <bool WIDE>
+__device__ __forceinline__ unsigned
+pc_early_filter8(const PcEarly &E, int64_t row0, bool full, unsigned am, uint64_t pol)
+{
+	const PcKeys8 keys = pc_warp_dense(full, am) ? pc_keys8_vec<WIDE>(E.col, row0, pol) : pc_keys8_pred<WIDE>(E.col, row0, am, pol);
+	uint32_t	bits[8], word[8];
+
+#pragma unroll
+	for (int u = 0; u < 8; u++)
+	{
+		const int64_t kv = pc_keys8_get<WIDE>(keys, u);
+		uint32_t	w;
+
+		bits[u] = ht_bloom_bits(pg_hash_combine(0u, WIDE ? jh_int8(kv) : jh_mix32((uint32_t) (int32_t) kv), false), &w, E.mask);
+		word[u] = ((am >> u) & 1) ? __ldg(E.bloom + w) : 0u;
+	}
+#pragma unroll
+	for (int u = 0; u < 8; u++)
+		if ((word[u] & bits[u]) != bits[u])
+			am &= ~(1u << u);
+	return am;
+}
+
 __global__ void __launch_bounds__(PC_THREADS, PC_OCC)
 k_probe_chain(const __grid_constant__ PcParams P)
 {
@@ -539,6 +849,8 @@ k_probe_chain(const __grid_constant__ PcParams P)
 	__shared__ long long s_tile;
 	__shared__ unsigned long long s_obase;
 	__shared__ PcPart part;
+	__shared__ uint64_t s_tbar;			/* completion of the shared-memory tables' bulk copies                */
+	extern __shared__ __align__(16) unsigned long long s_tables[];
 	const int	np = P.np;
 	const int	last = 2 * np + 1;		/* the sink's stage number; stage s reads queue s - 1         */
 	const bool	iota = P.nfilters == 0 && P.visimap == NULL && P.nearly == 0;
@@ -546,11 +858,31 @@ k_probe_chain(const __grid_constant__ PcParams P)
 	const int64_t ntiles = (P.nrows + tile_rows - 1) / tile_rows;
 	uint32_t   *const qg = P.qmem + (size_t) blockIdx.x * (size_t) P.q_cta_words;
 	int64_t		next_tile = blockIdx.x;	/* thread 0's */
+	bool		dense_prev = false;		/* this warp's previous tile: did most rows survive the quals?        */
 
 	if (threadIdx.x < PC_NQ)
 		cnt[threadIdx.x] = 0;
 	for (int i = threadIdx.x; i < (int) (np * sizeof(PcProbe) / sizeof(uint32_t)); i += PC_THREADS)
 		((uint32_t *) sprobe)[i] = ((const uint32_t *) P.probe)[i];
+	if (P.smem_table_bytes)
+	{
+		/* the small dimension tables: one TMA bulk copy each, global -> this CTA's shared memory; everybody waits on the
+		 * transaction barrier once */
+		if (threadIdx.x == 0)
+		{
+			mbar_init(&s_tbar, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			mbar_expect_tx(&s_tbar, P.smem_table_bytes);
+			for (int j = 0; j < np; j++)
+				if (P.probe[j].mode == 2)
+					tma_load_1d(s_tables + P.probe[j].smem_off, P.probe[j].ht.slots, (P.probe[j].ht.mask + 1u) * 8u, &s_tbar);
+		}
+		mbar_wait(&s_tbar, 0);
+	}
 	for (;;)
 	{
 		__syncthreads();				/* the previous run's pushes are in */
@@ -609,9 +941,21 @@ k_probe_chain(const __grid_constant__ PcParams P)
 			const unsigned o0 = threadIdx.x * 8;
 			const int	lane = threadIdx.x & 31;
 			const uint64_t pol_stream = l2_policy_evict_first();
+			const bool	full = o0 + 8 <= nvalid;
+			const bool	wide0 = sprobe[0].kind == 1;
 			unsigned	am = 0;
+			PcKeys8		keys0;
+			bool		have_keys0 = false;
 
-			if (o0 + 8 <= nvalid)
+			/* probe 0's keys ride along with the qual columns when this warp's previous tile was dense: their loads are
+			 * in flight together instead of one HBM latency after the other (late materialisation stays for sparse tiles) */
+			if (P.spec0 && dense_prev && __all_sync(0xffffffffu, full))
+			{
+				keys0 = wide0 ? pc_keys8_vec<true>(sprobe[0].key[0].data, base + o0, pol_stream)
+					: pc_keys8_vec<false>(sprobe[0].key[0].data, base + o0, pol_stream);
+				have_keys0 = true;
+			}
+			if (full)
 			{
 				int4		a0 = make_int4(0, 0, 0, 0), b0 = a0, a1 = a0, b1 = a0;
 				unsigned	vm = 0xff;
@@ -661,26 +1005,29 @@ k_probe_chain(const __grid_constant__ PcParams P)
 				}
 			/* scan-level runtime filters: the key columns of the rows still alive, 8 filter words in flight */
 			for (int f = 0; f < P.nearly && __any_sync(0xffffffffu, am != 0); f++)
+				am = P.early[f].width == 8 ? pc_early_filter8<true>(P.early[f], base + o0, full, am, pol_stream)
+					: pc_early_filter8<false>(P.early[f], base + o0, full, am, pol_stream);
+			/* every lane votes (full-mask).  Only a warp whose rows mostly survived runs probe 0 here: its 8 hashes and
+			 * filter words per thread are work for live rows.  A sparse warp hands its few survivors to queue 0, where
+			 * stage B_0 will see them packed into full batches. */
+			const bool	dense = P.fuse0 && pc_warp_dense(full, am, 96u);
+
+			dense_prev = dense;
+			if (dense)
 			{
-				const PcEarly &E = P.early[f];
-				uint32_t	bits[8], word[8];
-
-#pragma unroll
-				for (int u = 0; u < 8; u++)
+				if (wide0)
 				{
-					const int64_t r = base + o0 + u;
-					int64_t		kv = 0;
-					uint32_t	w = 0;
-
-					if ((am >> u) & 1)
-						kv = E.width == 4 ? (int64_t) __ldg((const int32_t *) E.col + r) : __ldg((const long long *) E.col + r);
-					bits[u] = ht_bloom_bits(pg_hash_combine(0u, pg_hash_datum(E.hashtype, kv, NULL), false), &w, E.mask);
-					word[u] = ((am >> u) & 1) ? __ldg(E.bloom + w) : 0u;
+					if (!have_keys0)
+						keys0 = pc_keys8_vec<true>(sprobe[0].key[0].data, base + o0, pol_stream);
+					pc_stage_f_probe0<true>(sprobe[0], base + o0, keys0, am, qg + P.q_off[1], (unsigned) P.q_cap[1], &cnt[1]);
 				}
-#pragma unroll
-				for (int u = 0; u < 8; u++)
-					if ((word[u] & bits[u]) != bits[u])
-						am &= ~(1u << u);
+				else
+				{
+					if (!have_keys0)
+						keys0 = pc_keys8_vec<false>(sprobe[0].key[0].data, base + o0, pol_stream);
+					pc_stage_f_probe0<false>(sprobe[0], base + o0, keys0, am, qg + P.q_off[1], (unsigned) P.q_cap[1], &cnt[1]);
+				}
+				continue;
 			}
 			const unsigned c = __popc(am);
 			unsigned	x = c;
@@ -732,7 +1079,7 @@ k_probe_chain(const __grid_constant__ PcParams P)
 		else
 		{
 			Q.q = qg + P.q_off[s - 1];
-			Q.cap = PC_QCAP;
+			Q.cap = (uint32_t) P.q_cap[s - 1];
 			Q.iota_base = 0;
 		}
 		if (s == last)
@@ -743,23 +1090,36 @@ k_probe_chain(const __grid_constant__ PcParams P)
 			const PcProbe &pr = sprobe[j];
 			uint32_t   *out = qg + P.q_off[s];
 
-			if (s & 1)
+			if ((s & 1) && pr.mode != 0)
+			{
+				/* one stage for this probe: straight into queue 2j + 2 */
+				const unsigned long long *slots = pr.mode == 2 ? s_tables + pr.smem_off : pr.ht.slots;
+				uint32_t   *out2 = qg + P.q_off[s + 1];
+
+				if (pr.kind == 0)
+					pc_stage_direct<0>(pr, j, Q, base, n, out2, (unsigned) P.q_cap[s + 1], &cnt[s + 1], slots);
+				else if (pr.kind == 1)
+					pc_stage_direct<1>(pr, j, Q, base, n, out2, (unsigned) P.q_cap[s + 1], &cnt[s + 1], slots);
+				else
+					pc_stage_direct<2>(pr, j, Q, base, n, out2, (unsigned) P.q_cap[s + 1], &cnt[s + 1], slots);
+			}
+			else if (s & 1)
 			{
 				if (pr.kind == 0)
-					pc_stage_bloom<0>(pr, j, Q, base, n, out, &cnt[s]);
+					pc_stage_bloom<0>(pr, j, Q, base, n, out, (unsigned) P.q_cap[s], &cnt[s]);
 				else if (pr.kind == 1)
-					pc_stage_bloom<1>(pr, j, Q, base, n, out, &cnt[s]);
+					pc_stage_bloom<1>(pr, j, Q, base, n, out, (unsigned) P.q_cap[s], &cnt[s]);
 				else
-					pc_stage_bloom<2>(pr, j, Q, base, n, out, &cnt[s]);
+					pc_stage_bloom<2>(pr, j, Q, base, n, out, (unsigned) P.q_cap[s], &cnt[s]);
 			}
 			else
 			{
 				if (pr.kind == 0)
-					pc_stage_ht<0>(pr, j, Q, base, n, out, &cnt[s]);
+					pc_stage_ht<0>(pr, j, Q, base, n, out, (unsigned) P.q_cap[s], &cnt[s]);
 				else if (pr.kind == 1)
-					pc_stage_ht<1>(pr, j, Q, base, n, out, &cnt[s]);
+					pc_stage_ht<1>(pr, j, Q, base, n, out, (unsigned) P.q_cap[s], &cnt[s]);
 				else
-					pc_stage_ht<2>(pr, j, Q, base, n, out, &cnt[s]);
+					pc_stage_ht<2>(pr, j, Q, base, n, out, (unsigned) P.q_cap[s], &cnt[s]);
 			}
 		}
 	}
@@ -819,22 +1179,22 @@ k_pc_early_build(PcEarlyBuild B)
 			for (int i = 0; i < B.red_nkeys[m]; i++)
 			{
 				kv[i] = cb_load_widen(B.red_key[m][i].data, B.red_key[m][i].type, (uint32_t) r);
-				h = pg_hash_combine(h, pg_hash_datum(B.red_keytype[m][i], kv[i], B.red_key[m][i].dict), false);
+				h = pg_hash_combine(h, jh_hash_datum(B.red_keytype[m][i], kv[i], B.red_key[m][i].dict), false);
 			}
 			uint32_t	pos = h & T.mask;
 
-			for (;;)
+			for (; !(T.keyslot && !ht_key_in_domain(T.keyslot, kv[0]));)
 			{
 				const unsigned long long e = T.slots[pos];
 
 				if (e == HT_EMPTY)
 					break;
-				if ((uint32_t) (e >> 32) == h)
+				if ((uint32_t) (e >> 32) == (T.keyslot ? (uint32_t) kv[0] : h))
 				{
 					const uint32_t ir = (uint32_t) e;
 
-					if (cb_load_widen(T.keydata[0], T.keytype[0], ir) == kv[0] &&
-						(B.red_nkeys[m] < 2 || cb_load_widen(T.keydata[1], T.keytype[1], ir) == kv[1]))
+					if (T.keyslot || (cb_load_widen(T.keydata[0], T.keytype[0], ir) == kv[0] &&
+									  (B.red_nkeys[m] < 2 || cb_load_widen(T.keydata[1], T.keytype[1], ir) == kv[1])))
 					{
 						found = true;
 						break;
@@ -850,7 +1210,7 @@ k_pc_early_build(PcEarlyBuild B)
 		{
 			uint32_t	w;
 			const int64_t kv = cb_load_widen(B.self.keydata[B.kc], B.self.keytype[B.kc], (uint32_t) r);
-			const uint32_t bits = ht_bloom_bits(pg_hash_combine(0u, pg_hash_datum(B.hashtype, kv, NULL), false), &w, B.mask);
+			const uint32_t bits = ht_bloom_bits(pg_hash_combine(0u, jh_hash_datum(B.hashtype, kv, NULL), false), &w, B.mask);
 
 			atomicOr(B.bloom + w, bits);
 		}
@@ -859,7 +1219,7 @@ k_pc_early_build(PcEarlyBuild B)
 
 #define PC_REJECT(n) \
 	do { \
-		if (getenv("CBGPU_DEBUG")) \
+		if (ctx->opt_debug) \
 			fprintf(stderr, "k_probe_chain: pipeline not matched (reason %d, line %d)\n", n, __LINE__); \
 		return CBGPU_OK; \
 	} while (0)
@@ -867,8 +1227,12 @@ k_pc_early_build(PcEarlyBuild B)
 int
 cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handled)
 {
-	static XProg x;
-	static PcParams P;
+	XProg	   *xp = (XProg *) cb_scratch(ctx, 2, sizeof(XProg));
+	PcParams   *Pp = (PcParams *) cb_scratch(ctx, 3, sizeof(PcParams));
+	if (!xp || !Pp)
+		return CBGPU_ERR_NOMEM;
+	XProg	   &x = *xp;
+	PcParams   &P = *Pp;
 	const CbpSink *s = &p->sink;
 	int			np = 0;
 	int			base = 1;
@@ -1107,9 +1471,12 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 	 * hash-table access instead of after several. */
 	void	   *early_mem[PC_MAXEARLY] = {NULL, NULL};
 
-	for (int k = 0; k < np && P.nearly < PC_MAXEARLY && !getenv("CBGPU_NO_EARLY_FILTER"); k++)
+	for (int k = 0; k < np && P.nearly < PC_MAXEARLY && !ctx->opt_no_early_filter; k++)
 	{
-		static PcEarlyBuild B;
+		PcEarlyBuild *Bp = (PcEarlyBuild *) cb_scratch(ctx, 4, sizeof(PcEarlyBuild));
+		if (!Bp)
+			return CBGPU_ERR_NOMEM;
+		PcEarlyBuild &B = *Bp;
 		PcProbe    *q = &P.probe[k];
 		const cbgpu_rel *inner = p->probes[k].ht->inner;
 		int			kc = -1;
@@ -1144,25 +1511,44 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 		if (kc < 0)
 			continue;
 		{
-			/* worth it only if the later probes thin the build side out: try the first 64 K build rows */
+			/* worth it only if the later probes thin the build side out: try the first 64 K build rows - once per
+			 * (build side, shape of the reducing tables): the sample costs a host round trip, and its answer stands
+			 * while the tables do (the decision is about speed, never about results) */
 			unsigned long long *d_passed,
 						h_passed = 0;
 			const int64_t sample = inner->nrows < 65536 ? inner->nrows : 65536;
+			const void *sig = (const void *) (uintptr_t) ((uintptr_t) B.red[0].mask * 31u + (uintptr_t) B.nred * 7u + (uintptr_t) B.red[0].keytype[0]);
+			int			known = -1;
 
-			CB_CUDA(ctx, cudaMallocAsync(&d_passed, sizeof(*d_passed), ctx->stream));
-			CB_CUDA(ctx, cudaMemsetAsync(d_passed, 0, sizeof(*d_passed), ctx->stream));
-			B.nrows = sample;
-			B.self = q->ht;
-			B.kc = kc;
-			B.hashtype = q->keytype[kc];
-			B.bloom = NULL;
-			B.passed = d_passed;
-			k_pc_early_build<<<(int) ((sample + 255) / 256), 256, 0, ctx->stream>>>(B);
-			CB_LAUNCHED(ctx, "k_pc_early_build");
-			CB_CUDA(ctx, cudaMemcpyAsync(&h_passed, d_passed, sizeof(h_passed), cudaMemcpyDeviceToHost, ctx->stream));
-			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-			CB_CUDA(ctx, cudaFreeAsync(d_passed, ctx->stream));
-			if ((int64_t) h_passed * 2 > sample)
+			for (int i = 0; i < ctx->early_cache_n; i++)
+				if (ctx->early_cache[i].keydata == q->ht.keydata[kc] && ctx->early_cache[i].nrows == inner->nrows && ctx->early_cache[i].red0 == sig)
+					known = ctx->early_cache[i].worth;
+			if (known < 0)
+			{
+				CB_CUDA(ctx, cudaMallocAsync(&d_passed, sizeof(*d_passed), ctx->stream));
+				CB_CUDA(ctx, cudaMemsetAsync(d_passed, 0, sizeof(*d_passed), ctx->stream));
+				B.nrows = sample;
+				B.self = q->ht;
+				B.kc = kc;
+				B.hashtype = q->keytype[kc];
+				B.bloom = NULL;
+				B.passed = d_passed;
+				k_pc_early_build<<<(int) ((sample + 255) / 256), 256, 0, ctx->stream>>>(B);
+				CB_LAUNCHED(ctx, "k_pc_early_build");
+				CB_CUDA(ctx, cudaMemcpyAsync(&h_passed, d_passed, sizeof(h_passed), cudaMemcpyDeviceToHost, ctx->stream));
+				CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				CB_CUDA(ctx, cudaFreeAsync(d_passed, ctx->stream));
+				known = (int64_t) h_passed * 2 <= sample;
+				{
+					const int	slot = ctx->early_cache_n < CB_EARLY_CACHE ? ctx->early_cache_n++ : (int) (inner->nrows % CB_EARLY_CACHE);
+
+					ctx->early_cache[slot].keydata = q->ht.keydata[kc];
+					ctx->early_cache[slot].nrows = inner->nrows;
+					ctx->early_cache[slot].red0 = sig;
+					ctx->early_cache[slot].worth = known;
+				}
+			}
+			if (!known)
 				continue;
 		}
 		while (words < inner->nrows / 2)
@@ -1198,23 +1584,66 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 
 	if (blocks > ntiles)
 		blocks = (int) ntiles;
+	/* probe 0 rides in stage F when its one integer key is a column of the driving relation that can be read 16 bytes at
+	 * a time, and stage F exists at all (without quals / visimap / scan-level filters the tiles start at B_0 already) */
+	/* how each table is reached (PcProbe.mode): a few thousand slots -> staged into shared memory by TMA (32 KB per CTA for
+	 * all of them together: four CTAs per SM stay resident); everything else Bloom filter first, then the table (probing an
+	 * L2-resident table in place, mode 1, is kept behind CBGPU_L2_DIRECT=1: it measured slower) */
+	{
+		uint32_t	smem_slots = 0;
+
+		for (int j = 0; j < np; j++)
+		{
+			const uint64_t bytes = ((uint64_t) P.probe[j].ht.mask + 1) * 8;
+
+			P.probe[j].mode = 0;
+			if (ctx->opt_no_smem_ht)
+				continue;
+			if (bytes <= 32768 && (smem_slots * 8 + bytes) <= 32768 && ((uintptr_t) P.probe[j].ht.slots & 15) == 0)
+			{
+				P.probe[j].mode = 2;
+				P.probe[j].smem_off = (int32_t) smem_slots;
+				smem_slots += (uint32_t) (bytes / 8);
+			}
+			else if (ctx->opt_l2_direct && bytes <= ((uint64_t) 16 << 20))
+				P.probe[j].mode = 1;	/* measured (SSB Q4.3, 4 MB supplier table): 10.5 ms against 5.1 ms with the filter in front -
+										 * a selective build side's Bloom filter sits in L1, its table does not: off unless asked for */
+		}
+		P.smem_table_bytes = smem_slots * 8;
+	}
+	P.fuse0 = !iota && np >= 1 && P.probe[0].mode == 0 && P.probe[0].nkeys == 1 && (P.probe[0].kind == 0 || P.probe[0].kind == 1) &&
+		P.probe[0].key[0].src == 0 && ((uintptr_t) P.probe[0].key[0].data & 15) == 0 && !ctx->opt_no_fuse0;
+	P.spec0 = P.fuse0 && !ctx->opt_no_spec0;
 	for (int k = 1; k <= 2 * np; k++)
 	{
 		P.q_off[k] = (int32_t) words;
-		words += (int64_t) PC_QCAP * ((k + 3) / 2);
+		P.q_cap[k] = (k == 1 && P.fuse0) ? PC_Q0CAP : PC_QCAP;
+		words += (int64_t) P.q_cap[k] * ((k + 3) / 2);
 	}
 	P.q_cta_words = words;
 	CB_CUDA(ctx, cudaMallocAsync(&P.qmem, (size_t) blocks * (size_t) (words ? words : 1) * sizeof(uint32_t), ctx->stream));
-	if (getenv("CBGPU_DEBUG"))
+	if (ctx->opt_debug)
+		fprintf(stderr, "k_probe_chain: modes %d %d %d %d (0 filter + HBM table, 1 table in L2, 2 table in shared memory: %u bytes) fuse0 %d\n",
+				P.probe[0].mode, P.probe[1].mode, P.probe[2].mode, P.probe[3].mode, P.smem_table_bytes, P.fuse0);
+	if (ctx->opt_debug)
 		fprintf(stderr, "k_probe_chain: np %d nrows %lld tiles %lld blocks %d queue words/CTA %lld filters %d sink %d kinds %d %d %d %d\n", np,
 				(long long) P.nrows, (long long) ntiles, blocks, (long long) words, P.nfilters, P.sink_kind, P.probe[0].kind,
 				P.probe[1].kind, P.probe[2].kind, P.probe[3].kind);
-	if (getenv("CBGPU_DEBUG") && P.nearly)
+	if (ctx->opt_debug && P.nearly)
 		fprintf(stderr, "k_probe_chain: %d scan-level runtime filter(s)\n", P.nearly);
 	CB_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
 	int			kl = cb_klog_begin(ctx, "k_probe_chain");
 
-	k_probe_chain<<<blocks, PC_THREADS, 0, ctx->stream>>>(P);
+	{
+		static bool attr_done = false;	/* idempotent: a race between two contexts sets the same value twice */
+
+		if (!attr_done)
+		{
+			CB_CUDA(ctx, cudaFuncSetAttribute(k_probe_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+			attr_done = true;
+		}
+	}
+	k_probe_chain<<<blocks, PC_THREADS, P.smem_table_bytes, ctx->stream>>>(P);
 	ctx->last_kernel_name = "k_probe_chain";
 	if (kl >= 0)
 		ctx->klog_name[kl] = ctx->last_kernel_name;

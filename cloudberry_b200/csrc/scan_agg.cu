@@ -113,53 +113,7 @@ sa_insert_key(unsigned *gkeys, unsigned key, int *retry)
 		atomicExch(retry, 1);	/* more distinct groups than register slots */
 }
 
-/* ---- TMA bulk-copy pipeline primitives (sm_90+ PTX; SASS: UBLKCP / SYNCS) ---- */
-__device__ __forceinline__ uint32_t
-smem_u32(const void *p)
-{
-	return (uint32_t) __cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void
-mbar_init(uint64_t *bar, unsigned count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-}
-
-__device__ __forceinline__ void
-mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void
-mbar_arrive(uint64_t *bar)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void
-mbar_wait(uint64_t *bar, unsigned parity)
-{
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"WAIT_%=:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra DONE_%=;\n"
-		"bra WAIT_%=;\n"
-		"DONE_%=:\n"
-		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-
-/* one contiguous global -> shared bulk copy, completion counted in bytes on `bar` */
-__device__ __forceinline__ void
-tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-				 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
+/* TMA bulk-copy pipeline primitives (mbar_*, tma_load_1d): common.cuh */
 #define SA_TILE 896				/* rows per pipeline stage                                            */
 #define SA_STAGES 5
 /* consumer threads (one extra warp produces): 448 + 32 threads leave 128 registers per thread for
@@ -522,7 +476,10 @@ col_plain(const CbPipeline *p, int c, int width)
 static int
 try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handled)
 {
-	static XProg x;
+	XProg	   *xp = (XProg *) cb_scratch(ctx, 5, sizeof(XProg));
+	if (!xp)
+		return CBGPU_ERR_NOMEM;
+	XProg	   &x = *xp;
 	SmallAggParams P;
 	int			colB = -1,
 				colC = -1,

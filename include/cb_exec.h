@@ -104,6 +104,17 @@ typedef struct CbEState
 	int32_t		es_force_generic;	/* tests: never use the pattern-specialised kernels              */
 	int64_t		es_processed;
 	void	   *es_cluster;		/* in-process multi-segment runs: the owning CbCluster               */
+	/* CHECK_FOR_INTERRUPTS / QueryFinishPending for the batch executor (miscadmin.h:161; execProcnode.c:642; the
+	 * reference polls them per tuple in nodeAgg.c:2342, nodeHashjoin.c:260): called between pipelines, i.e. before every
+	 * kernel that walks a relation.  Non-zero = stop: the query ends with CBGPU_ERR_INTERRUPTED (peers are told through the
+	 * interconnect's abandon()).  The callback must NOT longjmp (ereport): CUDA / NCCL frames are live; the shim raises the
+	 * error after cb_ExecEndNode has released device memory.  NULL: never interrupted. */
+	int			(*es_interrupt_pending) (struct CbEState *estate);
+	void	   *es_interrupt_arg;
+	/* operator memory budget in KB (PlanStateOperatorMemKB, execnodes.h:1166; nodeHash.c:980-990 turns it into nbatch):
+	 * a hash join build side or an aggregate table larger than this is processed in several passes (multi-batch hybrid
+	 * hash join, partitioned aggregation).  0 = whatever the device holds. */
+	int64_t		es_operator_mem_kb;
 } CbEState;
 
 CbEState   *cb_CreateExecutorState(cbgpu_ctx *ctx, cbgpu_rel **range_table, int32_t nrels);

@@ -88,6 +88,9 @@ const char *cbgpu_last_kernel_name(cbgpu_ctx *ctx);
 int			cbgpu_trace_begin(cbgpu_ctx *ctx);
 int			cbgpu_trace_end(cbgpu_ctx *ctx);
 int			cbgpu_trace_get(cbgpu_ctx *ctx, int i, char *name, int namelen, double *ms);
+/* NVTX ranges (profilers show one range per plan node around its kernels); no-ops without a profiler attached */
+void		cbgpu_range_push(const char *name);
+void		cbgpu_range_pop(void);
 /* write `bytes` of HBM so the next timed kernel starts with a cold L2 */
 int			cbgpu_flush_l2(cbgpu_ctx *ctx);
 /* pinned host memory for the end-to-end (host buffers) path */
@@ -275,6 +278,9 @@ int			cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, i
 void		cbgpu_ht_free(cbgpu_hashtable *ht);
 int64_t		cbgpu_ht_nrows(const cbgpu_hashtable *ht);
 int			cbgpu_ht_has_duplicates(const cbgpu_hashtable *ht);
+/* the per-code hash table (device pointer) of dictionary key column k of the build side, NULL for other types:
+ * the identity of the dictionary the build keys are coded by */
+const uint32_t *cbgpu_ht_key_dict_hash(const cbgpu_hashtable *ht, int32_t k);
 /* stand-alone probe emitting (outer_idx, inner_idx) pairs for an INNER join (all matches);
  * outer key columns by index.  pairs are written to two device arrays owned by the call result. */
 typedef struct cbgpu_pairs
@@ -417,6 +423,11 @@ int64_t		cbgpu_motion_direct_bytes(const cbgpu_motion *m);
  * device-side signalling is there to keep small (bench.py reports them per step) */
 int64_t		cbgpu_motion_host_syncs(const cbgpu_motion *m);
 int64_t		cbgpu_motion_collectives(const cbgpu_motion *m);
+/* the windows as arenas of the host packet channels (include/cb_chan.h: what the MotionIPCLayer implementation
+ * integration/cbgpu_ic_layer.c moves tuple chunks with): fills the channel's memory accessors; the arena (zero-filled at
+ * create time) is arena_bytes of every rank's window */
+struct CbChanMem;
+int			cbgpu_motion_chan_mem(cbgpu_motion *m, struct CbChanMem *mem, size_t *arena_bytes);
 /* Gather: the first nrows rows of every rank's `send` to rank `root` (others receive 0 rows) */
 int			cbgpu_motion_gather(cbgpu_motion *m, int root, cbgpu_rel *send, int64_t nrows, cbgpu_rel **recv);
 /* Broadcast: every rank receives every rank's first nrows rows */

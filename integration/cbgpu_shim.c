@@ -51,6 +51,7 @@
 #include "utils/lsyscache.h"
 #include "utils/memutils.h"
 #include "utils/numeric.h"
+#include "utils/rel.h"
 
 #include "cb_exec.h"
 
@@ -100,6 +101,8 @@ typedef struct CbgpuShim
 	int			natts;
 	CbTypeId   *atttypes;
 	int32	   *attdscales;
+	cbgpu_rel **rt;				/* the base tables loaded for this sub-tree: device memory this shim owns */
+	int			nrt;
 } CbgpuShim;
 
 /* ------------------------------------------------------------------------------------------
@@ -626,8 +629,36 @@ shim_release(void *arg)
 	if (shim->cbestate)
 		cb_FreeExecutorState(shim->cbestate);
 	shim->cbestate = NULL;
+	/* cb_FreeExecutorState frees the range table ARRAY only: the relations are this shim's (a session-lived backend
+	 * would otherwise lose a table's worth of HBM per query) */
+	for (int i = 0; i < shim->nrt; i++)
+		if (shim->rt && shim->rt[i])
+			cbgpu_rel_free(shim->rt[i]);
+	shim->nrt = 0;
 	shim_list = NULL;			/* the entries live in the query context that is going away */
 }
+
+/* does the sub-tree exchange rows with other segments?  Then every segment must run it on the same side (GPU or CPU):
+ * the take-over decision may depend on the plan's shape only, and whatever fails on one segment afterwards is an
+ * ERROR for the query, never a quiet return to the CPU executor while the peers wait in the GPU interconnect */
+static bool
+plan_has_motion(Plan *plan)
+{
+	if (plan == NULL)
+		return false;
+	if (IsA(plan, Motion))
+		return true;
+	return plan_has_motion(outerPlan(plan)) || plan_has_motion(innerPlan(plan));
+}
+
+#define SHIM_LOCAL_FAILURE(has_motion, shim, ...) \
+	do { \
+		if (shim) \
+			shim_release(shim); \
+		if (has_motion) \
+			ereport(ERROR, (errcode(ERRCODE_INTERNAL_ERROR), errmsg(__VA_ARGS__))); \
+		return false; \
+	} while (0)
 
 static TupleTableSlot *
 cbgpu_ExecNode(PlanState *ps)			/* ExecProcNodeMtd, nodes/execnodes.h:1056 */
@@ -691,25 +722,39 @@ shim_take_over(PlanState *ps, EState *estate)
 {
 	List	   *rels = NIL;
 	CbPlan	   *cplan = (pending_consts = NIL, translate_plan(ps->plan, estate, &rels));
-	cbgpu_rel **rt;
 	CbgpuShim  *shim;
 	ListCell   *lc;
 	int			i = 0;
 	TupleDesc	desc = ps->ps_ResultTupleSlot ? ps->ps_ResultTupleSlot->tts_tupleDescriptor : NULL;
+	const bool	has_motion = plan_has_motion(ps->plan);
 
+	/* 1. decisions that follow from the plan alone (the same on every segment): translation, node support */
 	if (cplan == NULL || desc == NULL)
 		return false;
 	if (shim_ctx == NULL && cbgpu_ctx_create(GpIdentity.segindex >= 0 ? GpIdentity.segindex % Max(cbgpu_device_count(), 1) : 0, &shim_ctx) != CBGPU_OK)
+		SHIM_LOCAL_FAILURE(has_motion, (CbgpuShim *) NULL, "cbgpu: no CUDA context on segment %d", GpIdentity.segindex);
+	shim = (CbgpuShim *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(CbgpuShim));
+	shim->rt = (cbgpu_rel **) MemoryContextAllocZero(estate->es_query_cxt, sizeof(cbgpu_rel *) * Max(list_length(rels), 1));
+	shim->cbestate = cb_CreateExecutorState(shim_ctx, shim->rt, list_length(rels));
+	shim->cbestate->es_segindex = GpIdentity.segindex;
+	shim->cbestate->es_numsegments = getgpsegmentCount();
+	shim->cbps = cb_ExecInitNode(cplan, shim->cbestate, 0);	/* validates the node types before a byte is loaded */
+	if (shim->cbps == NULL)
+	{
+		shim_release(shim);
 		return false;
-	rt = (cbgpu_rel **) palloc0(sizeof(cbgpu_rel *) * Max(list_length(rels), 1));
+	}
+	/* 2. from here on this segment is committed: load the base tables (device memory the shim owns from now on) */
 	foreach(lc, rels)
 	{
 		ShimScan   *sc = (ShimScan *) lfirst(lc);
 		Relation	r = ExecGetRangeTableRelation(estate, sc->scanrelid);
 
-		rt[i] = cbgpu_shim_load_relation(shim_ctx, r, sc->attnos);
-		if (rt[i] == NULL)
-			return false;
+		shim->rt[i] = cbgpu_shim_load_relation(shim_ctx, r, sc->attnos);
+		shim->nrt = i + 1;
+		if (shim->rt[i] == NULL)
+			SHIM_LOCAL_FAILURE(has_motion, shim, "cbgpu: relation \"%s\" cannot be loaded on segment %d", RelationGetRelationName(r), GpIdentity.segindex);
+		shim->cbestate->es_range_table[i] = shim->rt[i];
 		i++;
 	}
 	/* string literals -> this segment's dictionary codes, now that the dictionaries exist */
@@ -720,22 +765,14 @@ shim_take_over(PlanState *ps, EState *estate)
 		struct varlena *v = (struct varlena *) DatumGetPointer(pc->c->constvalue);
 
 		if (dict == NULL)
-			return false;
+			SHIM_LOCAL_FAILURE(has_motion, shim, "cbgpu: no dictionary for a string qual on segment %d", GpIdentity.segindex);
 		/* -1 (the value occurs nowhere in this segment's files) stays -1: = is false, <> true for every non-NULL row */
 		pc->x->constval = cbgpu_dict_lookup(dict, VARDATA_ANY(v), (int32) VARSIZE_ANY_EXHDR(v));
 	}
 	pending_consts = NIL;
-	shim = (CbgpuShim *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(CbgpuShim));
-	shim->cbestate = cb_CreateExecutorState(shim_ctx, rt, list_length(rels));
 	shim->cbestate->es_interconnect = cbgpu_shim_interconnect(shim_ctx, estate);
-	shim->cbestate->es_segindex = GpIdentity.segindex;
-	shim->cbestate->es_numsegments = getgpsegmentCount();
-	shim->cbps = cb_ExecInitNode(cplan, shim->cbestate, 0);
-	if (shim->cbps == NULL)
-	{
-		shim_release(shim);
-		return false;
-	}
+	if (has_motion && shim->cbestate->es_interconnect == NULL && getgpsegmentCount() > 1)
+		SHIM_LOCAL_FAILURE(true, shim, "cbgpu: no GPU interconnect on segment %d", GpIdentity.segindex);
 	shim->natts = desc->natts;
 	shim->atttypes = (CbTypeId *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(CbTypeId) * Max(desc->natts, 1));
 	shim->attdscales = (int32 *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(int32) * Max(desc->natts, 1));

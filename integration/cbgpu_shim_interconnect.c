@@ -118,9 +118,12 @@ cbgpu_shim_interconnect(cbgpu_ctx *ctx, EState *estate)
 		return session_ic;
 	if (session_ic != NULL)
 	{
-		/* the dispatcher replaced the token: the old communicator is abandoned on every segment alike */
+		/* the dispatcher replaced the token (it does after a query that died in error): the old communicator is abandoned on
+		 * every segment alike, WITHOUT a collective step - a peer may have left an exchange half done, and
+		 * cbgpu_motion_destroy's barrier would wait for it for ever (cbgpu_motion_abort: ncclCommAbort, unmap, free;
+		 * the reference's TeardownInterconnect with hasErrors, cdb/ml_ipc.h:106) */
 		cb_interconnect_destroy(session_ic);
-		cbgpu_motion_destroy(session_motion);
+		cbgpu_motion_abort(session_motion);
 		session_ic = NULL;
 		session_motion = NULL;
 	}

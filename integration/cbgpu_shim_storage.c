@@ -211,17 +211,44 @@ cbgpu_shim_load_relation(cbgpu_ctx *ctx, Relation rel, List *projected_attnos)
 		if (spec[c].varkind != CBGPU_AOCS_VAR_DICT)
 			continue;
 		if (cbgpu_dict_create(ctx, 1 << 20, (int64) 256 << 20, TupleDescAttr(td, attno[c] - 1)->atttypid == BPCHAROID, &spec[c].dict) != CBGPU_OK)
+		{
+			cbgpu_rel_free(out);
 			ereport(ERROR, (errcode(ERRCODE_INTERNAL_ERROR), errmsg("cbgpu: %s", cbgpu_last_error(ctx))));
+		}
 		for (int s = 0; s < nsegs; s++)
 		{
 			if (segs[s]->state != AOSEG_STATE_DEFAULT || segs[s]->total_tupcount == 0)
 				continue;
 			spec[c].eof = getAOCSVPEntry(segs[s], attno[c] - 1)->eof;
 			if (cb_aocs_dict_collect_segfile(ctx, basepath, segs[s]->segno, checksum, &spec[c], err, sizeof(err)) != CBGPU_OK)
+			{
+				cbgpu_dict_free(spec[c].dict);
+				cbgpu_rel_free(out);
 				ereport(ERROR, (errcode(ERRCODE_DATA_CORRUPTED), errmsg("cbgpu: %s", err)));
+			}
 		}
 		if (cbgpu_dict_finalize(spec[c].dict, NULL) != CBGPU_OK)
+		{
+			cbgpu_dict_free(spec[c].dict);
+			cbgpu_rel_free(out);
 			ereport(ERROR, (errcode(ERRCODE_INTERNAL_ERROR), errmsg("cbgpu: %s", cbgpu_last_error(ctx))));
+		}
+		/* a reload of the relation supersedes the older dictionary of this column: give its 256 MB arena back */
+		{
+			ListCell   *dl;
+
+			foreach(dl, shim_dicts)
+			{
+				ShimDict   *od = (ShimDict *) lfirst(dl);
+
+				if (od->relid == RelationGetRelid(rel) && od->attno == attno[c])
+				{
+					cbgpu_dict_free(od->dict);
+					shim_dicts = foreach_delete_current(shim_dicts, dl);
+					pfree(od);
+				}
+			}
+		}
 		old = MemoryContextSwitchTo(TopMemoryContext);
 		sd = palloc(sizeof(ShimDict));
 		sd->relid = RelationGetRelid(rel);

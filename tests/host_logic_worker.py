@@ -90,8 +90,31 @@ def main():
     out["ran"]["q1_after_refusals"] = {"rows": len(ex.run(tpch.q1_plan(1)).rows)}
     ex.close()
 
-    # 3b. device out-of-memory at every allocation of a join query in turn: an error (never a crash), and the next run is clean
+    # 3a. CHECK_FOR_INTERRUPTS: the callback is polled before every pipeline; pending after the 2nd poll -> the query stops with
+    #     CBGPU_ERR_INTERRUPTED having launched fewer kernels than a full run, and the executor runs the next query
     import ctypes as C
+    polls = {"n": 0}
+
+    def pending(_es):
+        polls["n"] += 1
+        return 1 if polls["n"] > 2 else 0
+    cb = C.CFUNCTYPE(C.c_int, C.c_void_p)(pending)
+    ex = capi.Executor(ctx, dev)
+    full = ctx.launches()
+    ex.run(tpch.q5_plan(reg, 1))
+    full = ctx.launches() - full
+    ex.estate.contents.es_interrupt_pending = C.cast(cb, C.c_void_p)
+    before = ctx.launches()
+    try:
+        ex.run(tpch.q5_plan(reg, 1))
+        out["interrupt"] = {"code": None}
+    except capi.CbgpuError as e:
+        out["interrupt"] = {"code": e.code, "msg": str(e), "launches": ctx.launches() - before, "full": full, "polls": polls["n"]}
+    ex.estate.contents.es_interrupt_pending = None
+    out["interrupt"]["rows_after"] = len(ex.run(tpch.q5_plan(reg, 1)).rows)
+    ex.close()
+
+    # 3b. device out-of-memory at every allocation of a join query in turn: an error (never a crash), and the next run is clean
     fake = C.CDLL(None)
     fake.fake_cudart_fail_alloc_in.argtypes = [C.c_long]
     ex = capi.Executor(ctx, dev)

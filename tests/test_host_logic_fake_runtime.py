@@ -52,6 +52,9 @@ def _check(out):
         assert refused[name]["code"] == code and frag in refused[name]["error"], refused[name]
     for name in ("having", "sorted_agg", "numeric_join_key", "bad_scanrelid"):
         assert refused[name]["launches"] == 0          # refused before anything reached the device
+    # CHECK_FOR_INTERRUPTS between pipelines: the query stops early with its own code, the next one runs
+    it = out["interrupt"]
+    assert it["code"] == -8 and "canceling statement" in it["msg"] and it["launches"] < it["full"] and it["polls"] == 3 and it["rows_after"] == 0
     # the segment file loader: reference file naming, bytes past the recorded EOF ignored, and what cannot be read says why
     seg = out["segfile"]
     rows = seg["rows"]["int4_plain"]

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Run TPC-H Q1 / Q3 / Q5 over device-generated synthetic tables on one GPU and print timings
+"""Run TPC-H Q1 / Q3 / Q5 (and SSB Q4.x: --queries ssb4.1,ssb4.2,ssb4.3) over device-generated synthetic tables and print timings
 (harness / profiling aid; bench.py is the contract benchmark)."""
 import argparse
 import json
@@ -40,23 +40,32 @@ def main():
     else:
         rt, sz = device_tables(ctx, args.sf)
     ex = capi.Executor(ctx, rt, force_generic=args.generic, motion=motion)
+    ssb_ex = None
+    if any(q.startswith("ssb") for q in args.queries.split(",")):
+        from cloudberry_b200 import ssb
+        ssb_dev, ssb_sz = ssb.device_tables(ctx, args.sf, capi.hashbpchar, rank, world)
+        ssb_ex = capi.Executor(ctx, ssb_dev, force_generic=args.generic, motion=motion)
     plans = {"q1": lambda: tpch.q1_plan(world), "q3": lambda: tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), world, customer_replicated=False),
              "q5": lambda: tpch.q5_plan(tpch.REGIONS.index("AMERICA"), world, replicated=False)}
     rows_in = {"q1": sz["lineitem"], "q3": sz["lineitem"] + sz["orders"] + sz["customer"],
                "q5": sz["lineitem"] + sz["orders"] + sz["customer"] + sz["supplier"] + 30}
     for q in args.queries.split(","):
+        if q.startswith("ssb"):
+            plans[q] = lambda q=q: ssb.PLANS["q" + q[3:]](world)
+            rows_in[q] = ssb.query_rows_bytes(ssb_sz)[0]
         plan = plans[q]()
-        res = ex.run(plan)       # warm-up
+        ex_q = ssb_ex if q.startswith("ssb") else ex
+        res = ex_q.run(plan)       # warm-up
         times = []
         for _ in range(args.steps):
             ctx.kernel_log_reset()
             ctx.timer_start()
-            res = ex.run(plan)
+            res = ex_q.run(plan)
             times.append(ctx.timer_stop_ms())
         kn, km = ctx.longest_kernel()
         if args.trace:
             ctx.trace_begin()
-            ex.run(plan)
+            ex_q.run(plan)
             tr = ctx.trace_end()
             if rank != 0:
                 continue
