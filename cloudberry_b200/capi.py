@@ -180,7 +180,7 @@ class CbTupleTableSlot(C.Structure):
 
 class CbInstrumentation(C.Structure):
     _fields_ = [("ntuples", C.c_double), ("nloops", C.c_double), ("kernels", C.c_int64), ("device_ms", C.c_double),
-                ("rows_in", C.c_int64), ("motion_repartitions", C.c_int64)]
+                ("rows_in", C.c_int64), ("motion_repartitions", C.c_int64), ("hashjoin_nbatch", C.c_int64), ("agg_npartitions", C.c_int64)]
 
 
 class CbPlanState(C.Structure):
@@ -199,7 +199,8 @@ class CbEState(C.Structure):
                 ("es_segindex", C.c_int32), ("es_numsegments", C.c_int32), ("es_interconnect", C.c_void_p),
                 ("es_errcode", C.c_int32), ("es_errmsg", C.c_char * 512), ("es_error_hook", C.c_void_p),
                 ("es_force_generic", C.c_int32), ("es_processed", C.c_int64), ("es_cluster", C.c_void_p),
-                ("es_interrupt_pending", C.c_void_p), ("es_interrupt_arg", C.c_void_p), ("es_operator_mem_kb", C.c_int64)]
+                ("es_interrupt_pending", C.c_void_p), ("es_interrupt_arg", C.c_void_p), ("es_operator_mem_kb", C.c_int64),
+                ("es_hashjoin_batches_run", C.c_int64), ("es_agg_partitions_run", C.c_int64)]
 
 
 def header_symbols(header):
@@ -713,7 +714,8 @@ def _collect_instrument(ps, out):
     ins = n.instrument
     out[n.plan.contents.plan_node_id] = {"node": n.type, "ntuples": ins.ntuples, "kernels": ins.kernels,
                                          "device_ms": ins.device_ms, "rows_in": ins.rows_in,
-                                         "motion_repartitions": ins.motion_repartitions}
+                                         "motion_repartitions": ins.motion_repartitions, "hashjoin_nbatch": ins.hashjoin_nbatch,
+                                         "agg_npartitions": ins.agg_npartitions}
     _collect_instrument(n.lefttree, out)
     _collect_instrument(n.righttree, out)
 
@@ -721,13 +723,15 @@ def _collect_instrument(ps, out):
 class Executor:
     """ExecutorStart / ExecutorRun / ExecutorEnd for one segment (one GPU)."""
 
-    def __init__(self, ctx, range_table, force_generic=False, motion=None):
+    def __init__(self, ctx, range_table, force_generic=False, motion=None, operator_mem_kb=0):
         self.ctx = ctx
         self.E = ex()
         n = len(range_table)
         arr = (C.c_void_p * max(n, 1))(*[r.h for r in range_table])
         self.estate = self.E.cb_CreateExecutorState(ctx.h, arr, n)
         self.estate.contents.es_force_generic = 1 if force_generic else 0
+        # PlanStateOperatorMemKB: hash join build sides / aggregate tables larger than this run in batches / partitions
+        self.estate.contents.es_operator_mem_kb = int(operator_mem_kb)
         self._keep = [arr, range_table]
         self.ic = None
         if motion is not None:

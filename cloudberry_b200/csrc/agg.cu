@@ -110,6 +110,26 @@ cbgpu_agg_create(cbgpu_ctx *ctx, int32_t nkeys, int32_t naccs, const int32_t *ac
 	return cbgpu_agg_reset(t);
 }
 
+/* device bytes one slot of an aggregate table takes (two slots per group are provisioned: load factor <= 0.5) */
+extern "C" int64_t
+cbgpu_agg_slot_bytes(int32_t nkeys, int32_t naccs)
+{
+	return 4 + 4 + 4 + 8 * (int64_t) (nkeys ? nkeys : 1) + (8 + 16) * (int64_t) (naccs ? naccs : 1);
+}
+
+extern "C" int
+cbgpu_agg_set_partition(cbgpu_aggtable *t, int32_t npart, int32_t part)
+{
+	if (npart < 1 || npart > 65536 || (npart & (npart - 1)) != 0 || part < 0 || part >= npart)
+		return cb_fail(t->ctx, CBGPU_ERR_INVALID, "aggregate partition %s%lld out of range", "", part);
+	t->d.npart = npart;
+	t->d.part_id = part;
+	t->d.part_shift = 32;
+	for (int b = npart; b > 1; b >>= 1)
+		t->d.part_shift--;
+	return CBGPU_OK;
+}
+
 extern "C" void
 cbgpu_agg_free(cbgpu_aggtable *t)
 {

@@ -108,6 +108,12 @@ struct AggDev
 	uint32_t	mask;			/* capacity - 1                                                       */
 	int32_t		nkeys;
 	int32_t		naccs;
+	/* partitioned aggregation (the reference's spill-and-reload of over-budget hash aggregation, nodeAgg.c:2149
+	 * hash_agg_check_limits, :3215 agg_refill_hash_table, done by re-scanning instead of spilling): a pass aggregates only the
+	 * rows whose group hash has part_id in its top bits; npart <= 1: off */
+	int32_t		npart;
+	int32_t		part_shift;
+	int32_t		part_id;
 	int32_t    *state;			/* [cap] 0 empty, 1 being written, 2 ready                            */
 	uint32_t   *hash;			/* [cap]                                                              */
 	int64_t    *keys;			/* [cap][nkeys]                                                       */
@@ -158,7 +164,20 @@ struct HtDev
 	 * dictionary codes, and int8 keys between INT32_MIN and INT32_MAX are not used: see 2), 2: the uint32 domain
 	 * (int8 keys in [0, 2^32): TPC-H order keys up to SF 1000).  0: hash in the slot, key verified by row id. */
 	int32_t		keyslot;
+	/* multi-batch hybrid hash join (nodeHash.c:980-990 nbatch, :2223-2242 ExecHashGetBucketAndBatch: the batch number
+	 * comes from hash bits the bucket number does not use): the table holds ONE batch of the build side at a time - the
+	 * rows whose (hash >> batch_shift) == batch_id - and a probe row of another batch is not this pass's business
+	 * (it is neither matched nor, for outer / anti joins, emitted unmatched: its own pass does that).  nbatch <= 1: off. */
+	int32_t		nbatch;
+	int32_t		batch_shift;
+	int32_t		batch_id;
 };
+
+CB_HD_DECL bool
+ht_in_batch(int32_t nbatch, int32_t batch_shift, int32_t batch_id, uint32_t hash)
+{
+	return nbatch <= 1 || (int32_t) (hash >> batch_shift) == batch_id;
+}
 
 /* is an outer key value inside a key-in-slot table's domain?  Outside it nothing can match. */
 CB_HD_DECL bool
@@ -176,6 +195,8 @@ struct cbgpu_hashtable
 	int64_t		ninserted;
 	int		   *d_flags;		/* [0] duplicates seen, [1] inserted count                            */
 	int			has_dups;
+	int64_t		total_rows;		/* multi-batch: rows of all batches                                   */
+	int64_t		built_bytes;	/* slots + filter of what is resident                                 */
 };
 
 /* ---------------------------------------------------------------------------------------------

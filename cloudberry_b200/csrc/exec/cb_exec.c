@@ -614,6 +614,41 @@ stream_over_rel(CbEState *es, CbStream *s, cbgpu_rel *rel, const PExpr *shape, i
 	return CBGPU_OK;
 }
 
+/*
+ * Run a pipeline.  When one of its probes is a multi-batch hash join (the build side did not fit the operator's memory,
+ * nodeHash.c:980-990) the pipeline runs once per batch, each pass with that batch of the build side resident and the
+ * probe rows of other batches skipped (ExecHashJoinImpl's HJ_NEED_NEW_BATCH loop, nodeHashjoin.c:709-738, without the
+ * spill files: the outer side is scanned again instead of being written out per batch - HBM bandwidth is cheaper than a
+ * temp file).  The sink accumulates over the passes: aggregates add up, materialised rows append, partitions fill on.
+ */
+static int
+run_pipeline(CbEState *es, CbPipeline *pl)
+{
+	int			multi = -1;
+
+	for (int j = 0; j < pl->nprobes; j++)
+		if (pl->probes[j].ht && cbgpu_ht_nbatch(pl->probes[j].ht) > 1)
+		{
+			if (multi >= 0)
+				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "two multi-batch hash joins in one pipeline (raise the operator memory)");
+			multi = j;
+		}
+	if (multi < 0)
+	{
+		GPU(es, cbgpu_pipeline_run(es->es_ctx, pl));
+		return CBGPU_OK;
+	}
+	for (int b = 0; b < cbgpu_ht_nbatch(pl->probes[multi].ht); b++)
+	{
+		if (es->es_interrupt_pending && es->es_interrupt_pending(es))
+			return es_fail(es, CBGPU_ERR_INTERRUPTED, "canceling statement due to user request");
+		GPU(es, cbgpu_ht_load_batch((cbgpu_hashtable *) pl->probes[multi].ht, b));
+		GPU(es, cbgpu_pipeline_run(es->es_ctx, pl));
+		es->es_hashjoin_batches_run++;
+	}
+	return CBGPU_OK;
+}
+
 /* run the stream into a new relation (MATERIALIZE sink); columns laid out as stream_over_rel expects */
 static int
 stream_materialize(CbEState *es, CbPlanState *ps, CbStream *s, Owned *own, cbgpu_rel **out, PExpr *shape, int *nshape)
@@ -695,7 +730,7 @@ stream_materialize(CbEState *es, CbPlanState *ps, CbStream *s, Owned *own, cbgpu
 	{
 		int64_t		before = cbgpu_kernel_launches(es->es_ctx);
 
-		GPU(es, cbgpu_pipeline_run(es->es_ctx, p));
+		TRY(run_pipeline(es, p));
 		GPU(es, cbgpu_dev_read(es->es_ctx, counter, sizeof(int64_t), &count));	/* the status word rides along */
 		GPU(es, cbgpu_check_status(es->es_ctx));
 		ps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
@@ -829,7 +864,20 @@ hash_build(CbPlanState *hashps)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "hash keys must be plain columns of the Hash node's child on the GPU path");
 		keycols[k] = p->inner_map[ke->varattno - 1];
 	}
-	GPU(es, cbgpu_ht_build(es->es_ctx, rel, keycols, h->nhashkeys, &p->ht));
+	{
+		/* ExecChooseHashTableSize (nodeHash.c:856): one batch if the table fits the operator's memory, else the smallest
+		 * power of two of batches that does */
+		int32_t		nbatch = 1;
+		const int64_t budget = es->es_operator_mem_kb > 0 ? es->es_operator_mem_kb * 1024 : 0;
+
+		while (budget > 0 && nbatch < 4096 && cbgpu_ht_bytes_for((cbgpu_rel_nrows(rel) + nbatch - 1) / nbatch) > budget)
+			nbatch <<= 1;
+		if (nbatch > 1)
+			GPU(es, cbgpu_ht_build_batched(es->es_ctx, rel, keycols, h->nhashkeys, nbatch, &p->ht));
+		else
+			GPU(es, cbgpu_ht_build(es->es_ctx, rel, keycols, h->nhashkeys, &p->ht));
+		hashps->instrument.hashjoin_nbatch = nbatch;
+	}
 	p->owned.hts[p->owned.nhts++] = p->ht;
 	p->inner_rel = rel;
 	hashps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
@@ -912,8 +960,8 @@ open_hashjoin(CbPlanState *ps, CbStream **out)
 		NodePriv   *me = np(ps);
 		int			c;
 
-		if (hj->jointype == CB_JOIN_LEFT)
-			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "LEFT hash join with duplicate build keys is not implemented on the GPU path");
+		if (cbgpu_ht_nbatch(hp->ht) > 1)
+			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "multi-batch hash join with duplicate build keys is not implemented on the GPU path (raise the operator memory)");
 		/* append the key expressions as extra output columns so the probe can read them */
 		for (int k = 0; k < hj->nhashkeys; k++)
 		{
@@ -930,7 +978,10 @@ open_hashjoin(CbPlanState *ps, CbStream **out)
 		if (me->owned.npairs >= 8)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "too many N:M joins under one node");
 		pairs = &me->owned.pairs[me->owned.npairs++];
-		GPU(es, cbgpu_ht_probe_pairs(es->es_ctx, hp->ht, orel, keycols, hj->nhashkeys, NULL, 0, pairs));
+		if (hj->jointype == CB_JOIN_LEFT)
+			GPU(es, cbgpu_ht_probe_pairs_left(es->es_ctx, hp->ht, orel, keycols, hj->nhashkeys, pairs));
+		else
+			GPU(es, cbgpu_ht_probe_pairs(es->es_ctx, hp->ht, orel, keycols, hj->nhashkeys, NULL, 0, pairs));
 		s2 = stream_new(me);
 		TRY(stream_over_rel(es, s2, orel, shape, nouter));
 		s2->pipe.nrows = pairs->npairs;
@@ -941,7 +992,7 @@ open_hashjoin(CbPlanState *ps, CbStream **out)
 		s2->rows_in = s->rows_in;
 		nouter = s2->nout;
 		memcpy(outer, s2->out, sizeof(int) * (size_t) nouter);
-		TRY(inner_out_exprs(es, s2, hp, 1, 0, inner));
+		TRY(inner_out_exprs(es, s2, hp, 1, hj->jointype == CB_JOIN_LEFT, inner));
 		s = s2;
 		vc.s = s;
 	}
@@ -1044,10 +1095,156 @@ typedef struct AggPlanInfo
 	int			key_of_target[MAX_OUT];
 	int			keys[CBP_MAX_KEYS];		/* PE ids                                                    */
 	int			nkeys;
+	/* HAVING: the Aggref nodes of the qual and the accumulators that hold their states */
+#define MAX_HAVING_AGGS 8
+	const CbExpr *having_ref[MAX_HAVING_AGGS];
+	int			having_acc[MAX_HAVING_AGGS];
+	int			nhaving;
 } AggPlanInfo;
 
+/* one Aggref of an Agg node's target list or HAVING clause -> its accumulator (transition state): aggregates with the same
+ * transition function and input share one (find_compatible_pertrans, nodeAgg.c) */
 static int
-agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream **child_stream)
+agg_add_aggref(CbEState *es, VarCtx *vcp, CbStream *s, const CbAgg *agg, AggPlanInfo *info, const CbExpr *te, int *acc_out)
+{
+	VarCtx		vc = *vcp;
+	AccMeta		m;
+	int			found = -1;
+
+	memset(&m, 0, sizeof(m));
+	m.arg[0] = m.arg[1] = m.arg[2] = -1;
+	if (agg->aggsplit == CB_AGGSPLIT_FINAL_DESERIAL)
+	{
+		/* combine functions over partial states */
+		int			a;
+		PExpr	   *st;
+
+		if (te->nargs != 1)
+			return es_fail(es, CBGPU_ERR_INVALID, "final aggregate needs the partial state as its argument");
+		TRY(translate(&vc, te->args[0], &a));
+		st = &s->pe[a];
+		if (st->kind != PE_STATE)
+			return es_fail(es, CBGPU_ERR_INVALID, "final aggregate input is not a partial aggregate state");
+		m.state_kind = st->acckind;
+		m.dscale = st->dscale;
+		m.argtype = st->argtype;
+		switch (st->acckind)
+		{
+			case CBP_ACC_COUNT:
+				m.kind = CBP_ACC_MERGE_COUNT;
+				m.arg[0] = st->cn;
+				m.nargs = 1;
+				break;
+			case CBP_ACC_SUM_INT:
+				m.kind = CBP_ACC_MERGE_INT;
+				m.arg[0] = st->cn; m.arg[1] = st->clo; m.arg[2] = st->chi;
+				m.nargs = 3;
+				break;
+			case CBP_ACC_SUM_FLOAT:
+				m.kind = CBP_ACC_MERGE_FLOAT;
+				m.arg[0] = st->cn; m.arg[1] = st->clo;
+				m.nargs = 2;
+				break;
+			case CBP_ACC_MIN:
+			case CBP_ACC_MAX:
+				m.kind = st->acckind == CBP_ACC_MIN ? CBP_ACC_MERGE_MIN : CBP_ACC_MERGE_MAX;
+				m.arg[0] = st->cn; m.arg[1] = st->clo;
+				m.nargs = 2;
+				break;
+			default:
+				return es_fail(es, CBGPU_ERR_INVALID, "unknown partial state kind %d", st->acckind);
+		}
+	}
+	else
+	{
+		int			a = -1;
+
+		if (te->nargs > 1)
+			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "aggregates with %d arguments are not supported", te->nargs);
+		if (te->nargs == 1)
+		{
+			TRY(translate(&vc, te->args[0], &a));
+			if (s->pe[a].kind == PE_STATE)
+				return es_fail(es, CBGPU_ERR_INVALID, "aggregate argument is a transition state");
+			m.argtype = s->pe[a].type;
+			m.dscale = s->pe[a].dscale;
+		}
+		switch (te->op)
+		{
+			case CB_AGG_COUNT_STAR:
+				m.kind = m.state_kind = CBP_ACC_COUNT;
+				break;
+			case CB_AGG_COUNT:
+				m.kind = m.state_kind = CBP_ACC_COUNT;
+				/* count(x) over a NOT NULL input is count(*) */
+				if (a >= 0 && s->pe[a].maybe_null)
+				{
+					m.arg[0] = a;
+					m.nargs = 1;
+				}
+				break;
+			case CB_AGG_SUM:
+			case CB_AGG_AVG:
+				if (a < 0)
+					return es_fail(es, CBGPU_ERR_INVALID, "sum/avg without an argument");
+				m.kind = m.state_kind = (m.argtype == CB_FLOAT8) ? CBP_ACC_SUM_FLOAT : CBP_ACC_SUM_INT;
+				m.arg[0] = a;
+				m.nargs = 1;
+				break;
+			case CB_AGG_MIN:
+			case CB_AGG_MAX:
+				if (a < 0 || m.argtype == CB_FLOAT8)
+					return es_fail(es, CBGPU_ERR_UNSUPPORTED, "min/max over float8 is not implemented on the GPU path");
+				m.kind = m.state_kind = te->op == CB_AGG_MIN ? CBP_ACC_MIN : CBP_ACC_MAX;
+				m.arg[0] = a;
+				m.nargs = 1;
+				break;
+			default:
+				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "aggregate function %d is not supported on the GPU path", te->op);
+		}
+	}
+	/* aggregates with the same transition function and input share one state
+	 * (find_compatible_pertrans, nodeAgg.c) */
+	for (int j = 0; j < info->naccs; j++)
+		if (info->acc[j].kind == m.kind && info->acc[j].arg[0] == m.arg[0] && info->acc[j].arg[1] == m.arg[1] &&
+			info->acc[j].arg[2] == m.arg[2])
+			found = j;
+	if (found < 0)
+	{
+		if (info->naccs >= CBP_MAX_AGGS)
+			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "more than %d distinct aggregate states", CBP_MAX_AGGS);
+		found = info->naccs++;
+		info->acc[found] = m;
+	}
+	*acc_out = found;
+	return CBGPU_OK;
+}
+
+/* HAVING: collect the accumulators its Aggrefs need (walks the qual tree) */
+static int
+agg_collect_having(CbEState *es, VarCtx *vc, CbStream *s, const CbAgg *agg, AggPlanInfo *info, const CbExpr *e)
+{
+	if (e->tag == T_CbAggref)
+	{
+		int			a;
+
+		if (info->nhaving >= MAX_HAVING_AGGS)
+			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "more than %d aggregates in HAVING", MAX_HAVING_AGGS);
+		TRY(agg_add_aggref(es, vc, s, agg, info, e, &a));
+		info->having_ref[info->nhaving] = e;
+		info->having_acc[info->nhaving] = a;
+		info->nhaving++;
+		return CBGPU_OK;
+	}
+	for (int i = 0; i < e->nargs && (e->tag == T_CbOpExpr || e->tag == T_CbBoolExpr); i++)
+		TRY(agg_collect_having(es, vc, s, agg, info, e->args[i]));
+	return CBGPU_OK;
+}
+
+/* the child's rows aggregated: *table_out holds the groups - or, when they did not fit the operator's memory and the
+ * aggregation ran in partitions, *parts_out holds them already as a relation (keys, then N / lo / hi per state) */
+static int
+agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream **child_stream, cbgpu_rel **parts_out)
 {
 	CbEState   *es = ps->state;
 	CbAgg	   *agg = (CbAgg *) ps->plan;
@@ -1069,8 +1266,6 @@ agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream
 		return es_fail(es, CBGPU_ERR_UNSUPPORTED, "GROUP BY with %d columns is beyond the GPU path's limit (%d)", agg->numCols, CBP_MAX_KEYS);
 	if (agg->aggstrategy != CB_AGG_HASHED && agg->aggstrategy != CB_AGG_PLAIN)
 		return es_fail(es, CBGPU_ERR_UNSUPPORTED, "only hashed / plain aggregation runs on the GPU path");
-	if (ps->plan->nquals > 0)
-		return es_fail(es, CBGPU_ERR_UNSUPPORTED, "HAVING is not implemented on the GPU path");
 	info->nkeys = agg->numCols;
 	for (int k = 0; k < agg->numCols; k++)
 	{
@@ -1085,7 +1280,6 @@ agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream
 	for (int i = 0; i < ps->plan->ntargets; i++)
 	{
 		const CbExpr *te = ps->plan->targetlist[i].expr;
-		AccMeta		m;
 		int			found = -1;
 
 		info->acc_of_target[i] = -1;
@@ -1101,113 +1295,12 @@ agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream
 		}
 		if (te->tag != T_CbAggref)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "Agg targetlist entries must be grouping Vars or Aggrefs on the GPU path");
-		memset(&m, 0, sizeof(m));
-		m.arg[0] = m.arg[1] = m.arg[2] = -1;
-		if (agg->aggsplit == CB_AGGSPLIT_FINAL_DESERIAL)
-		{
-			/* combine functions over partial states */
-			int			a;
-			PExpr	   *st;
-
-			if (te->nargs != 1)
-				return es_fail(es, CBGPU_ERR_INVALID, "final aggregate needs the partial state as its argument");
-			TRY(translate(&vc, te->args[0], &a));
-			st = &s->pe[a];
-			if (st->kind != PE_STATE)
-				return es_fail(es, CBGPU_ERR_INVALID, "final aggregate input is not a partial aggregate state");
-			m.state_kind = st->acckind;
-			m.dscale = st->dscale;
-			m.argtype = st->argtype;
-			switch (st->acckind)
-			{
-				case CBP_ACC_COUNT:
-					m.kind = CBP_ACC_MERGE_COUNT;
-					m.arg[0] = st->cn;
-					m.nargs = 1;
-					break;
-				case CBP_ACC_SUM_INT:
-					m.kind = CBP_ACC_MERGE_INT;
-					m.arg[0] = st->cn; m.arg[1] = st->clo; m.arg[2] = st->chi;
-					m.nargs = 3;
-					break;
-				case CBP_ACC_SUM_FLOAT:
-					m.kind = CBP_ACC_MERGE_FLOAT;
-					m.arg[0] = st->cn; m.arg[1] = st->clo;
-					m.nargs = 2;
-					break;
-				case CBP_ACC_MIN:
-				case CBP_ACC_MAX:
-					m.kind = st->acckind == CBP_ACC_MIN ? CBP_ACC_MERGE_MIN : CBP_ACC_MERGE_MAX;
-					m.arg[0] = st->cn; m.arg[1] = st->clo;
-					m.nargs = 2;
-					break;
-				default:
-					return es_fail(es, CBGPU_ERR_INVALID, "unknown partial state kind %d", st->acckind);
-			}
-		}
-		else
-		{
-			int			a = -1;
-
-			if (te->nargs > 1)
-				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "aggregates with %d arguments are not supported", te->nargs);
-			if (te->nargs == 1)
-			{
-				TRY(translate(&vc, te->args[0], &a));
-				if (s->pe[a].kind == PE_STATE)
-					return es_fail(es, CBGPU_ERR_INVALID, "aggregate argument is a transition state");
-				m.argtype = s->pe[a].type;
-				m.dscale = s->pe[a].dscale;
-			}
-			switch (te->op)
-			{
-				case CB_AGG_COUNT_STAR:
-					m.kind = m.state_kind = CBP_ACC_COUNT;
-					break;
-				case CB_AGG_COUNT:
-					m.kind = m.state_kind = CBP_ACC_COUNT;
-					/* count(x) over a NOT NULL input is count(*) */
-					if (a >= 0 && s->pe[a].maybe_null)
-					{
-						m.arg[0] = a;
-						m.nargs = 1;
-					}
-					break;
-				case CB_AGG_SUM:
-				case CB_AGG_AVG:
-					if (a < 0)
-						return es_fail(es, CBGPU_ERR_INVALID, "sum/avg without an argument");
-					m.kind = m.state_kind = (m.argtype == CB_FLOAT8) ? CBP_ACC_SUM_FLOAT : CBP_ACC_SUM_INT;
-					m.arg[0] = a;
-					m.nargs = 1;
-					break;
-				case CB_AGG_MIN:
-				case CB_AGG_MAX:
-					if (a < 0 || m.argtype == CB_FLOAT8)
-						return es_fail(es, CBGPU_ERR_UNSUPPORTED, "min/max over float8 is not implemented on the GPU path");
-					m.kind = m.state_kind = te->op == CB_AGG_MIN ? CBP_ACC_MIN : CBP_ACC_MAX;
-					m.arg[0] = a;
-					m.nargs = 1;
-					break;
-				default:
-					return es_fail(es, CBGPU_ERR_UNSUPPORTED, "aggregate function %d is not supported on the GPU path", te->op);
-			}
-		}
-		/* aggregates with the same transition function and input share one state
-		 * (find_compatible_pertrans, nodeAgg.c) */
-		for (int j = 0; j < info->naccs; j++)
-			if (info->acc[j].kind == m.kind && info->acc[j].arg[0] == m.arg[0] && info->acc[j].arg[1] == m.arg[1] &&
-				info->acc[j].arg[2] == m.arg[2])
-				found = j;
-		if (found < 0)
-		{
-			if (info->naccs >= CBP_MAX_AGGS)
-				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "more than %d distinct aggregate states", CBP_MAX_AGGS);
-			found = info->naccs++;
-			info->acc[found] = m;
-		}
+		TRY(agg_add_aggref(es, &vc, s, agg, info, te, &found));
 		info->acc_of_target[i] = found;
 	}
+
+	for (int i = 0; i < ps->plan->nquals; i++)
+		TRY(agg_collect_having(es, &vc, s, agg, info, ps->plan->qual[i]));
 
 	/* program tail: key values, then the accumulators' arguments */
 	CbPipeline *pl = &s->pipe;
@@ -1254,6 +1347,17 @@ agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream
 	for (int a = 0; a < info->naccs; a++)
 		kinds[a] = info->acc[a].kind;
 	pl->force_generic = es->es_force_generic;
+	*table_out = NULL;
+	if (parts_out)
+		*parts_out = NULL;
+	/* the operator's memory (PlanStateOperatorMemKB, execnodes.h:1166) bounds the table: two slots per group */
+	const int64_t max_cap = es->es_operator_mem_kb > 0 && parts_out ?
+		(es->es_operator_mem_kb * 1024 / (2 * cbgpu_agg_slot_bytes(info->nkeys, info->naccs)) > 1024 ?
+		 es->es_operator_mem_kb * 1024 / (2 * cbgpu_agg_slot_bytes(info->nkeys, info->naccs)) : 1024) : 0;
+	int			npart = 1;
+
+	if (max_cap > 0 && cap > max_cap)
+		cap = max_cap;
 	for (;;)
 	{
 		cbgpu_aggtable *t;
@@ -1261,9 +1365,11 @@ agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream
 		int			rc;
 		int64_t		before = cbgpu_kernel_launches(es->es_ctx);
 
+		if (npart > 1)
+			break;
 		GPU(es, cbgpu_agg_create(es->es_ctx, info->nkeys, info->naccs, kinds, cap, &t));
 		pl->sink.agg = t;
-		rc = cbgpu_pipeline_run(es->es_ctx, pl);
+		rc = run_pipeline(es, pl);
 		if (rc == CBGPU_OK)
 		{
 			/* the group count's read-back fetches the status word too: one round trip for both.  A full
@@ -1278,12 +1384,21 @@ agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream
 		ps->instrument.rows_in += s->rows_in;
 		if (cbgpu_last_kernel_ms(es->es_ctx) > 0)
 			ps->instrument.device_ms += cbgpu_last_kernel_ms(es->es_ctx);
+		if (rc == CBGPU_ERR_NOMEM && max_cap > 0 && cap >= max_cap)
+		{
+			/* the groups do not fit the operator's memory: aggregate in partitions (below) */
+			cbgpu_agg_free(t);
+			npart = 2;
+			continue;
+		}
 		if (rc == CBGPU_ERR_NOMEM && cap < pl->nrows)
 		{
 			/* more groups than estimated: the reference grows its table (simplehash SH_GROW) or
 			 * spills; here: a larger table and another pass */
 			cbgpu_agg_free(t);
 			cap = cap * 8 < pl->nrows ? cap * 8 : pl->nrows;
+			if (max_cap > 0 && cap > max_cap)
+				cap = max_cap;
 			continue;
 		}
 		if (rc != CBGPU_OK)
@@ -1294,6 +1409,101 @@ agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream
 		p->owned.aggs[p->owned.naggs++] = t;
 		*table_out = t;
 		break;
+	}
+	/* partitioned aggregation: pass k aggregates the groups whose hash selects partition k into a table of the budget's size
+	 * and hands them over as rows; a partition that still overflows doubles the partition count and starts over (the
+	 * reference halves its spill partitions recursively, nodeAgg.c:3215 agg_refill_hash_table) */
+	while (npart > 1)
+	{
+		cbgpu_rel  *pieces[256];
+		int			npieces = 0;
+		int64_t		total = 0;
+		int32_t		keytypes[CBP_MAX_KEYS];
+		int			rc = CBGPU_OK;
+		int			overflow = 0;
+
+		if (npart > 256)
+			return es_fail(es, CBGPU_ERR_NOMEM, "hash aggregation does not fit the operator's memory even in 256 partitions");
+		for (int k = 0; k < info->nkeys; k++)
+			keytypes[k] = s->pe[info->keys[k]].type;
+		for (int part = 0; part < npart && rc == CBGPU_OK && !overflow; part++)
+		{
+			cbgpu_aggtable *t;
+			int64_t		ng;
+			int			rc2;
+
+			if (es->es_interrupt_pending && es->es_interrupt_pending(es))
+				rc = es_fail(es, CBGPU_ERR_INTERRUPTED, "canceling statement due to user request");
+			if (rc == CBGPU_OK)
+				rc = cbgpu_agg_create(es->es_ctx, info->nkeys, info->naccs, kinds, max_cap, &t);
+			if (rc != CBGPU_OK)
+				break;
+			cbgpu_agg_set_partition(t, npart, part);
+			pl->sink.agg = t;
+			rc = run_pipeline(es, pl);
+			if (rc == CBGPU_OK)
+			{
+				rc2 = cbgpu_agg_ngroups(t, &ng);
+				rc = cbgpu_check_status(es->es_ctx);
+				if (rc == CBGPU_OK && rc2 == CBGPU_ERR_NOMEM)
+					overflow = 1;
+				else if (rc == CBGPU_OK)
+					rc = rc2;
+			}
+			if (rc == CBGPU_OK && !overflow)
+			{
+				rc = cbgpu_agg_to_rel(t, keytypes, &pieces[npieces]);
+				if (rc == CBGPU_OK)
+					total += cbgpu_rel_nrows(pieces[npieces++]);
+			}
+			cbgpu_agg_free(t);
+			es->es_agg_partitions_run++;
+			ps->instrument.rows_in += s->rows_in;
+		}
+		if (rc == CBGPU_OK && !overflow)
+		{
+			/* the pieces back to back: the groups of the whole input */
+			cbgpu_rel  *all = NULL;
+			int32_t		types[CBP_MAX_OUT];
+			const int	ncols = info->nkeys + 3 * info->naccs;
+			int64_t		at = 0;
+
+			for (int c = 0; c < ncols; c++)
+				types[c] = c < info->nkeys ? keytypes[c] : CB_INT8;
+			rc = cbgpu_rel_create(es->es_ctx, total, ncols, types, NULL, &all);
+			for (int k = 0; k < info->nkeys && rc == CBGPU_OK; k++)
+			{
+				int			anynull = 0;
+
+				for (int i = 0; i < npieces; i++)
+					anynull |= cbgpu_rel_has_nulls(pieces[i], k);
+				if (anynull)
+					rc = cbgpu_rel_add_nullmap(all, k);
+			}
+			for (int i = 0; i < npieces && rc == CBGPU_OK; i++)
+			{
+				const int64_t n = cbgpu_rel_nrows(pieces[i]);
+
+				if (n > 0)
+					rc = cbgpu_rel_copy_rows(all, at, pieces[i], 0, n);
+				at += n;
+			}
+			if (rc == CBGPU_OK)
+			{
+				p->owned.rels[p->owned.nrels++] = all;
+				*parts_out = all;
+				ps->instrument.agg_npartitions = npart;
+			}
+			else if (all)
+				cbgpu_rel_free(all);
+		}
+		for (int i = 0; i < npieces; i++)
+			cbgpu_rel_free(pieces[i]);
+		if (rc != CBGPU_OK)
+			return es->es_errcode ? es->es_errcode : es_fail(es, rc, "%s", cbgpu_last_error(es->es_ctx));
+		if (!overflow)
+			break;
+		npart *= 2;
 	}
 	pl->nops = saved_nops;
 	return CBGPU_OK;
@@ -1418,7 +1628,7 @@ agg_result(CbPlanState *ps)
 	uint32_t   *keynull;
 	int			nk, na;
 
-	TRY(agg_run(ps, &info, &t, &cs));
+	TRY(agg_run(ps, &info, &t, &cs, NULL));
 	GPU(es, cbgpu_agg_ngroups(t, &ng));
 	nk = info.nkeys ? info.nkeys : 1;
 	na = info.naccs ? info.naccs : 1;
@@ -1486,6 +1696,298 @@ agg_result(CbPlanState *ps)
 	return CBGPU_OK;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * HAVING (Agg.plan.qual; ExecQual over the finalised aggregates, nodeAgg.c:2460 / 3100): evaluated on the host over the
+ * groups' exact states - a value is the rational num / (den * 10^scale) - so that `sum(x) > 100.00` or `avg(x) <= y` decide
+ * exactly as numeric arithmetic does.  The groups that pass become a selection vector over the groups' relation.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct HVal
+{
+	__int128	num;
+	int64_t		den;			/* > 0                                                                */
+	int			scale;
+	int			isnull;
+	int			isbool;			/* num is 0 / 1                                                       */
+} HVal;
+
+typedef struct HCtx
+{
+	CbEState   *es;
+	const CbAgg *agg;
+	const AggPlanInfo *info;
+	CbStream   *cs;				/* the child's stream: types and scales of the grouping columns           */
+	int64_t		g;				/* group (row of the groups' relation)                                */
+	int64_t   **keycol;			/* [nkeys] widened key values                                         */
+	uint8_t   **keynull;
+	int64_t   **st_n, **st_lo, **st_hi;	/* [naccs]                                                  */
+	int			err;
+} HCtx;
+
+static int
+hv_scale_up(__int128 *v, int k)
+{
+	while (k-- > 0)
+		if (__builtin_mul_overflow(*v, (__int128) 10, v))
+			return 0;
+	return 1;
+}
+
+static HVal
+having_eval(HCtx *h, const CbExpr *e)
+{
+	HVal		r;
+
+	memset(&r, 0, sizeof(r));
+	r.den = 1;
+	switch (e->tag)
+	{
+		case T_CbConst:
+			r.isnull = e->constisnull;
+			r.num = e->constval;
+			r.scale = e->dscale;
+			if (e->restype == CB_FLOAT8)
+				h->err = 1;
+			return r;
+		case T_CbVar:
+			for (int k = 0; k < h->agg->numCols; k++)
+				if (e->varno == CB_OUTER_VAR && h->agg->grpColIdx[k] == e->varattno)
+				{
+					r.isnull = h->keynull[k] ? h->keynull[k][h->g] : 0;
+					r.num = h->keycol[k][h->g];
+					r.scale = h->cs->pe[h->info->keys[k]].dscale;
+					if (h->cs->pe[h->info->keys[k]].type == CB_FLOAT8)
+						h->err = 1;
+					return r;
+				}
+			h->err = 1;
+			return r;
+		case T_CbAggref:
+			for (int i = 0; i < h->info->nhaving; i++)
+				if (h->info->having_ref[i] == e)
+				{
+					const int	a = h->info->having_acc[i];
+					const AccMeta *m = &h->info->acc[a];
+					const int64_t n = h->st_n[a][h->g];
+
+					if (m->state_kind == CBP_ACC_SUM_FLOAT)
+					{
+						h->err = 1;		/* float8 aggregates compare inexactly: not decided here */
+						return r;
+					}
+					r.scale = m->dscale;
+					switch (e->op)
+					{
+						case CB_AGG_COUNT_STAR:
+						case CB_AGG_COUNT:
+							r.num = n;
+							r.scale = 0;
+							return r;
+						case CB_AGG_SUM:
+						case CB_AGG_AVG:
+							r.isnull = n == 0;
+							r.num = ((__int128) h->st_hi[a][h->g] << 64) | (unsigned __int128) (uint64_t) h->st_lo[a][h->g];
+							if (e->op == CB_AGG_AVG && n > 0)
+								r.den = n;
+							return r;
+						case CB_AGG_MIN:
+						case CB_AGG_MAX:
+							r.isnull = n == 0;
+							r.num = h->st_lo[a][h->g];
+							return r;
+					}
+				}
+			h->err = 1;
+			return r;
+		case T_CbOpExpr:
+			{
+				HVal		a,
+							b;
+				__int128	L,
+							R;
+				int			c;
+
+				if (e->nargs != 2 || e->op < CB_OP_EQ)
+				{
+					h->err = 1;		/* arithmetic over aggregates in HAVING: not on this path */
+					return r;
+				}
+				a = having_eval(h, e->args[0]);
+				b = having_eval(h, e->args[1]);
+				r.isbool = 1;
+				if (a.isnull || b.isnull)
+				{
+					r.isnull = 1;
+					return r;
+				}
+				/* a.num / (a.den 10^a.scale)  ?  b.num / (b.den 10^b.scale): cross-multiplied, exact or refused */
+				L = a.num;
+				R = b.num;
+				if (__builtin_mul_overflow(L, (__int128) b.den, &L) || __builtin_mul_overflow(R, (__int128) a.den, &R) ||
+					!hv_scale_up(&L, b.scale > a.scale ? b.scale - a.scale : 0) || !hv_scale_up(&R, a.scale > b.scale ? a.scale - b.scale : 0))
+				{
+					h->err = 2;
+					return r;
+				}
+				c = L < R ? -1 : L > R ? 1 : 0;
+				switch (e->op)
+				{
+					case CB_OP_EQ: r.num = c == 0; break;
+					case CB_OP_NE: r.num = c != 0; break;
+					case CB_OP_LT: r.num = c < 0; break;
+					case CB_OP_LE: r.num = c <= 0; break;
+					case CB_OP_GT: r.num = c > 0; break;
+					default: r.num = c >= 0; break;
+				}
+				return r;
+			}
+		case T_CbBoolExpr:
+			{
+				int			anynull = 0;
+
+				r.isbool = 1;
+				if (e->op == CB_NOT_EXPR)
+				{
+					HVal		a = having_eval(h, e->args[0]);
+
+					r.isnull = a.isnull;
+					r.num = !a.num;
+					return r;
+				}
+				/* three-valued AND / OR (ExecEvalBoolAndStep / OrStep, execExprInterp.c) */
+				r.num = e->op == CB_AND_EXPR;
+				for (int i = 0; i < e->nargs; i++)
+				{
+					HVal		a = having_eval(h, e->args[i]);
+
+					if (a.isnull)
+						anynull = 1;
+					else if (e->op == CB_AND_EXPR && !a.num)
+					{
+						r.num = 0;
+						return r;
+					}
+					else if (e->op == CB_OR_EXPR && a.num)
+					{
+						r.num = 1;
+						return r;
+					}
+				}
+				r.isnull = anynull;
+				return r;
+			}
+		default:
+			h->err = 1;
+			return r;
+	}
+}
+
+/* groups relation `rel` (keys, then N / lo / hi per accumulator) -> device selection vector of the groups HAVING keeps */
+static int
+having_select(CbPlanState *ps, const AggPlanInfo *info, CbStream *cs, cbgpu_rel *rel, uint32_t **sel_dev, int64_t *nsel)
+{
+	CbEState   *es = ps->state;
+	NodePriv   *p = np(ps);
+	const CbAgg *agg = (const CbAgg *) ps->plan;
+	const int64_t ng = cbgpu_rel_nrows(rel);
+	HCtx		h;
+	uint32_t   *sel = calloc((size_t) (ng ? ng : 1), sizeof(uint32_t));
+	int64_t		kept = 0;
+	int			rc = CBGPU_OK;
+	const int	nk = info->nkeys,
+				na = info->naccs;
+	void	   *dev = NULL;
+
+	memset(&h, 0, sizeof(h));
+	h.es = es;
+	h.agg = agg;
+	h.info = info;
+	h.cs = cs;
+	h.keycol = calloc((size_t) (nk ? nk : 1), sizeof(int64_t *));
+	h.keynull = calloc((size_t) (nk ? nk : 1), sizeof(uint8_t *));
+	h.st_n = calloc((size_t) (na ? na : 1), sizeof(int64_t *));
+	h.st_lo = calloc((size_t) (na ? na : 1), sizeof(int64_t *));
+	h.st_hi = calloc((size_t) (na ? na : 1), sizeof(int64_t *));
+	for (int k = 0; k < nk && rc == CBGPU_OK; k++)
+	{
+		const int	w = cb_type_width((CbTypeId) cbgpu_rel_col_type(rel, k));
+		char	   *raw = calloc((size_t) (ng ? ng : 1), (size_t) w);
+
+		h.keycol[k] = calloc((size_t) (ng ? ng : 1), sizeof(int64_t));
+		h.keynull[k] = calloc((size_t) (ng ? ng : 1), 1);
+		if (ng > 0)
+			rc = cbgpu_rel_read_column(rel, k, 0, ng, raw, h.keynull[k]);
+		for (int64_t g = 0; g < ng; g++)
+			h.keycol[k][g] = w == 1 ? ((uint8_t *) raw)[g] : w == 4 ? ((int32_t *) raw)[g] : ((int64_t *) raw)[g];
+		free(raw);
+	}
+	for (int i = 0; i < info->nhaving && rc == CBGPU_OK; i++)
+	{
+		const int	a = info->having_acc[i];
+
+		if (h.st_n[a])
+			continue;
+		h.st_n[a] = calloc((size_t) (ng ? ng : 1), sizeof(int64_t));
+		h.st_lo[a] = calloc((size_t) (ng ? ng : 1), sizeof(int64_t));
+		h.st_hi[a] = calloc((size_t) (ng ? ng : 1), sizeof(int64_t));
+		if (ng > 0)
+		{
+			rc = cbgpu_rel_read_column(rel, nk + 3 * a, 0, ng, h.st_n[a], NULL);
+			if (rc == CBGPU_OK)
+				rc = cbgpu_rel_read_column(rel, nk + 3 * a + 1, 0, ng, h.st_lo[a], NULL);
+			if (rc == CBGPU_OK)
+				rc = cbgpu_rel_read_column(rel, nk + 3 * a + 2, 0, ng, h.st_hi[a], NULL);
+		}
+	}
+	for (int64_t g = 0; g < ng && rc == CBGPU_OK && !h.err; g++)
+	{
+		int			keep = 1;
+
+		h.g = g;
+		for (int q = 0; q < ps->plan->nquals && keep; q++)
+		{
+			HVal		v = having_eval(&h, ps->plan->qual[q]);
+
+			keep = !v.isnull && v.num != 0;	/* ExecQual: NULL counts as false */
+		}
+		if (keep)
+			sel[kept++] = (uint32_t) g;
+	}
+	if (rc != CBGPU_OK)
+		rc = es_fail(es, rc, "%s", cbgpu_last_error(es->es_ctx));
+	else if (h.err == 2)
+		rc = es_fail(es, CBGPU_ERR_OVERFLOW, "HAVING: a comparison of aggregates left 128 bits");
+	else if (h.err)
+		rc = es_fail(es, CBGPU_ERR_UNSUPPORTED, "HAVING on the GPU path compares aggregates, grouping columns and constants (no arithmetic, no float8)");
+	if (rc == CBGPU_OK)
+	{
+		rc = cbgpu_dev_alloc(es->es_ctx, sizeof(uint32_t) * (size_t) (kept ? kept : 1), &dev);
+		if (rc == CBGPU_OK)
+		{
+			p->owned.devs[p->owned.ndevs++] = dev;
+			if (kept > 0)
+				rc = cbgpu_dev_write(es->es_ctx, dev, sizeof(uint32_t) * (size_t) kept, sel);
+		}
+		if (rc != CBGPU_OK)
+			rc = es_fail(es, rc, "%s", cbgpu_last_error(es->es_ctx));
+	}
+	for (int k = 0; k < nk; k++)
+	{
+		free(h.keycol[k]);
+		free(h.keynull[k]);
+	}
+	for (int a = 0; a < na; a++)
+	{
+		free(h.st_n[a]);
+		free(h.st_lo[a]);
+		free(h.st_hi[a]);
+	}
+	free(h.keycol); free(h.keynull); free(h.st_n); free(h.st_lo); free(h.st_hi);
+	free(sel);
+	*sel_dev = (uint32_t *) dev;
+	*nsel = kept;
+	return rc;
+}
+
 /* Agg feeding a parent on the device: groups become a relation (keys, then N / lo / hi per state) */
 static int
 open_agg(CbPlanState *ps, CbStream **out)
@@ -1500,11 +2002,14 @@ open_agg(CbPlanState *ps, CbStream **out)
 	cbgpu_rel  *rel;
 	int32_t		keytypes[CBP_MAX_KEYS];
 
-	TRY(agg_run(ps, &info, &t, &cs));
+	TRY(agg_run(ps, &info, &t, &cs, &rel));
 	for (int k = 0; k < info.nkeys; k++)
 		keytypes[k] = cs->pe[info.keys[k]].type;
-	GPU(es, cbgpu_agg_to_rel(t, keytypes, &rel));
-	p->owned.rels[p->owned.nrels++] = rel;
+	if (rel == NULL)
+	{
+		GPU(es, cbgpu_agg_to_rel(t, keytypes, &rel));
+		p->owned.rels[p->owned.nrels++] = rel;
+	}
 	for (int k = 0; k < info.nkeys; k++)
 	{
 		PExpr	   *kx = &cs->pe[info.keys[k]];
@@ -1517,6 +2022,17 @@ open_agg(CbPlanState *ps, CbStream **out)
 	s->rows_in = s->pipe.nrows;
 	s->nsrc = 1;
 	s->nout = ps->plan->ntargets;
+	if (ps->plan->nquals > 0)
+	{
+		/* HAVING: the stream reads the groups' relation through the selection of the groups that pass */
+		uint32_t   *sel = NULL;
+		int64_t		nsel = 0;
+
+		TRY(having_select(ps, &info, cs, rel, &sel, &nsel));
+		s->pipe.drv_nsrc = 1;
+		s->pipe.drv_idx[0] = sel;
+		s->pipe.nrows = nsel;
+	}
 	for (int i = 0; i < ps->plan->ntargets; i++)
 	{
 		if (info.key_of_target[i] >= 0)
@@ -1565,7 +2081,7 @@ partition_pass(CbPlanState *ps, CbStream *s, cbgpu_rel *out, void *counter, void
 	pl->sink.seg_base = base;
 	pl->sink.seg_cap = cap;
 	pl->sink.part_flags = (int32_t *) flagword;
-	GPU(es, cbgpu_pipeline_run(es->es_ctx, pl));
+	TRY(run_pipeline(es, pl));
 	GPU(es, cbgpu_dev_read(es->es_ctx, counter, sizeof(int64_t) * (size_t) nsegs, counts));	/* the status word rides along */
 	GPU(es, cbgpu_check_status(es->es_ctx));
 	ps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
@@ -1716,9 +2232,9 @@ motion_send_side(CbPlanState *ps, cbgpu_rel **send, int64_t *counts, int64_t *of
 					pl->sink.part_nulls = dest.nulls;
 					pl->sink.part_nullmask = nullmask;
 					pl->sink.part_flags = dest.flags;
-					rc = cbgpu_pipeline_run(es->es_ctx, pl);
+					rc = run_pipeline(es, pl);
 				}
-				if (rc)
+				if (rc && es->es_errcode == 0)
 					es_fail(es, rc, "%s", cbgpu_last_error(es->es_ctx));
 				rc2 = ic->direct_end(ic, es, m->motionID, rc ? CBGPU_DX_ERROR : 0, nullmask, (const int64_t *) counter, counts, &recv, &outcome);
 				p->xstage = 1;
@@ -2350,7 +2866,9 @@ node_result(CbPlanState *ps)
 
 	if (p->rs)
 		return CBGPU_OK;
-	if (ps->type == T_CbAgg)
+	/* with an operator memory budget the groups may come in partitions: then they are a relation already (open_agg), and the
+	 * rows are read from it like any other node's */
+	if (ps->type == T_CbAgg && !(es->es_operator_mem_kb > 0 && ((CbAgg *) ps->plan)->numCols > 0) && ps->plan->nquals == 0)
 		return agg_result(ps);
 	if (ps->type == T_CbLimitSort)
 		return limitsort_result(ps);

@@ -87,6 +87,8 @@ k_ht_build(BuildParams p)
 
 			h[u] = 0;
 			v[u] = i < p.nrows && ht_row_hash(p.ht, (uint32_t) i, &h[u], &key0);
+			if (v[u] && !ht_in_batch(p.ht.nbatch, p.ht.batch_shift, p.ht.batch_id, h[u]))
+				v[u] = false;		/* another batch's row */
 			if (v[u] && p.ht.keyslot && !ht_key_in_domain(p.ht.keyslot, key0))
 			{
 				outside = true;		/* the host builds the table again with hash values in the slots */
@@ -146,87 +148,26 @@ k_ht_build(BuildParams p)
 		atomicAdd(p.flags + 1, inserted);
 }
 
-extern "C" int
-cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t nkeys, cbgpu_hashtable **out)
+/* one fill of the table: every build row (nbatch <= 1) or the rows of batch `batch` */
+static int
+ht_fill(cbgpu_hashtable *ht, int batch)
 {
-	cbgpu_hashtable *ht;
-	int64_t		nslots = 64;
+	cbgpu_ctx  *ctx = ht->ctx;
+	cbgpu_rel  *inner = ht->inner;
 	BuildParams p;
 	int			h_flags[3];
 
-	if (nkeys < 1 || nkeys > CBP_MAX_KEYS)
-		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "hash join with %s%lld key columns is beyond the GPU path's limit (4)", "", nkeys);
-	while (nslots < inner->nrows * 2)
-		nslots <<= 1;
-	if (nslots > (1ll << 32))
-		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "hash join build side too large for 32-bit slots%s (%lld rows)", "", inner->nrows);
-	ht = (cbgpu_hashtable *) calloc(1, sizeof(cbgpu_hashtable));
-	if (!ht)
-		return CBGPU_ERR_NOMEM;
-	ht->ctx = ctx;
-	ht->inner = inner;
-	ht->nslots = nslots;
-	ht->d.mask = (uint32_t) (nslots - 1);
-	ht->d.nkeys = nkeys;
-	for (int k = 0; k < nkeys; k++)
-	{
-		int			c = keycols[k];
-
-		if (c < 0 || c >= inner->ncols)
-		{
-			free(ht);
-			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_ht_build: bad key column%s %lld", "", c);
-		}
-		if (inner->types[c] == CB_NUMERIC)
-		{
-			free(ht);
-			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "numeric hash join keys (hash_numeric) are not on the GPU path%s", "", 0);
-		}
-		if ((inner->types[c] == CB_DICT8 || inner->types[c] == CB_DICT32) && !inner->dict_hash[c])
-		{
-			free(ht);
-			return cb_fail(ctx, CBGPU_ERR_INVALID, "dictionary column %s%lld used as a join key without dict hashes", "", c);
-		}
-		ht->d.keydata[k] = inner->data[c];
-		ht->d.keynulls[k] = inner->nulls[c];
-		ht->d.keydict[k] = inner->dict_hash[c];
-		ht->d.keytype[k] = inner->types[c];
-	}
-	CB_CUDA(ctx, cudaSetDevice(ctx->device));
-	CB_CUDA(ctx, cudaMallocAsync(&ht->d.slots, (size_t) nslots * sizeof(unsigned long long), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&ht->d_flags, 3 * sizeof(int), ctx->stream));
-	/* one integer key: try the key-in-slot layout (int8 keys: as long as every build value lies in [0, 2^32)) */
-	if (nkeys == 1 && !ctx->opt_no_keyslot)
-		switch (ht->d.keytype[0])
-		{
-			case CB_INT8:
-				ht->d.keyslot = 2;
-				break;
-			case CB_INT4: case CB_DATE: case CB_DICT8: case CB_DICT32: case CB_BPCHAR1: case CB_BOOL:
-				ht->d.keyslot = 1;
-				break;
-			default:
-				break;
-		}
-	{
-		/* ~16 filter bits per build row, at least one cache line */
-		int64_t		words = 32;
-		const int	div = ctx->opt_bloom_div;	/* rows per 32-bit filter word (CBGPU_BLOOM_DIV, tuning aid), default 2 */
-
-		while (words < inner->nrows / div)
-			words <<= 1;
-		CB_CUDA(ctx, cudaMallocAsync(&ht->d.bloom, (size_t) words * sizeof(uint32_t), ctx->stream));
-		CB_CUDA(ctx, cudaMemsetAsync(ht->d.bloom, 0, (size_t) words * sizeof(uint32_t), ctx->stream));
-		ht->d.bloom_mask = (uint32_t) (words - 1);
-	}
+	ht->d.batch_id = batch;
+	if (ht->d.bloom)
+		CB_CUDA(ctx, cudaMemsetAsync(ht->d.bloom, 0, ((size_t) ht->d.bloom_mask + 1) * sizeof(uint32_t), ctx->stream));
 	for (;;)
 	{
-		int			blocks = (int) ((nslots + 255) / 256);
+		int			blocks = (int) ((ht->nslots + 255) / 256);
 
 		CB_CUDA(ctx, cudaMemsetAsync(ht->d_flags, 0, 3 * sizeof(int), ctx->stream));
 		if (blocks > ctx->sm_count * 8)
 			blocks = ctx->sm_count * 8;
-		k_ht_clear<<<blocks, 256, 0, ctx->stream>>>(ht->d.slots, (size_t) nslots);
+		k_ht_clear<<<blocks, 256, 0, ctx->stream>>>(ht->d.slots, (size_t) ht->nslots);
 		CB_LAUNCHED(ctx, "k_ht_clear");
 		p.ht = ht->d;
 		p.nrows = inner->nrows;
@@ -258,10 +199,203 @@ cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t
 		}
 		break;
 	}
-	ht->has_dups = h_flags[0];
+	if (h_flags[0])
+		ht->has_dups = 1;
 	ht->ninserted = h_flags[1];
+	return CBGPU_OK;
+}
+
+/* rows per batch of a build side (the batch number of every row's key hash), to size the resident table for the fullest */
+__global__ void
+k_ht_batch_histogram(HtDev ht, int64_t nrows, unsigned long long *hist)
+{
+	for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += (int64_t) gridDim.x * blockDim.x)
+	{
+		uint32_t	h;
+		int64_t		key0;
+
+		if (ht_row_hash(ht, (uint32_t) i, &h, &key0))
+			atomicAdd(hist + (h >> ht.batch_shift), 1ull);
+	}
+}
+
+static int
+ht_create(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t nkeys, int32_t nbatch, cbgpu_hashtable **out)
+{
+	cbgpu_hashtable *ht;
+	int64_t		nslots = 64;
+	int64_t		resident_rows = inner->nrows;
+
+	*out = NULL;
+	if (nkeys < 1 || nkeys > CBP_MAX_KEYS)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "hash join with %s%lld key columns is beyond the GPU path's limit (4)", "", nkeys);
+	if (nbatch < 1 || nbatch > 4096 || (nbatch & (nbatch - 1)) != 0)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "hash join with %s%lld batches (a power of two up to 4096 is expected)", "", nbatch);
+	ht = (cbgpu_hashtable *) calloc(1, sizeof(cbgpu_hashtable));
+	if (!ht)
+		return CBGPU_ERR_NOMEM;
+	ht->ctx = ctx;
+	ht->inner = inner;
+	ht->total_rows = inner->nrows;
+	ht->d.nkeys = nkeys;
+	ht->d.nbatch = nbatch;
+	ht->d.batch_shift = 32;
+	for (int b = nbatch; b > 1; b >>= 1)
+		ht->d.batch_shift--;
+	for (int k = 0; k < nkeys; k++)
+	{
+		int			c = keycols[k];
+
+		if (c < 0 || c >= inner->ncols)
+		{
+			free(ht);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_ht_build: bad key column%s %lld", "", c);
+		}
+		if (inner->types[c] == CB_NUMERIC)
+		{
+			free(ht);
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "numeric hash join keys (hash_numeric) are not on the GPU path%s", "", 0);
+		}
+		if ((inner->types[c] == CB_DICT8 || inner->types[c] == CB_DICT32) && !inner->dict_hash[c])
+		{
+			free(ht);
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "dictionary column %s%lld used as a join key without dict hashes", "", c);
+		}
+		ht->d.keydata[k] = inner->data[c];
+		ht->d.keynulls[k] = inner->nulls[c];
+		ht->d.keydict[k] = inner->dict_hash[c];
+		ht->d.keytype[k] = inner->types[c];
+	}
+	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (nbatch > 1 && inner->nrows > 0)
+	{
+		/* the fullest batch sizes the table (hash skew: duplicate keys all land in one batch) */
+		unsigned long long *d_hist,
+				   *h_hist = (unsigned long long *) calloc((size_t) nbatch, sizeof(unsigned long long));
+		int			blocks = (int) ((inner->nrows + 255) / 256);
+
+		if (!h_hist)
+		{
+			free(ht);
+			return CBGPU_ERR_NOMEM;
+		}
+		if (blocks > ctx->sm_count * 8)
+			blocks = ctx->sm_count * 8;
+		CB_CUDA(ctx, cudaMallocAsync(&d_hist, sizeof(unsigned long long) * (size_t) nbatch, ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (size_t) nbatch, ctx->stream));
+		k_ht_batch_histogram<<<blocks, 256, 0, ctx->stream>>>(ht->d, inner->nrows, d_hist);
+		CB_LAUNCHED(ctx, "k_ht_batch_histogram");
+		CB_CUDA(ctx, cudaMemcpyAsync(h_hist, d_hist, sizeof(unsigned long long) * (size_t) nbatch, cudaMemcpyDeviceToHost, ctx->stream));
+		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		CB_CUDA(ctx, cudaFreeAsync(d_hist, ctx->stream));
+		resident_rows = 0;
+		for (int b = 0; b < nbatch; b++)
+			if ((int64_t) h_hist[b] > resident_rows)
+				resident_rows = (int64_t) h_hist[b];
+		free(h_hist);
+	}
+	while (nslots < resident_rows * 2)
+		nslots <<= 1;
+	if (nslots > (1ll << 32))
+	{
+		free(ht);
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "hash join build side too large for 32-bit slots%s (%lld rows)", "", inner->nrows);
+	}
+	ht->nslots = nslots;
+	ht->d.mask = (uint32_t) (nslots - 1);
+	CB_CUDA(ctx, cudaMallocAsync(&ht->d.slots, (size_t) nslots * sizeof(unsigned long long), ctx->stream));
+	CB_CUDA(ctx, cudaMallocAsync(&ht->d_flags, 3 * sizeof(int), ctx->stream));
+	/* one integer key: try the key-in-slot layout (int8 keys: as long as every build value lies in [0, 2^32)) */
+	if (nkeys == 1 && !ctx->opt_no_keyslot)
+		switch (ht->d.keytype[0])
+		{
+			case CB_INT8:
+				ht->d.keyslot = 2;
+				break;
+			case CB_INT4: case CB_DATE: case CB_DICT8: case CB_DICT32: case CB_BPCHAR1: case CB_BOOL:
+				ht->d.keyslot = 1;
+				break;
+			default:
+				break;
+		}
+	{
+		/* ~16 filter bits per build row, at least one cache line */
+		int64_t		words = 32;
+		const int	div = ctx->opt_bloom_div;	/* rows per 32-bit filter word (CBGPU_BLOOM_DIV, tuning aid), default 2 */
+
+		while (words < resident_rows / div)
+			words <<= 1;
+		CB_CUDA(ctx, cudaMallocAsync(&ht->d.bloom, (size_t) words * sizeof(uint32_t), ctx->stream));
+		ht->d.bloom_mask = (uint32_t) (words - 1);
+		ht->built_bytes = nslots * 8 + words * 4;
+	}
 	*out = ht;
 	return CBGPU_OK;
+}
+
+extern "C" int
+cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t nkeys, cbgpu_hashtable **out)
+{
+	int			rc = ht_create(ctx, inner, keycols, nkeys, 1, out);
+
+	if (rc == CBGPU_OK)
+		rc = ht_fill(*out, 0);
+	if (rc != CBGPU_OK && *out)
+	{
+		cbgpu_ht_free(*out);
+		*out = NULL;
+	}
+	return rc;
+}
+
+/* what a single-batch table over `rows` build rows takes on the device (slots at load factor <= 0.5 + the filter):
+ * the caller's figure for choosing nbatch against its memory budget (ExecChooseHashTableSize, nodeHash.c:856-1100) */
+extern "C" int64_t
+cbgpu_ht_bytes_for(int64_t rows)
+{
+	int64_t		nslots = 64,
+				words = 32;
+
+	while (nslots < rows * 2)
+		nslots <<= 1;
+	while (words < rows / 2)
+		words <<= 1;
+	return nslots * 8 + words * 4;
+}
+
+extern "C" int
+cbgpu_ht_build_batched(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t nkeys, int32_t nbatch, cbgpu_hashtable **out)
+{
+	int			rc = ht_create(ctx, inner, keycols, nkeys, nbatch, out);
+
+	/* every batch is built once now: duplicates on the build side decide the join's shape (N:1 or N:M) before the
+	 * first probe, and the key-in-slot layout must hold for all batches alike */
+	for (int b = 0; b < nbatch && rc == CBGPU_OK; b++)
+		rc = ht_fill(*out, b);
+	if (rc == CBGPU_OK && (*out)->d.keyslot == 0 && nbatch > 1)
+		rc = ht_fill(*out, nbatch - 1);	/* a late fallback to hash-in-slot: the resident batch must use the final layout */
+	if (rc != CBGPU_OK && *out)
+	{
+		cbgpu_ht_free(*out);
+		*out = NULL;
+	}
+	return rc;
+}
+
+extern "C" int
+cbgpu_ht_nbatch(const cbgpu_hashtable *ht)
+{
+	return ht->d.nbatch > 1 ? ht->d.nbatch : 1;
+}
+
+extern "C" int
+cbgpu_ht_load_batch(cbgpu_hashtable *ht, int32_t batch)
+{
+	if (batch < 0 || batch >= cbgpu_ht_nbatch(ht))
+		return cb_fail(ht->ctx, CBGPU_ERR_INVALID, "hash join batch %s%lld out of range", "", batch);
+	if (ht->d.nbatch > 1 && ht->d.batch_id == batch)
+		return CBGPU_OK;
+	return ht_fill(ht, batch);
 }
 
 extern "C" void
@@ -280,7 +414,7 @@ cbgpu_ht_free(cbgpu_hashtable *ht)
 extern "C" int64_t
 cbgpu_ht_nrows(const cbgpu_hashtable *ht)
 {
-	return ht->ninserted;
+	return ht->d.nbatch > 1 ? ht->total_rows : ht->ninserted;
 }
 
 extern "C" int
@@ -309,6 +443,7 @@ struct ProbeParams
 	int32_t		otype[CBP_MAX_KEYS];
 	const uint32_t *sel;
 	int64_t		n;
+	int32_t		left;			/* LEFT join: an outer row without a partner yields one pair (row, 0xFFFFFFFF)  */
 	unsigned long long *counts;	/* [n + 1] match counts, then their exclusive scan                    */
 	uint32_t   *out_outer;
 	uint32_t   *out_inner;
@@ -347,6 +482,8 @@ k_ht_probe_pairs(ProbeParams p)
 		}
 		if (!isnull && p.ht.keyslot && !ht_key_in_domain(p.ht.keyslot, key[0]))
 			isnull = true;			/* outside the build side's key domain: no partner */
+		if (!isnull && !ht_in_batch(p.ht.nbatch, p.ht.batch_shift, p.ht.batch_id, h))
+			isnull = true;			/* multi-batch join: this row belongs to another pass */
 		if (!isnull)
 		{
 			uint32_t	pos = h & p.ht.mask;
@@ -377,6 +514,16 @@ k_ht_probe_pairs(ProbeParams p)
 				}
 				pos = (pos + 1) & p.ht.mask;
 			}
+		}
+		if (p.left && cnt == 0 && ht_in_batch(p.ht.nbatch, p.ht.batch_shift, p.ht.batch_id, h))
+		{
+			/* no partner (or a NULL key, which never has one): the outer row survives with a NULL inner side */
+			if (WRITE)
+			{
+				p.out_outer[base] = row;
+				p.out_inner[base] = 0xFFFFFFFFu;
+			}
+			cnt = 1;
 		}
 		if (!WRITE)
 			p.counts[i] = cnt;
@@ -439,9 +586,26 @@ k_exclusive_scan_u64(unsigned long long *a, int64_t n)
 		a[n] = carry;
 }
 
+static int	ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
+						   const uint32_t *sel, int64_t nsel, int left, cbgpu_pairs *out);
+
 extern "C" int
 cbgpu_ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
 					 const uint32_t *sel, int64_t nsel, cbgpu_pairs *out)
+{
+	return ht_probe_pairs(ctx, ht, outer, keycols, nkeys, sel, nsel, 0, out);
+}
+
+extern "C" int
+cbgpu_ht_probe_pairs_left(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
+						  cbgpu_pairs *out)
+{
+	return ht_probe_pairs(ctx, ht, outer, keycols, nkeys, NULL, 0, 1, out);
+}
+
+static int
+ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
+			   const uint32_t *sel, int64_t nsel, int left, cbgpu_pairs *out)
 {
 	ProbeParams p;
 	int64_t		n = sel ? nsel : outer->nrows;
@@ -465,6 +629,7 @@ cbgpu_ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer
 	}
 	p.sel = sel;
 	p.n = n;
+	p.left = left;
 	if (n == 0)
 		return CBGPU_OK;
 	CB_CUDA(ctx, cudaMallocAsync(&p.counts, (size_t) (n + 1) * sizeof(unsigned long long), ctx->stream));

@@ -439,7 +439,16 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 					ridx[0] = (uint32_t) base;
 				else
 					for (int s = 0; s < P.drv_nsrc; s++)
+					{
 						ridx[s] = P.drv_idx[s] ? P.drv_idx[s][base] : (uint32_t) base;
+						/* a LEFT join's unmatched outer row arrives as a pair with no inner row: that source is NULL
+						 * (ExecHashJoinImpl HJ_FILL_OUTER_TUPLE, nodeHashjoin.c:640-660) */
+						if (s > 0 && ridx[s] == 0xFFFFFFFFu)
+						{
+							rnull |= 1u << s;
+							ridx[s] = 0;
+						}
+					}
 				/* AppendOnlyVisimap_IsVisible (backend/access/appendonly/appendonly_visimap.c:198) */
 				if (P.visimap && !((P.visimap[ridx[0] >> 3] >> (ridx[0] & 7)) & 1))
 					alive = false;
@@ -562,6 +571,13 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 					uint32_t	bits = ht_bloom_bits(h, &w, pr.ht.bloom_mask);
 
 					maybe = (__ldg(pr.ht.bloom + w) & bits) == bits;
+				}
+				if (alive && !knull && !ht_in_batch(pr.ht.nbatch, pr.ht.batch_shift, pr.ht.batch_id, h))
+				{
+					/* multi-batch join: this row's batch is not resident - its own pass joins (or, for outer / anti joins,
+					 * emits) it; in this pass it does not exist */
+					alive = false;
+					maybe = false;
 				}
 				if (maybe && pr.ht.keyslot && !ht_key_in_domain(pr.ht.keyslot, key[0]))
 					maybe = false;		/* outside the build side's key domain: no partner */
@@ -821,7 +837,8 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 					h = pg_hash_combine(h, isn ? 0u : pg_hash_datum(S.keytype[k], st[k], S.keydict[k]), isn);
 				}
 				h = pg_murmurhash32(h);
-				int			slot = agg_find_or_insert(S.agg, h, st, knull);
+				/* partitioned aggregation: this pass owns the groups whose hash carries its number */
+				int			slot = (S.agg.npart > 1 && (int32_t) (h >> S.agg.part_shift) != S.agg.part_id) ? -1 : agg_find_or_insert(S.agg, h, st, knull);
 
 				if (slot >= 0)
 					for (int a = 0; a < S.naccs; a++)
@@ -926,7 +943,14 @@ cbgpu_pipeline_run(cbgpu_ctx *ctx, const CbPipeline *p)
 	ctx->kernel_timed = false;
 	if (p->nrows == 0)
 		return CBGPU_OK;
-	if (!p->force_generic)
+	bool		multibatch = false;
+
+	for (int j = 0; j < p->nprobes; j++)
+		if (p->probes[j].ht && p->probes[j].ht->d.nbatch > 1)
+			multibatch = true;	/* the compiled kernels know nothing of batches: the interpreter runs the passes */
+	if (p->sink.kind == CBP_SINK_AGG && p->sink.agg && p->sink.agg->d.npart > 1)
+		multibatch = true;		/* ... nor of aggregate partitions */
+	if (!p->force_generic && !multibatch)
 	{
 		rc = cb_try_specialised(ctx, p, &d, &handled);
 		if (rc)

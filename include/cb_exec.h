@@ -72,6 +72,8 @@ typedef struct CbInstrumentation
 	int64_t		rows_in;		/* rows of the driving relation(s) this node's pipelines scanned     */
 	int64_t		motion_repartitions;	/* Motion sender: passes redone with exact sizes after a destination
 								 * outgrew its share (data skew)                                     */
+	int64_t		hashjoin_nbatch;	/* Hash: batches the build side was split into (1: it fitted)        */
+	int64_t		agg_npartitions;	/* Agg: passes a partitioned aggregation took (1: the table fitted)  */
 } CbInstrumentation;
 
 typedef struct CbPlanState
@@ -115,6 +117,8 @@ typedef struct CbEState
 	 * a hash join build side or an aggregate table larger than this is processed in several passes (multi-batch hybrid
 	 * hash join, partitioned aggregation).  0 = whatever the device holds. */
 	int64_t		es_operator_mem_kb;
+	int64_t		es_hashjoin_batches_run;	/* passes of multi-batch hash joins so far (statistics)           */
+	int64_t		es_agg_partitions_run;		/* passes of partitioned aggregations so far                      */
 } CbEState;
 
 CbEState   *cb_CreateExecutorState(cbgpu_ctx *ctx, cbgpu_rel **range_table, int32_t nrels);

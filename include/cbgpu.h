@@ -275,6 +275,16 @@ int			cbgpu_pipeline_run(cbgpu_ctx *ctx, const CbPipeline *p);
  * NULL keys are not inserted (strict hash operators, nodeHash.c:2161). */
 int			cbgpu_ht_build(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t nkeys,
 						   cbgpu_hashtable **out);
+/* multi-batch hybrid hash join (nodeHash.c:980-990, 1133, 2223-2242): the build side is split into nbatch (a power of two)
+ * batches by bits of the key hash that the slot index does not use; the table holds one batch at a time
+ * (cbgpu_ht_load_batch) and sizes itself for the fullest.  A pipeline that probes it runs once per batch - probe rows of
+ * other batches are skipped in each pass - and its sink accumulates over the passes.  cbgpu_ht_bytes_for(rows) = device
+ * bytes of a one-batch table, for choosing nbatch against a budget. */
+int			cbgpu_ht_build_batched(cbgpu_ctx *ctx, cbgpu_rel *inner, const int32_t *keycols, int32_t nkeys, int32_t nbatch,
+								   cbgpu_hashtable **out);
+int			cbgpu_ht_nbatch(const cbgpu_hashtable *ht);
+int			cbgpu_ht_load_batch(cbgpu_hashtable *ht, int32_t batch);
+int64_t		cbgpu_ht_bytes_for(int64_t rows);
 void		cbgpu_ht_free(cbgpu_hashtable *ht);
 int64_t		cbgpu_ht_nrows(const cbgpu_hashtable *ht);
 int			cbgpu_ht_has_duplicates(const cbgpu_hashtable *ht);
@@ -292,6 +302,10 @@ typedef struct cbgpu_pairs
 int			cbgpu_ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer,
 								 const int32_t *keycols, int32_t nkeys, const uint32_t *sel, int64_t nsel,
 								 cbgpu_pairs *out);
+/* the same for a LEFT join: an outer row without a partner yields one pair whose inner_idx is 0xFFFFFFFF (a pipeline driven
+ * by the pairs reads that source as NULL: HJ_FILL_OUTER_TUPLE, nodeHashjoin.c:640-660) */
+int			cbgpu_ht_probe_pairs_left(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols,
+									  int32_t nkeys, cbgpu_pairs *out);
 void		cbgpu_pairs_free(cbgpu_pairs *p);
 int			cbgpu_read_u32(cbgpu_ctx *ctx, const uint32_t *dev, int64_t n, uint32_t *host);
 /* small device scratch (sink row counters, index vectors): zero-filled allocation, read-back, free */
@@ -318,6 +332,12 @@ int			cbgpu_rel_share_dict_hash(cbgpu_rel *dst, int32_t dcol, const cbgpu_rel *s
 int			cbgpu_agg_create(cbgpu_ctx *ctx, int32_t nkeys, int32_t naccs, const int32_t *acc_kinds,
 							 int64_t capacity_groups, cbgpu_aggtable **out);
 void		cbgpu_agg_free(cbgpu_aggtable *t);
+/* partitioned aggregation for group sets larger than the operator's memory (nodeAgg.c:2149, 3215): with npart (a power of two)
+ * partitions set, a pipeline's AGG sink aggregates only the rows whose group hash selects partition `part`; the caller runs
+ * the pipeline once per partition and takes each pass's groups away (cbgpu_agg_to_rel) before the next.
+ * cbgpu_agg_slot_bytes: device bytes per table slot (two slots are provisioned per group), for sizing against a budget. */
+int			cbgpu_agg_set_partition(cbgpu_aggtable *t, int32_t npart, int32_t part);
+int64_t		cbgpu_agg_slot_bytes(int32_t nkeys, int32_t naccs);
 int			cbgpu_agg_reset(cbgpu_aggtable *t);
 /* number of groups present (blocking) */
 int			cbgpu_agg_ngroups(cbgpu_aggtable *t, int64_t *ngroups);

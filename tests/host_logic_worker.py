@@ -78,7 +78,9 @@ def main():
         return P.Agg(s9, P.AGG_PLAIN, P.AGGSPLIT_SIMPLE, [], [("n", P.Aggref(P.AGG_COUNT_STAR))])
 
     ex = capi.Executor(ctx, dev)
-    for name, build in (("having", having), ("sorted_agg", sorted_agg), ("sort_without_limit", sort_without_limit),
+    # HAVING compares exact aggregate states on the host: it runs (and over the no-op runtime yields no group)
+    out["ran"]["having"] = {"rows": len(ex.run(having()).rows)}
+    for name, build in (("sorted_agg", sorted_agg), ("sort_without_limit", sort_without_limit),
                         ("right_join", right_join), ("numeric_join_key", numeric_join_key), ("bad_scanrelid", bad_scanrelid)):
         before = ctx.launches()
         try:

@@ -39,18 +39,18 @@ def _run(env):
 def _check(out):
     ran, refused = out["ran"], out["refused"]
     for name in ("q1", "q3", "q5", "q1_generic", "q3_generic", "q5_generic", "q1_3seg", "q3_3seg", "q5_3seg",
-                 "ssb_q4_1", "ssb_q4_2", "ssb_q4_3", "q1_after_refusals"):
+                 "ssb_q4_1", "ssb_q4_2", "ssb_q4_3", "q1_after_refusals", "having"):
         assert ran[name]["rows"] == 0, name            # nothing is computed on the host: no kernel, no rows
     for name in ("q1", "q3", "q5", "q1_3seg", "q3_3seg", "q5_3seg"):
         assert ran[name]["launches"] > 0
     assert ran["q3_3seg"]["launches"] > ran["q3"]["launches"]      # three segment executors and their Motions
-    want = {"having": (UNSUPPORTED, "HAVING"), "sorted_agg": (UNSUPPORTED, "hashed / plain"),
+    want = {"sorted_agg": (UNSUPPORTED, "hashed / plain"),
             "sort_without_limit": (UNSUPPORTED, "Sort without LIMIT"), "right_join": (UNSUPPORTED, "join type"),
             "numeric_join_key": (UNSUPPORTED, "hash_numeric"), "bad_scanrelid": (INVALID, "scanrelid 9")}
     for name, (code, frag) in want.items():
         assert refused[name]["error"] is not None, name
         assert refused[name]["code"] == code and frag in refused[name]["error"], refused[name]
-    for name in ("having", "sorted_agg", "numeric_join_key", "bad_scanrelid"):
+    for name in ("sorted_agg", "numeric_join_key", "bad_scanrelid"):
         assert refused[name]["launches"] == 0          # refused before anything reached the device
     # CHECK_FOR_INTERRUPTS between pipelines: the query stops early with its own code, the next one runs
     it = out["interrupt"]

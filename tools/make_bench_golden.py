@@ -272,6 +272,13 @@ def main():
         if "q1" in want:
             gold["q1_sf100"] = run_q1(pool, 100, args.q1_ranks)
             print("q1 sf100 %.0f s" % (time.time() - t0), flush=True)
+        if "sf10" in want:
+            # tests/test_gpu_sf.py: the same queries at a size between the oracle's reach and the bench's
+            gold["q3_sf10"] = run_q3(pool, 10)
+            gold["q5_sf10"] = run_q5(pool, 10)
+            gold["q1_sf10"] = run_q1(pool, 10, 1)
+            gold["ssb_sf10"] = run_ssb(pool, 10)
+            print("sf10 %.0f s" % (time.time() - t0), flush=True)
         for k in sorted(want):
             if k.startswith("small"):
                 # tests/test_bench_golden.py: the same code at a size the oracle can follow
