@@ -296,6 +296,9 @@ def gpu():
             "cbgpu_ht_has_duplicates": (C.c_int, [vp]),
             "cbgpu_ht_probe_pairs": (C.c_int, [vp, vp, vp, C.POINTER(i32), i32, vp, i64, vp]),
             "cbgpu_pairs_free": (None, [vp]),
+            "cbgpu_merge_sorted_runs": (C.c_int, [vp, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, i32, C.POINTER(vp),
+                                                  C.POINTER(i32)]),
+            "cbgpu_dev_free": (None, [vp, vp]),
             "cbgpu_read_u32": (C.c_int, [vp, vp, i64, vp]),
             "cbgpu_motion_unique_id": (C.c_int, [vp]),
             "cbgpu_motion_create": (C.c_int, [vp, C.c_int, C.c_int, vp, C.POINTER(vp)]),

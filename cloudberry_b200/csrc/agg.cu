@@ -22,9 +22,15 @@ next_pow2(int64_t v)
 	return p;
 }
 
-__global__ void
-k_agg_init(AggDev t, const int32_t *kinds)
+struct AggKinds
 {
+	int32_t		k[CBP_MAX_AGGS];
+};
+
+__global__ void
+k_agg_init(AggDev t, const AggKinds kk)
+{
+	const int32_t *kinds = kk.k;
 	size_t		cap = (size_t) t.mask + 1;
 	size_t		i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
 	size_t		stride = (size_t) gridDim.x * blockDim.x;
@@ -56,19 +62,17 @@ extern "C" int
 cbgpu_agg_reset(cbgpu_aggtable *t)
 {
 	cbgpu_ctx  *ctx = t->ctx;
-	int32_t    *dk;
+	AggKinds	kk;
 
 	t->counted = false;
-
-	CB_CUDA(ctx, cudaMallocAsync(&dk, sizeof(int32_t) * CBP_MAX_AGGS, ctx->stream));
-	CB_CUDA(ctx, cudaMemcpyAsync(dk, t->kinds, sizeof(int32_t) * CBP_MAX_AGGS, cudaMemcpyHostToDevice, ctx->stream));
+	t->snap_valid = false;
+	memcpy(kk.k, t->kinds, sizeof(kk.k));
 	int			blocks = (int) ((t->capacity + 255) / 256);
 
 	if (blocks > ctx->sm_count * 8)
 		blocks = ctx->sm_count * 8;
-	k_agg_init<<<blocks, 256, 0, ctx->stream>>>(t->d, dk);
+	k_agg_init<<<blocks, 256, 0, ctx->stream>>>(t->d, kk);
 	CB_LAUNCHED(ctx, "k_agg_init");
-	CB_CUDA(ctx, cudaFreeAsync(dk, ctx->stream));
 	return CBGPU_OK;
 }
 
@@ -98,13 +102,28 @@ cbgpu_agg_create(cbgpu_ctx *ctx, int32_t nkeys, int32_t naccs, const int32_t *ac
 	for (int a = 0; a < naccs; a++)
 		t->kinds[a] = acc_kinds ? acc_kinds[a] : CBP_ACC_SUM_INT;
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
-	CB_CUDA(ctx, cudaMallocAsync(&t->d.state, cap * sizeof(int32_t), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&t->d.hash, cap * sizeof(uint32_t), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&t->d.keys, cap * sizeof(int64_t) * (nkeys ? nkeys : 1), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&t->d.keynull, cap * sizeof(uint32_t), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&t->d.n, cap * sizeof(int64_t) * (naccs ? naccs : 1), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&t->d.sum, cap * 2 * sizeof(unsigned long long) * (naccs ? naccs : 1), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&t->d.ngroups, sizeof(int32_t) * 4, ctx->stream));
+	{
+		/* one allocation for all the arrays (a table is created per query: seven pool calls were a measurable part of a
+		 * 4 ms step) */
+		size_t		off[8];
+		size_t		sz[7] = {(size_t) cap * sizeof(int32_t), (size_t) cap * sizeof(uint32_t), (size_t) cap * sizeof(int64_t) * (nkeys ? nkeys : 1),
+							 (size_t) cap * sizeof(uint32_t), (size_t) cap * sizeof(int64_t) * (naccs ? naccs : 1),
+							 (size_t) cap * 2 * sizeof(unsigned long long) * (naccs ? naccs : 1), sizeof(int32_t) * 4};
+		char	   *base;
+
+		off[0] = 0;
+		for (int i = 0; i < 7; i++)
+			off[i + 1] = off[i] + ((sz[i] + 255) & ~(size_t) 255);
+		CB_CUDA(ctx, cudaMallocAsync(&base, off[7], ctx->stream));
+		t->base = base;
+		t->d.state = (int32_t *) (base + off[0]);
+		t->d.hash = (uint32_t *) (base + off[1]);
+		t->d.keys = (int64_t *) (base + off[2]);
+		t->d.keynull = (uint32_t *) (base + off[3]);
+		t->d.n = (int64_t *) (base + off[4]);
+		t->d.sum = (unsigned long long *) (base + off[5]);
+		t->d.ngroups = (int32_t *) (base + off[6]);
+	}
 	t->d.full = t->d.ngroups + 1;
 	*out = t;
 	return cbgpu_agg_reset(t);
@@ -136,13 +155,8 @@ cbgpu_agg_free(cbgpu_aggtable *t)
 	if (!t)
 		return;
 	cudaSetDevice(t->ctx->device);
-	cudaFreeAsync(t->d.state, t->ctx->stream);
-	cudaFreeAsync(t->d.hash, t->ctx->stream);
-	cudaFreeAsync(t->d.keys, t->ctx->stream);
-	cudaFreeAsync(t->d.keynull, t->ctx->stream);
-	cudaFreeAsync(t->d.n, t->ctx->stream);
-	cudaFreeAsync(t->d.sum, t->ctx->stream);
-	cudaFreeAsync(t->d.ngroups, t->ctx->stream);
+	cudaFreeAsync(t->base, t->ctx->stream);
+	free(t->snap);
 	free(t);
 }
 
@@ -176,12 +190,53 @@ k_agg_count(AggDev t, int *anynull)
 	}
 }
 
+/* small tables: count, flags and the groups themselves in one kernel and one round trip */
+__global__ void __launch_bounds__(256)
+k_agg_snapshot(AggDev t, AggSnap *out)
+{
+	if (threadIdx.x == 0)
+		out->retry = out->audit = 0;
+	agg_snapshot_block(t, out);
+}
+
+/* the snapshot the stream has just been synchronised on describes table t */
+void
+cb_agg_adopt_snapshot(cbgpu_aggtable *t, const AggSnap *snap)
+{
+	t->snap_valid = false;
+	if (snap->ngroups < 0)
+		return;
+	t->ngroups = snap->ngroups;
+	t->anynull = snap->anynull;
+	t->counted = !snap->full;
+	if (snap->full || snap->ngroups > AGG_SNAP_MAXG)
+		return;
+	if (!t->snap)
+		t->snap = (AggSnap *) malloc(sizeof(AggSnap));
+	if (!t->snap)
+		return;
+	memcpy(t->snap, snap, sizeof(AggSnap));
+	t->snap_valid = true;
+}
+
 extern "C" int
 cbgpu_agg_ngroups(cbgpu_aggtable *t, int64_t *ngroups)
 {
 	cbgpu_ctx  *ctx = t->ctx;
 	int32_t		h[3];
 
+	if (!t->counted && t->capacity <= AGG_SNAP_MAXCAP && ctx->agg_snap)
+	{
+		ctx->agg_snap->ngroups = -1;
+		k_agg_snapshot<<<1, 256, 0, ctx->stream>>>(t->d, ctx->agg_snap);
+		CB_LAUNCHED(ctx, "k_agg_snapshot");
+		CB_CUDA(ctx, CB_STATUS_RIDE(ctx));
+		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		CB_STATUS_FETCHED(ctx);
+		if (ctx->agg_snap->full)
+			return cb_fail(ctx, CBGPU_ERR_NOMEM, "aggregate hash table overflow (%s capacity %lld slots)", "", t->capacity);
+		cb_agg_adopt_snapshot(t, ctx->agg_snap);
+	}
 	if (!t->counted)
 	{
 		/* groups are counted here, once per fill, rather than with one same-address atomic per new
@@ -215,6 +270,7 @@ void
 cb_agg_touch(cbgpu_aggtable *t)
 {
 	t->counted = false;
+	t->snap_valid = false;
 }
 
 /* compaction: slots in `ready` state -> dense rows (agg_retrieve_hash_table's table walk,
@@ -275,6 +331,23 @@ cbgpu_agg_read(cbgpu_aggtable *t, int64_t maxgroups, int64_t *keys, uint32_t *ke
 		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_agg_read: %s%lld groups exceed the caller's buffer", "", ng);
 	if (ng == 0)
 		return CBGPU_OK;
+	if (t->snap_valid && t->snap->ngroups == ng)
+	{
+		/* the groups came with the count */
+		for (int64_t g = 0; g < ng; g++)
+		{
+			keynull[g] = t->snap->keynull[g];
+			for (int k = 0; k < t->d.nkeys; k++)
+				keys[g * t->d.nkeys + k] = t->snap->keys[g][k];
+			for (int a = 0; a < t->d.naccs; a++)
+			{
+				n[g * t->d.naccs + a] = t->snap->n[g][a];
+				sum_lo[g * t->d.naccs + a] = t->snap->lo[g][a];
+				sum_hi[g * t->d.naccs + a] = t->snap->hi[g][a];
+			}
+		}
+		return CBGPU_OK;
+	}
 	o.maxgroups = ng;
 	CB_CUDA(ctx, cudaMallocAsync(&o.keys, sizeof(int64_t) * ng * nk, ctx->stream));
 	CB_CUDA(ctx, cudaMallocAsync(&o.keynull, sizeof(uint32_t) * ng, ctx->stream));
@@ -650,6 +723,189 @@ k_topn_final(TopnParams p, const uint32_t *cand, const int *ncand, int64_t nall,
 		if (rank < p.k)
 			out[rank] = ri;
 	}
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * merge receive: a Gather Motion whose senders' streams are sorted (Motion.sendSorted; execMotionSortedReceiver,
+ * nodeMotion.c:433, merges them with a binary heap under CdbMergeComparator :1010).  The gathered relation holds the
+ * streams one after another, so it is a sequence of sorted runs: a row's place in the merged order is its place in its
+ * own run plus, for every other run, the number of rows there that go before it (binary search; equal keys: the earlier
+ * run first) - every row finds its place independently, no heap, no passes.
+ * --------------------------------------------------------------------------------------------- */
+#define MERGE_MAXRUNS 64
+
+struct MergeParams
+{
+	const void *key[TOPN_MAXKEYS];
+	const uint8_t *nulls[TOPN_MAXKEYS];
+	int32_t		keytype[TOPN_MAXKEYS];
+	int32_t		desc[TOPN_MAXKEYS];
+	int32_t		uns[TOPN_MAXKEYS];
+	int32_t		nkeys;
+	int32_t		nruns;
+	int64_t		n;
+	int64_t		start[MERGE_MAXRUNS + 1];
+	int32_t    *nfound;			/* run starts found (k_merge_find_runs)                               */
+	unsigned long long *found;
+	uint32_t   *order;
+};
+
+/* < 0: row a sorts before row b; 0: equal keys.  NULLS LAST ascending, NULLS FIRST descending (the defaults) */
+__device__ __forceinline__ int
+merge_cmp(const MergeParams &p, int64_t a, int64_t b)
+{
+	for (int i = 0; i < p.nkeys; i++)
+	{
+		const bool	an = p.nulls[i] && p.nulls[i][a];
+		const bool	bn = p.nulls[i] && p.nulls[i][b];
+		int			c;
+
+		if (an || bn)
+			c = (an && bn) ? 0 : (an ? 1 : -1);
+		else
+		{
+			const int64_t x = cb_load_widen(p.key[i], p.keytype[i], (uint32_t) a);
+			const int64_t y = cb_load_widen(p.key[i], p.keytype[i], (uint32_t) b);
+
+			if (x == y)
+				c = 0;
+			else if (p.uns[i])
+				c = (uint64_t) x < (uint64_t) y ? -1 : 1;
+			else
+				c = x < y ? -1 : 1;
+		}
+		if (p.desc[i])
+			c = -c;
+		if (c)
+			return c;
+	}
+	return 0;
+}
+
+/* a run starts wherever a row sorts before its predecessor */
+__global__ void
+k_merge_find_runs(MergeParams p)
+{
+	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x + 1;
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; i < p.n; i += stride)
+		if (merge_cmp(p, i, i - 1) < 0)
+		{
+			const int	at = atomicAdd(p.nfound, 1);
+
+			if (at < MERGE_MAXRUNS)
+				p.found[at] = (unsigned long long) i;
+		}
+}
+
+__global__ void
+k_merge_place(MergeParams p)
+{
+	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; i < p.n; i += stride)
+	{
+		int			r = 0;
+		int64_t		pos;
+
+		while (r + 1 < p.nruns && p.start[r + 1] <= i)
+			r++;
+		pos = i - p.start[r];
+		for (int q = 0; q < p.nruns; q++)
+		{
+			int64_t		lo = p.start[q],
+						hi = p.start[q + 1];
+
+			if (q == r)
+				continue;
+			/* rows of run q that go before row i: those that sort before it, and - in an earlier run - its equals too */
+			while (lo < hi)
+			{
+				const int64_t mid = lo + (hi - lo) / 2;
+				const int	c = merge_cmp(p, mid, i);
+
+				if (c < 0 || (c == 0 && q < r))
+					lo = mid + 1;
+				else
+					hi = mid;
+			}
+			pos += lo - p.start[q];
+		}
+		p.order[pos] = (uint32_t) i;
+	}
+}
+
+extern "C" int
+cbgpu_merge_sorted_runs(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const int32_t *descending, const int32_t *unsigned_cmp,
+						int32_t nkeys, int32_t max_runs, uint32_t **order_dev, int32_t *nruns_out)
+{
+	MergeParams p;
+	int32_t		nfound = 0;
+	unsigned long long found[MERGE_MAXRUNS];
+	int			blocks;
+
+	*order_dev = NULL;
+	if (nruns_out)
+		*nruns_out = rel->nrows > 0;
+	if (nkeys < 1 || nkeys > TOPN_MAXKEYS || max_runs < 1 || max_runs > MERGE_MAXRUNS)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "merge receive supports 1..4 sort keys and up to 64 senders (%s got %lld keys)", "", nkeys);
+	memset(&p, 0, sizeof(p));
+	for (int i = 0; i < nkeys; i++)
+	{
+		if (keycols[i] < 0 || keycols[i] >= rel->ncols)
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_merge_sorted_runs: bad key column%s %lld", "", keycols[i]);
+		p.key[i] = rel->data[keycols[i]];
+		p.nulls[i] = rel->nulls[keycols[i]];
+		p.keytype[i] = rel->types[keycols[i]];
+		p.desc[i] = descending[i];
+		p.uns[i] = unsigned_cmp ? unsigned_cmp[i] : 0;
+		if (p.keytype[i] == CB_FLOAT8)
+			return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "merge receive over a float8 key%s", "", 0);
+	}
+	p.nkeys = nkeys;
+	p.n = rel->nrows;
+	if (rel->nrows < 2)
+		return CBGPU_OK;
+	blocks = (int) ((rel->nrows + 255) / 256);
+	if (blocks > ctx->sm_count * 8)
+		blocks = ctx->sm_count * 8;
+	CB_CUDA(ctx, cudaMallocAsync(&p.nfound, sizeof(int32_t) + MERGE_MAXRUNS * sizeof(unsigned long long) + 8, ctx->stream));
+	p.found = (unsigned long long *) ((char *) p.nfound + 8);
+	CB_CUDA(ctx, cudaMemsetAsync(p.nfound, 0, sizeof(int32_t), ctx->stream));
+	k_merge_find_runs<<<blocks, 256, 0, ctx->stream>>>(p);
+	CB_LAUNCHED(ctx, "k_merge_find_runs");
+	CB_CUDA(ctx, cudaMemcpyAsync(&nfound, p.nfound, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(found, p.found, sizeof(found), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	CB_CUDA(ctx, cudaFreeAsync(p.nfound, ctx->stream));
+	if (nfound + 1 > max_runs)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "merge receive: %s%lld sorted runs arrived from fewer senders - a sender's stream is not in the Motion's sort order",
+					   "", (long long) nfound + 1);
+	if (nruns_out)
+		*nruns_out = nfound + 1;
+	if (nfound == 0)
+		return CBGPU_OK;		/* one run: arrival order is the order */
+	/* run starts in ascending order (found in atomic order) */
+	for (int a = 1; a < nfound; a++)
+		for (int b = a; b > 0 && found[b] < found[b - 1]; b--)
+		{
+			unsigned long long t = found[b];
+
+			found[b] = found[b - 1];
+			found[b - 1] = t;
+		}
+	p.nruns = nfound + 1;
+	p.start[0] = 0;
+	for (int a = 0; a < nfound; a++)
+		p.start[a + 1] = (int64_t) found[a];
+	p.start[p.nruns] = rel->nrows;
+	CB_CUDA(ctx, cudaMallocAsync(&p.order, (size_t) rel->nrows * sizeof(uint32_t), ctx->stream));
+	k_merge_place<<<blocks, 256, 0, ctx->stream>>>(p);
+	CB_LAUNCHED(ctx, "k_merge_place");
+	*order_dev = p.order;
+	return CBGPU_OK;
 }
 
 extern "C" int

@@ -69,6 +69,11 @@ struct cbgpu_ctx
 		int			worth;
 	}			early_cache[CB_EARLY_CACHE];
 	int			early_cache_n;
+	/* pinned (mapped) host buffer small aggregate tables are snapshotted into by the kernel that finishes them: group count,
+	 * flags and the groups themselves arrive with ONE synchronisation (struct AggSnap, below) */
+	struct AggSnap *agg_snap;
+	void	   *small_dev;		/* device scratch of the small-group scan kernel, grown on demand              */
+	size_t		small_dev_bytes;
 };
 
 /* zero-filled scratch block `slot` of at least `bytes` (grown on demand, freed with the context) */
@@ -124,17 +129,89 @@ struct AggDev
 	int32_t    *full;			/* set when an insert found no free slot                              */
 };
 
+/* what a finishing kernel leaves in pinned host memory for tables of at most AGG_SNAP_MAXCAP slots and AGG_SNAP_MAXG
+ * groups: everything agg_retrieve_hash_table (nodeAgg.c:2952) would walk the table for */
+#define AGG_SNAP_MAXG 64
+#define AGG_SNAP_MAXCAP 4096
+struct AggSnap
+{
+	int32_t		ngroups;		/* -1: not taken (retry / audit flags say why)                        */
+	int32_t		full;
+	int32_t		anynull;
+	int32_t		retry;
+	int32_t		audit;
+	int32_t		pad[3];
+	uint32_t	keynull[AGG_SNAP_MAXG];
+	int64_t		keys[AGG_SNAP_MAXG][CBP_MAX_KEYS];
+	int64_t		n[AGG_SNAP_MAXG][CBP_MAX_AGGS];
+	int64_t		lo[AGG_SNAP_MAXG][CBP_MAX_AGGS];
+	int64_t		hi[AGG_SNAP_MAXG][CBP_MAX_AGGS];
+};
+
 struct cbgpu_aggtable
 {
 	cbgpu_ctx  *ctx;
 	AggDev		d;
+	void	   *base;			/* the one device allocation all of d's arrays live in                */
 	int64_t		capacity;
 	int32_t		kinds[CBP_MAX_AGGS];
 	/* group count / "some group key is NULL", valid until the table is written again */
 	bool		counted;
 	int64_t		ngroups;
 	int32_t		anynull;
+	/* the groups themselves, when a snapshot brought them along (cb_agg_adopt_snapshot) */
+	bool		snap_valid;
+	AggSnap    *snap;			/* host copy, allocated on first use                                  */
 };
+
+#ifdef __CUDACC__
+/* one CTA walks a small table and writes the snapshot (call with all threads of the block, after the block's own
+ * updates of the table are ordered by __syncthreads) */
+__device__ __forceinline__ void
+agg_snapshot_block(const AggDev &t, AggSnap *out)
+{
+	__shared__ int s_n,
+				s_an;
+	const size_t cap = (size_t) t.mask + 1;
+
+	if (threadIdx.x == 0)
+	{
+		s_n = 0;
+		s_an = 0;
+	}
+	__syncthreads();
+	for (size_t i = threadIdx.x; i < cap; i += blockDim.x)
+	{
+		if (((volatile int32_t *) t.state)[i] != 2)
+			continue;
+		const int	g = atomicAdd(&s_n, 1);
+
+		if (t.keynull[i])
+			s_an = 1;
+		if (g >= AGG_SNAP_MAXG)
+			continue;
+		out->keynull[g] = t.keynull[i];
+		for (int k = 0; k < t.nkeys; k++)
+			out->keys[g][k] = t.keys[i * t.nkeys + k];
+		for (int a = 0; a < t.naccs; a++)
+		{
+			out->n[g][a] = ((volatile int64_t *) t.n)[i * t.naccs + a];
+			out->lo[g][a] = (int64_t) ((volatile unsigned long long *) t.sum)[(i * t.naccs + a) * 2];
+			out->hi[g][a] = (int64_t) ((volatile unsigned long long *) t.sum)[(i * t.naccs + a) * 2 + 1];
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		out->full = *(volatile int32_t *) t.full;
+		out->anynull = s_an;
+		out->ngroups = s_n;
+	}
+	__threadfence_system();
+}
+#endif
+void		cb_agg_adopt_snapshot(cbgpu_aggtable *t, const AggSnap *snap);
+
 
 #ifdef __CUDACC__
 #define CB_HD_DECL __host__ __device__ __forceinline__

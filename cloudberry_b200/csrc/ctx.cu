@@ -53,6 +53,8 @@ cbgpu_ctx_create(int device, cbgpu_ctx **out)
 	CB_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
 	CB_CUDA(ctx, cudaMallocHost(&ctx->h_status, sizeof(int)));
 	*ctx->h_status = 0;
+	CB_CUDA(ctx, cudaMallocHost(&ctx->agg_snap, sizeof(AggSnap)));
+	memset(ctx->agg_snap, 0, sizeof(AggSnap));
 	ctx->opt_debug = getenv("CBGPU_DEBUG") != NULL;
 	ctx->opt_no_early_filter = getenv("CBGPU_NO_EARLY_FILTER") != NULL;
 	ctx->opt_no_keyslot = getenv("CBGPU_NO_KEYSLOT") != NULL;
@@ -79,6 +81,9 @@ cbgpu_ctx_destroy(cbgpu_ctx *ctx)
 		cudaFree(ctx->flush_buf);
 	cudaFree(ctx->d_status);
 	cudaFreeHost(ctx->h_status);
+	cudaFreeHost(ctx->agg_snap);
+	if (ctx->small_dev)
+		cudaFree(ctx->small_dev);
 	for (int i = 0; i < CB_SCRATCH_SLOTS; i++)
 		free(ctx->scratch[i]);
 	cudaEventDestroy(ctx->ev_t0);
@@ -745,6 +750,89 @@ cbgpu_rel_copy_rows(cbgpu_rel *dst, int64_t dst_lo, cbgpu_rel *src, int64_t src_
 			CB_CUDA(ctx, cudaMemcpyAsync(dst->nulls[c] + dst_lo, src->nulls[c] + src_lo, (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
 		}
 	}
+	return CBGPU_OK;
+}
+
+/* dst rows [0, n) = src rows idx[0..n) (device index list), every column and NULL map: an ordered gather (the merged
+ * order of a sorted Motion, a selection) */
+struct TakeRows
+{
+	const void *src[CB_MAX_COLS_REL];
+	void	   *dst[CB_MAX_COLS_REL];
+	const uint8_t *snull[CB_MAX_COLS_REL];
+	uint8_t    *dnull[CB_MAX_COLS_REL];
+	int32_t		width[CB_MAX_COLS_REL];
+	int32_t		ncols;
+	int64_t		n;
+	const uint32_t *idx;
+};
+
+__global__ void
+k_take_rows(TakeRows p)
+{
+	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; i < p.n; i += stride)
+	{
+		const uint32_t r = p.idx[i];
+
+		for (int c = 0; c < p.ncols; c++)
+		{
+			switch (p.width[c])
+			{
+				case 1: ((uint8_t *) p.dst[c])[i] = ((const uint8_t *) p.src[c])[r]; break;
+				case 4: ((uint32_t *) p.dst[c])[i] = ((const uint32_t *) p.src[c])[r]; break;
+				case 16: ((uint4 *) p.dst[c])[i] = ((const uint4 *) p.src[c])[r]; break;
+				default: ((unsigned long long *) p.dst[c])[i] = ((const unsigned long long *) p.src[c])[r]; break;
+			}
+			if (p.dnull[c])
+				p.dnull[c][i] = p.snull[c][r];
+		}
+	}
+}
+
+extern "C" int
+cbgpu_rel_take_rows(cbgpu_rel *dst, cbgpu_rel *src, const uint32_t *dev_idx, int64_t n)
+{
+	cbgpu_ctx  *ctx = dst->ctx;
+	TakeRows	p;
+
+	if (dst->ncols != src->ncols || n < 0 || n > dst->capacity || dst->ncols > CB_MAX_COLS_REL)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_take_rows: shape / range mismatch%s (%lld rows)", "", n);
+	if (n == 0)
+		return CBGPU_OK;
+	memset(&p, 0, sizeof(p));
+	for (int c = 0; c < dst->ncols; c++)
+	{
+		if (dst->types[c] != src->types[c])
+			return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_take_rows: column %s%lld type mismatch", "", c);
+		if (src->nulls[c])
+		{
+			int			rc = cbgpu_rel_add_nullmap(dst, c);
+
+			if (rc)
+				return rc;
+		}
+		p.src[c] = src->data[c];
+		p.dst[c] = dst->data[c];
+		p.snull[c] = src->nulls[c];
+		p.dnull[c] = src->nulls[c] ? dst->nulls[c] : NULL;
+		p.width[c] = cb_type_w(dst->types[c]);
+	}
+	p.ncols = dst->ncols;
+	p.n = n;
+	p.idx = dev_idx;
+	{
+		int			blocks = (int) ((n + 255) / 256);
+
+		if (blocks > ctx->sm_count * 8)
+			blocks = ctx->sm_count * 8;
+		k_take_rows<<<blocks, 256, 0, ctx->stream>>>(p);
+		CB_LAUNCHED(ctx, "k_take_rows");
+	}
+	if (dst->nrows < n)
+		dst->nrows = n;
 	return CBGPU_OK;
 }
 

@@ -624,27 +624,50 @@ stream_over_rel(CbEState *es, CbStream *s, cbgpu_rel *rel, const PExpr *shape, i
 static int
 run_pipeline(CbEState *es, CbPipeline *pl)
 {
-	int			multi = -1;
+	int			multi[CBP_MAX_SRC],
+				at[CBP_MAX_SRC];
+	int			nmulti = 0;
+	int64_t		passes = 1;
 
 	for (int j = 0; j < pl->nprobes; j++)
 		if (pl->probes[j].ht && cbgpu_ht_nbatch(pl->probes[j].ht) > 1)
 		{
-			if (multi >= 0)
-				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "two multi-batch hash joins in one pipeline (raise the operator memory)");
-			multi = j;
+			multi[nmulti] = j;
+			at[nmulti++] = 0;
+			passes *= cbgpu_ht_nbatch(pl->probes[j].ht);
 		}
-	if (multi < 0)
+	if (nmulti == 0)
 	{
 		GPU(es, cbgpu_pipeline_run(es->es_ctx, pl));
 		return CBGPU_OK;
 	}
-	for (int b = 0; b < cbgpu_ht_nbatch(pl->probes[multi].ht); b++)
+	/* several multi-batch joins in one pipeline: a row reaches the sink in the one pass whose batch combination holds all
+	 * its partners (the reference's joins each re-read their own spilled batches; stacked here, the passes multiply) */
+	if (passes > 65536)
+		return es_fail(es, CBGPU_ERR_UNSUPPORTED, "%s%lld passes over the outer side for the multi-batch hash joins of one pipeline (raise the operator memory)", "", (long long) passes);
+	for (int k = 0; k < nmulti; k++)
+		GPU(es, cbgpu_ht_load_batch((cbgpu_hashtable *) pl->probes[multi[k]].ht, 0));
+	for (;;)
 	{
+		int			k;
+
 		if (es->es_interrupt_pending && es->es_interrupt_pending(es))
 			return es_fail(es, CBGPU_ERR_INTERRUPTED, "canceling statement due to user request");
-		GPU(es, cbgpu_ht_load_batch((cbgpu_hashtable *) pl->probes[multi].ht, b));
 		GPU(es, cbgpu_pipeline_run(es->es_ctx, pl));
 		es->es_hashjoin_batches_run++;
+		/* next combination: the LAST join's batch changes fastest (its table is usually the smallest to reload) */
+		for (k = nmulti - 1; k >= 0; k--)
+		{
+			if (++at[k] < cbgpu_ht_nbatch(pl->probes[multi[k]].ht))
+			{
+				GPU(es, cbgpu_ht_load_batch((cbgpu_hashtable *) pl->probes[multi[k]].ht, at[k]));
+				break;
+			}
+			at[k] = 0;
+			GPU(es, cbgpu_ht_load_batch((cbgpu_hashtable *) pl->probes[multi[k]].ht, 0));
+		}
+		if (k < 0)
+			break;
 	}
 	return CBGPU_OK;
 }
@@ -746,12 +769,17 @@ stream_materialize(CbEState *es, CbPlanState *ps, CbStream *s, Owned *own, cbgpu
 
 /* does the stream just expose the columns of one relation, untouched? */
 static int
-stream_is_plain(const CbStream *s, cbgpu_rel **rel)
+stream_is_plain(const CbStream *s, cbgpu_rel **rel, const uint32_t **sel)
 {
 	cbgpu_rel  *r = NULL;
 
-	if (s->pipe.nops != 0 || s->pipe.nprobes != 0 || s->pipe.drv_nsrc != 0 || s->pipe.visimap)
+	if (s->pipe.nops != 0 || s->pipe.nprobes != 0 || s->pipe.visimap)
 		return 0;
+	/* an ordered selection over the relation (merge receive) is plain too when the caller can take it (sel != NULL) */
+	if (s->pipe.drv_nsrc != 0 && !(sel && s->pipe.drv_nsrc == 1 && s->pipe.drv_idx[0]))
+		return 0;
+	if (sel)
+		*sel = s->pipe.drv_nsrc == 1 ? s->pipe.drv_idx[0] : NULL;
 	for (int i = 0; i < s->pipe.ncols; i++)
 	{
 		if (s->pipe.cols[i].src != 0)
@@ -760,7 +788,7 @@ stream_is_plain(const CbStream *s, cbgpu_rel **rel)
 			return 0;
 		r = s->col_rel[i];
 	}
-	if (!r || cbgpu_rel_nrows(r) != s->pipe.nrows)
+	if (!r || (cbgpu_rel_nrows(r) != s->pipe.nrows && !(sel && *sel)))
 		return 0;
 	*rel = r;
 	return 1;
@@ -774,6 +802,8 @@ static int	node_open_inner(CbPlanState *ps, CbStream **out);
 static const char *node_name(CbNodeTag t);
 static int	cluster_run_motion(CbPlanState *ps);
 static int	open_limitsort(CbPlanState *ps, CbStream **out);
+static int	sort_key_columns(CbEState *es, const PExpr *shape, int nshape, int lead, const CbSortKey *keys, int nkeys, int32_t *keycols,
+							 int32_t *desc, int32_t *uns, int *nk_out);
 
 static int
 open_seqscan(CbPlanState *ps, CbStream **out)
@@ -827,7 +857,7 @@ hash_build(CbPlanState *hashps)
 	if (h->nhashkeys < 1 || h->nhashkeys > CBP_MAX_KEYS)
 		return es_fail(es, CBGPU_ERR_UNSUPPORTED, "hash join with %d keys is beyond the GPU path's limit", h->nhashkeys);
 	p->inner_nout = is->nout;
-	if (stream_is_plain(is, &rel))
+	if (stream_is_plain(is, &rel, NULL))
 	{
 		/* a bare scan without quals: build straight over the base relation's columns */
 		for (int i = 0; i < is->nout; i++)
@@ -947,10 +977,15 @@ open_hashjoin(CbPlanState *ps, CbStream **out)
 		if (s->pe[keys[k]].kind == PE_STATE)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "join key over a transition state");
 	}
-	if (cbgpu_ht_has_duplicates(hp->ht) && (hj->jointype == CB_JOIN_INNER || hj->jointype == CB_JOIN_LEFT))
+	if ((cbgpu_ht_has_duplicates(hp->ht) && (hj->jointype == CB_JOIN_INNER || hj->jointype == CB_JOIN_LEFT)) ||
+		hj->jointype == CB_JOIN_RIGHT || hj->jointype == CB_JOIN_FULL)
 	{
-		/* N:M join: materialise the outer side, emit (outer, inner) row-id pairs for every match
-		 * (ExecScanHashBucket walks the whole chain, nodeHash.c:2255), continue from the pairs */
+		const int	fill_outer = hj->jointype == CB_JOIN_LEFT || hj->jointype == CB_JOIN_FULL;
+		const int	fill_inner = hj->jointype == CB_JOIN_RIGHT || hj->jointype == CB_JOIN_FULL;
+
+		/* N:M join, or a join that returns unmatched build rows: materialise the outer side, emit (outer, inner) row-id
+		 * pairs for every match (ExecScanHashBucket walks the whole chain, nodeHash.c:2255) - plus, per join type, one
+		 * pair with a missing side for every unmatched row - and continue from the pairs */
 		CbStream   *s2;
 		cbgpu_rel  *orel;
 		PExpr		shape[MAX_OUT + CBP_MAX_KEYS];
@@ -978,12 +1013,12 @@ open_hashjoin(CbPlanState *ps, CbStream **out)
 		if (me->owned.npairs >= 8)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "too many N:M joins under one node");
 		pairs = &me->owned.pairs[me->owned.npairs++];
-		if (hj->jointype == CB_JOIN_LEFT)
-			GPU(es, cbgpu_ht_probe_pairs_left(es->es_ctx, hp->ht, orel, keycols, hj->nhashkeys, pairs));
-		else
-			GPU(es, cbgpu_ht_probe_pairs(es->es_ctx, hp->ht, orel, keycols, hj->nhashkeys, NULL, 0, pairs));
+		GPU(es, cbgpu_ht_probe_pairs_outer(es->es_ctx, hp->ht, orel, keycols, hj->nhashkeys, fill_outer, fill_inner, pairs));
 		s2 = stream_new(me);
 		TRY(stream_over_rel(es, s2, orel, shape, nouter));
+		if (fill_inner)
+			for (int i = 0; i < s2->npe; i++)
+				s2->pe[i].maybe_null = 1;	/* the outer side of an unmatched build row is NULL */
 		s2->pipe.nrows = pairs->npairs;
 		s2->pipe.drv_nsrc = 2;
 		s2->pipe.drv_idx[0] = pairs->outer_idx;
@@ -992,7 +1027,7 @@ open_hashjoin(CbPlanState *ps, CbStream **out)
 		s2->rows_in = s->rows_in;
 		nouter = s2->nout;
 		memcpy(outer, s2->out, sizeof(int) * (size_t) nouter);
-		TRY(inner_out_exprs(es, s2, hp, 1, hj->jointype == CB_JOIN_LEFT, inner));
+		TRY(inner_out_exprs(es, s2, hp, 1, fill_outer, inner));
 		s = s2;
 		vc.s = s;
 	}
@@ -1352,8 +1387,8 @@ agg_run(CbPlanState *ps, AggPlanInfo *info, cbgpu_aggtable **table_out, CbStream
 		*parts_out = NULL;
 	/* the operator's memory (PlanStateOperatorMemKB, execnodes.h:1166) bounds the table: two slots per group */
 	const int64_t max_cap = es->es_operator_mem_kb > 0 && parts_out ?
-		(es->es_operator_mem_kb * 1024 / (2 * cbgpu_agg_slot_bytes(info->nkeys, info->naccs)) > 1024 ?
-		 es->es_operator_mem_kb * 1024 / (2 * cbgpu_agg_slot_bytes(info->nkeys, info->naccs)) : 1024) : 0;
+		(es->es_operator_mem_kb * 1024 / (2 * cbgpu_agg_slot_bytes(info->nkeys, info->naccs)) > 64 ?
+		 es->es_operator_mem_kb * 1024 / (2 * cbgpu_agg_slot_bytes(info->nkeys, info->naccs)) : 64) : 0;
 	int			npart = 1;
 
 	if (max_cap > 0 && cap > max_cap)
@@ -2437,6 +2472,30 @@ motion_recv_stream(CbPlanState *ps, cbgpu_rel *recv, CbStream **out)
 		if (s->out[i] < 0)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "too many columns in one pipeline");
 	}
+	if (m->nsortkeys > 0 && s->pipe.nrows > 1)
+	{
+		/* merge receive (execMotionSortedReceiver, nodeMotion.c:433): the senders' sorted streams lie one after another
+		 * in the receive buffer; read them in merged order */
+		int32_t		keycols[8],
+					desc[8],
+					uns[8];
+		int			nk = 0;
+		int32_t		nruns = 0;
+		uint32_t   *order = NULL;
+		int64_t		before = cbgpu_kernel_launches(es->es_ctx);
+
+		if (m->motionType != CB_MOTIONTYPE_GATHER && m->motionType != CB_MOTIONTYPE_GATHER_SINGLE)
+			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "a sorted Motion that is not a Gather");
+		TRY(sort_key_columns(es, p->send_pe, p->send_nout, lead, m->sortkeys, m->nsortkeys, keycols, desc, uns, &nk));
+		GPU(es, cbgpu_merge_sorted_runs(es->es_ctx, recv, keycols, desc, uns, nk, es->es_numsegments, &order, &nruns));
+		ps->instrument.kernels += cbgpu_kernel_launches(es->es_ctx) - before;
+		if (order)
+		{
+			p->owned.devs[p->owned.ndevs++] = order;
+			s->pipe.drv_nsrc = 1;
+			s->pipe.drv_idx[0] = order;
+		}
+	}
 	ps->instrument.ntuples = (double) s->pipe.nrows;
 	*out = s;
 	return CBGPU_OK;
@@ -2728,6 +2787,57 @@ rel_to_result(CbEState *es, cbgpu_rel *rel, const PExpr *shape, int nshape, cons
 	return CBGPU_OK;
 }
 
+/* sort keys over a materialised stream (columns laid out as stream_materialize / the Motion receive buffer does: one
+ * column per scalar, N / lo / hi per transition state, `lead` leading extra columns) -> the device comparators' key columns.
+ * Exact 128-bit sums order through (hi signed, lo unsigned). */
+static int
+sort_key_columns(CbEState *es, const PExpr *shape, int nshape, int lead, const CbSortKey *keys, int nkeys, int32_t *keycols,
+				 int32_t *desc, int32_t *uns, int *nk_out)
+{
+	int			colstart[MAX_OUT];
+	int			c = lead;
+	int			nk = 0;
+
+	for (int i = 0; i < nshape; i++)
+	{
+		colstart[i] = c;
+		c += shape[i].kind == PE_STATE ? 3 : 1;
+	}
+	for (int k = 0; k < nkeys; k++)
+	{
+		int			att = keys[k].attno;
+
+		if (att < 1 || att > nshape)
+			return es_fail(es, CBGPU_ERR_INVALID, "sort key %d out of range", att);
+		if (shape[att - 1].kind == PE_STATE)
+		{
+			/* ORDER BY sum(...): order the exact 128-bit sums through (hi signed, lo unsigned) */
+			if (!(shape[att - 1].aggfn == CB_AGG_SUM && shape[att - 1].acckind == CBP_ACC_SUM_INT) &&
+				shape[att - 1].aggfn != CB_AGG_COUNT && shape[att - 1].aggfn != CB_AGG_COUNT_STAR)
+				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "ORDER BY over this aggregate is not implemented on the GPU path");
+			if (nk + 2 > 4)
+				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "too many sort keys for the device comparators");
+			if (shape[att - 1].aggfn == CB_AGG_SUM)
+			{
+				keycols[nk] = colstart[att - 1] + 2; desc[nk] = keys[k].descending; uns[nk] = 0; nk++;
+				keycols[nk] = colstart[att - 1] + 1; desc[nk] = keys[k].descending; uns[nk] = 1; nk++;
+			}
+			else
+			{
+				keycols[nk] = colstart[att - 1]; desc[nk] = keys[k].descending; uns[nk] = 0; nk++;
+			}
+		}
+		else
+		{
+			if (nk + 1 > 4)
+				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "too many sort keys for the device comparators");
+			keycols[nk] = colstart[att - 1]; desc[nk] = keys[k].descending; uns[nk] = 0; nk++;
+		}
+	}
+	*nk_out = nk;
+	return CBGPU_OK;
+}
+
 /* Limit <- Sort: device top-N over the child's materialised rows */
 static int
 limitsort_run(CbPlanState *ps, cbgpu_rel **out_rel, PExpr *out_shape, int *out_nshape)
@@ -2745,20 +2855,10 @@ limitsort_run(CbPlanState *ps, cbgpu_rel **out_rel, PExpr *out_shape, int *out_n
 	int			nk = 0;
 	uint32_t	idx[64];
 	int64_t		nout = 0;
-	int			colstart[MAX_OUT];
 
 	TRY(node_open(ps->lefttree, &s));
 	/* the child's rows as a relation */
 	TRY(stream_materialize(es, ps, s, &p->owned, &rel, shape, &nshape));
-	{
-		int			c = 0;
-
-		for (int i = 0; i < nshape; i++)
-		{
-			colstart[i] = c;
-			c += shape[i].kind == PE_STATE ? 3 : 1;
-		}
-	}
 	for (int i = 0; i < ps->plan->ntargets; i++)
 	{
 		const CbExpr *te = ps->plan->targetlist[i].expr;
@@ -2766,37 +2866,7 @@ limitsort_run(CbPlanState *ps, cbgpu_rel **out_rel, PExpr *out_shape, int *out_n
 		if (te->tag != T_CbVar || te->varno != CB_OUTER_VAR || te->varattno != i + 1)
 			return es_fail(es, CBGPU_ERR_UNSUPPORTED, "Limit/Sort must pass its child's columns through unchanged on the GPU path");
 	}
-	for (int k = 0; k < ls->nkeys; k++)
-	{
-		int			att = ls->keys[k].attno;
-
-		if (att < 1 || att > nshape)
-			return es_fail(es, CBGPU_ERR_INVALID, "sort key %d out of range", att);
-		if (shape[att - 1].kind == PE_STATE)
-		{
-			/* ORDER BY sum(...): order the exact 128-bit sums through (hi signed, lo unsigned) */
-			if (!(shape[att - 1].aggfn == CB_AGG_SUM && shape[att - 1].acckind == CBP_ACC_SUM_INT) &&
-				shape[att - 1].aggfn != CB_AGG_COUNT && shape[att - 1].aggfn != CB_AGG_COUNT_STAR)
-				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "ORDER BY over this aggregate is not implemented on the GPU path");
-			if (nk + 2 > 4)
-				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "too many sort keys for the device top-N");
-			if (shape[att - 1].aggfn == CB_AGG_SUM)
-			{
-				keycols[nk] = colstart[att - 1] + 2; desc[nk] = ls->keys[k].descending; uns[nk] = 0; nk++;
-				keycols[nk] = colstart[att - 1] + 1; desc[nk] = ls->keys[k].descending; uns[nk] = 1; nk++;
-			}
-			else
-			{
-				keycols[nk] = colstart[att - 1]; desc[nk] = ls->keys[k].descending; uns[nk] = 0; nk++;
-			}
-		}
-		else
-		{
-			if (nk + 1 > 4)
-				return es_fail(es, CBGPU_ERR_UNSUPPORTED, "too many sort keys for the device top-N");
-			keycols[nk] = colstart[att - 1]; desc[nk] = ls->keys[k].descending; uns[nk] = 0; nk++;
-		}
-	}
+	TRY(sort_key_columns(es, shape, nshape, 0, ls->keys, ls->nkeys, keycols, desc, uns, &nk));
 	if (ls->limit < 0)
 		return es_fail(es, CBGPU_ERR_UNSUPPORTED, "Sort without LIMIT is not on the GPU path (nodeSort.c stays on the CPU)");
 	if (ls->limit > 0)
@@ -2878,8 +2948,10 @@ node_result(CbPlanState *ps)
 		PExpr		shape[MAX_OUT];
 		int			nshape;
 
+		const uint32_t *sel = NULL;
+
 		TRY(node_open(ps, &s));
-		if (stream_is_plain(s, &rel))
+		if (stream_is_plain(s, &rel, &sel))
 		{
 			/* already a relation with exactly these columns?  (Motion receive buffers, agg relations) */
 			int			exact = 1,
@@ -2903,8 +2975,25 @@ node_result(CbPlanState *ps)
 					c++;
 				}
 			}
-			if (exact && c == cbgpu_rel_ncols(rel))
+			if (exact && c == cbgpu_rel_ncols(rel) && !sel)
 				return rel_to_result(es, rel, shape, s->nout, NULL, 0, &p->rs);
+			if (exact && c == cbgpu_rel_ncols(rel))
+			{
+				/* the rows in the stream's order (a MATERIALIZE sink appends in whatever order its warps finish) */
+				int32_t		types[CBP_MAX_OUT],
+							dscales[CBP_MAX_OUT];
+				cbgpu_rel  *ordered;
+
+				for (int k = 0; k < c; k++)
+				{
+					types[k] = cbgpu_rel_col_type(rel, k);
+					dscales[k] = cbgpu_rel_col_dscale(rel, k);
+				}
+				GPU(es, cbgpu_rel_create(es->es_ctx, s->pipe.nrows, c, types, dscales, &ordered));
+				p->owned.rels[p->owned.nrels++] = ordered;
+				GPU(es, cbgpu_rel_take_rows(ordered, rel, sel, s->pipe.nrows));
+				return rel_to_result(es, ordered, shape, s->nout, NULL, 0, &p->rs);
+			}
 		}
 		TRY(stream_materialize(es, ps, s, &p->owned, &rel, shape, &nshape));
 		return rel_to_result(es, rel, shape, nshape, NULL, 0, &p->rs);

@@ -444,6 +444,9 @@ struct ProbeParams
 	const uint32_t *sel;
 	int64_t		n;
 	int32_t		left;			/* LEFT join: an outer row without a partner yields one pair (row, 0xFFFFFFFF)  */
+	uint8_t    *matched;		/* RIGHT / FULL join: [inner rows] set to 1 for every build row that found a partner
+								 * (HeapTupleHeaderSetMatch, nodeHashjoin.c:560); NULL otherwise */
+	int64_t		ninner;
 	unsigned long long *counts;	/* [n + 1] match counts, then their exclusive scan                    */
 	uint32_t   *out_outer;
 	uint32_t   *out_inner;
@@ -509,6 +512,8 @@ k_ht_probe_pairs(ProbeParams p)
 							p.out_outer[base + cnt] = row;
 							p.out_inner[base + cnt] = irow;
 						}
+						else if (p.matched)
+							p.matched[irow] = 1;
 						cnt++;
 					}
 				}
@@ -586,30 +591,68 @@ k_exclusive_scan_u64(unsigned long long *a, int64_t n)
 		a[n] = carry;
 }
 
+/* RIGHT / FULL join: the build rows no probe row matched, each as a pair (0xFFFFFFFF, row) behind the matches
+ * (ExecScanHashTableForUnmatched, nodeHash.c:2360; HJ_FILL_INNER_TUPLES, nodeHashjoin.c:676-706).  Rows whose key is NULL
+ * were never inserted and never match: they are emitted too (the reference keeps them in the table for this, keep_nulls
+ * nodeHash.c:209). */
+__global__ void
+k_ht_unmatched_count(ProbeParams p)
+{
+	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t		stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; i < p.ninner; i += stride)
+		p.counts[p.n + i] = p.matched[i] ? 0 : 1;
+}
+
+__global__ void
+k_ht_unmatched_write(ProbeParams p)
+{
+	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t		stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; i < p.ninner; i += stride)
+		if (!p.matched[i])
+		{
+			unsigned long long at = p.counts[p.n + i];
+
+			p.out_outer[at] = 0xFFFFFFFFu;
+			p.out_inner[at] = (uint32_t) i;
+		}
+}
+
 static int	ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
-						   const uint32_t *sel, int64_t nsel, int left, cbgpu_pairs *out);
+						   const uint32_t *sel, int64_t nsel, int left, int fill_inner, cbgpu_pairs *out);
+
+extern "C" int
+cbgpu_ht_probe_pairs_outer(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
+						   int32_t fill_outer, int32_t fill_inner, cbgpu_pairs *out)
+{
+	return ht_probe_pairs(ctx, ht, outer, keycols, nkeys, NULL, 0, fill_outer != 0, fill_inner != 0, out);
+}
 
 extern "C" int
 cbgpu_ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
 					 const uint32_t *sel, int64_t nsel, cbgpu_pairs *out)
 {
-	return ht_probe_pairs(ctx, ht, outer, keycols, nkeys, sel, nsel, 0, out);
+	return ht_probe_pairs(ctx, ht, outer, keycols, nkeys, sel, nsel, 0, 0, out);
 }
 
 extern "C" int
 cbgpu_ht_probe_pairs_left(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
 						  cbgpu_pairs *out)
 {
-	return ht_probe_pairs(ctx, ht, outer, keycols, nkeys, NULL, 0, 1, out);
+	return ht_probe_pairs(ctx, ht, outer, keycols, nkeys, NULL, 0, 1, 0, out);
 }
 
 static int
 ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols, int32_t nkeys,
-			   const uint32_t *sel, int64_t nsel, int left, cbgpu_pairs *out)
+			   const uint32_t *sel, int64_t nsel, int left, int fill_inner, cbgpu_pairs *out)
 {
 	ProbeParams p;
 	int64_t		n = sel ? nsel : outer->nrows;
 	unsigned long long total = 0;
+	const int64_t ninner = fill_inner ? ht->inner->nrows : 0;
 
 	memset(out, 0, sizeof(*out));
 	if (nkeys != ht->d.nkeys)
@@ -630,22 +673,43 @@ ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, cons
 	p.sel = sel;
 	p.n = n;
 	p.left = left;
-	if (n == 0)
+	p.ninner = ninner;
+	if (n + ninner == 0)
 		return CBGPU_OK;
-	CB_CUDA(ctx, cudaMallocAsync(&p.counts, (size_t) (n + 1) * sizeof(unsigned long long), ctx->stream));
+	if (fill_inner && ht->d.nbatch > 1)
+		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "RIGHT / FULL join over a multi-batch table is not implemented%s", "");
+	CB_CUDA(ctx, cudaMallocAsync(&p.counts, (size_t) (n + ninner + 1) * sizeof(unsigned long long), ctx->stream));
+	if (ninner)
+	{
+		CB_CUDA(ctx, cudaMallocAsync(&p.matched, (size_t) ninner, ctx->stream));
+		CB_CUDA(ctx, cudaMemsetAsync(p.matched, 0, (size_t) ninner, ctx->stream));
+	}
 	int			blocks = (int) ((n + 255) / 256);
+	int			iblocks = (int) ((ninner + 255) / 256);
 
 	if (blocks > ctx->sm_count * 8)
 		blocks = ctx->sm_count * 8;
-	k_ht_probe_pairs<false><<<blocks, 256, 0, ctx->stream>>>(p);
-	CB_LAUNCHED(ctx, "k_ht_probe_pairs<count>");
-	k_exclusive_scan_u64<<<1, 1024, 0, ctx->stream>>>(p.counts, n);
+	if (iblocks > ctx->sm_count * 8)
+		iblocks = ctx->sm_count * 8;
+	if (n)
+	{
+		k_ht_probe_pairs<false><<<blocks, 256, 0, ctx->stream>>>(p);
+		CB_LAUNCHED(ctx, "k_ht_probe_pairs<count>");
+	}
+	if (ninner)
+	{
+		k_ht_unmatched_count<<<iblocks, 256, 0, ctx->stream>>>(p);
+		CB_LAUNCHED(ctx, "k_ht_unmatched_count");
+	}
+	k_exclusive_scan_u64<<<1, 1024, 0, ctx->stream>>>(p.counts, n + ninner);
 	CB_LAUNCHED(ctx, "k_exclusive_scan_u64");
-	CB_CUDA(ctx, cudaMemcpyAsync(&total, p.counts + n, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(&total, p.counts + n + ninner, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
 	CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	if (total > 0xFFFFFFF0ull)
 	{
 		cudaFreeAsync(p.counts, ctx->stream);
+		if (p.matched)
+			cudaFreeAsync(p.matched, ctx->stream);
 		return cb_fail(ctx, CBGPU_ERR_UNSUPPORTED, "join result of %s%lld pairs exceeds the GPU path's 32-bit row ids", "", (long long) total);
 	}
 	out->npairs = (int64_t) total;
@@ -655,9 +719,19 @@ ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, cons
 		CB_CUDA(ctx, cudaMalloc(&out->inner_idx, (size_t) total * sizeof(uint32_t)));
 		p.out_outer = out->outer_idx;
 		p.out_inner = out->inner_idx;
-		k_ht_probe_pairs<true><<<blocks, 256, 0, ctx->stream>>>(p);
-		CB_LAUNCHED(ctx, "k_ht_probe_pairs<write>");
+		if (n)
+		{
+			k_ht_probe_pairs<true><<<blocks, 256, 0, ctx->stream>>>(p);
+			CB_LAUNCHED(ctx, "k_ht_probe_pairs<write>");
+		}
+		if (ninner)
+		{
+			k_ht_unmatched_write<<<iblocks, 256, 0, ctx->stream>>>(p);
+			CB_LAUNCHED(ctx, "k_ht_unmatched_write");
+		}
 	}
+	if (p.matched)
+		CB_CUDA(ctx, cudaFreeAsync(p.matched, ctx->stream));
 	CB_CUDA(ctx, cudaFreeAsync(p.counts, ctx->stream));
 	return CBGPU_OK;
 }

@@ -441,16 +441,17 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 					for (int s = 0; s < P.drv_nsrc; s++)
 					{
 						ridx[s] = P.drv_idx[s] ? P.drv_idx[s][base] : (uint32_t) base;
-						/* a LEFT join's unmatched outer row arrives as a pair with no inner row: that source is NULL
-						 * (ExecHashJoinImpl HJ_FILL_OUTER_TUPLE, nodeHashjoin.c:640-660) */
-						if (s > 0 && ridx[s] == 0xFFFFFFFFu)
+						/* a LEFT join's unmatched outer row arrives as a pair with no inner row, a RIGHT / FULL join's
+						 * unmatched build row as a pair with no outer row: that source is NULL (ExecHashJoinImpl
+						 * HJ_FILL_OUTER_TUPLE / HJ_FILL_INNER_TUPLES, nodeHashjoin.c:640-706) */
+						if (P.drv_idx[s] && ridx[s] == 0xFFFFFFFFu)
 						{
 							rnull |= 1u << s;
 							ridx[s] = 0;
 						}
 					}
 				/* AppendOnlyVisimap_IsVisible (backend/access/appendonly/appendonly_visimap.c:198) */
-				if (P.visimap && !((P.visimap[ridx[0] >> 3] >> (ridx[0] & 7)) & 1))
+				if (P.visimap && !(rnull & 1) && !((P.visimap[ridx[0] >> 3] >> (ridx[0] & 7)) & 1))
 					alive = false;
 			}
 		}
@@ -572,10 +573,12 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 
 					maybe = (__ldg(pr.ht.bloom + w) & bits) == bits;
 				}
-				if (alive && !knull && !ht_in_batch(pr.ht.nbatch, pr.ht.batch_shift, pr.ht.batch_id, h))
+				if (alive && pr.ht.nbatch > 1 &&
+					(knull ? pr.ht.batch_id != 0 : !ht_in_batch(pr.ht.nbatch, pr.ht.batch_shift, pr.ht.batch_id, h)))
 				{
 					/* multi-batch join: this row's batch is not resident - its own pass joins (or, for outer / anti joins,
-					 * emits) it; in this pass it does not exist */
+					 * emits) it; in this pass it does not exist.  A NULL key hashes to 0 in the reference (ExecHashGetHashValue
+					 * keep_nulls, nodeHash.c:2171-2190), i.e. belongs to batch 0 */
 					alive = false;
 					maybe = false;
 				}

@@ -55,6 +55,8 @@ struct SmallAggParams
 	int		   *status;
 	int		   *retry;			/* set when a CTA saw more than G distinct groups                     */
 	int		   *audit;			/* set when this variant's arithmetic could have overflowed           */
+	AggSnap    *snap;			/* pinned host: k_small_commit reports the flags and, for small tables, the groups  */
+	int			snap_groups;	/* 1: the table is small enough to be snapshotted                     */
 	/* per-CTA partial results, committed by k_small_commit once no CTA raised retry / audit */
 	unsigned long long *scratch;	/* [grid][G][SA_NSUM + 1][2]                                      */
 	unsigned   *skeys;			/* [grid][G]                                                          */
@@ -432,8 +434,21 @@ k_scan_agg_small(const __grid_constant__ SmallAggParams P)
 __global__ void
 k_small_commit(const __grid_constant__ SmallAggParams P, int G, int nblocks)
 {
+	/* ONE CTA (the host launches <<<1, 256>>>): commit, then report - flags, and for a small table its groups - straight
+	 * into pinned host memory, so the step's fate and its result arrive with one synchronisation */
 	if (*P.retry || *P.audit)
+	{
+		if (threadIdx.x == 0)
+		{
+			P.snap->retry = *P.retry;
+			P.snap->audit = *P.audit;
+			P.snap->ngroups = -1;
+			__threadfence_system();
+		}
 		return;
+	}
+	if (threadIdx.x == 0)
+		P.snap->retry = P.snap->audit = 0;
 	for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nblocks * G; e += gridDim.x * blockDim.x)
 	{
 		unsigned	key = P.skeys[e];
@@ -460,6 +475,15 @@ k_small_commit(const __grid_constant__ SmallAggParams P, int G, int nblocks)
 			if (s >= 0)
 				atomic_add128(P.agg.sum + ((size_t) slot * P.agg.naccs + a) * 2, r[s * 2], r[s * 2 + 1]);
 		}
+	}
+	__syncthreads();
+	if (P.snap_groups)
+		agg_snapshot_block(P.agg, P.snap);
+	else
+	{
+		if (threadIdx.x == 0)
+			P.snap->ngroups = -1;
+		__threadfence_system();
 	}
 }
 
@@ -664,7 +688,6 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 	const int	shape = (P.fcol && P.key0 && P.key1) ? 1 : ((P.fcol && !P.key0 && !P.key1) ? 2 : 0);
 
 	int		   *d_flags;
-	int			h_flags[2] = {0, 0};
 	int64_t		ntiles = (p->nrows + SA_TILE - 1) / SA_TILE;
 	int			blocks = ctx->sm_count;
 	const size_t smem = sizeof(SaStage) * SA_STAGES;
@@ -673,11 +696,32 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 
 	if (blocks > ntiles)
 		blocks = (int) ntiles;
-	CB_CUDA(ctx, cudaMallocAsync(&d_flags, 2 * sizeof(int), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&P.scratch, (size_t) blocks * 8 * (SA_NSUM + 1) * 2 * sizeof(unsigned long long), ctx->stream));
-	CB_CUDA(ctx, cudaMallocAsync(&P.skeys, (size_t) blocks * 8 * sizeof(unsigned), ctx->stream));
+	{
+		/* per-context device scratch, kept between queries: [flags 256 B][per-CTA partial sums][per-CTA keys] */
+		const size_t sbytes = (size_t) blocks * 8 * (SA_NSUM + 1) * 2 * sizeof(unsigned long long);
+		const size_t kbytes = (size_t) blocks * 8 * sizeof(unsigned);
+		const size_t need = 256 + sbytes + ((kbytes + 255) & ~(size_t) 255);
+
+		if (ctx->small_dev_bytes < need)
+		{
+			if (ctx->small_dev)
+			{
+				CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+				CB_CUDA(ctx, cudaFree(ctx->small_dev));
+				ctx->small_dev = NULL;
+				ctx->small_dev_bytes = 0;
+			}
+			CB_CUDA(ctx, cudaMalloc(&ctx->small_dev, need));
+			ctx->small_dev_bytes = need;
+		}
+		d_flags = (int *) ctx->small_dev;
+		P.scratch = (unsigned long long *) ((char *) ctx->small_dev + 256);
+		P.skeys = (unsigned *) ((char *) ctx->small_dev + 256 + sbytes);
+	}
 	P.retry = d_flags;
 	P.audit = d_flags + 1;
+	P.snap = ctx->agg_snap;
+	P.snap_groups = s->agg->capacity <= AGG_SNAP_MAXCAP;
 	/* ladder: (4 groups, narrow) -> wider arithmetic on a failed audit, 8 groups when a CTA saw more
 	 * than 4 keys -> the generic kernel.  A failed attempt commits nothing. */
 	for (;;)
@@ -725,10 +769,15 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 		cb_klog_end(ctx, kl);
 		CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
 		ctx->kernel_timed = true;
+		ctx->agg_snap->ngroups = -1;
+		ctx->agg_snap->retry = ctx->agg_snap->audit = 0;
 		k_small_commit<<<1, 256, 0, ctx->stream>>>(P, G, blocks);
 		CB_LAUNCHED(ctx, "k_small_commit");
-		CB_CUDA(ctx, cudaMemcpyAsync(h_flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		CB_CUDA(ctx, CB_STATUS_RIDE(ctx));
 		CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		CB_STATUS_FETCHED(ctx);
+		const int	h_flags[2] = {ctx->agg_snap->retry, ctx->agg_snap->audit};
+
 		if (h_flags[1])
 		{
 			if (!narrow || G == 8)
@@ -744,11 +793,10 @@ try_small_agg(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *handl
 			continue;
 		}
 		*handled = true;
+		/* the commit kernel brought the (small) table's groups along: count and read-back are answered from here */
+		cb_agg_adopt_snapshot((cbgpu_aggtable *) s->agg, ctx->agg_snap);
 		break;
 	}
-	CB_CUDA(ctx, cudaFreeAsync(d_flags, ctx->stream));
-	CB_CUDA(ctx, cudaFreeAsync(P.scratch, ctx->stream));
-	CB_CUDA(ctx, cudaFreeAsync(P.skeys, ctx->stream));
 	return CBGPU_OK;
 }
 

@@ -79,13 +79,14 @@ class CbAgg(C.Structure):
                 ("grpColIdx", C.POINTER(C.c_int32)), ("numGroups", C.c_int64), ("streaming", C.c_bool)]
 
 
-class CbMotion(C.Structure):
-    _fields_ = [("plan", CbPlan), ("motionType", C.c_int), ("motionID", C.c_int32), ("nhashExprs", C.c_int32),
-                ("hashExprs", C.POINTER(C.POINTER(CbExpr))), ("numHashSegments", C.c_int32)]
-
-
 class CbSortKey(C.Structure):
     _fields_ = [("attno", C.c_int32), ("descending", C.c_bool)]
+
+
+class CbMotion(C.Structure):
+    _fields_ = [("plan", CbPlan), ("motionType", C.c_int), ("motionID", C.c_int32), ("nhashExprs", C.c_int32),
+                ("hashExprs", C.POINTER(C.POINTER(CbExpr))), ("numHashSegments", C.c_int32), ("nsortkeys", C.c_int32),
+                ("sortkeys", C.POINTER(CbSortKey))]
 
 
 class CbLimitSort(C.Structure):
@@ -274,7 +275,8 @@ def Agg(child, strategy, split, grp_col_idx, targets, num_groups=0, quals=(), st
     return n
 
 
-def Motion(child, motion_type, hash_exprs=(), num_hash_segments=0, motion_id=None):
+def Motion(child, motion_type, hash_exprs=(), num_hash_segments=0, motion_id=None, sort_keys=()):
+    """sort_keys: [(attno, descending)] - a Gather whose receiver merges the senders' sorted streams (Motion.sendSorted)"""
     n = CbMotion()
     tl = [OuterVar(i + 1, child.plan.targetlist[i].expr.contents.restype, child.plan.targetlist[i].expr.contents.dscale)
           for i in range(child.plan.ntargets)]
@@ -286,7 +288,13 @@ def Motion(child, motion_type, hash_exprs=(), num_hash_segments=0, motion_id=Non
     n.nhashExprs = len(hash_exprs)
     n.hashExprs = ha
     n.numHashSegments = num_hash_segments
-    n._keep += [child, ha] + list(hash_exprs)
+    sk = (CbSortKey * max(len(sort_keys), 1))()
+    for i, (attno, desc) in enumerate(sort_keys):
+        sk[i].attno = attno
+        sk[i].descending = bool(desc)
+    n.nsortkeys = len(sort_keys)
+    n.sortkeys = C.cast(sk, C.POINTER(CbSortKey))
+    n._keep += [child, ha, sk] + list(hash_exprs)
     return n
 
 

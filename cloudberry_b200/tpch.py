@@ -279,7 +279,7 @@ def q1_plan(nsegs=1, cutoff=Q1_CUTOFF):
     return P.Motion(final, P.MOTIONTYPE_GATHER)
 
 
-def q3_plan(segment_code, nsegs=1, cutoff=None, limit=10, customer_replicated=True):
+def q3_plan(segment_code, nsegs=1, cutoff=None, limit=10, customer_replicated=True, merge_gather=False):
     """TPC-H Q3 (rpt_tpch.source:458-480).
     Limit/Sort <- [Gather] <- HashAggregate(l_orderkey, o_orderdate, o_shippriority)
        <- Hash Join (l_orderkey = o_orderkey)
@@ -321,7 +321,7 @@ def q3_plan(segment_code, nsegs=1, cutoff=None, limit=10, customer_replicated=Tr
         return top
     # each segment keeps its local top-N, the gather receiver merges (Limit <- Gather Motion (merge)
     # <- Limit <- Sort in the reference's plan)
-    g = P.Motion(top, P.MOTIONTYPE_GATHER)
+    g = P.Motion(top, P.MOTIONTYPE_GATHER, sort_keys=[(2, True), (3, False)] if merge_gather else ())
     return P.LimitSort(g, [(2, True), (3, False)], limit)
 
 

@@ -183,6 +183,7 @@ typedef enum CbMotionType
 	CB_MOTIONTYPE_GATHER = 0, CB_MOTIONTYPE_GATHER_SINGLE, CB_MOTIONTYPE_HASH, CB_MOTIONTYPE_BROADCAST
 } CbMotionType;
 
+typedef struct CbSortKey { int32_t attno; bool descending; } CbSortKey;
 typedef struct CbMotion
 {
 	CbPlan		plan;
@@ -191,6 +192,11 @@ typedef struct CbMotion
 	int32_t		nhashExprs;
 	CbExpr	  **hashExprs;		/* over OUTER_VAR                                                     */
 	int32_t		numHashSegments;
+	/* sendSorted (plannodes.h Motion.sendSorted / numSortCols / sortColIdx): every sender's stream is ordered by these
+	 * keys and the receiver merges the streams (execMotionSortedReceiver, nodeMotion.c:433; CdbMergeComparator :1010).
+	 * Gather motions only; 0 keys = arrival order */
+	int32_t		nsortkeys;
+	CbSortKey  *sortkeys;
 } CbMotion;
 
 /*
@@ -199,7 +205,6 @@ typedef struct CbMotion
  * (SURVEY.md 8a row a8).  CbLimitSort = Limit(Sort(child)) with a bounded heap, as
  * tuplesort's bounded mode would run it.
  */
-typedef struct CbSortKey { int32_t attno; bool descending; } CbSortKey;
 typedef struct CbLimitSort
 {
 	CbPlan		plan;

@@ -123,6 +123,9 @@ int			cbgpu_rel_read_visimap(cbgpu_rel *rel, uint8_t *bits);
 int			cbgpu_rel_set_dict_hash(cbgpu_rel *rel, int32_t col, const uint32_t *hashes, int32_t n);
 /* shrink the logical row count (relations allocated at an upper bound, e.g. Motion receive) */
 int			cbgpu_rel_set_nrows(cbgpu_rel *rel, int64_t nrows);
+/* dst rows [0, n) = src rows dev_idx[0..n) (a DEVICE index list), all columns and NULL maps: an ordered gather (the merged
+ * order of a sorted Motion) */
+int			cbgpu_rel_take_rows(cbgpu_rel *dst, cbgpu_rel *src, const uint32_t *dev_idx, int64_t n);
 /* n rows (host_idx[0..n), or the first n when host_idx is NULL) of EVERY column in one round trip: values widened
  * to int64 (float8: raw bits), row-major out[r * ncols + c], outnull likewise.  For small result sets. */
 int			cbgpu_rel_read_rows(cbgpu_rel *rel, const uint32_t *host_idx, int64_t n, int64_t *out, uint8_t *outnull);
@@ -306,6 +309,11 @@ int			cbgpu_ht_probe_pairs(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel 
  * by the pairs reads that source as NULL: HJ_FILL_OUTER_TUPLE, nodeHashjoin.c:640-660) */
 int			cbgpu_ht_probe_pairs_left(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols,
 									  int32_t nkeys, cbgpu_pairs *out);
+/* all outer-join flavours of the pair probe: fill_outer adds (row, 0xFFFFFFFF) for probe rows without a partner (LEFT /
+ * FULL), fill_inner adds (0xFFFFFFFF, row) for build rows no probe row matched, NULL-keyed build rows included (RIGHT /
+ * FULL: ExecScanHashTableForUnmatched nodeHash.c:2360, HJ_FILL_INNER_TUPLES nodeHashjoin.c:676-706) */
+int			cbgpu_ht_probe_pairs_outer(cbgpu_ctx *ctx, const cbgpu_hashtable *ht, cbgpu_rel *outer, const int32_t *keycols,
+									   int32_t nkeys, int32_t fill_outer, int32_t fill_inner, cbgpu_pairs *out);
 void		cbgpu_pairs_free(cbgpu_pairs *p);
 int			cbgpu_read_u32(cbgpu_ctx *ctx, const uint32_t *dev, int64_t n, uint32_t *host);
 /* small device scratch (sink row counters, index vectors): zero-filled allocation, read-back, free */
@@ -356,6 +364,13 @@ int			cbgpu_agg_to_rel(cbgpu_aggtable *t, const int32_t *keytypes, cbgpu_rel **o
 int			cbgpu_topn(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const int32_t *descending,
 					   const int32_t *unsigned_cmp, int32_t nkeys, int64_t limit, uint32_t *host_idx,
 					   int64_t *nout);
+/* Merge receive of a sorted Gather Motion (Motion.sendSorted; execMotionSortedReceiver nodeMotion.c:433, CdbMergeComparator
+ * :1010): `rel` holds the senders' sorted streams one after another; *order_dev (device, cbgpu_dev_free; NULL when the
+ * arrival order already is the order) lists its rows in merged order - equal keys: the earlier sender first.  NULLs sort
+ * last ascending, first descending.  More than max_runs sorted runs means a sender broke the order: CBGPU_ERR_INVALID. */
+int			cbgpu_merge_sorted_runs(cbgpu_ctx *ctx, cbgpu_rel *rel, const int32_t *keycols, const int32_t *descending,
+									const int32_t *unsigned_cmp, int32_t nkeys, int32_t max_runs, uint32_t **order_dev,
+									int32_t *nruns_out);
 
 /* ------------------------------------------------------------------------------------------
  * interconnect between GPU-segments, one process per GPU (backend/cdb/motion/cdbmotion.c:425,549 and

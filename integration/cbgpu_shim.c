@@ -574,8 +574,30 @@ translate_plan(Plan *p, EState *estate, List **rels)
 				Motion	   *m = (Motion *) p;
 				CbMotion   *c = (CbMotion *) palloc0(sizeof(CbMotion));
 
-				if (m->sendSorted || !fill_plan(&c->plan, T_CbMotion, p))
+				if (!fill_plan(&c->plan, T_CbMotion, p))
 					return NULL;
+				if (m->sendSorted)
+				{
+					/* merge receive (execMotionSortedReceiver, nodeMotion.c:433): the keys as (column, descending); only the
+					 * default NULL placement (last ascending, first descending) is what the device comparator implements */
+					if (m->motionType != MOTIONTYPE_GATHER && m->motionType != MOTIONTYPE_GATHER_SINGLE)
+						return NULL;
+					c->nsortkeys = m->numSortCols;
+					c->sortkeys = (CbSortKey *) palloc0(sizeof(CbSortKey) * Max(m->numSortCols, 1));
+					for (int i = 0; i < m->numSortCols; i++)
+					{
+						Oid			opfamily,
+									opcintype;
+						int16		strategy;
+
+						if (!get_ordering_op_properties(m->sortOperators[i], &opfamily, &opcintype, &strategy))
+							return NULL;
+						c->sortkeys[i].attno = m->sortColIdx[i];
+						c->sortkeys[i].descending = strategy == BTGreaterStrategyNumber;
+						if (m->nullsFirst[i] != c->sortkeys[i].descending)
+							return NULL;
+					}
+				}
 				switch (m->motionType)
 				{
 					case MOTIONTYPE_GATHER: c->motionType = CB_MOTIONTYPE_GATHER; break;

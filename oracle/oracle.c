@@ -556,6 +556,7 @@ typedef struct HJTuple
 	int64_t		next;			/* index of next tuple in bucket chain, -1 = end               */
 	uint32_t	hashvalue;
 	uint8_t		matched;
+	uint8_t		nullkey;		/* kept only to be returned unmatched (keep_nulls, nodeHash.c:209)  */
 } HJTuple;
 
 typedef struct HJPriv
@@ -572,6 +573,8 @@ typedef struct HJPriv
 	int			outer_matched;
 	int			need_outer;
 	OD		   *nullinner;
+	OD		   *nullouter;
+	int64_t		fill_cur;		/* HJ_FILL_INNER_TUPLES cursor, -1 = the probe phase is still on  */
 } HJPriv;
 
 static int
@@ -612,8 +615,12 @@ hj_build(PS *ps)
 	int64_t		i,
 				n;
 	uint32_t   *hv = NULL;
+	uint8_t    *nk = NULL;
 	int64_t		hvcap = 0;
+	const int	fill_inner = ((const CbHashJoin *) ps->plan)->jointype == CB_JOIN_RIGHT ||
+		((const CbHashJoin *) ps->plan)->jointype == CB_JOIN_FULL;
 
+	hp->fill_cur = -1;
 	hp->inner.ncols = child->ncols;
 	/* MultiExecPrivateHash (nodeHash.c:167-256) */
 	while ((row = child->next(child)) != NULL)
@@ -621,14 +628,20 @@ hj_build(PS *ps)
 		ECtx		c = {row, NULL, NULL, 0, ps->ex};
 		uint32_t	h;
 
-		if (!hash_keys(ps->ex, hplan->hashkeys, hplan->nhashkeys, &c, &h, NULL))
-			continue;			/* NULL key cannot match (inner/left/semi/anti all drop it)    */
+		int			keyed = hash_keys(ps->ex, hplan->hashkeys, hplan->nhashkeys, &c, &h, NULL);
+
+		/* NULL key cannot match (inner/left/semi/anti all drop it); HJ_FILL_INNER joins keep the tuple so that it comes
+		 * back NULL-extended (ExecHashGetHashValue keep_nulls, nodeHash.c:2171-2190) */
+		if (!keyed && !fill_inner)
+			continue;
 		if (hp->inner.nrows == hvcap)
 		{
 			hvcap = hvcap ? hvcap * 2 : 1024;
 			hv = realloc(hv, (size_t) hvcap * sizeof(uint32_t));
+			nk = realloc(nk, (size_t) hvcap);
 		}
 		hv[hp->inner.nrows] = h;
+		nk[hp->inner.nrows] = !keyed;
 		rowbuf_push(&hp->inner, row);
 	}
 	n = hp->inner.nrows;
@@ -647,10 +660,18 @@ hj_build(PS *ps)
 
 		hp->tup[i].hashvalue = hv[i];
 		hp->tup[i].matched = 0;
+		hp->tup[i].nullkey = nk[i];
 		hp->tup[i].next = hp->buckets[b];
 		hp->buckets[b] = i;
 	}
 	free(hv);
+	free(nk);
+	hp->nullouter = calloc((size_t) (ps->left->ncols ? ps->left->ncols : 1), sizeof(OD));
+	for (i = 0; i < ps->left->ncols; i++)
+	{
+		hp->nullouter[i].isnull = 1;
+		hp->nullouter[i].type = (uint8_t) ps->left->plan->targetlist[i].expr->restype;
+	}
 	hp->nullinner = calloc((size_t) (child->ncols ? child->ncols : 1), sizeof(OD));
 	for (i = 0; i < child->ncols; i++)
 	{
@@ -681,6 +702,23 @@ hashjoin_next(PS *ps)
 	{
 		if (g_failed)
 			return NULL;
+		if (hp->fill_cur >= 0)
+		{
+			/* HJ_FILL_INNER_TUPLES (nodeHashjoin.c:676-706): ExecScanHashTableForUnmatched (nodeHash.c:2360) */
+			while (hp->fill_cur < hp->inner.nrows)
+			{
+				int64_t		t = hp->fill_cur++;
+				ECtx		cj = {hp->nullouter, hp->inner.rows + t * hp->inner.ncols, NULL, 0, ps->ex};
+
+				if (hp->tup[t].matched)
+					continue;
+				if (!quals_pass(ps->plan->qual, ps->plan->nquals, &cj))
+					continue;
+				project(ps, &cj);
+				return ps->slot;
+			}
+			return NULL;
+		}
 		if (hp->need_outer)
 		{
 			/* HJ_NEED_NEW_OUTER (nodeHashjoin.c:476) */
@@ -689,7 +727,14 @@ hashjoin_next(PS *ps)
 
 			hp->outer = ps->left->next(ps->left);
 			if (!hp->outer)
+			{
+				if (hj->jointype == CB_JOIN_RIGHT || hj->jointype == CB_JOIN_FULL)
+				{
+					hp->fill_cur = 0;
+					continue;
+				}
 				return NULL;
+			}
 			c.outer = hp->outer;
 			ok = hash_keys(ps->ex, hj->hashkeys, hj->nhashkeys, &c, &hp->curhash, NULL);
 			hp->outer_matched = 0;
@@ -708,7 +753,7 @@ hashjoin_next(PS *ps)
 						eq = 1;
 
 			hp->cur = hp->tup[t].next;
-			if (hp->tup[t].hashvalue != hp->curhash)
+			if (hp->tup[t].hashvalue != hp->curhash || hp->tup[t].nullkey)
 				continue;
 			for (k = 0; k < hj->nhashkeys && eq; k++)
 			{
@@ -721,6 +766,7 @@ hashjoin_next(PS *ps)
 			if (!quals_pass(hj->joinqual, hj->njoinquals, &cj))
 				continue;
 			hp->outer_matched = 1;
+			hp->tup[t].matched = 1;	/* HeapTupleHeaderSetMatch (nodeHashjoin.c:560) */
 			if (hj->jointype == CB_JOIN_ANTI)
 			{
 				hp->cur = -1;	/* one match is enough to reject (nodeHashjoin.c:610) */
@@ -735,7 +781,7 @@ hashjoin_next(PS *ps)
 		}
 		/* HJ_FILL_OUTER_TUPLE (nodeHashjoin.c:663) */
 		hp->need_outer = 1;
-		if (!hp->outer_matched && (hj->jointype == CB_JOIN_LEFT || hj->jointype == CB_JOIN_ANTI))
+		if (!hp->outer_matched && (hj->jointype == CB_JOIN_LEFT || hj->jointype == CB_JOIN_FULL || hj->jointype == CB_JOIN_ANTI))
 		{
 			ECtx		cj = {hp->outer, hp->nullinner, NULL, 0, ps->ex};
 
@@ -1121,21 +1167,20 @@ motion_recv_next(PS *ps)
 	return bp->buf->rows + (bp->row++) * bp->buf->ncols;
 }
 
-static const CbLimitSort *g_sort_plan;	/* qsort has no context argument; sorts are serialised */
+static const CbSortKey *g_sort_keys;	/* qsort has no context argument; sorts are serialised */
+static int	g_sort_nkeys;
 static pthread_mutex_t g_sort_mu = PTHREAD_MUTEX_INITIALIZER;
-static int	g_sort_ncols;
 
+/* the ordering of two rows under a sort key list (tuplesort's comparetup_heap; CdbMergeComparator nodeMotion.c:1010) */
 static int
-sort_cmp(const void *pa, const void *pb)
+rows_cmp(const CbSortKey *keys, int nkeys, const OD *a, const OD *b)
 {
-	const OD   *a = pa,
-			   *b = pb;
 	int			k;
 
-	for (k = 0; k < g_sort_plan->nkeys; k++)
+	for (k = 0; k < nkeys; k++)
 	{
-		const OD   *x = &a[g_sort_plan->keys[k].attno - 1];
-		const OD   *y = &b[g_sort_plan->keys[k].attno - 1];
+		const OD   *x = &a[keys[k].attno - 1];
+		const OD   *y = &b[keys[k].attno - 1];
 		int			c;
 
 		/* NULLS LAST for ASC, NULLS FIRST for DESC (PostgreSQL defaults) */
@@ -1143,12 +1188,18 @@ sort_cmp(const void *pa, const void *pb)
 			c = (x->isnull && y->isnull) ? 0 : (x->isnull ? 1 : -1);
 		else
 			c = od_cmp(*x, *y);
-		if (g_sort_plan->keys[k].descending)
+		if (keys[k].descending)
 			c = -c;
 		if (c)
 			return c;
 	}
 	return 0;
+}
+
+static int
+sort_cmp(const void *pa, const void *pb)
+{
+	return rows_cmp(g_sort_keys, g_sort_nkeys, pa, pb);
 }
 
 static OD  *
@@ -1165,8 +1216,8 @@ limitsort_next(PS *ps)
 		while ((row = ps->left->next(ps->left)) != NULL)
 			rowbuf_push(&bp->own, row);
 		pthread_mutex_lock(&g_sort_mu);
-		g_sort_plan = ls;
-		g_sort_ncols = bp->own.ncols;
+		g_sort_keys = ls->keys;
+		g_sort_nkeys = ls->nkeys;
 		if (bp->own.nrows > 1)
 			qsort(bp->own.rows, (size_t) bp->own.nrows, sizeof(OD) * (size_t) bp->own.ncols, sort_cmp);
 		pthread_mutex_unlock(&g_sort_mu);
@@ -1420,6 +1471,33 @@ materialize_motions(Exec *ex, const CbPlan *p)
 		for (d = 0; d < ex->nsegs; d++)
 		{
 			ex->recv[slot][d].ncols = ncols;
+			if (m->nsortkeys > 0)
+			{
+				/* execMotionSortedReceiver (nodeMotion.c:433): the senders' streams are sorted; return the smallest head
+				 * until all are drained.  Equal heads: the lower sender first (the reference's binary heap leaves the
+				 * order of equal keys to its internals; this is one of the orders it can produce) */
+				int64_t    *at = calloc((size_t) ex->nsegs, sizeof(int64_t));
+
+				for (;;)
+				{
+					int			best = -1;
+
+					for (s = 0; s < ex->nsegs; s++)
+					{
+						if (at[s] >= jobs[s].out[d].nrows)
+							continue;
+						if (best < 0 || rows_cmp(m->sortkeys, m->nsortkeys, jobs[s].out[d].rows + at[s] * ncols,
+												 jobs[best].out[d].rows + at[best] * ncols) < 0)
+							best = s;
+					}
+					if (best < 0)
+						break;
+					rowbuf_push(&ex->recv[slot][d], jobs[best].out[d].rows + at[best] * ncols);
+					at[best]++;
+				}
+				free(at);
+				continue;
+			}
 			for (s = 0; s < ex->nsegs; s++)
 			{
 				int64_t		r;

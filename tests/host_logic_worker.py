@@ -64,7 +64,9 @@ def main():
         o = rels[1]
         so = P.SeqScan(2, [("o_orderkey", P.Var(2, o.attno("o_orderkey"), P.INT8))])
         h = P.Hash(so, [P.out_var(so, 1)])
-        j = P.HashJoin(P.JOIN_RIGHT, sc, h, [P.out_var(sc, 3)], [("l_quantity", P.out_var(sc, 2))])
+        # RIGHT joins run (pairs with a missing side); extra join quals on an outer join are still refused
+        j = P.HashJoin(P.JOIN_RIGHT, sc, h, [P.out_var(sc, 3)], [("l_quantity", P.out_var(sc, 2))],
+                       joinquals=[P.OpExpr(P.OP_GT, P.out_var(sc, 3), P.Const(P.INT8, 5))])
         return P.Agg(j, P.AGG_PLAIN, P.AGGSPLIT_SIMPLE, [], [("n", P.Aggref(P.AGG_COUNT_STAR))])
 
     def numeric_join_key():

@@ -19,9 +19,9 @@ def ctx():
     c.close()
 
 
-@pytest.mark.parametrize("mem_kb", [64, 1024])
+@pytest.mark.parametrize("mem_kb", [16, 1024])
 def test_q3_q5_with_a_tiny_operator_memory(ctx, oracle, mem_kb):
-    """SF0.05: the orders / customer build sides and Q3's ~5.7 K groups exceed a 64 KB budget many times over -> batches and
+    """SF0.05: the orders / customer build sides and Q3's ~570 groups exceed a 16 KB budget many times over -> batches and
     partitions; the rows are the oracle's all the same"""
     rels_o = tpch.gen_tables(0.05, oracle.hashbpchar)
     rels_p = tpch.gen_tables(0.05, capi.hashbpchar)
@@ -36,11 +36,11 @@ def test_q3_q5_with_a_tiny_operator_memory(ctx, oracle, mem_kb):
         assert fmt(got.rows) == fmt(want.rows) == fmt(ex1.run(plan).rows)
         nb = [v["hashjoin_nbatch"] for v in got.instrument.values()]
         npart = [v["agg_npartitions"] for v in got.instrument.values()]
-        if mem_kb == 64:
+        if mem_kb == 16:
             assert max(nb) > 1, nb                      # some build side was split
             if plan is q3:
                 assert max(npart) > 1, npart            # and the aggregate ran in partitions
-    assert ex.estate.contents.es_hashjoin_batches_run > 0
+    assert (ex.estate.contents.es_hashjoin_batches_run > 0) == (mem_kb == 16)
     ex.close()
     ex1.close()
     for d in dev:
@@ -51,8 +51,8 @@ def test_q3_q5_with_a_tiny_operator_memory(ctx, oracle, mem_kb):
 def test_multi_batch_join_types(ctx, oracle, jointype):
     """every N:1 join type through a build side split into batches (unmatched LEFT / ANTI rows must come out exactly once: in
     their own batch's pass)"""
-    fo, fp = make(fact, 30011, seed=11, null_frac=0.05)
-    do, dp = make(dim, 4000, seed=12)
+    fo, fp = make(fact, 30011, seed=11, null_frac=0.05, kmax=6000)
+    do, dp = make(dim, 4000, seed=12, kmax=6000)
     sf = scan(1, fo, ["k", "amt", "g"])
     sd = scan(2, do, ["dk", "w", "c"])
     h = P.Hash(sd, [P.out_var(sd, 1)])
@@ -129,3 +129,34 @@ def test_having(ctx, oracle, generic):
     ex.close()
     for d in dev:
         d.free()
+
+
+def _outer_join_plan(jointype, fo, do):
+    sf = scan(1, fo, ["k", "v", "amt", "g"])
+    sd = scan(2, do, ["dk", "w", "c"])
+    h = P.Hash(sd, [P.out_var(sd, 1)])
+    return P.HashJoin(jointype, sf, h, [P.out_var(sf, 1)],
+                      [("k", P.out_var(sf, 1)), ("g", P.out_var(sf, 4)), ("amt", P.out_var(sf, 3)), ("dk", P.InnerVar(1, P.INT4)),
+                       ("w", P.InnerVar(2, P.INT8)), ("c", P.InnerVar(3, P.DICT8))])
+
+
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("jointype", [P.JOIN_RIGHT, P.JOIN_FULL])
+@pytest.mark.parametrize("nf,nd,dup", [(0, 40, 1), (5000, 0, 1), (300, 40, 1), (20011, 90, 3), (40, 45, 1)])
+def test_right_and_full_joins(ctx, oracle, jointype, nf, nd, dup, generic):
+    """RIGHT / FULL hash joins (HJ_FILL_INNER_TUPLES, nodeHashjoin.c:676-706): build rows nobody matched - NULL-keyed ones
+    included - come back once, NULL-extended on the probe side; FULL also keeps the unmatched probe rows.  Both the joined rows
+    themselves and an aggregate over them."""
+    fo, fp = make(fact, nf, seed=31, null_frac=0.1, kmax=60)
+    do, dp = make(dim, nd, seed=32, null_frac=0.1, dup=dup, kmax=60)
+    j = _outer_join_plan(jointype, fo, do)
+    got, want = run_both(ctx, oracle, j, [fo, do], [fp, dp], generic)
+    assert canon(got) == canon(want)
+    if nd > 1 and nf > 0:
+        assert any(r[0] is None and r[2] is None for r in want)         # unmatched build rows exist
+    if jointype == P.JOIN_FULL and nf:
+        assert any(r[4] is None for r in want)                          # and unmatched probe rows
+    names = ["k", "g", "amt", "dk", "w", "c"]
+    plan = agg_over(j, names, ["g", "c"], [("s", P.AGG_SUM, "amt"), ("n", P.AGG_COUNT_STAR, None), ("ck", P.AGG_COUNT, "k"), ("sw", P.AGG_SUM, "w")])
+    got, want = run_both(ctx, oracle, plan, [fo, do], [fp, dp], generic)
+    assert canon(got) == canon(want)

@@ -45,7 +45,7 @@ def _check(out):
         assert ran[name]["launches"] > 0
     assert ran["q3_3seg"]["launches"] > ran["q3"]["launches"]      # three segment executors and their Motions
     want = {"sorted_agg": (UNSUPPORTED, "hashed / plain"),
-            "sort_without_limit": (UNSUPPORTED, "Sort without LIMIT"), "right_join": (UNSUPPORTED, "join type"),
+            "sort_without_limit": (UNSUPPORTED, "Sort without LIMIT"), "right_join": (UNSUPPORTED, "extra join quals"),
             "numeric_join_key": (UNSUPPORTED, "hash_numeric"), "bad_scanrelid": (INVALID, "scanrelid 9")}
     for name, (code, frag) in want.items():
         assert refused[name]["error"] is not None, name
