@@ -288,6 +288,7 @@ def gpu():
             "cbgpu_aocs_apply_visimap": (C.c_int, [vp, vp, i64, i32, vp, i32, vp, i64, C.POINTER(i64)]),
             "cbgpu_rel_set_dict_hash": (C.c_int, [vp, i32, vp, i32]),
             "cbgpu_rel_set_nrows": (C.c_int, [vp, i64]),
+            "cbgpu_rel_copy_rows": (C.c_int, [vp, i64, vp, i64, i64]),
             "cbgpu_rel_col_devptr": (vp, [vp, i32]),
             "cbgpu_rel_nbytes": (C.c_size_t, [vp]),
             "cbgpu_ht_build": (C.c_int, [vp, vp, C.POINTER(i32), i32, C.POINTER(vp)]),

@@ -105,6 +105,7 @@ struct cbgpu_rel
 	int32_t		dict_n[CB_MAX_COLS_REL];
 	uint8_t	   *visimap;
 	bool		owns[CB_MAX_COLS_REL];
+	void	   *slab;			/* small relations: the one allocation all columns live in (owns[] = false) */
 };
 
 /* agg table, device view (struct of arrays; open addressing, linear probing) */

@@ -385,6 +385,9 @@ cbgpu_rel_create(cbgpu_ctx *ctx, int64_t nrows, int32_t ncols, const int32_t *ty
 	r->capacity = nrows;
 	r->ncols = ncols;
 	CB_CUDA(ctx, cudaSetDevice(ctx->device));
+	size_t		total = 0;
+	size_t		colbytes[CB_MAX_COLS_REL];
+
 	for (int i = 0; i < ncols; i++)
 	{
 		size_t		bytes = (size_t) (nrows ? nrows : 1) * cb_type_w(types[i]);
@@ -397,10 +400,30 @@ cbgpu_rel_create(cbgpu_ctx *ctx, int64_t nrows, int32_t ncols, const int32_t *ty
 		r->types[i] = types[i];
 		r->dscales[i] = dscales ? dscales[i] : 0;
 		/* pad so 16-byte vector loads and TMA bulk copies may read a whole final vector */
-		bytes = (bytes + 255) & ~(size_t) 255;
-		CB_CUDA(ctx, cudaMallocAsync(&r->data[i], bytes, ctx->stream));
-		r->owns[i] = true;
+		colbytes[i] = (bytes + 255) & ~(size_t) 255;
+		total += colbytes[i];
 	}
+	if (ncols > 1 && total <= ((size_t) 64 << 20))
+	{
+		/* intermediate results (group relations, Motion buffers of a few rows) are created per query with dozens of
+		 * columns: one pool call instead of one per column */
+		char	   *base;
+
+		CB_CUDA(ctx, cudaMallocAsync(&base, total, ctx->stream));
+		r->slab = base;
+		for (int i = 0; i < ncols; i++)
+		{
+			r->data[i] = base;
+			r->owns[i] = false;
+			base += colbytes[i];
+		}
+	}
+	else
+		for (int i = 0; i < ncols; i++)
+		{
+			CB_CUDA(ctx, cudaMallocAsync(&r->data[i], colbytes[i], ctx->stream));
+			r->owns[i] = true;
+		}
 	*out = r;
 	return CBGPU_OK;
 }
@@ -424,6 +447,8 @@ cbgpu_rel_free(cbgpu_rel *rel)
 	}
 	if (rel->visimap)
 		cudaFreeAsync(rel->visimap, rel->ctx->stream);
+	if (rel->slab)
+		cudaFreeAsync(rel->slab, rel->ctx->stream);
 	free(rel);
 }
 

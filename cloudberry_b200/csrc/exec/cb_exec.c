@@ -672,9 +672,31 @@ run_pipeline(CbEState *es, CbPipeline *pl)
 	return CBGPU_OK;
 }
 
-/* run the stream into a new relation (MATERIALIZE sink); columns laid out as stream_over_rel expects */
+static int	stream_materialize_ex(CbEState *es, CbPlanState *ps, CbStream *s, Owned *own, cbgpu_rel **out, PExpr *shape, int *nshape,
+								  int borrow);
+static int	stream_is_plain(const CbStream *s, cbgpu_rel **rel, const uint32_t **sel);
+
+/* the stream's rows as a relation: a new one (MATERIALIZE sink) or, when the stream is a relation already, that one */
 static int
 stream_materialize(CbEState *es, CbPlanState *ps, CbStream *s, Owned *own, cbgpu_rel **out, PExpr *shape, int *nshape)
+{
+	return stream_materialize_ex(es, ps, s, own, out, shape, nshape, 1);
+}
+
+/* is rel one of the executor's base tables?  (those are never handed out as somebody's result: a consumer may free or
+ * re-shape what it is given) */
+static int
+cbgpu_rel_is_base(const CbEState *es, const cbgpu_rel *rel)
+{
+	for (int i = 0; i < es->es_nrels; i++)
+		if (es->es_range_table[i] == rel)
+			return 1;
+	return 0;
+}
+
+/* run the stream into a new relation (MATERIALIZE sink); columns laid out as stream_over_rel expects */
+static int
+stream_materialize_ex(CbEState *es, CbPlanState *ps, CbStream *s, Owned *own, cbgpu_rel **out, PExpr *shape, int *nshape, int borrow)
 {
 	int32_t		types[CBP_MAX_OUT],
 				dscales[CBP_MAX_OUT];
@@ -686,6 +708,47 @@ stream_materialize(CbEState *es, CbPlanState *ps, CbStream *s, Owned *own, cbgpu
 	CbPipeline *p = &s->pipe;
 	int			saved_nops = p->nops;
 
+	if (borrow && stream_is_plain(s, &rel, NULL))
+	{
+		/* the stream already IS a relation with exactly these columns (an aggregate's group relation, a Motion's receive
+		 * buffer): hand it over instead of copying it through a kernel.  The caller does not own it - its producer does. */
+		int			exact = 1,
+					c = 0;
+
+		for (int i = 0; i < s->nout && exact; i++)
+		{
+			PExpr	   *x = &s->pe[s->out[i]];
+
+			shape[i] = *x;
+			if (x->kind == PE_STATE)
+			{
+				if (s->pe[x->cn].kind != PE_COL || s->col_idx[s->pe[x->cn].col] != c || s->pe[x->clo].kind != PE_COL ||
+					s->col_idx[s->pe[x->clo].col] != c + 1 || s->pe[x->chi].kind != PE_COL || s->col_idx[s->pe[x->chi].col] != c + 2)
+					exact = 0;
+				c += 3;
+			}
+			else
+			{
+				if (x->kind != PE_COL || s->col_idx[x->col] != c)
+					exact = 0;
+				c++;
+			}
+		}
+		if (exact && c == cbgpu_rel_ncols(rel) && !cbgpu_rel_is_base(es, rel) && borrow == 2)
+		{
+			/* the caller takes the relation over: only if it is this node's own */
+			exact = 0;
+			for (int i = 0; i < own->nrels; i++)
+				if (own->rels[i] == rel)
+					exact = 1;
+		}
+		if (exact && c == cbgpu_rel_ncols(rel) && !cbgpu_rel_is_base(es, rel))
+		{
+			*nshape = s->nout;
+			*out = rel;
+			return CBGPU_OK;
+		}
+	}
 	for (int i = 0; i < s->nout; i++)
 	{
 		PExpr	   *x = &s->pe[s->out[i]];
@@ -2890,8 +2953,16 @@ limitsort_run(CbPlanState *ps, cbgpu_rel **out_rel, PExpr *out_shape, int *out_n
 		}
 		GPU(es, cbgpu_rel_create(es->es_ctx, nout, ncols, types, dscales, &small));
 		p->owned.rels[p->owned.nrels++] = small;
-		for (int64_t r = 0; r < nout; r++)
-			GPU(es, cbgpu_rel_copy_rows(small, r, rel, idx[r], 1));
+		if (nout > 0)
+		{
+			/* one gather kernel for all rows and columns (row-by-row copies were 60 tiny memcpys for Q3's ten rows) */
+			void	   *didx;
+
+			GPU(es, cbgpu_dev_alloc(es->es_ctx, sizeof(uint32_t) * (size_t) nout, &didx));
+			p->owned.devs[p->owned.ndevs++] = didx;
+			GPU(es, cbgpu_dev_write(es->es_ctx, didx, sizeof(uint32_t) * (size_t) nout, idx));
+			GPU(es, cbgpu_rel_take_rows(small, rel, (const uint32_t *) didx, nout));
+		}
 		for (int c = 0; c < ncols; c++)
 			if (cbgpu_rel_dict_hash_dev(rel, c))
 				GPU(es, cbgpu_rel_share_dict_hash(small, c, rel, c));
@@ -3121,7 +3192,7 @@ cb_ExecProcNodeBatch(CbPlanState *ps, cbgpu_rel **out)
 	if (ps->type == T_CbHash || ps->type == T_CbAgg || ps->type == T_CbLimitSort)
 		return es_fail(es, CBGPU_ERR_UNSUPPORTED, "batch output of node type %d (its result is finalised on the host)", (int) ps->type);
 	TRY(node_open(ps, &s));
-	TRY(stream_materialize(es, ps, s, &p->owned, &rel, shape, &nshape));
+	TRY(stream_materialize_ex(es, ps, s, &p->owned, &rel, shape, &nshape, 2));
 	for (int i = 0; i < p->owned.nrels; i++)
 		if (p->owned.rels[i] == rel)
 			found = i;

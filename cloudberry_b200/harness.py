@@ -141,7 +141,7 @@ def distribute_by_hash(ctx, motion, rel, keycol, name):
     return out
 
 
-def distributed_tables(ctx, motion, sf, rank, world, seed=42):
+def distributed_tables(ctx, motion, sf, rank, world, seed=42, max_piece_rows=150_000_000):
     """The six relations of an SF-sized database spread over `world` GPU-segments the way the reference's
     DDL would: lineitem and orders by orderkey, customer by c_custkey, supplier by s_suppkey, nation and
     region replicated.  Each rank generates a 1/world row range of every distributed table, then the
@@ -156,19 +156,41 @@ def distributed_tables(ctx, motion, sf, rank, world, seed=42):
         n = sz[name]
         lo, hi = rank * n // world, (rank + 1) * n // world
         types = [t for _, t in tpch.SCHEMA[name]]
-        sl = capi.DeviceRelation(ctx, hi - lo, types, name=name + "_slice")
-        if name == "lineitem":
-            ctx.check(G.cbgpu_gen_lineitem(ctx.h, sl.h, seed, lo, sz["supplier"], sz["part"]))
-        elif name == "orders":
-            ctx.check(G.cbgpu_gen_orders(ctx.h, sl.h, seed, lo, sz["customer"]))
-        elif name == "customer":
-            ctx.check(G.cbgpu_gen_customer_range(ctx.h, sl.h, seed, lo))
-            sl.set_dict_hash(2, seg_hash)
+        # load in pieces: a piece's slice, its Motion buffers and its share of the shard are all that is in flight, so a
+        # table far larger than the peer-memory window (SF300 lineitem on 2 GPUs: 50 GB per rank) loads without ever holding
+        # slice + send buffer + receive buffer of the whole table at once.  Every rank cuts the same number of pieces.
+        piece_rows = max_piece_rows
+        npieces = max(1, -(-max(((r + 1) * n // world - r * n // world) for r in range(world)) // piece_rows))
+        pieces = []
+        for k in range(npieces):
+            plo, phi = lo + (hi - lo) * k // npieces, lo + (hi - lo) * (k + 1) // npieces
+            sl = capi.DeviceRelation(ctx, phi - plo, types, name=name + "_slice")
+            if name == "lineitem":
+                ctx.check(G.cbgpu_gen_lineitem(ctx.h, sl.h, seed, plo, sz["supplier"], sz["part"]))
+            elif name == "orders":
+                ctx.check(G.cbgpu_gen_orders(ctx.h, sl.h, seed, plo, sz["customer"]))
+            elif name == "customer":
+                ctx.check(G.cbgpu_gen_customer_range(ctx.h, sl.h, seed, plo))
+                sl.set_dict_hash(2, seg_hash)
+            else:
+                ctx.check(G.cbgpu_gen_supplier_range(ctx.h, sl.h, seed, plo))
+            ctx.sync()
+            pieces.append(distribute_by_hash(ctx, motion, sl, keys[name], name))
+            sl.free()
+        if len(pieces) == 1:
+            shards[name] = pieces[0]
         else:
-            ctx.check(G.cbgpu_gen_supplier_range(ctx.h, sl.h, seed, lo))
-        ctx.sync()
-        shards[name] = distribute_by_hash(ctx, motion, sl, keys[name], name)
-        sl.free()
+            total = sum(p.nrows for p in pieces)
+            whole = capi.DeviceRelation(ctx, total, types, name=name)
+            at = 0
+            for p in pieces:
+                if p.nrows:
+                    ctx.check(G.cbgpu_rel_copy_rows(whole.h, at, p.h, 0, p.nrows))
+                at += p.nrows
+                p.free()
+            if name == "customer":
+                whole.set_dict_hash(2, seg_hash)
+            shards[name] = whole
     nation, region = tpch.gen_nation_region()
     for name, cols, texts in (("nation", nation, {"n_name": tpch.NATIONS}), ("region", region, {"r_name": tpch.REGIONS})):
         types = [t for _, t in tpch.SCHEMA[name]]

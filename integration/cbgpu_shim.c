@@ -219,7 +219,27 @@ translate_expr(Expr *e)
 				Var		   *v = (Var *) e;
 				CbExpr	   *x;
 
-				if (v->varlevelsup != 0 || v->varattno <= 0 || !translate_type(v->vartype, v->vartypmod, &t, &ds))
+				if (v->varlevelsup != 0 || v->varattno <= 0)
+					return NULL;
+				if (is_string_type(v->vartype, v->vartypmod))
+				{
+					/* character(n) / varchar / text columns are dictionary codes on the device (the loader's choice:
+					 * integration/cbgpu_shim_storage.c gives them CB_DICT32), here and in every node above */
+					t = CB_DICT32;
+					ds = 0;
+				}
+				else if ((v->vartype == BYTEAOID || v->vartype == INTERNALOID || (v->vartype == NUMERICOID && v->vartypmod < (int32) VARHDRSZ)) &&
+						 (v->varno == OUTER_VAR || v->varno == INNER_VAR))
+				{
+					/* a partial aggregate's serialised state travelling up (Motion target lists, the Finalize Aggref's
+					 * argument), or an aggregate's / expression's numeric result (no typmod above the node that computes
+					 * it): the device keeps states as (N, sum) columns and numerics as scaled integers whose type and
+					 * display scale are the producing expression's, known once the child is translated - resolve_plan
+					 * fills them in */
+					t = (CbTypeId) 0;
+					ds = 0;
+				}
+				else if (!translate_type(v->vartype, v->vartypmod, &t, &ds))
 					return NULL;
 				x = new_expr(T_CbVar, t, ds);
 				x->varno = v->varno;	/* INNER_VAR / OUTER_VAR keep their values (65000 / 65001) */
@@ -400,9 +420,18 @@ translate_expr(Expr *e)
 				else if (strcmp(name, "max") == 0) fn = CB_AGG_MAX;
 				else
 					return NULL;
-				if (!translate_type(a->aggtype, -1, &t, &ds) && a->aggtype != NUMERICOID)
-					return NULL;
-				x = new_expr(T_CbAggref, a->aggtype == NUMERICOID ? CB_NUMERIC : t, 0);
+				{
+					/* a partial aggregate's aggtype is its serialised transition type (bytea for the numeric aggregates:
+					 * mark_partial_aggref, optimizer/plan/planner.c); the device keeps typed (N, sum) states, so the type
+					 * that matters is the aggregate's own result type */
+					Oid			rettype = a->aggtype;
+
+					if (DO_AGGSPLIT_SKIPFINAL(a->aggsplit))
+						rettype = get_func_rettype(a->aggfnoid);
+					if (!translate_type(rettype, -1, &t, &ds) && rettype != NUMERICOID)
+						return NULL;
+					x = new_expr(T_CbAggref, rettype == NUMERICOID ? CB_NUMERIC : t, 0);
+				}
 				x->op = fn;
 				if (!translate_args(x, a->args))
 					return NULL;
@@ -534,7 +563,9 @@ translate_plan(Plan *p, EState *estate, List **rels)
 					case JOIN_LEFT: c->jointype = CB_JOIN_LEFT; break;
 					case JOIN_SEMI: c->jointype = CB_JOIN_SEMI; break;
 					case JOIN_ANTI: c->jointype = CB_JOIN_ANTI; break;
-					default: return NULL;	/* RIGHT / FULL / LASJ_NOTIN stay on the CPU */
+					case JOIN_RIGHT: c->jointype = CB_JOIN_RIGHT; break;
+					case JOIN_FULL: c->jointype = CB_JOIN_FULL; break;
+					default: return NULL;	/* LASJ_NOTIN and the rest stay on the CPU */
 				}
 				if (!translate_exprs(hj->hashkeys, &c->nhashkeys, &c->hashkeys) ||
 					!translate_exprs(hj->join.joinqual, &c->njoinquals, &c->joinqual))
@@ -615,6 +646,75 @@ translate_plan(Plan *p, EState *estate, List **rels)
 			}
 		default:
 			return NULL;
+	}
+}
+
+/* Second pass: Vars that carry a partial aggregate's state take the type and display scale of the target entry they
+ * point at (the child's Aggref), bottom-up; a Finalize Aggref over such a Var then gets its display scale
+ * (numeric_sum / numeric_avg keep their input's, utils/adt/numeric.c:6091). */
+static bool
+resolve_expr(CbExpr *x, const CbPlan *outer, const CbPlan *inner)
+{
+	if (x == NULL)
+		return true;
+	if (x->tag == T_CbVar && x->restype == 0)
+	{
+		const CbPlan *src = x->varno == OUTER_VAR ? outer : x->varno == INNER_VAR ? inner : NULL;
+		const CbExpr *t;
+
+		if (src == NULL || x->varattno < 1 || x->varattno > src->ntargets)
+			return false;
+		t = src->targetlist[x->varattno - 1].expr;
+		if (t->restype == 0)
+			return false;
+		x->restype = t->restype;
+		x->dscale = t->dscale;
+	}
+	for (int i = 0; i < x->nargs; i++)
+		if (!resolve_expr(x->args[i], outer, inner))
+			return false;
+	if (x->tag == T_CbAggref && x->nargs == 1 && x->restype == CB_NUMERIC)
+		x->dscale = x->args[0]->dscale;
+	return true;
+}
+
+static bool
+resolve_exprs(CbExpr **l, int n, const CbPlan *outer, const CbPlan *inner)
+{
+	for (int i = 0; i < n; i++)
+		if (!resolve_expr(l[i], outer, inner))
+			return false;
+	return true;
+}
+
+static bool
+resolve_plan(CbPlan *c)
+{
+	const CbPlan *outer,
+			   *inner;
+
+	if (c == NULL)
+		return true;
+	if (!resolve_plan(c->lefttree) || !resolve_plan(c->righttree))
+		return false;
+	outer = c->lefttree;
+	inner = c->righttree;
+	for (int i = 0; i < c->ntargets; i++)
+		if (!resolve_expr(c->targetlist[i].expr, outer, inner))
+			return false;
+	if (!resolve_exprs(c->qual, c->nquals, outer, inner))
+		return false;
+	switch (c->type)
+	{
+		case T_CbHash:
+			return resolve_exprs(((CbHash *) c)->hashkeys, ((CbHash *) c)->nhashkeys, outer, inner);
+		case T_CbHashJoin:
+			return resolve_exprs(((CbHashJoin *) c)->hashkeys, ((CbHashJoin *) c)->nhashkeys, outer, inner) &&
+				resolve_exprs(((CbHashJoin *) c)->joinqual, ((CbHashJoin *) c)->njoinquals, outer, inner);
+		case T_CbMotion:
+			return resolve_exprs(((CbMotion *) c)->hashExprs, ((CbMotion *) c)->nhashExprs, outer, inner);
+		default:
+			return true;
 	}
 }
 
@@ -751,7 +851,7 @@ shim_take_over(PlanState *ps, EState *estate)
 	const bool	has_motion = plan_has_motion(ps->plan);
 
 	/* 1. decisions that follow from the plan alone (the same on every segment): translation, node support */
-	if (cplan == NULL || desc == NULL)
+	if (cplan == NULL || desc == NULL || !resolve_plan(cplan))
 		return false;
 	if (shim_ctx == NULL && cbgpu_ctx_create(GpIdentity.segindex >= 0 ? GpIdentity.segindex % Max(cbgpu_device_count(), 1) : 0, &shim_ctx) != CBGPU_OK)
 		SHIM_LOCAL_FAILURE(has_motion, (CbgpuShim *) NULL, "cbgpu: no CUDA context on segment %d", GpIdentity.segindex);

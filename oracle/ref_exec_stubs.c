@@ -25,7 +25,9 @@ REF_STUB(cstring_to_text_with_len)
 REF_STUB(end_MultiFuncCall)
 REF_STUB(enlargeStringInfo)
 REF_STUB(estimateHyperLogLog)
+#ifndef REF_PLAN_LIB				/* libplan_ref.so links the reference's nodes/nodeFuncs.c, which defines these */
 REF_STUB(exprTypmod)
+#endif
 REF_STUB(float4in)
 REF_STUB(float8in)
 REF_STUB(format_type_be)
@@ -50,7 +52,9 @@ REF_STUB(pq_getmsgint)
 REF_STUB(pq_getmsgint64)
 REF_STUB(pq_getmsgtext)
 REF_STUB(pq_sendbytes)
+#ifndef REF_PLAN_LIB
 REF_STUB(relabel_to_typmod)
+#endif
 REF_STUB(text_to_cstring)
 REF_STUB(textsend)
 REF_STUB(toast_raw_datum_size)

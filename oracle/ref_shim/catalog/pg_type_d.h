@@ -26,6 +26,8 @@
 #define TIMESTAMPOID 1114
 #define TIMESTAMPTZOID 1184
 #define NUMERICOID 1700
+#define RECORDOID 2249
+#define INTERNALOID 2281
 /* the EXPOSE_TO_CLIENT_CODE part of catalog/pg_type.h:280-300 that genbki copies here */
 #define TYPTYPE_BASE 'b'
 #define TYPTYPE_COMPOSITE 'c'
