@@ -275,6 +275,7 @@ def gpu():
             "cbgpu_rel_col_type": (i32, [vp, i32]),
             "cbgpu_rel_col_dscale": (i32, [vp, i32]),
             "cbgpu_rel_load_column": (C.c_int, [vp, i32, vp, vp]),
+            "cbgpu_rel_load_column_narrow": (C.c_int, [vp, i32, vp, i32]),
             "cbgpu_rel_read_column": (C.c_int, [vp, i32, i64, i64, vp, vp]),
             "cbgpu_rel_set_visimap": (C.c_int, [vp, vp]),
             "cbgpu_rel_read_visimap": (C.c_int, [vp, vp]),
@@ -657,8 +658,12 @@ class DeviceRelation:
         self.ctx.check(self.ctx.L.cbgpu_rel_read_visimap(self.h, out.ctypes.data))
         return np.unpackbits(out, bitorder="little")[:self.rows()].astype(bool)
 
-    def load_column_ptr(self, col, host_ptr):
-        self.ctx.check(self.ctx.L.cbgpu_rel_load_column(self.h, col, host_ptr, None))
+    def load_column_ptr(self, col, host_ptr, host_width=None):
+        """host_width: the host column's integer width when it is narrower than the column's own (sign-extended on the device)"""
+        if host_width is None or host_width == P.TYPE_WIDTH[self.types[col]]:
+            self.ctx.check(self.ctx.L.cbgpu_rel_load_column(self.h, col, host_ptr, None))
+        else:
+            self.ctx.check(self.ctx.L.cbgpu_rel_load_column_narrow(self.h, col, host_ptr, host_width))
 
     def set_dict_hash(self, col, hashes):
         dh = np.ascontiguousarray(hashes, dtype=np.uint32)

@@ -50,7 +50,7 @@ struct cbgpu_ctx
 								 * synchronising read-back fetches the status word too, so the check
 								 * after it costs no second round trip                                 */
 	/* environment knobs, read ONCE when the context is created - not per launch */
-	bool		opt_debug, opt_no_early_filter, opt_no_keyslot, opt_no_fuse0, opt_no_spec0, opt_no_smem_ht, opt_l2_direct;
+	bool		opt_debug, opt_no_early_filter, opt_no_keyslot, opt_no_fuse0, opt_no_spec0, opt_no_smem_ht, opt_l2_direct, opt_no_prefilter;
 	int			opt_bloom_div;
 	int			opt_htb_u;		/* rows a hash-build thread keeps in flight (CBGPU_HTB_U: 1, 2, 4)          */
 	/* host-side scratch of the launch path (decompiled programs, kernel parameter blocks: too large for the
@@ -71,6 +71,10 @@ struct cbgpu_ctx
 	int			early_cache_n;
 	/* pinned (mapped) host buffer small aggregate tables are snapshotted into by the kernel that finishes them: group count,
 	 * flags and the groups themselves arrive with ONE synchronisation (struct AggSnap, below) */
+	/* pipelines whose prefilter pass cut too little (k_prefilter, probe_chain.cu): not tried again */
+	uint64_t	pf_cache[32];
+	int			pf_cache_n;
+	int64_t		opt_pf_min_rows;	/* scans below this many rows stay in the fused kernel (CBGPU_PREFILTER_MIN_ROWS)        */
 	struct AggSnap *agg_snap;
 	void	   *small_dev;		/* device scratch of the small-group scan kernel, grown on demand              */
 	size_t		small_dev_bytes;

@@ -61,6 +61,8 @@ cbgpu_ctx_create(int device, cbgpu_ctx **out)
 	ctx->opt_no_fuse0 = getenv("CBGPU_NO_FUSE0") != NULL;
 	ctx->opt_no_spec0 = getenv("CBGPU_SPEC0") == NULL;	/* measured: loading probe 0's keys with the qual columns loses (Q3 3.49 vs 3.18 ms) */
 	ctx->opt_no_smem_ht = getenv("CBGPU_NO_SMEM_HT") != NULL;
+	ctx->opt_no_prefilter = getenv("CBGPU_NO_PREFILTER") != NULL;
+	ctx->opt_pf_min_rows = getenv("CBGPU_PREFILTER_MIN_ROWS") ? atoll(getenv("CBGPU_PREFILTER_MIN_ROWS")) : ((int64_t) 16 << 20);
 	ctx->opt_l2_direct = getenv("CBGPU_L2_DIRECT") != NULL;
 	ctx->opt_htb_u = getenv("CBGPU_HTB_U") && atoi(getenv("CBGPU_HTB_U")) > 0 ? atoi(getenv("CBGPU_HTB_U")) : 1;
 	ctx->opt_bloom_div = getenv("CBGPU_BLOOM_DIV") && atoi(getenv("CBGPU_BLOOM_DIV")) > 0 ? atoi(getenv("CBGPU_BLOOM_DIV")) : 2;
@@ -498,6 +500,60 @@ cbgpu_rel_load_column(cbgpu_rel *rel, int32_t col, const void *host, const uint8
 		cudaFreeAsync(rel->nulls[col], ctx->stream);
 		rel->nulls[col] = NULL;
 	}
+	return CBGPU_OK;
+}
+
+/* host columns shipped in a narrower integer width than the column's own (PCIe is the bottleneck of a load: a
+ * numeric(15,2) whose values fit 16 bits travels as int16) and sign-extended on the device */
+template <typename NARROW, typename WIDE>
+__global__ void
+k_widen(const NARROW *__restrict__ src, WIDE *__restrict__ dst, int64_t n)
+{
+	int64_t		i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+
+	for (; i < n; i += stride)
+		dst[i] = (WIDE) src[i];
+}
+
+extern "C" int
+cbgpu_rel_load_column_narrow(cbgpu_rel *rel, int32_t col, const void *host, int32_t host_width)
+{
+	cbgpu_ctx  *ctx = rel->ctx;
+	void	   *stage;
+	int			w;
+	int			blocks;
+
+	if (col < 0 || col >= rel->ncols)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_load_column_narrow: bad column%s %lld", "", col);
+	w = cb_type_w(rel->types[col]);
+	if (host_width == w)
+		return cbgpu_rel_load_column(rel, col, host, NULL);
+	if (rel->types[col] == CB_FLOAT8 || (w != 8 && w != 4) || (host_width != 1 && host_width != 2 && host_width != 4) || host_width > w)
+		return cb_fail(ctx, CBGPU_ERR_INVALID, "cbgpu_rel_load_column_narrow: a %s%lld-byte host column cannot be widened into this column", "", host_width);
+	if (rel->nrows == 0)
+		return CBGPU_OK;
+	CB_CUDA(ctx, cudaMallocAsync(&stage, (size_t) rel->nrows * host_width, ctx->stream));
+	CB_CUDA(ctx, cudaMemcpyAsync(stage, host, (size_t) rel->nrows * host_width, cudaMemcpyHostToDevice, ctx->stream));
+	blocks = ctx->sm_count * 8;
+	if (w == 8)
+	{
+		if (host_width == 1)
+			k_widen<int8_t, int64_t><<<blocks, 256, 0, ctx->stream>>>((const int8_t *) stage, (int64_t *) rel->data[col], rel->nrows);
+		else if (host_width == 2)
+			k_widen<int16_t, int64_t><<<blocks, 256, 0, ctx->stream>>>((const int16_t *) stage, (int64_t *) rel->data[col], rel->nrows);
+		else
+			k_widen<int32_t, int64_t><<<blocks, 256, 0, ctx->stream>>>((const int32_t *) stage, (int64_t *) rel->data[col], rel->nrows);
+	}
+	else
+	{
+		if (host_width == 1)
+			k_widen<int8_t, int32_t><<<blocks, 256, 0, ctx->stream>>>((const int8_t *) stage, (int32_t *) rel->data[col], rel->nrows);
+		else
+			k_widen<int16_t, int32_t><<<blocks, 256, 0, ctx->stream>>>((const int16_t *) stage, (int32_t *) rel->data[col], rel->nrows);
+	}
+	CB_LAUNCHED(ctx, "k_widen");
+	CB_CUDA(ctx, cudaFreeAsync(stage, ctx->stream));
 	return CBGPU_OK;
 }
 

@@ -94,6 +94,9 @@ struct PcEarly
 struct PcParams
 {
 	int64_t		nrows;
+	/* the driving rows are sel[0 .. nrows) instead of 0 .. nrows: what k_prefilter left of a big scan (quals, visimap and
+	 * scan-level filters are then done: nfilters = nearly = 0, visimap = NULL) */
+	const uint32_t *sel;
 	const uint8_t *visimap;
 	int32_t		nfilters;
 	int32_t		np;
@@ -159,13 +162,14 @@ struct PcQ
 {
 	const uint32_t *q;
 	uint32_t	cap;
-	uint32_t	iota_base;		/* q == NULL: entry e is driving row iota_base + e (no quals)         */
+	uint32_t	iota_base;		/* q == NULL: entry e is driving row iota_base + e (no quals) ...     */
+	const uint32_t *sel;		/* ... or, after a prefilter pass, sel[iota_base + e]                 */
 };
 
 __device__ __forceinline__ uint32_t
 pc_row(const PcQ &Q, int src, uint32_t e)
 {
-	return Q.q ? Q.q[(size_t) src * Q.cap + e] : Q.iota_base + e;
+	return Q.q ? Q.q[(size_t) src * Q.cap + e] : (Q.sel ? Q.sel[Q.iota_base + e] : Q.iota_base + e);
 }
 
 __device__ __forceinline__ int64_t
@@ -838,6 +842,136 @@ pc_early_filter8(const PcEarly &E, int64_t row0, bool full, unsigned am, uint64_
 	return am;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * k_prefilter: the selective head of a join pipeline over a big scan, as a kernel of its own.
+ *
+ * k_probe_chain keeps a whole pipeline in one kernel, which costs it registers (64 per thread: half occupancy) - fine for
+ * the stages that see few rows, wasteful for the one that sees them all.  When a scan of tens of millions of rows is cut
+ * down hard before the first hash-table access - range quals, visimap, scan-level runtime filters, and the Bloom filter of
+ * every INNER / SEMI probe whose single integer key is a column of the scan itself (the reference pushes exactly these
+ * filters into its SeqScan: PassByBloomFilter, nodeSeqscan.c:413) - this lean kernel does the cutting at full occupancy and
+ * leaves the surviving row ids, in row order per tile, for k_probe_chain to start from (PcParams.sel).
+ * --------------------------------------------------------------------------------------------- */
+#define PF_MAXBLOOM 6
+struct PfParams
+{
+	int64_t		nrows;
+	const uint8_t *visimap;
+	int32_t		nfilters;
+	PcFilter	filt[2];
+	int32_t		nbloom;
+	PcEarly		bloom[PF_MAXBLOOM];
+	uint32_t   *out;
+	unsigned long long *out_count;
+};
+
+__global__ void __launch_bounds__(PC_THREADS, 6)
+k_prefilter(const __grid_constant__ PfParams P)
+{
+	__shared__ uint32_t buf[PC_TILE];
+	__shared__ unsigned s_cnt;
+	__shared__ unsigned long long s_gbase;
+	const int64_t ntiles = (P.nrows + PC_TILE - 1) / PC_TILE;
+	const unsigned o0 = threadIdx.x * 8;
+	const int	lane = threadIdx.x & 31;
+	const uint64_t pol_stream = l2_policy_evict_first();
+
+	for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+	{
+		const int64_t base = tile * PC_TILE;
+		const unsigned nvalid = (unsigned) (P.nrows - base < PC_TILE ? P.nrows - base : PC_TILE);
+		const bool	full = o0 + 8 <= nvalid;
+		unsigned	am = 0;
+
+		if (threadIdx.x == 0)
+			s_cnt = 0;
+		if (full)
+		{
+			int4		a0 = make_int4(0, 0, 0, 0), b0 = a0, a1 = a0, b1 = a0;
+			unsigned	vm = 0xff;
+
+			if (P.nfilters > 0)
+			{
+				if (P.filt[0].width == 4)
+				{
+					a0 = ldg_stream_v4((const int4 *) ((const int32_t *) P.filt[0].col + base + o0), pol_stream);
+					b0 = ldg_stream_v4((const int4 *) ((const int32_t *) P.filt[0].col + base + o0) + 1, pol_stream);
+				}
+				else
+					pc_unpack8(ldg_stream_u64((const unsigned long long *) ((const uint8_t *) P.filt[0].col + base + o0), pol_stream), &a0, &b0);
+			}
+			if (P.nfilters > 1)
+			{
+				if (P.filt[1].width == 4)
+				{
+					a1 = ldg_stream_v4((const int4 *) ((const int32_t *) P.filt[1].col + base + o0), pol_stream);
+					b1 = ldg_stream_v4((const int4 *) ((const int32_t *) P.filt[1].col + base + o0) + 1, pol_stream);
+				}
+				else
+					pc_unpack8(ldg_stream_u64((const unsigned long long *) ((const uint8_t *) P.filt[1].col + base + o0), pol_stream), &a1, &b1);
+			}
+			if (P.visimap)
+				vm = __ldg(P.visimap + ((base + o0) >> 3));
+			am = vm;
+			if (P.nfilters > 0)
+				am &= pc_range8(a0, b0, P.filt[0].lo, P.filt[0].span);
+			if (P.nfilters > 1)
+				am &= pc_range8(a1, b1, P.filt[1].lo, P.filt[1].span);
+		}
+		else
+			for (int u = 0; u < 8; u++)
+			{
+				const int64_t r = base + o0 + u;
+				bool		alive = o0 + u < nvalid;
+
+				if (alive && P.visimap)
+					alive = (__ldg(P.visimap + (r >> 3)) >> (r & 7)) & 1;
+				if (alive && P.nfilters > 0)
+					alive = (unsigned) (pc_filter_value(P.filt[0], r) - P.filt[0].lo) <= P.filt[0].span;
+				if (alive && P.nfilters > 1)
+					alive = (unsigned) (pc_filter_value(P.filt[1], r) - P.filt[1].lo) <= P.filt[1].span;
+				am |= (unsigned) alive << u;
+			}
+		for (int f = 0; f < P.nbloom && __any_sync(0xffffffffu, am != 0); f++)
+			am = P.bloom[f].width == 8 ? pc_early_filter8<true>(P.bloom[f], base + o0, full, am, pol_stream)
+				: pc_early_filter8<false>(P.bloom[f], base + o0, full, am, pol_stream);
+		__syncthreads();				/* s_cnt = 0 is in */
+		{
+			/* the tile's survivors, in row order within each warp: one scan + one shared atomic per warp */
+			const unsigned c = __popc(am);
+			unsigned	x = c;
+
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const unsigned y = __shfl_up_sync(0xffffffffu, x, d);
+
+				if (lane >= d)
+					x += y;
+			}
+			const unsigned total = __shfl_sync(0xffffffffu, x, 31);
+			unsigned	wb = 0;
+
+			if (lane == 31 && total)
+				wb = atomicAdd(&s_cnt, total);
+			wb = __shfl_sync(0xffffffffu, wb, 31);
+			unsigned	pos = wb + x - c;
+
+#pragma unroll
+			for (int u = 0; u < 8; u++)
+				if ((am >> u) & 1)
+					buf[pos++] = (uint32_t) (base + o0 + u);
+		}
+		__syncthreads();
+		if (threadIdx.x == 0 && s_cnt)
+			s_gbase = atomicAdd(P.out_count, (unsigned long long) s_cnt);
+		__syncthreads();
+		for (unsigned i = threadIdx.x; i < s_cnt; i += PC_THREADS)
+			P.out[s_gbase + i] = buf[i];
+		__syncthreads();				/* buf and s_cnt are free for the next tile */
+	}
+}
+
 __global__ void __launch_bounds__(PC_THREADS, PC_OCC)
 k_probe_chain(const __grid_constant__ PcParams P)
 {
@@ -853,7 +987,7 @@ k_probe_chain(const __grid_constant__ PcParams P)
 	extern __shared__ __align__(16) unsigned long long s_tables[];
 	const int	np = P.np;
 	const int	last = 2 * np + 1;		/* the sink's stage number; stage s reads queue s - 1         */
-	const bool	iota = P.nfilters == 0 && P.visimap == NULL && P.nearly == 0;
+	const bool	iota = P.nfilters == 0 && P.visimap == NULL && P.nearly == 0;	/* always so with P.sel */
 	const int64_t tile_rows = iota ? PC_BATCH : PC_TILE;
 	const int64_t ntiles = (P.nrows + tile_rows - 1) / tile_rows;
 	uint32_t   *const qg = P.qmem + (size_t) blockIdx.x * (size_t) P.q_cta_words;
@@ -1067,6 +1201,7 @@ k_probe_chain(const __grid_constant__ PcParams P)
 			Q.q = NULL;
 			Q.cap = 0;
 			Q.iota_base = (uint32_t) tb;
+			Q.sel = P.sel;
 			n = (unsigned) (P.nrows - tb < PC_BATCH ? P.nrows - tb : PC_BATCH);
 			base = 0;
 		}
@@ -1075,12 +1210,14 @@ k_probe_chain(const __grid_constant__ PcParams P)
 			Q.q = q0;
 			Q.cap = PC_Q0CAP;
 			Q.iota_base = 0;
+			Q.sel = NULL;
 		}
 		else
 		{
 			Q.q = qg + P.q_off[s - 1];
 			Q.cap = (uint32_t) P.q_cap[s - 1];
 			Q.iota_base = 0;
+			Q.sel = NULL;
 		}
 		if (s == last)
 			pc_stage_sink(P, Q, base, n, &s_obase, &part);
@@ -1576,9 +1713,85 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 		P.early[P.nearly].mask = B.mask;
 		P.nearly++;
 	}
+	/* ---- a selective head over a big scan runs as its own lean kernel (k_prefilter); the chain starts from its survivors ---- */
+	uint32_t   *pf_sel = NULL;
+	unsigned long long *pf_count = NULL;
+
+	if (!ctx->opt_no_prefilter && P.nrows >= ctx->opt_pf_min_rows && np >= 1)	/* below ~16 M rows the fused kernel's fixed costs win */
+	{
+		PfParams   *Fp = (PfParams *) cb_scratch(ctx, 6, sizeof(PfParams));
+
+		if (!Fp)
+			return CBGPU_ERR_NOMEM;
+		PfParams   &F = *Fp;
+		const uint64_t sig = (uint64_t) (uintptr_t) (P.nfilters ? P.filt[0].col : NULL) ^ ((uint64_t) (uintptr_t) P.probe[0].key[0].data << 1) ^
+			((uint64_t) P.nrows << 20) ^ (uint64_t) P.nfilters ^ ((uint64_t) np << 4) ^ ((uint64_t) P.nearly << 8);
+		bool		known_unselective = false;
+
+		memset(&F, 0, sizeof(F));
+		F.nrows = P.nrows;
+		F.visimap = P.visimap;
+		F.nfilters = P.nfilters;
+		F.filt[0] = P.filt[0];
+		F.filt[1] = P.filt[1];
+		for (int f = 0; f < P.nearly; f++)
+			F.bloom[F.nbloom++] = P.early[f];
+		for (int j = 0; j < np && F.nbloom < PF_MAXBLOOM; j++)
+		{
+			const PcProbe &q = P.probe[j];
+
+			if ((q.jointype != CB_JOIN_INNER && q.jointype != CB_JOIN_SEMI) || q.nkeys != 1 || (q.kind != 0 && q.kind != 1) ||
+				q.key[0].src != 0 || !q.ht.bloom || ((uintptr_t) q.key[0].data & 15) != 0)
+				continue;
+			F.bloom[F.nbloom].col = q.key[0].data;
+			F.bloom[F.nbloom].width = q.kind == 1 ? 8 : 4;
+			F.bloom[F.nbloom].hashtype = q.keytype[0];
+			F.bloom[F.nbloom].bloom = q.ht.bloom;
+			F.bloom[F.nbloom].mask = q.ht.bloom_mask;
+			F.nbloom++;
+		}
+		for (int i = 0; i < ctx->pf_cache_n; i++)
+			if (ctx->pf_cache[i] == sig)
+				known_unselective = true;
+		if (F.nbloom + F.nfilters > 0 && !known_unselective)
+		{
+			unsigned long long nsel = 0;
+			int			fb = ctx->sm_count * 6;
+			const int64_t ft = (P.nrows + PC_TILE - 1) / PC_TILE;
+
+			if (fb > ft)
+				fb = (int) ft;
+			CB_CUDA(ctx, cudaMallocAsync(&pf_sel, (size_t) P.nrows * sizeof(uint32_t), ctx->stream));
+			CB_CUDA(ctx, cudaMallocAsync(&pf_count, sizeof(unsigned long long), ctx->stream));
+			CB_CUDA(ctx, cudaMemsetAsync(pf_count, 0, sizeof(unsigned long long), ctx->stream));
+			F.out = pf_sel;
+			F.out_count = pf_count;
+			k_prefilter<<<fb, PC_THREADS, 0, ctx->stream>>>(F);
+			CB_LAUNCHED(ctx, "k_prefilter");
+			CB_CUDA(ctx, cudaMemcpyAsync(&nsel, pf_count, sizeof(nsel), cudaMemcpyDeviceToHost, ctx->stream));
+			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			if (ctx->opt_debug)
+				fprintf(stderr, "k_prefilter: %lld of %lld rows survive %d qual(s) + %d filter(s)\n", (long long) nsel, (long long) P.nrows, F.nfilters, F.nbloom);
+			if (nsel * 2 <= (unsigned long long) P.nrows)
+			{
+				P.sel = pf_sel;
+				P.nrows = (int64_t) nsel;
+				P.nfilters = 0;
+				P.visimap = NULL;
+				P.nearly = 0;
+			}
+			else
+			{
+				/* it cut too little to pay for a second pass over its survivors: the fused kernel does the whole job, and the
+				 * next run of this pipeline does not ask again */
+				if (ctx->pf_cache_n < (int) (sizeof(ctx->pf_cache) / sizeof(ctx->pf_cache[0])))
+					ctx->pf_cache[ctx->pf_cache_n++] = sig;
+			}
+		}
+	}
 	/* persistent grid: 4 CTAs per SM; queue k >= 1 holds (k + 3) / 2 words per entry */
 	const bool	iota = P.nfilters == 0 && P.visimap == NULL && P.nearly == 0;
-	const int64_t ntiles = (p->nrows + (iota ? PC_BATCH : PC_TILE) - 1) / (iota ? PC_BATCH : PC_TILE);
+	const int64_t ntiles = (P.nrows + (iota ? PC_BATCH : PC_TILE) - 1) / (iota ? PC_BATCH : PC_TILE);
 	int			blocks = ctx->sm_count * PC_OCC;
 	int64_t		words = 0;
 
@@ -1651,6 +1864,10 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 	cb_klog_end(ctx, kl);
 	CB_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
 	CB_CUDA(ctx, cudaFreeAsync(P.qmem, ctx->stream));
+	if (pf_sel)
+		CB_CUDA(ctx, cudaFreeAsync(pf_sel, ctx->stream));
+	if (pf_count)
+		CB_CUDA(ctx, cudaFreeAsync(pf_count, ctx->stream));
 	for (int f = 0; f < PC_MAXEARLY; f++)
 		if (early_mem[f])
 			CB_CUDA(ctx, cudaFreeAsync(early_mem[f], ctx->stream));

@@ -113,6 +113,11 @@ int32_t		cbgpu_rel_col_dscale(const cbgpu_rel *rel, int32_t col);
 /* host -> device copy of one whole column (asynchronous on the context stream when `host` is
  * pinned); nulls: NULL or one byte per row (1 = NULL) */
 int			cbgpu_rel_load_column(cbgpu_rel *rel, int32_t col, const void *host, const uint8_t *nulls);
+/* the same for a host column held in a NARROWER two's-complement integer width than the column's own (host_width 1, 2 or 4
+ * bytes into an 8- or 4-byte integer / date / scaled-numeric column): copied as it is and sign-extended on the device.  A
+ * load is PCIe-bound, so a loader that knows a column's value range (block min / max) ships a numeric(15,2) quantity as
+ * int16 instead of int64; the relation in HBM is the same either way.  No NULL map (use cbgpu_rel_load_column for those). */
+int			cbgpu_rel_load_column_narrow(cbgpu_rel *rel, int32_t col, const void *host, int32_t host_width);
 /* device -> host copy of rows [lo, hi) of a column (blocking) */
 int			cbgpu_rel_read_column(cbgpu_rel *rel, int32_t col, int64_t lo, int64_t hi, void *host, uint8_t *nulls);
 /* visibility bitmap, one bit per row, 1 = visible (appendonly_visimap.c:198); NULL clears it */

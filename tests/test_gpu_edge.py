@@ -181,3 +181,72 @@ def test_overflow_is_refused(ctx, oracle, generic):
     ex.close()
     for d in dev:
         d.free()
+
+
+@pytest.mark.parametrize("typ,host_dtype", [(P.NUMERIC, np.int8), (P.NUMERIC, np.int16), (P.NUMERIC, np.int32), (P.INT8, np.int16),
+                                            (P.INT4, np.int8), (P.DATE, np.int16)])
+def test_narrow_host_columns_are_sign_extended(ctx, typ, host_dtype):
+    """cbgpu_rel_load_column_narrow: a host column shipped in a narrower integer width arrives as the column's own width, negative
+    values included; widths that cannot be widened into the column are refused"""
+    n = 100003
+    rng = np.random.default_rng(int(typ) * 100 + np.dtype(host_dtype).itemsize)
+    info = np.iinfo(host_dtype)
+    vals = rng.integers(info.min, info.max, n, endpoint=True).astype(host_dtype)
+    vals[:4] = [info.min, info.max, -1, 0]
+    rel = capi.DeviceRelation(ctx, n, [typ], name="narrow")
+    rel.load_column_ptr(0, vals.ctypes.data, vals.dtype.itemsize)
+    got, nulls = rel.read_column(0)
+    assert np.array_equal(got.astype(np.int64), vals.astype(np.int64)) and not nulls.any()
+    with pytest.raises(capi.CbgpuError):
+        ctx.check(ctx.L.cbgpu_rel_load_column_narrow(rel.h, 0, vals.ctypes.data, 3))
+    rel.free()
+    f = capi.DeviceRelation(ctx, n, [P.FLOAT8], name="f8")
+    with pytest.raises(capi.CbgpuError):
+        ctx.check(ctx.L.cbgpu_rel_load_column_narrow(f.h, 0, vals.ctypes.data, 4))
+    f.free()
+
+
+def test_prefilter_pass_on_small_inputs(oracle):
+    """the two-kernel plan of big selective scans (k_prefilter leaves row ids, k_probe_chain starts from them) forced onto small
+    tables (CBGPU_PREFILTER_MIN_ROWS=1; knobs are read when a context is created): join types, quals, visimap, NULL-free keys,
+    empty sides - the same rows as the oracle's; and a pipeline it cannot thin is remembered and left to the fused kernel"""
+    import os
+    from cloudberry_b200 import tpch
+    os.environ["CBGPU_PREFILTER_MIN_ROWS"] = "1"
+    try:
+        c = capi.Context(0)
+    finally:
+        del os.environ["CBGPU_PREFILTER_MIN_ROWS"]
+    try:
+        for jointype in (P.JOIN_INNER, P.JOIN_SEMI, P.JOIN_ANTI):
+            for nf, nd, vis in ((5000, 40, 1.0), (100003, 30, 0.7), (2049, 1, 1.0), (5000, 0, 1.0)):
+                fo, fp = make(fact, nf, seed=3, visible_frac=vis)
+                do, dp = make(dim, nd, seed=4)
+                sf = scan(1, fo, ["k", "amt", "g"], [P.OpExpr(P.OP_LT, P.Var(1, fo.attno("d"), P.DATE), P.Const(P.DATE, 1500))])
+                sd = scan(2, do, ["dk", "w", "c"])
+                h = P.Hash(sd, [P.out_var(sd, 1)])
+                targets = [("k", P.out_var(sf, 1)), ("amt", P.out_var(sf, 2)), ("g", P.out_var(sf, 3))]
+                if jointype == P.JOIN_INNER:
+                    targets += [("w", P.InnerVar(2, P.INT8)), ("c", P.InnerVar(3, P.DICT8))]
+                j = P.HashJoin(jointype, sf, h, [P.out_var(sf, 1)], targets)
+                names = [t[0] for t in targets]
+                aggs = [("s", P.AGG_SUM, "amt"), ("n", P.AGG_COUNT_STAR, None)] + ([("sw", P.AGG_SUM, "w")] if "w" in names else [])
+                plan = agg_over(j, names, ["g"] + (["c"] if "c" in names else []), aggs)
+                for _ in range(2):                       # the second run meets the selectivity cache
+                    got, want = run_both(c, oracle, plan, [fo, do], [fp, dp], False)
+                    assert canon(got) == canon(want), (jointype, nf, nd, vis)
+        # TPC-H Q3 / Q5 shapes
+        rels_o = tpch.gen_tables(0.05, oracle.hashbpchar)
+        rels_p = tpch.gen_tables(0.05, capi.hashbpchar)
+        dev = to_device(c, rels_p)
+        ex = capi.Executor(c, dev)
+        for plan, fmt in ((tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), 1), tpch.format_q3),
+                          (tpch.q5_plan(tpch.REGIONS.index("AMERICA"), 1), lambda r: tpch.format_q5(r, tpch.NATIONS))):
+            assert fmt(ex.run(plan).rows) == fmt(oracle.execute(plan, [rels_o]).rows)
+        names = {v["node"] for v in ex.run(tpch.q3_plan(tpch.SEGMENTS.index("MACHINERY"), 1)).instrument.values()}
+        assert names
+        ex.close()
+        for d in dev:
+            d.free()
+    finally:
+        c.close()

@@ -143,7 +143,10 @@ def test_bench_main_arm_control_flow(fake):
     assert line["gpu_launches"] > 0 and "impl" not in line and "cpu_baseline" not in line
     rows = line["config"]["rows_per_gpu"]
     assert line["roofline"]["algorithmic_bytes_per_launch"] == 38 * rows and line["roofline"]["bound"] == "hbm"
-    assert line["e2e"]["h2d_bytes_per_step"] == 38 * rows and line["e2e"]["unit"] == "rows/s"
+    # host columns travel in the narrowest width holding their values (all zero over the no-op runtime: one byte each); the
+    # decoded-width variant is measured beside it
+    assert line["e2e"]["decoded_int64"]["h2d_bytes_per_step"] == 38 * rows and line["e2e"]["unit"] == "rows/s"
+    assert line["e2e"]["h2d_bytes_per_step"] == 7 * rows and line["e2e"]["bytes_per_row_shipped"] == 7
     for q in ("q3", "q5"):
         assert line[q]["gpu_launches_per_step"] > 0 and line[q]["roofline"]["algorithmic_bytes"] > 0
 
