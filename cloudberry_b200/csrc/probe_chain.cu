@@ -972,6 +972,208 @@ k_prefilter(const __grid_constant__ PfParams P)
 	}
 }
 
+/*
+ * The same filter pass fed by a TMA ring (the shape of k_scan_agg_small): one persistent CTA per SM; a producer warp streams
+ * every column the filters read - qual columns and filter key columns, a 4096-row tile at a time - into a ring of
+ * shared-memory stages with bulk copies (cp.async.bulk + mbarrier), as many stages as fit ~200 KB, so HBM streams at
+ * full rate whatever the consumers do.  16 consumer warps evaluate the quals from shared memory and look the keys up in the
+ * Bloom filters (L2-resident, evict_last); each thread owns 8 rows of a tile, so 8 filter words are in flight per thread.
+ * Survivors are compacted per tile in shared memory (32-row runs stay in row order) and appended with one global atomic.
+ * The load-and-test version above (k_prefilter) needs one HBM latency per filter column and one L2 latency per filter,
+ * one after the other, per tile: it ran at 2 - 4 TB/s; this one is bound by the stream.
+ */
+#define PFT_TILE 4096
+#define PFT_NCONS 512
+#define PFT_MAXCOLS 8
+#define PFT_MAXSTAGES 8
+#define PFT_SMEM_BUDGET (200 * 1024)
+
+struct PftCol
+{
+	const void *data;
+	int32_t		width;			/* bytes per value: 1, 4 or 8                                         */
+	int32_t		off;			/* byte offset of the column inside a stage                           */
+};
+
+struct PftParams
+{
+	int64_t		nrows;
+	const uint8_t *visimap;
+	int32_t		ncols;
+	PftCol		col[PFT_MAXCOLS];
+	int32_t		nfilters;
+	int32_t		filt_col[2];	/* index into col[]                                                   */
+	int32_t		filt_lo[2];
+	uint32_t	filt_span[2];
+	int32_t		nbloom;
+	int32_t		bloom_col[PF_MAXBLOOM];
+	const uint32_t *bloom[PF_MAXBLOOM];
+	uint32_t	bloom_mask[PF_MAXBLOOM];
+	int32_t		nstages;
+	uint32_t	stage_bytes;
+	uint32_t   *out;
+	unsigned long long *out_count;
+};
+
+__global__ void __launch_bounds__(PFT_NCONS + 32, 1)
+k_prefilter_tma(const __grid_constant__ PftParams P)
+{
+	extern __shared__ __align__(128) unsigned char pft_smem[];
+	__shared__ uint64_t full_bar[PFT_MAXSTAGES];
+	__shared__ uint64_t empty_bar[PFT_MAXSTAGES];
+	__shared__ uint32_t obuf[PFT_TILE];
+	__shared__ unsigned s_cnt[2];
+	__shared__ unsigned long long s_gbase;
+	const int	warp = threadIdx.x >> 5;
+	const int	lane = threadIdx.x & 31;
+	const int64_t ntiles = (P.nrows + PFT_TILE - 1) / PFT_TILE;
+	const int	nst = P.nstages;
+
+	if (threadIdx.x == 0)
+	{
+		for (int s = 0; s < nst; s++)
+		{
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], PFT_NCONS / 32);
+		}
+		s_cnt[0] = s_cnt[1] = 0;
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (warp == 0)
+	{
+		/* ---- producer ---- */
+		if (lane == 0)
+		{
+			int			it = 0;
+
+			for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
+			{
+				const int	s = it % nst;
+				const unsigned ph = (unsigned) (it / nst) & 1;
+				const int64_t r0 = t * PFT_TILE;
+				const int64_t rows = P.nrows - r0 < PFT_TILE ? P.nrows - r0 : PFT_TILE;
+				unsigned char *st = pft_smem + (size_t) s * P.stage_bytes;
+				unsigned	total = 0;
+
+				/* bulk copies move multiples of 16 bytes; relations are allocated padded */
+				for (int c = 0; c < P.ncols; c++)
+					total += ((unsigned) (rows * P.col[c].width) + 15u) & ~15u;
+				mbar_wait(&empty_bar[s], ph ^ 1);
+				mbar_expect_tx(&full_bar[s], total);
+				for (int c = 0; c < P.ncols; c++)
+					tma_load_1d(st + P.col[c].off, (const unsigned char *) P.col[c].data + r0 * P.col[c].width,
+								((unsigned) (rows * P.col[c].width) + 15u) & ~15u, &full_bar[s]);
+			}
+		}
+		return;
+	}
+	/* ---- consumers ---- */
+	{
+		const int	ct = threadIdx.x - 32;
+		const uint64_t pol_keep = l2_policy_evict_last();
+		int			it = 0;
+
+		for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
+		{
+			const int	s = it % nst;
+			const unsigned ph = (unsigned) (it / nst) & 1;
+			const int64_t r0 = t * PFT_TILE;
+			const int	rows = (int) (P.nrows - r0 < PFT_TILE ? P.nrows - r0 : PFT_TILE);
+			const unsigned char *st = pft_smem + (size_t) s * P.stage_bytes;
+			unsigned	am = 0;
+
+			mbar_wait(&full_bar[s], ph);
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+			{
+				const int	r = ct + j * PFT_NCONS;
+				bool		alive = r < rows;
+
+				if (alive && P.visimap)
+					alive = (__ldg(P.visimap + ((r0 + r) >> 3)) >> ((r0 + r) & 7)) & 1;
+				for (int f = 0; f < P.nfilters; f++)
+				{
+					const PftCol &c = P.col[P.filt_col[f]];
+					const int32_t v = c.width == 4 ? ((const int32_t *) (st + c.off))[r] : (int32_t) ((const uint8_t *) (st + c.off))[r];
+
+					alive = alive && (unsigned) (v - P.filt_lo[f]) <= P.filt_span[f];
+				}
+				am |= (unsigned) alive << j;
+			}
+			for (int f = 0; f < P.nbloom; f++)
+			{
+				const PftCol &c = P.col[P.bloom_col[f]];
+				uint32_t	bits[8], word[8];
+
+				if (!__any_sync(0xffffffffu, am != 0))
+					break;
+#pragma unroll
+				for (int j = 0; j < 8; j++)
+				{
+					const int	r = ct + j * PFT_NCONS;
+					uint32_t	w = 0;
+
+					bits[j] = 0;
+					word[j] = 0;
+					if ((am >> j) & 1)
+					{
+						const uint32_t h = c.width == 8 ? jh_int8(((const int64_t *) (st + c.off))[r])
+							: jh_mix32((uint32_t) ((const int32_t *) (st + c.off))[r]);
+
+						bits[j] = ht_bloom_bits(pg_hash_combine(0u, h, false), &w, P.bloom_mask[f]);
+						word[j] = ldg_hint_u32(P.bloom[f] + w, pol_keep);
+					}
+				}
+#pragma unroll
+				for (int j = 0; j < 8; j++)
+					if ((word[j] & bits[j]) != bits[j])
+						am &= ~(1u << j);
+			}
+			/* the stage's bytes are not needed any more: hand it back before the output work */
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(&empty_bar[s]);
+			/* survivors -> obuf: a warp's 32 consecutive rows of one j stay in order.  Two counters take turns, so that the
+			 * one the next tile will use can be zeroed while this tile's is being read */
+			{
+				unsigned   *cnt = &s_cnt[it & 1];
+
+#pragma unroll
+				for (int j = 0; j < 8; j++)
+				{
+					const unsigned m = __ballot_sync(0xffffffffu, (am >> j) & 1);
+					unsigned	wb = 0;
+
+					if (m == 0)
+						continue;
+					if (lane == 0)
+						wb = atomicAdd(cnt, (unsigned) __popc(m));
+					wb = __shfl_sync(0xffffffffu, wb, 0);
+					if ((am >> j) & 1)
+						obuf[wb + __popc(m & ((1u << lane) - 1))] = (uint32_t) (r0 + ct + j * PFT_NCONS);
+				}
+				asm volatile("bar.sync 1, %0;" :: "r"(PFT_NCONS) : "memory");	/* every push of this tile is in */
+				if (ct == 0)
+				{
+					if (*cnt)
+						s_gbase = atomicAdd(P.out_count, (unsigned long long) *cnt);
+					s_cnt[(it + 1) & 1] = 0;
+				}
+				asm volatile("bar.sync 1, %0;" :: "r"(PFT_NCONS) : "memory");
+				{
+					const unsigned n = *cnt;
+					const unsigned long long gb = s_gbase;
+
+					for (unsigned i = ct; i < n; i += PFT_NCONS)
+						P.out[gb + i] = obuf[i];
+				}
+				asm volatile("bar.sync 1, %0;" :: "r"(PFT_NCONS) : "memory");	/* obuf is free for the next tile */
+			}
+		}
+	}
+}
+
 __global__ void __launch_bounds__(PC_THREADS, PC_OCC)
 k_probe_chain(const __grid_constant__ PcParams P)
 {
@@ -1716,6 +1918,8 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 	/* ---- a selective head over a big scan runs as its own lean kernel (k_prefilter); the chain starts from its survivors ---- */
 	uint32_t   *pf_sel = NULL;
 	unsigned long long *pf_count = NULL;
+	bool		pf_bloom_done[PC_MAXP] = {false, false, false, false};	/* probe j's Bloom filter was applied by the prefilter pass */
+	bool		pf_cand[PC_MAXP] = {false, false, false, false};
 
 	if (!ctx->opt_no_prefilter && P.nrows >= ctx->opt_pf_min_rows && np >= 1)	/* below ~16 M rows the fused kernel's fixed costs win */
 	{
@@ -1749,6 +1953,7 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 			F.bloom[F.nbloom].bloom = q.ht.bloom;
 			F.bloom[F.nbloom].mask = q.ht.bloom_mask;
 			F.nbloom++;
+			pf_cand[j] = true;
 		}
 		for (int i = 0; i < ctx->pf_cache_n; i++)
 			if (ctx->pf_cache[i] == sig)
@@ -1766,8 +1971,77 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 			CB_CUDA(ctx, cudaMemsetAsync(pf_count, 0, sizeof(unsigned long long), ctx->stream));
 			F.out = pf_sel;
 			F.out_count = pf_count;
-			k_prefilter<<<fb, PC_THREADS, 0, ctx->stream>>>(F);
-			CB_LAUNCHED(ctx, "k_prefilter");
+			{
+				/* the TMA-fed version when the filters' columns fit the ring (they do unless there are many wide ones) */
+				PftParams  *Tp = (PftParams *) cb_scratch(ctx, 7, sizeof(PftParams));
+				bool		tma = Tp != NULL && !ctx->opt_prefilter_ldg;
+
+				if (tma)
+				{
+					PftParams  &T = *Tp;
+					uint32_t	off = 0;
+
+					T.nrows = F.nrows;
+					T.visimap = F.visimap;
+					T.out = pf_sel;
+					T.out_count = pf_count;
+					auto colidx = [&](const void *data, int width) -> int
+					{
+						for (int c = 0; c < T.ncols; c++)
+							if (T.col[c].data == data)
+								return c;
+						if (T.ncols >= PFT_MAXCOLS || ((uintptr_t) data & 15) != 0)
+							return -1;
+						T.col[T.ncols].data = data;
+						T.col[T.ncols].width = width;
+						T.col[T.ncols].off = (int32_t) off;
+						off += ((uint32_t) PFT_TILE * (uint32_t) width + 127u) & ~127u;
+						return T.ncols++;
+					};
+					T.nfilters = F.nfilters;
+					for (int f = 0; f < F.nfilters && tma; f++)
+					{
+						T.filt_col[f] = colidx(F.filt[f].col, F.filt[f].width);
+						T.filt_lo[f] = F.filt[f].lo;
+						T.filt_span[f] = F.filt[f].span;
+						tma = T.filt_col[f] >= 0;
+					}
+					T.nbloom = F.nbloom;
+					for (int f = 0; f < F.nbloom && tma; f++)
+					{
+						T.bloom_col[f] = colidx(F.bloom[f].col, F.bloom[f].width);
+						T.bloom[f] = F.bloom[f].bloom;
+						T.bloom_mask[f] = F.bloom[f].mask;
+						tma = T.bloom_col[f] >= 0;
+					}
+					T.stage_bytes = off;
+					T.nstages = off ? (int32_t) (PFT_SMEM_BUDGET / off) : 0;
+					if (T.nstages > PFT_MAXSTAGES)
+						T.nstages = PFT_MAXSTAGES;
+					tma = tma && T.nstages >= 2;
+					if (tma)
+					{
+						static bool attr_done = false;
+						const int64_t tt = (T.nrows + PFT_TILE - 1) / PFT_TILE;
+						int			tb = ctx->sm_count;
+
+						if (!attr_done)
+						{
+							CB_CUDA(ctx, cudaFuncSetAttribute(k_prefilter_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, PFT_SMEM_BUDGET));
+							attr_done = true;
+						}
+						if (tb > tt)
+							tb = (int) tt;
+						k_prefilter_tma<<<tb, PFT_NCONS + 32, (size_t) T.nstages * T.stage_bytes, ctx->stream>>>(T);
+						CB_LAUNCHED(ctx, "k_prefilter_tma");
+					}
+				}
+				if (!tma)
+				{
+					k_prefilter<<<fb, PC_THREADS, 0, ctx->stream>>>(F);
+					CB_LAUNCHED(ctx, "k_prefilter");
+				}
+			}
 			CB_CUDA(ctx, cudaMemcpyAsync(&nsel, pf_count, sizeof(nsel), cudaMemcpyDeviceToHost, ctx->stream));
 			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			if (ctx->opt_debug)
@@ -1779,6 +2053,8 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 				P.nfilters = 0;
 				P.visimap = NULL;
 				P.nearly = 0;
+				for (int j = 0; j < np; j++)
+					pf_bloom_done[j] = pf_cand[j];
 			}
 			else
 			{
@@ -1797,6 +2073,8 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 
 	if (blocks > ntiles)
 		blocks = (int) ntiles;
+	if (blocks < 1)
+		blocks = 1;				/* nothing survived the prefilter: one CTA finds no tile and leaves */
 	/* probe 0 rides in stage F when its one integer key is a column of the driving relation that can be read 16 bytes at
 	 * a time, and stage F exists at all (without quals / visimap / scan-level filters the tiles start at B_0 already) */
 	/* how each table is reached (PcProbe.mode): a few thousand slots -> staged into shared memory by TMA (32 KB per CTA for
@@ -1818,6 +2096,8 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 				P.probe[j].smem_off = (int32_t) smem_slots;
 				smem_slots += (uint32_t) (bytes / 8);
 			}
+			else if (pf_bloom_done[j])
+				P.probe[j].mode = 1;	/* the rows that reach it passed its Bloom filter in the prefilter pass: straight to the table */
 			else if (ctx->opt_l2_direct && bytes <= ((uint64_t) 16 << 20))
 				P.probe[j].mode = 1;	/* measured (SSB Q4.3, 4 MB supplier table): 10.5 ms against 5.1 ms with the filter in front -
 										 * a selective build side's Bloom filter sits in L1, its table does not: off unless asked for */
