@@ -50,7 +50,7 @@ struct cbgpu_ctx
 								 * synchronising read-back fetches the status word too, so the check
 								 * after it costs no second round trip                                 */
 	/* environment knobs, read ONCE when the context is created - not per launch */
-	bool		opt_debug, opt_no_early_filter, opt_no_keyslot, opt_no_fuse0, opt_no_spec0, opt_no_smem_ht, opt_l2_direct, opt_no_prefilter, opt_prefilter_ldg;
+	bool		opt_debug, opt_no_early_filter, opt_no_keyslot, opt_no_fuse0, opt_no_spec0, opt_no_smem_ht, opt_l2_direct, opt_no_prefilter, opt_prefilter_tma, opt_pf_spec, opt_pf_occ6;
 	int			opt_bloom_div;
 	int			opt_htb_u;		/* rows a hash-build thread keeps in flight (CBGPU_HTB_U: 1, 2, 4)          */
 	/* host-side scratch of the launch path (decompiled programs, kernel parameter blocks: too large for the

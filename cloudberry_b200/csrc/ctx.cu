@@ -62,7 +62,9 @@ cbgpu_ctx_create(int device, cbgpu_ctx **out)
 	ctx->opt_no_spec0 = getenv("CBGPU_SPEC0") == NULL;	/* measured: loading probe 0's keys with the qual columns loses (Q3 3.49 vs 3.18 ms) */
 	ctx->opt_no_smem_ht = getenv("CBGPU_NO_SMEM_HT") != NULL;
 	ctx->opt_no_prefilter = getenv("CBGPU_NO_PREFILTER") != NULL;
-	ctx->opt_prefilter_ldg = getenv("CBGPU_PREFILTER_LDG") != NULL;
+	ctx->opt_prefilter_tma = getenv("CBGPU_PREFILTER_TMA") != NULL;
+	ctx->opt_pf_spec = getenv("CBGPU_PF_SPEC") != NULL;
+	ctx->opt_pf_occ6 = getenv("CBGPU_PF_OCC6") != NULL;
 	ctx->opt_pf_min_rows = getenv("CBGPU_PREFILTER_MIN_ROWS") ? atoll(getenv("CBGPU_PREFILTER_MIN_ROWS")) : ((int64_t) 16 << 20);
 	ctx->opt_l2_direct = getenv("CBGPU_L2_DIRECT") != NULL;
 	ctx->opt_htb_u = getenv("CBGPU_HTB_U") && atoi(getenv("CBGPU_HTB_U")) > 0 ? atoi(getenv("CBGPU_HTB_U")) : 1;

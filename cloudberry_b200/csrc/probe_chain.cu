@@ -842,6 +842,29 @@ pc_early_filter8(const PcEarly &E, int64_t row0, bool full, unsigned am, uint64_
 	return am;
 }
 
+/* the same test over keys that are in registers already */
+template <bool WIDE>
+__device__ __forceinline__ unsigned
+pc_bloom8_keys(const PcEarly &E, const PcKeys8 &keys, unsigned am)
+{
+	uint32_t	bits[8], word[8];
+
+#pragma unroll
+	for (int u = 0; u < 8; u++)
+	{
+		const int64_t kv = pc_keys8_get<WIDE>(keys, u);
+		uint32_t	w;
+
+		bits[u] = ht_bloom_bits(pg_hash_combine(0u, WIDE ? jh_int8(kv) : jh_mix32((uint32_t) (int32_t) kv), false), &w, E.mask);
+		word[u] = ((am >> u) & 1) ? __ldg(E.bloom + w) : 0u;
+	}
+#pragma unroll
+	for (int u = 0; u < 8; u++)
+		if ((word[u] & bits[u]) != bits[u])
+			am &= ~(1u << u);
+	return am;
+}
+
 /* ---------------------------------------------------------------------------------------------
  * k_prefilter: the selective head of a join pipeline over a big scan, as a kernel of its own.
  *
@@ -865,7 +888,8 @@ struct PfParams
 	unsigned long long *out_count;
 };
 
-__global__ void __launch_bounds__(PC_THREADS, 6)
+template <bool SPEC, int OCC>
+__global__ void __launch_bounds__(PC_THREADS, OCC)
 k_prefilter(const __grid_constant__ PfParams P)
 {
 	__shared__ uint32_t buf[PC_TILE];
@@ -883,8 +907,19 @@ k_prefilter(const __grid_constant__ PfParams P)
 		const bool	full = o0 + 8 <= nvalid;
 		unsigned	am = 0;
 
+		PcKeys8		keys0;
+		bool		have0 = false;
+
 		if (threadIdx.x == 0)
 			s_cnt = 0;
+		/* SPEC: the first filter's keys are requested together with the qual columns - one HBM latency per tile instead of
+		 * two, for 8 - 16 more registers per thread (4 resident CTAs instead of 6) */
+		if (SPEC && P.nbloom > 0 && __all_sync(0xffffffffu, full))
+		{
+			keys0 = P.bloom[0].width == 8 ? pc_keys8_vec<true>(P.bloom[0].col, base + o0, pol_stream)
+				: pc_keys8_vec<false>(P.bloom[0].col, base + o0, pol_stream);
+			have0 = true;
+		}
 		if (full)
 		{
 			int4		a0 = make_int4(0, 0, 0, 0), b0 = a0, a1 = a0, b1 = a0;
@@ -933,8 +968,13 @@ k_prefilter(const __grid_constant__ PfParams P)
 				am |= (unsigned) alive << u;
 			}
 		for (int f = 0; f < P.nbloom && __any_sync(0xffffffffu, am != 0); f++)
-			am = P.bloom[f].width == 8 ? pc_early_filter8<true>(P.bloom[f], base + o0, full, am, pol_stream)
-				: pc_early_filter8<false>(P.bloom[f], base + o0, full, am, pol_stream);
+		{
+			if (SPEC && f == 0 && have0)
+				am = P.bloom[0].width == 8 ? pc_bloom8_keys<true>(P.bloom[0], keys0, am) : pc_bloom8_keys<false>(P.bloom[0], keys0, am);
+			else
+				am = P.bloom[f].width == 8 ? pc_early_filter8<true>(P.bloom[f], base + o0, full, am, pol_stream)
+					: pc_early_filter8<false>(P.bloom[f], base + o0, full, am, pol_stream);
+		}
 		__syncthreads();				/* s_cnt = 0 is in */
 		{
 			/* the tile's survivors, in row order within each warp: one scan + one shared atomic per warp */
@@ -974,19 +1014,23 @@ k_prefilter(const __grid_constant__ PfParams P)
 
 /*
  * The same filter pass fed by a TMA ring (the shape of k_scan_agg_small): one persistent CTA per SM; a producer warp streams
- * every column the filters read - qual columns and filter key columns, a 4096-row tile at a time - into a ring of
- * shared-memory stages with bulk copies (cp.async.bulk + mbarrier), as many stages as fit ~200 KB, so HBM streams at
- * full rate whatever the consumers do.  16 consumer warps evaluate the quals from shared memory and look the keys up in the
- * Bloom filters (L2-resident, evict_last); each thread owns 8 rows of a tile, so 8 filter words are in flight per thread.
- * Survivors are compacted per tile in shared memory (32-row runs stay in row order) and appended with one global atomic.
+ * every column the filters read - qual columns and filter key columns, a 1024-row tile at a time - into a ring of
+ * shared-memory stages with bulk copies (cp.async.bulk + mbarrier), as many stages as fit ~168 KB, so HBM streams at
+ * full rate whatever the consumers do.  Seven independent consumer groups of four warps take the tiles in turn (a tile's
+ * critical path is one L2 round trip per Bloom filter: seven tiles in flight hide it); each thread owns 8 rows of its
+ * group's tile, so 8 filter words are in flight per thread.  A group collects its survivors in shared memory (32-row runs
+ * stay in row order) and appends them to the output with one global atomic per ~1000 survivors, not per tile.
  * The load-and-test version above (k_prefilter) needs one HBM latency per filter column and one L2 latency per filter,
- * one after the other, per tile: it ran at 2 - 4 TB/s; this one is bound by the stream.
+ * one after the other, per tile: it ran at 2 - 4 TB/s.
  */
-#define PFT_TILE 4096
-#define PFT_NCONS 512
+#define PFT_TILE 1024
+#define PFT_GROUPS 7
+#define PFT_GTHREADS 128
+#define PFT_NCONS (PFT_GROUPS * PFT_GTHREADS)
+#define PFT_OBUF 1536			/* survivors a group holds back; flushed when a tile might not fit any more */
 #define PFT_MAXCOLS 8
-#define PFT_MAXSTAGES 8
-#define PFT_SMEM_BUDGET (200 * 1024)
+#define PFT_MAXSTAGES 28
+#define PFT_SMEM_BUDGET (168 * 1024)
 
 struct PftCol
 {
@@ -1021,9 +1065,9 @@ k_prefilter_tma(const __grid_constant__ PftParams P)
 	extern __shared__ __align__(128) unsigned char pft_smem[];
 	__shared__ uint64_t full_bar[PFT_MAXSTAGES];
 	__shared__ uint64_t empty_bar[PFT_MAXSTAGES];
-	__shared__ uint32_t obuf[PFT_TILE];
-	__shared__ unsigned s_cnt[2];
-	__shared__ unsigned long long s_gbase;
+	__shared__ uint32_t obuf[PFT_GROUPS][PFT_OBUF];
+	__shared__ unsigned s_cnt[PFT_GROUPS];
+	__shared__ unsigned long long s_gbase[PFT_GROUPS];
 	const int	warp = threadIdx.x >> 5;
 	const int	lane = threadIdx.x & 31;
 	const int64_t ntiles = (P.nrows + PFT_TILE - 1) / PFT_TILE;
@@ -1034,9 +1078,10 @@ k_prefilter_tma(const __grid_constant__ PftParams P)
 		for (int s = 0; s < nst; s++)
 		{
 			mbar_init(&full_bar[s], 1);
-			mbar_init(&empty_bar[s], PFT_NCONS / 32);
+			mbar_init(&empty_bar[s], PFT_GTHREADS / 32);
 		}
-		s_cnt[0] = s_cnt[1] = 0;
+		for (int g = 0; g < PFT_GROUPS; g++)
+			s_cnt[g] = 0;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -1068,13 +1113,17 @@ k_prefilter_tma(const __grid_constant__ PftParams P)
 		}
 		return;
 	}
-	/* ---- consumers ---- */
+	/* ---- consumers: group g takes the CTA's tiles g, g + 7, g + 14, ... ---- */
 	{
-		const int	ct = threadIdx.x - 32;
+		const int	g = (threadIdx.x - 32) / PFT_GTHREADS;
+		const int	ct = (threadIdx.x - 32) % PFT_GTHREADS;
 		const uint64_t pol_keep = l2_policy_evict_last();
-		int			it = 0;
+		uint32_t   *const ob = obuf[g];
+		unsigned   *const cnt = &s_cnt[g];
+		const int	bar_id = 1 + g;
+		int			it = g;
 
-		for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, it++)
+		for (int64_t t = blockIdx.x + (int64_t) g * gridDim.x; t < ntiles; t += (int64_t) PFT_GROUPS * gridDim.x, it += PFT_GROUPS)
 		{
 			const int	s = it % nst;
 			const unsigned ph = (unsigned) (it / nst) & 1;
@@ -1087,7 +1136,7 @@ k_prefilter_tma(const __grid_constant__ PftParams P)
 #pragma unroll
 			for (int j = 0; j < 8; j++)
 			{
-				const int	r = ct + j * PFT_NCONS;
+				const int	r = ct + j * PFT_GTHREADS;
 				bool		alive = r < rows;
 
 				if (alive && P.visimap)
@@ -1111,7 +1160,7 @@ k_prefilter_tma(const __grid_constant__ PftParams P)
 #pragma unroll
 				for (int j = 0; j < 8; j++)
 				{
-					const int	r = ct + j * PFT_NCONS;
+					const int	r = ct + j * PFT_GTHREADS;
 					uint32_t	w = 0;
 
 					bits[j] = 0;
@@ -1134,41 +1183,40 @@ k_prefilter_tma(const __grid_constant__ PftParams P)
 			__syncwarp();
 			if (lane == 0)
 				mbar_arrive(&empty_bar[s]);
-			/* survivors -> obuf: a warp's 32 consecutive rows of one j stay in order.  Two counters take turns, so that the
-			 * one the next tile will use can be zeroed while this tile's is being read */
-			{
-				unsigned   *cnt = &s_cnt[it & 1];
-
+			/* survivors -> the group's buffer: a warp's 32 consecutive rows of one j stay in order */
 #pragma unroll
-				for (int j = 0; j < 8; j++)
-				{
-					const unsigned m = __ballot_sync(0xffffffffu, (am >> j) & 1);
-					unsigned	wb = 0;
+			for (int j = 0; j < 8; j++)
+			{
+				const unsigned m = __ballot_sync(0xffffffffu, (am >> j) & 1);
+				unsigned	wb = 0;
 
-					if (m == 0)
-						continue;
-					if (lane == 0)
-						wb = atomicAdd(cnt, (unsigned) __popc(m));
-					wb = __shfl_sync(0xffffffffu, wb, 0);
-					if ((am >> j) & 1)
-						obuf[wb + __popc(m & ((1u << lane) - 1))] = (uint32_t) (r0 + ct + j * PFT_NCONS);
+				if (m == 0)
+					continue;
+				if (lane == 0)
+					wb = atomicAdd(cnt, (unsigned) __popc(m));
+				wb = __shfl_sync(0xffffffffu, wb, 0);
+				if ((am >> j) & 1)
+					ob[wb + __popc(m & ((1u << lane) - 1))] = (uint32_t) (r0 + ct + j * PFT_GTHREADS);
+			}
+			asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(PFT_GTHREADS) : "memory");	/* every push of this tile is in */
+			/* flush when the next tile might not fit, and after the group's last tile */
+			if (*cnt > PFT_OBUF - PFT_TILE || t + (int64_t) PFT_GROUPS * gridDim.x >= ntiles)
+			{
+				const unsigned n = *cnt;
+
+				if (ct == 0 && n)
+					s_gbase[g] = atomicAdd(P.out_count, (unsigned long long) n);
+				asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(PFT_GTHREADS) : "memory");
+				{
+					const unsigned long long gb = s_gbase[g];
+
+					for (unsigned i = ct; i < n; i += PFT_GTHREADS)
+						P.out[gb + i] = ob[i];
 				}
-				asm volatile("bar.sync 1, %0;" :: "r"(PFT_NCONS) : "memory");	/* every push of this tile is in */
+				asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(PFT_GTHREADS) : "memory");	/* the buffer is free */
 				if (ct == 0)
-				{
-					if (*cnt)
-						s_gbase = atomicAdd(P.out_count, (unsigned long long) *cnt);
-					s_cnt[(it + 1) & 1] = 0;
-				}
-				asm volatile("bar.sync 1, %0;" :: "r"(PFT_NCONS) : "memory");
-				{
-					const unsigned n = *cnt;
-					const unsigned long long gb = s_gbase;
-
-					for (unsigned i = ct; i < n; i += PFT_NCONS)
-						P.out[gb + i] = obuf[i];
-				}
-				asm volatile("bar.sync 1, %0;" :: "r"(PFT_NCONS) : "memory");	/* obuf is free for the next tile */
+					*cnt = 0;
+				asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(PFT_GTHREADS) : "memory");
 			}
 		}
 	}
@@ -1971,10 +2019,11 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 			CB_CUDA(ctx, cudaMemsetAsync(pf_count, 0, sizeof(unsigned long long), ctx->stream));
 			F.out = pf_sel;
 			F.out_count = pf_count;
+			const int	pkl = cb_klog_begin(ctx, "k_prefilter");
 			{
 				/* the TMA-fed version when the filters' columns fit the ring (they do unless there are many wide ones) */
 				PftParams  *Tp = (PftParams *) cb_scratch(ctx, 7, sizeof(PftParams));
-				bool		tma = Tp != NULL && !ctx->opt_prefilter_ldg;
+				bool		tma = Tp != NULL && ctx->opt_prefilter_tma;
 
 				if (tma)
 				{
@@ -2038,10 +2087,19 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 				}
 				if (!tma)
 				{
-					k_prefilter<<<fb, PC_THREADS, 0, ctx->stream>>>(F);
+					/* 32 registers per thread: all 64 warps of an SM resident.  (Tried: 6 CTAs at 40 registers - slower; the first
+					 * filter's keys requested together with the qual columns, 64 registers, 4 CTAs - slower still: this pass
+					 * lives on occupancy.) */
+					if (ctx->opt_pf_spec)
+						k_prefilter<true, 4><<<ctx->sm_count * 4 < ft ? ctx->sm_count * 4 : (int) ft, PC_THREADS, 0, ctx->stream>>>(F);
+					else if (ctx->opt_pf_occ6)
+						k_prefilter<false, 6><<<fb, PC_THREADS, 0, ctx->stream>>>(F);
+					else
+						k_prefilter<false, 8><<<ctx->sm_count * 8 < ft ? ctx->sm_count * 8 : (int) ft, PC_THREADS, 0, ctx->stream>>>(F);
 					CB_LAUNCHED(ctx, "k_prefilter");
 				}
 			}
+			cb_klog_end(ctx, pkl);
 			CB_CUDA(ctx, cudaMemcpyAsync(&nsel, pf_count, sizeof(nsel), cudaMemcpyDeviceToHost, ctx->stream));
 			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			if (ctx->opt_debug)
