@@ -42,6 +42,10 @@
 #include "fmgr.h"
 #include "miscadmin.h"
 #include "nodes/execnodes.h"
+#include "nodes/extensible.h"
+#include "nodes/makefuncs.h"
+#include "optimizer/planner.h"
+#include "utils/guc.h"
 #include "nodes/nodeFuncs.h"
 #include "nodes/plannodes.h"
 #include "nodes/primnodes.h"
@@ -779,14 +783,13 @@ plan_has_motion(Plan *plan)
 			shim_release(shim); \
 		if (has_motion) \
 			ereport(ERROR, (errcode(ERRCODE_INTERNAL_ERROR), errmsg(__VA_ARGS__))); \
-		return false; \
+		return NULL; \
 	} while (0)
 
+/* the next row of the device sub-tree into `slot` (empty at end of data): shared by both routes */
 static TupleTableSlot *
-cbgpu_ExecNode(PlanState *ps)			/* ExecProcNodeMtd, nodes/execnodes.h:1056 */
+shim_next_tuple(CbgpuShim *shim, TupleTableSlot *slot)
 {
-	CbgpuShim  *shim = shim_of(ps);
-	TupleTableSlot *slot = ps->ps_ResultTupleSlot;
 	CbTupleTableSlot *cs;
 
 	CHECK_FOR_INTERRUPTS();				/* miscadmin.h */
@@ -838,21 +841,28 @@ cbgpu_ExecNode(PlanState *ps)			/* ExecProcNodeMtd, nodes/execnodes.h:1056 */
 	return ExecStoreVirtualTuple(slot);
 }
 
-/* try to take over the sub-tree rooted at ps; true when its ExecProcNode now points at the GPU path */
-static bool
-shim_take_over(PlanState *ps, EState *estate)
+static TupleTableSlot *
+cbgpu_ExecNode(PlanState *ps)			/* ExecProcNodeMtd, nodes/execnodes.h:1056 */
+{
+	return shim_next_tuple(shim_of(ps), ps->ps_ResultTupleSlot);
+}
+
+/* everything a sub-tree needs before its first row: translation, device context, executor state, base tables on the device,
+ * string literals as dictionary codes, interconnect, the result's column types.  NULL: the sub-tree stays with the CPU
+ * executor (or, with Motions below and a local failure, the query ends in an error: see SHIM_LOCAL_FAILURE) */
+static CbgpuShim *
+shim_prepare(Plan *plan, TupleDesc desc, EState *estate)
 {
 	List	   *rels = NIL;
-	CbPlan	   *cplan = (pending_consts = NIL, translate_plan(ps->plan, estate, &rels));
+	CbPlan	   *cplan = (pending_consts = NIL, translate_plan(plan, estate, &rels));
 	CbgpuShim  *shim;
 	ListCell   *lc;
 	int			i = 0;
-	TupleDesc	desc = ps->ps_ResultTupleSlot ? ps->ps_ResultTupleSlot->tts_tupleDescriptor : NULL;
-	const bool	has_motion = plan_has_motion(ps->plan);
+	const bool	has_motion = plan_has_motion(plan);
 
 	/* 1. decisions that follow from the plan alone (the same on every segment): translation, node support */
 	if (cplan == NULL || desc == NULL || !resolve_plan(cplan))
-		return false;
+		return NULL;
 	if (shim_ctx == NULL && cbgpu_ctx_create(GpIdentity.segindex >= 0 ? GpIdentity.segindex % Max(cbgpu_device_count(), 1) : 0, &shim_ctx) != CBGPU_OK)
 		SHIM_LOCAL_FAILURE(has_motion, (CbgpuShim *) NULL, "cbgpu: no CUDA context on segment %d", GpIdentity.segindex);
 	shim = (CbgpuShim *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(CbgpuShim));
@@ -864,7 +874,7 @@ shim_take_over(PlanState *ps, EState *estate)
 	if (shim->cbps == NULL)
 	{
 		shim_release(shim);
-		return false;
+		return NULL;
 	}
 	/* 2. from here on this segment is committed: load the base tables (device memory the shim owns from now on) */
 	foreach(lc, rels)
@@ -903,12 +913,23 @@ shim_take_over(PlanState *ps, EState *estate)
 			TupleDescAttr(desc, a)->atttypid != NUMERICOID)
 		{
 			shim_release(shim);
-			return false;
+			return NULL;
 		}
 	/* device state goes away with the query context, error or not (utils/palloc.h MemoryContextRegisterResetCallback) */
 	shim->reset_cb.func = shim_release;
 	shim->reset_cb.arg = shim;
 	MemoryContextRegisterResetCallback(estate->es_query_cxt, &shim->reset_cb);
+	return shim;
+}
+
+/* route 2: try to take over the sub-tree rooted at ps; true when its ExecProcNode now points at the GPU path */
+static bool
+shim_take_over(PlanState *ps, EState *estate)
+{
+	CbgpuShim  *shim = shim_prepare(ps->plan, ps->ps_ResultTupleSlot ? ps->ps_ResultTupleSlot->tts_tupleDescriptor : NULL, estate);
+
+	if (shim == NULL)
+		return false;
 	{
 		ShimEntry  *e = (ShimEntry *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(ShimEntry));
 
@@ -942,6 +963,168 @@ shim_walk(PlanState *ps, EState *estate, bool may_rescan)
 		return;					/* the whole sub-tree is the GPU's: do not descend */
 	shim_walk(outerPlanState(ps), estate, may_rescan);
 	shim_walk(innerPlanState(ps), estate, may_rescan || IsA(ps, NestLoopState) || IsA(ps, MergeJoinState));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * route 1: the sub-tree as a CustomScan node (nodes/extensible.h:108-154, plannodes.h:1079).
+ *
+ * With cbgpu.route = 'customscan' the planner hook wraps every top-most translatable sub-tree of the finished plan in a
+ * CustomScan: custom_plans keeps the original sub-tree (EXPLAIN shows it, and it is what BeginCustomScan translates),
+ * custom_scan_tlist describes the tuple it returns, the node's own target list is plain INDEX_VAR references to that.
+ * What this route has over the ExecProcNode swap (route 2): the executor knows the node - ReScanCustomScan gives
+ * rescans (cb_ExecReScan resets the device sub-tree), EXPLAIN names it, and no PlanState pointer is overwritten.
+ * Same device path underneath: shim_prepare / shim_next_tuple.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct CbgpuScanState
+{
+	CustomScanState css;		/* must be first */
+	CbgpuShim  *shim;
+} CbgpuScanState;
+
+static Node *cbgpu_create_scan_state(CustomScan *cscan);
+static void cbgpu_begin_scan(CustomScanState *node, EState *estate, int eflags);
+static TupleTableSlot *cbgpu_exec_scan(CustomScanState *node);
+static void cbgpu_end_scan(CustomScanState *node);
+static void cbgpu_rescan_scan(CustomScanState *node);
+
+static const CustomScanMethods cbgpu_scan_methods = {"cbgpu", cbgpu_create_scan_state};
+static const CustomExecMethods cbgpu_exec_methods = {
+	.CustomName = "cbgpu",
+	.BeginCustomScan = cbgpu_begin_scan,
+	.ExecCustomScan = cbgpu_exec_scan,
+	.EndCustomScan = cbgpu_end_scan,
+	.ReScanCustomScan = cbgpu_rescan_scan,
+};
+
+static Node *
+cbgpu_create_scan_state(CustomScan *cscan)
+{
+	CbgpuScanState *st = (CbgpuScanState *) newNode(sizeof(CbgpuScanState), T_CustomScanState);
+
+	(void) cscan;
+	st->css.methods = &cbgpu_exec_methods;
+	return (Node *) st;
+}
+
+static void
+cbgpu_begin_scan(CustomScanState *node, EState *estate, int eflags)
+{
+	CbgpuScanState *st = (CbgpuScanState *) node;
+	CustomScan *cscan = (CustomScan *) node->ss.ps.plan;
+	Plan	   *subtree = (Plan *) linitial(cscan->custom_plans);
+
+	if (eflags & EXEC_FLAG_EXPLAIN_ONLY)
+		return;
+	/* the scan tuple is the sub-tree's result (custom_scan_tlist): ExecInitCustomScan built ss_ScanTupleSlot from it */
+	st->shim = shim_prepare(subtree, node->ss.ss_ScanTupleSlot->tts_tupleDescriptor, estate);
+	if (st->shim == NULL)
+		ereport(ERROR, (errcode(ERRCODE_FEATURE_NOT_SUPPORTED),
+						errmsg("cbgpu: the sub-tree wrapped at plan time cannot run on the device on segment %d", GpIdentity.segindex)));
+}
+
+static TupleTableSlot *
+cbgpu_exec_scan(CustomScanState *node)
+{
+	CbgpuScanState *st = (CbgpuScanState *) node;
+	TupleTableSlot *slot = shim_next_tuple(st->shim, node->ss.ss_ScanTupleSlot);
+
+	if (TupIsNull(slot))
+		return NULL;
+	/* the node's own target list is one INDEX_VAR per scan column: project only if the planner put something else there */
+	if (node->ss.ps.ps_ProjInfo)
+	{
+		node->ss.ps.ps_ExprContext->ecxt_scantuple = slot;
+		return ExecProject(node->ss.ps.ps_ProjInfo);
+	}
+	return slot;
+}
+
+static void
+cbgpu_end_scan(CustomScanState *node)
+{
+	CbgpuScanState *st = (CbgpuScanState *) node;
+
+	if (st->shim)
+		shim_release(st->shim);		/* idempotent: the query context's reset callback may run it again */
+	st->shim = NULL;
+}
+
+static void
+cbgpu_rescan_scan(CustomScanState *node)
+{
+	CbgpuScanState *st = (CbgpuScanState *) node;
+
+	/* ExecReScan (execAmi.c:77) reaches us through ExecReScanCustomScan: start the device sub-tree over */
+	if (st->shim && st->shim->cbps)
+		cb_ExecReScan(st->shim->cbps);
+}
+
+/* can translate_plan take this sub-tree?  (plan-time check: no estate, nothing is loaded) */
+static bool
+subtree_translatable(Plan *plan)
+{
+	List	   *rels = NIL;
+	CbPlan	   *c;
+
+	if (plan == NULL || !bms_is_empty(plan->allParam) || !(IsA(plan, Agg) || IsA(plan, HashJoin) || IsA(plan, Motion)))
+		return false;				/* bare scans are not worth a device round trip */
+	pending_consts = NIL;
+	c = translate_plan(plan, NULL, &rels);
+	pending_consts = NIL;
+	return c != NULL && resolve_plan(c);
+}
+
+static Plan *
+wrap_subtrees(Plan *plan)
+{
+	if (plan == NULL)
+		return NULL;
+	if (subtree_translatable(plan))
+	{
+		CustomScan *cs = makeNode(CustomScan);
+		ListCell   *lc;
+		int			resno = 1;
+
+		cs->scan.plan.startup_cost = plan->startup_cost;
+		cs->scan.plan.total_cost = plan->total_cost;
+		cs->scan.plan.plan_rows = plan->plan_rows;
+		cs->scan.plan.plan_width = plan->plan_width;
+		cs->scan.plan.flow = plan->flow;
+		cs->scan.scanrelid = 0;			/* not a base relation scan: the tuple is described by custom_scan_tlist */
+		cs->flags = 0;
+		cs->custom_plans = list_make1(plan);
+		cs->custom_scan_tlist = plan->targetlist;
+		foreach(lc, plan->targetlist)
+		{
+			TargetEntry *te = (TargetEntry *) lfirst(lc);
+			Var		   *v = makeVar(INDEX_VAR, resno, exprType((Node *) te->expr), exprTypmod((Node *) te->expr),
+									exprCollation((Node *) te->expr), 0);
+
+			cs->scan.plan.targetlist = lappend(cs->scan.plan.targetlist, makeTargetEntry((Expr *) v, resno, te->resname, te->resjunk));
+			resno++;
+		}
+		cs->methods = &cbgpu_scan_methods;
+		return &cs->scan.plan;
+	}
+	plan->lefttree = wrap_subtrees(plan->lefttree);
+	/* the inner side of a NestLoop / MergeJoin is rescanned per outer row or restored to a mark: leave it to the CPU */
+	if (!IsA(plan, NestLoop) && !IsA(plan, MergeJoin))
+		plan->righttree = wrap_subtrees(plan->righttree);
+	return plan;
+}
+
+static planner_hook_type prev_planner = NULL;
+static char *cbgpu_route = NULL;		/* GUC cbgpu.route: "execprocnode" (default) or "customscan" */
+
+static PlannedStmt *
+cbgpu_planner(Query *parse, const char *query_string, int cursorOptions, ParamListInfo boundParams, OptimizerOptions *optimizer_options)
+{
+	PlannedStmt *stmt = prev_planner ? prev_planner(parse, query_string, cursorOptions, boundParams, optimizer_options)
+		: standard_planner(parse, query_string, cursorOptions, boundParams, optimizer_options);
+
+	if (stmt && stmt->commandType == CMD_SELECT && cbgpu_route && strcmp(cbgpu_route, "customscan") == 0)
+		stmt->planTree = wrap_subtrees(stmt->planTree);
+	return stmt;
 }
 
 /* dispatcher-side bookkeeping for the interconnect token: how many counted queries are between ExecutorStart and ExecutorEnd */
@@ -998,7 +1181,8 @@ cbgpu_ExecutorStart(QueryDesc *queryDesc, int eflags)
 		prev_ExecutorStart(queryDesc, eflags);
 	else
 		standard_ExecutorStart(queryDesc, eflags);
-	if (!(eflags & EXEC_FLAG_EXPLAIN_ONLY))
+	/* route 2 swaps ExecProcNode pointers of the started plan; with route 1 the planner hook has wrapped the sub-trees already */
+	if (!(eflags & EXEC_FLAG_EXPLAIN_ONLY) && !(cbgpu_route && strcmp(cbgpu_route, "customscan") == 0))
 		shim_walk(queryDesc->planstate, queryDesc->estate, (eflags & (EXEC_FLAG_REWIND | EXEC_FLAG_BACKWARD | EXEC_FLAG_MARK)) != 0);
 }
 
@@ -1011,4 +1195,11 @@ _PG_init(void)
 	ExecutorEnd_hook = cbgpu_ExecutorEnd;
 	RegisterXactCallback(cbgpu_xact_callback, NULL);
 	cbgpu_shim_define_gucs();
+	/* route 1: a CustomScan provider (RegisterCustomScanMethods lets the node be read back from a serialised plan on the
+	 * QEs: nodes/readfuncs.c looks the methods up by name) and the planner hook that wraps sub-trees when asked to */
+	RegisterCustomScanMethods(&cbgpu_scan_methods);
+	DefineCustomStringVariable("cbgpu.route", "how GPU sub-trees enter the plan: execprocnode (default) or customscan", NULL,
+							   &cbgpu_route, "execprocnode", PGC_USERSET, 0, NULL, NULL, NULL);
+	prev_planner = planner_hook;
+	planner_hook = cbgpu_planner;
 }

@@ -118,6 +118,7 @@ void	   *MemoryContextAllocZeroAligned(MemoryContext context, Size size) { retur
 void		check_stack_depth(void) {}
 ExecutorStart_hook_type ExecutorStart_hook = NULL;
 ExecutorEnd_hook_type ExecutorEnd_hook = NULL;
+planner_hook_type planner_hook = NULL;
 GpId		GpIdentity = {0};
 GpRoleValue Gp_role = GP_ROLE_UTILITY;
 
@@ -519,6 +520,58 @@ ref_plan_translate(const char *which, const char *text, int a, int b, int c)
 		out = NULL;
 	last_pending = pending_consts;
 	return out;
+}
+
+/* Route 1: what the planner hook does to the same plans - wrap_subtrees() must put ONE CustomScan on top (every harness plan
+ * is translatable as a whole), keep the original sub-tree in custom_plans, describe the tuple with custom_scan_tlist and give the
+ * node a target list of INDEX_VAR references of the right types.  Returns the number of columns, or a negative code. */
+int
+ref_plan_wrap(const char *which, const char *text, int a, int b, int c)
+{
+	Plan	   *p,
+			   *w;
+	CustomScan *cs;
+	ListCell   *lc,
+			   *lo;
+	int			n = 0;
+
+	if (setjmp(*ref_exec_jmp()) != 0)
+		return -100;
+	next_plan_id = 0;
+	if (strcmp(which, "q1") == 0)
+		p = build_q1(a, b);
+	else if (strcmp(which, "q3") == 0)
+		p = build_q3(text, b);
+	else if (strcmp(which, "q5") == 0)
+		p = build_q5(text, b, c);
+	else
+		return -1;
+	w = wrap_subtrees(p);
+	if (w == NULL || !IsA(w, CustomScan))
+		return -2;
+	cs = (CustomScan *) w;
+	if (list_length(cs->custom_plans) != 1 || linitial(cs->custom_plans) != (void *) p || cs->custom_scan_tlist != p->targetlist ||
+		cs->methods != &cbgpu_scan_methods || cs->scan.scanrelid != 0)
+		return -3;
+	if (list_length(cs->scan.plan.targetlist) != list_length(p->targetlist))
+		return -4;
+	forboth(lc, cs->scan.plan.targetlist, lo, p->targetlist)
+	{
+		TargetEntry *te = (TargetEntry *) lfirst(lc);
+		Var		   *v = (Var *) te->expr;
+
+		n++;
+		if (!IsA(v, Var) || v->varno != INDEX_VAR || v->varattno != n || te->resno != n ||
+			v->vartype != exprType((Node *) ((TargetEntry *) lfirst(lo))->expr))
+			return -5;
+	}
+	/* and what BeginCustomScan would translate is still the plan the other route takes */
+	last_rels = NIL;
+	pending_consts = NIL;
+	if (translate_plan((Plan *) linitial(cs->custom_plans), NULL, &last_rels) == NULL)
+		return -6;
+	pending_consts = NIL;
+	return n;
 }
 
 /* the i-th scan of the translated tree (= range-table index i + 1 of the CbPlan): the reference range-table index it reads

@@ -18,6 +18,9 @@ REF_STUB(MemoryContextRegisterResetCallback)
 REF_STUB(RegisterXactCallback)
 REF_STUB(standard_ExecutorStart)
 REF_STUB(standard_ExecutorEnd)
+REF_STUB(standard_planner)
+REF_STUB(RegisterCustomScanMethods)
+REF_STUB(DefineCustomStringVariable)
 REF_STUB(getgpsegmentCount)
 REF_STUB(get_opcode)
 REF_STUB(get_rel_name)
@@ -44,6 +47,7 @@ REF_STUB(cb_CreateExecutorState)
 REF_STUB(cb_ExecEndNode)
 REF_STUB(cb_ExecInitNode)
 REF_STUB(cb_ExecProcNode)
+REF_STUB(cb_ExecReScan)
 REF_STUB(cb_FreeExecutorState)
 REF_STUB(cb_estate_error)
 REF_STUB(cb_slot_float8)

@@ -57,3 +57,16 @@ def test_q5_grouped_by_a_string_column(oracle, golden):
     assert sorted(s[0] for s in t.scans) == ["customer", "lineitem", "nation", "orders", "region", "supplier"]
     rt = t.range_table(rels, oracle.hashbpchar)
     assert tpch.format_q5(oracle.execute(t.plan, [rt]).rows, exp["dict"]["n_name_dict"]) == exp["q5"]
+
+
+def test_customscan_route_wraps_the_same_plans():
+    """route 1 of SURVEY.md 8b: the planner-hook side (wrap_subtrees) on the reference-built plans - one CustomScan on top, the
+    original sub-tree in custom_plans, custom_scan_tlist = its target list, INDEX_VAR references of the right types; and the wrapped
+    sub-tree is still what translate_plan takes (what BeginCustomScan does).  exprType / exprTypmod / exprCollation are the
+    reference's own (nodes/nodeFuncs.c compiled where it lies)."""
+    L = SP.lib()
+    L.ref_plan_wrap.argtypes = L.ref_plan_translate.argtypes
+    assert L.ref_plan_wrap(b"q1", None, 1, tpch.Q1_CUTOFF, 0) == 10
+    assert L.ref_plan_wrap(b"q1", None, 3, tpch.Q1_CUTOFF, 0) == 10
+    assert L.ref_plan_wrap(b"q3", b"MACHINERY", 0, tpch.date_to_days(1995, 3, 15), 0) == 4
+    assert L.ref_plan_wrap(b"q5", b"AMERICA", 0, tpch.date_to_days(1997, 1, 1), tpch.date_to_days(1998, 1, 1)) == 2
