@@ -74,6 +74,7 @@ struct cbgpu_ctx
 	/* pipelines whose prefilter pass cut too little (k_prefilter, probe_chain.cu): not tried again */
 	uint64_t	pf_cache[32];
 	int			pf_cache_n;
+	int			opt_pf_keep_div;	/* the prefilter's result is used when survivors * this <= rows (CBGPU_PREFILTER_KEEP_DIV, 12) */
 	int64_t		opt_pf_min_rows;	/* scans below this many rows stay in the fused kernel (CBGPU_PREFILTER_MIN_ROWS)        */
 	struct AggSnap *agg_snap;
 	void	   *small_dev;		/* device scratch of the small-group scan kernel, grown on demand              */

@@ -64,6 +64,7 @@ cbgpu_ctx_create(int device, cbgpu_ctx **out)
 	ctx->opt_no_prefilter = getenv("CBGPU_NO_PREFILTER") != NULL;
 	ctx->opt_prefilter_tma = getenv("CBGPU_PREFILTER_TMA") != NULL;
 	ctx->opt_pf_spec = getenv("CBGPU_PF_SPEC") != NULL;
+	ctx->opt_pf_keep_div = getenv("CBGPU_PREFILTER_KEEP_DIV") && atoi(getenv("CBGPU_PREFILTER_KEEP_DIV")) > 0 ? atoi(getenv("CBGPU_PREFILTER_KEEP_DIV")) : 12;
 	ctx->opt_pf_occ6 = getenv("CBGPU_PF_OCC6") != NULL;
 	ctx->opt_pf_min_rows = getenv("CBGPU_PREFILTER_MIN_ROWS") ? atoll(getenv("CBGPU_PREFILTER_MIN_ROWS")) : ((int64_t) 16 << 20);
 	ctx->opt_l2_direct = getenv("CBGPU_L2_DIRECT") != NULL;

@@ -2104,7 +2104,10 @@ cb_try_probe_chain(cbgpu_ctx *ctx, const CbPipeline *p, const PipeDev *d, bool *
 			CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 			if (ctx->opt_debug)
 				fprintf(stderr, "k_prefilter: %lld of %lld rows survive %d qual(s) + %d filter(s)\n", (long long) nsel, (long long) P.nrows, F.nfilters, F.nbloom);
-			if (nsel * 2 <= (unsigned long long) P.nrows)
+			/* worth it only when few rows survive: the chain over the survivors is latency-bound (about 0.14 ms per million rows)
+			 * and, run on its own, no longer hides behind the scan as it does inside the fused kernel.  Measured: 1.5 - 3 % of
+			 * the rows left (Q3 / Q5 / SSB fact scans) pays, 10 - 14 % does not */
+			if (nsel * (unsigned long long) ctx->opt_pf_keep_div <= (unsigned long long) P.nrows)
 			{
 				P.sel = pf_sel;
 				P.nrows = (int64_t) nsel;

@@ -213,10 +213,12 @@ def test_prefilter_pass_on_small_inputs(oracle):
     import os
     from cloudberry_b200 import tpch
     os.environ["CBGPU_PREFILTER_MIN_ROWS"] = "1"
+    os.environ["CBGPU_PREFILTER_KEEP_DIV"] = "1"         # use the survivors however many they are
     try:
         c = capi.Context(0)
     finally:
         del os.environ["CBGPU_PREFILTER_MIN_ROWS"]
+        del os.environ["CBGPU_PREFILTER_KEEP_DIV"]
     try:
         for jointype in (P.JOIN_INNER, P.JOIN_SEMI, P.JOIN_ANTI):
             for nf, nd, vis in ((5000, 40, 1.0), (100003, 30, 0.7), (2049, 1, 1.0), (5000, 0, 1.0)):
