@@ -639,7 +639,7 @@ ldg_stream_s64(const long long *a, uint64_t pol)
 {
 	long long	v;
 
-	asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
 	return v;
 }
 
