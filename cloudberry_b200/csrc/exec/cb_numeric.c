@@ -293,3 +293,233 @@ cb_numeric_avg_text(int64_t lo, int64_t hi, int32_t dscale, int64_t n, char *out
 	nd = big_to_digits(&q, digits);
 	put_decimal(digits, nd, rscale, neg && q.n != 0, out, outlen);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Partial aggregate states in the reference's serialised form.
+ *
+ * When a Partial Aggregate runs on the device and its Finalize stage on a CPU process (or the other way round), the
+ * state crosses the Motion as the `bytea` the aggregate's serialisation function makes (AGGSPLIT_INITIAL_SERIAL /
+ * FINAL_DESERIAL, nodes/nodes.h:977-1000):
+ *
+ *   numeric_avg_serialize (utils/adt/numeric.c:5025-5080; sum / avg over numeric):
+ *       int64 N | numeric_send(sumX) | int32 maxScale | int64 maxScaleCount | int64 NaNcount | int64 pInfcount | int64 nInfcount
+ *   int8_avg_serialize (numeric.c:5793; sum / avg over int8 with 128-bit states):
+ *       int64 N | numeric_send(sumX)
+ *   numeric_send (numeric.c:1069): int16 ndigits | int16 weight | int16 sign | int16 dscale | ndigits x int16 base-10000 digits
+ *
+ * all big-endian (pq_send*).  The device state (N, exact 128-bit sum scaled by 10^dscale) determines every field: the
+ * columns on this path have ONE display scale, so maxScale = dscale and maxScaleCount = N (numeric.c:4690-4705
+ * do_numeric_accum keeps the count of inputs at the largest scale seen), and NaN / infinity counts are 0 - the device has no
+ * such values.  sumX is normalised as make_result does (strip_var: no leading / trailing zero digits, weight 0 for zero).
+ * ------------------------------------------------------------------------------------------ */
+static int
+put_be16(uint8_t *out, int at, int v)
+{
+	out[at] = (uint8_t) ((unsigned) v >> 8);
+	out[at + 1] = (uint8_t) v;
+	return at + 2;
+}
+
+static int
+put_be64(uint8_t *out, int at, int64_t v)
+{
+	for (int i = 0; i < 8; i++)
+		out[at + i] = (uint8_t) ((uint64_t) v >> (56 - 8 * i));
+	return at + 8;
+}
+
+/* numeric_send of (hi:lo) * 10^-dscale; returns the new offset, or -1 when it does not fit `cap` */
+static int
+numeric_send_i128(int64_t lo, int64_t hi, int32_t dscale, uint8_t *out, int at, int cap)
+{
+	i128		sv = ((i128) hi << 64) | (u128) (uint64_t) lo;
+	const int	neg = sv < 0;
+	u128		v = neg ? (u128) (-sv) : (u128) sv;
+	const int	groups_after = (dscale + 3) / 4;
+	uint16_t	rev[16],
+				digits[16];
+	int			k = 0,
+				nd,
+				first = 0,
+				weight;
+	BigDec		b;
+
+	/* align the decimal point to a base-10000 digit boundary: value * 10^(4 * groups_after - dscale), in limbs (the product
+	 * can leave 128 bits) */
+	big_from_u128(&b, v);
+	for (int i = 0; i < 4 * groups_after - dscale; i++)
+		big_mul_small(&b, 10);
+	{
+		/* base 1e9 limbs -> decimal string -> groups of four from the right */
+		char		dec[MAXLIMBS * 9 + 2];
+		int			len = 0;
+
+		if (b.n == 0)
+			dec[len++] = '0';
+		else
+		{
+			len += snprintf(dec + len, sizeof(dec) - (size_t) len, "%u", b.l[b.n - 1]);
+			for (int i = b.n - 2; i >= 0; i--)
+				len += snprintf(dec + len, sizeof(dec) - (size_t) len, "%09u", b.l[i]);
+		}
+		for (int end = len; end > 0 && k < 16; end -= 4)
+		{
+			int			start = end - 4 < 0 ? 0 : end - 4;
+			int			g = 0;
+
+			for (int i = start; i < end; i++)
+				g = g * 10 + (dec[i] - '0');
+			rev[k++] = (uint16_t) g;
+		}
+	}
+	nd = k;
+	for (int i = 0; i < k; i++)
+		digits[i] = rev[k - 1 - i];
+	weight = nd - groups_after - 1;
+	while (first < nd && digits[first] == 0)
+	{
+		first++;
+		weight--;
+	}
+	while (nd > first && digits[nd - 1] == 0)
+		nd--;
+	if (nd == first)
+		weight = 0;				/* strip_var: zero has weight 0 and no digits */
+	if (at + 8 + 2 * (nd - first) > cap)
+		return -1;
+	at = put_be16(out, at, nd - first);
+	at = put_be16(out, at, weight);
+	at = put_be16(out, at, (nd > first && neg) ? 0x4000 : 0x0000);	/* NUMERIC_NEG / NUMERIC_POS */
+	at = put_be16(out, at, dscale);
+	for (int i = first; i < nd; i++)
+		at = put_be16(out, at, digits[i]);
+	return at;
+}
+
+int
+cb_numeric_avg_serialize(int64_t n, int64_t sum_lo, int64_t sum_hi, int32_t dscale, uint8_t *out, int32_t cap)
+{
+	int			at = 0;
+
+	if (cap < 8 || dscale < 0 || dscale > 0x3FFF || n < 0)
+		return -1;
+	at = put_be64(out, at, n);
+	at = numeric_send_i128(sum_lo, sum_hi, dscale, out, at, cap);
+	if (at < 0 || at + 4 + 4 * 8 > cap)
+		return -1;
+	/* maxScale: do_numeric_accum records the largest display scale seen, 0 before the first input */
+	out[at++] = 0;
+	out[at++] = 0;
+	at = put_be16(out, at, n > 0 ? dscale : 0);
+	at = put_be64(out, at, n > 0 ? n : 0);	/* maxScaleCount */
+	at = put_be64(out, at, 0);				/* NaNcount */
+	at = put_be64(out, at, 0);				/* pInfcount */
+	at = put_be64(out, at, 0);				/* nInfcount */
+	return at;
+}
+
+int
+cb_int8_avg_serialize(int64_t n, int64_t sum_lo, int64_t sum_hi, uint8_t *out, int32_t cap)
+{
+	int			at = 0;
+
+	if (cap < 8 || n < 0)
+		return -1;
+	at = put_be64(out, at, n);
+	at = numeric_send_i128(sum_lo, sum_hi, 0, out, at, cap);
+	return at;
+}
+
+static int64_t
+get_be64(const uint8_t *in)
+{
+	uint64_t	v = 0;
+
+	for (int i = 0; i < 8; i++)
+		v = (v << 8) | in[i];
+	return (int64_t) v;
+}
+
+static int
+get_be16(const uint8_t *in)
+{
+	return (int) (int16_t) (((unsigned) in[0] << 8) | in[1]);
+}
+
+/* the reverse (numeric_avg_deserialize numeric.c:5092 / int8_avg_deserialize): a state serialised by a CPU Partial Aggregate
+ * -> (N, 128-bit sum at display scale *dscale).  with_tail: numeric_avg_serialize's trailing fields are present and checked.
+ * Returns 0, or < 0: -1 malformed, -2 NaN / infinity inputs (no device representation), -3 the sum leaves 128 bits or carries
+ * more fractional digits than its display scale. */
+int
+cb_numeric_avg_deserialize(const uint8_t *in, int32_t len, int32_t with_tail, int64_t *n, int64_t *sum_lo, int64_t *sum_hi, int32_t *dscale)
+{
+	int			nd,
+				weight,
+				sign,
+				ds;
+	i128		v = 0;
+
+	if (len < 16)
+		return -1;
+	*n = get_be64(in);
+	nd = get_be16(in + 8);
+	weight = get_be16(in + 10);
+	sign = get_be16(in + 12) & 0xFFFF;
+	ds = get_be16(in + 14);
+	if (nd < 0 || 16 + 2 * nd + (with_tail ? 36 : 0) != len || ds < 0)
+		return -1;
+	if (sign != 0x0000 && sign != 0x4000)
+		return -2;				/* NUMERIC_NAN / infinities */
+	if (with_tail)
+	{
+		const uint8_t *t = in + 16 + 2 * nd;
+
+		if (get_be64(t + 12) != 0 || get_be64(t + 20) != 0 || get_be64(t + 28) != 0)
+			return -2;
+	}
+	/* value = sum digit[i] * 10000^(weight - i); scaled = value * 10^ds must be an integer that fits 127 bits */
+	for (int i = 0; i < nd; i++)
+	{
+		const int	e = 4 * (weight - i) + ds;
+		i128		d = get_be16(in + 16 + 2 * i);
+
+		if (d < 0 || d > 9999)
+			return -1;
+		if (e < 0)
+		{
+			i128		div = 1;
+
+			if (-e > 4)
+			{
+				if (d)
+					return -3;
+				continue;
+			}
+			for (int k = 0; k < -e; k++)
+				div *= 10;
+			if (d % div)
+				return -3;
+			d /= div;
+		}
+		else
+		{
+			if (e > 38)
+				return -3;
+			for (int k = 0; k < e; k++)
+			{
+				if (d > ((((i128) 1) << 126) / 10))
+					return -3;
+				d *= 10;
+			}
+		}
+		if (v > ((((i128) 1) << 126)) - d)
+			return -3;
+		v += d;
+	}
+	if (sign == 0x4000)
+		v = -v;
+	*sum_lo = (int64_t) (uint64_t) (u128) v;
+	*sum_hi = (int64_t) (v >> 64);
+	*dscale = ds;
+	return 0;
+}

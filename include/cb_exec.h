@@ -151,6 +151,16 @@ int			cb_slot_text(const CbTupleTableSlot *slot, int attno, char *buf, int bufle
  * select_div_scale :9194): exact text from (sum, dscale[, N]) */
 void		cb_numeric_sum_text(int64_t lo, int64_t hi, int32_t dscale, char *out, int32_t outlen);
 void		cb_numeric_avg_text(int64_t lo, int64_t hi, int32_t dscale, int64_t n, char *out, int32_t outlen);
+/* A partial aggregate state (N, exact 128-bit sum scaled by 10^dscale) as the bytea the reference's serialisation function
+ * makes of it, for a Finalize stage that runs on a CPU process behind a Motion - and back (AGGSPLIT_INITIAL_SERIAL /
+ * FINAL_DESERIAL, nodes/nodes.h:977-1000): numeric_avg_serialize / _deserialize (utils/adt/numeric.c:5025-5156) for sum / avg
+ * over numeric, int8_avg_serialize / _deserialize (numeric.c:5793-5870) for sum / avg over int8.  Serialise: the bytes written,
+ * or -1 when `cap` is too small.  Deserialise: 0, -1 malformed, -2 NaN / infinity inputs, -3 not representable as a 128-bit sum
+ * at its display scale. */
+int			cb_numeric_avg_serialize(int64_t n, int64_t sum_lo, int64_t sum_hi, int32_t dscale, uint8_t *out, int32_t cap);
+int			cb_int8_avg_serialize(int64_t n, int64_t sum_lo, int64_t sum_hi, uint8_t *out, int32_t cap);
+int			cb_numeric_avg_deserialize(const uint8_t *in, int32_t len, int32_t with_tail, int64_t *n, int64_t *sum_lo, int64_t *sum_hi,
+									   int32_t *dscale);
 
 /* ------------------------------------------------------------------------------------------
  * interconnect: what the reference reaches through MotionIPCLayer (include/cdb/ml_ipc.h:36)

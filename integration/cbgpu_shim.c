@@ -105,6 +105,9 @@ typedef struct CbgpuShim
 	int			natts;
 	CbTypeId   *atttypes;
 	int32	   *attdscales;
+	/* columns that leave as serialised partial aggregate states (the sub-tree's top is a Partial Aggregate whose Finalize
+	 * stage stays on the CPU): 0 plain value, 1 numeric_avg_serialize form, 2 int8_avg_serialize form */
+	int		   *attserial;
 	cbgpu_rel **rt;				/* the base tables loaded for this sub-tree: device memory this shim owns */
 	int			nrt;
 } CbgpuShim;
@@ -807,6 +810,24 @@ shim_next_tuple(CbgpuShim *shim, TupleTableSlot *slot)
 		return slot;					/* end of data: an empty slot (TupIsNull, executor/tuptable.h) */
 	for (int i = 0; i < shim->natts; i++)
 	{
+		if (shim->attserial[i] != 0)
+		{
+			/* (N, sum) -> the serialisation function's bytea; a state is never NULL once the group exists */
+			uint8		buf[256];
+			const int	len = shim->attserial[i] == 1
+				? cb_numeric_avg_serialize(cs->tts_state_n[i], cs->tts_state_lo[i], cs->tts_state_hi[i], shim->attdscales[i], buf, (int32) sizeof(buf))
+				: cb_int8_avg_serialize(cs->tts_state_n[i], cs->tts_state_lo[i], cs->tts_state_hi[i], buf, (int32) sizeof(buf));
+			bytea	   *b;
+
+			if (len < 0)
+				ereport(ERROR, (errcode(ERRCODE_INTERNAL_ERROR), errmsg("cbgpu: a partial aggregate state does not fit its serialised form")));
+			b = (bytea *) palloc(VARHDRSZ + len);
+			SET_VARSIZE(b, VARHDRSZ + len);
+			memcpy(VARDATA(b), buf, len);
+			slot->tts_isnull[i] = false;
+			slot->tts_values[i] = PointerGetDatum(b);
+			continue;
+		}
 		slot->tts_isnull[i] = cb_slot_isnull(cs, i);
 		if (slot->tts_isnull[i])
 		{
@@ -908,13 +929,30 @@ shim_prepare(Plan *plan, TupleDesc desc, EState *estate)
 	shim->natts = desc->natts;
 	shim->atttypes = (CbTypeId *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(CbTypeId) * Max(desc->natts, 1));
 	shim->attdscales = (int32 *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(int32) * Max(desc->natts, 1));
+	shim->attserial = (int *) MemoryContextAllocZero(estate->es_query_cxt, sizeof(int) * Max(desc->natts, 1));
 	for (int a = 0; a < desc->natts; a++)
+	{
+		if (TupleDescAttr(desc, a)->atttypid == BYTEAOID && IsA(plan, Agg) && DO_AGGSPLIT_SERIALIZE(((Agg *) plan)->aggsplit) &&
+			a < list_length(plan->targetlist) && IsA(((TargetEntry *) list_nth(plan->targetlist, a))->expr, Aggref))
+		{
+			/* a partial state on its way to a CPU Finalize stage: it leaves in the form the aggregate's serialisation function
+			 * gives it (pg_aggregate.dat serialfn; cb_numeric_avg_serialize / cb_int8_avg_serialize make the same bytes from
+			 * the device's (N, exact sum): tests/test_partial_state_serialize.py) */
+			Aggref	   *ar = (Aggref *) ((TargetEntry *) list_nth(plan->targetlist, a))->expr;
+			Oid			argtype = ar->aggargtypes != NIL ? linitial_oid(ar->aggargtypes) : InvalidOid;
+
+			shim->attserial[a] = argtype == NUMERICOID ? 1 : argtype == INT8OID ? 2 : 0;
+			shim->attdscales[a] = cplan->targetlist[a].expr->dscale;
+			if (shim->attserial[a] != 0)
+				continue;
+		}
 		if (!translate_type(TupleDescAttr(desc, a)->atttypid, TupleDescAttr(desc, a)->atttypmod, &shim->atttypes[a], &shim->attdscales[a]) &&
 			TupleDescAttr(desc, a)->atttypid != NUMERICOID)
 		{
 			shim_release(shim);
 			return NULL;
 		}
+	}
 	/* device state goes away with the query context, error or not (utils/palloc.h MemoryContextRegisterResetCallback) */
 	shim->reset_cb.func = shim_release;
 	shim->reset_cb.arg = shim;

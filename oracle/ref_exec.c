@@ -602,3 +602,102 @@ ref_int4_sum(const int32 *vals, int n, int64 *out)
 	*out = DatumGetInt64(state);
 	return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * partial aggregate states as the reference ships them between a Partial and a Finalize stage (serialfn / deserialfn of
+ * pg_aggregate.dat: numeric_avg_serialize / numeric_avg_deserialize for sum / avg over numeric, int8_avg_serialize /
+ * int8_avg_deserialize for sum / avg over int8) - the checker of cb_numeric_avg_serialize / cb_int8_avg_serialize /
+ * cb_numeric_avg_deserialize (csrc/exec/cb_numeric.c).
+ * ------------------------------------------------------------------------------------------ */
+static int
+bytea_out(Datum d, unsigned char *out, int cap)
+{
+	struct varlena *v = pg_detoast_datum((struct varlena *) DatumGetPointer(d));
+	int			len = (int) VARSIZE_ANY_EXHDR(v);
+
+	if (len > cap)
+		return -2;
+	memcpy(out, VARDATA_ANY(v), len);
+	return len;
+}
+
+static Datum
+unary_call(PGFunction f, Datum arg)
+{
+	LOCAL_FCINFO(fcinfo, 2);
+
+	InitFunctionCallInfoData(*fcinfo, NULL, 2, InvalidOid, NULL, NULL);
+	fcinfo->args[0].value = arg;
+	fcinfo->args[0].isnull = false;
+	fcinfo->args[1].value = (Datum) 0;	/* the deserialisation functions' dummy second argument */
+	fcinfo->args[1].isnull = false;
+	return (*f) (fcinfo);
+}
+
+/* Partial stage on the CPU: accumulate, then the serialisation function's bytea (its payload, without the varlena header) */
+int
+ref_numeric_avg_serialize(const char *const *vals, int n, unsigned char *out, int cap)
+{
+	Datum		state = (Datum) 0;
+	bool		isnull = true;
+
+	if (setjmp(ref_jmp))
+		return -1;
+	for (int i = 0; i < n; i++)
+		state = trans_call(numeric_avg_accum, state, isnull, num_in(vals[i]), &isnull);
+	if (isnull)
+		return -3;
+	return bytea_out(unary_call(numeric_avg_serialize, state), out, cap);
+}
+
+int
+ref_int8_avg_serialize(const int64 *vals, int n, unsigned char *out, int cap)
+{
+	Datum		state = (Datum) 0;
+	bool		isnull = true;
+
+	if (setjmp(ref_jmp))
+		return -1;
+	for (int i = 0; i < n; i++)
+		state = trans_call(int8_avg_accum, state, isnull, Int64GetDatum(vals[i]), &isnull);
+	if (isnull)
+		return -3;
+	return bytea_out(unary_call(int8_avg_serialize, state), out, cap);
+}
+
+static Datum
+make_bytea(const unsigned char *bytes, int len)
+{
+	struct varlena *v = (struct varlena *) palloc(VARHDRSZ + len);
+
+	SET_VARSIZE(v, VARHDRSZ + len);
+	memcpy(VARDATA(v), bytes, len);
+	return PointerGetDatum(v);
+}
+
+/* Finalize stage on the CPU over a state somebody else serialised: deserialise, then the final functions (sum and avg as text) */
+int
+ref_numeric_avg_finalize(const unsigned char *bytes, int len, char *sum_out, char *avg_out, int cap)
+{
+	Datum		state;
+
+	if (setjmp(ref_jmp))
+		return -1;
+	state = unary_call(numeric_avg_deserialize, make_bytea(bytes, len));
+	final_call(numeric_sum, state, false, sum_out, cap);
+	final_call(numeric_avg, state, false, avg_out, cap);
+	return 0;
+}
+
+int
+ref_int8_avg_finalize(const unsigned char *bytes, int len, char *sum_out, char *avg_out, int cap)
+{
+	Datum		state;
+
+	if (setjmp(ref_jmp))
+		return -1;
+	state = unary_call(int8_avg_deserialize, make_bytea(bytes, len));
+	final_call(numeric_poly_sum, state, false, sum_out, cap);
+	final_call(numeric_poly_avg, state, false, avg_out, cap);
+	return 0;
+}

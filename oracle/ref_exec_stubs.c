@@ -7,6 +7,12 @@
 extern void ref_exec_abort(const char *what);
 
 #define REF_STUB(name) void name(void); void name(void) { ref_exec_abort(#name); }
+/* libpq/pqformat.c and common/stringinfo.c are compiled in (the aggregate serialisation functions write their bytea through
+ * them); what THEY reference but this library never reaches: */
+REF_STUB(pg_server_to_client)
+REF_STUB(pg_client_to_server)
+REF_STUB(pvsnprintf)
+void	   *PqCommMethods = 0;
 REF_STUB(ArrayGetIntegerTypmods)
 REF_STUB(BackoffBackendTickExpired)
 REF_STUB(GetDefaultOpClass)
@@ -18,12 +24,10 @@ REF_STUB(ResolveOpClass)
 REF_STUB(SearchSysCacheList)
 REF_STUB(UpdateTimeAtomically)
 REF_STUB(addHyperLogLog)
-REF_STUB(appendBinaryStringInfo)
 REF_STUB(cdblegacyhash_null)
 REF_STUB(cstring_to_text)
 REF_STUB(cstring_to_text_with_len)
 REF_STUB(end_MultiFuncCall)
-REF_STUB(enlargeStringInfo)
 REF_STUB(estimateHyperLogLog)
 #ifndef REF_PLAN_LIB				/* libplan_ref.so links the reference's nodes/nodeFuncs.c, which defines these */
 REF_STUB(exprTypmod)
@@ -36,7 +40,6 @@ REF_STUB(get_opclass_family)
 REF_STUB(get_opfamily_member)
 REF_STUB(get_opfamily_proc)
 REF_STUB(initHyperLogLog)
-REF_STUB(initStringInfo)
 REF_STUB(init_MultiFuncCall)
 REF_STUB(lookup_type_cache)
 REF_STUB(per_MultiFuncCall)
@@ -45,13 +48,6 @@ REF_STUB(pg_mbcharcliplen)
 REF_STUB(pg_mbcliplen)
 REF_STUB(pg_mbstrlen_with_len)
 REF_STUB(pg_newlocale_from_collation)
-REF_STUB(pq_begintypsend)
-REF_STUB(pq_endtypsend)
-REF_STUB(pq_getmsgend)
-REF_STUB(pq_getmsgint)
-REF_STUB(pq_getmsgint64)
-REF_STUB(pq_getmsgtext)
-REF_STUB(pq_sendbytes)
 #ifndef REF_PLAN_LIB
 REF_STUB(relabel_to_typmod)
 #endif

@@ -49,6 +49,8 @@ REF_STUB(cb_ExecInitNode)
 REF_STUB(cb_ExecProcNode)
 REF_STUB(cb_ExecReScan)
 REF_STUB(cb_FreeExecutorState)
+REF_STUB(cb_numeric_avg_serialize)
+REF_STUB(cb_int8_avg_serialize)
 REF_STUB(cb_estate_error)
 REF_STUB(cb_slot_float8)
 REF_STUB(cb_slot_int64)
