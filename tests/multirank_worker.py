@@ -141,8 +141,27 @@ def main():
         print("MULTIRANK FAIL: query after a failed one returned %d rows" % len(rb.rows))
     exb.close()
     dbad.free()
+    # sorted Gather (Motion.sendSorted): every segment sends its local top 30 by (count desc, k), the receiver merges the
+    # streams on the device - between processes the rows arrive through the window's per-sender slots (or NCCL)
+    nsg = 20011
+    rng = np.random.default_rng(77 + rank)
+    tsg = HostRelation("sg", ["k", "v"], [P.INT4, P.INT8], [rng.integers(0, 300, nsg).astype(np.int32), rng.integers(0, 1000, nsg)])
+    dsg = capi.DeviceRelation.from_host(ctx, tsg)
+    exg = capi.Executor(ctx, [dsg], motion=motion)
+    scg = P.SeqScan(1, [("k", P.Var(1, 1, P.INT4)), ("v", P.Var(1, 2, P.INT8))])
+    agg_g = P.Agg(scg, P.AGG_HASHED, P.AGGSPLIT_SIMPLE, [1], [("k", P.out_var(scg, 1)), ("s", P.Aggref(P.AGG_SUM, P.out_var(scg, 2))),
+                                                                 ("n", P.Aggref(P.AGG_COUNT_STAR))], num_groups=512)
+    keys_g = [(3, True), (1, False)]
+    rsg = exg.run(P.Motion(P.LimitSort(agg_g, keys_g, 30), P.MOTIONTYPE_GATHER, sort_keys=keys_g))
+    if rank == 0:
+        order = [(-int(r[2]), int(r[0])) for r in rsg.rows]
+        if len(rsg.rows) != 30 * world or order != sorted(order):
+            ok = False
+            print("MULTIRANK FAIL: sorted Gather returned %d rows, in order: %s" % (len(rsg.rows), order == sorted(order)))
+    exg.close()
+    dsg.free()
     r1 = ex.run(tpch.q1_plan(world))
-    r3 = ex.run(tpch.q3_plan(seg, world, customer_replicated=replicated))
+    r3 = ex.run(tpch.q3_plan(seg, world, customer_replicated=replicated, merge_gather=True))
     r5 = ex.run(tpch.q5_plan(reg, world, replicated=replicated))
     if rank == 0:
         ok = ok and tpch.format_q1(r1.rows) == exp["q1"]
