@@ -332,7 +332,7 @@ put_be64(uint8_t *out, int at, int64_t v)
 static int
 numeric_send_i128(int64_t lo, int64_t hi, int32_t dscale, uint8_t *out, int at, int cap)
 {
-	i128		sv = ((i128) hi << 64) | (u128) (uint64_t) lo;
+	i128		sv = (i128) ((((u128) (uint64_t) hi) << 64) | (u128) (uint64_t) lo);
 	const int	neg = sv < 0;
 	u128		v = neg ? (u128) (-sv) : (u128) sv;
 	const int	groups_after = (dscale + 3) / 4;
@@ -519,7 +519,7 @@ cb_numeric_avg_deserialize(const uint8_t *in, int32_t len, int32_t with_tail, in
 	if (sign == 0x4000)
 		v = -v;
 	*sum_lo = (int64_t) (uint64_t) (u128) v;
-	*sum_hi = (int64_t) (v >> 64);
+	*sum_hi = (int64_t) (uint64_t) (((u128) v) >> 64);
 	*dscale = ds;
 	return 0;
 }

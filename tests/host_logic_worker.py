@@ -273,6 +273,47 @@ def main():
             rel.free()
         out["aocs_fuzz"] = {"calls": calls, "errors": errors}
     ctx.close()
+    # 6. partial aggregate states in the reference's serialised form (cb_numeric.c): round trips over exact-size malloc'd buffers,
+    #    then the deserialiser over damaged and random bytes - under the sanitizer build any read past the buffer shows
+    import ctypes as C
+    import random
+    E = capi.ex()
+    E.cb_numeric_avg_serialize.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]
+    E.cb_int8_avg_serialize.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32]
+    E.cb_numeric_avg_deserialize.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.POINTER(C.c_int64)] * 3 + [C.POINTER(C.c_int32)]
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    rnd = random.Random(5)
+    ser = {"roundtrips": 0, "refused": 0, "accepted_garbage": 0}
+    n_, lo_, hi_, ds_ = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+    for _ in range(300):
+        v = rnd.randrange(-(1 << 100), 1 << 100)
+        u = v & ((1 << 128) - 1)
+        lo, hi = u & ((1 << 64) - 1), u >> 64
+        lo, hi = (lo - (1 << 64) if lo >= 1 << 63 else lo), (hi - (1 << 64) if hi >= 1 << 63 else hi)
+        ds, cnt = rnd.randrange(0, 12), rnd.randrange(0, 1 << 40)
+        tmp = C.create_string_buffer(256)
+        k = E.cb_numeric_avg_serialize(cnt, lo, hi, ds, tmp, 256)
+        assert k > 0
+        buf = libc.malloc(k)                            # exact size: one byte too many read is a heap overflow report
+        C.memmove(buf, tmp, k)
+        assert E.cb_numeric_avg_deserialize(buf, k, 1, C.byref(n_), C.byref(lo_), C.byref(hi_), C.byref(ds_)) == 0
+        assert (n_.value, lo_.value, hi_.value, ds_.value) == (cnt, lo, hi, ds)
+        ser["roundtrips"] += 1
+        for cut in (0, 1, 8, 15, 16, k - 1):            # truncations
+            if cut < k and E.cb_numeric_avg_deserialize(buf, cut, 1, C.byref(n_), C.byref(lo_), C.byref(hi_), C.byref(ds_)) < 0:
+                ser["refused"] += 1
+        libc.free(buf)
+    for _ in range(3000):
+        k = rnd.randrange(0, 90)
+        buf = libc.malloc(max(k, 1))
+        C.memmove(buf, bytes(rnd.randrange(256) for _ in range(k)), k)
+        rc = E.cb_numeric_avg_deserialize(buf, k, rnd.randrange(2), C.byref(n_), C.byref(lo_), C.byref(hi_), C.byref(ds_))
+        ser["refused" if rc < 0 else "accepted_garbage"] += 1
+        libc.free(buf)
+    out["serialize"] = ser
     print("HOSTLOGIC " + json.dumps(out))
 
 

@@ -38,6 +38,9 @@ def _run(env):
 
 def _check(out):
     ran, refused = out["ran"], out["refused"]
+    # partial-state (de)serialisation: every round trip exact, every truncation refused, random bytes (almost) never a state
+    assert out["serialize"]["roundtrips"] == 300 and out["serialize"]["refused"] >= 300 * 5
+    assert out["serialize"]["accepted_garbage"] < 30
     for name in ("q1", "q3", "q5", "q1_generic", "q3_generic", "q5_generic", "q1_3seg", "q3_3seg", "q5_3seg",
                  "ssb_q4_1", "ssb_q4_2", "ssb_q4_3", "q1_after_refusals", "having"):
         assert ran[name]["rows"] == 0, name            # nothing is computed on the host: no kernel, no rows
