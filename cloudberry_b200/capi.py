@@ -29,9 +29,16 @@ class CbgpuVisimapEntry(C.Structure):
     _fields_ = [("first_row_num", C.c_int64), ("data", C.c_void_p), ("len", C.c_int32)]
 
 
+class CbAggStateDatum(C.Structure):
+    _fields_ = [("n", C.c_int64), ("lo", C.c_int64), ("hi", C.c_int64)]
+
+
+TUPSER_STATE_NUMERIC, TUPSER_STATE_INT8 = 101, 102
+
+
 class CbTupAttr(C.Structure):
     _fields_ = [("type", C.c_int32), ("dscale", C.c_int32), ("bpchar_len", C.c_int32), ("ntexts", C.c_int32),
-                ("texts", C.POINTER(C.c_char_p)), ("text_lens", C.POINTER(C.c_int32))]
+                ("texts", C.POINTER(C.c_char_p)), ("text_lens", C.POINTER(C.c_int32)), ("state", C.POINTER(CbAggStateDatum))]
 
 
 def _tup_attrs(attrs):
@@ -41,6 +48,10 @@ def _tup_attrs(attrs):
     keep = []
     for i, a in enumerate(attrs):
         arr[i].type, arr[i].dscale, arr[i].bpchar_len = a[0], a[1], a[2]
+        if a[0] in (TUPSER_STATE_NUMERIC, TUPSER_STATE_INT8):
+            st = CbAggStateDatum()
+            keep.append(st)
+            arr[i].state = C.pointer(st)
         texts = a[3] if len(a) > 3 and a[3] is not None else []
         if texts:
             bufs = [C.create_string_buffer(bytes(t), len(t)) for t in texts]
@@ -62,7 +73,15 @@ def tupser_rows(attrs, rows, nulls=None, max_chunk=8160, end=True):
     out = bytearray()
     buf = C.create_string_buffer(1 << 20)
     for r, row in enumerate(rows):
-        vals = (C.c_int64 * max(n, 1))(*[int(v) for v in row])
+        cells, held = [], []
+        for i, v in enumerate(row):
+            if attrs[i][0] in (TUPSER_STATE_NUMERIC, TUPSER_STATE_INT8) and v is not None:
+                st = CbAggStateDatum(*[int(x) for x in v])      # (N, lo, hi)
+                held.append(st)
+                cells.append(C.addressof(st))
+            else:
+                cells.append(0 if v is None else int(v))
+        vals = (C.c_int64 * max(n, 1))(*cells)
         isn = (C.c_uint8 * max(n, 1))(*([int(x) for x in nulls[r]] if nulls is not None else [0] * n))
         k = L.cb_tupser_row(arr, n, vals, isn, max_chunk, buf, len(buf))
         if k < 0:
@@ -88,7 +107,14 @@ def tupser_parse(attrs, data):
     while True:
         rc = L.cb_tupser_next(arr, n, C.byref(buf, pos), len(data) - pos, C.byref(used), vals, isn)
         if rc == 1:
-            rows.append([int(vals[i]) for i in range(n)])
+            row = []
+            for i in range(n):
+                if attrs[i][0] in (TUPSER_STATE_NUMERIC, TUPSER_STATE_INT8) and not isn[i]:
+                    st = arr[i].state.contents
+                    row.append((int(st.n), int(st.lo), int(st.hi)))
+                else:
+                    row.append(int(vals[i]))
+            rows.append(row)
             nulls.append([int(isn[i]) for i in range(n)])
             pos += used.value
             continue

@@ -22,6 +22,7 @@
  */
 #include "../../../include/cb_exec.h"
 
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -41,7 +42,8 @@ enum
 static int
 attr_is_varlena(int32_t type)
 {
-	return type == CB_NUMERIC || type == CB_BPCHAR1 || type == CB_DICT8 || type == CB_DICT32;
+	return type == CB_NUMERIC || type == CB_BPCHAR1 || type == CB_DICT8 || type == CB_DICT32 || type == CB_TUPSER_STATE_NUMERIC ||
+		type == CB_TUPSER_STATE_INT8;
 }
 
 /* bytes of the attribute's by-value datum, and its alignment */
@@ -141,6 +143,20 @@ varlena_payload(const CbTupAttr *a, int64_t v, unsigned char *scratch, const uns
 		scratch[0] = (unsigned char) v;
 		*data = scratch;
 		*len = 1;
+		return 0;
+	}
+	if (a->type == CB_TUPSER_STATE_NUMERIC || a->type == CB_TUPSER_STATE_INT8)
+	{
+		/* a partial aggregate state: the bytea its serialisation function would make (numeric.c:5025 / :5793) */
+		const CbAggStateDatum *st = (const CbAggStateDatum *) (intptr_t) v;
+		const int	n = st == NULL ? -1 : a->type == CB_TUPSER_STATE_NUMERIC
+			? cb_numeric_avg_serialize(st->n, st->lo, st->hi, a->dscale, scratch, 256)
+			: cb_int8_avg_serialize(st->n, st->lo, st->hi, scratch, 256);
+
+		if (n < 0)
+			return -1;
+		*data = scratch;
+		*len = n;
 		return 0;
 	}
 	{
@@ -564,6 +580,34 @@ cb_tupser_next(const CbTupAttr *attrs, int natts, const unsigned char *in, int64
 				}
 				else if (attrs[i].type == CB_BPCHAR1)
 					values[i] = l > 0 ? d[0] : ' ';
+				else if (attrs[i].type == CB_TUPSER_STATE_NUMERIC || attrs[i].type == CB_TUPSER_STATE_INT8)
+				{
+					/* a CPU Partial Aggregate's serialised state -> (N, sum): numeric_avg_deserialize / int8_avg_deserialize */
+					CbAggStateDatum *st = attrs[i].state;
+					int32_t		ds = 0;
+
+					if (st == NULL || cb_numeric_avg_deserialize(d, l, attrs[i].type == CB_TUPSER_STATE_NUMERIC, &st->n, &st->lo, &st->hi, &ds) != 0)
+						goto bad;
+					if (ds != (attrs[i].type == CB_TUPSER_STATE_NUMERIC ? attrs[i].dscale : 0))
+					{
+						/* the sender's sum carries another display scale (inputs of mixed scale): bring it to ours if exact */
+						if (ds > attrs[i].dscale || attrs[i].type != CB_TUPSER_STATE_NUMERIC)
+							goto bad;
+						{
+							__int128	v = (__int128) ((((unsigned __int128) (uint64_t) st->hi) << 64) | (uint64_t) st->lo);
+
+							for (int k = ds; k < attrs[i].dscale; k++)
+							{
+								if (v > (((__int128) 1) << 122) || v < -(((__int128) 1) << 122))
+									goto bad;
+								v *= 10;
+							}
+							st->lo = (int64_t) (uint64_t) (unsigned __int128) v;
+							st->hi = (int64_t) (uint64_t) (((unsigned __int128) v) >> 64);
+						}
+					}
+					values[i] = (int64_t) (intptr_t) st;
+				}
 				else
 				{
 					const int32_t code = text_code(&attrs[i], d, l);

@@ -272,7 +272,20 @@ typedef struct CbTupAttr
 	int32_t		ntexts;			/* dictionary columns: the texts of codes 0 .. ntexts-1, in byte order  */
 	const char *const *texts;	/* (what cbgpu_dict_entry returns for each code; character(n) texts     */
 	const int32_t *text_lens;	/* without their trailing blanks)                                      */
+	struct CbAggStateDatum *state;	/* CB_TUPSER_STATE_*: where cb_tupser_next puts the row's state        */
 } CbTupAttr;
+/* A partial aggregate state as a tuple attribute: on the wire it is the bytea the aggregate's serialisation function makes
+ * (cb_numeric_avg_serialize / cb_int8_avg_serialize above; AGGSPLIT_INITIAL_SERIAL target lists are typed bytea), in the
+ * executor it is (N, exact 128-bit sum).  cb_tupser_row takes values[i] = a pointer to the CbAggStateDatum to send;
+ * cb_tupser_next fills attrs[i].state and returns that pointer in values[i].  dscale = the sum's display scale. */
+typedef struct CbAggStateDatum
+{
+	int64_t		n,
+				lo,
+				hi;
+} CbAggStateDatum;
+#define CB_TUPSER_STATE_NUMERIC 101	/* sum / avg over numeric: numeric_avg_serialize form                  */
+#define CB_TUPSER_STATE_INT8 102	/* sum / avg over int8: int8_avg_serialize form                        */
 /* One row (values as the executor holds them: by-value datums, scaled numerics, dictionary codes) -> its tuple chunks:
  * TC_WHOLE, or TC_PARTIAL_START / _MID / _END when [int32 length][MinimalTuple body] exceeds max_chunk
  * (Gp_max_tuple_chunk_size) minus the 4-byte chunk header.  Returns the bytes written, < 0 on error (-2: out too small). */

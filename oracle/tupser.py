@@ -3,7 +3,7 @@ tupchunklist.c driven by oracle/ref_tupser.c).  Test infrastructure: what a Moti
 what a receiver makes of a chunk stream.
 
 Columns are (kind, dscale, n): kind in int4 / int8 / date / float8 / bool / numeric / bpchar (character(n), value = text,
-blank-padded to n here as bpcharin does) / text."""
+blank-padded to n here as bpcharin does) / text / bytea (value = bytes: a partial aggregate's serialised state)."""
 import ctypes as C
 
 import numpy as np
@@ -12,7 +12,8 @@ from . import aocs_format as A
 
 # kind -> (type oid, typlen, byval, align, storage)
 KINDS = {"int4": (23, 4, 1, "i", "p"), "int8": (20, 8, 1, "d", "p"), "date": (1082, 4, 1, "i", "p"), "float8": (701, 8, 1, "d", "p"),
-         "bool": (16, 1, 1, "c", "p"), "numeric": (1700, -1, 0, "i", "m"), "bpchar": (1042, -1, 0, "i", "x"), "text": (25, -1, 0, "i", "x")}
+         "bool": (16, 1, 1, "c", "p"), "numeric": (1700, -1, 0, "i", "m"), "bpchar": (1042, -1, 0, "i", "x"), "text": (25, -1, 0, "i", "x"),
+         "bytea": (17, -1, 0, "i", "x")}
 
 
 def _lib():

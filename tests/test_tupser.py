@@ -152,3 +152,64 @@ def test_partial_buffers_and_malformed_streams():
         capi.tupser_parse(poorer, data)
     # the direct-buffer form of a row without attributes (TC_EMPTY) is read as a row too
     assert capi.tupser_parse([], bytes([0, 0, 5, 0, 0, 0, 4, 0]))[0] == [[]]
+
+
+@pytest.mark.skipif(A.ref_lib() is None, reason="reference library only where /root/reference exists")
+def test_partial_aggregate_states_travel_as_the_reference_serialises_them():
+    """a Partial Aggregate's output row (group key, sum(numeric) state, avg(int8) state, count) between a device stage and a CPU
+    stage: the state columns are bytea on the wire (AGGSPLIT_INITIAL_SERIAL), (N, sum) in the executor.  Our chunks equal the
+    reference's SerializeTuple over the same bytea values, the reference's receiver reads our chunks, and our receiver turns the
+    reference's chunks back into states - also when the sender's sum has a smaller display scale than the receiver expects."""
+    import ctypes as C
+    E = capi.ex()
+    E.cb_numeric_avg_serialize.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]
+    E.cb_int8_avg_serialize.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32]
+
+    def split(v):
+        u = v & ((1 << 128) - 1)
+        lo, hi = u & ((1 << 64) - 1), u >> 64
+        return (lo - (1 << 64) if lo >= 1 << 63 else lo), (hi - (1 << 64) if hi >= 1 << 63 else hi)
+
+    def ser(kind, n, v, ds=0):
+        buf = C.create_string_buffer(256)
+        lo, hi = split(v)
+        k = E.cb_numeric_avg_serialize(n, lo, hi, ds, buf, 256) if kind == "numeric" else E.cb_int8_avg_serialize(n, lo, hi, buf, 256)
+        assert k > 0
+        return buf.raw[:k]
+    rng = np.random.default_rng(9)
+    cols = [("int4", 0, 0), ("bytea", 0, 0), ("bytea", 0, 0), ("int8", 0, 0)]
+    attrs = [(P.INT4, 0, 0), (capi.TUPSER_STATE_NUMERIC, 4, 0), (capi.TUPSER_STATE_INT8, 0, 0), (P.INT8, 0, 0)]
+    states, ref_rows, our_rows = [], [], []
+    for r in range(200):
+        n = int(rng.integers(1, 10**9))
+        vnum = int(rng.integers(-2**62, 2**62)) * int(rng.choice([1, 1, 10**6, 2**30]))       # some beyond 64 bits
+        vint = int(rng.integers(-2**62, 2**62)) * int(rng.choice([1, 3, 2**20]))
+        states.append(((n, *split(vnum)), (n, *split(vint))))
+        ref_rows.append([r, ser("numeric", n, vnum, 4), ser("int8", n, vint), n])
+        our_rows.append([r, (n, *split(vnum)), (n, *split(vint)), n])
+    for max_chunk in (8160, 64):
+        want, _ = T.serialize(cols, ref_rows, None, max_chunk)
+        got = capi.tupser_rows(attrs, our_rows, None, max_chunk, end=False)
+        assert got == want
+        back, backnull, used, ended = capi.tupser_parse(attrs, want + capi.tupser_rows(attrs, [], end=True))
+        assert ended and [tuple(b[1:3]) for b in back] == states and [b[0] for b in back] == list(range(200))
+        refback = T.deserialize(cols, got)
+        for r in range(200):
+            for a in (1, 2):
+                body = refback[r][a][1:] if refback[r][a][0] & 1 else refback[r][a][4:]
+                assert body == ref_rows[r][a]
+    # a CPU partial stage whose inputs all had display scale 2 feeding a receiver that keeps scale 4: the sum is rescaled exactly
+    low = [[0, ser("numeric", 5, 12345, 2), ser("int8", 5, 7), 5]]
+    data, _ = T.serialize(cols, low, None, 8160)
+    back, _, _, _ = capi.tupser_parse(attrs, data + capi.tupser_rows(attrs, [], end=True))
+    assert back[0][1] == (5, 1234500, 0)
+    # damaged state bytes are a malformed stream, not a crash or a wrong state
+    for damage in ("nan", "short"):
+        st = bytearray(ser("numeric", 5, 12345, 2))
+        if damage == "nan":
+            st[12:14] = b"\xc0\x00"             # NUMERIC_NAN in the sum's sign field: a NaN went into the CPU stage
+        else:
+            st = st[:-3]
+        data, _ = T.serialize(cols, [[0, bytes(st), ser("int8", 5, 7), 5]], None, 8160)
+        with pytest.raises(capi.CbgpuError):
+            capi.tupser_parse(attrs, data + capi.tupser_rows(attrs, [], end=True))
