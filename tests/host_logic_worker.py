@@ -94,6 +94,34 @@ def main():
     out["ran"]["q1_after_refusals"] = {"rows": len(ex.run(tpch.q1_plan(1)).rows)}
     ex.close()
 
+    # 3b. the round-2 host paths over the no-op runtime: outer joins through the pair probe, a sorted Gather's merge receive on a
+    #     3-segment cluster, and an operator memory budget small enough for multi-batch joins and partitioned aggregation (the
+    #     passes are host loops: every one of them runs, with kernels that compute nothing)
+    o = rels[1]
+    so = P.SeqScan(2, [("o_orderkey", P.Var(2, o.attno("o_orderkey"), P.INT8)), ("o_custkey", P.Var(2, o.attno("o_custkey"), P.INT4))])
+    sl = P.SeqScan(1, [("l_orderkey", P.Var(1, li.attno("l_orderkey"), P.INT8)), ("l_suppkey", P.Var(1, li.attno("l_suppkey"), P.INT4))])
+    ex = capi.Executor(ctx, dev)
+    for jt, nme in ((P.JOIN_RIGHT, "right_join_runs"), (P.JOIN_FULL, "full_join_runs")):
+        hh = P.Hash(so, [P.out_var(so, 1)])
+        jj = P.HashJoin(jt, sl, hh, [P.out_var(sl, 1)], [("l_suppkey", P.out_var(sl, 2)), ("o_custkey", P.InnerVar(2, P.INT4))])
+        before = ctx.launches()
+        out["ran"][nme] = {"rows": len(ex.run(P.Agg(jj, P.AGG_PLAIN, P.AGGSPLIT_SIMPLE, [], [("n", P.Aggref(P.AGG_COUNT_STAR))])).rows),
+                           "launches": ctx.launches() - before}
+    ex.close()
+    exm = capi.Executor(ctx, dev, operator_mem_kb=16)
+    before = ctx.launches()
+    # the build side is a bare scan of orders (a base relation has its rows even here): 16 KB splits it into many batches
+    hh = P.Hash(so, [P.out_var(so, 1)])
+    jj = P.HashJoin(P.JOIN_INNER, sl, hh, [P.out_var(sl, 1)], [("l_suppkey", P.out_var(sl, 2)), ("o_custkey", P.InnerVar(2, P.INT4))])
+    r3 = exm.run(P.Agg(jj, P.AGG_HASHED, P.AGGSPLIT_SIMPLE, [1], [("l_suppkey", P.out_var(jj, 1)), ("n", P.Aggref(P.AGG_COUNT_STAR))], num_groups=64))
+    out["ran"]["q3_tiny_memory"] = {"rows": len(r3.rows), "launches": ctx.launches() - before,
+                                    "batches": int(exm.estate.contents.es_hashjoin_batches_run)}
+    exm.close()
+    cl = capi.Cluster(ctx, [dev, dev, dev])
+    before = ctx.launches()
+    out["ran"]["q3_merge_gather_3seg"] = {"rows": len(cl.run(tpch.q3_plan(seg, 3, merge_gather=True)).rows), "launches": ctx.launches() - before}
+    cl.close()
+
     # 3a. CHECK_FOR_INTERRUPTS: the callback is polled before every pipeline; pending after the 2nd poll -> the query stops with
     #     CBGPU_ERR_INTERRUPTED having launched fewer kernels than a full run, and the executor runs the next query
     import ctypes as C

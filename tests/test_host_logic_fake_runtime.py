@@ -42,11 +42,17 @@ def _check(out):
     assert out["serialize"]["roundtrips"] == 300 and out["serialize"]["refused"] >= 300 * 5
     assert out["serialize"]["accepted_garbage"] < 30
     for name in ("q1", "q3", "q5", "q1_generic", "q3_generic", "q5_generic", "q1_3seg", "q3_3seg", "q5_3seg",
-                 "ssb_q4_1", "ssb_q4_2", "ssb_q4_3", "q1_after_refusals", "having"):
+                 "ssb_q4_1", "ssb_q4_2", "ssb_q4_3", "q1_after_refusals", "having", "q3_tiny_memory",
+                 "q3_merge_gather_3seg"):
         assert ran[name]["rows"] == 0, name            # nothing is computed on the host: no kernel, no rows
     for name in ("q1", "q3", "q5", "q1_3seg", "q3_3seg", "q5_3seg"):
         assert ran[name]["launches"] > 0
     assert ran["q3_3seg"]["launches"] > ran["q3"]["launches"]      # three segment executors and their Motions
+    # outer joins go through the pair probe (count, scan, write, unmatched build rows); a PLAIN count over nothing is one row
+    assert ran["right_join_runs"]["rows"] <= 1 and ran["right_join_runs"]["launches"] > 0 and ran["full_join_runs"]["launches"] > 0
+    # a 16 KB operator memory: the build sides are split, every pass is a host loop iteration that launches (no-op) kernels
+    assert ran["q3_tiny_memory"]["batches"] > 1 and ran["q3_tiny_memory"]["launches"] > ran["q3"]["launches"]
+    assert ran["q3_merge_gather_3seg"]["launches"] > 0
     want = {"sorted_agg": (UNSUPPORTED, "hashed / plain"),
             "sort_without_limit": (UNSUPPORTED, "Sort without LIMIT"), "right_join": (UNSUPPORTED, "extra join quals"),
             "numeric_join_key": (UNSUPPORTED, "hash_numeric"), "bad_scanrelid": (INVALID, "scanrelid 9")}
