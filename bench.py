@@ -231,7 +231,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    nthreads = min(cores, 64)
+    nthreads = min(cores, 256)          # every host core the process may use: one CPU segment (process) each
     from cloudberry_b200 import tpch as _tpch
     per_ref = 1_000_000
     steps = ref_q1_steps(nthreads, per_ref, args.warmup + args.steps)
