@@ -1109,6 +1109,25 @@ open_hashjoin(CbPlanState *ps, CbStream **out)
 		memset(pr, 0, sizeof(*pr));
 		pr->ht = hp->ht;
 		pr->jointype = hj->jointype;
+		if (hj->jointype == CB_JOIN_LASJ_NOTIN)
+		{
+			/* x NOT IN (build side): an ANTI probe, except that NULLs are unknowns (nodeHashjoin.c:371-390, 578-590): a NULL
+			 * key on the build side leaves nothing (hs_hashkeys_null -> the join returns no row at all); a NULL key on the
+			 * probe side drops that row unless the build side is empty */
+			const int64_t inner_rows = cbgpu_rel_nrows(hp->inner_rel);
+
+			pr->jointype = CB_JOIN_ANTI;
+			pr->null_key_drops = inner_rows > 0;
+			if (inner_rows > cbgpu_ht_nrows(hp->ht))
+			{
+				int			never = pe_const(s, CB_BOOL, 0, 0);
+
+				if (never < 0)
+					return es_fail(es, CBGPU_ERR_UNSUPPORTED, "pipeline program too long");
+				TRY(emit_expr(es, s, never));
+				TRY(emit_op(es, s, CBP_FILTER, 0, 0));
+			}
+		}
 		pr->nkeys = hj->nhashkeys;
 		for (int k = 0; k < hj->nhashkeys; k++)
 		{
@@ -1134,7 +1153,7 @@ open_hashjoin(CbPlanState *ps, CbStream **out)
 		}
 		s->pipe.nprobes = j + 1;
 		s->nsrc = base + j + 1;
-		if (hj->jointype == CB_JOIN_SEMI || hj->jointype == CB_JOIN_ANTI)
+		if (hj->jointype == CB_JOIN_SEMI || hj->jointype == CB_JOIN_ANTI || hj->jointype == CB_JOIN_LASJ_NOTIN)
 		{
 			/* no inner columns survive a semi / anti join */
 			for (int i = 0; i < hp->inner_nout; i++)

@@ -117,6 +117,7 @@ cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
 			return cb_fail(ctx, CBGPU_ERR_INVALID, "fused probe %s%lld needs unique build keys; use cbgpu_ht_probe_pairs", "", j);
 		d->probes[j].ht = pp->ht->d;
 		d->probes[j].jointype = pp->jointype;
+		d->probes[j].null_key_drops = pp->null_key_drops;
 		d->probes[j].nkeys = pp->nkeys;
 		for (int k = 0; k < pp->nkeys; k++)
 		{
@@ -563,6 +564,8 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 				}
 				for (int k = 0; k < pr.nkeys; k++)
 					h = pg_hash_combine(h, jh_hash_datum(pr.keytype[k], key[k], pr.keydict[k]), false);
+				if (knull && pr.null_key_drops)
+					alive = false;		/* NOT IN over a non-empty set: NULL <> everything is unknown, the row goes */
 				bool		maybe = alive && !knull;
 
 				if (maybe && pr.ht.bloom)

@@ -19,6 +19,7 @@ struct DProbe
 	int32_t		nkeys;
 	int32_t		keytype[CBP_MAX_KEYS];
 	const uint32_t *keydict[CBP_MAX_KEYS];
+	int32_t		null_key_drops;
 };
 
 struct DSink

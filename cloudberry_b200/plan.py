@@ -26,7 +26,7 @@ OP_ADD, OP_SUB, OP_MUL = 1, 2, 3
 OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE = 10, 11, 12, 13, 14, 15
 AND_EXPR, OR_EXPR, NOT_EXPR = 0, 1, 2
 AGG_COUNT_STAR, AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX = 1, 2, 3, 4, 5, 6
-JOIN_INNER, JOIN_LEFT, JOIN_FULL, JOIN_RIGHT, JOIN_SEMI, JOIN_ANTI = range(6)
+JOIN_INNER, JOIN_LEFT, JOIN_FULL, JOIN_RIGHT, JOIN_SEMI, JOIN_ANTI, JOIN_LASJ_NOTIN = range(7)
 AGG_PLAIN, AGG_SORTED, AGG_HASHED, AGG_MIXED = range(4)
 AGGSPLIT_SIMPLE, AGGSPLIT_INITIAL_SERIAL, AGGSPLIT_FINAL_DESERIAL = range(3)
 MOTIONTYPE_GATHER, MOTIONTYPE_GATHER_SINGLE, MOTIONTYPE_HASH, MOTIONTYPE_BROADCAST = range(4)

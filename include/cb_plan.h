@@ -143,7 +143,8 @@ typedef struct CbHash
 /* nodes/nodes.h JoinType */
 typedef enum CbJoinType
 {
-	CB_JOIN_INNER = 0, CB_JOIN_LEFT, CB_JOIN_FULL, CB_JOIN_RIGHT, CB_JOIN_SEMI, CB_JOIN_ANTI
+	CB_JOIN_INNER = 0, CB_JOIN_LEFT, CB_JOIN_FULL, CB_JOIN_RIGHT, CB_JOIN_SEMI, CB_JOIN_ANTI,
+	CB_JOIN_LASJ_NOTIN			/* left anti semi join with NOT IN semantics (nodes/nodes.h:897; nodeHashjoin.c:371-390, 578-590) */
 } CbJoinType;
 
 typedef struct CbHashJoin

@@ -190,6 +190,8 @@ typedef struct CbpProbe
 	int32_t		nkeys;
 	int32_t		keytype[CBP_MAX_KEYS];	/* CbTypeId of each outer key value (for its hash function)   */
 	const uint32_t *key_dict_hash[CBP_MAX_KEYS];
+	int32_t		null_key_drops;	/* ANTI probe of a NOT IN join over a non-empty build side: an outer row whose key is
+								 * NULL is dropped, not kept (x NOT IN (...) is unknown: nodeHashjoin.c:578-590)    */
 } CbpProbe;
 
 typedef enum CbpSinkKind

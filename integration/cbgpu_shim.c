@@ -572,7 +572,8 @@ translate_plan(Plan *p, EState *estate, List **rels)
 					case JOIN_ANTI: c->jointype = CB_JOIN_ANTI; break;
 					case JOIN_RIGHT: c->jointype = CB_JOIN_RIGHT; break;
 					case JOIN_FULL: c->jointype = CB_JOIN_FULL; break;
-					default: return NULL;	/* LASJ_NOTIN and the rest stay on the CPU */
+					case JOIN_LASJ_NOTIN: c->jointype = CB_JOIN_LASJ_NOTIN; break;
+					default: return NULL;	/* unique-ified and dedup semi joins stay on the CPU */
 				}
 				if (!translate_exprs(hj->hashkeys, &c->nhashkeys, &c->hashkeys) ||
 					!translate_exprs(hj->join.joinqual, &c->njoinquals, &c->joinqual))

@@ -574,6 +574,7 @@ typedef struct HJPriv
 	int			need_outer;
 	OD		   *nullinner;
 	OD		   *nullouter;
+	int			inner_null_key;	/* LASJ_NOTIN: a build row's key was NULL (hs_hashkeys_null, nodeHashjoin.c:388) */
 	int64_t		fill_cur;		/* HJ_FILL_INNER_TUPLES cursor, -1 = the probe phase is still on  */
 } HJPriv;
 
@@ -629,6 +630,9 @@ hj_build(PS *ps)
 		uint32_t	h;
 
 		int			keyed = hash_keys(ps->ex, hplan->hashkeys, hplan->nhashkeys, &c, &h, NULL);
+
+		if (!keyed)
+			hp->inner_null_key = 1;
 
 		/* NULL key cannot match (inner/left/semi/anti all drop it); HJ_FILL_INNER joins keep the tuple so that it comes
 		 * back NULL-extended (ExecHashGetHashValue keep_nulls, nodeHash.c:2171-2190) */
@@ -693,6 +697,9 @@ hashjoin_next(PS *ps)
 
 	if (!hp->built)
 		hj_build(ps);			/* HJ_BUILD_HASHTABLE (nodeHashjoin.c:264) */
+	/* NOT IN over a set that holds a NULL is never true (nodeHashjoin.c:386-390) */
+	if (hj->jointype == CB_JOIN_LASJ_NOTIN && hp->inner_null_key)
+		return NULL;
 	if (hj->nhashkeys > 8)
 	{
 		ora_error("too many hash keys");
@@ -740,6 +747,12 @@ hashjoin_next(PS *ps)
 			hp->outer_matched = 0;
 			hp->need_outer = 0;
 			hp->cur = ok ? hp->buckets[hp->curhash & (hp->nbuckets - 1)] : -1;
+			/* LASJ_NOTIN: a NULL outer key against a non-empty inner side is dropped (nodeHashjoin.c:578-590) */
+			if (hj->jointype == CB_JOIN_LASJ_NOTIN && !ok && hp->inner.nrows > 0)
+			{
+				hp->need_outer = 1;
+				continue;
+			}
 		}
 		/* HJ_SCAN_BUCKET (nodeHashjoin.c:575) / ExecScanHashBucket (nodeHash.c:2255) */
 		while (hp->cur >= 0)
@@ -767,7 +780,7 @@ hashjoin_next(PS *ps)
 				continue;
 			hp->outer_matched = 1;
 			hp->tup[t].matched = 1;	/* HeapTupleHeaderSetMatch (nodeHashjoin.c:560) */
-			if (hj->jointype == CB_JOIN_ANTI)
+			if (hj->jointype == CB_JOIN_ANTI || hj->jointype == CB_JOIN_LASJ_NOTIN)
 			{
 				hp->cur = -1;	/* one match is enough to reject (nodeHashjoin.c:610) */
 				break;
@@ -781,7 +794,8 @@ hashjoin_next(PS *ps)
 		}
 		/* HJ_FILL_OUTER_TUPLE (nodeHashjoin.c:663) */
 		hp->need_outer = 1;
-		if (!hp->outer_matched && (hj->jointype == CB_JOIN_LEFT || hj->jointype == CB_JOIN_FULL || hj->jointype == CB_JOIN_ANTI))
+		if (!hp->outer_matched && (hj->jointype == CB_JOIN_LEFT || hj->jointype == CB_JOIN_FULL || hj->jointype == CB_JOIN_ANTI ||
+									hj->jointype == CB_JOIN_LASJ_NOTIN))
 		{
 			ECtx		cj = {hp->outer, hp->nullinner, NULL, 0, ps->ex};
 

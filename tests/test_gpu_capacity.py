@@ -160,3 +160,21 @@ def test_right_and_full_joins(ctx, oracle, jointype, nf, nd, dup, generic):
     plan = agg_over(j, names, ["g", "c"], [("s", P.AGG_SUM, "amt"), ("n", P.AGG_COUNT_STAR, None), ("ck", P.AGG_COUNT, "k"), ("sw", P.AGG_SUM, "w")])
     got, want = run_both(ctx, oracle, plan, [fo, do], [fp, dp], generic)
     assert canon(got) == canon(want)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("nf,nd,fnull,dnull", [(5000, 40, 0.1, 0.0), (5000, 40, 0.1, 0.2), (5000, 0, 0.1, 0.0), (0, 40, 0.0, 0.0), (20011, 45, 0.0, 0.0)])
+def test_not_in_join(ctx, oracle, nf, nd, fnull, dnull, generic):
+    """LASJ_NOTIN (nodeHashjoin.c:371-390, 578-590): a NULL on the build side empties the result, a NULL probe key is dropped
+    unless the build side is empty, the rest is an anti join; with NULL-free keys the compiled probe kernel takes it as ANTI"""
+    from test_oracle_outer_joins import _notin_plan
+    fo, fp = make(fact, nf, seed=43, null_frac=fnull, kmax=60)
+    do, dp = make(dim, nd, seed=44, null_frac=dnull, kmax=60)
+    j = _notin_plan(fo, do)
+    got, want = run_both(ctx, oracle, j, [fo, do], [fp, dp], generic)
+    assert canon(got) == canon(want)
+    if dnull > 0:
+        assert got == []
+    plan = agg_over(j, ["k", "amt", "g"], ["g"], [("s", P.AGG_SUM, "amt"), ("n", P.AGG_COUNT_STAR, None)])
+    got, want = run_both(ctx, oracle, plan, [fo, do], [fp, dp], generic)
+    assert canon(got) == canon(want)
