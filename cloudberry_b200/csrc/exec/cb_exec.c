@@ -1310,8 +1310,16 @@ agg_add_aggref(CbEState *es, VarCtx *vcp, CbStream *s, const CbAgg *agg, AggPlan
 				break;
 			case CB_AGG_MIN:
 			case CB_AGG_MAX:
-				if (a < 0 || m.argtype == CB_FLOAT8)
-					return es_fail(es, CBGPU_ERR_UNSUPPORTED, "min/max over float8 is not implemented on the GPU path");
+				if (a < 0)
+					return es_fail(es, CBGPU_ERR_INVALID, "min/max without an argument");
+				if (m.argtype == CB_FLOAT8)
+				{
+					/* float8smaller / float8larger order NaN above everything (float8_cmp_internal, utils/adt/float.c): map the
+					 * bits to integers with that order, use the integer accumulators, map back when the state is finalised */
+					a = pe_op(s, CBP_F8ORD, a, -1, CB_INT8, 0, 0);
+					if (a < 0)
+						return es_fail(es, CBGPU_ERR_UNSUPPORTED, "pipeline program too long");
+				}
 				m.kind = m.state_kind = te->op == CB_AGG_MIN ? CBP_ACC_MIN : CBP_ACC_MAX;
 				m.arg[0] = a;
 				m.nargs = 1;
@@ -1703,6 +1711,12 @@ finalize_state(const PExpr *st, int64_t n, int64_t lo, int64_t hi, int64_t *val,
 				cb_numeric_sum_text(num->lo, num->hi, st->dscale, num->text, sizeof(num->text));
 				*val = (int64_t) (intptr_t) num;
 				*type = CB_NUMERIC;
+			}
+			else if (st->argtype == CB_FLOAT8)
+			{
+				/* the state holds the order-preserving integer (CBP_F8ORD): back to float8 bits */
+				*val = lo >= 0 ? lo : (int64_t) ((uint64_t) lo ^ 0x7FFFFFFFFFFFFFFFull);
+				*type = CB_FLOAT8;
 			}
 			else
 			{

@@ -75,7 +75,7 @@ cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
 					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld underflows the stack", "", i);
 				depth--;
 				break;
-			case CBP_NOT: case CBP_I2F:
+			case CBP_NOT: case CBP_I2F: case CBP_F8ORD:
 				if (depth < 1)
 					return cb_fail(ctx, CBGPU_ERR_INVALID, "pipeline op %s%lld underflows the stack", "", i);
 				break;
@@ -284,7 +284,7 @@ cb_pipeline_to_dev(cbgpu_ctx *ctx, const CbPipeline *p, PipeDev *d)
 				dep--;
 			else if (c == CBP_PROBE)
 				dep -= p->probes[d->ops[i].a].nkeys;
-			else if (c != CBP_NOT && c != CBP_I2F && c != CBP_END && c != XOP_FILTER_COL && c != XOP_PROBE_COLS)
+			else if (c != CBP_NOT && c != CBP_I2F && c != CBP_F8ORD && c != CBP_END && c != XOP_FILTER_COL && c != XOP_PROBE_COLS)
 				dep--;
 			if ((c == CBP_PROBE || c == XOP_PROBE_COLS) && dep == 0 && ns < CBP_MAX_STAGES && i + 1 < d->nops)
 				d->stage_pc[ns++] = i + 1;
@@ -712,6 +712,15 @@ k_pipeline_generic(const __grid_constant__ PipeDev P)
 						sp--;
 						st[sp - 1] = __double_as_longlong(r);
 						snull = n ? (snull | (1ull << (sp - 1))) : (snull & ~(1ull << (sp - 1)));
+						break;
+					}
+				case CBP_F8ORD:
+					{
+						long long	b = st[sp - 1];
+
+						if (__longlong_as_double(b) != __longlong_as_double(b))
+							b = 0x7FF8000000000000ll;	/* every NaN is the same value, above +Infinity */
+						st[sp - 1] = b >= 0 ? b : (b ^ 0x7FFFFFFFFFFFFFFFll);
 						break;
 					}
 				case CBP_I2F:

@@ -61,6 +61,8 @@ xm_decompile(const CbPipeline *p, XProg *x)
 			case CBP_POP:
 				x->depth--;
 				break;
+			case CBP_F8ORD:
+				return false;		/* float arithmetic stays with the generic kernel */
 			case CBP_NOT:
 			case CBP_I2F:
 				if (x->n >= XM_MAXNODES)

@@ -163,7 +163,10 @@ typedef enum CbpOpCode
 	CBP_FILTER,			/* pop; the row survives only if the value is true (not NULL)                 */
 	CBP_PROBE,			/* a = probe index; pops that probe's key values (pushed in key order)        */
 	CBP_DUP,			/* push a copy of stack[a] (common sub-expressions)                           */
-	CBP_POP
+	CBP_POP,
+	CBP_F8ORD			/* float8 bits -> an int64 whose integer order is float8's (float8_cmp_internal, utils/adt/float.c: every
+						 * NaN equal and above everything); its own inverse on non-NaN values.  Lets min / max(float8) use
+						 * the integer min / max accumulators */
 } CbpOpCode;
 
 typedef struct CbpOp

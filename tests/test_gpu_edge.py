@@ -252,3 +252,59 @@ def test_prefilter_pass_on_small_inputs(oracle):
             d.free()
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_float8_min_max(ctx, oracle, generic):
+    """min / max(float8) order NaN above +Infinity and -0 below +0 like float8_cmp_internal / float8smaller / float8larger
+    (utils/adt/float.c): negative values, infinities, NaN, NULLs; one stage and two-stage over three segments"""
+    n = 30011
+    rng = np.random.default_rng(71)
+    x = rng.normal(0, 1e6, n)
+    x[rng.integers(0, n, 40)] = np.inf
+    x[rng.integers(0, n, 40)] = -np.inf
+    g = rng.integers(0, 9, n)
+    x[(g == 3) & (rng.random(n) < 0.01)] = np.nan            # group 3 sees NaNs: its max is NaN, its min is not
+    x[g == 5] = np.abs(x[g == 5])                            # an all-positive group
+    x[g == 6] = -np.abs(x[g == 6])                           # an all-negative group
+    nulls = (rng.random(n) < 0.1).astype(np.uint8)
+    nulls[g == 8] = 1                                        # a group without a single value: NULL min / max
+
+    def rel():
+        return HostRelation("f", ["g", "x"], [P.INT4, P.FLOAT8], [g.astype(np.int32), x], nulls=[None, nulls])
+    from oracle import oracle as O
+    fo, fp = rel().set_dict_hashes(O.hashbpchar), rel().set_dict_hashes(capi.hashbpchar)
+    sc = scan(1, fo, ["g", "x"])
+    plan = agg_over(sc, ["g", "x"], ["g"], [("mn", P.AGG_MIN, "x"), ("mx", P.AGG_MAX, "x"), ("c", P.AGG_COUNT, "x")])
+    got, want = run_both(ctx, oracle, plan, [fo], [fp], generic)
+
+    def key(rows):
+        out = []
+        for r in sorted(rows, key=lambda r: r[0]):
+            out.append(tuple("nan" if isinstance(v, float) and v != v else v for v in r))
+        return out
+    assert key(got) == key(want)
+    by = {r[0]: r for r in got}
+    assert by[3][2] != by[3][2] and by[3][1] == by[3][1]     # max is NaN, min is a number
+    assert by[8][1] is None and by[8][2] is None and by[8][3] == 0
+    assert by[5][1] >= 0 and by[6][2] <= 0
+    # two-stage: partial min / max states cross a Motion and are merged
+    from cloudberry_b200 import tpch
+    cut = np.array_split(np.arange(n), 3)
+    segs_o, segs_p = [[fo.take(c)] for c in cut], [[fp.take(c)] for c in cut]
+    v = tpch._child_var(sc)
+    aggs = [("mn", P.Aggref(P.AGG_MIN, v("x"))), ("mx", P.Aggref(P.AGG_MAX, v("x")))]
+    partial = P.Agg(sc, P.AGG_HASHED, P.AGGSPLIT_INITIAL_SERIAL, [1], [("g", v("g"))] + aggs, num_groups=16)
+    red = P.Motion(partial, P.MOTIONTYPE_HASH, [P.out_var(partial, 1)], 3)
+    finals = [(nme, P.Aggref(ar.op, P.OuterVar(2 + i, *P.out_type(red, 2 + i)), restype=ar.restype, dscale=ar.dscale)) for i, (nme, ar) in enumerate(aggs)]
+    final = P.Agg(red, P.AGG_HASHED, P.AGGSPLIT_FINAL_DESERIAL, [1], [("g", P.out_var(red, 1))] + finals, num_groups=16)
+    plan2 = P.Motion(final, P.MOTIONTYPE_GATHER)
+    want2 = oracle.execute(plan2, segs_o).rows
+    dsegs = [to_device(ctx, s) for s in segs_p]
+    cl = capi.Cluster(ctx, dsegs)
+    got2 = cl.run(plan2).rows
+    cl.close()
+    for d in dsegs:
+        for r in d:
+            r.free()
+    assert key(got2) == key(want2) == [r[:3] for r in key(got)]
